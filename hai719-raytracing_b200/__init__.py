@@ -1,0 +1,302 @@
+"""hai719-raytracing_b200 — ctypes bindings of the B200 render path.
+
+Two in-tree shared libraries (built by ``make -C hai719-raytracing_b200`` or ``__graft_entry__.build()``):
+
+* ``lib/libhai719_rt.so``   hand-written sm_100a CUDA kernels behind the C ABI of ``include/hai719_rt.h``
+* ``lib/libhai719_host.so`` the GL-free C++ host API (Scene / Camera / Mesh / Material / KDTree, OFF and PPM
+  loaders, flatten, ``ray_trace_from_camera``) behind ``include/hai719_host.h``
+
+This module only marshals arguments. There is no Python or CPU implementation of the render path: if the
+libraries are missing, importing raises; if no B200 is present, every render call raises ``RtError``.
+The package directory name contains a hyphen, so import it with
+``importlib.import_module("hai719-raytracing_b200")``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_RT = os.path.join(HERE, "lib", "libhai719_rt.so")
+LIB_HOST = os.path.join(HERE, "lib", "libhai719_host.so")
+DEFAULT_ASSETS = os.path.join(ROOT, "assets", "_ref")
+
+# scene ids of Scene::setup_by_id (main.cpp:421-432 order; 11 = flamingo_lake; 100 = BASELINE config 5)
+SCENES = {
+    "single_sphere": 0, "single_square": 1, "cornell_box": 2, "mesh": 3, "rt_in_a_weekend": 4,
+    "random_spheres": 5, "debug_refraction": 6, "flamingo": 7, "raccoon": 8, "flamingo_pond": 9,
+    "backrooms_pool": 10, "flamingo_lake": 11, "config5": 100,
+}
+
+
+class RtError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("hai719_rt error %d: %s" % (status, msg))
+        self.status = status
+
+
+class RtMaterial(C.Structure):
+    _fields_ = [("type", C.c_int32), ("texture_type", C.c_int32), ("diffuse", C.c_float * 3),
+                ("transparency", C.c_float), ("index_medium", C.c_float), ("checker1", C.c_float * 3),
+                ("checker2", C.c_float * 3), ("texture_scale_x", C.c_float), ("texture_scale_y", C.c_float),
+                ("emissive", C.c_int32), ("light_color", C.c_float * 3), ("light_intensity", C.c_float),
+                ("image", C.c_int32), ("normal_map", C.c_int32), ("motion", C.c_float * 3)]
+
+
+class RtSphere(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("radius", C.c_float), ("material", RtMaterial)]
+
+
+class RtSquare(C.Structure):
+    _fields_ = [("v0", C.c_float * 3), ("v1", C.c_float * 3), ("v3", C.c_float * 3), ("right", C.c_float * 3),
+                ("up", C.c_float * 3), ("material", RtMaterial)]
+
+
+class RtLight(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("radius", C.c_float), ("color", C.c_float * 3)]
+
+
+class RtImage(C.Structure):
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("rgb", C.c_void_p)]
+
+
+class RtKdNode(C.Structure):
+    _fields_ = [("bmin", C.c_float * 3), ("skip", C.c_uint32), ("bmax", C.c_float * 3), ("first_ref", C.c_uint32),
+                ("n_refs", C.c_uint32), ("is_leaf", C.c_uint32)]
+
+
+class RtTriRef(C.Structure):
+    _fields_ = [("v", C.c_uint32 * 3), ("tri_index", C.c_uint32)]
+
+
+class RtSceneMesh(C.Structure):
+    _fields_ = [("n_vertices", C.c_uint32), ("n_triangles", C.c_uint32), ("positions", C.POINTER(C.c_float)),
+                ("triangles", C.POINTER(C.c_uint32)), ("color_type", C.c_int32),
+                ("vert_colors", C.POINTER(C.c_float)), ("face_colors", C.POINTER(C.c_float)),
+                ("root_bmin", C.c_float * 3), ("root_bmax", C.c_float * 3), ("n_nodes", C.c_uint32),
+                ("nodes", C.POINTER(RtKdNode)), ("n_leaf_refs", C.c_uint32), ("leaf_refs", C.POINTER(RtTriRef)),
+                ("material", RtMaterial)]
+
+
+class RtSceneDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32),
+                ("n_spheres", C.c_uint32), ("spheres", C.POINTER(RtSphere)),
+                ("n_squares", C.c_uint32), ("squares", C.POINTER(RtSquare)),
+                ("n_meshes", C.c_uint32), ("meshes", C.POINTER(RtSceneMesh)),
+                ("n_lights", C.c_uint32), ("lights", C.POINTER(RtLight)),
+                ("n_textures", C.c_uint32), ("textures", C.POINTER(RtImage)),
+                ("n_normal_maps", C.c_uint32), ("normal_maps", C.POINTER(RtImage)),
+                ("skybox", RtImage), ("dark_sky", C.c_int32)]
+
+
+class RtCamera(C.Structure):
+    _fields_ = [("modelview_inverse", C.c_double * 16), ("projection_inverse", C.c_double * 16),
+                ("depth_near", C.c_double)]
+
+
+class RtRenderParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("max_bounces", C.c_int32),
+                ("nb_ech", C.c_int32), ("seed", C.c_uint32), ("x0", C.c_int32), ("y0", C.c_int32),
+                ("x1", C.c_int32), ("y1", C.c_int32), ("rank", C.c_int32), ("n_ranks", C.c_int32),
+                ("tile_w", C.c_int32), ("tile_h", C.c_int32), ("collect_stats", C.c_int32), ("variant", C.c_int32)]
+
+
+class RtStats(C.Structure):
+    _fields_ = [("n_samples", C.c_uint64), ("n_closest_rays", C.c_uint64), ("n_shadow_rays", C.c_uint64),
+                ("n_sphere_tests", C.c_uint64), ("n_square_tests", C.c_uint64), ("n_mesh_tests", C.c_uint64),
+                ("n_node_visits", C.c_uint64), ("n_tri_tests", C.c_uint64), ("n_tri_full", C.c_uint64),
+                ("n_tex_fetches", C.c_uint64), ("n_random", C.c_uint64), ("kernel_ms", C.c_double),
+                ("n_launches", C.c_uint32), ("n_tiles", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol the two headers declare — tests check the libraries export exactly these
+RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy",
+              "rt_scene_device_bytes", "rt_render_pixel_count", "rt_render", "rt_render_device", "rt_untile_device",
+              "rt_trace_primary", "rt_trace_rays", "rt_shade_rays"]
+HOST_SYMBOLS = ["hai_last_error", "hai_scene_new", "hai_scene_free", "hai_scene_setup", "hai_scene_dump",
+                "hai_scene_flatten", "hai_scene_kd_stats", "hai_scene_counts", "hai_default_camera", "hai_render",
+                "hai_scene_device", "hai_ray_trace_from_camera"]
+
+if not (os.path.exists(LIB_RT) and os.path.exists(LIB_HOST)):
+    raise ImportError("hai719-raytracing_b200: native libraries not built (%s). Run `make -C %s` or "
+                      "`python -c 'import __graft_entry__ as g; g.build()'` — there is no Python fallback." % (LIB_RT, HERE))
+
+rt = C.CDLL(LIB_RT, mode=C.RTLD_GLOBAL)
+host = C.CDLL(LIB_HOST)
+
+rt.rt_last_error.restype = C.c_char_p
+rt.rt_scene_create.argtypes = [C.POINTER(RtSceneDesc), C.c_int, C.POINTER(C.c_void_p)]
+rt.rt_scene_destroy.argtypes = [C.c_void_p]
+rt.rt_scene_device_bytes.restype = C.c_size_t
+rt.rt_scene_device_bytes.argtypes = [C.c_void_p]
+rt.rt_render_pixel_count.restype = C.c_int64
+rt.rt_render_pixel_count.argtypes = [C.POINTER(RtRenderParams)]
+rt.rt_render.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p,
+                         C.POINTER(RtStats)]
+rt.rt_render_device.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.POINTER(RtStats)]
+rt.rt_untile_device.argtypes = [C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+rt.rt_trace_primary.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p]
+rt.rt_trace_rays.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+rt.rt_shade_rays.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RtRenderParams),
+                             C.c_void_p]
+
+host.hai_last_error.restype = C.c_char_p
+host.hai_scene_new.restype = C.c_void_p
+host.hai_scene_new.argtypes = [C.c_char_p]
+host.hai_scene_free.argtypes = [C.c_void_p]
+host.hai_scene_setup.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_uint32]
+host.hai_scene_dump.restype = C.c_size_t
+host.hai_scene_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+host.hai_scene_flatten.restype = C.POINTER(RtSceneDesc)
+host.hai_scene_flatten.argtypes = [C.c_void_p]
+host.hai_scene_kd_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+host.hai_scene_counts.argtypes = [C.c_void_p, C.c_void_p]
+host.hai_default_camera.argtypes = [C.c_int, C.c_int, C.POINTER(RtCamera)]
+host.hai_render.argtypes = [C.c_void_p, C.c_int, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p,
+                            C.c_void_p, C.POINTER(RtStats)]
+host.hai_scene_device.restype = C.c_void_p
+host.hai_scene_device.argtypes = [C.c_void_p, C.c_int]
+host.hai_ray_trace_from_camera.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
+                                           C.c_void_p]
+
+
+def _rt_check(rc):
+    if rc != 0:
+        raise RtError(rc, rt.rt_last_error().decode(errors="replace"))
+
+
+def _host_check(rc):
+    if rc != 0:
+        raise RtError(rc, host.hai_last_error().decode(errors="replace"))
+
+
+def device_count():
+    """Number of sm_100 devices the CUDA library can use (0 on a CPU-only box)."""
+    return int(rt.rt_device_count())
+
+
+def render_params(width, height, spp, max_bounces=6, nb_ech=10, seed=0, crop=None, rank=0, n_ranks=1, tile=(0, 0),
+                  collect_stats=False, variant=0):
+    p = RtRenderParams()
+    p.width, p.height, p.spp, p.max_bounces, p.nb_ech, p.seed = width, height, spp, max_bounces, nb_ech, seed
+    if crop:
+        p.x0, p.y0, p.x1, p.y1 = crop
+    p.rank, p.n_ranks, p.tile_w, p.tile_h = rank, n_ranks, tile[0], tile[1]
+    p.collect_stats, p.variant = int(collect_stats), variant
+    return p
+
+
+def default_camera(width, height):
+    """The reference's start-up camera (Camera() + move(0,0,-3.1), main.cpp:418) for a width x height window."""
+    cam = RtCamera()
+    _host_check(host.hai_default_camera(width, height, C.byref(cam)))
+    return cam
+
+
+class Scene:
+    """A host-side Scene (C++ object) built by one of the reference's setup_*() builders."""
+
+    def __init__(self, name=None, aspect=850.0 / 480.0, seed=0, assets=DEFAULT_ASSETS):
+        self.h = host.hai_scene_new(assets.encode() if assets else None)
+        if name is not None:
+            self.setup(name, aspect, seed)
+
+    def setup(self, name, aspect=850.0 / 480.0, seed=0):
+        sid = SCENES[name] if isinstance(name, str) else int(name)
+        _host_check(host.hai_scene_setup(self.h, sid, aspect, seed))
+        return self
+
+    def close(self):
+        if self.h:
+            host.hai_scene_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def dump(self):
+        n = host.hai_scene_dump(self.h, None, 0)
+        out = np.zeros(n, np.uint32)
+        host.hai_scene_dump(self.h, out.ctypes.data, n)
+        return out
+
+    def counts(self):
+        o = np.zeros(8, np.uint32)
+        host.hai_scene_counts(self.h, o.ctypes.data)
+        return dict(zip(["spheres", "squares", "meshes", "lights", "textures", "normals", "sky_w", "sky_h"], o.tolist()))
+
+    def kd_stats(self, mesh):
+        o = np.zeros(6, np.uint64)
+        _host_check(host.hai_scene_kd_stats(self.h, mesh, o.ctypes.data))
+        return dict(zip(["nodes", "leaves", "empty_leaves", "refs", "max_leaf", "max_depth"], o.tolist()))
+
+    def flatten(self):
+        d = host.hai_scene_flatten(self.h)
+        if not d:
+            raise RtError(-1, host.hai_last_error().decode(errors="replace"))
+        return d
+
+    def device_handle(self, device=0):
+        h = host.hai_scene_device(self.h, device)
+        if not h:
+            raise RtError(-1, host.hai_last_error().decode(errors="replace"))
+        return h
+
+    # ---- render path (GPU only) -------------------------------------------------------------------
+    def render(self, width, height, spp, seed=0, device=0, camera=None, want_linear=True, stats=False, **kw):
+        """hai_render(): upload (cached) + rt_render() with host output buffers. Returns a dict with
+        'gamma' (the reference's `image`), 'linear' and 'stats'."""
+        cam = camera or default_camera(width, height)
+        p = render_params(width, height, spp, seed=seed, collect_stats=stats, **kw)
+        x0, y0, x1, y1 = (p.x0, p.y0, p.x1, p.y1) if (p.x0 | p.y0 | p.x1 | p.y1) else (0, 0, width, height)
+        gam = np.zeros((y1 - y0, x1 - x0, 3), np.float32)
+        lin = np.zeros_like(gam) if want_linear else None
+        st = RtStats()
+        _host_check(host.hai_render(self.h, device, C.byref(cam), C.byref(p), gam.ctypes.data,
+                                    lin.ctypes.data if lin is not None else None, C.byref(st)))
+        return {"gamma": gam, "linear": lin, "stats": st.as_dict()}
+
+    def trace_primary(self, width, height, seed=0, device=0, camera=None, crop=None):
+        cam = camera or default_camera(width, height)
+        p = render_params(width, height, 1, seed=seed, crop=crop)
+        x0, y0, x1, y1 = crop if crop else (0, 0, width, height)
+        ids = np.zeros((y1 - y0, x1 - x0, 4), np.uint32)
+        _rt_check(rt.rt_trace_primary(self.device_handle(device), C.byref(cam), C.byref(p), ids.ctypes.data))
+        return ids
+
+    def trace_rays(self, org, dirs, time=None, device=0):
+        org = np.ascontiguousarray(org, np.float32)
+        dirs = np.ascontiguousarray(dirs, np.float32)
+        t = None if time is None else np.ascontiguousarray(time, np.float32)
+        n = org.shape[0]
+        ids = np.zeros((n, 4), np.uint32)
+        aux = np.zeros((n, 8), np.float32)
+        _rt_check(rt.rt_trace_rays(self.device_handle(device), n, org.ctypes.data, dirs.ctypes.data,
+                                   t.ctypes.data if t is not None else None, ids.ctypes.data, aux.ctypes.data))
+        return ids, aux
+
+    def shade_rays(self, org, dirs, time=None, seed=0, device=0, max_bounces=6, nb_ech=10):
+        org = np.ascontiguousarray(org, np.float32)
+        dirs = np.ascontiguousarray(dirs, np.float32)
+        t = None if time is None else np.ascontiguousarray(time, np.float32)
+        n = org.shape[0]
+        rgb = np.zeros((n, 3), np.float32)
+        p = render_params(1, 1, 1, max_bounces=max_bounces, nb_ech=nb_ech, seed=seed)
+        _rt_check(rt.rt_shade_rays(self.device_handle(device), n, org.ctypes.data, dirs.ctypes.data,
+                                   t.ctypes.data if t is not None else None, C.byref(p), rgb.ctypes.data))
+        return rgb
+
+    def ray_trace_from_camera(self, width, height, nsamples, seed=0, device=0, ppm_path=None):
+        """The whole of the reference's ray_trace_from_camera(): default camera, render, optional P3 file."""
+        out = np.zeros((height, width, 3), np.float32)
+        _host_check(host.hai_ray_trace_from_camera(self.h, device, width, height, nsamples, seed,
+                                                   ppm_path.encode() if ppm_path else None, out.ctypes.data))
+        return out

@@ -1,0 +1,810 @@
+// rt_capi.cu — kernels and the extern "C" layer of include/hai719_rt.h (sm_100a only).
+//
+// Kernel map (reference function each replaces; device functions in rt_core.cuh):
+//   k_precompute_squares / k_precompute_tris   per-primitive constants that Square::intersect
+//                          (Square.h:68-72) and the Triangle constructor (Triangle.h:26-37, called
+//                          per ray per triangle from KDTree.cpp:38-40) recompute for every ray
+//   k_render_paths         trace_line's pixel x sample loop (main.cpp:183-193) + Scene::rayTrace:
+//                          persistent CTAs, warps fetch batches of 32 paths from an atomic counter
+//   k_resolve              image[x+y*w] += color in sample order, /= nsamples, gamma_correct
+//                          (main.cpp:193-196)
+//   k_primary_ids / k_trace_rays / k_shade_rays   Scene::computeIntersection / rayTrace on given rays
+//   k_untile               packed tiles -> row-major image (no reference equivalent)
+//
+// No CPU fallback: every entry point that needs the GPU fails with RT_ERR_NO_DEVICE without one.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hai719_rt.h"
+#include "rt_core.cuh"
+
+using namespace rt;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define RT_CUDA(expr)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            cudaGetLastError();                                                                        \
+            return fail(e_ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA,                     \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                           \
+        }                                                                                              \
+    } while (0)
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// device-side records used by the kernels
+// ------------------------------------------------------------------------------------------------
+struct TileRec { int x0, y0, w, h; };   // one tile of this rank, in full-image pixel coordinates
+
+struct RenderArgs {
+    const TileRec *tiles;
+    const unsigned int *tile_off;       // n_tiles + 1 prefix sums of tile pixel counts (packed order)
+    int n_tiles;
+    int width, height, spp, max_bounces, nb_ech;
+    unsigned int seed;
+    unsigned long long pixel_begin;     // first packed pixel of this chunk
+    unsigned long long n_paths;         // paths in this chunk = chunk pixels * spp
+    float *samples;                     // n_paths * 3, path-major
+    unsigned long long *work_counter;
+    unsigned long long *stats;          // 10 counters, or null
+};
+
+// packed pixel index -> (x, y) via the tile prefix array
+__device__ __forceinline__ void packed_to_xy(const RenderArgs &a, unsigned int lp, int &x, int &y) {
+    int lo = 0, hi = a.n_tiles - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(a.tile_off + mid) <= lp) lo = mid; else hi = mid - 1;
+    }
+    const TileRec t = a.tiles[lo];
+    const unsigned int r = lp - __ldg(a.tile_off + lo);
+    x = t.x0 + (int)(r % (unsigned int)t.w);
+    y = t.y0 + (int)(r / (unsigned int)t.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+struct SquareIn { float v0[3], v1[3], v3[3], right[3], up[3], motion[3]; int glass; };
+
+__global__ void k_precompute_squares(const SquareIn *in, DSquare *out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SquareIn s = in[i];
+    const V3 v0 = ld3(s.v0);
+    const V3 right = ld3(s.v1) - v0, up = ld3(s.v3) - v0;
+    const V3 nrm = normalized(cross(right, up));
+    DSquare q;
+    q.v0[0] = v0.x; q.v0[1] = v0.y; q.v0[2] = v0.z;
+    q.n[0] = nrm.x; q.n[1] = nrm.y; q.n[2] = nrm.z;
+    q.right[0] = right.x; q.right[1] = right.y; q.right[2] = right.z;
+    q.up[0] = up.x; q.up[1] = up.y; q.up[2] = up.z;
+    q.len_r = length(right);
+    q.len_u = length(up);
+    for (int k = 0; k < 3; ++k) { q.motion[k] = s.motion[k]; q.tan_r[k] = s.right[k]; q.tan_u[k] = s.up[k]; }
+    q.glass = s.glass;
+    out[i] = q;
+}
+
+__global__ void k_precompute_tris(const float *positions, const RtTriRef *refs, unsigned int n_refs, float4 *plane,
+                                  float4 *edge, float2 *den) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_refs) return;
+    const RtTriRef r = refs[i];
+    const TriConst k = precompute_triangle(ld3(positions + 3 * r.v[0]), ld3(positions + 3 * r.v[1]),
+                                           ld3(positions + 3 * r.v[2]), r.tri_index);
+    plane[i] = k.plane;
+    edge[3 * i] = k.c0;
+    edge[3 * i + 1] = k.e0;
+    edge[3 * i + 2] = k.e1;
+    den[i] = k.den;
+}
+
+__device__ __forceinline__ void flush_counters(const Counters &c, unsigned long long *g) {
+    const unsigned long long v[10] = {c.closest, c.shadow, c.sphere, c.square, c.mesh, c.node, c.tri, c.tri_full, c.tex, c.rnd};
+    for (int k = 0; k < 10; ++k) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(g + k, x);
+    }
+}
+
+// One path per lane; warps pull batches of 32 consecutive paths (same pixel for spp >= 32, so a
+// warp's primary rays are coherent) from a global counter until the chunk is exhausted.
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_render_paths(const DScene scene, const DCamera cam, const RenderArgs a) {
+    Counters cnt;
+    if (STATS) memset(&cnt, 0, sizeof cnt);
+    const unsigned int lane = threadIdx.x & 31u;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.work_counter, 32ull);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= a.n_paths) break;
+        const unsigned long long p = base + lane;
+        if (p < a.n_paths) {
+            const unsigned int lp = (unsigned int)(a.pixel_begin + p / (unsigned int)a.spp);
+            const unsigned int smp = (unsigned int)(p % (unsigned int)a.spp);
+            int x, y;
+            packed_to_xy(a, lp, x, y);
+            Rng rng;
+            rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, smp);
+            if (STATS) cnt.rnd += 3;
+            const Ray ray = primary_ray(cam, x, y, a.width, a.height, rng);
+            const V3 c = trace_path<STATS>(scene, ray, rng, a.max_bounces, a.nb_ech, &cnt);
+            float *o = a.samples + 3ull * p;
+            o[0] = c.x; o[1] = c.y; o[2] = c.z;
+        }
+    }
+    if (STATS) flush_counters(cnt, a.stats);
+}
+
+// image[pixel] = (sum of its samples, in sample order) / nsamples ; then gamma
+__global__ void k_resolve(const float *samples, unsigned long long pixel_begin, unsigned int n_pixels, int spp,
+                          float *linear_out, float *gamma_out) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    const float *s = samples + 3ull * i * (unsigned int)spp;
+    V3 acc = v3(0.f);
+    for (int k = 0; k < spp; ++k) acc = acc + v3(s[3 * k], s[3 * k + 1], s[3 * k + 2]);
+    acc = acc / (float)(unsigned int)spp;
+    const unsigned long long o = 3ull * (pixel_begin + i);
+    if (linear_out) { linear_out[o] = acc.x; linear_out[o + 1] = acc.y; linear_out[o + 2] = acc.z; }
+    if (gamma_out) { gamma_out[o] = gamma_channel(acc.x); gamma_out[o + 1] = gamma_channel(acc.y); gamma_out[o + 2] = gamma_channel(acc.z); }
+}
+
+__global__ void k_untile(const TileRec *tiles, const unsigned int *tile_off, int n_tiles, const float *packed,
+                         float *image, int rect_x0, int rect_y0, int rect_w, unsigned int n_pixels) {
+    const unsigned int lp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= n_pixels) return;
+    int lo = 0, hi = n_tiles - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tile_off[mid] <= lp) lo = mid; else hi = mid - 1;
+    }
+    const TileRec t = tiles[lo];
+    const unsigned int r = lp - tile_off[lo];
+    const int x = t.x0 + (int)(r % (unsigned int)t.w) - rect_x0, y = t.y0 + (int)(r / (unsigned int)t.w) - rect_y0;
+    const size_t o = 3 * ((size_t)y * rect_w + x);
+    image[o] = packed[3ull * lp]; image[o + 1] = packed[3ull * lp + 1]; image[o + 2] = packed[3ull * lp + 2];
+}
+
+__global__ void k_primary_ids(const DScene scene, const DCamera cam, int width, int height, unsigned int seed, int x0,
+                              int y0, int rw, int rh, uint32_t *ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rw * rh) return;
+    const int x = x0 + i % rw, y = y0 + i / rw;
+    Rng rng;
+    rng.init(seed, (unsigned int)x + (unsigned int)y * (unsigned int)width, 0u);
+    const Ray ray = primary_ray(cam, x, y, width, height, rng);
+    float u, v;
+    const Hit h = closest_hit<false>(scene, ray, u, v, nullptr);
+    uint32_t *o = ids + 4 * (size_t)i;
+    o[0] = (uint32_t)h.type;
+    o[1] = h.type ? (uint32_t)h.obj : 0u;
+    o[2] = h.type == 3 ? f2u(__ldg(scene.meshes[h.obj].tri_den + h.ref).y) : 0u;
+    o[3] = f2u(h.t);
+}
+
+__global__ void k_trace_rays(const DScene scene, size_t n, const float *org, const float *dir, const float *time,
+                             uint32_t *ids, float *aux) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Ray ray = make_ray(ld3(org + 3 * i), ld3(dir + 3 * i), time ? time[i] : 0.f);
+    float u = 0.f, v = 0.f;
+    const Hit h = closest_hit<false>(scene, ray, u, v, nullptr);
+    uint32_t *o = ids + 4 * i;
+    o[0] = (uint32_t)h.type;
+    o[1] = h.type ? (uint32_t)h.obj : 0u;
+    o[2] = h.type == 3 ? f2u(__ldg(scene.meshes[h.obj].tri_den + h.ref).y) : 0u;
+    o[3] = f2u(h.t);
+    if (!aux) return;
+    float *q = aux + 8 * i;
+    for (int k = 0; k < 8; ++k) q[k] = 0.f;
+    if (h.type == 1) {
+        const float4 a = scene.sph_a[h.obj], b = scene.sph_b[h.obj];
+        const V3 c = v3(a.x, a.y, a.z) + ray.time * v3(b.x, b.y, b.z);
+        const V3 P = ray.o + h.t * ray.d;
+        const V3 nn = normalized(P - c);
+        q[0] = (float)acos((double)nn.y * -1.);
+        q[1] = (float)(atan2((double)nn.z * -1., (double)nn.x) + RT_PI);
+        q[2] = nn.x; q[3] = nn.y; q[4] = nn.z;
+    } else if (h.type == 2) {
+        q[0] = u; q[1] = v;
+        q[2] = scene.squares[h.obj].n[0]; q[3] = scene.squares[h.obj].n[1]; q[4] = scene.squares[h.obj].n[2];
+    } else if (h.type == 3) {
+        const DMesh &m = scene.meshes[h.obj];
+        float w0 = 0, w1 = 0, w2 = 0;
+        triangle_t<false>(ray, m, h.ref, w0, w1, w2, nullptr);
+        const float4 pl = m.tri_plane[h.ref];
+        q[0] = w0; q[1] = w1; q[2] = w2; q[3] = pl.x; q[4] = pl.y; q[5] = pl.z;
+    }
+}
+
+__global__ void k_shade_rays(const DScene scene, size_t n, const float *org, const float *dir, const float *time,
+                             unsigned int seed, int max_bounces, int nb_ech, float *rgb) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Ray ray = make_ray(ld3(org + 3 * i), ld3(dir + 3 * i), time ? time[i] : 0.f);
+    Rng rng;
+    rng.init(seed, (unsigned int)i, 0u);
+    rng.ctr = 3;
+    const V3 c = trace_path<false>(scene, ray, rng, max_bounces, nb_ech, nullptr);
+    rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of the C ABI
+// ------------------------------------------------------------------------------------------------
+struct RtScene {
+    int device = 0;
+    int sm_count = 0;
+    DScene d{};
+    std::vector<void *> allocs;
+    size_t bytes = 0;
+    // grow-only scratch, reused across calls on the same stream
+    float *samples = nullptr; size_t samples_cap = 0;
+    unsigned long long *counters = nullptr;   // [0] work counter, [1..10] stats
+    TileRec *d_tiles = nullptr; unsigned int *d_tile_off = nullptr; size_t tiles_cap = 0;
+    std::vector<TileRec> h_tiles; std::vector<unsigned int> h_tile_off;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+struct Rect { int x0, y0, x1, y1, tw, th; };
+
+int resolve_rect(const RtRenderParams &p, Rect &r) {
+    if (p.width < 1 || p.height < 1) return fail(RT_ERR_INVALID, "width/height must be >= 1");
+    if (p.spp < 1) return fail(RT_ERR_INVALID, "spp must be >= 1");
+    if (p.max_bounces < 0 || p.max_bounces > RT_MAX_BOUNCES) return fail(RT_ERR_INVALID, "max_bounces must be in [0, 16]");
+    if (p.nb_ech < 1) return fail(RT_ERR_INVALID, "nb_ech must be >= 1");
+    const bool full = (p.x0 | p.y0 | p.x1 | p.y1) == 0;
+    r.x0 = full ? 0 : p.x0; r.y0 = full ? 0 : p.y0; r.x1 = full ? p.width : p.x1; r.y1 = full ? p.height : p.y1;
+    if (r.x0 < 0 || r.y0 < 0 || r.x1 > p.width || r.y1 > p.height || r.x0 >= r.x1 || r.y0 >= r.y1)
+        return fail(RT_ERR_INVALID, "render rectangle out of range");
+    r.tw = p.tile_w > 0 ? p.tile_w : 32;
+    r.th = p.tile_h > 0 ? p.tile_h : 32;
+    if (p.n_ranks > 1 && (p.rank < 0 || p.rank >= p.n_ranks)) return fail(RT_ERR_INVALID, "rank out of range");
+    return RT_OK;
+}
+
+// tiles of the rectangle, row-major numbering; keep t % n_ranks == rank
+void build_tiles(const RtRenderParams &p, const Rect &r, std::vector<TileRec> &tiles, std::vector<unsigned int> &off) {
+    tiles.clear(); off.clear();
+    const int ntx = (r.x1 - r.x0 + r.tw - 1) / r.tw, nty = (r.y1 - r.y0 + r.th - 1) / r.th;
+    const int nr = p.n_ranks > 1 ? p.n_ranks : 1, rk = p.n_ranks > 1 ? p.rank : 0;
+    unsigned int acc = 0;
+    off.push_back(0);
+    for (int ty = 0; ty < nty; ++ty)
+        for (int tx = 0; tx < ntx; ++tx) {
+            const int t = ty * ntx + tx;
+            if (t % nr != rk) continue;
+            TileRec tr;
+            tr.x0 = r.x0 + tx * r.tw; tr.y0 = r.y0 + ty * r.th;
+            tr.w = std::min(r.tw, r.x1 - tr.x0); tr.h = std::min(r.th, r.y1 - tr.y0);
+            tiles.push_back(tr);
+            acc += (unsigned int)(tr.w * tr.h);
+            off.push_back(acc);
+        }
+}
+
+template <class T> int dev_upload(RtScene *s, const T *host, size_t n, const T **out) {
+    *out = nullptr;
+    if (n == 0) return RT_OK;
+    void *p = nullptr;
+    RT_CUDA(cudaMalloc(&p, n * sizeof(T)));
+    s->allocs.push_back(p);
+    s->bytes += n * sizeof(T);
+    RT_CUDA(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T *)p;
+    return RT_OK;
+}
+template <class T> int dev_alloc(RtScene *s, size_t n, T **out) {
+    *out = nullptr;
+    if (n == 0) return RT_OK;
+    void *p = nullptr;
+    RT_CUDA(cudaMalloc(&p, n * sizeof(T)));
+    s->allocs.push_back(p);
+    s->bytes += n * sizeof(T);
+    *out = (T *)p;
+    return RT_OK;
+}
+
+DMaterial to_dmat(const RtMaterial &m) {
+    DMaterial d{};
+    d.type = m.type; d.texture_type = m.texture_type;
+    for (int k = 0; k < 3; ++k) { d.kd[k] = m.diffuse[k]; d.checker1[k] = m.checker1[k]; d.checker2[k] = m.checker2[k]; d.light_color[k] = m.light_color[k]; d.motion[k] = m.motion[k]; }
+    d.transparency = m.transparency; d.index_medium = m.index_medium;
+    d.tsx = m.texture_scale_x; d.tsy = m.texture_scale_y;
+    d.emissive = m.emissive; d.light_intensity = m.light_intensity;
+    d.image = m.image; d.normal_map = m.normal_map;
+    return d;
+}
+
+int upload_image(RtScene *s, const RtImage &im, DImage &out) {
+    out.w = 0; out.h = 0; out.rgb = nullptr;
+    if (im.w < 1 || im.h < 1 || !im.rgb) return RT_OK;
+    const unsigned char *d = nullptr;
+    int rc = dev_upload<unsigned char>(s, im.rgb, (size_t)im.w * im.h * 3, &d);
+    if (rc) return rc;
+    out.w = im.w; out.h = im.h; out.rgb = d;
+    return RT_OK;
+}
+
+int check_material(const RtMaterial &m, const RtSceneDesc &d) {
+    if (m.type < 0 || m.type > 2 || m.texture_type < 0 || m.texture_type > 2) return fail(RT_ERR_INVALID, "material enum out of range");
+    if (m.image >= (int)d.n_textures || m.normal_map >= (int)d.n_normal_maps) return fail(RT_ERR_INVALID, "material image index out of range");
+    return RT_OK;
+}
+
+int select_device(int device, int *sm_count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(RT_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)"); }
+    if (device < 0 || device >= n) return fail(RT_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    RT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(RT_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this library is built for sm_100a only");
+    RT_CUDA(cudaSetDevice(device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    return RT_OK;
+}
+
+int fill_camera(const RtCamera &c, DCamera &d) {
+    for (int i = 0; i < 16; ++i) { d.mvi[i] = c.modelview_inverse[i]; d.pi[i] = c.projection_inverse[i]; }
+    d.depth_near = c.depth_near;
+    // cameraSpaceToWorldSpace(Vec3(0,0,0)) (matrixUtilities.h:53-58): MV^-1 * (0,0,0,1), dehomogenised in fp64
+    const double *m = c.modelview_inverse;
+    double r[4];
+    r[0] = m[0] * 0.0 + m[4] * 0.0 + m[8] * 0.0 + m[12] * 1.0;
+    r[1] = m[1] * 0.0 + m[5] * 0.0 + m[9] * 0.0 + m[13] * 1.0;
+    r[2] = m[2] * 0.0 + m[6] * 0.0 + m[10] * 0.0 + m[14] * 1.0;
+    r[3] = m[3] * 0.0 + m[7] * 0.0 + m[11] * 0.0 + m[15] * 1.0;
+    for (int k = 0; k < 3; ++k) d.pos[k] = (float)(r[k] / r[3]);
+    return RT_OK;
+}
+
+int persistent_grid(RtScene *s, const void *kernel, int threads) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
+    return s->sm_count * per_sm;
+}
+
+int ensure_scratch(RtScene *s, size_t sample_floats, size_t n_tiles) {
+    if (sample_floats > s->samples_cap) {
+        if (s->samples) cudaFree(s->samples);
+        s->samples = nullptr; s->samples_cap = 0;
+        RT_CUDA(cudaMalloc((void **)&s->samples, sample_floats * sizeof(float)));
+        s->samples_cap = sample_floats;
+    }
+    if (!s->counters) RT_CUDA(cudaMalloc((void **)&s->counters, 16 * sizeof(unsigned long long)));
+    if (n_tiles + 1 > s->tiles_cap) {
+        if (s->d_tiles) cudaFree(s->d_tiles);
+        if (s->d_tile_off) cudaFree(s->d_tile_off);
+        s->d_tiles = nullptr; s->d_tile_off = nullptr; s->tiles_cap = 0;
+        RT_CUDA(cudaMalloc((void **)&s->d_tiles, (n_tiles + 1) * sizeof(TileRec)));
+        RT_CUDA(cudaMalloc((void **)&s->d_tile_off, (n_tiles + 2) * sizeof(unsigned int)));
+        s->tiles_cap = n_tiles + 1;
+    }
+    if (!s->ev0) { RT_CUDA(cudaEventCreate(&s->ev0)); RT_CUDA(cudaEventCreate(&s->ev1)); }
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_abi_version(void) { return HAI719_RT_ABI_VERSION; }
+
+const char *rt_last_error(void) { return g_err.c_str(); }
+
+int rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+void rt_scene_destroy(RtScene *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (void *p : s->allocs) cudaFree(p);
+    if (s->samples) cudaFree(s->samples);
+    if (s->counters) cudaFree(s->counters);
+    if (s->d_tiles) cudaFree(s->d_tiles);
+    if (s->d_tile_off) cudaFree(s->d_tile_off);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+size_t rt_scene_device_bytes(const RtScene *s) { return s ? s->bytes : 0; }
+
+int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
+    if (!desc || !out) return fail(RT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (desc->abi_version != HAI719_RT_ABI_VERSION) return fail(RT_ERR_INVALID, "RtSceneDesc.abi_version mismatch");
+    if ((desc->n_spheres && !desc->spheres) || (desc->n_squares && !desc->squares) || (desc->n_meshes && !desc->meshes) ||
+        (desc->n_lights && !desc->lights) || (desc->n_textures && !desc->textures) || (desc->n_normal_maps && !desc->normal_maps))
+        return fail(RT_ERR_INVALID, "count > 0 with a null array");
+    int sm_count = 0;
+    int rc = select_device(device, &sm_count);
+    if (rc) return rc;
+
+    RtScene *s = new RtScene;
+    s->device = device;
+    s->sm_count = sm_count;
+    struct Guard { RtScene *s; bool keep = false; ~Guard() { if (!keep) rt_scene_destroy(s); } } guard{s};
+    DScene &d = s->d;
+    d.n_spheres = (int)desc->n_spheres; d.n_squares = (int)desc->n_squares; d.n_meshes = (int)desc->n_meshes; d.n_lights = (int)desc->n_lights;
+    d.dark_sky = desc->dark_sky;
+
+    // images
+    std::vector<DImage> tex(desc->n_textures), nrm(desc->n_normal_maps);
+    for (uint32_t i = 0; i < desc->n_textures; ++i) if ((rc = upload_image(s, desc->textures[i], tex[i]))) return rc;
+    for (uint32_t i = 0; i < desc->n_normal_maps; ++i) if ((rc = upload_image(s, desc->normal_maps[i], nrm[i]))) return rc;
+    if ((rc = dev_upload(s, tex.data(), tex.size(), &d.textures))) return rc;
+    if ((rc = dev_upload(s, nrm.data(), nrm.size(), &d.normal_maps))) return rc;
+    if ((rc = upload_image(s, desc->skybox, d.sky))) return rc;
+
+    // spheres
+    {
+        std::vector<float4> a(desc->n_spheres), b(desc->n_spheres);
+        std::vector<DMaterial> m(desc->n_spheres);
+        for (uint32_t i = 0; i < desc->n_spheres; ++i) {
+            const RtSphere &sp = desc->spheres[i];
+            if ((rc = check_material(sp.material, *desc))) return rc;
+            a[i] = make_float4(sp.center[0], sp.center[1], sp.center[2], sp.radius);
+            b[i] = make_float4(sp.material.motion[0], sp.material.motion[1], sp.material.motion[2], sp.material.transparency);
+            m[i] = to_dmat(sp.material);
+        }
+        if ((rc = dev_upload(s, a.data(), a.size(), &d.sph_a))) return rc;
+        if ((rc = dev_upload(s, b.data(), b.size(), &d.sph_b))) return rc;
+        if ((rc = dev_upload(s, m.data(), m.size(), &d.sph_mat))) return rc;
+    }
+    // squares
+    if (desc->n_squares) {
+        std::vector<SquareIn> in(desc->n_squares);
+        std::vector<DMaterial> m(desc->n_squares);
+        std::vector<float> tr(desc->n_squares);
+        for (uint32_t i = 0; i < desc->n_squares; ++i) {
+            const RtSquare &q = desc->squares[i];
+            if ((rc = check_material(q.material, *desc))) return rc;
+            for (int k = 0; k < 3; ++k) { in[i].v0[k] = q.v0[k]; in[i].v1[k] = q.v1[k]; in[i].v3[k] = q.v3[k]; in[i].right[k] = q.right[k]; in[i].up[k] = q.up[k]; in[i].motion[k] = q.material.motion[k]; }
+            in[i].glass = q.material.type == RT_MAT_GLASS;
+            m[i] = to_dmat(q.material);
+            tr[i] = q.material.transparency;
+        }
+        const SquareIn *d_in = nullptr;
+        DSquare *d_sq = nullptr;
+        if ((rc = dev_upload(s, in.data(), in.size(), &d_in))) return rc;
+        if ((rc = dev_alloc(s, in.size(), &d_sq))) return rc;
+        k_precompute_squares<<<(unsigned)((in.size() + 127) / 128), 128>>>(d_in, d_sq, (int)in.size());
+        RT_CUDA(cudaGetLastError());
+        d.squares = d_sq;
+        if ((rc = dev_upload(s, m.data(), m.size(), &d.sq_mat))) return rc;
+        if ((rc = dev_upload(s, tr.data(), tr.size(), &d.sq_transparency))) return rc;
+    }
+    // lights
+    {
+        std::vector<DLight> l(desc->n_lights);
+        for (uint32_t i = 0; i < desc->n_lights; ++i) {
+            for (int k = 0; k < 3; ++k) { l[i].pos[k] = desc->lights[i].pos[k]; l[i].color[k] = desc->lights[i].color[k]; }
+            l[i].radius = desc->lights[i].radius;
+        }
+        if ((rc = dev_upload(s, l.data(), l.size(), &d.lights))) return rc;
+    }
+    // meshes
+    if (desc->n_meshes) {
+        std::vector<DMesh> dm(desc->n_meshes);
+        std::vector<DMaterial> m(desc->n_meshes);
+        std::vector<float> tr(desc->n_meshes);
+        for (uint32_t i = 0; i < desc->n_meshes; ++i) {
+            const RtSceneMesh &src = desc->meshes[i];
+            if ((rc = check_material(src.material, *desc))) return rc;
+            if ((src.n_vertices && !src.positions) || (src.n_triangles && !src.triangles) || (src.n_nodes && !src.nodes) || (src.n_leaf_refs && !src.leaf_refs))
+                return fail(RT_ERR_INVALID, "mesh with a null array");
+            if (src.color_type == RT_COLOR_VERTEX && !src.vert_colors) return fail(RT_ERR_INVALID, "vertex-coloured mesh without vert_colors");
+            if (src.color_type == RT_COLOR_FACE && !src.face_colors) return fail(RT_ERR_INVALID, "face-coloured mesh without face_colors");
+            DMesh &o = dm[i];
+            memset(&o, 0, sizeof o);
+            for (int k = 0; k < 3; ++k) { o.bmin[k] = src.root_bmin[k]; o.bmax[k] = src.root_bmax[k]; }
+            o.n_nodes = src.n_nodes;
+            o.color_type = src.color_type;
+            // validate + pack nodes
+            std::vector<float4> lo(src.n_nodes), hi(src.n_nodes);
+            for (uint32_t k = 0; k < src.n_nodes; ++k) {
+                const RtKdNode &n = src.nodes[k];
+                if (n.is_leaf) {
+                    if ((uint64_t)n.first_ref + n.n_refs > src.n_leaf_refs || n.n_refs >= 0x80000000u) return fail(RT_ERR_INVALID, "KD leaf range out of bounds");
+                    lo[k] = make_float4(n.bmin[0], n.bmin[1], n.bmin[2], u2f(n.first_ref));
+                    hi[k] = make_float4(n.bmax[0], n.bmax[1], n.bmax[2], u2f(0x80000000u | n.n_refs));
+                } else {
+                    if (n.skip <= k || n.skip > src.n_nodes) return fail(RT_ERR_INVALID, "KD skip link out of bounds");
+                    lo[k] = make_float4(n.bmin[0], n.bmin[1], n.bmin[2], u2f(n.skip));
+                    hi[k] = make_float4(n.bmax[0], n.bmax[1], n.bmax[2], u2f(0u));
+                }
+            }
+            for (uint32_t k = 0; k < src.n_leaf_refs; ++k)
+                for (int j = 0; j < 3; ++j)
+                    if (src.leaf_refs[k].v[j] >= src.n_vertices) return fail(RT_ERR_INVALID, "leaf ref vertex index out of bounds");
+            for (uint32_t k = 0; k < src.n_leaf_refs; ++k)
+                if (src.leaf_refs[k].tri_index >= src.n_triangles) return fail(RT_ERR_INVALID, "leaf ref triangle index out of bounds");
+            if ((rc = dev_upload(s, lo.data(), lo.size(), &o.node_lo))) return rc;
+            if ((rc = dev_upload(s, hi.data(), hi.size(), &o.node_hi))) return rc;
+            if ((rc = dev_upload(s, src.triangles, (size_t)3 * src.n_triangles, &o.triangles))) return rc;
+            if (src.color_type == RT_COLOR_VERTEX && (rc = dev_upload(s, src.vert_colors, (size_t)3 * src.n_vertices, &o.vert_colors))) return rc;
+            if (src.color_type == RT_COLOR_FACE && (rc = dev_upload(s, src.face_colors, (size_t)3 * src.n_triangles, &o.face_colors))) return rc;
+            if (src.n_leaf_refs) {
+                float *d_pos = nullptr; RtTriRef *d_refs = nullptr;
+                RT_CUDA(cudaMalloc((void **)&d_pos, (size_t)3 * src.n_vertices * sizeof(float)));
+                cudaError_t e = cudaMalloc((void **)&d_refs, (size_t)src.n_leaf_refs * sizeof(RtTriRef));
+                if (e != cudaSuccess) { cudaFree(d_pos); RT_CUDA(e); }
+                float4 *pl = nullptr, *ed = nullptr; float2 *dn = nullptr;
+                rc = dev_alloc(s, (size_t)src.n_leaf_refs, &pl);
+                if (!rc) rc = dev_alloc(s, (size_t)3 * src.n_leaf_refs, &ed);
+                if (!rc) rc = dev_alloc(s, (size_t)src.n_leaf_refs, &dn);
+                cudaError_t e1 = cudaSuccess;
+                if (!rc) {
+                    e1 = cudaMemcpy(d_pos, src.positions, (size_t)3 * src.n_vertices * sizeof(float), cudaMemcpyHostToDevice);
+                    if (e1 == cudaSuccess) e1 = cudaMemcpy(d_refs, src.leaf_refs, (size_t)src.n_leaf_refs * sizeof(RtTriRef), cudaMemcpyHostToDevice);
+                    if (e1 == cudaSuccess) {
+                        k_precompute_tris<<<(src.n_leaf_refs + 127) / 128, 128>>>(d_pos, d_refs, src.n_leaf_refs, pl, ed, dn);
+                        e1 = cudaGetLastError();
+                        if (e1 == cudaSuccess) e1 = cudaDeviceSynchronize();
+                    }
+                }
+                cudaFree(d_pos); cudaFree(d_refs);
+                if (rc) return rc;
+                RT_CUDA(e1);
+                o.tri_plane = pl; o.tri_edge = ed; o.tri_den = dn;
+            }
+            m[i] = to_dmat(src.material);
+            tr[i] = src.material.transparency;
+        }
+        if ((rc = dev_upload(s, dm.data(), dm.size(), &d.meshes))) return rc;
+        if ((rc = dev_upload(s, m.data(), m.size(), &d.mesh_mat))) return rc;
+        if ((rc = dev_upload(s, tr.data(), tr.size(), &d.mesh_transparency))) return rc;
+    }
+    RT_CUDA(cudaDeviceSynchronize());
+    guard.keep = true;
+    *out = s;
+    return RT_OK;
+}
+
+int64_t rt_render_pixel_count(const RtRenderParams *p) {
+    if (!p) return -1;
+    Rect r;
+    if (resolve_rect(*p, r)) return -1;
+    std::vector<TileRec> tiles; std::vector<unsigned int> off;
+    build_tiles(*p, r, tiles, off);
+    return (int64_t)off.back();
+}
+
+int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p, float *d_gamma, float *d_linear,
+                     void *cuda_stream, RtStats *stats) {
+    if (!s || !camera || !p) return fail(RT_ERR_INVALID, "null argument");
+    Rect r;
+    int rc = resolve_rect(*p, r);
+    if (rc) return rc;
+    RT_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    build_tiles(*p, r, s->h_tiles, s->h_tile_off);
+    const size_t n_tiles = s->h_tiles.size();
+    const unsigned long long n_pixels = s->h_tile_off.back();
+    if (stats) { memset(stats, 0, sizeof *stats); stats->n_tiles = (uint32_t)n_tiles; stats->n_samples = n_pixels * (unsigned long long)p->spp; }
+    if (n_pixels == 0) return RT_OK;
+
+    // chunking: whole pixels, at most ~16 Mi paths in flight (192 MiB of samples)
+    const unsigned long long max_paths = 16ull << 20;
+    unsigned long long chunk_pixels = std::max<unsigned long long>(1, max_paths / (unsigned long long)p->spp);
+    chunk_pixels = std::min(chunk_pixels, n_pixels);
+    if ((rc = ensure_scratch(s, (size_t)(chunk_pixels * p->spp * 3ull), n_tiles))) return rc;
+    RT_CUDA(cudaMemcpyAsync(s->d_tiles, s->h_tiles.data(), n_tiles * sizeof(TileRec), cudaMemcpyHostToDevice, st));
+    RT_CUDA(cudaMemcpyAsync(s->d_tile_off, s->h_tile_off.data(), (n_tiles + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+
+    DCamera cam;
+    fill_camera(*camera, cam);
+    const bool want_stats = p->collect_stats != 0 && stats != nullptr;
+    const void *kern = want_stats ? (const void *)k_render_paths<true> : (const void *)k_render_paths<false>;
+    const int grid = persistent_grid(s, kern, 128);
+
+    RenderArgs a{};
+    a.tiles = s->d_tiles; a.tile_off = s->d_tile_off; a.n_tiles = (int)n_tiles;
+    a.width = p->width; a.height = p->height; a.spp = p->spp; a.max_bounces = p->max_bounces; a.nb_ech = p->nb_ech;
+    a.seed = p->seed; a.samples = s->samples; a.work_counter = s->counters; a.stats = want_stats ? s->counters + 1 : nullptr;
+    uint32_t launches = 0;
+    RT_CUDA(cudaMemsetAsync(s->counters, 0, 16 * sizeof(unsigned long long), st));
+    if (stats) RT_CUDA(cudaEventRecord(s->ev0, st));
+    for (unsigned long long pb = 0; pb < n_pixels; pb += chunk_pixels) {
+        const unsigned long long np = std::min(chunk_pixels, n_pixels - pb);
+        a.pixel_begin = pb;
+        a.n_paths = np * (unsigned long long)p->spp;
+        if (pb) RT_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long), st));
+        const unsigned long long batches = (a.n_paths + 31) / 32;
+        const int g = (int)std::min<unsigned long long>((unsigned long long)grid, (batches + 3) / 4);
+        if (want_stats) k_render_paths<true><<<g, 128, 0, st>>>(s->d, cam, a);
+        else k_render_paths<false><<<g, 128, 0, st>>>(s->d, cam, a);
+        RT_CUDA(cudaGetLastError());
+        k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(s->samples, pb, (unsigned int)np, p->spp, d_linear, d_gamma);
+        RT_CUDA(cudaGetLastError());
+        launches += 2;
+    }
+    if (stats) {
+        RT_CUDA(cudaEventRecord(s->ev1, st));
+        RT_CUDA(cudaEventSynchronize(s->ev1));
+        float ms = 0.f;
+        RT_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        stats->kernel_ms = ms;
+        stats->n_launches = launches;
+        if (want_stats) {
+            unsigned long long c[11];
+            RT_CUDA(cudaMemcpy(c, s->counters, sizeof c, cudaMemcpyDeviceToHost));
+            stats->n_closest_rays = c[1]; stats->n_shadow_rays = c[2]; stats->n_sphere_tests = c[3]; stats->n_square_tests = c[4];
+            stats->n_mesh_tests = c[5]; stats->n_node_visits = c[6]; stats->n_tri_tests = c[7]; stats->n_tri_full = c[8];
+            stats->n_tex_fetches = c[9]; stats->n_random = c[10];
+        }
+    }
+    return RT_OK;
+}
+
+int rt_untile_device(const RtRenderParams *p, const float *d_packed, const int64_t *pixel_offsets, float *d_image,
+                     int device, void *cuda_stream) {
+    if (!p || !d_packed || !d_image) return fail(RT_ERR_INVALID, "null argument");
+    Rect r;
+    int rc = resolve_rect(*p, r);
+    if (rc) return rc;
+    RT_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int nr = p->n_ranks > 1 ? p->n_ranks : 1;
+    for (int rk = 0; rk < nr; ++rk) {
+        RtRenderParams q = *p;
+        q.rank = rk;
+        std::vector<TileRec> tiles; std::vector<unsigned int> off;
+        build_tiles(q, r, tiles, off);
+        if (tiles.empty()) continue;
+        TileRec *dt = nullptr; unsigned int *doff = nullptr;
+        RT_CUDA(cudaMallocAsync((void **)&dt, tiles.size() * sizeof(TileRec), st));
+        RT_CUDA(cudaMallocAsync((void **)&doff, off.size() * sizeof(unsigned int), st));
+        RT_CUDA(cudaMemcpyAsync(dt, tiles.data(), tiles.size() * sizeof(TileRec), cudaMemcpyHostToDevice, st));
+        RT_CUDA(cudaMemcpyAsync(doff, off.data(), off.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+        RT_CUDA(cudaStreamSynchronize(st));   // the host vectors go out of scope below
+        const unsigned int np = off.back();
+        const float *src = d_packed + 3 * (pixel_offsets ? pixel_offsets[rk] : 0);
+        k_untile<<<(np + 255) / 256, 256, 0, st>>>(dt, doff, (int)tiles.size(), src, d_image, r.x0, r.y0, r.x1 - r.x0, np);
+        RT_CUDA(cudaGetLastError());
+        RT_CUDA(cudaFreeAsync(dt, st));
+        RT_CUDA(cudaFreeAsync(doff, st));
+    }
+    return RT_OK;
+}
+
+int rt_render(RtScene *s, const RtCamera *camera, const RtRenderParams *p, float *gamma_rgb, float *linear_rgb, RtStats *stats) {
+    if (!s || !camera || !p) return fail(RT_ERR_INVALID, "null argument");
+    if (!gamma_rgb && !linear_rgb) return fail(RT_ERR_INVALID, "no output buffer");
+    Rect r;
+    int rc = resolve_rect(*p, r);
+    if (rc) return rc;
+    RT_CUDA(cudaSetDevice(s->device));
+    const int64_t np = rt_render_pixel_count(p);
+    if (np <= 0) { if (stats) memset(stats, 0, sizeof *stats); return RT_OK; }
+    const size_t rect_px = (size_t)(r.x1 - r.x0) * (size_t)(r.y1 - r.y0);
+    const int n_out = (gamma_rgb ? 1 : 0) + (linear_rgb ? 1 : 0);
+    float *d_packed = nullptr, *d_image = nullptr;
+    RT_CUDA(cudaMalloc((void **)&d_packed, (size_t)np * 3 * sizeof(float) * n_out));
+    struct Free { float *&p; ~Free() { if (p) cudaFree(p); } } f1{d_packed}, f2{d_image};
+    float *dg = gamma_rgb ? d_packed : nullptr;
+    float *dl = linear_rgb ? d_packed + (gamma_rgb ? (size_t)np * 3 : 0) : nullptr;
+    RtStats local;
+    rc = rt_render_device(s, camera, p, dg, dl, nullptr, stats ? stats : &local);
+    if (rc) return rc;
+    const bool sharded = p->n_ranks > 1;
+    if (!sharded) {
+        RT_CUDA(cudaMalloc((void **)&d_image, rect_px * 3 * sizeof(float)));
+        float *outs[2] = {gamma_rgb, linear_rgb};
+        const float *srcs[2] = {dg, dl};
+        for (int k = 0; k < 2; ++k) {
+            if (!outs[k]) continue;
+            if ((rc = rt_untile_device(p, srcs[k], nullptr, d_image, s->device, nullptr))) return rc;
+            RT_CUDA(cudaMemcpy(outs[k], d_image, rect_px * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+    } else {
+        // other ranks' tiles must stay untouched: bring the packed pixels back and scatter rows on the host
+        std::vector<float> h((size_t)np * 3);
+        float *outs[2] = {gamma_rgb, linear_rgb};
+        const float *srcs[2] = {dg, dl};
+        const int rw = r.x1 - r.x0;
+        for (int k = 0; k < 2; ++k) {
+            if (!outs[k]) continue;
+            RT_CUDA(cudaMemcpy(h.data(), srcs[k], h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            for (size_t t = 0; t < s->h_tiles.size(); ++t) {
+                const TileRec &tr = s->h_tiles[t];
+                const float *src = h.data() + 3 * (size_t)s->h_tile_off[t];
+                for (int y = 0; y < tr.h; ++y)
+                    memcpy(outs[k] + 3 * ((size_t)(tr.y0 - r.y0 + y) * rw + (tr.x0 - r.x0)), src + 3 * (size_t)y * tr.w, (size_t)tr.w * 3 * sizeof(float));
+            }
+        }
+    }
+    return RT_OK;
+}
+
+int rt_trace_primary(RtScene *s, const RtCamera *camera, const RtRenderParams *p, uint32_t *ids) {
+    if (!s || !camera || !p || !ids) return fail(RT_ERR_INVALID, "null argument");
+    Rect r;
+    int rc = resolve_rect(*p, r);
+    if (rc) return rc;
+    RT_CUDA(cudaSetDevice(s->device));
+    const int rw = r.x1 - r.x0, rh = r.y1 - r.y0;
+    const size_t n = (size_t)rw * rh;
+    uint32_t *d = nullptr;
+    RT_CUDA(cudaMalloc((void **)&d, n * 4 * sizeof(uint32_t)));
+    DCamera cam;
+    fill_camera(*camera, cam);
+    k_primary_ids<<<(unsigned)((n + 127) / 128), 128>>>(s->d, cam, p->width, p->height, p->seed, r.x0, r.y0, rw, rh, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(ids, d, n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    RT_CUDA(e);
+    return RT_OK;
+}
+
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t put(const void *h, size_t bytes) {
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e == cudaSuccess && h && bytes) e = cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice);
+        return e;
+    }
+};
+}  // namespace
+
+int rt_trace_rays(RtScene *s, size_t n, const float *org, const float *dir, const float *time, uint32_t *ids, float *aux) {
+    if (!s || !org || !dir || !ids) return fail(RT_ERR_INVALID, "null argument");
+    if (n == 0) return RT_OK;
+    RT_CUDA(cudaSetDevice(s->device));
+    DevBuf o, d, t, i, a;
+    RT_CUDA(o.put(org, n * 12)); RT_CUDA(d.put(dir, n * 12));
+    if (time) RT_CUDA(t.put(time, n * 4));
+    RT_CUDA(i.put(nullptr, n * 16));
+    if (aux) RT_CUDA(a.put(nullptr, n * 32));
+    k_trace_rays<<<(unsigned)((n + 127) / 128), 128>>>(s->d, n, (const float *)o.p, (const float *)d.p, time ? (const float *)t.p : nullptr, (uint32_t *)i.p, aux ? (float *)a.p : nullptr);
+    RT_CUDA(cudaGetLastError());
+    RT_CUDA(cudaMemcpy(ids, i.p, n * 16, cudaMemcpyDeviceToHost));
+    if (aux) RT_CUDA(cudaMemcpy(aux, a.p, n * 32, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+int rt_shade_rays(RtScene *s, size_t n, const float *org, const float *dir, const float *time, const RtRenderParams *p, float *rgb) {
+    if (!s || !org || !dir || !rgb || !p) return fail(RT_ERR_INVALID, "null argument");
+    if (p->max_bounces < 0 || p->max_bounces > RT_MAX_BOUNCES || p->nb_ech < 1) return fail(RT_ERR_INVALID, "bad max_bounces / nb_ech");
+    if (n == 0) return RT_OK;
+    RT_CUDA(cudaSetDevice(s->device));
+    DevBuf o, d, t, c;
+    RT_CUDA(o.put(org, n * 12)); RT_CUDA(d.put(dir, n * 12));
+    if (time) RT_CUDA(t.put(time, n * 4));
+    RT_CUDA(c.put(nullptr, n * 12));
+    k_shade_rays<<<(unsigned)((n + 127) / 128), 128>>>(s->d, n, (const float *)o.p, (const float *)d.p, time ? (const float *)t.p : nullptr, p->seed, p->max_bounces, p->nb_ech, (float *)c.p);
+    RT_CUDA(cudaGetLastError());
+    RT_CUDA(cudaMemcpy(rgb, c.p, n * 12, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,652 @@
+// rt_core.cuh — the render path as device functions (sm_100a).
+//
+// Everything the reference does per ray lives here, restated for the flattened scene:
+//   closest hit      Scene::computeIntersection  Scene.h:202-230
+//   occlusion        Scene::computeShadow        Scene.h:235-255
+//   sphere           Sphere::intersect           Sphere.h:91-132
+//   square           Square::intersect           Square.h:65-126
+//   box slab         AABB::intersects            AABB.h:48-65
+//   triangle         Triangle ctor/getIntersection/computeBarycentricCoordinates  Triangle.h:26-37,62-126
+//   KD traversal     KDTree::intersect / Node::intersect  KDTree.cpp:31-85
+//   shading          Scene::rayTraceRecursive    Scene.h:258-342
+//   materials        Material::{scatter,emit,texture,sphere_texture,get_normal}  Material.cpp:13-130
+//   helpers          reflect/refract/reflectance/random_unit_vector  Functions.cpp:14-54
+//   sky              Scene::skyboxTexture        Scene.h:149-161
+//
+// PARITY RULES. The reference is plain IEEE fp32 evaluated left to right with NO
+// fused multiply-add (g++ -O3, x86-64 baseline), promoting to fp64 at specific places. This file
+// is compiled with -fmad=false -prec-div=true -prec-sqrt=true -ftz=false, every expression keeps
+// the reference's association, and the fp64 promotions are written out. Comparisons keep the
+// reference's polarity so NaNs (zero-area triangles, rays parallel to a slab) fall the same way.
+// Comparisons against the double constant EPSILON = 0.00001 are folded to float compares:
+//   x >= EPSILON  <=>  x > 1e-5f ;  x < -EPSILON  <=>  x < -1e-5f ;  x <= EPSILON  <=>  x <= 1e-5f
+// because 1e-5f = 9.99999975e-6 is the largest float below the double 1.0000000000000001e-5.
+//
+// The file also compiles as plain C++ (RT_HD expands to `inline`) so that tests can run these
+// exact functions on the CPU for debugging; that build is test-only (tests/hostsim/) and is never
+// linked into the product library.
+#ifndef HAI719_RT_CORE_CUH
+#define HAI719_RT_CORE_CUH
+
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#ifdef __CUDACC__
+#define RT_HD __device__ __forceinline__
+#define RT_HHD __host__ __device__ __forceinline__
+#define RT_LDG(p) __ldg(p)
+#else
+#define RT_HD inline
+#define RT_HHD inline
+#define RT_LDG(p) (*(p))
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+#endif
+
+namespace rt {
+
+#define RT_EPSF 1e-5f          /* (float)EPSILON */
+#define RT_MAX_BOUNCES 16      /* capacity of the per-path radiance records */
+#define RT_PI 3.14159265358979323846 /* M_PI */
+
+// ---- vectors -----------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+RT_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+RT_HD V3 v3(float f) { return v3(f, f, f); }
+RT_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_HD V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+RT_HD V3 operator*(V3 a, float s) { return v3(s * a.x, s * a.y, s * a.z); }
+RT_HD V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+RT_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }   // (x+y)+z, Vec3.h:36
+RT_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+RT_HD V3 comp_product(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RT_HD float length(V3 a) { return sqrtf(dot(a, a)); }                        // Vec3.h:32
+RT_HD V3 normalized(V3 a) { const float L = length(a); return v3(a.x / L, a.y / L, a.z / L); }  // Vec3.h:35
+RT_HD V3 ld3(const float *p) { return v3(p[0], p[1], p[2]); }
+RT_HD float fminr(float a, float b) { return a < b ? a : b; }                // ::min, Functions.cpp:20
+RT_HD float fmaxr(float a, float b) { return a > b ? a : b; }                // ::max, Functions.cpp:24
+RT_HHD uint32_t f2u(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+RT_HHD float u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+
+// ---- random stream (definition in include/hai719_rt.h) ----------------------------------------
+RT_HD uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+struct Rng {
+    uint32_t key, ctr;
+    RT_HD void init(uint32_t seed, uint32_t pixel, uint32_t sample) {
+        key = fmix32(fmix32(seed ^ ((pixel + 1u) * 0x9E3779B9u)) + (sample + 1u) * 0x85EBCA6Bu);
+        ctr = 0;
+    }
+    RT_HD float next() {   // random_float(), Functions.cpp:4-8
+        const uint32_t r = fmix32(key + ctr * 0x9E3779B9u);
+        ++ctr;
+        return (float)(r >> 8) * (1.0f / 16777216.0f);
+    }
+};
+// random_unit_vector (Functions.cpp:14-18): a point of the cube [-1,1]^3, normalised. The three
+// draws are constructor arguments, evaluated right to left by g++: z, then y, then x.
+RT_HD V3 random_unit_vector(Rng &rng) {
+    const float z = -1.f + 2.f * rng.next();
+    const float y = -1.f + 2.f * rng.next();
+    const float x = -1.f + 2.f * rng.next();
+    return normalized(v3(x, y, z));
+}
+
+// ---- device scene ------------------------------------------------------------------------------
+struct DMaterial {          // mirrors RtMaterial (include/hai719_rt.h)
+    int type, texture_type;
+    float kd[3];
+    float transparency, index_medium;
+    float checker1[3], checker2[3];
+    float tsx, tsy;
+    int emissive;
+    float light_color[3];
+    float light_intensity;
+    int image, normal_map;
+    float motion[3];
+};
+struct DImage { int w, h; const unsigned char *rgb; };
+struct DSquare {            // per-square constants of Square::intersect hoisted out of the ray loop
+    float v0[3];            // vertices[0].position
+    float n[3];             // normalize(cross(v1-v0, v3-v0))            Square.h:69-72
+    float right[3], up[3];  // v1-v0, v3-v0
+    float len_r, len_u;     // |right|, |up|                             Square.h:106,110
+    float motion[3];
+    int glass;              // material.type == Material_Glass           Square.h:84
+    float tan_r[3], tan_u[3];  // m_right_vector / m_up_vector members (normal-map frame)
+};
+struct DMesh {
+    float bmin[3], bmax[3];
+    uint32_t n_nodes;
+    // node i: lo = {bmin.xyz, bits(inner: skip | leaf: first_ref)}, hi = {bmax.xyz, bits(leaf: 0x80000000|n_refs, inner: 0)}
+    const float4 *node_lo, *node_hi;
+    const float4 *tri_plane;   // per leaf ref: {n.xyz, D = c0.n}
+    const float4 *tri_edge;    // per leaf ref, 3 entries: {c0.xyz, d00}, {e0.xyz, d01}, {e1.xyz, d11}
+    const float2 *tri_den;     // per leaf ref: {denom, bits(tri_index)}
+    int color_type;
+    const float *vert_colors, *face_colors;
+    const uint32_t *triangles;
+};
+struct DLight { float pos[3]; float radius; float color[3]; };
+struct DScene {
+    int n_spheres, n_squares, n_meshes, n_lights;
+    const float4 *sph_a;       // {c.xyz, r}
+    const float4 *sph_b;       // {motion.xyz, transparency}
+    const DSquare *squares;
+    const float *sq_transparency;
+    const DMesh *meshes;
+    const float *mesh_transparency;
+    const DMaterial *sph_mat, *sq_mat, *mesh_mat;
+    const DLight *lights;
+    const DImage *textures, *normal_maps;
+    DImage sky;
+    int dark_sky;
+};
+
+struct Counters {   // per-thread work counters (only touched when STATS)
+    unsigned long long closest, shadow, sphere, square, mesh, node, tri, tri_full, tex, rnd;
+};
+
+struct Ray {
+    V3 o, d;
+    float time;
+};
+// Ray(o, d, time): the Line constructor normalises d (Line.h:13-16)
+RT_HD Ray make_ray(V3 o, V3 d, float time) { Ray r; r.o = o; r.d = normalized(d); r.time = time; return r; }
+
+struct Hit {
+    int type;       // 0 miss, 1 sphere, 2 square, 3 mesh
+    int obj;
+    float t;
+    uint32_t ref;   // mesh: leaf-ref index of the winning triangle test
+};
+
+// ---- sphere ------------------------------------------------------------------------------------
+// Sphere::intersect up to t (Sphere.h:94-123). Returns NaN when delta < 0 (sqrt of a negative),
+// which every caller's "t > eps && t < best" rejects, exactly like intersectionExists == false.
+// Only the near root is ever reported (Sphere.h:112-117 can never take the far one).
+RT_HD float sphere_t(const Ray &ray, float4 a, float4 b) {
+    const V3 c = v3(a.x, a.y, a.z) + ray.time * v3(b.x, b.y, b.z);
+    const V3 oc = ray.o - c;
+    const float A = dot(ray.d, ray.d);
+    const float B = 2.f * dot(ray.d, oc);
+    const float C = dot(oc, oc) - a.w * a.w;
+    const float delta = B * B - 4.f * A * C;
+    return (-B - sqrtf(delta)) / (2.f * A);
+}
+
+// ---- square ------------------------------------------------------------------------------------
+// Square::intersect (Square.h:65-126). Returns t and (u, v), or FLT_MAX when there is no hit.
+RT_HD float square_t(const Ray &ray, const DSquare &q, float &u, float &v) {
+    const V3 n = ld3(q.n);
+    const float dotRN = dot(ray.d, n);
+    // parallel (== 0) or back face of a non-glass quad (> 0) miss; a NaN goes on and fails below
+    if (dotRN == 0.f) return FLT_MAX;
+    if (dotRN > 0.f && !q.glass) return FLT_MAX;
+    const V3 bl = ld3(q.v0) + ray.time * ld3(q.motion);
+    const float D = dot(bl, n);
+    const float t = (D - dot(ray.o, n)) / dotRN;
+    if (t < -RT_EPSF) return FLT_MAX;
+    if (t > RT_EPSF) {
+        const V3 p = ray.o + t * ray.d;
+        const V3 w = p - bl;
+        const float proj1 = dot(w, ld3(q.right)) / q.len_r;
+        const float proj2 = dot(w, ld3(q.up)) / q.len_u;
+        if ((proj1 <= q.len_r && proj1 >= 0.f) && (proj2 <= q.len_u && proj2 >= 0.f)) {
+            u = proj1 / q.len_r;
+            v = proj2 / q.len_u;
+            return t;
+        }
+    }
+    return FLT_MAX;
+}
+
+// ---- box ---------------------------------------------------------------------------------------
+// AABB::intersects (AABB.h:48-65): tmin = (float)EPSILON, tmax = FLT_MAX; 1/d and the two products
+// in fp64, rounded to float when stored in t0/t1. inv = 1.0 / (double)d per axis, hoisted per ray.
+struct RayInv { double x, y, z; };
+RT_HD RayInv make_inv(const Ray &r) { RayInv i; i.x = 1.0 / (double)r.d.x; i.y = 1.0 / (double)r.d.y; i.z = 1.0 / (double)r.d.z; return i; }
+
+#define RT_SLAB_AXIS(LO, HI, O, INV)                                  \
+    {                                                                 \
+        const float t0 = (float)((double)((LO) - (O)) * (INV));       \
+        const float t1 = (float)((double)((HI) - (O)) * (INV));       \
+        if (t0 < t1) {                                                \
+            if (t0 > tmin) tmin = t0;                                 \
+            if (t1 < tmax) tmax = t1;                                 \
+        } else {                                                      \
+            if (t1 > tmin) tmin = t1;                                 \
+            if (t0 < tmax) tmax = t0;                                 \
+        }                                                             \
+        if (tmax <= tmin) return false;                               \
+    }
+RT_HD bool slab_hit(const Ray &r, const RayInv &inv, float lx, float ly, float lz, float hx, float hy, float hz) {
+    float tmin = RT_EPSF, tmax = FLT_MAX;
+    RT_SLAB_AXIS(lx, hx, r.o.x, inv.x)
+    RT_SLAB_AXIS(ly, hy, r.o.y, inv.y)
+    RT_SLAB_AXIS(lz, hz, r.o.z, inv.z)
+    return true;
+}
+
+// ---- triangle ----------------------------------------------------------------------------------
+// Per-reference constants (computed once by precompute_triangle, same arithmetic as the Triangle
+// constructor that the reference runs per ray per triangle, KDTree.cpp:38-40):
+//   c_i = 1.000001f * vertex_i ; e0 = c1-c0 ; e1 = c2-c0 ; n = cross(e0,e1)/|cross| ; D = c0.n
+//   d00 = e0.e0 ; d01 = e0.e1 ; d11 = e1.e1 ; denom = d00*d11 - d01*d01
+struct TriConst { float4 plane, c0, e0, e1; float2 den; };
+RT_HD TriConst precompute_triangle(V3 p0, V3 p1, V3 p2, uint32_t tri_index) {
+    const float s = 1.000001f;
+    const V3 c0 = p0 * s, c1 = p1 * s, c2 = p2 * s;
+    const V3 e0 = c1 - c0, e1 = c2 - c0;
+    const V3 nn = cross(e0, e1);
+    const float norm = length(nn);
+    const V3 n = nn / norm;                       // 0/0 = NaN for zero-area triangles, kept (A.1-18)
+    TriConst k;
+    k.plane = make_float4(n.x, n.y, n.z, dot(c0, n));
+    const float d00 = dot(e0, e0), d01 = dot(e0, e1), d11 = dot(e1, e1);
+    k.c0 = make_float4(c0.x, c0.y, c0.z, d00);
+    k.e0 = make_float4(e0.x, e0.y, e0.z, d01);
+    k.e1 = make_float4(e1.x, e1.y, e1.z, d11);
+    k.den = make_float2(d00 * d11 - d01 * d01, u2f(tri_index));
+    return k;
+}
+
+// Triangle::getIntersection (Triangle.h:77-126). Returns t, or FLT_MAX for "no intersection".
+template <bool STATS>
+RT_HD float triangle_t(const Ray &ray, const DMesh &m, uint32_t ref, float &w0, float &w1, float &w2, Counters *cnt) {
+    const float4 pl = RT_LDG(m.tri_plane + ref);
+    const V3 n = v3(pl.x, pl.y, pl.z);
+    const float dotRN = dot(ray.d, n);
+    if (!(dotRN < 0.f)) return FLT_MAX;           // == 0, > 0; a NaN normal can never pass the final test
+    const float t = (pl.w - dot(ray.o, n)) / dotRN;
+    if (!(t >= 0.f)) return FLT_MAX;              // t < 0; NaN likewise ends in "no intersection"
+    if (STATS) cnt->tri_full++;
+    const V3 p = ray.o + t * ray.d;
+    const float4 a = RT_LDG(m.tri_edge + 3 * ref), b = RT_LDG(m.tri_edge + 3 * ref + 1), c = RT_LDG(m.tri_edge + 3 * ref + 2);
+    const V3 q = p - v3(a.x, a.y, a.z);
+    const float d20 = dot(q, v3(b.x, b.y, b.z));
+    const float d21 = dot(q, v3(c.x, c.y, c.z));
+    const float denom = RT_LDG(m.tri_den + ref).x;
+    const float u1 = (c.w * d20 - b.w * d21) / denom;
+    const float u2 = (a.w * d21 - b.w * d20) / denom;
+    const float u0 = 1.f - u1 - u2;
+    if (u0 >= 0.f && u0 <= 1.f && u1 >= 0.f && u1 <= 1.f && u2 >= 0.f && u2 <= 1.f) {
+        w0 = u0; w1 = u1; w2 = u2;
+        return t;
+    }
+    return FLT_MAX;
+}
+
+// ---- mesh: stackless pre-order KD traversal ----------------------------------------------------
+// KDTree::intersect + Node::intersect. The reference recurses into BOTH children of every node
+// whose box the ray touches, without ordering or early exit, and combines with
+// "left.t < right.t ? left : right"  =>  over the leaves in depth-first order the result is the
+// minimum t, the LAST leaf winning ties; inside a leaf the FIRST triangle wins ties (strict <).
+// The pre-order array reproduces that order with no stack: a missed box jumps to `skip`.
+template <bool STATS>
+RT_HD bool mesh_closest(const Ray &ray, const RayInv &inv, const DMesh &m, float &t_out, uint32_t &ref_out, Counters *cnt) {
+    if (m.n_nodes == 0) return false;
+    if (!slab_hit(ray, inv, m.bmin[0], m.bmin[1], m.bmin[2], m.bmax[0], m.bmax[1], m.bmax[2])) return false;
+    float best_t = FLT_MAX;
+    uint32_t best_ref = 0xFFFFFFFFu;
+    uint32_t i = 0;
+    const uint32_t n_nodes = m.n_nodes;
+    while (i < n_nodes) {
+        const float4 lo = RT_LDG(m.node_lo + i), hi = RT_LDG(m.node_hi + i);
+        const uint32_t hw = f2u(hi.w);
+        const bool leaf = (hw & 0x80000000u) != 0u;
+        if (STATS) cnt->node++;
+        if (!slab_hit(ray, inv, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) {
+            i = leaf ? i + 1 : f2u(lo.w);
+            continue;
+        }
+        if (leaf) {
+            const uint32_t first = f2u(lo.w), count = hw & 0x7FFFFFFFu;
+            float leaf_t = FLT_MAX;
+            uint32_t leaf_ref = 0xFFFFFFFFu;
+            for (uint32_t k = first; k < first + count; ++k) {
+                float a, b, c;
+                if (STATS) cnt->tri++;
+                const float t = triangle_t<STATS>(ray, m, k, a, b, c, cnt);
+                if (t < leaf_t) { leaf_t = t; leaf_ref = k; }
+            }
+            if (leaf_ref != 0xFFFFFFFFu && leaf_t <= best_t) { best_t = leaf_t; best_ref = leaf_ref; }
+        }
+        ++i;
+    }
+    if (best_ref == 0xFFFFFFFFu) return false;
+    t_out = best_t;
+    ref_out = best_ref;
+    return true;
+}
+
+// ---- scene: closest hit ------------------------------------------------------------------------
+// Scene::computeIntersection: spheres, then squares, then meshes; a candidate replaces the current
+// best only if t < best.t && t >= EPSILON (strict <: first object wins ties within a type, and
+// spheres beat squares beat meshes).
+template <bool STATS>
+RT_HD Hit closest_hit(const DScene &s, const Ray &ray, float &aux_u, float &aux_v, Counters *cnt) {
+    Hit h; h.type = 0; h.obj = -1; h.t = FLT_MAX; h.ref = 0;
+    if (STATS) cnt->closest++;
+    for (int i = 0; i < s.n_spheres; ++i) {
+        if (STATS) cnt->sphere++;
+        const float t = sphere_t(ray, RT_LDG(s.sph_a + i), RT_LDG(s.sph_b + i));
+        if (t < h.t && t > RT_EPSF) { h.type = 1; h.obj = i; h.t = t; }
+    }
+    for (int i = 0; i < s.n_squares; ++i) {
+        if (STATS) cnt->square++;
+        float u, v;
+        const float t = square_t(ray, s.squares[i], u, v);
+        if (t < h.t && t > RT_EPSF) { h.type = 2; h.obj = i; h.t = t; aux_u = u; aux_v = v; }
+    }
+    if (s.n_meshes > 0) {
+        const RayInv inv = make_inv(ray);
+        for (int i = 0; i < s.n_meshes; ++i) {
+            if (STATS) cnt->mesh++;
+            float t; uint32_t ref;
+            if (mesh_closest<STATS>(ray, inv, s.meshes[i], t, ref, cnt) && t < h.t && t > RT_EPSF) {
+                h.type = 3; h.obj = i; h.t = t; h.ref = ref;
+            }
+        }
+    }
+    return h;
+}
+
+// ---- scene: occlusion --------------------------------------------------------------------------
+// Scene::computeShadow: every candidate blocker with EPSILON <= t < tLight draws one
+// random_float(); it blocks if the draw exceeds its transparency. For a mesh the candidate is the
+// mesh's CLOSEST hit (t >= 0), so a hit below EPSILON hides farther triangles.
+template <bool STATS>
+RT_HD bool shadow_hit(const DScene &s, const Ray &ray, float t_light, Rng &rng, Counters *cnt) {
+    if (STATS) cnt->shadow++;
+    for (int i = 0; i < s.n_spheres; ++i) {
+        if (STATS) cnt->sphere++;
+        const float4 b = RT_LDG(s.sph_b + i);
+        const float t = sphere_t(ray, RT_LDG(s.sph_a + i), b);
+        if (t < t_light && t > RT_EPSF) {
+            if (STATS) cnt->rnd++;
+            if (rng.next() > b.w) return true;
+        }
+    }
+    for (int i = 0; i < s.n_squares; ++i) {
+        if (STATS) cnt->square++;
+        float u, v;
+        const float t = square_t(ray, s.squares[i], u, v);
+        if (t < t_light && t > RT_EPSF) {
+            if (STATS) cnt->rnd++;
+            if (rng.next() > RT_LDG(s.sq_transparency + i)) return true;
+        }
+    }
+    if (s.n_meshes > 0) {
+        const RayInv inv = make_inv(ray);
+        for (int i = 0; i < s.n_meshes; ++i) {
+            if (STATS) cnt->mesh++;
+            float t; uint32_t ref;
+            if (mesh_closest<STATS>(ray, inv, s.meshes[i], t, ref, cnt) && t < t_light && t > RT_EPSF) {
+                if (STATS) cnt->rnd++;
+                if (rng.next() > RT_LDG(s.mesh_transparency + i)) return true;
+            }
+        }
+    }
+    return false;
+}
+
+// ---- textures ----------------------------------------------------------------------------------
+RT_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// texel address of Material::texture / get_normal (Material.cpp:82-86,119-123): fmod wrap in fp64,
+// v flipped, truncation to int — nearest texel, no filtering. The index is clamped to the image
+// (the reference would read out of bounds for negative u; squares and spheres never produce one).
+RT_HD int texel_index(const DImage &im, float u, float v, float sx, float sy) {
+    u = (float)fmod((double)(u * sx), 1.);
+    v = (float)(1 - fmod((double)(v * sy), 1.));
+    const int x = (int)(u * (im.w - 1));
+    const int y = (int)(v * (im.h - 1));
+    return clampi(y * im.w + x, 0, im.w * im.h - 1);
+}
+
+// Material::texture (Material.cpp:63-92). `color` is left untouched for Texture_None.
+template <bool STATS>
+RT_HD void material_texture(const DScene &s, const DMaterial &m, V3 &color, float u, float v, Counters *cnt) {
+    if (m.texture_type == 1) {
+        color = ((int)(u * m.tsx) % 2 == (int)(v * m.tsy) % 2) ? ld3(m.checker1) : ld3(m.checker2);
+    } else if (m.texture_type == 2) {
+        DImage im; im.w = 0; im.h = 0; im.rgb = nullptr;
+        if (m.image >= 0) im = s.textures[m.image];
+        if (im.w < 1 || im.h < 1) {   // Material.cpp:74-80: magenta/black 8x8 fallback
+            color = ((int)(u * 8.) % 2 == (int)(v * 8.) % 2) ? v3(0.f) : v3(1.f, 0.f, 1.f);
+            return;
+        }
+        if (STATS) cnt->tex++;
+        const unsigned char *p = im.rgb + 3 * (size_t)texel_index(im, u, v, m.tsx, m.tsy);
+        color = v3((float)(p[0] / 255.), (float)(p[1] / 255.), (float)(p[2] / 255.));
+    }
+}
+
+// Material::emit (Material.cpp:13-24)
+template <bool STATS>
+RT_HD V3 material_emit(const DScene &s, const DMaterial &m, float u, float v, Counters *cnt) {
+    if (!m.emissive) return v3(0.f);
+    V3 c = v3(0.f);
+    if (m.texture_type == 0) c = ld3(m.light_color);
+    else material_texture<STATS>(s, m, c, u, v, cnt);
+    return c * m.light_intensity;
+}
+
+// Material::get_normal (Material.cpp:114-130): tangent-space map, T/B = the square's stale
+// m_right_vector / m_up_vector members.
+template <bool STATS>
+RT_HD V3 material_normal(const DScene &s, const DMaterial &m, V3 n, float u, float v, V3 T, V3 B, Counters *cnt) {
+    if (m.normal_map < 0) return n;
+    const DImage im = s.normal_maps[m.normal_map];
+    if (im.w < 1 || im.h < 1) return n;   // reference would dereference an empty image; defined as "no map"
+    if (STATS) cnt->tex++;
+    const unsigned char *p = im.rgb + 3 * (size_t)texel_index(im, u, v, m.tsx, m.tsy);
+    const float a = (float)(p[0] / 127.5 - 1.), b = (float)(p[1] / 127.5 - 1.), c = (float)(p[2] / 127.5 - 1.);
+    return normalized(a * T + b * B + c * n);
+}
+
+// Scene::skyboxTexture (Scene.h:149-161)
+template <bool STATS>
+RT_HD V3 sky_color(const DScene &s, V3 d, int n_remaining, Counters *cnt) {
+    if (s.sky.w < 1 || s.sky.h < 1) {
+        if (s.dark_sky) return v3(0.f);
+        const float a = (float)(0.5 * ((double)d.y + 1.0));
+        // (1-a)*white + a*blue*(N+1): only the second term is scaled (operator precedence)
+        return (float)(1.0 - (double)a) * v3(1.f, 1.f, 1.f) + (a * v3(0.5f, 0.7f, 1.0f)) * (float)(n_remaining + 1);
+    }
+    if (STATS) cnt->tex++;
+    // atan2f / asinf, correctly rounded (fp64 function rounded once) — see oracle/libm_pin.cpp
+    const float at = (float)atan2((double)d.z, (double)d.x);
+    const float as = (float)asin((double)d.y);
+    const float u = (float)(0.5 + (double)at / (2 * RT_PI));
+    const float v = (float)(0.5 - (double)as / RT_PI);
+    const int x = (int)(u * s.sky.w);
+    const int y = (int)(v * s.sky.h);
+    // the reference does not clamp (u == 1 or v == 1 read past the row / the image)
+    const int idx = clampi(y * s.sky.w + x, 0, s.sky.w * s.sky.h - 1);
+    const unsigned char *p = s.sky.rgb + 3 * (size_t)idx;
+    return v3((float)(p[0] / 255.), (float)(p[1] / 255.), (float)(p[2] / 255.)) * (float)n_remaining;
+}
+
+// ---- scattering --------------------------------------------------------------------------------
+RT_HD V3 reflect_dir(V3 d, V3 n) { return d - (2.f * dot(d, n)) * n; }            // Functions.cpp:38-40
+RT_HD V3 refract_dir(V3 d, V3 n, float eta) {                                      // Functions.cpp:42-47
+    const float cos_theta = fminr(dot(d, n), 1.0f);
+    const V3 perp = eta * (d + cos_theta * n);
+    const V3 par = (float)(-sqrt(fabs(1.0 - (double)dot(perp, perp)))) * n;
+    return perp + par;
+}
+RT_HD float schlick(float cosine, float ref_idx) {                                 // Functions.cpp:49-54
+    float r0 = (1.f - ref_idx) / (1.f + ref_idx);
+    r0 = r0 * r0;
+    return (float)((double)r0 + (double)(1.f - r0) * pow((double)(1.f - cosine), 5.0));
+}
+// Material::scatter (Material.cpp:26-60). Returns the new ray (origin P + EPSILON*dir).
+template <bool STATS>
+RT_HD Ray material_scatter(const DMaterial &m, const Ray &in, V3 n, V3 P, Rng &rng, Counters *cnt) {
+    V3 dir = v3(0.f);
+    if (m.type == 1) {          // glass (inverted convention and the -0.6 test are the reference's, A.1-8)
+        const float ri = dot(in.d, n) > 0.f ? (float)(1. / (double)m.index_medium) : m.index_medium;
+        const float cos_theta = fminr(dot(in.d * -1.f, n), 1.0f);
+        const float sin_theta = (float)sqrt(1. - (double)(cos_theta * cos_theta));
+        const bool cannot_refract = (double)(ri * sin_theta) - 0.6 > 1.0;
+        bool do_reflect = cannot_refract;
+        if (!do_reflect) {
+            if (STATS) cnt->rnd++;
+            do_reflect = schlick(cos_theta, ri) > rng.next();
+        }
+        dir = do_reflect ? reflect_dir(in.d, n) : refract_dir(in.d, n, ri);
+    } else if (m.type == 0) {   // diffuse: normal + normalised cube point
+        if (STATS) cnt->rnd += 3;
+        dir = n + random_unit_vector(rng);
+        if (length(dir) <= RT_EPSF) dir = n;
+    } else if (m.type == 2) {   // mirror
+        dir = reflect_dir(in.d, n);
+    }
+    dir = normalized(dir);
+    return make_ray(P + RT_EPSF * dir, dir, in.time);
+}
+
+// ---- one path ----------------------------------------------------------------------------------
+// Scene::rayTrace = rayTraceRecursive(ray, MAXBOUNCES) / MAXBOUNCES, unrolled into a loop. The
+// recursion returns (color_k + result_{k+1} (*) kd_k) + e_k; to reproduce its rounding the loop
+// records (color, kd, e) per depth and folds them back to front once the path ends.
+template <bool STATS>
+RT_HD V3 trace_path(const DScene &s, Ray ray, Rng &rng, int max_bounces, int nb_ech, Counters *cnt) {
+    V3 rec_c[RT_MAX_BOUNCES], rec_kd[RT_MAX_BOUNCES], rec_e[RT_MAX_BOUNCES];
+    int depth = 0;
+    V3 tail = v3(0.f);
+    for (int N = max_bounces; N > 0; --N) {
+        float hu = 0.f, hv = 0.f;
+        const Hit h = closest_hit<STATS>(s, ray, hu, hv, cnt);
+        if (h.type == 0) { tail = sky_color<STATS>(s, ray.d, N, cnt); break; }
+
+        V3 P, n, kd, e;
+        float transparency;
+        const DMaterial *mat;
+        if (h.type == 1) {
+            // Sphere.h:124-130 for the winning sphere only
+            mat = s.sph_mat + h.obj;
+            const float4 a = RT_LDG(s.sph_a + h.obj), b = RT_LDG(s.sph_b + h.obj);
+            const V3 c = v3(a.x, a.y, a.z) + ray.time * v3(b.x, b.y, b.z);
+            P = ray.o + h.t * ray.d;
+            n = normalized(P - c);
+            const float theta = (float)acos((double)n.y * -1.);
+            const float phi = (float)(atan2((double)n.z * -1., (double)n.x) + RT_PI);
+            kd = ld3(mat->kd);
+            const float tu = (float)((double)phi / (2 * RT_PI)), tv = (float)((double)theta / RT_PI);
+            if (mat->texture_type != 0) material_texture<STATS>(s, *mat, kd, tu, tv, cnt);   // sphere_texture
+            e = material_emit<STATS>(s, *mat, tu, tv, cnt);
+        } else if (h.type == 2) {
+            mat = s.sq_mat + h.obj;
+            const DSquare &q = s.squares[h.obj];
+            P = ray.o + h.t * ray.d;
+            n = ld3(q.n);
+            kd = ld3(mat->kd);
+            material_texture<STATS>(s, *mat, kd, hu, hv, cnt);
+            n = material_normal<STATS>(s, *mat, n, hu, hv, ld3(q.tan_r), ld3(q.tan_u), cnt);
+            e = material_emit<STATS>(s, *mat, hu, hv, cnt);
+        } else {
+            mat = s.mesh_mat + h.obj;
+            const DMesh &m = s.meshes[h.obj];
+            float w0, w1, w2;
+            triangle_t<false>(ray, m, h.ref, w0, w1, w2, nullptr);   // recompute the barycentrics of the winner
+            P = ray.o + h.t * ray.d;
+            const float4 pl = RT_LDG(m.tri_plane + h.ref);
+            n = v3(pl.x, pl.y, pl.z);                                // flat face normal (Triangle.h:119)
+            kd = ld3(mat->kd);
+            const uint32_t ti = f2u(RT_LDG(m.tri_den + h.ref).y);
+            if (m.color_type == 0) {
+                const uint32_t i0 = m.triangles[3 * ti], i1 = m.triangles[3 * ti + 1], i2 = m.triangles[3 * ti + 2];
+                kd = w0 * ld3(m.vert_colors + 3 * i0) + w1 * ld3(m.vert_colors + 3 * i1) + w2 * ld3(m.vert_colors + 3 * i2);
+            } else if (m.color_type == 1) {
+                kd = ld3(m.face_colors + 3 * ti);
+            }
+            e = v3(0.f);
+        }
+        transparency = mat->transparency;
+
+        // direct lighting with soft shadows (Scene.h:305-334)
+        V3 color = v3(0.f);
+        for (int i = 0; i < s.n_lights; ++i) {
+            const V3 lp = ld3(s.lights[i].pos);
+            const V3 L = normalized(lp - P);
+            const float dotLN = dot(L, n);
+            // lights[0].material for every light; (1 - transparency) in fp64 (Scene.h:311)
+            color = color + (comp_product(ld3(s.lights[0].color), kd) * fmaxr(0.0f, dotLN)) * (float)(1. - (double)transparency);
+            int blocked = 0;
+            const float delta = s.lights[i].radius / 2.f;
+            for (int j = 0; j < nb_ech; ++j) {
+                if (STATS) cnt->rnd += 3;
+                const V3 lj = lp + random_unit_vector(rng) * delta;
+                const V3 Lj = normalized(lj - P);
+                const float t_light = length(lj - P);
+                const Ray sh = make_ray(P + Lj * RT_EPSF, Lj, ray.time);
+                if (shadow_hit<STATS>(s, sh, t_light, rng, cnt)) ++blocked;
+            }
+            const float shadow = (float)(1. - (double)((float)blocked / (float)nb_ech));
+            color = color * shadow;   // scales the light accumulated so far, earlier lights included
+        }
+
+        ray = material_scatter<STATS>(*mat, ray, n, P, rng, cnt);
+        rec_c[depth] = color; rec_kd[depth] = kd; rec_e[depth] = e;
+        ++depth;
+    }
+    V3 r = tail;
+    for (int k = depth - 1; k >= 0; --k) r = (rec_c[k] + comp_product(r, rec_kd[k])) + rec_e[k];
+    r = v3(0.f) + r;
+    return r / (float)max_bounces;
+}
+
+// ---- camera ------------------------------------------------------------------------------------
+// MatrixUtilities::screen_space_to_world_space_ray (matrixUtilities.h:53-74): unprojection in fp64
+// (sums left to right), dehomogenised in fp64, cast to float; direction normalised there and
+// again by the Ray constructor. cam_pos is cameraSpaceToWorldSpace(0,0,0), constant per frame.
+struct DCamera { double mvi[16], pi[16], depth_near; float pos[3]; };
+RT_HD void mat4_mul(const double *m, double x, double y, double z, double w, double *r) {
+    r[0] = m[0] * x + m[4] * y + m[8] * z + m[12] * w;
+    r[1] = m[1] * x + m[5] * y + m[9] * z + m[13] * w;
+    r[2] = m[2] * x + m[6] * y + m[10] * z + m[14] * w;
+    r[3] = m[3] * x + m[7] * y + m[11] * z + m[15] * w;
+}
+RT_HD Ray camera_ray(const DCamera &c, float u, float v, float time) {
+    double a[4], b[4];
+    mat4_mul(c.pi, 2.0 * (double)u - 1.0, -(2.0 * (double)v - 1.0), c.depth_near, 1.0, a);
+    mat4_mul(c.mvi, a[0], a[1], a[2], a[3], b);
+    const V3 p = v3((float)(b[0] / b[3]), (float)(b[1] / b[3]), (float)(b[2] / b[3]));
+    const V3 pos = ld3(c.pos);
+    const V3 dir = normalized(p - pos);
+    return make_ray(pos, dir, time);
+}
+// trace_line's per-sample prologue (main.cpp:189-192): u, v, time are draws 0, 1, 2
+RT_HD Ray primary_ray(const DCamera &c, int x, int y, int w, int h, Rng &rng) {
+    const float u = ((float)x + rng.next()) / (float)w;
+    const float v = ((float)y + rng.next()) / (float)h;
+    const float time = rng.next();
+    return camera_ray(c, u, v, time);
+}
+
+// gamma_correct (Functions.cpp:56-60)
+RT_HD float gamma_channel(float c) { return (float)pow((double)c, 1.0 / 2.2); }
+
+}  // namespace rt
+#endif

@@ -1,0 +1,68 @@
+// Host API — the headless replacement of ray_trace_from_camera() (main.cpp:200-263).
+//
+// Reference flow:  w,h from GLUT -> camera.apply() -> matrixUtilities.updated()/updateMatrices()
+//                  -> one std::thread per scanline running trace_line() -> "Done in" print
+//                  -> P3 ./rendu.ppm
+// This flow:       w,h from the caller -> camera.apply() -> MatrixUtilities::updateMatrices(camera)
+//                  -> Scene::flatten() -> rt_scene_create() (cached in DeviceScene)
+//                  -> rt_render() on the GPU -> same P3 writer.
+// There is no CPU path: if the CUDA library reports an error, RenderError is thrown.
+#ifndef HAI719_HOST_RENDERER_H
+#define HAI719_HOST_RENDERER_H
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "Camera.h"
+#include "Scene.h"
+#include "hai719_rt.h"
+#include "matrixUtilities.h"
+
+namespace hai719 {
+
+struct RenderError : std::runtime_error {
+    int status;
+    RenderError(int status, const std::string &what) : std::runtime_error(what), status(status) {}
+};
+
+struct RenderOptions {
+    int max_bounces = MAXBOUNCES;
+    int nb_ech = NB_ECH;
+    uint32_t seed = 0;
+    int device = 0;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;     // pixel rectangle, all 0 = full image
+    int rank = 0, n_ranks = 1;              // tile sharding (see RtRenderParams)
+    int tile_w = 0, tile_h = 0;
+    bool collect_stats = false;
+    int variant = 0;
+    std::string ppm_path = "./rendu.ppm";   // "" = do not write (the reference always writes)
+    bool verbose = true;                    // the reference's two std::cout lines
+};
+
+// A scene uploaded to one device. Re-create after changing the Scene.
+class DeviceScene {
+public:
+    DeviceScene(const Scene &scene, int device = 0);
+    ~DeviceScene();
+    DeviceScene(const DeviceScene &) = delete;
+    DeviceScene &operator=(const DeviceScene &) = delete;
+    RtScene *handle() const { return handle_; }
+    int device() const { return device_; }
+private:
+    RtScene *handle_ = nullptr;
+    int device_ = 0;
+};
+
+RtRenderParams make_params(int w, int h, unsigned int nsamples, const RenderOptions &opt);
+
+// Render `image` (w*h gamma-corrected Vec3, row 0 = top, like main.cpp:202) from the camera.
+void ray_trace_from_camera(const DeviceScene &scene, Camera &camera, int w, int h, unsigned int nsamples,
+                           std::vector<Vec3> &image, const RenderOptions &opt = RenderOptions(), RtStats *stats = nullptr);
+// Convenience: uploads the scene, renders, frees.
+void ray_trace_from_camera(const Scene &scene, Camera &camera, int w, int h, unsigned int nsamples,
+                           std::vector<Vec3> &image, const RenderOptions &opt = RenderOptions(), RtStats *stats = nullptr);
+
+// main.cpp:252-262 — "P3\n w h\n255\n" then (int)(255.f*min(1.f,c)) per channel, space separated.
+bool write_ppm_p3(const std::string &filename, int w, int h, const std::vector<Vec3> &image);
+
+}  // namespace hai719
+#endif

@@ -1,0 +1,137 @@
+// C wrappers over the C++ host API (declared in include/hai719_host.h).
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include "Camera.h"
+#include "Renderer.h"
+#include "Scene.h"
+#include "errors.h"
+#include "hai719_host.h"
+#include "matrixUtilities.h"
+
+struct HaiScene {
+    Scene scene;
+    FlatScene flat;
+    bool flat_valid = false;
+    std::map<int, std::unique_ptr<hai719::DeviceScene>> on_device;
+    void touch() { flat_valid = false; on_device.clear(); }
+};
+
+namespace {
+thread_local std::string g_err;
+template <class F> int guarded(F &&f) {
+    try {
+        hai719::set_fatal_throws(true);
+        f();
+        return 0;
+    } catch (const hai719::RenderError &e) {
+        g_err = e.what();
+        return e.status;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char *hai_last_error(void) { return g_err.c_str(); }
+
+HaiScene *hai_scene_new(const char *asset_root) {
+    HaiScene *s = new HaiScene;
+    if (asset_root) s->scene.asset_root = asset_root;
+    return s;
+}
+void hai_scene_free(HaiScene *s) { delete s; }
+
+int hai_scene_setup(HaiScene *s, int scene_id, float ar, uint32_t seed) {
+    return guarded([&] {
+        s->touch();
+        seed_scene_random(seed);
+        if (!s->scene.setup_by_id(scene_id, ar)) throw std::runtime_error("unknown scene id " + std::to_string(scene_id));
+    });
+}
+
+size_t hai_scene_dump(HaiScene *s, uint32_t *out, size_t cap) {
+    std::vector<uint32_t> w;
+    s->scene.dump(w);
+    if (out) std::memcpy(out, w.data(), std::min(cap, w.size()) * 4);
+    return w.size();
+}
+
+const RtSceneDesc *hai_scene_flatten(HaiScene *s) {
+    const int rc = guarded([&] {
+        if (!s->flat_valid) { s->scene.flatten(s->flat); s->flat_valid = true; }
+    });
+    return rc == 0 ? &s->flat.desc : nullptr;
+}
+
+int hai_scene_kd_stats(HaiScene *s, int mesh, uint64_t *o) {
+    if (mesh < 0 || (size_t)mesh >= s->scene.meshes.size() || !s->scene.meshes[mesh].kdtree) { g_err = "no such KD-tree"; return -1; }
+    const KDTree::Stats st = s->scene.meshes[mesh].kdtree->stats();
+    o[0] = st.nodes; o[1] = st.leaves; o[2] = st.empty_leaves; o[3] = st.refs; o[4] = st.max_leaf; o[5] = st.max_depth;
+    return 0;
+}
+
+int hai_scene_counts(HaiScene *s, uint32_t *o) {
+    const Scene &c = s->scene;
+    o[0] = (uint32_t)c.spheres.size(); o[1] = (uint32_t)c.squares.size(); o[2] = (uint32_t)c.meshes.size();
+    o[3] = (uint32_t)c.lights.size(); o[4] = (uint32_t)c.textures.size(); o[5] = (uint32_t)c.normals.size();
+    o[6] = (uint32_t)std::max(0, c.skybox.w); o[7] = (uint32_t)std::max(0, c.skybox.h);
+    return 0;
+}
+
+int hai_default_camera(int w, int h, RtCamera *out) {
+    return guarded([&] {
+        Camera camera;
+        camera.resize(w, h);
+        camera.move(0., 0., -3.1);
+        camera.apply();
+        MatrixUtilities mu;
+        mu.updateMatrices(camera);
+        mu.fill(*out);
+    });
+}
+
+RtScene *hai_scene_device(HaiScene *s, int device) {
+    RtScene *h = nullptr;
+    guarded([&] {
+        auto it = s->on_device.find(device);
+        if (it == s->on_device.end())
+            it = s->on_device.emplace(device, std::unique_ptr<hai719::DeviceScene>(new hai719::DeviceScene(s->scene, device))).first;
+        h = it->second->handle();
+    });
+    return h;
+}
+
+int hai_render(HaiScene *s, int device, const RtCamera *cam, const RtRenderParams *params, float *gamma_rgb,
+               float *linear_rgb, RtStats *stats) {
+    RtScene *h = hai_scene_device(s, device);
+    if (!h) return -1;
+    const int rc = rt_render(h, cam, params, gamma_rgb, linear_rgb, stats);
+    if (rc != RT_OK) g_err = rt_last_error();
+    return rc;
+}
+
+int hai_ray_trace_from_camera(HaiScene *s, int device, int w, int h, int nsamples, uint32_t seed, const char *ppm_path,
+                              float *gamma_rgb) {
+    return guarded([&] {
+        RtScene *dev = hai_scene_device(s, device);
+        if (!dev) throw std::runtime_error(g_err);
+        Camera camera;
+        camera.resize(w, h);
+        camera.move(0., 0., -3.1);
+        hai719::RenderOptions opt;
+        opt.seed = seed;
+        opt.device = device;
+        opt.ppm_path = ppm_path ? ppm_path : "";
+        opt.verbose = false;
+        std::vector<Vec3> image;
+        hai719::ray_trace_from_camera(*s->on_device[device], camera, w, h, (unsigned)nsamples, image, opt);
+        if (gamma_rgb) std::memcpy(gamma_rgb, image.data(), image.size() * sizeof(Vec3));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+#include "imageLoader.h"
+
+namespace ppmLoader {
+namespace {
+// skip line breaks, then at most one '#' comment line (imageLoader.cpp:10-18)
+void skip_comment(std::ifstream &f) {
+    int c;
+    while ((c = f.peek()) == '\n' || c == '\r') f.get();
+    if (c == '#') { std::string junk; std::getline(f, junk); }
+}
+bool fail(ImageRGB &img, const std::string &why) {
+    std::cout << why << std::endl;
+    img.w = img.h = 0;
+    img.data.clear();
+    return false;
+}
+}  // namespace
+
+bool load_ppm(ImageRGB &img, const std::string &name) {
+    std::ifstream f(name.c_str(), std::ios::binary);
+    if (f.fail()) return fail(img, "Could not open file: " + name);
+    std::string magic;
+    int bits = 0;
+    skip_comment(f); f >> magic;
+    skip_comment(f); f >> img.w;
+    skip_comment(f); f >> img.h;
+    skip_comment(f); f >> bits;
+    const bool p3 = magic == "P3", p6 = magic == "P6";
+    if (!p3 && !p6) return fail(img, "Unsupported magic number");
+    if (img.w < 1) return fail(img, "Unsupported width: " + std::to_string(img.w));
+    if (img.h < 1) return fail(img, "Unsupported height: " + std::to_string(img.h));
+    if (bits < 1 || bits > 255) return fail(img, "Unsupported number of bits: " + std::to_string(bits));
+    img.data.assign((size_t)img.w * (size_t)img.h, RGB{0, 0, 0});
+    if (p6) {
+        f.get();  // the single whitespace byte after maxval
+        f.read((char *)img.data.data(), (std::streamsize)(img.data.size() * 3));
+    } else {
+        for (RGB &px : img.data) {
+            int v;
+            f >> v; px.r = (unsigned char)v;
+            f >> v; px.g = (unsigned char)v;
+            f >> v; px.b = (unsigned char)v;
+        }
+    }
+    return true;
+}
+}  // namespace ppmLoader

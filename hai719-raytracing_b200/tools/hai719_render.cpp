@@ -1,0 +1,50 @@
+// hai719_render — the headless stand-in for "press r" in the reference's GLUT shell
+// (main.cpp:321-326 -> ray_trace_from_camera). Builds one of the reference's scenes with the host
+// API, renders it on the GPU and writes the same P3 rendu.ppm.
+//   hai719_render [--scene N] [--w W --h H] [--spp S] [--seed K] [--assets DIR] [--out FILE] [--device D]
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include "Camera.h"
+#include "Constants.h"
+#include "Renderer.h"
+#include "Scene.h"
+
+int main(int argc, char **argv) {
+    int scene_id = DEFAULT_SELECTED_SCENE, w = 850, h = 480, spp = DEFAULT_NSAMPLES, device = 0;
+    unsigned int seed = 0;
+    std::string assets, out = "./rendu.ppm";
+    for (int i = 1; i + 1 < argc; i += 2) {
+        const std::string k = argv[i];
+        const char *v = argv[i + 1];
+        if (k == "--scene") scene_id = std::atoi(v);
+        else if (k == "--w") w = std::atoi(v);
+        else if (k == "--h") h = std::atoi(v);
+        else if (k == "--spp") spp = std::atoi(v);
+        else if (k == "--seed") seed = (unsigned int)std::strtoul(v, nullptr, 10);
+        else if (k == "--assets") assets = v;
+        else if (k == "--out") out = v;
+        else if (k == "--device") device = std::atoi(v);
+        else { std::cerr << "unknown option " << k << std::endl; return 2; }
+    }
+    Scene scene;
+    scene.asset_root = assets;
+    seed_scene_random(seed);
+    if (!scene.setup_by_id(scene_id, float(w) / float(h))) { std::cerr << "unknown scene " << scene_id << std::endl; return 2; }
+    Camera camera;
+    camera.resize(w, h);
+    camera.move(0., 0., -3.1);   // main.cpp:418
+    hai719::RenderOptions opt;
+    opt.seed = seed;
+    opt.device = device;
+    opt.ppm_path = out;
+    std::vector<Vec3> image;
+    try {
+        hai719::ray_trace_from_camera(scene, camera, w, h, (unsigned int)spp, image, opt);
+    } catch (const std::exception &e) {
+        std::cerr << "render failed: " << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,53 @@
+/* hai719_host.h — C entry points of the C++ host API (hai719-raytracing_b200/host/), so that
+ * tests, bench.py and non-C++ callers can drive the same objects a C++ user of the drop-in would:
+ * build a Scene with the reference's setup_*() builders (Scene.h:358-1882) or the OFF/PPM
+ * loaders, get the default camera of main.cpp:418 (Camera() + move(0,0,-3.1)), flatten
+ * to the RtSceneDesc of hai719_rt.h, and render through ray_trace_from_camera()'s replacement.
+ *
+ * All functions return 0 on success, negative on error (hai_last_error() has the text), unless
+ * documented otherwise. Nothing here computes an image on the CPU.
+ */
+#ifndef HAI719_HOST_H
+#define HAI719_HOST_H
+#include <stddef.h>
+#include <stdint.h>
+#include "hai719_rt.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct HaiScene HaiScene;
+
+const char *hai_last_error(void);
+
+HaiScene *hai_scene_new(const char *asset_root);
+void hai_scene_free(HaiScene *s);
+/* scene_id: 0..10 = main.cpp:421-432 order, 11 = flamingo_lake, 100 = BASELINE config 5.
+ * seed feeds the scene-construction randomness (random spheres). */
+int hai_scene_setup(HaiScene *s, int scene_id, float aspect_ratio, uint32_t seed);
+/* canonical dump (same word layout as the oracle's ref_scene_dump); out == NULL returns the size */
+size_t hai_scene_dump(HaiScene *s, uint32_t *out, size_t cap_words);
+/* Flatten; the returned description stays valid until the scene is changed or freed. */
+const RtSceneDesc *hai_scene_flatten(HaiScene *s);
+/* per-mesh KD statistics: out6 = {nodes, leaves, empty_leaves, refs, max_leaf, max_depth} */
+int hai_scene_kd_stats(HaiScene *s, int mesh, uint64_t *out6);
+int hai_scene_counts(HaiScene *s, uint32_t *out8); /* spheres, squares, meshes, lights, textures, normals, sky_w, sky_h */
+
+/* Camera() ; resize(w,h) ; move(0,0,-3.1) ; apply() ; MatrixUtilities::updateMatrices() */
+int hai_default_camera(int w, int h, RtCamera *out);
+
+/* Upload (cached per scene+device until the scene changes) and render; host output buffers as
+ * in rt_render(). This is the call a user of the drop-in makes: the e2e number in bench.py. */
+int hai_render(HaiScene *s, int device, const RtCamera *cam, const RtRenderParams *params, float *gamma_rgb,
+               float *linear_rgb, RtStats *stats);
+/* The device-resident scene handle (uploading if needed), for rt_render_device() etc. */
+RtScene *hai_scene_device(HaiScene *s, int device);
+
+/* ray_trace_from_camera() end to end, including the P3 file (main.cpp:252-262); ppm_path may be NULL */
+int hai_ray_trace_from_camera(HaiScene *s, int device, int w, int h, int nsamples, uint32_t seed, const char *ppm_path,
+                              float *gamma_rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,248 @@
+/* hai719_rt.h — C ABI of the B200 (sm_100a) render path.
+ *
+ * The reference (Kuuro-neko/HAI719-Raytracing) has no plugin/FFI boundary: its render is the body
+ * of ray_trace_from_camera() (main.cpp:200-263), reachable only from a GLUT key handler. This
+ * header is the boundary that body is replaced behind. Inputs are what that function reads —
+ * the selected Scene (Scene.h:57-65), the camera's inverse matrices (matrixUtilities.h:15-19),
+ * w, h, nsamples (main.cpp:64,201) and the compile-time knobs of Constants.h:10-12 made runtime —
+ * and the output is what it produces: `image`, w*h gamma-corrected float RGB (main.cpp:202,193-196).
+ *
+ * Plain C: POD structs, pointers and sizes; no C++/torch types. The host-side C++ API
+ * (hai719-raytracing_b200/host/, same class names as the reference) fills RtSceneDesc with
+ * flatten(); any other host language can do the same through its FFI.
+ *
+ * All functions return 0 on success or a negative RtStatus; rt_last_error() gives the text for
+ * the calling thread. There is NO CPU fallback: without a CUDA device every entry point that
+ * needs one fails with RT_ERR_NO_DEVICE.
+ */
+#ifndef HAI719_RT_H
+#define HAI719_RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HAI719_RT_ABI_VERSION 1
+
+typedef enum RtStatus {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,    /* bad argument / inconsistent description */
+    RT_ERR_NO_DEVICE = -2,  /* no CUDA device, or not an sm_100 part */
+    RT_ERR_CUDA = -3,       /* a CUDA runtime call failed (text in rt_last_error) */
+    RT_ERR_OOM = -4
+} RtStatus;
+
+/* ---- scene description (host memory, read during rt_scene_create only) ------------------- */
+
+/* Material.h:10-20 */
+enum { RT_MAT_DIFFUSE = 0, RT_MAT_GLASS = 1, RT_MAT_MIRROR = 2 };
+enum { RT_TEX_NONE = 0, RT_TEX_CHECKER = 1, RT_TEX_IMAGE = 2 };
+/* Mesh.h:72-76 */
+enum { RT_COLOR_VERTEX = 0, RT_COLOR_FACE = 1, RT_COLOR_NONE = 2 };
+
+/* The fields of `struct Material` (Material.h:22-58) that the tracer reads. Pointers to images
+ * become indices into RtSceneDesc.textures / .normal_maps (-1 = none). */
+typedef struct RtMaterial {
+    int32_t type;           /* RT_MAT_* */
+    int32_t texture_type;   /* RT_TEX_* */
+    float diffuse[3];
+    float transparency;
+    float index_medium;
+    float checker1[3];
+    float checker2[3];
+    float texture_scale_x, texture_scale_y;
+    int32_t emissive;
+    float light_color[3];
+    float light_intensity;
+    int32_t image;          /* index into textures, used when texture_type == RT_TEX_IMAGE */
+    int32_t normal_map;     /* index into normal_maps, or -1 (Material::has_normal_map) */
+    float motion[3];        /* motion_blur_translation */
+} RtMaterial;
+
+/* Sphere.h:41-47 */
+typedef struct RtSphere {
+    float center[3];
+    float radius;
+    RtMaterial material;
+} RtSphere;
+
+/* Square.h:20-63. v0,v1,v3 are the TRANSFORMED vertices[0,1,3].position that Square::intersect
+ * reads (Square.h:68-72); right/up are the m_right_vector / m_up_vector MEMBERS, which transforms
+ * never update and which only the normal-map tangent frame uses (Scene.h:284). */
+typedef struct RtSquare {
+    float v0[3], v1[3], v3[3];
+    float right[3], up[3];
+    RtMaterial material;
+} RtSquare;
+
+/* Scene.h:28-42 (pos, radius, material are the only fields the tracer reads) */
+typedef struct RtLight {
+    float pos[3];
+    float radius;
+    float color[3];
+} RtLight;
+
+/* ppmLoader::ImageRGB (imageLoader.h:17-26): 8-bit RGB, row-major, w*h*3 bytes. w < 1 or h < 1
+ * means "no image" (the reference's own test, Material.cpp:74, Scene.h:150). */
+typedef struct RtImage {
+    int32_t w, h;
+    const uint8_t *rgb;
+} RtImage;
+
+/* One node of the host-built KD-tree (KDTree.cpp:6-29), flattened in PRE-ORDER (node, left
+ * subtree, right subtree — the reference's visiting order, KDTree.cpp:49-61). Null children
+ * are simply absent. `skip` is the index of the first node after this node's subtree, so the
+ * device walks the array front to back with no stack: box missed -> jump to skip, else next.
+ * Leaves (KDTree::Node::leaf()) carry a range of RtSceneMesh.leaf_refs, in build order. */
+typedef struct RtKdNode {
+    float bmin[3];
+    uint32_t skip;          /* inner: first index after the subtree; leaf: own index + 1 */
+    float bmax[3];
+    uint32_t first_ref;     /* leaf: first leaf ref; inner: 0 */
+    uint32_t n_refs;        /* leaf: number of refs (may be 0) */
+    uint32_t is_leaf;
+} RtKdNode;
+
+/* One triangle reference of a leaf: MeshTriangle::v[0..3] (Mesh.h:48-68); v[3] is the index of
+ * the triangle in the mesh (Mesh.cpp:71-73), which shading uses (Scene.h:292-297). */
+typedef struct RtTriRef {
+    uint32_t v[3];
+    uint32_t tri_index;
+} RtTriRef;
+
+typedef struct RtSceneMesh {
+    uint32_t n_vertices, n_triangles;
+    const float *positions;      /* 3*n_vertices, as transformed by the scene builder        */
+    const uint32_t *triangles;   /* 3*n_triangles vertex indices                              */
+    int32_t color_type;          /* RT_COLOR_*                                                */
+    const float *vert_colors;    /* 3*n_vertices if RT_COLOR_VERTEX else NULL                 */
+    const float *face_colors;    /* 3*n_triangles if RT_COLOR_FACE else NULL                  */
+    float root_bmin[3], root_bmax[3]; /* KDTree::aabb (== Mesh::aabb), gate of KDTree::intersect */
+    uint32_t n_nodes;            /* 0 = empty tree (root == nullptr): never hit               */
+    const RtKdNode *nodes;
+    uint32_t n_leaf_refs;
+    const RtTriRef *leaf_refs;
+    RtMaterial material;
+} RtSceneMesh;
+
+typedef struct RtSceneDesc {
+    uint32_t abi_version;        /* HAI719_RT_ABI_VERSION */
+    uint32_t n_spheres;  const RtSphere *spheres;
+    uint32_t n_squares;  const RtSquare *squares;
+    uint32_t n_meshes;   const RtSceneMesh *meshes;
+    uint32_t n_lights;   const RtLight *lights;
+    uint32_t n_textures; const RtImage *textures;
+    uint32_t n_normal_maps; const RtImage *normal_maps;
+    RtImage skybox;
+    int32_t dark_sky;
+} RtSceneDesc;
+
+/* ---- camera and render parameters ---------------------------------------------------------- */
+
+/* MatrixUtilities::modelviewInverse / projectionInverse / nearAndFarPlanes[0]
+ * (matrixUtilities.h:15-19), column-major doubles exactly as gluInvertMatrix leaves them. */
+typedef struct RtCamera {
+    double modelview_inverse[16];
+    double projection_inverse[16];
+    double depth_near;           /* GL_DEPTH_RANGE[0], 0.0 by default */
+} RtCamera;
+
+typedef struct RtRenderParams {
+    int32_t width, height;       /* full image, as glutGet(GLUT_WINDOW_WIDTH/HEIGHT), main.cpp:201 */
+    int32_t spp;                 /* nsamples (main.cpp:64; DEFAULT_NSAMPLES 20)                      */
+    int32_t max_bounces;         /* MAXBOUNCES (Constants.h:11), 6                                   */
+    int32_t nb_ech;              /* NB_ECH shadow samples per light (Constants.h:12), 10             */
+    uint32_t seed;               /* deterministic stream, see "Random numbers" below                 */
+    int32_t x0, y0, x1, y1;      /* pixel rectangle to render; all 0 = whole image                   */
+    /* tile sharding: the rectangle is cut into tile_w x tile_h tiles, numbered row-major; this
+     * call renders the tiles t with t % n_ranks == rank. n_ranks <= 1 renders everything.         */
+    int32_t rank, n_ranks;
+    int32_t tile_w, tile_h;      /* 0 = default 32 x 32                                              */
+    int32_t collect_stats;       /* fill the work counters of RtStats (slower)                       */
+    int32_t variant;             /* 0 = default kernel path; see DESIGN.md for the others            */
+} RtRenderParams;
+
+typedef struct RtStats {
+    uint64_t n_samples;          /* rayTrace() calls = pixels * spp                                  */
+    uint64_t n_closest_rays;     /* computeIntersection() calls                                      */
+    uint64_t n_shadow_rays;      /* computeShadow() calls                                            */
+    uint64_t n_sphere_tests, n_square_tests, n_mesh_tests;
+    uint64_t n_node_visits;      /* KD nodes whose box was tested                                    */
+    uint64_t n_tri_tests;        /* triangle tests (culled + full)                                   */
+    uint64_t n_tri_full;         /* triangle tests that passed the facing + t >= 0 checks            */
+    uint64_t n_tex_fetches;
+    uint64_t n_random;           /* random_float() draws                                             */
+    double   kernel_ms;          /* device time of the trace kernels of this call (CUDA events)      */
+    uint32_t n_launches;         /* kernels launched by this call                                    */
+    uint32_t n_tiles;            /* tiles rendered by this rank                                      */
+} RtStats;
+
+/* Random numbers. The reference draws from a time-seeded mt19937 shared by all threads without a
+ * lock (Functions.cpp:4-8) plus a thread_local one for jitter (main.cpp:181), so its images are
+ * not reproducible. This implementation draws, in the reference's call order of random_float(),
+ * from a counter-based stream keyed per path:
+ *     fmix32(h): h^=h>>16; h*=0x85EBCA6B; h^=h>>13; h*=0xC2B2AE35; h^=h>>16
+ *     key  = fmix32( fmix32(seed ^ (pixel+1)*0x9E3779B9) + (sample+1)*0x85EBCA6B )
+ *     draw_i = (fmix32(key + i*0x9E3779B9) >> 8) * 2^-24
+ * pixel = x + y*width in full-image coordinates; draws 0,1,2 are the jitter u, v and the ray time
+ * (main.cpp:189-192); random_float() continues from 3. Results therefore do not depend on the
+ * rectangle, the tile size or the number of ranks. */
+
+typedef struct RtScene RtScene;  /* opaque, device-resident, bound to one device */
+
+int rt_abi_version(void);
+int rt_device_count(void);                       /* number of usable sm_100 devices, <= 0 if none */
+const char *rt_last_error(void);
+
+/* Copies everything it needs to `device`; the caller keeps ownership of the host arrays. */
+int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out);
+void rt_scene_destroy(RtScene *scene);
+size_t rt_scene_device_bytes(const RtScene *scene);
+
+/* Number of pixels this rank renders under `params` (rectangle + tile sharding), i.e. the
+ * element count / 3 of the packed output of rt_render_device(). */
+int64_t rt_render_pixel_count(const RtRenderParams *params);
+
+/* Drop-in for the render part of ray_trace_from_camera(): HOST output buffers.
+ * gamma_rgb  : rect_h*rect_w*3 floats, row-major, after gamma_correct (the reference's `image`).
+ * linear_rgb : same shape, the value before gamma (sum/nsamples); may be NULL.
+ * With n_ranks > 1 pixels of other ranks' tiles are left untouched. */
+int rt_render(RtScene *scene, const RtCamera *camera, const RtRenderParams *params,
+              float *gamma_rgb, float *linear_rgb, RtStats *stats);
+
+/* Same render with DEVICE output, asynchronous on `cuda_stream` (a cudaStream_t; NULL = default
+ * stream). d_gamma_rgb / d_linear_rgb (either may be NULL) receive this rank's pixels PACKED
+ * tile after tile (tiles in increasing tile index, each tile row-major, edge tiles clipped), the
+ * layout rt_untile_device() reads after a gather. stats->kernel_ms is valid only if
+ * stats->... was requested with collect_stats or after a stream synchronise. */
+int rt_render_device(RtScene *scene, const RtCamera *camera, const RtRenderParams *params,
+                     float *d_gamma_rgb, float *d_linear_rgb, void *cuda_stream, RtStats *stats);
+
+/* Scatter packed per-rank tile buffers (as gathered on one device: rank r's buffer starts at
+ * float offset 3*pixel_offsets[r]) into a row-major rect_h*rect_w*3 image. */
+int rt_untile_device(const RtRenderParams *params, const float *d_packed, const int64_t *pixel_offsets,
+                     float *d_image, int device, void *cuda_stream);
+
+/* Primary-hit identification of sample 0's camera ray of every pixel in the rectangle
+ * (Scene::computeIntersection, Scene.h:202-230). ids: 4 uint32 per pixel
+ * {type (0 miss, 1 sphere, 2 square, 3 mesh), objectIndex, tIndex (meshes), float bits of t}. */
+int rt_trace_primary(RtScene *scene, const RtCamera *camera, const RtRenderParams *params, uint32_t *ids);
+
+/* Scene::computeIntersection on caller-supplied rays (directions are normalised as the Ray
+ * constructor does, Line.h:13-16). ids as above; aux (8 floats per ray, may be NULL):
+ * sphere {theta, phi, n.xyz}, square {u, v, n.xyz}, mesh {w0, w1, w2, n.xyz}. */
+int rt_trace_rays(RtScene *scene, size_t n, const float *origins, const float *directions,
+                  const float *times, uint32_t *ids, float *aux);
+
+/* Scene::rayTrace (Scene.h:345-350) on caller-supplied rays; ray i draws from
+ * key(seed, pixel = i, sample = 0) starting at counter 3. rgb: 3 floats per ray. */
+int rt_shade_rays(RtScene *scene, size_t n, const float *origins, const float *directions,
+                  const float *times, const RtRenderParams *params, float *rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAI719_RT_H */

@@ -30,6 +30,10 @@
 #include <unistd.h>
 #include <vector>
 
+// NOTE on include order: <math.h> (libstdc++'s wrapper, which injects the float overloads of
+// cos/sin/... into the global namespace) must NOT be included before the reference headers:
+// Mesh::rotate_* (Mesh.h:198-224) call cos()/sin() unqualified and, in the reference's own
+// translation units, bind to the double versions.
 #include "Vec3.h"
 #include "Camera.h"
 #include "Scene.h"

@@ -116,10 +116,10 @@ class RtStats(C.Structure):
 # every symbol the two headers declare — tests check the libraries export exactly these
 RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy",
               "rt_scene_device_bytes", "rt_render_pixel_count", "rt_render", "rt_render_device", "rt_untile_device",
-              "rt_trace_primary", "rt_trace_rays", "rt_shade_rays"]
+              "rt_trace_primary", "rt_trace_rays", "rt_shade_rays", "rt_measure_fp32_peak"]
 HOST_SYMBOLS = ["hai_last_error", "hai_scene_new", "hai_scene_free", "hai_scene_setup", "hai_scene_dump",
                 "hai_scene_flatten", "hai_scene_kd_stats", "hai_scene_counts", "hai_default_camera", "hai_render",
-                "hai_scene_device", "hai_ray_trace_from_camera"]
+                "hai_scene_device", "hai_scene_invalidate_device", "hai_ray_trace_from_camera"]
 
 if not (os.path.exists(LIB_RT) and os.path.exists(LIB_HOST)):
     raise ImportError("hai719-raytracing_b200: native libraries not built (%s). Run `make -C %s` or "
@@ -145,6 +145,8 @@ rt.rt_trace_rays.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c
 rt.rt_shade_rays.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RtRenderParams),
                              C.c_void_p]
 
+rt.rt_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+
 host.hai_last_error.restype = C.c_char_p
 host.hai_scene_new.restype = C.c_void_p
 host.hai_scene_new.argtypes = [C.c_char_p]
@@ -161,6 +163,7 @@ host.hai_render.argtypes = [C.c_void_p, C.c_int, C.POINTER(RtCamera), C.POINTER(
                             C.c_void_p, C.POINTER(RtStats)]
 host.hai_scene_device.restype = C.c_void_p
 host.hai_scene_device.argtypes = [C.c_void_p, C.c_int]
+host.hai_scene_invalidate_device.argtypes = [C.c_void_p]
 host.hai_ray_trace_from_camera.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
                                            C.c_void_p]
 
@@ -178,6 +181,13 @@ def _host_check(rc):
 def device_count():
     """Number of sm_100 devices the CUDA library can use (0 on a CPU-only box)."""
     return int(rt.rt_device_count())
+
+
+def measure_fp32_peak(device=0):
+    """(unfused FMUL+FADD, fused FFMA) Tflop/s measured on `device`."""
+    a, b = C.c_double(0), C.c_double(0)
+    _rt_check(rt.rt_measure_fp32_peak(device, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def render_params(width, height, spp, max_bounces=6, nb_ech=10, seed=0, crop=None, rank=0, n_ranks=1, tile=(0, 0),
@@ -243,6 +253,12 @@ class Scene:
         if not d:
             raise RtError(-1, host.hai_last_error().decode(errors="replace"))
         return d
+
+    def invalidate_device(self):
+        host.hai_scene_invalidate_device(self.h)
+
+    def device_bytes(self, device=0):
+        return int(rt.rt_scene_device_bytes(self.device_handle(device)))
 
     def device_handle(self, device=0):
         h = host.hai_scene_device(self.h, device)

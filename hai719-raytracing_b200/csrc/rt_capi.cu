@@ -244,6 +244,22 @@ __global__ void k_shade_rays(const DScene scene, size_t n, const float *org, con
     rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z;
 }
 
+// FP32 peak probes: 8 independent register chains per thread, 4096 iterations, no memory traffic.
+template <bool FUSED>
+__global__ void __launch_bounds__(256) k_fp32_peak(float *out, float a, float b, int iters) {
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+        if (FUSED) {
+            x0 = __fmaf_rn(x0, a, b); x1 = __fmaf_rn(x1, a, b); x2 = __fmaf_rn(x2, a, b); x3 = __fmaf_rn(x3, a, b);
+            x4 = __fmaf_rn(x4, a, b); x5 = __fmaf_rn(x5, a, b); x6 = __fmaf_rn(x6, a, b); x7 = __fmaf_rn(x7, a, b);
+        } else {
+            x0 = __fadd_rn(__fmul_rn(x0, a), b); x1 = __fadd_rn(__fmul_rn(x1, a), b); x2 = __fadd_rn(__fmul_rn(x2, a), b); x3 = __fadd_rn(__fmul_rn(x3, a), b);
+            x4 = __fadd_rn(__fmul_rn(x4, a), b); x5 = __fadd_rn(__fmul_rn(x5, a), b); x6 = __fadd_rn(__fmul_rn(x6, a), b); x7 = __fadd_rn(__fmul_rn(x7, a), b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------------
@@ -741,6 +757,37 @@ int rt_render(RtScene *s, const RtCamera *camera, const RtRenderParams *p, float
             }
         }
     }
+    return RT_OK;
+}
+
+int rt_measure_fp32_peak(int device, double *unfused, double *fused) {
+    int sm = 0;
+    int rc = select_device(device, &sm);
+    if (rc) return rc;
+    const int blocks = sm * 8, threads = 256, iters = 4096;
+    float *d = nullptr;
+    RT_CUDA(cudaMalloc((void **)&d, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best[2] = {0, 0};
+    for (int mode = 0; mode < 2; ++mode)
+        for (int rep = 0; rep < 6; ++rep) {
+            cudaEventRecord(e0);
+            if (mode) k_fp32_peak<true><<<blocks, threads>>>(d, 0.999f, 0.001f, iters);
+            else k_fp32_peak<false><<<blocks, threads>>>(d, 0.999f, 0.001f, iters);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            const double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+            if (rep > 0 && ms > 0.f) best[mode] = std::max(best[mode], flops / (ms * 1e-3) / 1e12);
+        }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaError_t e = cudaGetLastError();
+    cudaFree(d);
+    RT_CUDA(e);
+    if (unfused) *unfused = best[0];
+    if (fused) *fused = best[1];
     return RT_OK;
 }
 

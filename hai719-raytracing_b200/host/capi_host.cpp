@@ -106,6 +106,8 @@ RtScene *hai_scene_device(HaiScene *s, int device) {
     return h;
 }
 
+void hai_scene_invalidate_device(HaiScene *s) { s->on_device.clear(); }
+
 int hai_render(HaiScene *s, int device, const RtCamera *cam, const RtRenderParams *params, float *gamma_rgb,
                float *linear_rgb, RtStats *stats) {
     RtScene *h = hai_scene_device(s, device);

@@ -43,6 +43,10 @@ int hai_render(HaiScene *s, int device, const RtCamera *cam, const RtRenderParam
 /* The device-resident scene handle (uploading if needed), for rt_render_device() etc. */
 RtScene *hai_scene_device(HaiScene *s, int device);
 
+/* Drop the cached device copy, so the next hai_render()/hai_scene_device() uploads again (what a
+ * fresh ray_trace_from_camera(scene, ...) call does every time). */
+void hai_scene_invalidate_device(HaiScene *s);
+
 /* ray_trace_from_camera() end to end, including the P3 file (main.cpp:252-262); ppm_path may be NULL */
 int hai_ray_trace_from_camera(HaiScene *s, int device, int w, int h, int nsamples, uint32_t seed, const char *ppm_path,
                               float *gamma_rgb);

@@ -242,6 +242,12 @@ int rt_trace_rays(RtScene *scene, size_t n, const float *origins, const float *d
 int rt_shade_rays(RtScene *scene, size_t n, const float *origins, const float *directions,
                   const float *times, const RtRenderParams *params, float *rgb);
 
+/* Measurement helper (not on the render path): FP32 peak of `device` in Tflop/s, measured with
+ * register-resident dependent chains over all SMs. unfused = separate FMUL + FADD (what the parity
+ * build issues, -fmad=false); fused = FFMA counted as 2 flops. MEASURED_PEAKS.json has no FP32
+ * figure, so bench.py takes its roofline denominator from here. */
+int rt_measure_fp32_peak(int device, double *unfused_tflops, double *fused_tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,193 @@
+// TEST-ONLY DEBUG AID — csrc/rt_core.cuh compiled as plain C++ and run on the CPU.
+//
+// This is NOT a fallback and is never linked into, loaded by, or reachable from the product
+// libraries (hai719-raytracing_b200/lib/*.so). It exists because the development container has no
+// GPU: running the very same device functions on the host against the oracle catches logic errors
+// in rt_core.cuh before GPU time is spent. Only tests/test_hostsim.py builds and loads it.
+// It consumes the same RtSceneDesc the CUDA library does and mirrors rt_scene_create's
+// precomputation (k_precompute_squares / k_precompute_tris) and k_render_paths / k_resolve.
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include <atomic>
+
+#include "hai719_rt.h"
+#include "rt_core.cuh"
+
+using namespace rt;
+
+struct SimScene {
+    DScene d{};
+    std::vector<float4> sph_a, sph_b;
+    std::vector<DMaterial> sph_mat, sq_mat, mesh_mat;
+    std::vector<DSquare> squares;
+    std::vector<float> sq_tr, mesh_tr;
+    std::vector<DLight> lights;
+    std::vector<DImage> tex, nrm;
+    std::vector<DMesh> meshes;
+    std::vector<std::vector<float4>> lo, hi, plane, edge;
+    std::vector<std::vector<float2>> den;
+};
+
+static DMaterial to_dmat(const RtMaterial &m) {
+    DMaterial d{};
+    d.type = m.type; d.texture_type = m.texture_type;
+    for (int k = 0; k < 3; ++k) { d.kd[k] = m.diffuse[k]; d.checker1[k] = m.checker1[k]; d.checker2[k] = m.checker2[k]; d.light_color[k] = m.light_color[k]; d.motion[k] = m.motion[k]; }
+    d.transparency = m.transparency; d.index_medium = m.index_medium; d.tsx = m.texture_scale_x; d.tsy = m.texture_scale_y;
+    d.emissive = m.emissive; d.light_intensity = m.light_intensity; d.image = m.image; d.normal_map = m.normal_map;
+    return d;
+}
+static DImage to_dimg(const RtImage &im) {
+    DImage d; d.w = 0; d.h = 0; d.rgb = nullptr;
+    if (im.w >= 1 && im.h >= 1 && im.rgb) { d.w = im.w; d.h = im.h; d.rgb = im.rgb; }
+    return d;
+}
+
+extern "C" {
+
+void *sim_scene_create(const RtSceneDesc *desc) {
+    SimScene *s = new SimScene;
+    DScene &d = s->d;
+    d.n_spheres = desc->n_spheres; d.n_squares = desc->n_squares; d.n_meshes = desc->n_meshes; d.n_lights = desc->n_lights;
+    d.dark_sky = desc->dark_sky;
+    for (uint32_t i = 0; i < desc->n_textures; ++i) s->tex.push_back(to_dimg(desc->textures[i]));
+    for (uint32_t i = 0; i < desc->n_normal_maps; ++i) s->nrm.push_back(to_dimg(desc->normal_maps[i]));
+    d.textures = s->tex.data(); d.normal_maps = s->nrm.data(); d.sky = to_dimg(desc->skybox);
+    for (uint32_t i = 0; i < desc->n_spheres; ++i) {
+        const RtSphere &sp = desc->spheres[i];
+        s->sph_a.push_back(make_float4(sp.center[0], sp.center[1], sp.center[2], sp.radius));
+        s->sph_b.push_back(make_float4(sp.material.motion[0], sp.material.motion[1], sp.material.motion[2], sp.material.transparency));
+        s->sph_mat.push_back(to_dmat(sp.material));
+    }
+    d.sph_a = s->sph_a.data(); d.sph_b = s->sph_b.data(); d.sph_mat = s->sph_mat.data();
+    for (uint32_t i = 0; i < desc->n_squares; ++i) {
+        const RtSquare &q = desc->squares[i];
+        const V3 v0 = ld3(q.v0), right = ld3(q.v1) - v0, up = ld3(q.v3) - v0;
+        const V3 n = normalized(cross(right, up));
+        DSquare o;
+        o.v0[0] = v0.x; o.v0[1] = v0.y; o.v0[2] = v0.z; o.n[0] = n.x; o.n[1] = n.y; o.n[2] = n.z;
+        o.right[0] = right.x; o.right[1] = right.y; o.right[2] = right.z; o.up[0] = up.x; o.up[1] = up.y; o.up[2] = up.z;
+        o.len_r = length(right); o.len_u = length(up);
+        for (int k = 0; k < 3; ++k) { o.motion[k] = q.material.motion[k]; o.tan_r[k] = q.right[k]; o.tan_u[k] = q.up[k]; }
+        o.glass = q.material.type == RT_MAT_GLASS;
+        s->squares.push_back(o);
+        s->sq_mat.push_back(to_dmat(q.material));
+        s->sq_tr.push_back(q.material.transparency);
+    }
+    d.squares = s->squares.data(); d.sq_mat = s->sq_mat.data(); d.sq_transparency = s->sq_tr.data();
+    for (uint32_t i = 0; i < desc->n_lights; ++i) {
+        DLight l;
+        for (int k = 0; k < 3; ++k) { l.pos[k] = desc->lights[i].pos[k]; l.color[k] = desc->lights[i].color[k]; }
+        l.radius = desc->lights[i].radius;
+        s->lights.push_back(l);
+    }
+    d.lights = s->lights.data();
+    const uint32_t nm = desc->n_meshes;
+    s->lo.resize(nm); s->hi.resize(nm); s->plane.resize(nm); s->edge.resize(nm); s->den.resize(nm);
+    for (uint32_t i = 0; i < nm; ++i) {
+        const RtSceneMesh &src = desc->meshes[i];
+        DMesh o;
+        memset(&o, 0, sizeof o);
+        for (int k = 0; k < 3; ++k) { o.bmin[k] = src.root_bmin[k]; o.bmax[k] = src.root_bmax[k]; }
+        o.n_nodes = src.n_nodes; o.color_type = src.color_type;
+        for (uint32_t k = 0; k < src.n_nodes; ++k) {
+            const RtKdNode &n = src.nodes[k];
+            if (n.is_leaf) {
+                s->lo[i].push_back(make_float4(n.bmin[0], n.bmin[1], n.bmin[2], u2f(n.first_ref)));
+                s->hi[i].push_back(make_float4(n.bmax[0], n.bmax[1], n.bmax[2], u2f(0x80000000u | n.n_refs)));
+            } else {
+                s->lo[i].push_back(make_float4(n.bmin[0], n.bmin[1], n.bmin[2], u2f(n.skip)));
+                s->hi[i].push_back(make_float4(n.bmax[0], n.bmax[1], n.bmax[2], u2f(0u)));
+            }
+        }
+        for (uint32_t k = 0; k < src.n_leaf_refs; ++k) {
+            const RtTriRef &r = src.leaf_refs[k];
+            const TriConst c = precompute_triangle(ld3(src.positions + 3 * r.v[0]), ld3(src.positions + 3 * r.v[1]), ld3(src.positions + 3 * r.v[2]), r.tri_index);
+            s->plane[i].push_back(c.plane);
+            s->edge[i].push_back(c.c0); s->edge[i].push_back(c.e0); s->edge[i].push_back(c.e1);
+            s->den[i].push_back(c.den);
+        }
+        o.node_lo = s->lo[i].data(); o.node_hi = s->hi[i].data();
+        o.tri_plane = s->plane[i].data(); o.tri_edge = s->edge[i].data(); o.tri_den = s->den[i].data();
+        o.triangles = src.triangles; o.vert_colors = src.vert_colors; o.face_colors = src.face_colors;
+        s->meshes.push_back(o);
+        s->mesh_mat.push_back(to_dmat(src.material));
+        s->mesh_tr.push_back(src.material.transparency);
+    }
+    d.meshes = s->meshes.data(); d.mesh_mat = s->mesh_mat.data(); d.mesh_transparency = s->mesh_tr.data();
+    return s;
+}
+
+void sim_scene_destroy(void *h) { delete (SimScene *)h; }
+
+static DCamera make_cam(const RtCamera *c) {
+    DCamera d;
+    for (int i = 0; i < 16; ++i) { d.mvi[i] = c->modelview_inverse[i]; d.pi[i] = c->projection_inverse[i]; }
+    d.depth_near = c->depth_near;
+    const double *m = c->modelview_inverse;
+    double r[4];
+    for (int k = 0; k < 4; ++k) r[k] = m[k] * 0.0 + m[4 + k] * 0.0 + m[8 + k] * 0.0 + m[12 + k] * 1.0;
+    for (int k = 0; k < 3; ++k) d.pos[k] = (float)(r[k] / r[3]);
+    return d;
+}
+
+// row-major rectangle, no tiling; linear, gamma: rect_h*rect_w*3; ids: 4 per pixel (sample 0)
+void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float *linear, float *gamma, uint32_t *ids, int threads) {
+    const SimScene *s = (const SimScene *)h;
+    const DCamera cam = make_cam(camera);
+    const bool full = (p->x0 | p->y0 | p->x1 | p->y1) == 0;
+    const int x0 = full ? 0 : p->x0, y0 = full ? 0 : p->y0, x1 = full ? p->width : p->x1, y1 = full ? p->height : p->y1;
+    const int rw = x1 - x0, rh = y1 - y0;
+    if (threads < 1) threads = (int)std::thread::hardware_concurrency();
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int r = next.fetch_add(1);
+            if (r >= rh) break;
+            const int y = y0 + r;
+            for (int x = x0; x < x1; ++x) {
+                const size_t o = (size_t)r * rw + (x - x0);
+                V3 acc = v3(0.f);
+                for (int sm = 0; sm < p->spp; ++sm) {
+                    Rng rng;
+                    rng.init(p->seed, (uint32_t)x + (uint32_t)y * (uint32_t)p->width, (uint32_t)sm);
+                    const Ray ray = primary_ray(cam, x, y, p->width, p->height, rng);
+                    if (sm == 0 && ids) {
+                        float u, v;
+                        const Hit hit = closest_hit<false>(s->d, ray, u, v, nullptr);
+                        uint32_t *q = ids + 4 * o;
+                        q[0] = hit.type; q[1] = hit.type ? hit.obj : 0; q[2] = hit.type == 3 ? f2u(s->d.meshes[hit.obj].tri_den[hit.ref].y) : 0; q[3] = f2u(hit.t);
+                    }
+                    acc = acc + trace_path<false>(s->d, ray, rng, p->max_bounces, p->nb_ech, nullptr);
+                }
+                acc = acc / (float)(unsigned int)p->spp;
+                if (linear) { linear[3 * o] = acc.x; linear[3 * o + 1] = acc.y; linear[3 * o + 2] = acc.z; }
+                if (gamma) { gamma[3 * o] = gamma_channel(acc.x); gamma[3 * o + 1] = gamma_channel(acc.y); gamma[3 * o + 2] = gamma_channel(acc.z); }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(work);
+    for (auto &t : pool) t.join();
+}
+
+void sim_stats(void *h, const RtCamera *camera, const RtRenderParams *p, unsigned long long *out10) {
+    const SimScene *s = (const SimScene *)h;
+    const DCamera cam = make_cam(camera);
+    Counters c;
+    memset(&c, 0, sizeof c);
+    for (int y = 0; y < p->height; ++y)
+        for (int x = 0; x < p->width; ++x)
+            for (int sm = 0; sm < p->spp; ++sm) {
+                Rng rng;
+                rng.init(p->seed, (uint32_t)x + (uint32_t)y * (uint32_t)p->width, (uint32_t)sm);
+                c.rnd += 3;
+                const Ray ray = primary_ray(cam, x, y, p->width, p->height, rng);
+                trace_path<true>(s->d, ray, rng, p->max_bounces, p->nb_ech, &c);
+            }
+    const unsigned long long v[10] = {c.closest, c.shadow, c.sphere, c.square, c.mesh, c.node, c.tri, c.tri_full, c.tex, c.rnd};
+    memcpy(out10, v, sizeof v);
+}
+
+}  // extern "C"

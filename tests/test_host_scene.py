@@ -1,0 +1,164 @@
+"""Host API (GL-free C++ Scene/Camera/Mesh/KDTree/loaders + flatten) against the reference. CPU only.
+
+The strongest check is the canonical dump: every float of every vertex, KD node, leaf list, material
+and image hash that the tracer reads must equal, bit for bit, what the reference's own classes hold after
+the same setup_*() call (oracle/ref_driver.cpp : dump_scene)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ALL_SCENES, ROOT
+
+
+def test_libraries_export_every_declared_symbol(hb):
+    for lib, names in ((hb.rt, hb.RT_SYMBOLS), (hb.host, hb.HOST_SYMBOLS)):
+        for n in names:
+            assert hasattr(lib, n), n
+    # and the headers declare nothing else
+    import re
+    for header, names, prefix in (("hai719_rt.h", hb.RT_SYMBOLS, "rt_"), ("hai719_host.h", hb.HOST_SYMBOLS, "hai_")):
+        src = open(os.path.join(ROOT, "include", header)).read()
+        declared = set(re.findall(r"\b(%s[a-z_0-9]+)\s*\(" % prefix, src))
+        assert declared == set(names), (declared ^ set(names))
+    assert hb.rt.rt_abi_version() == 1
+
+
+def test_struct_sizes_match_the_c_header(hb, tmp_path):
+    """ctypes mirrors vs sizeof() from the real header, via a tiny C program."""
+    prog = tmp_path / "sz.c"
+    prog.write_text('#include <stdio.h>\n#include "hai719_rt.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                    "sizeof(RtMaterial),sizeof(RtSphere),sizeof(RtSquare),sizeof(RtLight),sizeof(RtImage),sizeof(RtKdNode),"
+                    "sizeof(RtTriRef),sizeof(RtSceneMesh),sizeof(RtSceneDesc),sizeof(RtCamera),sizeof(RtRenderParams),sizeof(RtStats));return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(t) for t in (hb.RtMaterial, hb.RtSphere, hb.RtSquare, hb.RtLight, hb.RtImage, hb.RtKdNode,
+                                  hb.RtTriRef, hb.RtSceneMesh, hb.RtSceneDesc, hb.RtCamera, hb.RtRenderParams, hb.RtStats)]
+    assert got == want
+
+
+@pytest.mark.parametrize("name", ALL_SCENES)
+def test_scene_dump_equals_reference(hb, ref, assets, name):
+    a = ref.scene(name, aspect=850 / 480.0, seed=0)
+    da = a.dump()
+    a.close()
+    db = hb.Scene(name, aspect=850 / 480.0, seed=0).dump()
+    assert da.size == db.size
+    assert np.array_equal(da, db)
+
+
+@pytest.mark.parametrize("seed", [1, 12345])
+def test_random_scene_is_seeded_like_the_oracle(hb, ref, assets, seed):
+    for name in ("random_spheres", "config5"):
+        a = ref.scene(name, seed=seed)
+        da = a.dump()
+        a.close()
+        assert np.array_equal(da, hb.Scene(name, seed=seed).dump())
+    assert not np.array_equal(hb.Scene("random_spheres", seed=seed).dump(), hb.Scene("random_spheres", seed=seed + 1).dump())
+
+
+@pytest.mark.parametrize("wh", [(850, 480), (1920, 1080), (3840, 2160), (7680, 4320), (96, 54), (33, 77)])
+def test_camera_matrices_equal_reference(hb, ref, wh):
+    mv, pr, dr = ref.camera(*wh)
+    cam = hb.default_camera(*wh)
+    assert np.array_equal(mv, np.array(cam.modelview_inverse))
+    assert np.array_equal(pr, np.array(cam.projection_inverse))
+    assert cam.depth_near == dr[0] == 0.0
+
+
+def test_cornell_geometry_follows_aspect_ratio(hb, assets):
+    a = hb.Scene("cornell_box", aspect=1.0).dump()
+    b = hb.Scene("cornell_box", aspect=2.0).dump()
+    assert a.size == b.size and not np.array_equal(a, b)
+
+
+def test_kd_tree_shapes_match_survey(hb, assets):
+    """topology of the trees as built in the scenes."""
+    s = hb.Scene("flamingo")
+    assert s.kd_stats(0) == {"nodes": 1, "leaves": 1, "empty_leaves": 0, "refs": 832, "max_leaf": 832, "max_depth": 0}
+    s = hb.Scene("flamingo_pond")
+    k = s.kd_stats(0)
+    assert (k["nodes"], k["refs"], k["max_depth"]) == (3575, 53772, 100)
+    k = s.kd_stats(1)
+    assert (k["nodes"], k["leaves"], k["refs"], k["max_leaf"], k["max_depth"]) == (161, 81, 2637, 106, 11)
+    s = hb.Scene("backrooms_pool")
+    assert s.counts()["squares"] == 28 and s.counts()["meshes"] == 3 and s.counts()["lights"] == 0
+    assert (s.kd_stats(0)["nodes"], s.kd_stats(1)["nodes"], s.kd_stats(2)["nodes"]) == (5801, 671, 429)
+
+
+def test_flatten_is_consistent(hb, assets):
+    s = hb.Scene("flamingo_pond")
+    d = s.flatten().contents
+    assert d.abi_version == 1 and d.n_meshes == 2 and d.n_squares == 1 and d.n_lights == 1
+    for i in range(d.n_meshes):
+        m = d.meshes[i]
+        nodes = np.ctypeslib.as_array(C.cast(m.nodes, C.POINTER(C.c_uint32)), shape=(m.n_nodes, 10))
+        skip, first, nrefs, leaf = nodes[:, 3], nodes[:, 7], nodes[:, 8], nodes[:, 9]
+        idx = np.arange(m.n_nodes)
+        assert (skip > idx).all() and (skip <= m.n_nodes).all()
+        assert (skip[leaf == 1] == idx[leaf == 1] + 1).all()
+        # leaf ranges tile the ref array in order
+        lf = np.nonzero(leaf == 1)[0]
+        assert (first[lf] == np.concatenate([[0], np.cumsum(nrefs[lf])[:-1]])).all()
+        assert nrefs[lf].sum() == m.n_leaf_refs
+
+
+def test_missing_mesh_is_an_error_not_an_exit(hb, tmp_path):
+    s = hb.Scene(assets=str(tmp_path))
+    with pytest.raises(hb.RtError):
+        s.setup("flamingo")
+
+
+def test_loaders_handle_format_variants(hb, tmp_path):
+    """OFF plain / face-coloured / COFF, blank line after header; PPM P3 + P6 with comments."""
+    os.makedirs(tmp_path / "mesh")
+    os.makedirs(tmp_path / "img" / "textures")
+    # the flamingo scene loads mesh/flamingo_lowpoly_colored.off: feed it a COFF tetrahedron
+    (tmp_path / "mesh" / "flamingo_lowpoly_colored.off").write_text(
+        "COFF\n4 4 0\n0 0 0 255 0 0 255 \n1 0 0 0 255 0 255 \n0 1 0 0 0 255 255 \n0 0 1 255 255 255 255 \n"
+        "3 0 1 2 \n3 0 1 3 \n3 0 2 3 \n3 1 2 3 \n")
+    s = hb.Scene(assets=str(tmp_path))
+    s.setup("flamingo")
+    d = s.flatten().contents
+    m = d.meshes[0]
+    assert (m.n_vertices, m.n_triangles, m.color_type) == (4, 4, 0)
+    vc = np.ctypeslib.as_array(m.vert_colors, shape=(4, 3))
+    assert np.array_equal(vc[0], np.array([1, 0, 0], np.float32)) and np.array_equal(vc[3], np.ones(3, np.float32))
+    # face colours, detected from the first face line
+    (tmp_path / "mesh" / "flamingo_lowpoly_colored.off").write_text(
+        "OFF\n4 4 0\n0 0 0\n1 0 0\n0 1 0\n0 0 1\n3 0 1 2 255 0 0\n3 0 1 3 0 255 0\n3 0 2 3 0 0 255\n3 1 2 3 51 102 153\n")
+    s.setup("flamingo")
+    m = s.flatten().contents.meshes[0]
+    assert m.color_type == 1
+    fc = np.ctypeslib.as_array(m.face_colors, shape=(4, 3))
+    assert np.allclose(fc[3], np.array([51, 102, 153]) / 255.0, atol=1e-7)
+    # PPM: P3 with a comment line, as sky for single_sphere
+    (tmp_path / "img" / "textures" / "space.ppm").write_text("P3\n# made by hand\n2 2\n255\n255 0 0  0 255 0\n0 0 255  9 8 7\n")
+    s.setup("single_sphere")
+    d = s.flatten().contents
+    assert (d.skybox.w, d.skybox.h) == (2, 2)
+    px = np.ctypeslib.as_array(C.cast(d.skybox.rgb, C.POINTER(C.c_uint8)), shape=(4, 3))
+    assert px.tolist() == [[255, 0, 0], [0, 255, 0], [0, 0, 255], [9, 8, 7]]
+    # P6 with a comment after the magic
+    with open(tmp_path / "img" / "textures" / "space.ppm", "wb") as f:
+        f.write(b"P6\n# c\n2 1\n255\n" + bytes([1, 2, 3, 4, 5, 6]))
+    s.setup("single_sphere")
+    d = s.flatten().contents
+    assert (d.skybox.w, d.skybox.h) == (2, 1)
+    # unreadable image: empty, not an error (reference prints and carries on)
+    os.remove(tmp_path / "img" / "textures" / "space.ppm")
+    s.setup("single_sphere")
+    assert s.flatten().contents.skybox.w == 0
+
+
+def test_no_gpu_means_error_not_fallback(hb, assets):
+    """On the CPU-only build box the render path must fail loudly."""
+    if hb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    s = hb.Scene("single_square")
+    with pytest.raises(hb.RtError) as e:
+        s.render(16, 9, 1)
+    assert e.value.status == -2 or "no CUDA device" in str(e.value)

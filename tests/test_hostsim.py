@@ -1,0 +1,52 @@
+"""DEBUG AID, CPU only: the device functions of csrc/rt_core.cuh compiled as plain C++ (tests/hostsim)
+and compared with the oracle. This is how the path logic is checked in a container without a GPU; it is
+not a product path (nothing under hai719-raytracing_b200/ links or loads it) and it does not replace the
+-m gpu parity tests, which exercise the real sm_100a kernels through the C ABI."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+SIM_DIR = os.path.join(ROOT, "tests", "hostsim")
+
+
+@pytest.fixture(scope="module")
+def sim(hb):
+    so = os.path.join(SIM_DIR, "libhostsim.so")
+    src = os.path.join(SIM_DIR, "hostsim.cpp")
+    core = os.path.join(ROOT, "hai719-raytracing_b200", "csrc", "rt_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.check_call(["/usr/bin/g++", "-O3", "-fPIC", "-shared", "-std=c++17", "-I", os.path.join(ROOT, "include"),
+                               "-I", os.path.dirname(core), src, "-o", so, "-lpthread"])
+    L = C.CDLL(so)
+    L.sim_scene_create.restype = C.c_void_p
+    L.sim_scene_create.argtypes = [C.POINTER(hb.RtSceneDesc)]
+    L.sim_scene_destroy.argtypes = [C.c_void_p]
+    L.sim_render.argtypes = [C.c_void_p, C.POINTER(hb.RtCamera), C.POINTER(hb.RtRenderParams), C.c_void_p, C.c_void_p,
+                             C.c_void_p, C.c_int]
+    return L
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "random_spheres", "flamingo_pond", "backrooms_pool", "raccoon",
+                                  "rt_in_a_weekend", "flamingo_lake", "config5"])
+def test_core_functions_on_cpu_match_oracle(hb, ref, assets, sim, name):
+    W, H, SPP = 64, 36, 2
+    a = ref.scene(name, aspect=W / H)
+    want = a.render(W, H, SPP, seed=2, threads=0)
+    a.close()
+    s = hb.Scene(name, aspect=W / H)
+    h = sim.sim_scene_create(s.flatten())
+    cam = hb.default_camera(W, H)
+    p = hb.render_params(W, H, SPP, seed=2)
+    lin = np.zeros((H, W, 3), np.float32)
+    gam = np.zeros((H, W, 3), np.float32)
+    ids = np.zeros((H, W, 4), np.uint32)
+    sim.sim_render(h, C.byref(cam), C.byref(p), lin.ctypes.data, gam.ctypes.data, ids.ctypes.data, 0)
+    sim.sim_scene_destroy(h)
+    assert np.array_equal(ids, want["ids"])
+    assert np.array_equal(lin.view(np.uint32), want["linear"].view(np.uint32))
+    assert np.array_equal(gam.view(np.uint32), want["gamma"].view(np.uint32))

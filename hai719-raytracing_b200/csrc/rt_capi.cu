@@ -22,6 +22,7 @@
 
 #include "hai719_rt.h"
 #include "rt_core.cuh"
+#include "rt_pack.hpp"
 
 using namespace rt;
 
@@ -58,6 +59,7 @@ struct RenderArgs {
     float *samples;                     // n_paths * 3, path-major
     unsigned long long *work_counter;
     unsigned long long *stats;          // 10 counters, or null
+    int regen_min;                      // variant 1: refill idle lanes once at least this many are idle
 };
 
 // packed pixel index -> (x, y) via the tile prefix array
@@ -123,7 +125,7 @@ __device__ __forceinline__ void flush_counters(const Counters &c, unsigned long 
 // One path per lane; warps pull batches of 32 consecutive paths (same pixel for spp >= 32, so a
 // warp's primary rays are coherent) from a global counter until the chunk is exhausted.
 template <bool STATS>
-__global__ void __launch_bounds__(128) k_render_paths(const DScene scene, const DCamera cam, const RenderArgs a) {
+__global__ void __launch_bounds__(128, 4) k_render_paths(const DScene scene, const DCamera cam, const RenderArgs a) {
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
@@ -145,6 +147,68 @@ __global__ void __launch_bounds__(128) k_render_paths(const DScene scene, const 
             const V3 c = trace_path<STATS>(scene, ray, rng, a.max_bounces, a.nb_ech, &cnt);
             float *o = a.samples + 3ull * p;
             o[0] = c.x; o[1] = c.y; o[2] = c.z;
+        }
+    }
+    if (STATS) flush_counters(cnt, a.stats);
+}
+
+// Variant 1: ray-level state machine with per-lane path regeneration. Every loop iteration each
+// lane intersects ONE ray (closest-hit or shadow sample) and advances its path; a lane whose path
+// has ended takes the next path index from the global counter (one warp-aggregated atomicAdd,
+// __ballot_sync/__popc ranks). Lanes stay busy whatever the depth at which their paths end.
+template <bool STATS>
+__global__ void __launch_bounds__(128, 4) k_render_regen(const DScene scene, const DCamera cam, const RenderArgs a) {
+    Counters cnt;
+    if (STATS) memset(&cnt, 0, sizeof cnt);
+    const unsigned int lane = threadIdx.x & 31u;
+    PathState st;
+    st.mode = 2;
+    st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f; st.t_light = 0.f;
+    st.rng.key = 0; st.rng.ctr = 0;
+    bool exhausted = false;
+    for (;;) {
+        if (!exhausted) {
+            const unsigned int need = __ballot_sync(0xFFFFFFFFu, st.mode == 2);
+            if (__popc(need) >= a.regen_min || need == 0xFFFFFFFFu) {
+                const int leader = __ffs(need) - 1;
+                const unsigned long long n = (unsigned long long)__popc(need);
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(a.work_counter, n);
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (base + n >= a.n_paths) exhausted = true;
+                if (st.mode == 2) {
+                    const unsigned long long p = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
+                    if (p < a.n_paths) {
+                        const unsigned int lp = (unsigned int)(a.pixel_begin + p / (unsigned int)a.spp);
+                        const unsigned int smp = (unsigned int)(p % (unsigned int)a.spp);
+                        int x, y;
+                        packed_to_xy(a, lp, x, y);
+                        Rng rng;
+                        rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, smp);
+                        if (STATS) cnt.rnd += 3;
+                        const Ray ray = primary_ray(cam, x, y, a.width, a.height, rng);
+                        path_begin(st, ray, rng, (uint32_t)p, a.max_bounces);
+                        if (a.max_bounces == 0) {   // rayTraceRecursive(ray, 0) / 0
+                            const V3 c = path_fold(st, v3(0.f));
+                            float *o = a.samples + 3ull * p;
+                            o[0] = c.x; o[1] = c.y; o[2] = c.z;
+                            st.mode = 2;
+                        }
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xFFFFFFFFu, st.mode == 2)) break;
+        Hit h;
+        float hu = 0.f, hv = 0.f;
+        bool blocked;
+        intersect_ray<STATS>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
+        if (st.mode != 2) {
+            V3 c;
+            if (path_advance<STATS>(scene, st, h, hu, hv, blocked, a.nb_ech, c, &cnt)) {
+                float *o = a.samples + 3ull * st.path;
+                o[0] = c.x; o[1] = c.y; o[2] = c.z;
+            }
         }
     }
     if (STATS) flush_counters(cnt, a.stats);
@@ -193,7 +257,7 @@ __global__ void k_primary_ids(const DScene scene, const DCamera cam, int width, 
     uint32_t *o = ids + 4 * (size_t)i;
     o[0] = (uint32_t)h.type;
     o[1] = h.type ? (uint32_t)h.obj : 0u;
-    o[2] = h.type == 3 ? f2u(__ldg(scene.meshes[h.obj].tri_den + h.ref).y) : 0u;
+    o[2] = h.type == 3 ? f2u(__ldg(scene.tri_den + h.ref).y) : 0u;
     o[3] = f2u(h.t);
 }
 
@@ -207,7 +271,7 @@ __global__ void k_trace_rays(const DScene scene, size_t n, const float *org, con
     uint32_t *o = ids + 4 * i;
     o[0] = (uint32_t)h.type;
     o[1] = h.type ? (uint32_t)h.obj : 0u;
-    o[2] = h.type == 3 ? f2u(__ldg(scene.meshes[h.obj].tri_den + h.ref).y) : 0u;
+    o[2] = h.type == 3 ? f2u(__ldg(scene.tri_den + h.ref).y) : 0u;
     o[3] = f2u(h.t);
     if (!aux) return;
     float *q = aux + 8 * i;
@@ -224,10 +288,9 @@ __global__ void k_trace_rays(const DScene scene, size_t n, const float *org, con
         q[0] = u; q[1] = v;
         q[2] = scene.squares[h.obj].n[0]; q[3] = scene.squares[h.obj].n[1]; q[4] = scene.squares[h.obj].n[2];
     } else if (h.type == 3) {
-        const DMesh &m = scene.meshes[h.obj];
         float w0 = 0, w1 = 0, w2 = 0;
-        triangle_t<false>(ray, m, h.ref, w0, w1, w2, nullptr);
-        const float4 pl = m.tri_plane[h.ref];
+        triangle_t<false>(ray, scene, h.ref, w0, w1, w2, nullptr);
+        const float4 pl = scene.tri_plane[h.ref];
         q[0] = w0; q[1] = w1; q[2] = w2; q[3] = pl.x; q[4] = pl.y; q[5] = pl.z;
     }
 }
@@ -337,6 +400,16 @@ template <class T> int dev_alloc(RtScene *s, size_t n, T **out) {
     *out = (T *)p;
     return RT_OK;
 }
+
+struct DevTmp {   // scratch device buffer, freed on scope exit
+    void *p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+    cudaError_t put(const void *h, size_t bytes) {
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e == cudaSuccess && h && bytes) e = cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice);
+        return e;
+    }
+};
 
 DMaterial to_dmat(const RtMaterial &m) {
     DMaterial d{};
@@ -526,70 +599,41 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
         }
         if ((rc = dev_upload(s, l.data(), l.size(), &d.lights))) return rc;
     }
-    // meshes
+    // meshes: one shared node array + shared per-ref triangle constants (rt_pack.hpp, rt::DMesh)
     if (desc->n_meshes) {
+        PackedMeshes pk;
+        const std::string why = pack_meshes(*desc, pk);
+        if (!why.empty()) return fail(RT_ERR_INVALID, why);
+        if ((rc = dev_upload(s, pk.lo.data(), pk.lo.size(), &d.node_lo))) return rc;
+        if ((rc = dev_upload(s, pk.hi.data(), pk.hi.size(), &d.node_hi))) return rc;
+        float4 *pl = nullptr, *ed = nullptr; float2 *dn = nullptr;
+        if ((rc = dev_alloc(s, (size_t)pk.total_refs, &pl))) return rc;
+        if ((rc = dev_alloc(s, (size_t)3 * pk.total_refs, &ed))) return rc;
+        if ((rc = dev_alloc(s, (size_t)pk.total_refs, &dn))) return rc;
+        d.tri_plane = pl; d.tri_edge = ed; d.tri_den = dn;
         std::vector<DMesh> dm(desc->n_meshes);
         std::vector<DMaterial> m(desc->n_meshes);
         std::vector<float> tr(desc->n_meshes);
         for (uint32_t i = 0; i < desc->n_meshes; ++i) {
             const RtSceneMesh &src = desc->meshes[i];
             if ((rc = check_material(src.material, *desc))) return rc;
-            if ((src.n_vertices && !src.positions) || (src.n_triangles && !src.triangles) || (src.n_nodes && !src.nodes) || (src.n_leaf_refs && !src.leaf_refs))
-                return fail(RT_ERR_INVALID, "mesh with a null array");
-            if (src.color_type == RT_COLOR_VERTEX && !src.vert_colors) return fail(RT_ERR_INVALID, "vertex-coloured mesh without vert_colors");
-            if (src.color_type == RT_COLOR_FACE && !src.face_colors) return fail(RT_ERR_INVALID, "face-coloured mesh without face_colors");
             DMesh &o = dm[i];
             memset(&o, 0, sizeof o);
-            for (int k = 0; k < 3; ++k) { o.bmin[k] = src.root_bmin[k]; o.bmax[k] = src.root_bmax[k]; }
-            o.n_nodes = src.n_nodes;
+            o.node_begin = pk.node_begin[i];
+            o.node_end = pk.node_end[i];
             o.color_type = src.color_type;
-            // validate + pack nodes
-            std::vector<float4> lo(src.n_nodes), hi(src.n_nodes);
-            for (uint32_t k = 0; k < src.n_nodes; ++k) {
-                const RtKdNode &n = src.nodes[k];
-                if (n.is_leaf) {
-                    if ((uint64_t)n.first_ref + n.n_refs > src.n_leaf_refs || n.n_refs >= 0x80000000u) return fail(RT_ERR_INVALID, "KD leaf range out of bounds");
-                    lo[k] = make_float4(n.bmin[0], n.bmin[1], n.bmin[2], u2f(n.first_ref));
-                    hi[k] = make_float4(n.bmax[0], n.bmax[1], n.bmax[2], u2f(0x80000000u | n.n_refs));
-                } else {
-                    if (n.skip <= k || n.skip > src.n_nodes) return fail(RT_ERR_INVALID, "KD skip link out of bounds");
-                    lo[k] = make_float4(n.bmin[0], n.bmin[1], n.bmin[2], u2f(n.skip));
-                    hi[k] = make_float4(n.bmax[0], n.bmax[1], n.bmax[2], u2f(0u));
-                }
-            }
-            for (uint32_t k = 0; k < src.n_leaf_refs; ++k)
-                for (int j = 0; j < 3; ++j)
-                    if (src.leaf_refs[k].v[j] >= src.n_vertices) return fail(RT_ERR_INVALID, "leaf ref vertex index out of bounds");
-            for (uint32_t k = 0; k < src.n_leaf_refs; ++k)
-                if (src.leaf_refs[k].tri_index >= src.n_triangles) return fail(RT_ERR_INVALID, "leaf ref triangle index out of bounds");
-            if ((rc = dev_upload(s, lo.data(), lo.size(), &o.node_lo))) return rc;
-            if ((rc = dev_upload(s, hi.data(), hi.size(), &o.node_hi))) return rc;
             if ((rc = dev_upload(s, src.triangles, (size_t)3 * src.n_triangles, &o.triangles))) return rc;
             if (src.color_type == RT_COLOR_VERTEX && (rc = dev_upload(s, src.vert_colors, (size_t)3 * src.n_vertices, &o.vert_colors))) return rc;
             if (src.color_type == RT_COLOR_FACE && (rc = dev_upload(s, src.face_colors, (size_t)3 * src.n_triangles, &o.face_colors))) return rc;
             if (src.n_leaf_refs) {
-                float *d_pos = nullptr; RtTriRef *d_refs = nullptr;
-                RT_CUDA(cudaMalloc((void **)&d_pos, (size_t)3 * src.n_vertices * sizeof(float)));
-                cudaError_t e = cudaMalloc((void **)&d_refs, (size_t)src.n_leaf_refs * sizeof(RtTriRef));
-                if (e != cudaSuccess) { cudaFree(d_pos); RT_CUDA(e); }
-                float4 *pl = nullptr, *ed = nullptr; float2 *dn = nullptr;
-                rc = dev_alloc(s, (size_t)src.n_leaf_refs, &pl);
-                if (!rc) rc = dev_alloc(s, (size_t)3 * src.n_leaf_refs, &ed);
-                if (!rc) rc = dev_alloc(s, (size_t)src.n_leaf_refs, &dn);
-                cudaError_t e1 = cudaSuccess;
-                if (!rc) {
-                    e1 = cudaMemcpy(d_pos, src.positions, (size_t)3 * src.n_vertices * sizeof(float), cudaMemcpyHostToDevice);
-                    if (e1 == cudaSuccess) e1 = cudaMemcpy(d_refs, src.leaf_refs, (size_t)src.n_leaf_refs * sizeof(RtTriRef), cudaMemcpyHostToDevice);
-                    if (e1 == cudaSuccess) {
-                        k_precompute_tris<<<(src.n_leaf_refs + 127) / 128, 128>>>(d_pos, d_refs, src.n_leaf_refs, pl, ed, dn);
-                        e1 = cudaGetLastError();
-                        if (e1 == cudaSuccess) e1 = cudaDeviceSynchronize();
-                    }
-                }
-                cudaFree(d_pos); cudaFree(d_refs);
-                if (rc) return rc;
-                RT_CUDA(e1);
-                o.tri_plane = pl; o.tri_edge = ed; o.tri_den = dn;
+                DevTmp d_pos, d_refs;
+                RT_CUDA(d_pos.put(src.positions, (size_t)3 * src.n_vertices * sizeof(float)));
+                RT_CUDA(d_refs.put(src.leaf_refs, (size_t)src.n_leaf_refs * sizeof(RtTriRef)));
+                const uint32_t rb = pk.ref_begin[i];
+                k_precompute_tris<<<(src.n_leaf_refs + 127) / 128, 128>>>((const float *)d_pos.p, (const RtTriRef *)d_refs.p, src.n_leaf_refs,
+                                                                         pl + rb, ed + 3 * (size_t)rb, dn + rb);
+                RT_CUDA(cudaGetLastError());
+                RT_CUDA(cudaDeviceSynchronize());
             }
             m[i] = to_dmat(src.material);
             tr[i] = src.material.transparency;
@@ -638,12 +682,21 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     DCamera cam;
     fill_camera(*camera, cam);
     const bool want_stats = p->collect_stats != 0 && stats != nullptr;
-    const void *kern = want_stats ? (const void *)k_render_paths<true> : (const void *)k_render_paths<false>;
+    // variant: low byte = kernel (0 auto, 1 k_render_paths: one path per lane to completion,
+    // 2 k_render_regen: ray-level state machine with path regeneration and warp-voted KD traversal);
+    // bits 8..15 = regeneration threshold of kernel 2 (idle lanes needed before a refill; 0 = 16)
+    if (p->variant < 0 || (p->variant & 0xFF) > 2 || (p->variant >> 16)) return fail(RT_ERR_INVALID, "unknown kernel variant");
+    int kind = p->variant & 0xFF;
+    if (kind == 0) kind = (s->d.n_meshes > 0 && s->d.n_lights > 0) ? 2 : 1;   // measured: profiles/r01_variants.md
+    const bool regen = kind == 2;
+    const void *kern = regen ? (want_stats ? (const void *)k_render_regen<true> : (const void *)k_render_regen<false>)
+                             : (want_stats ? (const void *)k_render_paths<true> : (const void *)k_render_paths<false>);
     const int grid = persistent_grid(s, kern, 128);
 
     RenderArgs a{};
     a.tiles = s->d_tiles; a.tile_off = s->d_tile_off; a.n_tiles = (int)n_tiles;
     a.width = p->width; a.height = p->height; a.spp = p->spp; a.max_bounces = p->max_bounces; a.nb_ech = p->nb_ech;
+    a.regen_min = ((p->variant >> 8) & 0xFF) ? std::min(32, (p->variant >> 8) & 0xFF) : 16;
     a.seed = p->seed; a.samples = s->samples; a.work_counter = s->counters; a.stats = want_stats ? s->counters + 1 : nullptr;
     uint32_t launches = 0;
     RT_CUDA(cudaMemsetAsync(s->counters, 0, 16 * sizeof(unsigned long long), st));
@@ -655,8 +708,13 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
         if (pb) RT_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long), st));
         const unsigned long long batches = (a.n_paths + 31) / 32;
         const int g = (int)std::min<unsigned long long>((unsigned long long)grid, (batches + 3) / 4);
-        if (want_stats) k_render_paths<true><<<g, 128, 0, st>>>(s->d, cam, a);
-        else k_render_paths<false><<<g, 128, 0, st>>>(s->d, cam, a);
+        if (regen) {
+            if (want_stats) k_render_regen<true><<<g, 128, 0, st>>>(s->d, cam, a);
+            else k_render_regen<false><<<g, 128, 0, st>>>(s->d, cam, a);
+        } else {
+            if (want_stats) k_render_paths<true><<<g, 128, 0, st>>>(s->d, cam, a);
+            else k_render_paths<false><<<g, 128, 0, st>>>(s->d, cam, a);
+        }
         RT_CUDA(cudaGetLastError());
         k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(s->samples, pb, (unsigned int)np, p->spp, d_linear, d_gamma);
         RT_CUDA(cudaGetLastError());

@@ -133,14 +133,12 @@ struct DSquare {            // per-square constants of Square::intersect hoisted
     int glass;              // material.type == Material_Glass           Square.h:84
     float tan_r[3], tan_u[3];  // m_right_vector / m_up_vector members (normal-map frame)
 };
+// All meshes share one node array and one set of triangle arrays (rt_pack.hpp). Mesh m owns the node
+// range [node_begin, node_end): first a synthetic root whose box is KDTree::aabb — the gate
+// KDTree::intersect tests before descending (KDTree.cpp:80-83) — then the tree in pre-order, skip
+// links and leaf ranges already offset into the shared arrays. An empty tree owns an empty range.
 struct DMesh {
-    float bmin[3], bmax[3];
-    uint32_t n_nodes;
-    // node i: lo = {bmin.xyz, bits(inner: skip | leaf: first_ref)}, hi = {bmax.xyz, bits(leaf: 0x80000000|n_refs, inner: 0)}
-    const float4 *node_lo, *node_hi;
-    const float4 *tri_plane;   // per leaf ref: {n.xyz, D = c0.n}
-    const float4 *tri_edge;    // per leaf ref, 3 entries: {c0.xyz, d00}, {e0.xyz, d01}, {e1.xyz, d11}
-    const float2 *tri_den;     // per leaf ref: {denom, bits(tri_index)}
+    uint32_t node_begin, node_end;
     int color_type;
     const float *vert_colors, *face_colors;
     const uint32_t *triangles;
@@ -154,6 +152,11 @@ struct DScene {
     const float *sq_transparency;
     const DMesh *meshes;
     const float *mesh_transparency;
+    // node i: lo = {bmin.xyz, bits(inner: skip | leaf: first_ref)}, hi = {bmax.xyz, bits(leaf: 0x80000000|n_refs, inner: 0)}
+    const float4 *node_lo, *node_hi;
+    const float4 *tri_plane;   // per leaf ref: {n.xyz, D = c0.n}
+    const float4 *tri_edge;    // per leaf ref, 3 entries: {c0.xyz, d00}, {e0.xyz, d01}, {e1.xyz, d11}
+    const float2 *tri_den;     // per leaf ref: {denom, bits(tri_index within its mesh)}
     const DMaterial *sph_mat, *sq_mat, *mesh_mat;
     const DLight *lights;
     const DImage *textures, *normal_maps;
@@ -180,17 +183,28 @@ struct Hit {
 };
 
 // ---- sphere ------------------------------------------------------------------------------------
-// Sphere::intersect up to t (Sphere.h:94-123). Returns NaN when delta < 0 (sqrt of a negative),
-// which every caller's "t > eps && t < best" rejects, exactly like intersectionExists == false.
-// Only the near root is ever reported (Sphere.h:112-117 can never take the far one).
-RT_HD float sphere_t(const Ray &ray, float4 a, float4 b) {
+// Sphere::intersect up to t (Sphere.h:94-123):  t = (-b - sqrt(delta)) / (2a), near root only (the
+// far-root branch at Sphere.h:112-117 can never be taken). Every caller keeps a hit
+// only if EPSILON <= t < something, so the two cheap rejections below are exact:
+//   * b >= 0 (or -0)  =>  -b - sqrt(delta) <= 0  =>  t <= 0 < EPSILON           (a = d.d > 0)
+//   * delta < 0       =>  intersectionExists == false
+// NaNs fail both "proceed" tests and are dropped, as they are by the reference's comparisons.
+// Returns FLT_MAX for "no usable hit". A4 = 4*a and A2 = 2*a are per-ray constants (same products
+// the reference forms: 4*a*c associates as (4*a)*c).
+struct SphereRay { float A4, A2; };
+RT_HD SphereRay make_sphere_ray(const Ray &ray) {
+    const float A = dot(ray.d, ray.d);
+    SphereRay r; r.A4 = 4.f * A; r.A2 = 2.f * A; return r;
+}
+RT_HD float sphere_t(const Ray &ray, const SphereRay &sr, float4 a, float4 b) {
     const V3 c = v3(a.x, a.y, a.z) + ray.time * v3(b.x, b.y, b.z);
     const V3 oc = ray.o - c;
-    const float A = dot(ray.d, ray.d);
     const float B = 2.f * dot(ray.d, oc);
+    if (!(B < 0.f)) return FLT_MAX;
     const float C = dot(oc, oc) - a.w * a.w;
-    const float delta = B * B - 4.f * A * C;
-    return (-B - sqrtf(delta)) / (2.f * A);
+    const float delta = B * B - sr.A4 * C;
+    if (!(delta >= 0.f)) return FLT_MAX;
+    return (-B - sqrtf(delta)) / sr.A2;
 }
 
 // ---- square ------------------------------------------------------------------------------------
@@ -271,7 +285,7 @@ RT_HD TriConst precompute_triangle(V3 p0, V3 p1, V3 p2, uint32_t tri_index) {
 
 // Triangle::getIntersection (Triangle.h:77-126). Returns t, or FLT_MAX for "no intersection".
 template <bool STATS>
-RT_HD float triangle_t(const Ray &ray, const DMesh &m, uint32_t ref, float &w0, float &w1, float &w2, Counters *cnt) {
+RT_HD float triangle_t(const Ray &ray, const DScene &m, uint32_t ref, float &w0, float &w1, float &w2, Counters *cnt) {
     const float4 pl = RT_LDG(m.tri_plane + ref);
     const V3 n = v3(pl.x, pl.y, pl.z);
     const float dotRN = dot(ray.d, n);
@@ -302,15 +316,13 @@ RT_HD float triangle_t(const Ray &ray, const DMesh &m, uint32_t ref, float &w0, 
 // minimum t, the LAST leaf winning ties; inside a leaf the FIRST triangle wins ties (strict <).
 // The pre-order array reproduces that order with no stack: a missed box jumps to `skip`.
 template <bool STATS>
-RT_HD bool mesh_closest(const Ray &ray, const RayInv &inv, const DMesh &m, float &t_out, uint32_t &ref_out, Counters *cnt) {
-    if (m.n_nodes == 0) return false;
-    if (!slab_hit(ray, inv, m.bmin[0], m.bmin[1], m.bmin[2], m.bmax[0], m.bmax[1], m.bmax[2])) return false;
+RT_HD bool mesh_closest(const Ray &ray, const RayInv &inv, const DScene &s, const DMesh &m, float &t_out, uint32_t &ref_out, Counters *cnt) {
     float best_t = FLT_MAX;
     uint32_t best_ref = 0xFFFFFFFFu;
-    uint32_t i = 0;
-    const uint32_t n_nodes = m.n_nodes;
-    while (i < n_nodes) {
-        const float4 lo = RT_LDG(m.node_lo + i), hi = RT_LDG(m.node_hi + i);
+    uint32_t i = m.node_begin;
+    const uint32_t end = m.node_end;
+    while (i < end) {
+        const float4 lo = RT_LDG(s.node_lo + i), hi = RT_LDG(s.node_hi + i);
         const uint32_t hw = f2u(hi.w);
         const bool leaf = (hw & 0x80000000u) != 0u;
         if (STATS) cnt->node++;
@@ -325,7 +337,7 @@ RT_HD bool mesh_closest(const Ray &ray, const RayInv &inv, const DMesh &m, float
             for (uint32_t k = first; k < first + count; ++k) {
                 float a, b, c;
                 if (STATS) cnt->tri++;
-                const float t = triangle_t<STATS>(ray, m, k, a, b, c, cnt);
+                const float t = triangle_t<STATS>(ray, s, k, a, b, c, cnt);
                 if (t < leaf_t) { leaf_t = t; leaf_ref = k; }
             }
             if (leaf_ref != 0xFFFFFFFFu && leaf_t <= best_t) { best_t = leaf_t; best_ref = leaf_ref; }
@@ -346,9 +358,10 @@ template <bool STATS>
 RT_HD Hit closest_hit(const DScene &s, const Ray &ray, float &aux_u, float &aux_v, Counters *cnt) {
     Hit h; h.type = 0; h.obj = -1; h.t = FLT_MAX; h.ref = 0;
     if (STATS) cnt->closest++;
+    const SphereRay sr = make_sphere_ray(ray);
     for (int i = 0; i < s.n_spheres; ++i) {
         if (STATS) cnt->sphere++;
-        const float t = sphere_t(ray, RT_LDG(s.sph_a + i), RT_LDG(s.sph_b + i));
+        const float t = sphere_t(ray, sr, RT_LDG(s.sph_a + i), RT_LDG(s.sph_b + i));
         if (t < h.t && t > RT_EPSF) { h.type = 1; h.obj = i; h.t = t; }
     }
     for (int i = 0; i < s.n_squares; ++i) {
@@ -362,7 +375,7 @@ RT_HD Hit closest_hit(const DScene &s, const Ray &ray, float &aux_u, float &aux_
         for (int i = 0; i < s.n_meshes; ++i) {
             if (STATS) cnt->mesh++;
             float t; uint32_t ref;
-            if (mesh_closest<STATS>(ray, inv, s.meshes[i], t, ref, cnt) && t < h.t && t > RT_EPSF) {
+            if (mesh_closest<STATS>(ray, inv, s, s.meshes[i], t, ref, cnt) && t < h.t && t > RT_EPSF) {
                 h.type = 3; h.obj = i; h.t = t; h.ref = ref;
             }
         }
@@ -377,10 +390,11 @@ RT_HD Hit closest_hit(const DScene &s, const Ray &ray, float &aux_u, float &aux_
 template <bool STATS>
 RT_HD bool shadow_hit(const DScene &s, const Ray &ray, float t_light, Rng &rng, Counters *cnt) {
     if (STATS) cnt->shadow++;
+    const SphereRay sr = make_sphere_ray(ray);
     for (int i = 0; i < s.n_spheres; ++i) {
         if (STATS) cnt->sphere++;
         const float4 b = RT_LDG(s.sph_b + i);
-        const float t = sphere_t(ray, RT_LDG(s.sph_a + i), b);
+        const float t = sphere_t(ray, sr, RT_LDG(s.sph_a + i), b);
         if (t < t_light && t > RT_EPSF) {
             if (STATS) cnt->rnd++;
             if (rng.next() > b.w) return true;
@@ -400,7 +414,7 @@ RT_HD bool shadow_hit(const DScene &s, const Ray &ray, float t_light, Rng &rng, 
         for (int i = 0; i < s.n_meshes; ++i) {
             if (STATS) cnt->mesh++;
             float t; uint32_t ref;
-            if (mesh_closest<STATS>(ray, inv, s.meshes[i], t, ref, cnt) && t < t_light && t > RT_EPSF) {
+            if (mesh_closest<STATS>(ray, inv, s, s.meshes[i], t, ref, cnt) && t < t_light && t > RT_EPSF) {
                 if (STATS) cnt->rnd++;
                 if (rng.next() > RT_LDG(s.mesh_transparency + i)) return true;
             }
@@ -550,11 +564,17 @@ RT_HD V3 trace_path(const DScene &s, Ray ray, Rng &rng, int max_bounces, int nb_
             const V3 c = v3(a.x, a.y, a.z) + ray.time * v3(b.x, b.y, b.z);
             P = ray.o + h.t * ray.d;
             n = normalized(P - c);
-            const float theta = (float)acos((double)n.y * -1.);
-            const float phi = (float)(atan2((double)n.z * -1., (double)n.x) + RT_PI);
             kd = ld3(mat->kd);
-            const float tu = (float)((double)phi / (2 * RT_PI)), tv = (float)((double)theta / RT_PI);
-            if (mat->texture_type != 0) material_texture<STATS>(s, *mat, kd, tu, tv, cnt);   // sphere_texture
+            float tu = 0.f, tv = 0.f;
+            if (mat->texture_type != 0) {
+                // theta/phi (Sphere.h:129-130) feed only sphere_texture() and a textured emit(); the
+                // reference evaluates them for every candidate, the result is the same without
+                const float theta = (float)acos((double)n.y * -1.);
+                const float phi = (float)(atan2((double)n.z * -1., (double)n.x) + RT_PI);
+                tu = (float)((double)phi / (2 * RT_PI));
+                tv = (float)((double)theta / RT_PI);
+                material_texture<STATS>(s, *mat, kd, tu, tv, cnt);   // sphere_texture
+            }
             e = material_emit<STATS>(s, *mat, tu, tv, cnt);
         } else if (h.type == 2) {
             mat = s.sq_mat + h.obj;
@@ -569,12 +589,12 @@ RT_HD V3 trace_path(const DScene &s, Ray ray, Rng &rng, int max_bounces, int nb_
             mat = s.mesh_mat + h.obj;
             const DMesh &m = s.meshes[h.obj];
             float w0, w1, w2;
-            triangle_t<false>(ray, m, h.ref, w0, w1, w2, nullptr);   // recompute the barycentrics of the winner
+            triangle_t<false>(ray, s, h.ref, w0, w1, w2, nullptr);   // recompute the barycentrics of the winner
             P = ray.o + h.t * ray.d;
-            const float4 pl = RT_LDG(m.tri_plane + h.ref);
+            const float4 pl = RT_LDG(s.tri_plane + h.ref);
             n = v3(pl.x, pl.y, pl.z);                                // flat face normal (Triangle.h:119)
             kd = ld3(mat->kd);
-            const uint32_t ti = f2u(RT_LDG(m.tri_den + h.ref).y);
+            const uint32_t ti = f2u(RT_LDG(s.tri_den + h.ref).y);
             if (m.color_type == 0) {
                 const uint32_t i0 = m.triangles[3 * ti], i1 = m.triangles[3 * ti + 1], i2 = m.triangles[3 * ti + 2];
                 kd = w0 * ld3(m.vert_colors + 3 * i0) + w1 * ld3(m.vert_colors + 3 * i1) + w2 * ld3(m.vert_colors + 3 * i2);
@@ -615,6 +635,246 @@ RT_HD V3 trace_path(const DScene &s, Ray ray, Rng &rng, int max_bounces, int nb_
     for (int k = depth - 1; k >= 0; --k) r = (rec_c[k] + comp_product(r, rec_kd[k])) + rec_e[k];
     r = v3(0.f) + r;
     return r / (float)max_bounces;
+}
+
+// ---- one path, as a ray-level state machine ----------------------------------------------------
+// Same arithmetic and the same random_float() order as trace_path above, cut at every ray: a lane
+// holds one path and, per step, ONE ray to intersect — a closest-hit ray (Scene::computeIntersection)
+// or one soft-shadow sample (Scene::computeShadow). The kernel (k_render_regen) runs the steps of
+// 32 paths in lockstep, so lanes that are at different bounces, or one shading and one shadowing,
+// still execute the intersection loops together; a lane whose path ends takes a new path at once.
+#ifdef __CUDA_ARCH__
+#define RT_WARP_ALL(pred) __all_sync(0xFFFFFFFFu, (pred))
+#define RT_BALLOT(pred) __ballot_sync(0xFFFFFFFFu, (pred))
+#define RT_POPC(x) __popc(x)
+#else   /* one lane */
+#define RT_WARP_ALL(pred) (pred)
+#define RT_BALLOT(pred) ((pred) ? 1u : 0u)
+#define RT_POPC(x) ((int)((x) != 0u))
+#endif
+
+struct PathState {
+    Rng rng;
+    Ray ray;             // the ray to intersect next
+    int mode;            // 0 closest hit, 1 shadow sample, 2 idle (no path)
+    int N;               // remaining bounces (NRemainingBounces of rayTraceRecursive)
+    int depth;           // records written so far
+    uint32_t path;       // index of the path in the chunk (output slot)
+    // context of the hit being lit (valid while mode == 1)
+    V3 P, n, kd, e, color, in_d;
+    const DMaterial *mat;
+    int light, j, blocked;
+    float t_light;
+    int max_bounces;
+    V3 rec_c[RT_MAX_BOUNCES], rec_kd[RT_MAX_BOUNCES], rec_e[RT_MAX_BOUNCES];
+};
+
+// Scene::computeIntersection and Scene::computeShadow over the same loops. mode 0: closest hit into
+// (h, hu, hv). mode 1: `blocked` is computeShadow's return value; candidates draw from rng in the
+// reference's order (spheres, squares, meshes) until one blocks. Lanes that have their answer
+// (blocked, or idle) skip the tests; the loops end early only when the whole warp is done.
+template <bool STATS>
+RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_light, Rng &rng, Hit &h, float &hu, float &hv,
+                         bool &blocked, Counters *cnt) {
+    h.type = 0; h.obj = -1; h.t = (mode == 0) ? FLT_MAX : t_light; h.ref = 0;
+    blocked = false;
+    bool done = (mode == 2);
+    if (STATS) { if (mode == 0) cnt->closest++; else if (mode == 1) cnt->shadow++; }
+    const SphereRay sr = make_sphere_ray(ray);
+    for (int i = 0; i < s.n_spheres; ++i) {
+        if ((i & 3) == 0 && RT_WARP_ALL(done)) break;
+        if (done) continue;
+        if (STATS) cnt->sphere++;
+        const float4 b = RT_LDG(s.sph_b + i);
+        const float t = sphere_t(ray, sr, RT_LDG(s.sph_a + i), b);
+        if (t < h.t && t > RT_EPSF) {
+            if (mode == 0) { h.type = 1; h.obj = i; h.t = t; }
+            else { if (STATS) cnt->rnd++; if (rng.next() > b.w) { blocked = true; done = true; } }
+        }
+    }
+    for (int i = 0; i < s.n_squares; ++i) {
+        if ((i & 3) == 0 && RT_WARP_ALL(done)) break;
+        if (done) continue;
+        if (STATS) cnt->square++;
+        float u, v;
+        const float t = square_t(ray, s.squares[i], u, v);
+        if (t < h.t && t > RT_EPSF) {
+            if (mode == 0) { h.type = 2; h.obj = i; h.t = t; hu = u; hv = v; }
+            else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.sq_transparency + i)) { blocked = true; done = true; } }
+        }
+    }
+    if (s.n_meshes > 0) {
+        // Every lane walks the shared pre-order node array with its own ray: mesh after mesh, node
+        // after node, and inside a leaf triangle after triangle. A lane is always in one of two
+        // states — "next step is a triangle test" or "next step is a node (box test / leaf open /
+        // mesh hand-over)". Each round the warp votes (__ballot_sync/__popc) and executes only the
+        // step kind the MAJORITY of its lanes needs; the others wait one round. That keeps the two
+        // expensive bodies (triangle test, fp64 slab test) convergent although the 32 rays are in
+        // different nodes: a plain per-lane nested loop ran at 3.5 of 32 lanes (profiles/r01).
+        const RayInv inv = make_inv(ray);
+        const uint32_t NONE = 0xFFFFFFFFu;
+        bool active = !done;
+        int mi = 0;
+        uint32_t i = 0, mesh_end = 0, k = 0, kend = 0;
+        if (active) { i = s.meshes[0].node_begin; mesh_end = s.meshes[0].node_end; if (STATS) cnt->mesh++; }
+        float leaf_t = FLT_MAX, best_t = FLT_MAX;
+        uint32_t leaf_ref = NONE, best_ref = NONE;
+        for (;;) {
+            const bool want_tri = active && k < kend;
+            const bool want_node = active && !want_tri;
+            const unsigned int bt = RT_BALLOT(want_tri), bn = RT_BALLOT(want_node);
+            if ((bt | bn) == 0u) break;
+            if (RT_POPC(bt) >= RT_POPC(bn)) {
+                if (want_tri) {
+                    float a, b, c;
+                    if (STATS) cnt->tri++;
+                    const float t = triangle_t<STATS>(ray, s, k, a, b, c, cnt);
+                    if (t < leaf_t) { leaf_t = t; leaf_ref = k; }        // first triangle wins ties inside a leaf
+                    ++k;
+                    if (k == kend && leaf_ref != NONE && leaf_t <= best_t) { best_t = leaf_t; best_ref = leaf_ref; }  // last leaf wins ties
+                }
+            } else if (want_node) {
+                if (i >= mesh_end) {
+                    // mesh mi is done: Scene-level acceptance (Scene.h:221-228 closest, 248-253 shadow)
+                    if (best_ref != NONE && best_t < h.t && best_t > RT_EPSF) {
+                        if (mode == 0) { h.type = 3; h.obj = mi; h.t = best_t; h.ref = best_ref; }
+                        else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.mesh_transparency + mi)) { blocked = true; active = false; } }
+                    }
+                    if (++mi >= s.n_meshes) active = false;
+                    if (active) {
+                        i = s.meshes[mi].node_begin; mesh_end = s.meshes[mi].node_end;
+                        best_t = FLT_MAX; best_ref = NONE;
+                        if (STATS) cnt->mesh++;
+                    }
+                } else {
+                    const float4 lo = RT_LDG(s.node_lo + i), hi = RT_LDG(s.node_hi + i);
+                    const uint32_t hw = f2u(hi.w);
+                    const bool leaf = (hw & 0x80000000u) != 0u;
+                    if (STATS) cnt->node++;
+                    if (!slab_hit(ray, inv, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z)) {
+                        i = leaf ? i + 1 : f2u(lo.w);
+                    } else {
+                        if (leaf) { k = f2u(lo.w); kend = k + (hw & 0x7FFFFFFFu); leaf_t = FLT_MAX; leaf_ref = NONE; }
+                        ++i;
+                    }
+                }
+            }
+        }
+    }
+}
+
+RT_HD void path_begin(PathState &st, const Ray &primary, const Rng &rng, uint32_t path, int max_bounces) {
+    st.rng = rng; st.ray = primary; st.mode = 0; st.N = max_bounces; st.depth = 0; st.path = path; st.max_bounces = max_bounces;
+}
+
+// fold the records back to front: result_k = (color_k + result_{k+1} (*) kd_k) + e_k  (Scene.h:339-341)
+RT_HD V3 path_fold(const PathState &st, V3 tail) {
+    V3 r = tail;
+    for (int k = st.depth - 1; k >= 0; --k) r = (st.rec_c[k] + comp_product(r, st.rec_kd[k])) + st.rec_e[k];
+    r = v3(0.f) + r;
+    return r / (float)st.max_bounces;
+}
+
+// next soft-shadow sample of light st.light (Scene.h:325-330)
+template <bool STATS>
+RT_HD void path_shadow_sample(const DScene &s, PathState &st, Counters *cnt) {
+    if (STATS) cnt->rnd += 3;
+    const V3 lp = ld3(s.lights[st.light].pos);
+    const float delta = s.lights[st.light].radius / 2.f;
+    const V3 lj = lp + random_unit_vector(st.rng) * delta;
+    const V3 Lj = normalized(lj - st.P);
+    st.t_light = length(lj - st.P);
+    const float time = st.ray.time;
+    st.ray = make_ray(st.P + Lj * RT_EPSF, Lj, time);
+    st.mode = 1;
+}
+
+// Start lighting with light st.light, or — when the lights are exhausted — scatter and continue.
+// Returns true when the path has ended (result in `out`).
+template <bool STATS>
+RT_HD bool path_next_light_or_bounce(const DScene &s, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
+    if (st.light < s.n_lights) {
+        const V3 L = normalized(ld3(s.lights[st.light].pos) - st.P);
+        const float dotLN = dot(L, st.n);
+        st.color = st.color + (comp_product(ld3(s.lights[0].color), st.kd) * fmaxr(0.0f, dotLN)) * (float)(1. - (double)st.mat->transparency);
+        st.j = 0; st.blocked = 0;
+        path_shadow_sample<STATS>(s, st, cnt);
+        return false;
+    }
+    Ray in; in.o = st.P; in.d = st.in_d; in.time = st.ray.time;
+    st.ray = material_scatter<STATS>(*st.mat, in, st.n, st.P, st.rng, cnt);
+    st.rec_c[st.depth] = st.color; st.rec_kd[st.depth] = st.kd; st.rec_e[st.depth] = st.e;
+    ++st.depth;
+    --st.N;
+    if (st.N == 0) { out = path_fold(st, v3(0.f)); st.mode = 2; return true; }
+    st.mode = 0;
+    return false;
+}
+
+// Consume the result of intersect_ray for this lane's ray and set up the next ray.
+template <bool STATS>
+RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, float hv, bool blocked, int nb_ech, V3 &out,
+                        Counters *cnt) {
+    if (st.mode == 1) {
+        if (blocked) ++st.blocked;
+        if (++st.j < nb_ech) { path_shadow_sample<STATS>(s, st, cnt); return false; }
+        const float shadow = (float)(1. - (double)((float)st.blocked / (float)nb_ech));
+        st.color = st.color * shadow;
+        ++st.light;
+        return path_next_light_or_bounce<STATS>(s, st, nb_ech, out, cnt);
+    }
+    // mode 0: shade the closest hit (Scene.h:270-304)
+    const Ray &ray = st.ray;
+    if (h.type == 0) { out = path_fold(st, sky_color<STATS>(s, ray.d, st.N, cnt)); st.mode = 2; return true; }
+    V3 P, n, kd, e;
+    const DMaterial *mat;
+    if (h.type == 1) {
+        mat = s.sph_mat + h.obj;
+        const float4 a = RT_LDG(s.sph_a + h.obj), b = RT_LDG(s.sph_b + h.obj);
+        const V3 c = v3(a.x, a.y, a.z) + ray.time * v3(b.x, b.y, b.z);
+        P = ray.o + h.t * ray.d;
+        n = normalized(P - c);
+        kd = ld3(mat->kd);
+        float tu = 0.f, tv = 0.f;
+        if (mat->texture_type != 0) {
+            const float theta = (float)acos((double)n.y * -1.);
+            const float phi = (float)(atan2((double)n.z * -1., (double)n.x) + RT_PI);
+            tu = (float)((double)phi / (2 * RT_PI));
+            tv = (float)((double)theta / RT_PI);
+            material_texture<STATS>(s, *mat, kd, tu, tv, cnt);
+        }
+        e = material_emit<STATS>(s, *mat, tu, tv, cnt);
+    } else if (h.type == 2) {
+        mat = s.sq_mat + h.obj;
+        const DSquare &q = s.squares[h.obj];
+        P = ray.o + h.t * ray.d;
+        n = ld3(q.n);
+        kd = ld3(mat->kd);
+        material_texture<STATS>(s, *mat, kd, hu, hv, cnt);
+        n = material_normal<STATS>(s, *mat, n, hu, hv, ld3(q.tan_r), ld3(q.tan_u), cnt);
+        e = material_emit<STATS>(s, *mat, hu, hv, cnt);
+    } else {
+        mat = s.mesh_mat + h.obj;
+        const DMesh &m = s.meshes[h.obj];
+        float w0, w1, w2;
+        triangle_t<false>(ray, s, h.ref, w0, w1, w2, nullptr);
+        P = ray.o + h.t * ray.d;
+        const float4 pl = RT_LDG(s.tri_plane + h.ref);
+        n = v3(pl.x, pl.y, pl.z);
+        kd = ld3(mat->kd);
+        const uint32_t ti = f2u(RT_LDG(s.tri_den + h.ref).y);
+        if (m.color_type == 0) {
+            const uint32_t i0 = m.triangles[3 * ti], i1 = m.triangles[3 * ti + 1], i2 = m.triangles[3 * ti + 2];
+            kd = w0 * ld3(m.vert_colors + 3 * i0) + w1 * ld3(m.vert_colors + 3 * i1) + w2 * ld3(m.vert_colors + 3 * i2);
+        } else if (m.color_type == 1) {
+            kd = ld3(m.face_colors + 3 * ti);
+        }
+        e = v3(0.f);
+    }
+    st.P = P; st.n = n; st.kd = kd; st.e = e; st.mat = mat; st.in_d = ray.d;
+    st.color = v3(0.f);
+    st.light = 0;
+    return path_next_light_or_bounce<STATS>(s, st, nb_ech, out, cnt);
 }
 
 // ---- camera ------------------------------------------------------------------------------------

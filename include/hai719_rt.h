@@ -162,7 +162,9 @@ typedef struct RtRenderParams {
     int32_t rank, n_ranks;
     int32_t tile_w, tile_h;      /* 0 = default 32 x 32                                              */
     int32_t collect_stats;       /* fill the work counters of RtStats (slower)                       */
-    int32_t variant;             /* 0 = default kernel path; see DESIGN.md for the others            */
+    int32_t variant;             /* 0 = auto. Low byte: 1 = one path per lane (k_render_paths), 2 = ray-level
+                                    state machine with path regeneration (k_render_regen); bits 8..15 =
+                                    regeneration threshold of kernel 2. All variants give identical bits. */
 } RtRenderParams;
 
 typedef struct RtStats {

@@ -14,6 +14,7 @@
 
 #include "hai719_rt.h"
 #include "rt_core.cuh"
+#include "rt_pack.hpp"
 
 using namespace rt;
 
@@ -26,8 +27,9 @@ struct SimScene {
     std::vector<DLight> lights;
     std::vector<DImage> tex, nrm;
     std::vector<DMesh> meshes;
-    std::vector<std::vector<float4>> lo, hi, plane, edge;
-    std::vector<std::vector<float2>> den;
+    PackedMeshes pk;
+    std::vector<float4> plane, edge;
+    std::vector<float2> den;
 };
 
 static DMaterial to_dmat(const RtMaterial &m) {
@@ -84,37 +86,26 @@ void *sim_scene_create(const RtSceneDesc *desc) {
     }
     d.lights = s->lights.data();
     const uint32_t nm = desc->n_meshes;
-    s->lo.resize(nm); s->hi.resize(nm); s->plane.resize(nm); s->edge.resize(nm); s->den.resize(nm);
+    if (!pack_meshes(*desc, s->pk).empty()) { delete s; return nullptr; }
     for (uint32_t i = 0; i < nm; ++i) {
         const RtSceneMesh &src = desc->meshes[i];
         DMesh o;
         memset(&o, 0, sizeof o);
-        for (int k = 0; k < 3; ++k) { o.bmin[k] = src.root_bmin[k]; o.bmax[k] = src.root_bmax[k]; }
-        o.n_nodes = src.n_nodes; o.color_type = src.color_type;
-        for (uint32_t k = 0; k < src.n_nodes; ++k) {
-            const RtKdNode &n = src.nodes[k];
-            if (n.is_leaf) {
-                s->lo[i].push_back(make_float4(n.bmin[0], n.bmin[1], n.bmin[2], u2f(n.first_ref)));
-                s->hi[i].push_back(make_float4(n.bmax[0], n.bmax[1], n.bmax[2], u2f(0x80000000u | n.n_refs)));
-            } else {
-                s->lo[i].push_back(make_float4(n.bmin[0], n.bmin[1], n.bmin[2], u2f(n.skip)));
-                s->hi[i].push_back(make_float4(n.bmax[0], n.bmax[1], n.bmax[2], u2f(0u)));
-            }
-        }
+        o.node_begin = s->pk.node_begin[i]; o.node_end = s->pk.node_end[i]; o.color_type = src.color_type;
         for (uint32_t k = 0; k < src.n_leaf_refs; ++k) {
             const RtTriRef &r = src.leaf_refs[k];
             const TriConst c = precompute_triangle(ld3(src.positions + 3 * r.v[0]), ld3(src.positions + 3 * r.v[1]), ld3(src.positions + 3 * r.v[2]), r.tri_index);
-            s->plane[i].push_back(c.plane);
-            s->edge[i].push_back(c.c0); s->edge[i].push_back(c.e0); s->edge[i].push_back(c.e1);
-            s->den[i].push_back(c.den);
+            s->plane.push_back(c.plane);
+            s->edge.push_back(c.c0); s->edge.push_back(c.e0); s->edge.push_back(c.e1);
+            s->den.push_back(c.den);
         }
-        o.node_lo = s->lo[i].data(); o.node_hi = s->hi[i].data();
-        o.tri_plane = s->plane[i].data(); o.tri_edge = s->edge[i].data(); o.tri_den = s->den[i].data();
         o.triangles = src.triangles; o.vert_colors = src.vert_colors; o.face_colors = src.face_colors;
         s->meshes.push_back(o);
         s->mesh_mat.push_back(to_dmat(src.material));
         s->mesh_tr.push_back(src.material.transparency);
     }
+    d.node_lo = s->pk.lo.data(); d.node_hi = s->pk.hi.data();
+    d.tri_plane = s->plane.data(); d.tri_edge = s->edge.data(); d.tri_den = s->den.data();
     d.meshes = s->meshes.data(); d.mesh_mat = s->mesh_mat.data(); d.mesh_transparency = s->mesh_tr.data();
     return s;
 }
@@ -157,8 +148,21 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         float u, v;
                         const Hit hit = closest_hit<false>(s->d, ray, u, v, nullptr);
                         uint32_t *q = ids + 4 * o;
-                        q[0] = hit.type; q[1] = hit.type ? hit.obj : 0; q[2] = hit.type == 3 ? f2u(s->d.meshes[hit.obj].tri_den[hit.ref].y) : 0; q[3] = f2u(hit.t);
+                        q[0] = hit.type; q[1] = hit.type ? hit.obj : 0; q[2] = hit.type == 3 ? f2u(s->d.tri_den[hit.ref].y) : 0; q[3] = f2u(hit.t);
                     }
+                    if ((p->variant & 0xFF) == 2) {   // the ray-level state machine of k_render_regen, one lane
+                        PathState st;
+                        path_begin(st, ray, rng, 0u, p->max_bounces);
+                        V3 c = v3(0.f);
+                        bool fin = false;
+                        if (p->max_bounces == 0) { c = path_fold(st, v3(0.f)); fin = true; }
+                        while (!fin) {
+                            Hit hit; float hu = 0.f, hv = 0.f; bool blocked;
+                            intersect_ray<false>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
+                            fin = path_advance<false>(s->d, st, hit, hu, hv, blocked, p->nb_ech, c, nullptr);
+                        }
+                        acc = acc + c;
+                    } else
                     acc = acc + trace_path<false>(s->d, ray, rng, p->max_bounces, p->nb_ech, nullptr);
                 }
                 acc = acc / (float)(unsigned int)p->spp;

@@ -98,6 +98,24 @@ def test_ray_known_answers(gpu, assets, name):
     assert (rgb.view(np.uint32) == g["rgb"].view(np.uint32)).all(-1).mean() >= 0.99
 
 
+@pytest.mark.parametrize("name", ["cornell_box", "random_spheres", "flamingo_pond", "backrooms_pool", "rt_in_a_weekend", "config5"])
+def test_kernel_variants_agree_bit_for_bit(gpu, assets, name):
+    """variant 1 = one path per lane to completion; variant 2 = ray-level state machine with path regeneration
+    (threshold 1 and 16); 0 = auto."""
+    g = np.load(os.path.join(GOLDEN, "%s_%dx%dx%d.npz" % (name, W, H, SPP)))
+    s = gpu.Scene(name, aspect=W / H, seed=0)
+    a = s.render(W, H, SPP, seed=0, variant=1, stats=True)
+    b = s.render(W, H, SPP, seed=0, variant=2 | (1 << 8), stats=True)
+    c = s.render(W, H, SPP, seed=0, variant=2 | (16 << 8))
+    d = s.render(W, H, SPP, seed=0, variant=0)
+    assert np.array_equal(a["linear"].view(np.uint32), b["linear"].view(np.uint32))
+    assert np.array_equal(a["linear"].view(np.uint32), c["linear"].view(np.uint32))
+    assert np.array_equal(a["linear"].view(np.uint32), d["linear"].view(np.uint32))
+    assert np.array_equal(b["linear"].view(np.uint32), g["linear"].view(np.uint32))
+    for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
+        assert a["stats"][k] == b["stats"][k], k
+
+
 def test_crop_tiles_and_ranks_do_not_change_pixels(gpu, assets):
     w, h, spp = 200, 120, 3
     s = gpu.Scene("config5", aspect=w / h)

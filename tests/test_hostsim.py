@@ -33,7 +33,8 @@ def sim(hb):
 
 @pytest.mark.parametrize("name", ["cornell_box", "random_spheres", "flamingo_pond", "backrooms_pool", "raccoon",
                                   "rt_in_a_weekend", "flamingo_lake", "config5"])
-def test_core_functions_on_cpu_match_oracle(hb, ref, assets, sim, name):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_core_functions_on_cpu_match_oracle(hb, ref, assets, sim, name, variant):
     W, H, SPP = 64, 36, 2
     a = ref.scene(name, aspect=W / H)
     want = a.render(W, H, SPP, seed=2, threads=0)
@@ -41,7 +42,7 @@ def test_core_functions_on_cpu_match_oracle(hb, ref, assets, sim, name):
     s = hb.Scene(name, aspect=W / H)
     h = sim.sim_scene_create(s.flatten())
     cam = hb.default_camera(W, H)
-    p = hb.render_params(W, H, SPP, seed=2)
+    p = hb.render_params(W, H, SPP, seed=2, variant=variant)
     lin = np.zeros((H, W, 3), np.float32)
     gam = np.zeros((H, W, 3), np.float32)
     ids = np.zeros((H, W, 4), np.uint32)

@@ -207,21 +207,34 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # untimed counting pass: rays / work counters of this rank's shard (deterministic => same as the timed steps)
-    pc = hb.render_params(w, h, spp, seed=0, rank=rank, n_ranks=world, tile=(32, 32), collect_stats=True, variant=args.variant)
-    st = hb.RtStats()
-    rc = hb.rt.rt_render_device(handle, C.byref(cam), C.byref(pc), packed.data_ptr(), None, stream.cuda_stream, C.byref(st))
-    if rc != 0:
-        raise RuntimeError(hb.rt.rt_last_error().decode())
-    my = st.as_dict()
+    # untimed counting passes (deterministic => the same rays as the timed steps):
+    #  A. the timed variant with its counters on, full size: exact ray / sample counts of this rank's shard
+    #  B. the reference-order traversal (variant 1) at <= 4 spp: the ALGORITHMIC work per ray of SURVEY 8(d)
+    #     (spheres, squares, KD nodes and triangles the reference's traversal visits), scaled to the full spp
     keys = ["n_samples", "n_closest_rays", "n_shadow_rays", "n_sphere_tests", "n_square_tests", "n_mesh_tests", "n_node_visits",
             "n_tri_tests", "n_tri_full", "n_tex_fetches", "n_random"]
-    tot = torch.tensor([float(my[k]) for k in keys], dtype=torch.float64, device=dev)
+
+    def count(variant, c_spp):
+        pc = hb.render_params(w, h, c_spp, seed=0, rank=rank, n_ranks=world, tile=(32, 32), collect_stats=True, variant=variant)
+        st = hb.RtStats()
+        rc = hb.rt.rt_render_device(handle, C.byref(cam), C.byref(pc), packed.data_ptr(), None, stream.cuda_stream, C.byref(st))
+        if rc != 0:
+            raise RuntimeError(hb.rt.rt_last_error().decode())
+        return st.as_dict()
+
+    executed = count(args.variant, spp)
+    c_spp = min(spp, 4)
+    alg = count(1, c_spp)
+    scale = (executed["n_closest_rays"] + executed["n_shadow_rays"]) / max(1, alg["n_closest_rays"] + alg["n_shadow_rays"])
+    my = {k: (executed[k] if k in ("n_samples", "n_closest_rays", "n_shadow_rays", "n_random") else int(round(alg[k] * scale))) for k in keys}
+    tot = torch.tensor([float(my[k]) for k in keys] + [float(executed[k]) for k in keys], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot)
-    total = {k: int(v) for k, v in zip(keys, tot.tolist())}
+    total = {k: int(v) for k, v in zip(keys, tot.tolist()[:len(keys)])}
+    total_executed = {k: int(v) for k, v in zip(keys, tot.tolist()[len(keys):])}
     rays, flops, byts = flops_and_bytes(total)
     my_rays, my_flops, my_byts = flops_and_bytes(my)
+    ex_rays, ex_flops, ex_byts = flops_and_bytes(executed)
 
     for _ in range(args.warmup):
         flush.zero_()
@@ -301,6 +314,10 @@ def main():
                  "algorithmic_flops_per_ray": my_flops / max(1, my_rays)},
         "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak,
                 "algorithmic_bytes_per_ray": my_byts / max(1, my_rays)},
+        "executed": {"note": "work the timed variant actually performed (variant 3 culls tests exactly; node/triangle counts are then "
+                             "those of its own hierarchy), same per-test flop/byte figures",
+                     "flops_per_ray": ex_flops / max(1, ex_rays), "bytes_per_ray": ex_byts / max(1, ex_rays),
+                     "tflops": ex_flops / n_launch / (k_ms * 1e-3) / 1e12, "frac_fp32": ex_flops / n_launch / (k_ms * 1e-3) / 1e12 / fp32_unfused},
         "roofline_mrays_per_s": my_rays / max(t_fp, t_mem) / 1e6,
         "frac_of_roofline_rays": (my_rays / (k_ms * 1e-3 * n_launch)) / (my_rays / max(t_fp, t_mem)),
     }
@@ -350,6 +367,7 @@ def main():
         "roofline": roof,
         "cpu_baseline": cpu,
         "work": total,
+        "work_executed": total_executed,
     }
     print(json.dumps(out))
     if world > 1:

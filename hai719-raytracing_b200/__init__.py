@@ -125,7 +125,7 @@ if not (os.path.exists(LIB_RT) and os.path.exists(LIB_HOST)):
     raise ImportError("hai719-raytracing_b200: native libraries not built (%s). Run `make -C %s` or "
                       "`python -c 'import __graft_entry__ as g; g.build()'` — there is no Python fallback." % (LIB_RT, HERE))
 
-rt = C.CDLL(LIB_RT, mode=C.RTLD_GLOBAL)
+rt = C.CDLL(LIB_RT)
 host = C.CDLL(LIB_HOST)
 
 rt.rt_last_error.restype = C.c_char_p

@@ -1,0 +1,249 @@
+// rt_bvh.hpp — host-side construction of the EXACT culling structure used by kernel variant 3.
+//
+// Why this exists. The reference's KD traversal (KDTree.cpp:31-69) enters BOTH children of every
+// node whose box the ray touches, never orders them and never stops early, and its build leaves
+// 30-170-triangle leaves and 3-5x duplicated references: per ray that is ~130 box tests and ~580
+// triangle tests on the pond scene for an answer that depends on a handful of them. The result of
+// that traversal, however, has a closed form:
+//
+//     t*  =  min { t(T) : triangle T is hit by the ray (Triangle::getIntersection, unchanged
+//                         arithmetic) and T lies in at least one leaf whose whole ancestor chain
+//                         of boxes passes AABB::intersects for this ray }
+//
+// (t(T) does not depend on which leaf holds the reference; ties between different triangles go to
+// the last such leaf in depth-first order, first reference inside it.) Variant 3 evaluates exactly
+// that set expression, but finds the candidate triangles with a conventional bounding-volume
+// hierarchy over the mesh's distinct triangles instead of walking the reference tree:
+//   * the BVH only PRUNES — boxes are padded and tested conservatively in fp32, so it can return
+//     extra candidates but never lose a triangle the reference would hit;
+//   * every candidate is tested with the reference's own triangle arithmetic (rt::triangle_t);
+//   * a candidate that would become the new minimum must be REACHABLE in the reference tree.
+//     Almost always its hit parameter lies strictly inside the slab interval of a leaf that holds
+//     it (with a margin far above rounding), which implies every ancestor test passes; otherwise the
+//     ancestor chain is re-tested with the reference's fp64 slab arithmetic (rt::slab_hit).
+// The arrays built here are derived data: they never cross the C ABI and the host KD-tree stays the
+// single source of truth (tests compare variant 3 with the reference-order variants bit for bit).
+#ifndef HAI719_RT_BVH_HPP
+#define HAI719_RT_BVH_HPP
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+#include "hai719_rt.h"
+#include "rt_pack.hpp"
+
+namespace rt {
+
+struct Accel {
+    // BVH, 4 float4 per node: {c0lo.xyz, c0hi.x} {c0hi.yz, c1lo.xy} {c1lo.z, c1hi.xyz} {bits child0, bits child1, -, -}
+    // child >= 0: inner node index; child < 0: leaf, -(child+1) = first*8 + count (count 1..7) into bvh_tris
+    std::vector<float4> nodes;
+    std::vector<uint32_t> tris;          // representative (first) leaf-ref index of each distinct triangle, in BVH leaf order
+    std::vector<int32_t> mesh_root;      // per mesh: root node index, -1 = no hierarchy
+    // per mesh: range of `tris` holding the triangles that are tested for EVERY ray (barycentric test too
+    // ill-conditioned to bound the region it accepts, see build_accel)
+    std::vector<uint32_t> always_first, always_count;
+    // reference-tree bookkeeping for the reachability test
+    std::vector<uint32_t> ref_next;      // per leaf ref: next leaf ref (ascending) of the same triangle, 0xFFFFFFFF = none
+    std::vector<uint32_t> ref_leaf;      // per leaf ref: node index (shared node array) of the leaf holding it
+    std::vector<uint32_t> node_parent;   // per node of the shared node array: parent index, 0xFFFFFFFF for a mesh's synthetic root
+};
+
+namespace bvh_detail {
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; ++a) { lo[a] = FLT_MAX; hi[a] = -FLT_MAX; } }
+    void grow(const float *p) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    void grow(const Box &b) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    float area() const {
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return (dx < 0 || dy < 0 || dz < 0) ? 0.f : 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+struct Prim { Box box; float c[3]; uint32_t ref; };
+
+inline int32_t leaf_code(uint32_t first, uint32_t count) { return -(int32_t)(first * 8u + count) - 1; }
+
+// returns a child code (>= 0 inner node, < 0 leaf). `median` forces balanced splits (depth <= log2 n),
+// used when the SAH tree came out deeper than the device's traversal stack.
+inline int32_t build(std::vector<Prim> &prims, size_t begin, size_t end, Accel &out, bool median, int depth, int &max_depth) {
+    const size_t n = end - begin;
+    max_depth = std::max(max_depth, depth);
+    Box cb; cb.reset();
+    for (size_t i = begin; i < end; ++i) cb.grow(prims[i].c);
+    int axis = 0;
+    float ext = -1.f;
+    for (int a = 0; a < 3; ++a) if (cb.hi[a] - cb.lo[a] > ext) { ext = cb.hi[a] - cb.lo[a]; axis = a; }
+    size_t mid = begin;
+    if (n > 2 && median) {
+        mid = begin + n / 2;
+        std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end,
+                         [&](const Prim &a, const Prim &b) { return a.c[axis] < b.c[axis]; });
+    } else if (n > 2 && ext > 0.f) {
+        // binned SAH on the widest centroid axis
+        const int NB = 16;
+        Box bb[NB]; int bc[NB];
+        for (int b = 0; b < NB; ++b) { bb[b].reset(); bc[b] = 0; }
+        const float k = NB * (1.f - 1e-6f) / ext;
+        for (size_t i = begin; i < end; ++i) {
+            int b = (int)((prims[i].c[axis] - cb.lo[axis]) * k);
+            b = std::max(0, std::min(NB - 1, b));
+            bb[b].grow(prims[i].box); bc[b]++;
+        }
+        float la[NB], ra[NB]; int lc[NB], rc[NB];
+        Box acc; acc.reset(); int cnt = 0;
+        for (int b = 0; b < NB; ++b) { acc.grow(bb[b]); cnt += bc[b]; la[b] = acc.area(); lc[b] = cnt; }
+        acc.reset(); cnt = 0;
+        for (int b = NB - 1; b >= 0; --b) { acc.grow(bb[b]); cnt += bc[b]; ra[b] = acc.area(); rc[b] = cnt; }
+        float best = FLT_MAX; int bs = -1;
+        for (int b = 0; b + 1 < NB; ++b) {
+            if (lc[b] == 0 || rc[b + 1] == 0) continue;
+            const float cost = la[b] * lc[b] + ra[b + 1] * rc[b + 1];
+            if (cost < best) { best = cost; bs = b; }
+        }
+        if (bs >= 0) {
+            auto it = std::partition(prims.begin() + begin, prims.begin() + end, [&](const Prim &p) {
+                int b = (int)((p.c[axis] - cb.lo[axis]) * k);
+                b = std::max(0, std::min(NB - 1, b));
+                return b <= bs;
+            });
+            mid = (size_t)(it - prims.begin());
+        }
+    }
+    if (n <= 2 || ((mid == begin || mid == end) && n <= 7)) {
+        const uint32_t first = (uint32_t)out.tris.size();
+        for (size_t i = begin; i < end; ++i) out.tris.push_back(prims[i].ref);
+        return leaf_code(first, (uint32_t)n);
+    }
+    if (mid == begin || mid == end) {   // all centroids equal but too many for one leaf: split by count
+        mid = begin + n / 2;
+    }
+    const size_t id = out.nodes.size() / 4;
+    out.nodes.resize(out.nodes.size() + 4);
+    Box b0, b1; b0.reset(); b1.reset();
+    for (size_t i = begin; i < mid; ++i) b0.grow(prims[i].box);
+    for (size_t i = mid; i < end; ++i) b1.grow(prims[i].box);
+    const int32_t c0 = build(prims, begin, mid, out, median, depth + 1, max_depth);
+    const int32_t c1 = build(prims, mid, end, out, median, depth + 1, max_depth);
+    out.nodes[4 * id + 0] = make_float4(b0.lo[0], b0.lo[1], b0.lo[2], b0.hi[0]);
+    out.nodes[4 * id + 1] = make_float4(b0.hi[1], b0.hi[2], b1.lo[0], b1.lo[1]);
+    out.nodes[4 * id + 2] = make_float4(b1.lo[2], b1.hi[0], b1.hi[1], b1.hi[2]);
+    out.nodes[4 * id + 3] = make_float4(u2f((uint32_t)c0), u2f((uint32_t)c1), 0.f, 0.f);
+    return (int32_t)id;
+}
+}  // namespace bvh_detail
+
+inline void build_accel(const RtSceneDesc &d, const PackedMeshes &pk, Accel &out) {
+    using namespace bvh_detail;
+    out = Accel();
+    const uint32_t NONE = 0xFFFFFFFFu;
+    out.ref_next.assign(pk.total_refs, NONE);
+    out.ref_leaf.assign(pk.total_refs, NONE);
+    out.node_parent.assign(pk.lo.size(), NONE);
+    for (uint32_t mi = 0; mi < d.n_meshes; ++mi) {
+        const RtSceneMesh &m = d.meshes[mi];
+        // parents and leaf owners from the pre-order array
+        std::vector<uint32_t> stack;
+        for (uint32_t i = pk.node_begin[mi]; i < pk.node_end[mi]; ++i) {
+            const uint32_t hw = f2u(pk.hi[i].w);
+            const bool leaf = (hw & 0x80000000u) != 0u;
+            while (!stack.empty() && f2u(pk.lo[stack.back()].w) <= i) stack.pop_back();
+            out.node_parent[i] = stack.empty() ? NONE : stack.back();
+            if (leaf) {
+                const uint32_t first = f2u(pk.lo[i].w), cnt = hw & 0x7FFFFFFFu;
+                for (uint32_t r = first; r < first + cnt; ++r) out.ref_leaf[r] = i;
+            } else {
+                stack.push_back(i);
+            }
+        }
+        // distinct triangles: chain their references in ascending order
+        const uint32_t rb = pk.ref_begin[mi];
+        std::vector<uint32_t> first_ref(m.n_triangles, NONE), last_ref(m.n_triangles, NONE);
+        for (uint32_t k = 0; k < m.n_leaf_refs; ++k) {
+            const uint32_t T = m.leaf_refs[k].tri_index, r = rb + k;
+            if (first_ref[T] == NONE) first_ref[T] = r; else out.ref_next[last_ref[T]] = r;
+            last_ref[T] = r;
+        }
+        std::vector<Prim> prims;
+        std::vector<uint32_t> always;
+        for (uint32_t T = 0; T < m.n_triangles; ++T) {
+            if (first_ref[T] == NONE) continue;   // dropped by the depth-100 cut-off: never hit (KDTree.cpp:101-103)
+            const RtTriRef &r = m.leaf_refs[first_ref[T] - rb];
+            Prim p; p.box.reset(); p.ref = first_ref[T];
+            bool finite = true;
+            double c[3][3];
+            for (int v = 0; v < 3; ++v) {
+                float q[3];
+                for (int a = 0; a < 3; ++a) { q[a] = 1.000001f * m.positions[3 * r.v[v] + a]; finite = finite && std::isfinite(q[a]); c[v][a] = q[a]; }
+                p.box.grow(q);
+            }
+            if (!finite) continue;                // a NaN/inf vertex can only produce "no intersection"
+            // How far outside the true triangle can a point be and still pass the reference's barycentric
+            // test? u1, u2 are quotients by denom = d00*d11 - d01^2 (Triangle.h:62-75), which cancels
+            // catastrophically for slivers: the slop is ~ eps * kappa * (longest edge), kappa = d00*d11/denom
+            // = 1/sin^2 of the corner angle (measured: 2.8e-4 on a 1.7-long, 4.5-degree sliver of pond.off).
+            double e0[3], e1[3], d00 = 0, d01 = 0, d11 = 0;
+            for (int a = 0; a < 3; ++a) { e0[a] = c[1][a] - c[0][a]; e1[a] = c[2][a] - c[0][a]; d00 += e0[a] * e0[a]; d01 += e0[a] * e1[a]; d11 += e1[a] * e1[a]; }
+            const double denom = d00 * d11 - d01 * d01;
+            // zero area in exact arithmetic (the fp32 inputs are exact in fp64; only the last products round):
+            // identical or collinear corners. If the fp32 cross product is exactly 0 the normal is 0/0 = NaN and
+            // every test fails; if rounding leaves a residue the plane is garbage but finite, so
+            // such a triangle goes to the always-tested list rather than being dropped.
+            if (!(denom > 0.0)) {
+                // the device's own fp32 arithmetic (precompute_triangle), replayed on the host without FMA
+                const float fe0[3] = {(float)c[1][0] - (float)c[0][0], (float)c[1][1] - (float)c[0][1], (float)c[1][2] - (float)c[0][2]};
+                const float fe1[3] = {(float)c[2][0] - (float)c[0][0], (float)c[2][1] - (float)c[0][1], (float)c[2][2] - (float)c[0][2]};
+                const volatile float m0 = fe0[1] * fe1[2], m1 = fe0[2] * fe1[1], m2 = fe0[2] * fe1[0], m3 = fe0[0] * fe1[2],
+                                     m4 = fe0[0] * fe1[1], m5 = fe0[1] * fe1[0];
+                const float nx = m0 - m1, ny = m2 - m3, nz = m4 - m5;
+                if (nx == 0.f && ny == 0.f && nz == 0.f) continue;   // n = 0/0 = NaN: dotRN < 0 is never true
+                always.push_back(p.ref);
+                continue;
+            }
+            const double kappa = d00 * d11 / denom;
+            const double lmax = std::sqrt(std::max(d00, d11));
+            // error analysis of u1 = (d11*d20 - d01*d21)/denom in fp32 gives <= ~36 eps kappa lmax of spatial
+            // slop; 128 leaves a 3.5x margin. Beyond kappa = 1e5 the fp32 denominator has lost most of its
+            // bits (its sign can flip near 1e7) and the accepted region is not usefully bounded: those few
+            // triangles (<= 8 per mesh in the reference's assets) are simply tested for every ray.
+            if (!(kappa <= 1e5)) { always.push_back(p.ref); continue; }
+            const double slop = 128.0 * 5.96e-8 * kappa * lmax;
+            for (int a = 0; a < 3; ++a) {
+                // + hundreds of ulps of the coordinates involved, plus an absolute floor
+                const float pad = (float)slop + 1e-4f * (std::fabs(p.box.lo[a]) + std::fabs(p.box.hi[a]) + (p.box.hi[a] - p.box.lo[a])) + 1e-5f;
+                p.box.lo[a] -= pad; p.box.hi[a] += pad;
+                p.c[a] = 0.5f * (p.box.lo[a] + p.box.hi[a]);
+            }
+            prims.push_back(p);
+        }
+        out.always_first.push_back((uint32_t)out.tris.size());
+        out.always_count.push_back((uint32_t)always.size());
+        out.tris.insert(out.tris.end(), always.begin(), always.end());
+        if (prims.empty()) { out.mesh_root.push_back(-1); continue; }
+        const size_t nodes_mark = out.nodes.size(), tris_mark = out.tris.size();
+        int max_depth = 0;
+        int32_t root = build(prims, 0, prims.size(), out, false, 0, max_depth);
+        if (max_depth > 56) {   // device stack holds 64 entries
+            out.nodes.resize(nodes_mark); out.tris.resize(tris_mark);
+            max_depth = 0;
+            root = build(prims, 0, prims.size(), out, true, 0, max_depth);
+        }
+        if (root >= 0) {
+            out.mesh_root.push_back(root);
+        } else {
+            // a mesh so small that it is a single leaf: wrap it in a node whose second child is empty
+            Box b; b.reset();
+            for (const Prim &p : prims) b.grow(p.box);
+            const size_t id = out.nodes.size() / 4;
+            out.nodes.push_back(make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]));
+            out.nodes.push_back(make_float4(b.hi[1], b.hi[2], FLT_MAX, FLT_MAX));
+            out.nodes.push_back(make_float4(FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX));
+            out.nodes.push_back(make_float4(u2f((uint32_t)root), u2f((uint32_t)leaf_code(0, 0)), 0.f, 0.f));
+            out.mesh_root.push_back((int32_t)id);
+        }
+    }
+}
+
+}  // namespace rt
+#endif

@@ -23,6 +23,7 @@
 #include "hai719_rt.h"
 #include "rt_core.cuh"
 #include "rt_pack.hpp"
+#include "rt_bvh.hpp"
 
 using namespace rt;
 
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(128, 4) k_render_paths(const DScene scene, con
 // lane intersects ONE ray (closest-hit or shadow sample) and advances its path; a lane whose path
 // has ended takes the next path index from the global counter (one warp-aggregated atomicAdd,
 // __ballot_sync/__popc ranks). Lanes stay busy whatever the depth at which their paths end.
-template <bool STATS>
+template <bool STATS, bool ACCEL>
 __global__ void __launch_bounds__(128, 4) k_render_regen(const DScene scene, const DCamera cam, const RenderArgs a) {
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(128, 4) k_render_regen(const DScene scene, con
         Hit h;
         float hu = 0.f, hv = 0.f;
         bool blocked;
-        intersect_ray<STATS>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
+        intersect_ray<STATS, ACCEL>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
         if (st.mode != 2) {
             V3 c;
             if (path_advance<STATS>(scene, st, h, hu, hv, blocked, a.nb_ech, c, &cnt)) {
@@ -611,6 +612,13 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
         if ((rc = dev_alloc(s, (size_t)3 * pk.total_refs, &ed))) return rc;
         if ((rc = dev_alloc(s, (size_t)pk.total_refs, &dn))) return rc;
         d.tri_plane = pl; d.tri_edge = ed; d.tri_den = dn;
+        Accel ac;
+        build_accel(*desc, pk, ac);
+        if ((rc = dev_upload(s, ac.nodes.data(), ac.nodes.size(), &d.bvh_nodes))) return rc;
+        if ((rc = dev_upload(s, ac.tris.data(), ac.tris.size(), &d.bvh_tris))) return rc;
+        if ((rc = dev_upload(s, ac.ref_next.data(), ac.ref_next.size(), &d.ref_next))) return rc;
+        if ((rc = dev_upload(s, ac.ref_leaf.data(), ac.ref_leaf.size(), &d.ref_leaf))) return rc;
+        if ((rc = dev_upload(s, ac.node_parent.data(), ac.node_parent.size(), &d.node_parent))) return rc;
         std::vector<DMesh> dm(desc->n_meshes);
         std::vector<DMaterial> m(desc->n_meshes);
         std::vector<float> tr(desc->n_meshes);
@@ -621,6 +629,7 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
             memset(&o, 0, sizeof o);
             o.node_begin = pk.node_begin[i];
             o.node_end = pk.node_end[i];
+            o.bvh_root = ac.mesh_root[i]; o.always_first = ac.always_first[i]; o.always_count = ac.always_count[i];
             o.color_type = src.color_type;
             if ((rc = dev_upload(s, src.triangles, (size_t)3 * src.n_triangles, &o.triangles))) return rc;
             if (src.color_type == RT_COLOR_VERTEX && (rc = dev_upload(s, src.vert_colors, (size_t)3 * src.n_vertices, &o.vert_colors))) return rc;
@@ -685,12 +694,13 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     // variant: low byte = kernel (0 auto, 1 k_render_paths: one path per lane to completion,
     // 2 k_render_regen: ray-level state machine with path regeneration and warp-voted KD traversal);
     // bits 8..15 = regeneration threshold of kernel 2 (idle lanes needed before a refill; 0 = 16)
-    if (p->variant < 0 || (p->variant & 0xFF) > 2 || (p->variant >> 16)) return fail(RT_ERR_INVALID, "unknown kernel variant");
+    if (p->variant < 0 || (p->variant & 0xFF) > 3 || (p->variant >> 16)) return fail(RT_ERR_INVALID, "unknown kernel variant");
     int kind = p->variant & 0xFF;
-    if (kind == 0) kind = (s->d.n_meshes > 0 && s->d.n_lights > 0) ? 2 : 1;   // measured: profiles/r01_variants.md
-    const bool regen = kind == 2;
-    const void *kern = regen ? (want_stats ? (const void *)k_render_regen<true> : (const void *)k_render_regen<false>)
-                             : (want_stats ? (const void *)k_render_paths<true> : (const void *)k_render_paths<false>);
+    if (kind == 0) kind = s->d.n_meshes > 0 ? 3 : 1;   // measured: profiles/r01_variants.md
+    const bool regen = kind >= 2, accel = kind == 3;
+    const void *kern = accel   ? (want_stats ? (const void *)k_render_regen<true, true> : (const void *)k_render_regen<false, true>)
+                       : regen ? (want_stats ? (const void *)k_render_regen<true, false> : (const void *)k_render_regen<false, false>)
+                               : (want_stats ? (const void *)k_render_paths<true> : (const void *)k_render_paths<false>);
     const int grid = persistent_grid(s, kern, 128);
 
     RenderArgs a{};
@@ -708,9 +718,12 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
         if (pb) RT_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long), st));
         const unsigned long long batches = (a.n_paths + 31) / 32;
         const int g = (int)std::min<unsigned long long>((unsigned long long)grid, (batches + 3) / 4);
-        if (regen) {
-            if (want_stats) k_render_regen<true><<<g, 128, 0, st>>>(s->d, cam, a);
-            else k_render_regen<false><<<g, 128, 0, st>>>(s->d, cam, a);
+        if (accel) {
+            if (want_stats) k_render_regen<true, true><<<g, 128, 0, st>>>(s->d, cam, a);
+            else k_render_regen<false, true><<<g, 128, 0, st>>>(s->d, cam, a);
+        } else if (regen) {
+            if (want_stats) k_render_regen<true, false><<<g, 128, 0, st>>>(s->d, cam, a);
+            else k_render_regen<false, false><<<g, 128, 0, st>>>(s->d, cam, a);
         } else {
             if (want_stats) k_render_paths<true><<<g, 128, 0, st>>>(s->d, cam, a);
             else k_render_paths<false><<<g, 128, 0, st>>>(s->d, cam, a);

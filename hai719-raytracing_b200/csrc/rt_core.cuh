@@ -139,6 +139,8 @@ struct DSquare {            // per-square constants of Square::intersect hoisted
 // links and leaf ranges already offset into the shared arrays. An empty tree owns an empty range.
 struct DMesh {
     uint32_t node_begin, node_end;
+    int bvh_root;              // variant 3 (rt_bvh.hpp): root of this mesh's culling BVH, -1 = none
+    uint32_t always_first, always_count;   // range of bvh_tris tested for every ray (ill-conditioned triangles)
     int color_type;
     const float *vert_colors, *face_colors;
     const uint32_t *triangles;
@@ -157,6 +159,10 @@ struct DScene {
     const float4 *tri_plane;   // per leaf ref: {n.xyz, D = c0.n}
     const float4 *tri_edge;    // per leaf ref, 3 entries: {c0.xyz, d00}, {e0.xyz, d01}, {e1.xyz, d11}
     const float2 *tri_den;     // per leaf ref: {denom, bits(tri_index within its mesh)}
+    // exact culling structure of variant 3 (rt_bvh.hpp)
+    const float4 *bvh_nodes;   // 4 per node
+    const uint32_t *bvh_tris;  // representative leaf ref per distinct triangle, BVH leaf order
+    const uint32_t *ref_next, *ref_leaf, *node_parent;
     const DMaterial *sph_mat, *sq_mat, *mesh_mat;
     const DLight *lights;
     const DImage *textures, *normal_maps;
@@ -345,6 +351,138 @@ RT_HD bool mesh_closest(const Ray &ray, const RayInv &inv, const DScene &s, cons
         ++i;
     }
     if (best_ref == 0xFFFFFFFFu) return false;
+    t_out = best_t;
+    ref_out = best_ref;
+    return true;
+}
+
+// ---- mesh: exact culling traversal (variant 3, construction and proof sketch in rt_bvh.hpp) ------
+// Is the leaf that holds reference r reachable by the reference's traversal for this ray, given that
+// the triangle was hit at parameter t?  Fast accept: t lies strictly inside the slab interval of
+// the leaf's box on every axis, with a margin (1e-5 relative to the slab parameters + 1e-6) far above
+// the rounding of either arithmetic, and t > 1e-3 >> EPSILON: then for the leaf and for every
+// ancestor (whose boxes contain it) AABB::intersects keeps tmin < t < tmax at every step and
+// returns true. Anything else — grazing, axis-parallel, tiny t — re-runs the reference's own fp64
+// slab test (slab_hit) up the parent chain, synthetic root (= KDTree::aabb gate) included.
+RT_HD bool leaf_reachable(const DScene &s, const Ray &ray, float t, uint32_t leaf) {
+    const float4 lo = RT_LDG(s.node_lo + leaf), hi = RT_LDG(s.node_hi + leaf);
+    bool ok = t > 1e-3f;
+    {
+        const float ix = 1.f / ray.d.x, iy = 1.f / ray.d.y, iz = 1.f / ray.d.z;
+        const float a0 = (lo.x - ray.o.x) * ix, a1 = (hi.x - ray.o.x) * ix;
+        const float b0 = (lo.y - ray.o.y) * iy, b1 = (hi.y - ray.o.y) * iy;
+        const float c0 = (lo.z - ray.o.z) * iz, c1 = (hi.z - ray.o.z) * iz;
+        const float ma = 1e-5f * (fabsf(a0) + fabsf(a1)) + 1e-6f, mb = 1e-5f * (fabsf(b0) + fabsf(b1)) + 1e-6f,
+                    mc = 1e-5f * (fabsf(c0) + fabsf(c1)) + 1e-6f;
+        ok = ok && (fminr(a0, a1) + ma < t) && (t < fmaxr(a0, a1) - ma);
+        ok = ok && (fminr(b0, b1) + mb < t) && (t < fmaxr(b0, b1) - mb);
+        ok = ok && (fminr(c0, c1) + mc < t) && (t < fmaxr(c0, c1) - mc);
+    }
+    if (ok) return true;
+    const RayInv inv = make_inv(ray);
+    uint32_t n = leaf;
+    while (n != 0xFFFFFFFFu) {
+        const float4 l = RT_LDG(s.node_lo + n), h = RT_LDG(s.node_hi + n);
+        if (!slab_hit(ray, inv, l.x, l.y, l.z, h.x, h.y, h.z)) return false;
+        n = RT_LDG(s.node_parent + n);
+    }
+    return true;
+}
+// first reachable reference of the triangle whose references start at r0, or NONE
+RT_HD uint32_t tri_first_reachable(const DScene &s, const Ray &ray, float t, uint32_t r0) {
+    for (uint32_t r = r0; r != 0xFFFFFFFFu; r = RT_LDG(s.ref_next + r))
+        if (leaf_reachable(s, ray, t, RT_LDG(s.ref_leaf + r))) return r;
+    return 0xFFFFFFFFu;
+}
+// last reachable reference (decides ties between different triangles at the same t)
+RT_HD uint32_t tri_last_reachable(const DScene &s, const Ray &ray, float t, uint32_t r0) {
+    uint32_t last = 0xFFFFFFFFu;
+    for (uint32_t r = r0; r != 0xFFFFFFFFu; r = RT_LDG(s.ref_next + r))
+        if (leaf_reachable(s, ray, t, RT_LDG(s.ref_leaf + r))) last = r;
+    return last;
+}
+
+struct Inv32 { float x, y, z; };
+RT_HD float safe_inv(float d) { return fabsf(d) > 1e-30f ? 1.f / d : (d < 0.f ? -1e30f : 1e30f); }
+// conservative ray/box overlap on [0, limit]; returns the entry parameter through `near`
+RT_HD bool bvh_box(const Ray &r, const Inv32 &iv, float lx, float ly, float lz, float hx, float hy, float hz, float limit, float &near) {
+    const float a0 = (lx - r.o.x) * iv.x, a1 = (hx - r.o.x) * iv.x;
+    const float b0 = (ly - r.o.y) * iv.y, b1 = (hy - r.o.y) * iv.y;
+    const float c0 = (lz - r.o.z) * iv.z, c1 = (hz - r.o.z) * iv.z;
+    const float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fminf(c0, c1));
+    const float tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fmaxf(c0, c1));
+    const float slack = 1e-5f * (fabsf(tn) + fabsf(tf)) + 1e-6f;
+    near = tn;
+    return (tn - slack <= tf + slack) && (tf + slack >= 0.f) && (tn - slack <= limit);
+}
+
+// Closest reachable hit of mesh m with t < limit (limit = the scene's current best / the light
+// distance, exactly the bound Scene::computeIntersection / computeShadow apply to the mesh's
+// answer). Same (t, triangle) as mesh_closest() whenever that answer would be accepted.
+// One candidate triangle (first reference r0) against the running minimum.
+template <bool STATS>
+RT_HD void bvh_consider(const Ray &ray, const DScene &s, uint32_t r0, float &best_t, uint32_t &best_ref, Counters *cnt) {
+    const uint32_t NONE = 0xFFFFFFFFu;
+    float a, b, c;
+    if (STATS) cnt->tri++;
+    const float t = triangle_t<STATS>(ray, s, r0, a, b, c, cnt);
+    if (t < best_t) {
+        if (tri_first_reachable(s, ray, t, r0) != NONE) { best_t = t; best_ref = r0; }
+    } else if (t == best_t && best_ref != NONE && r0 != best_ref) {
+        // two different triangles at the same parameter: the reference keeps the one in the LAST
+        // reachable leaf (KDTree.cpp:63-67), the FIRST reference inside a shared leaf (:42)
+        const uint32_t ln = tri_last_reachable(s, ray, t, r0);
+        if (ln != NONE) {
+            const uint32_t lb = tri_last_reachable(s, ray, t, best_ref);
+            const bool same_leaf = RT_LDG(s.ref_leaf + ln) == RT_LDG(s.ref_leaf + lb);
+            if (same_leaf ? (ln < lb) : (ln > lb)) best_ref = r0;
+        }
+    }
+}
+
+// Closest reachable hit of mesh m with t < limit (limit = the scene's current best / the light
+// distance, exactly the bound Scene::computeIntersection / computeShadow apply to the mesh's
+// answer). Same (t, triangle) as mesh_closest() whenever that answer would be accepted.
+template <bool STATS>
+RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, float limit, float &t_out, uint32_t &ref_out, Counters *cnt) {
+    const uint32_t NONE = 0xFFFFFFFFu;
+    float best_t = limit;
+    uint32_t best_ref = NONE;
+    for (uint32_t k = m.always_first; k < m.always_first + m.always_count; ++k)
+        bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+    if (m.bvh_root >= 0) {
+        Inv32 iv; iv.x = safe_inv(ray.d.x); iv.y = safe_inv(ray.d.y); iv.z = safe_inv(ray.d.z);
+        int stack[64];
+        int sp = 0;
+        int node = m.bvh_root;
+        for (;;) {
+            if (node >= 0) {
+                const float4 n0 = RT_LDG(s.bvh_nodes + 4 * node), n1 = RT_LDG(s.bvh_nodes + 4 * node + 1),
+                             n2 = RT_LDG(s.bvh_nodes + 4 * node + 2), n3 = RT_LDG(s.bvh_nodes + 4 * node + 3);
+                if (STATS) cnt->node++;
+                float d0, d1;
+                const bool h0 = bvh_box(ray, iv, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, best_t, d0);
+                const bool h1 = bvh_box(ray, iv, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, best_t, d1);
+                const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
+                if (h0 && h1) {
+                    const bool swap = d1 < d0;
+                    node = swap ? c1 : c0;
+                    stack[sp++] = swap ? c0 : c1;    // depth <= 56 by construction (rt_bvh.hpp)
+                    continue;
+                }
+                if (h0) { node = c0; continue; }
+                if (h1) { node = c1; continue; }
+            } else {
+                const uint32_t code = (uint32_t)(-(node + 1));
+                const uint32_t first = code >> 3, count = code & 7u;
+                for (uint32_t k = first; k < first + count; ++k)
+                    bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    if (best_ref == NONE) return false;
     t_out = best_t;
     ref_out = best_ref;
     return true;
@@ -673,7 +811,7 @@ struct PathState {
 // (h, hu, hv). mode 1: `blocked` is computeShadow's return value; candidates draw from rng in the
 // reference's order (spheres, squares, meshes) until one blocks. Lanes that have their answer
 // (blocked, or idle) skip the tests; the loops end early only when the whole warp is done.
-template <bool STATS>
+template <bool STATS, bool ACCEL>
 RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_light, Rng &rng, Hit &h, float &hu, float &hv,
                          bool &blocked, Counters *cnt) {
     h.type = 0; h.obj = -1; h.t = (mode == 0) ? FLT_MAX : t_light; h.ref = 0;
@@ -703,7 +841,18 @@ RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_ligh
             else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.sq_transparency + i)) { blocked = true; done = true; } }
         }
     }
-    if (s.n_meshes > 0) {
+    if (ACCEL) {
+        // variant 3: per-mesh exact culling traversal (mesh_closest_bvh), same acceptance rules
+        for (int i = 0; i < s.n_meshes; ++i) {
+            if (done) break;
+            if (STATS) cnt->mesh++;
+            float t; uint32_t ref;
+            if (mesh_closest_bvh<STATS>(ray, s, s.meshes[i], h.t, t, ref, cnt) && t < h.t && t > RT_EPSF) {
+                if (mode == 0) { h.type = 3; h.obj = i; h.t = t; h.ref = ref; }
+                else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.mesh_transparency + i)) { blocked = true; done = true; } }
+            }
+        }
+    } else if (s.n_meshes > 0) {
         // Every lane walks the shared pre-order node array with its own ray: mesh after mesh, node
         // after node, and inside a leaf triangle after triangle. A lane is always in one of two
         // states — "next step is a triangle test" or "next step is a node (box test / leaf open /

@@ -15,6 +15,10 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+/* the libraries are built with -fvisibility=hidden: only what is declared here is exported */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 typedef struct HaiScene HaiScene;
 
@@ -51,6 +55,9 @@ void hai_scene_invalidate_device(HaiScene *s);
 int hai_ray_trace_from_camera(HaiScene *s, int device, int w, int h, int nsamples, uint32_t seed, const char *ppm_path,
                               float *gamma_rgb);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,10 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+/* the libraries are built with -fvisibility=hidden: only what is declared here is exported */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 #define HAI719_RT_ABI_VERSION 1
 
@@ -250,6 +254,9 @@ int rt_shade_rays(RtScene *scene, size_t n, const float *origins, const float *d
  * figure, so bench.py takes its roofline denominator from here. */
 int rt_measure_fp32_peak(int device, double *unfused_tflops, double *fused_tflops);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@
 #include "hai719_rt.h"
 #include "rt_core.cuh"
 #include "rt_pack.hpp"
+#include "rt_bvh.hpp"
 
 using namespace rt;
 
@@ -28,6 +29,7 @@ struct SimScene {
     std::vector<DImage> tex, nrm;
     std::vector<DMesh> meshes;
     PackedMeshes pk;
+    Accel ac;
     std::vector<float4> plane, edge;
     std::vector<float2> den;
 };
@@ -87,11 +89,15 @@ void *sim_scene_create(const RtSceneDesc *desc) {
     d.lights = s->lights.data();
     const uint32_t nm = desc->n_meshes;
     if (!pack_meshes(*desc, s->pk).empty()) { delete s; return nullptr; }
+    build_accel(*desc, s->pk, s->ac);
+    d.bvh_nodes = s->ac.nodes.data(); d.bvh_tris = s->ac.tris.data();
+    d.ref_next = s->ac.ref_next.data(); d.ref_leaf = s->ac.ref_leaf.data(); d.node_parent = s->ac.node_parent.data();
     for (uint32_t i = 0; i < nm; ++i) {
         const RtSceneMesh &src = desc->meshes[i];
         DMesh o;
         memset(&o, 0, sizeof o);
         o.node_begin = s->pk.node_begin[i]; o.node_end = s->pk.node_end[i]; o.color_type = src.color_type;
+        o.bvh_root = s->ac.mesh_root[i]; o.always_first = s->ac.always_first[i]; o.always_count = s->ac.always_count[i];
         for (uint32_t k = 0; k < src.n_leaf_refs; ++k) {
             const RtTriRef &r = src.leaf_refs[k];
             const TriConst c = precompute_triangle(ld3(src.positions + 3 * r.v[0]), ld3(src.positions + 3 * r.v[1]), ld3(src.positions + 3 * r.v[2]), r.tri_index);
@@ -150,7 +156,8 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         uint32_t *q = ids + 4 * o;
                         q[0] = hit.type; q[1] = hit.type ? hit.obj : 0; q[2] = hit.type == 3 ? f2u(s->d.tri_den[hit.ref].y) : 0; q[3] = f2u(hit.t);
                     }
-                    if ((p->variant & 0xFF) == 2) {   // the ray-level state machine of k_render_regen, one lane
+                    if ((p->variant & 0xFF) >= 2) {   // the ray-level state machine of k_render_regen, one lane
+                        const bool accel = (p->variant & 0xFF) == 3;
                         PathState st;
                         path_begin(st, ray, rng, 0u, p->max_bounces);
                         V3 c = v3(0.f);
@@ -158,7 +165,8 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         if (p->max_bounces == 0) { c = path_fold(st, v3(0.f)); fin = true; }
                         while (!fin) {
                             Hit hit; float hu = 0.f, hv = 0.f; bool blocked;
-                            intersect_ray<false>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
+                            if (accel) intersect_ray<false, true>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
+                            else intersect_ray<false, false>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
                             fin = path_advance<false>(s->d, st, hit, hu, hv, blocked, p->nb_ech, c, nullptr);
                         }
                         acc = acc + c;

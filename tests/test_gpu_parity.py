@@ -100,20 +100,53 @@ def test_ray_known_answers(gpu, assets, name):
 
 @pytest.mark.parametrize("name", ["cornell_box", "random_spheres", "flamingo_pond", "backrooms_pool", "rt_in_a_weekend", "config5"])
 def test_kernel_variants_agree_bit_for_bit(gpu, assets, name):
-    """variant 1 = one path per lane to completion; variant 2 = ray-level state machine with path regeneration
-    (threshold 1 and 16); 0 = auto."""
+    """variant 1 = one path per lane to completion; 2 = ray-level state machine with path regeneration (threshold
+    1 and 16) walking the reference's KD order; 3 = the same with the exact culling hierarchy; 0 = auto."""
     g = np.load(os.path.join(GOLDEN, "%s_%dx%dx%d.npz" % (name, W, H, SPP)))
     s = gpu.Scene(name, aspect=W / H, seed=0)
     a = s.render(W, H, SPP, seed=0, variant=1, stats=True)
     b = s.render(W, H, SPP, seed=0, variant=2 | (1 << 8), stats=True)
     c = s.render(W, H, SPP, seed=0, variant=2 | (16 << 8))
     d = s.render(W, H, SPP, seed=0, variant=0)
+    e = s.render(W, H, SPP, seed=0, variant=3, stats=True)
+    assert np.array_equal(a["linear"].view(np.uint32), e["linear"].view(np.uint32))
+    for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
+        assert a["stats"][k] == e["stats"][k], k
     assert np.array_equal(a["linear"].view(np.uint32), b["linear"].view(np.uint32))
     assert np.array_equal(a["linear"].view(np.uint32), c["linear"].view(np.uint32))
     assert np.array_equal(a["linear"].view(np.uint32), d["linear"].view(np.uint32))
     assert np.array_equal(b["linear"].view(np.uint32), g["linear"].view(np.uint32))
     for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
         assert a["stats"][k] == b["stats"][k], k
+
+
+@pytest.mark.parametrize("name,w,h,spp", [("flamingo_pond", 480, 270, 4), ("backrooms_pool", 480, 270, 8), ("raccoon", 480, 270, 4),
+                                          ("config5", 480, 270, 8), ("flamingo", 480, 270, 2), ("mesh", 480, 270, 4)])
+def test_exact_culling_equals_reference_order(gpu, assets, name, w, h, spp):
+    """Variant 3 never walks the reference's KD-tree; it must still pick the same triangle at the same t for every
+    ray of every bounce (depth-100 trees, dropped triangles, NaN normals, transparent shadow casters included)."""
+    s = gpu.Scene(name, aspect=w / h, seed=2)
+    a = s.render(w, h, spp, seed=8, variant=1)
+    b = s.render(w, h, spp, seed=8, variant=3)
+    assert np.array_equal(a["linear"].view(np.uint32), b["linear"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name,w,h,spp", [("flamingo_pond", 1600, 900, 4), ("backrooms_pool", 1600, 900, 8), ("config5", 1600, 900, 4),
+                                          ("raccoon", 1280, 720, 4), ("flamingo_lake", 1280, 720, 2)])
+def test_exact_culling_at_scale(gpu, assets, name, w, h, spp):
+    """Tens of millions of rays per scene: the culled traversal (variant 3) against the reference-order traversal
+    (variant 1). Images must be bit-identical and the ray / random-draw counters equal — one wrong hit anywhere
+    changes the continuation of its path and therefore the counts (this is how a 1-in-1e8 miss was caught:
+    profiles/r01_notes.md, 'sliver triangles')."""
+    s = gpu.Scene(name, aspect=w / h, seed=0)
+    a = s.render(w, h, spp, seed=21, variant=1, stats=True)
+    b = s.render(w, h, spp, seed=21, variant=3, stats=True)
+    for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
+        assert a["stats"][k] == b["stats"][k], (k, a["stats"][k], b["stats"][k])
+    diff = (a["linear"].view(np.uint32) != b["linear"].view(np.uint32)).any(-1)
+    assert not diff.any(), np.argwhere(diff)[:8]
+    print(name, "rays %d, reference-order %.0f ms, culled %.0f ms" % (a["stats"]["n_closest_rays"] + a["stats"]["n_shadow_rays"],
+                                                                   a["stats"]["kernel_ms"], b["stats"]["kernel_ms"]))
 
 
 def test_crop_tiles_and_ranks_do_not_change_pixels(gpu, assets):

@@ -236,13 +236,13 @@ def main():
     my_rays, my_flops, my_byts = flops_and_bytes(my)
     ex_rays, ex_flops, ex_byts = flops_and_bytes(executed)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # started before the warm-up so that nvidia-smi's own start-up is over when timing begins
     for _ in range(args.warmup):
         flush.zero_()
         render_step()
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kst = hb.RtStats()
     kernel_ms = 0.0

@@ -115,7 +115,7 @@ class RtStats(C.Structure):
 
 # every symbol the two headers declare — tests check the libraries export exactly these
 RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy",
-              "rt_scene_device_bytes", "rt_render_pixel_count", "rt_render", "rt_render_device", "rt_untile_device",
+              "rt_scene_device_bytes", "rt_render_pixel_count", "rt_tile_layout", "rt_render", "rt_render_device", "rt_untile_device",
               "rt_trace_primary", "rt_trace_rays", "rt_shade_rays", "rt_measure_fp32_peak"]
 HOST_SYMBOLS = ["hai_last_error", "hai_scene_new", "hai_scene_free", "hai_scene_setup", "hai_scene_dump",
                 "hai_scene_flatten", "hai_scene_kd_stats", "hai_scene_counts", "hai_default_camera", "hai_render",
@@ -135,6 +135,8 @@ rt.rt_scene_device_bytes.restype = C.c_size_t
 rt.rt_scene_device_bytes.argtypes = [C.c_void_p]
 rt.rt_render_pixel_count.restype = C.c_int64
 rt.rt_render_pixel_count.argtypes = [C.POINTER(RtRenderParams)]
+rt.rt_tile_layout.restype = C.c_int64
+rt.rt_tile_layout.argtypes = [C.POINTER(RtRenderParams), C.c_void_p, C.c_int64]
 rt.rt_render.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p,
                          C.POINTER(RtStats)]
 rt.rt_render_device.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p,
@@ -199,6 +201,16 @@ def render_params(width, height, spp, max_bounces=6, nb_ech=10, seed=0, crop=Non
     p.rank, p.n_ranks, p.tile_w, p.tile_h = rank, n_ranks, tile[0], tile[1]
     p.collect_stats, p.variant = int(collect_stats), variant
     return p
+
+
+def tile_layout(params):
+    """(n, 4) int32 array {x0, y0, w, h} of the tiles `params.rank` renders, in packed order (host arithmetic only)."""
+    n = rt.rt_tile_layout(C.byref(params), None, 0)
+    if n < 0:
+        raise RtError(-1, rt.rt_last_error().decode(errors="replace"))
+    out = np.zeros((n, 4), np.int32)
+    rt.rt_tile_layout(C.byref(params), out.ctypes.data, n)
+    return out
 
 
 def default_camera(width, height):

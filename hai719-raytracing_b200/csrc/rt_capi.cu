@@ -666,6 +666,19 @@ int64_t rt_render_pixel_count(const RtRenderParams *p) {
     return (int64_t)off.back();
 }
 
+int64_t rt_tile_layout(const RtRenderParams *p, int32_t *out, int64_t cap) {
+    if (!p) return -1;
+    Rect r;
+    if (resolve_rect(*p, r)) return -1;
+    std::vector<TileRec> tiles; std::vector<unsigned int> off;
+    build_tiles(*p, r, tiles, off);
+    if (out)
+        for (int64_t i = 0; i < (int64_t)tiles.size() && i < cap; ++i) {
+            out[4 * i] = tiles[i].x0; out[4 * i + 1] = tiles[i].y0; out[4 * i + 2] = tiles[i].w; out[4 * i + 3] = tiles[i].h;
+        }
+    return (int64_t)tiles.size();
+}
+
 int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p, float *d_gamma, float *d_linear,
                      void *cuda_stream, RtStats *stats) {
     if (!s || !camera || !p) return fail(RT_ERR_INVALID, "null argument");

@@ -212,6 +212,10 @@ size_t rt_scene_device_bytes(const RtScene *scene);
  * element count / 3 of the packed output of rt_render_device(). */
 int64_t rt_render_pixel_count(const RtRenderParams *params);
 
+/* The tiles this rank renders under `params`, in packed order: 4 ints per tile {x0, y0, w, h} in full-image
+ * pixel coordinates. tiles == NULL returns the count. No device needed (host arithmetic only). */
+int64_t rt_tile_layout(const RtRenderParams *params, int32_t *tiles, int64_t cap_tiles);
+
 /* Drop-in for the render part of ray_trace_from_camera(): HOST output buffers.
  * gamma_rgb  : rect_h*rect_w*3 floats, row-major, after gamma_correct (the reference's `image`).
  * linear_rgb : same shape, the value before gamma (sum/nsamples); may be NULL.

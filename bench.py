@@ -55,45 +55,88 @@ def flops_and_bytes(st):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled every 200 ms while the timed region runs.
+
+    Uses NVML in-process (nvidia_ml_py): two cheap queries per sample. An `nvidia-smi -lms 200` child, as in the
+    profiling recipe, was measured to add 50-200 ms of launch/synchronise latency to EVERY ~190 ms step here
+    (kernel time 184.1 ms, step time 241-390 ms: profiles/r01_notes.md), so it is only the fallback."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = threading.Event()
+        self.thread = None
         self.proc = None
-        self.lines = []
+        self.how = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+            except Exception:
+                pass
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.how = "nvml"
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for bit, name in self.REASONS.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(0.2)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.how = "nvidia-smi"
+            q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                threading.Thread(target=self._pump, daemon=True).start()
+            except OSError:
+                self.proc = None
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                self.sm.append(float(f[1])); self.mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def stop(self):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=1.0)
         if self.proc:
             time.sleep(0.25)
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
 
 
 def run_reference(args, wl):
@@ -236,13 +279,13 @@ def main():
     my_rays, my_flops, my_byts = flops_and_bytes(my)
     ex_rays, ex_flops, ex_byts = flops_and_bytes(executed)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()          # started before the warm-up so that nvidia-smi's own start-up is over when timing begins
     for _ in range(args.warmup):
         flush.zero_()
         render_step()
+    sampler = ClockSampler(local)
     barrier()
+    if rank == 0:
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kst = hb.RtStats()
     kernel_ms = 0.0
@@ -253,6 +296,8 @@ def main():
         render_step(C.byref(kst))      # stats != NULL makes the call wait on its own end event: kernel_ms is that kernel time
         kernel_ms += kst.kernel_ms
         launches += kst.n_launches + (1 if rank == 0 else 0)
+        if os.environ.get("BENCH_DEBUG"):
+            sys.stderr.write("rank %d step kernel_ms %.2f\n" % (rank, kst.kernel_ms))
     ev1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None

@@ -61,13 +61,14 @@ struct Box {
         return (dx < 0 || dy < 0 || dz < 0) ? 0.f : 2.f * (dx * dy + dy * dz + dz * dx);
     }
 };
-struct Prim { Box box; float c[3]; uint32_t ref; };
+struct Prim { Box box; float c[3]; uint32_t ref; float coef = 0.f; };
 
 inline int32_t leaf_code(uint32_t first, uint32_t count) { return -(int32_t)(first * 8u + count) - 1; }
 
 // returns a child code (>= 0 inner node, < 0 leaf). `median` forces balanced splits (depth <= log2 n),
 // used when the SAH tree came out deeper than the device's traversal stack.
-inline int32_t build(std::vector<Prim> &prims, size_t begin, size_t end, Accel &out, bool median, int depth, int &max_depth) {
+template <class A>
+inline int32_t build(std::vector<Prim> &prims, size_t begin, size_t end, A &out, bool median, int depth, int &max_depth) {
     const size_t n = end - begin;
     max_depth = std::max(max_depth, depth);
     Box cb; cb.reset();
@@ -122,14 +123,15 @@ inline int32_t build(std::vector<Prim> &prims, size_t begin, size_t end, Accel &
     const size_t id = out.nodes.size() / 4;
     out.nodes.resize(out.nodes.size() + 4);
     Box b0, b1; b0.reset(); b1.reset();
-    for (size_t i = begin; i < mid; ++i) b0.grow(prims[i].box);
-    for (size_t i = mid; i < end; ++i) b1.grow(prims[i].box);
+    float k0 = 0.f, k1 = 0.f;   // largest per-primitive padding coefficient below each child (0 for triangles)
+    for (size_t i = begin; i < mid; ++i) { b0.grow(prims[i].box); k0 = std::max(k0, prims[i].coef); }
+    for (size_t i = mid; i < end; ++i) { b1.grow(prims[i].box); k1 = std::max(k1, prims[i].coef); }
     const int32_t c0 = build(prims, begin, mid, out, median, depth + 1, max_depth);
     const int32_t c1 = build(prims, mid, end, out, median, depth + 1, max_depth);
     out.nodes[4 * id + 0] = make_float4(b0.lo[0], b0.lo[1], b0.lo[2], b0.hi[0]);
     out.nodes[4 * id + 1] = make_float4(b0.hi[1], b0.hi[2], b1.lo[0], b1.lo[1]);
     out.nodes[4 * id + 2] = make_float4(b1.lo[2], b1.hi[0], b1.hi[1], b1.hi[2]);
-    out.nodes[4 * id + 3] = make_float4(u2f((uint32_t)c0), u2f((uint32_t)c1), 0.f, 0.f);
+    out.nodes[4 * id + 3] = make_float4(u2f((uint32_t)c0), u2f((uint32_t)c1), k0, k1);
     return (int32_t)id;
 }
 }  // namespace bvh_detail
@@ -243,6 +245,81 @@ inline void build_accel(const RtSceneDesc &d, const PackedMeshes &pk, Accel &out
             out.mesh_root.push_back((int32_t)id);
         }
     }
+}
+
+// ---- the same idea for the analytic primitives -------------------------------------------------
+// Scene::computeIntersection / computeShadow test every sphere and every square for every ray
+// (Scene.h:207-220, 236-247): 82 sphere tests per ray on config 2. Each test is independent of the
+// others, so a conservative hierarchy over their (motion-swept) bounds may skip tests that cannot
+// produce an acceptable hit; accepted candidates go through the reference's own sphere / square
+// arithmetic, and the ORDER semantics are restored explicitly: closest hit = smallest t, the earliest
+// primitive in the reference's sequence (spheres by index, then squares by index) winning ties;
+// occlusion = candidates collected in a bit mask and replayed in sequence order so that the
+// random_float() draws of computeShadow happen exactly as in the reference.
+// Conservativeness: a sphere test can report a hit for a ray that misses the true sphere by up to
+// ~eps*|o-c|^2/(2r) (the discriminant cancels for grazing rays), so boxes are enlarged PER RAY by
+// k_ray*coef with coef = 1/r and k_ray = 32 eps (|o-C|+R)^2, (C, R) a bounding sphere of all
+// analytic primitives, on top of a static 1e-4 relative pad; squares get coef 0 and the linear term.
+struct AnalyticAccel {
+    std::vector<float4> nodes;     // same node format as Accel; n3.z / n3.w = max 1/r below child 0 / 1
+    std::vector<uint32_t> tris;    // leaf contents: sequence index (sphere i -> i, square j -> n_spheres + j)
+    int32_t root = -1;             // -1: not built (too few or too many primitives)
+    float center[3] = {0, 0, 0};
+    float radius = 0.f;
+};
+
+inline void build_analytic_accel(const RtSceneDesc &d, AnalyticAccel &out) {
+    using namespace bvh_detail;
+    out = AnalyticAccel();
+    const uint32_t n = d.n_spheres + d.n_squares;
+    if (n < 24 || n > 128) return;   // below: the linear loops are as fast; above: the occlusion mask is 128 bits
+    std::vector<Prim> prims;
+    Box all; all.reset();
+    for (uint32_t i = 0; i < d.n_spheres; ++i) {
+        const RtSphere &s = d.spheres[i];
+        Prim p; p.box.reset(); p.ref = i;
+        const float r = std::fabs(s.radius);
+        for (int e = 0; e < 2; ++e) {      // time 0 and time 1 (ray.time is in [0,1), motion is linear)
+            float lo[3], hi[3];
+            for (int a = 0; a < 3; ++a) { const float c = s.center[a] + (float)e * s.material.motion[a]; lo[a] = c - r; hi[a] = c + r; }
+            p.box.grow(lo); p.box.grow(hi);
+        }
+        p.coef = r > 0.f ? 1.f / r : 1e30f;
+        prims.push_back(p);
+    }
+    for (uint32_t j = 0; j < d.n_squares; ++j) {
+        const RtSquare &q = d.squares[j];
+        Prim p; p.box.reset(); p.ref = d.n_spheres + j;
+        for (int e = 0; e < 2; ++e)
+            for (int corner = 0; corner < 4; ++corner) {
+                float c[3];
+                for (int a = 0; a < 3; ++a) {
+                    const float right = q.v1[a] - q.v0[a], up = q.v3[a] - q.v0[a];
+                    c[a] = q.v0[a] + (float)e * q.material.motion[a] + ((corner & 1) ? right : 0.f) + ((corner & 2) ? up : 0.f);
+                }
+                p.box.grow(c);
+            }
+        p.coef = 0.f;
+        prims.push_back(p);
+    }
+    for (Prim &p : prims) {
+        bool finite = true;
+        for (int a = 0; a < 3; ++a) finite = finite && std::isfinite(p.box.lo[a]) && std::isfinite(p.box.hi[a]);
+        if (!finite) { for (int a = 0; a < 3; ++a) { p.box.lo[a] = -1e30f; p.box.hi[a] = 1e30f; } }
+        for (int a = 0; a < 3; ++a) {
+            const float pad = 1e-4f * (std::fabs(p.box.lo[a]) + std::fabs(p.box.hi[a]) + (p.box.hi[a] - p.box.lo[a])) + 1e-4f;
+            p.box.lo[a] -= pad; p.box.hi[a] += pad;
+            p.c[a] = 0.5f * (p.box.lo[a] + p.box.hi[a]);
+        }
+        if (finite) all.grow(p.box);
+    }
+    float r2 = 0.f;
+    for (int a = 0; a < 3; ++a) { out.center[a] = 0.5f * (all.lo[a] + all.hi[a]); const float h = 0.5f * (all.hi[a] - all.lo[a]); r2 += h * h; }
+    out.radius = std::sqrt(r2);
+    int max_depth = 0;
+    int32_t root = build(prims, 0, prims.size(), out, false, 0, max_depth);
+    if (max_depth > 56) { out.nodes.clear(); out.tris.clear(); max_depth = 0; root = build(prims, 0, prims.size(), out, true, 0, max_depth); }
+    out.root = root >= 0 ? root : -1;   // n >= 24 always yields an inner root
 }
 
 }  // namespace rt

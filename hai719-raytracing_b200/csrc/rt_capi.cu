@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -157,8 +159,8 @@ __global__ void __launch_bounds__(128, 4) k_render_paths(const DScene scene, con
 // lane intersects ONE ray (closest-hit or shadow sample) and advances its path; a lane whose path
 // has ended takes the next path index from the global counter (one warp-aggregated atomicAdd,
 // __ballot_sync/__popc ranks). Lanes stay busy whatever the depth at which their paths end.
-template <bool STATS, bool ACCEL>
-__global__ void __launch_bounds__(128, 4) k_render_regen(const DScene scene, const DCamera cam, const RenderArgs a) {
+template <bool STATS, bool ACCEL, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_render_regen(const DScene scene, const DCamera cam, const RenderArgs a) {
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
@@ -600,6 +602,18 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
         }
         if ((rc = dev_upload(s, l.data(), l.size(), &d.lights))) return rc;
     }
+    // culling hierarchy over the analytic primitives (variant 3)
+    {
+        AnalyticAccel aa;
+        build_analytic_accel(*desc, aa);
+        d.abvh_root = aa.root;
+        for (int k = 0; k < 3; ++k) d.abvh_c[k] = aa.center[k];
+        d.abvh_r = aa.radius;
+        if (aa.root >= 0) {
+            if ((rc = dev_upload(s, aa.nodes.data(), aa.nodes.size(), &d.abvh_nodes))) return rc;
+            if ((rc = dev_upload(s, aa.tris.data(), aa.tris.size(), &d.abvh_prims))) return rc;
+        }
+    }
     // meshes: one shared node array + shared per-ref triangle constants (rt_pack.hpp, rt::DMesh)
     if (desc->n_meshes) {
         PackedMeshes pk;
@@ -707,12 +721,18 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     // variant: low byte = kernel (0 auto, 1 k_render_paths: one path per lane to completion,
     // 2 k_render_regen: ray-level state machine with path regeneration and warp-voted KD traversal);
     // bits 8..15 = regeneration threshold of kernel 2 (idle lanes needed before a refill; 0 = 16)
-    if (p->variant < 0 || (p->variant & 0xFF) > 3 || (p->variant >> 16)) return fail(RT_ERR_INVALID, "unknown kernel variant");
+    if (p->variant < 0 || (p->variant & 0xFF) > 3 || (p->variant >> 20)) return fail(RT_ERR_INVALID, "unknown kernel variant");
+    // bits 16..19: CTAs per SM of kernel 3 — 0 auto, 1 = 4 (<= 128 registers), 2 = 6 (<= 80), 3 = 8 (<= 64, a few spills)
+    int occ = (p->variant >> 16) & 0xF;
+    if (occ == 0) occ = 3;   // 8 CTAs/SM beat 6 and 4 on every config (profiles/r01_notes.md)
+    const int minb = occ - 1;
     int kind = p->variant & 0xFF;
-    if (kind == 0) kind = s->d.n_meshes > 0 ? 3 : 1;   // measured: profiles/r01_variants.md
+    if (kind == 0) kind = (s->d.n_meshes > 0 || s->d.abvh_root >= 0) ? 3 : 1;   // measured: profiles/r01_notes.md
     const bool regen = kind >= 2, accel = kind == 3;
-    const void *kern = accel   ? (want_stats ? (const void *)k_render_regen<true, true> : (const void *)k_render_regen<false, true>)
-                       : regen ? (want_stats ? (const void *)k_render_regen<true, false> : (const void *)k_render_regen<false, false>)
+    const void *kern = accel   ? (want_stats ? (const void *)k_render_regen<true, true, 4>
+                                             : minb == 1 ? (const void *)k_render_regen<false, true, 6>
+                                             : minb == 2 ? (const void *)k_render_regen<false, true, 8> : (const void *)k_render_regen<false, true, 4>)
+                       : regen ? (want_stats ? (const void *)k_render_regen<true, false, 4> : (const void *)k_render_regen<false, false, 4>)
                                : (want_stats ? (const void *)k_render_paths<true> : (const void *)k_render_paths<false>);
     const int grid = persistent_grid(s, kern, 128);
 
@@ -732,11 +752,13 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
         const unsigned long long batches = (a.n_paths + 31) / 32;
         const int g = (int)std::min<unsigned long long>((unsigned long long)grid, (batches + 3) / 4);
         if (accel) {
-            if (want_stats) k_render_regen<true, true><<<g, 128, 0, st>>>(s->d, cam, a);
-            else k_render_regen<false, true><<<g, 128, 0, st>>>(s->d, cam, a);
+            if (want_stats) k_render_regen<true, true, 4><<<g, 128, 0, st>>>(s->d, cam, a);
+            else if (minb == 1) k_render_regen<false, true, 6><<<g, 128, 0, st>>>(s->d, cam, a);
+            else if (minb == 2) k_render_regen<false, true, 8><<<g, 128, 0, st>>>(s->d, cam, a);
+            else k_render_regen<false, true, 4><<<g, 128, 0, st>>>(s->d, cam, a);
         } else if (regen) {
-            if (want_stats) k_render_regen<true, false><<<g, 128, 0, st>>>(s->d, cam, a);
-            else k_render_regen<false, false><<<g, 128, 0, st>>>(s->d, cam, a);
+            if (want_stats) k_render_regen<true, false, 4><<<g, 128, 0, st>>>(s->d, cam, a);
+            else k_render_regen<false, false, 4><<<g, 128, 0, st>>>(s->d, cam, a);
         } else {
             if (want_stats) k_render_paths<true><<<g, 128, 0, st>>>(s->d, cam, a);
             else k_render_paths<false><<<g, 128, 0, st>>>(s->d, cam, a);
@@ -764,6 +786,18 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     return RT_OK;
 }
 
+namespace {
+// device copies of per-rank tile tables for rt_untile_device, kept per (device, geometry) so that the
+// per-frame call allocates nothing and never synchronises
+struct UntileKey {
+    int device, w, h, x0, y0, x1, y1, tw, th, nr, rk;
+    bool operator<(const UntileKey &o) const { return memcmp(this, &o, sizeof *this) < 0; }
+};
+struct UntileTab { TileRec *tiles = nullptr; unsigned int *off = nullptr; int n = 0; unsigned int pixels = 0; };
+std::map<UntileKey, UntileTab> g_untile;
+std::mutex g_untile_mu;
+}  // namespace
+
 int rt_untile_device(const RtRenderParams *p, const float *d_packed, const int64_t *pixel_offsets, float *d_image,
                      int device, void *cuda_stream) {
     if (!p || !d_packed || !d_image) return fail(RT_ERR_INVALID, "null argument");
@@ -774,23 +808,36 @@ int rt_untile_device(const RtRenderParams *p, const float *d_packed, const int64
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int nr = p->n_ranks > 1 ? p->n_ranks : 1;
     for (int rk = 0; rk < nr; ++rk) {
-        RtRenderParams q = *p;
-        q.rank = rk;
-        std::vector<TileRec> tiles; std::vector<unsigned int> off;
-        build_tiles(q, r, tiles, off);
-        if (tiles.empty()) continue;
-        TileRec *dt = nullptr; unsigned int *doff = nullptr;
-        RT_CUDA(cudaMallocAsync((void **)&dt, tiles.size() * sizeof(TileRec), st));
-        RT_CUDA(cudaMallocAsync((void **)&doff, off.size() * sizeof(unsigned int), st));
-        RT_CUDA(cudaMemcpyAsync(dt, tiles.data(), tiles.size() * sizeof(TileRec), cudaMemcpyHostToDevice, st));
-        RT_CUDA(cudaMemcpyAsync(doff, off.data(), off.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
-        RT_CUDA(cudaStreamSynchronize(st));   // the host vectors go out of scope below
-        const unsigned int np = off.back();
+        UntileKey key;
+        memset(&key, 0, sizeof key);
+        key.device = device; key.w = p->width; key.h = p->height; key.x0 = r.x0; key.y0 = r.y0; key.x1 = r.x1; key.y1 = r.y1;
+        key.tw = r.tw; key.th = r.th; key.nr = nr; key.rk = rk;
+        UntileTab tab;
+        {
+            std::lock_guard<std::mutex> lock(g_untile_mu);
+            auto it = g_untile.find(key);
+            if (it == g_untile.end()) {
+                RtRenderParams q = *p;
+                q.rank = rk;
+                std::vector<TileRec> tiles; std::vector<unsigned int> off;
+                build_tiles(q, r, tiles, off);
+                UntileTab t;
+                t.n = (int)tiles.size();
+                t.pixels = off.back();
+                if (t.n) {
+                    RT_CUDA(cudaMalloc((void **)&t.tiles, tiles.size() * sizeof(TileRec)));
+                    RT_CUDA(cudaMalloc((void **)&t.off, off.size() * sizeof(unsigned int)));
+                    RT_CUDA(cudaMemcpy(t.tiles, tiles.data(), tiles.size() * sizeof(TileRec), cudaMemcpyHostToDevice));
+                    RT_CUDA(cudaMemcpy(t.off, off.data(), off.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+                }
+                it = g_untile.emplace(key, t).first;
+            }
+            tab = it->second;
+        }
+        if (!tab.n) continue;
         const float *src = d_packed + 3 * (pixel_offsets ? pixel_offsets[rk] : 0);
-        k_untile<<<(np + 255) / 256, 256, 0, st>>>(dt, doff, (int)tiles.size(), src, d_image, r.x0, r.y0, r.x1 - r.x0, np);
+        k_untile<<<(tab.pixels + 255) / 256, 256, 0, st>>>(tab.tiles, tab.off, tab.n, src, d_image, r.x0, r.y0, r.x1 - r.x0, tab.pixels);
         RT_CUDA(cudaGetLastError());
-        RT_CUDA(cudaFreeAsync(dt, st));
-        RT_CUDA(cudaFreeAsync(doff, st));
     }
     return RT_OK;
 }

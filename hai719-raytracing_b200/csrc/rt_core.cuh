@@ -35,10 +35,16 @@
 #ifdef __CUDACC__
 #define RT_HD __device__ __forceinline__
 #define RT_HHD __host__ __device__ __forceinline__
+// Per-hit code that drags in software fp64 routines (acos, atan2, asin, pow, fmod, fp64 division) is kept
+// OUT of line: inlined everywhere, k_render_regen was ~10 000 SASS instructions (160 KB) and its warps spent
+// most of their stalled cycles waiting for instruction fetch (ncu: stall_no_instruction 6.5 per issue,
+// profiles/r01_notes.md). The intersection loops stay inline.
+#define RT_COLD __device__ __noinline__
 #define RT_LDG(p) __ldg(p)
 #else
 #define RT_HD inline
 #define RT_HHD inline
+#define RT_COLD inline
 #define RT_LDG(p) (*(p))
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
@@ -163,6 +169,11 @@ struct DScene {
     const float4 *bvh_nodes;   // 4 per node
     const uint32_t *bvh_tris;  // representative leaf ref per distinct triangle, BVH leaf order
     const uint32_t *ref_next, *ref_leaf, *node_parent;
+    // culling hierarchy over spheres + squares (rt_bvh.hpp : build_analytic_accel); abvh_root < 0 = linear loops
+    const float4 *abvh_nodes;
+    const uint32_t *abvh_prims;
+    int abvh_root;
+    float abvh_c[3], abvh_r;
     const DMaterial *sph_mat, *sq_mat, *mesh_mat;
     const DLight *lights;
     const DImage *textures, *normal_maps;
@@ -364,6 +375,16 @@ RT_HD bool mesh_closest(const Ray &ray, const RayInv &inv, const DScene &s, cons
 // ancestor (whose boxes contain it) AABB::intersects keeps tmin < t < tmax at every step and
 // returns true. Anything else — grazing, axis-parallel, tiny t — re-runs the reference's own fp64
 // slab test (slab_hit) up the parent chain, synthetic root (= KDTree::aabb gate) included.
+RT_COLD bool leaf_reachable_exact(const DScene &s, const Ray &ray, uint32_t leaf) {
+    const RayInv inv = make_inv(ray);
+    uint32_t n = leaf;
+    while (n != 0xFFFFFFFFu) {
+        const float4 l = RT_LDG(s.node_lo + n), h = RT_LDG(s.node_hi + n);
+        if (!slab_hit(ray, inv, l.x, l.y, l.z, h.x, h.y, h.z)) return false;
+        n = RT_LDG(s.node_parent + n);
+    }
+    return true;
+}
 RT_HD bool leaf_reachable(const DScene &s, const Ray &ray, float t, uint32_t leaf) {
     const float4 lo = RT_LDG(s.node_lo + leaf), hi = RT_LDG(s.node_hi + leaf);
     bool ok = t > 1e-3f;
@@ -379,14 +400,7 @@ RT_HD bool leaf_reachable(const DScene &s, const Ray &ray, float t, uint32_t lea
         ok = ok && (fminr(c0, c1) + mc < t) && (t < fmaxr(c0, c1) - mc);
     }
     if (ok) return true;
-    const RayInv inv = make_inv(ray);
-    uint32_t n = leaf;
-    while (n != 0xFFFFFFFFu) {
-        const float4 l = RT_LDG(s.node_lo + n), h = RT_LDG(s.node_hi + n);
-        if (!slab_hit(ray, inv, l.x, l.y, l.z, h.x, h.y, h.z)) return false;
-        n = RT_LDG(s.node_parent + n);
-    }
-    return true;
+    return leaf_reachable_exact(s, ray, leaf);
 }
 // first reachable reference of the triangle whose references start at r0, or NONE
 RT_HD uint32_t tri_first_reachable(const DScene &s, const Ray &ray, float t, uint32_t r0) {
@@ -395,7 +409,7 @@ RT_HD uint32_t tri_first_reachable(const DScene &s, const Ray &ray, float t, uin
     return 0xFFFFFFFFu;
 }
 // last reachable reference (decides ties between different triangles at the same t)
-RT_HD uint32_t tri_last_reachable(const DScene &s, const Ray &ray, float t, uint32_t r0) {
+RT_COLD uint32_t tri_last_reachable(const DScene &s, const Ray &ray, float t, uint32_t r0) {
     uint32_t last = 0xFFFFFFFFu;
     for (uint32_t r = r0; r != 0xFFFFFFFFu; r = RT_LDG(s.ref_next + r))
         if (leaf_reachable(s, ray, t, RT_LDG(s.ref_leaf + r))) last = r;
@@ -488,6 +502,47 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
     return true;
 }
 
+// ---- analytic primitives through their culling hierarchy (variant 3) ----------------------------
+// Visits every sphere/square whose padded, motion-swept box the ray can touch within [0, limit] and
+// calls f(seq) for it (seq: sphere i -> i, square j -> n_spheres + j). `limit` is re-read after every
+// call so a closest-hit caller can shrink it.
+template <bool STATS, class F>
+RT_HD void analytic_candidates(const DScene &s, const Ray &ray, const float &limit, F &&f, Counters *cnt) {
+    Inv32 iv; iv.x = safe_inv(ray.d.x); iv.y = safe_inv(ray.d.y); iv.z = safe_inv(ray.d.z);
+    // per-ray enlargement (see build_analytic_accel): quadratic term x 1/r of the spheres below, plus a linear term
+    const float dist = length(ray.o - ld3(s.abvh_c)) + s.abvh_r;
+    const float kq = 32.f * 5.96e-8f * dist * dist, kl = 64.f * 5.96e-8f * dist;
+    int stack[64];
+    int sp = 0;
+    int node = s.abvh_root;
+    for (;;) {
+        if (node >= 0) {
+            const float4 n0 = RT_LDG(s.abvh_nodes + 4 * node), n1 = RT_LDG(s.abvh_nodes + 4 * node + 1),
+                         n2 = RT_LDG(s.abvh_nodes + 4 * node + 2), n3 = RT_LDG(s.abvh_nodes + 4 * node + 3);
+            if (STATS) cnt->node++;
+            const float p0 = kq * n3.z + kl, p1 = kq * n3.w + kl;
+            float d0, d1;
+            const bool h0 = bvh_box(ray, iv, n0.x - p0, n0.y - p0, n0.z - p0, n0.w + p0, n1.x + p0, n1.y + p0, limit, d0);
+            const bool h1 = bvh_box(ray, iv, n1.z - p1, n1.w - p1, n2.x - p1, n2.y + p1, n2.z + p1, n2.w + p1, limit, d1);
+            const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
+            if (h0 && h1) {
+                const bool swap = d1 < d0;
+                node = swap ? c1 : c0;
+                stack[sp++] = swap ? c0 : c1;
+                continue;
+            }
+            if (h0) { node = c0; continue; }
+            if (h1) { node = c1; continue; }
+        } else {
+            const uint32_t code = (uint32_t)(-(node + 1));
+            const uint32_t first = code >> 3, count = code & 7u;
+            for (uint32_t k = first; k < first + count; ++k) f(RT_LDG(s.abvh_prims + k));
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+}
+
 // ---- scene: closest hit ------------------------------------------------------------------------
 // Scene::computeIntersection: spheres, then squares, then meshes; a candidate replaces the current
 // best only if t < best.t && t >= EPSILON (strict <: first object wins ties within a type, and
@@ -561,6 +616,14 @@ RT_HD bool shadow_hit(const DScene &s, const Ray &ray, float t_light, Rng &rng, 
     return false;
 }
 
+// theta, phi of a sphere normal (Sphere.h:129-130) mapped to texture coordinates (Material.cpp:98, Scene.h:277)
+RT_COLD void sphere_uv(V3 n, float &tu, float &tv) {
+    const float theta = (float)acos((double)n.y * -1.);
+    const float phi = (float)(atan2((double)n.z * -1., (double)n.x) + RT_PI);
+    tu = (float)((double)phi / (2 * RT_PI));
+    tv = (float)((double)theta / RT_PI);
+}
+
 // ---- textures ----------------------------------------------------------------------------------
 RT_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -577,7 +640,7 @@ RT_HD int texel_index(const DImage &im, float u, float v, float sx, float sy) {
 
 // Material::texture (Material.cpp:63-92). `color` is left untouched for Texture_None.
 template <bool STATS>
-RT_HD void material_texture(const DScene &s, const DMaterial &m, V3 &color, float u, float v, Counters *cnt) {
+RT_COLD void material_texture(const DScene &s, const DMaterial &m, V3 &color, float u, float v, Counters *cnt) {
     if (m.texture_type == 1) {
         color = ((int)(u * m.tsx) % 2 == (int)(v * m.tsy) % 2) ? ld3(m.checker1) : ld3(m.checker2);
     } else if (m.texture_type == 2) {
@@ -595,7 +658,7 @@ RT_HD void material_texture(const DScene &s, const DMaterial &m, V3 &color, floa
 
 // Material::emit (Material.cpp:13-24)
 template <bool STATS>
-RT_HD V3 material_emit(const DScene &s, const DMaterial &m, float u, float v, Counters *cnt) {
+RT_COLD V3 material_emit(const DScene &s, const DMaterial &m, float u, float v, Counters *cnt) {
     if (!m.emissive) return v3(0.f);
     V3 c = v3(0.f);
     if (m.texture_type == 0) c = ld3(m.light_color);
@@ -606,7 +669,7 @@ RT_HD V3 material_emit(const DScene &s, const DMaterial &m, float u, float v, Co
 // Material::get_normal (Material.cpp:114-130): tangent-space map, T/B = the square's stale
 // m_right_vector / m_up_vector members.
 template <bool STATS>
-RT_HD V3 material_normal(const DScene &s, const DMaterial &m, V3 n, float u, float v, V3 T, V3 B, Counters *cnt) {
+RT_COLD V3 material_normal(const DScene &s, const DMaterial &m, V3 n, float u, float v, V3 T, V3 B, Counters *cnt) {
     if (m.normal_map < 0) return n;
     const DImage im = s.normal_maps[m.normal_map];
     if (im.w < 1 || im.h < 1) return n;   // reference would dereference an empty image; defined as "no map"
@@ -618,7 +681,7 @@ RT_HD V3 material_normal(const DScene &s, const DMaterial &m, V3 n, float u, flo
 
 // Scene::skyboxTexture (Scene.h:149-161)
 template <bool STATS>
-RT_HD V3 sky_color(const DScene &s, V3 d, int n_remaining, Counters *cnt) {
+RT_COLD V3 sky_color(const DScene &s, V3 d, int n_remaining, Counters *cnt) {
     if (s.sky.w < 1 || s.sky.h < 1) {
         if (s.dark_sky) return v3(0.f);
         const float a = (float)(0.5 * ((double)d.y + 1.0));
@@ -654,7 +717,7 @@ RT_HD float schlick(float cosine, float ref_idx) {                              
 }
 // Material::scatter (Material.cpp:26-60). Returns the new ray (origin P + EPSILON*dir).
 template <bool STATS>
-RT_HD Ray material_scatter(const DMaterial &m, const Ray &in, V3 n, V3 P, Rng &rng, Counters *cnt) {
+RT_COLD Ray material_scatter(const DMaterial &m, const Ray &in, V3 n, V3 P, Rng &rng, Counters *cnt) {
     V3 dir = v3(0.f);
     if (m.type == 1) {          // glass (inverted convention and the -0.6 test are the reference's, A.1-8)
         const float ri = dot(in.d, n) > 0.f ? (float)(1. / (double)m.index_medium) : m.index_medium;
@@ -707,10 +770,7 @@ RT_HD V3 trace_path(const DScene &s, Ray ray, Rng &rng, int max_bounces, int nb_
             if (mat->texture_type != 0) {
                 // theta/phi (Sphere.h:129-130) feed only sphere_texture() and a textured emit(); the
                 // reference evaluates them for every candidate, the result is the same without
-                const float theta = (float)acos((double)n.y * -1.);
-                const float phi = (float)(atan2((double)n.z * -1., (double)n.x) + RT_PI);
-                tu = (float)((double)phi / (2 * RT_PI));
-                tv = (float)((double)theta / RT_PI);
+                sphere_uv(n, tu, tv);
                 material_texture<STATS>(s, *mat, kd, tu, tv, cnt);   // sphere_texture
             }
             e = material_emit<STATS>(s, *mat, tu, tv, cnt);
@@ -785,7 +845,9 @@ RT_HD V3 trace_path(const DScene &s, Ray ray, Rng &rng, int max_bounces, int nb_
 #define RT_WARP_ALL(pred) __all_sync(0xFFFFFFFFu, (pred))
 #define RT_BALLOT(pred) __ballot_sync(0xFFFFFFFFu, (pred))
 #define RT_POPC(x) __popc(x)
+#define RT_FFS(x) __ffs(x)
 #else   /* one lane */
+#define RT_FFS(x) __builtin_ffs(x)
 #define RT_WARP_ALL(pred) (pred)
 #define RT_BALLOT(pred) ((pred) ? 1u : 0u)
 #define RT_POPC(x) ((int)((x) != 0u))
@@ -819,26 +881,65 @@ RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_ligh
     bool done = (mode == 2);
     if (STATS) { if (mode == 0) cnt->closest++; else if (mode == 1) cnt->shadow++; }
     const SphereRay sr = make_sphere_ray(ray);
-    for (int i = 0; i < s.n_spheres; ++i) {
-        if ((i & 3) == 0 && RT_WARP_ALL(done)) break;
-        if (done) continue;
-        if (STATS) cnt->sphere++;
-        const float4 b = RT_LDG(s.sph_b + i);
-        const float t = sphere_t(ray, sr, RT_LDG(s.sph_a + i), b);
-        if (t < h.t && t > RT_EPSF) {
-            if (mode == 0) { h.type = 1; h.obj = i; h.t = t; }
-            else { if (STATS) cnt->rnd++; if (rng.next() > b.w) { blocked = true; done = true; } }
+    if (ACCEL && s.abvh_root >= 0) {
+        // variant 3: candidates from the culling hierarchy, exact tests, order semantics restored
+        if (!done) {
+            const int ns = s.n_spheres;
+            int best_seq = 0x7FFFFFFF;
+            uint32_t mask[4] = {0u, 0u, 0u, 0u};
+            // one traversal for both ray kinds (h.t is the limit either way: current best, or the light distance)
+            analytic_candidates<STATS>(s, ray, h.t, [&](uint32_t seq) {
+                float t, u = 0.f, v = 0.f;
+                if ((int)seq < ns) { if (STATS) cnt->sphere++; t = sphere_t(ray, sr, RT_LDG(s.sph_a + seq), RT_LDG(s.sph_b + seq)); }
+                else { if (STATS) cnt->square++; t = square_t(ray, s.squares[seq - ns], u, v); }
+                if (!(t > RT_EPSF)) return;
+                if (mode == 0) {
+                    // sequential strict '<' of the reference == smallest t, earliest in sequence on ties
+                    if (t < h.t || (t == h.t && best_seq != 0x7FFFFFFF && (int)seq < best_seq)) {
+                        best_seq = (int)seq; h.t = t;
+                        if ((int)seq < ns) { h.type = 1; h.obj = (int)seq; } else { h.type = 2; h.obj = (int)seq - ns; hu = u; hv = v; }
+                    }
+                } else if (t < h.t) {
+                    mask[seq >> 5] |= 1u << (seq & 31u);
+                }
+            }, cnt);
+            if (mode != 0) {
+                // replay the candidate blockers in the reference's order: one draw each until one blocks
+                for (int w = 0; w < 4 && !done; ++w) {
+                    uint32_t m = mask[w];
+                    while (m) {
+                        const int bit = RT_FFS((int)m) - 1;
+                        m &= m - 1u;
+                        const int seq = w * 32 + bit;
+                        const float tr = seq < ns ? RT_LDG(s.sph_b + seq).w : RT_LDG(s.sq_transparency + (seq - ns));
+                        if (STATS) cnt->rnd++;
+                        if (rng.next() > tr) { blocked = true; done = true; break; }
+                    }
+                }
+            }
         }
-    }
-    for (int i = 0; i < s.n_squares; ++i) {
-        if ((i & 3) == 0 && RT_WARP_ALL(done)) break;
-        if (done) continue;
-        if (STATS) cnt->square++;
-        float u, v;
-        const float t = square_t(ray, s.squares[i], u, v);
-        if (t < h.t && t > RT_EPSF) {
-            if (mode == 0) { h.type = 2; h.obj = i; h.t = t; hu = u; hv = v; }
-            else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.sq_transparency + i)) { blocked = true; done = true; } }
+    } else {
+        for (int i = 0; i < s.n_spheres; ++i) {
+            if ((i & 3) == 0 && RT_WARP_ALL(done)) break;
+            if (done) continue;
+            if (STATS) cnt->sphere++;
+            const float4 b = RT_LDG(s.sph_b + i);
+            const float t = sphere_t(ray, sr, RT_LDG(s.sph_a + i), b);
+            if (t < h.t && t > RT_EPSF) {
+                if (mode == 0) { h.type = 1; h.obj = i; h.t = t; }
+                else { if (STATS) cnt->rnd++; if (rng.next() > b.w) { blocked = true; done = true; } }
+            }
+        }
+        for (int i = 0; i < s.n_squares; ++i) {
+            if ((i & 3) == 0 && RT_WARP_ALL(done)) break;
+            if (done) continue;
+            if (STATS) cnt->square++;
+            float u, v;
+            const float t = square_t(ray, s.squares[i], u, v);
+            if (t < h.t && t > RT_EPSF) {
+                if (mode == 0) { h.type = 2; h.obj = i; h.t = t; hu = u; hv = v; }
+                else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.sq_transparency + i)) { blocked = true; done = true; } }
+            }
         }
     }
     if (ACCEL) {
@@ -926,7 +1027,7 @@ RT_HD V3 path_fold(const PathState &st, V3 tail) {
 
 // next soft-shadow sample of light st.light (Scene.h:325-330)
 template <bool STATS>
-RT_HD void path_shadow_sample(const DScene &s, PathState &st, Counters *cnt) {
+RT_COLD void path_shadow_sample(const DScene &s, PathState &st, Counters *cnt) {
     if (STATS) cnt->rnd += 3;
     const V3 lp = ld3(s.lights[st.light].pos);
     const float delta = s.lights[st.light].radius / 2.f;
@@ -986,10 +1087,7 @@ RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, 
         kd = ld3(mat->kd);
         float tu = 0.f, tv = 0.f;
         if (mat->texture_type != 0) {
-            const float theta = (float)acos((double)n.y * -1.);
-            const float phi = (float)(atan2((double)n.z * -1., (double)n.x) + RT_PI);
-            tu = (float)((double)phi / (2 * RT_PI));
-            tv = (float)((double)theta / RT_PI);
+            sphere_uv(n, tu, tv);
             material_texture<STATS>(s, *mat, kd, tu, tv, cnt);
         }
         e = material_emit<STATS>(s, *mat, tu, tv, cnt);
@@ -1047,7 +1145,7 @@ RT_HD Ray camera_ray(const DCamera &c, float u, float v, float time) {
     return make_ray(pos, dir, time);
 }
 // trace_line's per-sample prologue (main.cpp:189-192): u, v, time are draws 0, 1, 2
-RT_HD Ray primary_ray(const DCamera &c, int x, int y, int w, int h, Rng &rng) {
+RT_COLD Ray primary_ray(const DCamera &c, int x, int y, int w, int h, Rng &rng) {
     const float u = ((float)x + rng.next()) / (float)w;
     const float v = ((float)y + rng.next()) / (float)h;
     const float time = rng.next();

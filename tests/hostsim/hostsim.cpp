@@ -30,6 +30,7 @@ struct SimScene {
     std::vector<DMesh> meshes;
     PackedMeshes pk;
     Accel ac;
+    AnalyticAccel aa;
     std::vector<float4> plane, edge;
     std::vector<float2> den;
 };
@@ -87,6 +88,10 @@ void *sim_scene_create(const RtSceneDesc *desc) {
         s->lights.push_back(l);
     }
     d.lights = s->lights.data();
+    build_analytic_accel(*desc, s->aa);
+    d.abvh_root = s->aa.root; d.abvh_nodes = s->aa.nodes.data(); d.abvh_prims = s->aa.tris.data();
+    for (int k = 0; k < 3; ++k) d.abvh_c[k] = s->aa.center[k];
+    d.abvh_r = s->aa.radius;
     const uint32_t nm = desc->n_meshes;
     if (!pack_meshes(*desc, s->pk).empty()) { delete s; return nullptr; }
     build_accel(*desc, s->pk, s->ac);

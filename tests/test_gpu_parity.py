@@ -132,7 +132,8 @@ def test_exact_culling_equals_reference_order(gpu, assets, name, w, h, spp):
 
 
 @pytest.mark.parametrize("name,w,h,spp", [("flamingo_pond", 1600, 900, 4), ("backrooms_pool", 1600, 900, 8), ("config5", 1600, 900, 4),
-                                          ("raccoon", 1280, 720, 4), ("flamingo_lake", 1280, 720, 2)])
+                                          ("raccoon", 1280, 720, 4), ("flamingo_lake", 1280, 720, 2), ("random_spheres", 1920, 1080, 8),
+                                          ("rt_in_a_weekend", 1280, 720, 4)])
 def test_exact_culling_at_scale(gpu, assets, name, w, h, spp):
     """Tens of millions of rays per scene: the culled traversal (variant 3) against the reference-order traversal
     (variant 1). Images must be bit-identical and the ray / random-draw counters equal — one wrong hit anywhere

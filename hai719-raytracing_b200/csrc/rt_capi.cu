@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128, 4) k_render_paths(const DScene scene, con
 // lane intersects ONE ray (closest-hit or shadow sample) and advances its path; a lane whose path
 // has ended takes the next path index from the global counter (one warp-aggregated atomicAdd,
 // __ballot_sync/__popc ranks). Lanes stay busy whatever the depth at which their paths end.
-template <bool STATS, bool ACCEL, int MINB>
+template <bool STATS, int ACCEL, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_render_regen(const DScene scene, const DCamera cam, const RenderArgs a) {
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const DScene scene, 
         Hit h;
         float hu = 0.f, hv = 0.f;
         bool blocked;
-        intersect_ray<STATS, ACCEL>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
+        if (ACCEL == 2) intersect_ray_voted<STATS>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
+        else intersect_ray<STATS, ACCEL == 1>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
         if (st.mode != 2) {
             V3 c;
             if (path_advance<STATS>(scene, st, h, hu, hv, blocked, a.nb_ech, c, &cnt)) {
@@ -721,19 +722,21 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     // variant: low byte = kernel (0 auto, 1 k_render_paths: one path per lane to completion,
     // 2 k_render_regen: ray-level state machine with path regeneration and warp-voted KD traversal);
     // bits 8..15 = regeneration threshold of kernel 2 (idle lanes needed before a refill; 0 = 16)
-    if (p->variant < 0 || (p->variant & 0xFF) > 3 || (p->variant >> 20)) return fail(RT_ERR_INVALID, "unknown kernel variant");
+    if (p->variant < 0 || (p->variant & 0xFF) > 4 || (p->variant >> 20)) return fail(RT_ERR_INVALID, "unknown kernel variant");
     // bits 16..19: CTAs per SM of kernel 3 — 0 auto, 1 = 4 (<= 128 registers), 2 = 6 (<= 80), 3 = 8 (<= 64, a few spills)
     int occ = (p->variant >> 16) & 0xF;
     if (occ == 0) occ = 3;   // 8 CTAs/SM beat 6 and 4 on every config (profiles/r01_notes.md)
     const int minb = occ - 1;
     int kind = p->variant & 0xFF;
     if (kind == 0) kind = (s->d.n_meshes > 0 || s->d.abvh_root >= 0) ? 3 : 1;   // measured: profiles/r01_notes.md
-    const bool regen = kind >= 2, accel = kind == 3;
-    const void *kern = accel   ? (want_stats ? (const void *)k_render_regen<true, true, 4>
-                                             : minb == 1 ? (const void *)k_render_regen<false, true, 6>
-                                             : minb == 2 ? (const void *)k_render_regen<false, true, 8> : (const void *)k_render_regen<false, true, 4>)
-                       : regen ? (want_stats ? (const void *)k_render_regen<true, false, 4> : (const void *)k_render_regen<false, false, 4>)
-                               : (want_stats ? (const void *)k_render_paths<true> : (const void *)k_render_paths<false>);
+    const bool regen = kind >= 2, accel = kind >= 3, voted = kind == 4;
+    typedef void (*RenderKernel)(const DScene, const DCamera, const RenderArgs);
+    RenderKernel fn;
+    if (voted)      fn = want_stats ? k_render_regen<true, 2, 4> : minb == 0 ? k_render_regen<false, 2, 4> : minb == 1 ? k_render_regen<false, 2, 6> : k_render_regen<false, 2, 8>;
+    else if (accel) fn = want_stats ? k_render_regen<true, 1, 4> : minb == 0 ? k_render_regen<false, 1, 4> : minb == 1 ? k_render_regen<false, 1, 6> : k_render_regen<false, 1, 8>;
+    else if (regen) fn = want_stats ? k_render_regen<true, 0, 4> : k_render_regen<false, 0, 4>;
+    else            fn = want_stats ? k_render_paths<true> : k_render_paths<false>;
+    const void *kern = (const void *)fn;
     const int grid = persistent_grid(s, kern, 128);
 
     RenderArgs a{};
@@ -751,18 +754,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
         if (pb) RT_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long), st));
         const unsigned long long batches = (a.n_paths + 31) / 32;
         const int g = (int)std::min<unsigned long long>((unsigned long long)grid, (batches + 3) / 4);
-        if (accel) {
-            if (want_stats) k_render_regen<true, true, 4><<<g, 128, 0, st>>>(s->d, cam, a);
-            else if (minb == 1) k_render_regen<false, true, 6><<<g, 128, 0, st>>>(s->d, cam, a);
-            else if (minb == 2) k_render_regen<false, true, 8><<<g, 128, 0, st>>>(s->d, cam, a);
-            else k_render_regen<false, true, 4><<<g, 128, 0, st>>>(s->d, cam, a);
-        } else if (regen) {
-            if (want_stats) k_render_regen<true, false, 4><<<g, 128, 0, st>>>(s->d, cam, a);
-            else k_render_regen<false, false, 4><<<g, 128, 0, st>>>(s->d, cam, a);
-        } else {
-            if (want_stats) k_render_paths<true><<<g, 128, 0, st>>>(s->d, cam, a);
-            else k_render_paths<false><<<g, 128, 0, st>>>(s->d, cam, a);
-        }
+        fn<<<g, 128, 0, st>>>(s->d, cam, a);
         RT_CUDA(cudaGetLastError());
         k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(s->samples, pb, (unsigned int)np, p->spp, d_linear, d_gamma);
         RT_CUDA(cudaGetLastError());

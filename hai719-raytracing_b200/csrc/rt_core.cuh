@@ -52,6 +52,21 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #endif
 
+// warp-level helpers (the plain-C++ build of this header is a single lane)
+#ifdef __CUDA_ARCH__
+#define RT_WARP_ALL(pred) __all_sync(0xFFFFFFFFu, (pred))
+#define RT_BALLOT(pred) __ballot_sync(0xFFFFFFFFu, (pred))
+#define RT_POPC(x) __popc(x)
+#define RT_FFS(x) __ffs(x)
+#define RT_FAST_RCP(x) __fdividef(1.f, (x))   /* 2-ulp reciprocal: only used where a 1e-5 relative margin follows */
+#else   /* one lane */
+#define RT_FFS(x) __builtin_ffs(x)
+#define RT_FAST_RCP(x) (1.f / (x))
+#define RT_WARP_ALL(pred) (pred)
+#define RT_BALLOT(pred) ((pred) ? 1u : 0u)
+#define RT_POPC(x) ((int)((x) != 0u))
+#endif
+
 namespace rt {
 
 #define RT_EPSF 1e-5f          /* (float)EPSILON */
@@ -389,7 +404,7 @@ RT_HD bool leaf_reachable(const DScene &s, const Ray &ray, float t, uint32_t lea
     const float4 lo = RT_LDG(s.node_lo + leaf), hi = RT_LDG(s.node_hi + leaf);
     bool ok = t > 1e-3f;
     {
-        const float ix = 1.f / ray.d.x, iy = 1.f / ray.d.y, iz = 1.f / ray.d.z;
+        const float ix = RT_FAST_RCP(ray.d.x), iy = RT_FAST_RCP(ray.d.y), iz = RT_FAST_RCP(ray.d.z);
         const float a0 = (lo.x - ray.o.x) * ix, a1 = (hi.x - ray.o.x) * ix;
         const float b0 = (lo.y - ray.o.y) * iy, b1 = (hi.y - ray.o.y) * iy;
         const float c0 = (lo.z - ray.o.z) * iz, c1 = (hi.z - ray.o.z) * iz;
@@ -417,7 +432,7 @@ RT_COLD uint32_t tri_last_reachable(const DScene &s, const Ray &ray, float t, ui
 }
 
 struct Inv32 { float x, y, z; };
-RT_HD float safe_inv(float d) { return fabsf(d) > 1e-30f ? 1.f / d : (d < 0.f ? -1e30f : 1e30f); }
+RT_HD float safe_inv(float d) { return fabsf(d) > 1e-30f ? RT_FAST_RCP(d) : (d < 0.f ? -1e30f : 1e30f); }
 // conservative ray/box overlap on [0, limit]; returns the entry parameter through `near`
 RT_HD bool bvh_box(const Ray &r, const Inv32 &iv, float lx, float ly, float lz, float hx, float hy, float hz, float limit, float &near) {
     const float a0 = (lx - r.o.x) * iv.x, a1 = (hx - r.o.x) * iv.x;
@@ -841,17 +856,7 @@ RT_HD V3 trace_path(const DScene &s, Ray ray, Rng &rng, int max_bounces, int nb_
 // or one soft-shadow sample (Scene::computeShadow). The kernel (k_render_regen) runs the steps of
 // 32 paths in lockstep, so lanes that are at different bounces, or one shading and one shadowing,
 // still execute the intersection loops together; a lane whose path ends takes a new path at once.
-#ifdef __CUDA_ARCH__
-#define RT_WARP_ALL(pred) __all_sync(0xFFFFFFFFu, (pred))
-#define RT_BALLOT(pred) __ballot_sync(0xFFFFFFFFu, (pred))
-#define RT_POPC(x) __popc(x)
-#define RT_FFS(x) __ffs(x)
-#else   /* one lane */
-#define RT_FFS(x) __builtin_ffs(x)
-#define RT_WARP_ALL(pred) (pred)
-#define RT_BALLOT(pred) ((pred) ? 1u : 0u)
-#define RT_POPC(x) ((int)((x) != 0u))
-#endif
+
 
 struct PathState {
     Rng rng;
@@ -1007,6 +1012,159 @@ RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_ligh
                         if (leaf) { k = f2u(lo.w); kend = k + (hw & 0x7FFFFFFFu); leaf_t = FLT_MAX; leaf_ref = NONE; }
                         ++i;
                     }
+                }
+            }
+        }
+    }
+}
+
+// ---- variant 4: ONE warp-voted walk over the analytic hierarchy and every mesh hierarchy ---------
+// Same candidates, same exact tests and same order rules as the ACCEL path of intersect_ray; what
+// changes is the control flow. A lane is always either about to TEST a primitive (sphere, square or
+// triangle) or about to handle a NODE (pop, box tests, open a leaf, finish a phase); each round the
+// warp executes only the kind most of its lanes want (__ballot_sync/__popc), so the two bodies stay
+// convergent although every lane walks its own path through its own hierarchy — per-lane loops ran
+// at 7 of 32 lanes on the pond scene (profiles/r01_notes.md).
+template <bool STATS>
+RT_HD void intersect_ray_voted(const DScene &s, const Ray &ray, int mode, float t_light, Rng &rng, Hit &h, float &hu, float &hv,
+                               bool &blocked, Counters *cnt) {
+    const uint32_t NONE = 0xFFFFFFFFu;
+    const int EMPTY = 0x7FFFFFFF;
+    h.type = 0; h.obj = -1; h.t = (mode == 0) ? FLT_MAX : t_light; h.ref = 0;
+    blocked = false;
+    bool active = (mode != 2);
+    if (STATS) { if (mode == 0) cnt->closest++; else if (mode == 1) cnt->shadow++; }
+    const SphereRay sr = make_sphere_ray(ray);
+    const int ns = s.n_spheres;
+    if (s.abvh_root < 0) {   // few analytic primitives: the reference's linear loops
+        for (int i = 0; i < s.n_spheres; ++i) {
+            if (!active) break;
+            if (STATS) cnt->sphere++;
+            const float4 b = RT_LDG(s.sph_b + i);
+            const float t = sphere_t(ray, sr, RT_LDG(s.sph_a + i), b);
+            if (t < h.t && t > RT_EPSF) {
+                if (mode == 0) { h.type = 1; h.obj = i; h.t = t; }
+                else { if (STATS) cnt->rnd++; if (rng.next() > b.w) { blocked = true; active = false; } }
+            }
+        }
+        for (int i = 0; i < s.n_squares; ++i) {
+            if (!active) break;
+            if (STATS) cnt->square++;
+            float u, v;
+            const float t = square_t(ray, s.squares[i], u, v);
+            if (t < h.t && t > RT_EPSF) {
+                if (mode == 0) { h.type = 2; h.obj = i; h.t = t; hu = u; hv = v; }
+                else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.sq_transparency + i)) { blocked = true; active = false; } }
+            }
+        }
+    }
+    Inv32 iv; iv.x = safe_inv(ray.d.x); iv.y = safe_inv(ray.d.y); iv.z = safe_inv(ray.d.z);
+    float kq = 0.f, kl = 0.f;          // per-ray box enlargement, analytic phase only (build_analytic_accel)
+    int phase = -1;                    // -1: analytic hierarchy; m >= 0: mesh m
+    int node = EMPTY, sp = 0;
+    int stack[64];
+    uint32_t k = 0, kend = 0;
+    float best_t = h.t;
+    uint32_t best_ref = NONE;
+    int best_seq = 0x7FFFFFFF;
+    uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+    if (s.abvh_root >= 0) {
+        const float dist = length(ray.o - ld3(s.abvh_c)) + s.abvh_r;
+        kq = 32.f * 5.96e-8f * dist * dist; kl = 64.f * 5.96e-8f * dist;
+        node = s.abvh_root;
+    }
+    for (;;) {
+        const bool want_test = active && k < kend;
+        const bool want_node = active && !want_test;
+        const unsigned int bt = RT_BALLOT(want_test), bn = RT_BALLOT(want_node);
+        if ((bt | bn) == 0u) break;
+        if (RT_POPC(bt) >= RT_POPC(bn)) {
+            if (want_test) {
+                if (phase < 0) {
+                    const uint32_t seq = RT_LDG(s.abvh_prims + k);
+                    float t, u = 0.f, v = 0.f;
+                    if ((int)seq < ns) { if (STATS) cnt->sphere++; t = sphere_t(ray, sr, RT_LDG(s.sph_a + seq), RT_LDG(s.sph_b + seq)); }
+                    else { if (STATS) cnt->square++; t = square_t(ray, s.squares[seq - ns], u, v); }
+                    if (t > RT_EPSF) {
+                        if (mode == 0) {
+                            if (t < h.t || (t == h.t && best_seq != 0x7FFFFFFF && (int)seq < best_seq)) {
+                                best_seq = (int)seq; h.t = t;
+                                if ((int)seq < ns) { h.type = 1; h.obj = (int)seq; } else { h.type = 2; h.obj = (int)seq - ns; hu = u; hv = v; }
+                            }
+                        } else if (t < h.t) {
+                            const uint32_t bit = 1u << (seq & 31u);
+                            const uint32_t w = seq >> 5;
+                            if (w == 0u) m0 |= bit; else if (w == 1u) m1 |= bit; else if (w == 2u) m2 |= bit; else m3 |= bit;
+                        }
+                    }
+                } else {
+                    bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+                }
+                ++k;
+            }
+        } else if (want_node) {
+            if (node == EMPTY) {
+                if (sp > 0) {
+                    node = stack[--sp];
+                } else {
+                    // the current phase is exhausted
+                    if (phase < 0) {
+                        if (s.abvh_root >= 0 && mode != 0) {
+                            // replay the candidate blockers in the reference's order: one draw each until one blocks
+                            for (int w = 0; w < 4 && active; ++w) {
+                                uint32_t m = w == 0 ? m0 : (w == 1 ? m1 : (w == 2 ? m2 : m3));
+                                while (m) {
+                                    const int bit = RT_FFS((int)m) - 1;
+                                    m &= m - 1u;
+                                    const int seq = w * 32 + bit;
+                                    const float tr = seq < ns ? RT_LDG(s.sph_b + seq).w : RT_LDG(s.sq_transparency + (seq - ns));
+                                    if (STATS) cnt->rnd++;
+                                    if (rng.next() > tr) { blocked = true; active = false; break; }
+                                }
+                            }
+                        }
+                    } else {
+                        // mesh `phase` is done: Scene-level acceptance (Scene.h:221-228 closest, 248-253 shadow)
+                        if (best_ref != NONE && best_t < h.t && best_t > RT_EPSF) {
+                            if (mode == 0) { h.type = 3; h.obj = phase; h.t = best_t; h.ref = best_ref; }
+                            else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.mesh_transparency + phase)) { blocked = true; active = false; } }
+                        }
+                    }
+                    ++phase;
+                    if (phase >= s.n_meshes) active = false;
+                    if (active) {
+                        const DMesh &m = s.meshes[phase];
+                        if (STATS) cnt->mesh++;
+                        k = m.always_first; kend = k + m.always_count;
+                        node = m.bvh_root >= 0 ? m.bvh_root : EMPTY;
+                        best_t = h.t; best_ref = NONE;
+                        kq = 0.f; kl = 0.f;
+                    }
+                }
+            }
+            if (active && node != EMPTY && k >= kend) {
+                if (node >= 0) {
+                    const float4 *nodes = phase < 0 ? s.abvh_nodes : s.bvh_nodes;
+                    const float4 n0 = RT_LDG(nodes + 4 * node), n1 = RT_LDG(nodes + 4 * node + 1), n2 = RT_LDG(nodes + 4 * node + 2),
+                                 n3 = RT_LDG(nodes + 4 * node + 3);
+                    if (STATS) cnt->node++;
+                    const float p0 = kq * n3.z + kl, p1 = kq * n3.w + kl;
+                    const float limit = phase < 0 ? h.t : best_t;
+                    float d0, d1;
+                    const bool h0 = bvh_box(ray, iv, n0.x - p0, n0.y - p0, n0.z - p0, n0.w + p0, n1.x + p0, n1.y + p0, limit, d0);
+                    const bool h1 = bvh_box(ray, iv, n1.z - p1, n1.w - p1, n2.x - p1, n2.y + p1, n2.z + p1, n2.w + p1, limit, d1);
+                    const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
+                    if (h0 && h1) {
+                        const bool swap = d1 < d0;
+                        node = swap ? c1 : c0;
+                        stack[sp++] = swap ? c0 : c1;
+                    } else if (h0) node = c0;
+                    else if (h1) node = c1;
+                    else node = EMPTY;
+                } else {
+                    const uint32_t code = (uint32_t)(-(node + 1));
+                    k = code >> 3; kend = k + (code & 7u);
+                    node = EMPTY;
                 }
             }
         }

@@ -162,7 +162,7 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         q[0] = hit.type; q[1] = hit.type ? hit.obj : 0; q[2] = hit.type == 3 ? f2u(s->d.tri_den[hit.ref].y) : 0; q[3] = f2u(hit.t);
                     }
                     if ((p->variant & 0xFF) >= 2) {   // the ray-level state machine of k_render_regen, one lane
-                        const bool accel = (p->variant & 0xFF) == 3;
+                        const bool accel = (p->variant & 0xFF) == 3, voted = (p->variant & 0xFF) == 4;
                         PathState st;
                         path_begin(st, ray, rng, 0u, p->max_bounces);
                         V3 c = v3(0.f);
@@ -170,7 +170,8 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         if (p->max_bounces == 0) { c = path_fold(st, v3(0.f)); fin = true; }
                         while (!fin) {
                             Hit hit; float hu = 0.f, hv = 0.f; bool blocked;
-                            if (accel) intersect_ray<false, true>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
+                            if (voted) intersect_ray_voted<false>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
+                            else if (accel) intersect_ray<false, true>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
                             else intersect_ray<false, false>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
                             fin = path_advance<false>(s->d, st, hit, hu, hv, blocked, p->nb_ech, c, nullptr);
                         }

@@ -109,7 +109,9 @@ def test_kernel_variants_agree_bit_for_bit(gpu, assets, name):
     c = s.render(W, H, SPP, seed=0, variant=2 | (16 << 8))
     d = s.render(W, H, SPP, seed=0, variant=0)
     e = s.render(W, H, SPP, seed=0, variant=3, stats=True)
+    f = s.render(W, H, SPP, seed=0, variant=4 | (2 << 16))
     assert np.array_equal(a["linear"].view(np.uint32), e["linear"].view(np.uint32))
+    assert np.array_equal(a["linear"].view(np.uint32), f["linear"].view(np.uint32))
     for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
         assert a["stats"][k] == e["stats"][k], k
     assert np.array_equal(a["linear"].view(np.uint32), b["linear"].view(np.uint32))
@@ -142,9 +144,13 @@ def test_exact_culling_at_scale(gpu, assets, name, w, h, spp):
     s = gpu.Scene(name, aspect=w / h, seed=0)
     a = s.render(w, h, spp, seed=21, variant=1, stats=True)
     b = s.render(w, h, spp, seed=21, variant=3, stats=True)
+    c = s.render(w, h, spp, seed=21, variant=4, stats=True)
     for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
         assert a["stats"][k] == b["stats"][k], (k, a["stats"][k], b["stats"][k])
+        assert a["stats"][k] == c["stats"][k], (k, a["stats"][k], c["stats"][k])
     diff = (a["linear"].view(np.uint32) != b["linear"].view(np.uint32)).any(-1)
+    assert not diff.any(), np.argwhere(diff)[:8]
+    diff = (a["linear"].view(np.uint32) != c["linear"].view(np.uint32)).any(-1)
     assert not diff.any(), np.argwhere(diff)[:8]
     print(name, "rays %d, reference-order %.0f ms, culled %.0f ms" % (a["stats"]["n_closest_rays"] + a["stats"]["n_shadow_rays"],
                                                                    a["stats"]["kernel_ms"], b["stats"]["kernel_ms"]))

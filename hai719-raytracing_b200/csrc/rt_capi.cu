@@ -63,6 +63,7 @@ struct RenderArgs {
     unsigned long long *work_counter;
     unsigned long long *stats;          // 10 counters, or null
     int regen_min;                      // variant 1: refill idle lanes once at least this many are idle
+    int t_min;                          // variant 5: run a traversal step once at least this many lanes wait for one
 };
 
 // packed pixel index -> (x, y) via the tile prefix array
@@ -205,6 +206,24 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const DScene scene, 
         Hit h;
         float hu = 0.f, hv = 0.f;
         bool blocked;
+        if (ACCEL == 3) {
+            // variant 5: a lane wants either a TRAVERSAL step (mode 0 closest hit, mode 3 occluder candidates of a
+            // light) or a SHADOW-SAMPLE step (mode 1: exact tests on its candidate mask). One kind per iteration for
+            // the whole warp: traversal once enough lanes wait for it (or nobody wants a sample), samples otherwise.
+            const bool want_t = st.mode == 0 || st.mode == 3;
+            const unsigned int bt = __ballot_sync(0xFFFFFFFFu, want_t), bs = __ballot_sync(0xFFFFFFFFu, st.mode == 1);
+            const bool run_t = bs == 0u || __popc(bt) >= a.t_min;
+            const bool mine = run_t ? want_t : (st.mode == 1);
+            intersect_lc<STATS>(scene, st, run_t, mine, h, hu, hv, blocked, &cnt);
+            if (mine) {
+                V3 c;
+                if (path_advance<STATS, true>(scene, st, h, hu, hv, blocked, a.nb_ech, c, &cnt)) {
+                    float *o = a.samples + 3ull * st.path;
+                    o[0] = c.x; o[1] = c.y; o[2] = c.z;
+                }
+            }
+            continue;
+        }
         if (ACCEL == 2) intersect_ray_voted<STATS>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
         else intersect_ray<STATS, ACCEL == 1>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
         if (st.mode != 2) {
@@ -722,17 +741,21 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     // variant: low byte = kernel (0 auto, 1 k_render_paths: one path per lane to completion,
     // 2 k_render_regen: ray-level state machine with path regeneration and warp-voted KD traversal);
     // bits 8..15 = regeneration threshold of kernel 2 (idle lanes needed before a refill; 0 = 16)
-    if (p->variant < 0 || (p->variant & 0xFF) > 4 || (p->variant >> 20)) return fail(RT_ERR_INVALID, "unknown kernel variant");
+    if (p->variant < 0 || (p->variant & 0xFF) > 5 || (p->variant >> 28)) return fail(RT_ERR_INVALID, "unknown kernel variant");
     // bits 16..19: CTAs per SM of kernel 3 — 0 auto, 1 = 4 (<= 128 registers), 2 = 6 (<= 80), 3 = 8 (<= 64, a few spills)
     int occ = (p->variant >> 16) & 0xF;
     if (occ == 0) occ = 3;   // 8 CTAs/SM beat 6 and 4 on every config (profiles/r01_notes.md)
     const int minb = occ - 1;
     int kind = p->variant & 0xFF;
-    if (kind == 0) kind = (s->d.n_meshes > 0 || s->d.abvh_root >= 0) ? 3 : 1;   // measured: profiles/r01_notes.md
-    const bool regen = kind >= 2, accel = kind >= 3, voted = kind == 4;
+    // 5 = occluder candidates per (hit, light): needs the analytic hierarchy and at least one light
+    const bool lc_ok = s->d.abvh_root >= 0 && s->d.n_lights > 0;
+    if (kind == 0) kind = lc_ok ? 5 : (s->d.n_meshes > 0 || s->d.abvh_root >= 0) ? 3 : 1;   // measured: profiles/r01_notes.md
+    if (kind == 5 && !lc_ok) kind = 3;
+    const bool regen = kind >= 2, accel = kind >= 3, voted = kind == 4, lc = kind == 5;
     typedef void (*RenderKernel)(const DScene, const DCamera, const RenderArgs);
     RenderKernel fn;
-    if (voted)      fn = want_stats ? k_render_regen<true, 2, 4> : minb == 0 ? k_render_regen<false, 2, 4> : minb == 1 ? k_render_regen<false, 2, 6> : k_render_regen<false, 2, 8>;
+    if (lc)         fn = want_stats ? k_render_regen<true, 3, 4> : minb == 0 ? k_render_regen<false, 3, 4> : minb == 1 ? k_render_regen<false, 3, 6> : k_render_regen<false, 3, 8>;
+    else if (voted)      fn = want_stats ? k_render_regen<true, 2, 4> : minb == 0 ? k_render_regen<false, 2, 4> : minb == 1 ? k_render_regen<false, 2, 6> : k_render_regen<false, 2, 8>;
     else if (accel) fn = want_stats ? k_render_regen<true, 1, 4> : minb == 0 ? k_render_regen<false, 1, 4> : minb == 1 ? k_render_regen<false, 1, 6> : k_render_regen<false, 1, 8>;
     else if (regen) fn = want_stats ? k_render_regen<true, 0, 4> : k_render_regen<false, 0, 4>;
     else            fn = want_stats ? k_render_paths<true> : k_render_paths<false>;
@@ -743,6 +766,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     a.tiles = s->d_tiles; a.tile_off = s->d_tile_off; a.n_tiles = (int)n_tiles;
     a.width = p->width; a.height = p->height; a.spp = p->spp; a.max_bounces = p->max_bounces; a.nb_ech = p->nb_ech;
     a.regen_min = ((p->variant >> 8) & 0xFF) ? std::min(32, (p->variant >> 8) & 0xFF) : 16;
+    a.t_min = ((p->variant >> 20) & 0xFF) ? std::min(32, (p->variant >> 20) & 0xFF) : 16;   // bits 20..27: traversal threshold of kernel 5
     a.seed = p->seed; a.samples = s->samples; a.work_counter = s->counters; a.stats = want_stats ? s->counters + 1 : nullptr;
     uint32_t launches = 0;
     RT_CUDA(cudaMemsetAsync(s->counters, 0, 16 * sizeof(unsigned long long), st));

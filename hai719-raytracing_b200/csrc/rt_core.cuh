@@ -861,7 +861,7 @@ RT_HD V3 trace_path(const DScene &s, Ray ray, Rng &rng, int max_bounces, int nb_
 struct PathState {
     Rng rng;
     Ray ray;             // the ray to intersect next
-    int mode;            // 0 closest hit, 1 shadow sample, 2 idle (no path)
+    int mode;            // 0 closest hit, 1 shadow sample, 2 idle (no path), 3 collect the occluder candidates of light `light` (variant 5)
     int N;               // remaining bounces (NRemainingBounces of rayTraceRecursive)
     int depth;           // records written so far
     uint32_t path;       // index of the path in the chunk (output slot)
@@ -871,6 +871,7 @@ struct PathState {
     int light, j, blocked;
     float t_light;
     int max_bounces;
+    uint32_t cm0, cm1, cm2, cm3;   // variant 5: analytic primitives (sequence index = bit) that can occlude light `light` from P
     V3 rec_c[RT_MAX_BOUNCES], rec_kd[RT_MAX_BOUNCES], rec_e[RT_MAX_BOUNCES];
 };
 
@@ -1171,6 +1172,184 @@ RT_HD void intersect_ray_voted(const DScene &s, const Ray &ray, int mode, float 
     }
 }
 
+// ---- variant 5: occluder candidates per (hit point, light) instead of per shadow ray ---------------
+// Scene::rayTraceRecursive fires NB_ECH shadow rays per light from the same point P towards points
+// lj = light.pos + delta * u, |u| = 1 (Scene.h:325-330): 81 % of all rays on config 2, each of which
+// walked the culling hierarchy on its own in variant 3. Every point such a ray can report a hit at,
+// P + t*Lj with t < |lj - P|, lies on the segment P..lj, hence within s*delta of the point
+// P + s*(light.pos - P) of the central segment (s in [0,1]): inside a CONE with apex P. Variant 5
+// walks the hierarchy ONCE with that cone (mode 3 of the path state machine), collecting every
+// primitive whose padded box the cone can touch into a 128-bit mask; the NB_ECH shadow samples then
+// run the reference's own sphere/square arithmetic on the candidates only, in sequence order, with
+// the reference's random_float() draws. The filter can only add candidates (it is conservative by
+// construction: max-norm cone, padded boxes, slack on every comparison), never drop an occluder, so
+// the bits are those of variants 1-4 (tests: test_kernel_variants_agree_bit_for_bit, test_exact_culling_at_scale).
+//
+// The box test is the slab test generalised to a cone of max-norm radius s*delta around O + s*D:
+//   lo - s*delta <= O + s*D <= hi + s*delta   per axis
+//   <=>  s*(D + delta) >= lo - O   and   s*(D - delta) <= hi - O
+// Each inequality bounds s from below or above depending on the sign of its coefficient; with
+// delta = 0 it is the ordinary slab test, so closest-hit rays (mode 0) and cones (mode 3) run the
+// same instructions side by side.
+struct Cone {
+    V3 o;
+    float iax, iay, iaz;    // 1 / (D + delta)
+    float ibx, iby, ibz;    // 1 / (D - delta)
+    bool nnx, nny, nnz;     // both coefficients negative: the upper face bounds s from below
+    bool pnx, pny, pnz;     // D + delta >= 0 > D - delta: both faces bound s from below, none from above
+};
+RT_HD void cone_axis(float d, float delta, float &ia, float &ib, bool &nn, bool &pn) {
+    const float A = d + delta, B = d - delta;
+    ia = safe_inv(A); ib = safe_inv(B);
+    nn = A < 0.f;
+    pn = !(A < 0.f) && (B < 0.f);
+}
+RT_HD Cone make_cone(V3 o, V3 D, float delta) {
+    Cone c; c.o = o;
+    cone_axis(D.x, delta, c.iax, c.ibx, c.nnx, c.pnx);
+    cone_axis(D.y, delta, c.iay, c.iby, c.nny, c.pny);
+    cone_axis(D.z, delta, c.iaz, c.ibz, c.nnz, c.pnz);
+    return c;
+}
+#define RT_CONE_AXIS(LO, HI, O, IA, IB, NN, PN, TN, TF)                    \
+    {                                                                      \
+        const float x0 = ((LO) - (O)) * (IA), x1 = ((HI) - (O)) * (IB);    \
+        const float un = (NN) ? x1 : x0, uf = (NN) ? x0 : x1;              \
+        TN = (PN) ? fmaxf(un, uf) : un;                                    \
+        TF = (PN) ? FLT_MAX : uf;                                          \
+    }
+// conservative cone/box overlap for s in [0, limit]; `near` = entry parameter (child ordering only)
+RT_HD bool cone_box(const Cone &c, float lx, float ly, float lz, float hx, float hy, float hz, float limit, float &near) {
+    float tnx, tfx, tny, tfy, tnz, tfz;
+    RT_CONE_AXIS(lx, hx, c.o.x, c.iax, c.ibx, c.nnx, c.pnx, tnx, tfx)
+    RT_CONE_AXIS(ly, hy, c.o.y, c.iay, c.iby, c.nny, c.pny, tny, tfy)
+    RT_CONE_AXIS(lz, hz, c.o.z, c.iaz, c.ibz, c.nnz, c.pnz, tnz, tfz)
+    const float tn = fmaxf(fmaxf(tnx, tny), tnz);
+    const float tf = fminf(fminf(fminf(tfx, tfy), tfz), limit);
+    const float slack = 1e-5f * (fabsf(tn) + fabsf(tf)) + 1e-6f;
+    near = tn;
+    return (tn - slack <= tf + slack) && (tf + slack >= 0.f);
+}
+
+// One step of the variant-5 state machine for the lanes selected by `mine`.
+//   run_t (warp-uniform) true : lanes in mode 0 (closest hit) and mode 3 (collect candidates) walk the
+//                               analytic hierarchy together; mode 0 goes on to the meshes.
+//   run_t false               : lanes in mode 1 test their candidate mask, then the meshes.
+// Requires s.abvh_root >= 0 (the kernel is only selected for such scenes).
+template <bool STATS>
+RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, Hit &h, float &hu, float &hv, bool &blocked,
+                        Counters *cnt) {
+    const Ray &ray = st.ray;
+    const int mode = st.mode;
+    h.type = 0; h.obj = -1; h.t = (mode == 0) ? FLT_MAX : st.t_light; h.ref = 0;
+    blocked = false;
+    bool done = !mine;
+    const int ns = s.n_spheres;
+    if (run_t) {
+        if (mine) {
+            const bool collect = (mode == 3);
+            if (STATS && !collect) cnt->closest++;
+            Cone cone;
+            float limit_c = 1.0001f;
+            if (collect) {
+                const DLight &L = s.lights[st.light];
+                cone = make_cone(st.P, ld3(L.pos) - st.P, (L.radius / 2.f) * 1.0001f + 1e-6f);
+            } else {
+                cone = make_cone(ray.o, ray.d, 0.f);
+            }
+            const SphereRay sr = make_sphere_ray(ray);
+            const float dist = length(cone.o - ld3(s.abvh_c)) + s.abvh_r;
+            const float kq = 32.f * 5.96e-8f * dist * dist, kl = 64.f * 5.96e-8f * dist;
+            uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+            int best_seq = 0x7FFFFFFF;
+            int stack[64];
+            int sp = 0;
+            int node = s.abvh_root;
+            for (;;) {
+                if (node >= 0) {
+                    const float4 n0 = RT_LDG(s.abvh_nodes + 4 * node), n1 = RT_LDG(s.abvh_nodes + 4 * node + 1),
+                                 n2 = RT_LDG(s.abvh_nodes + 4 * node + 2), n3 = RT_LDG(s.abvh_nodes + 4 * node + 3);
+                    if (STATS) cnt->node++;
+                    const float p0 = kq * n3.z + kl, p1 = kq * n3.w + kl;
+                    const float limit = collect ? limit_c : h.t;
+                    float d0, d1;
+                    const bool h0 = cone_box(cone, n0.x - p0, n0.y - p0, n0.z - p0, n0.w + p0, n1.x + p0, n1.y + p0, limit, d0);
+                    const bool h1 = cone_box(cone, n1.z - p1, n1.w - p1, n2.x - p1, n2.y + p1, n2.z + p1, n2.w + p1, limit, d1);
+                    const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
+                    if (h0 && h1) {
+                        const bool swap = d1 < d0;
+                        node = swap ? c1 : c0;
+                        stack[sp++] = swap ? c0 : c1;
+                        continue;
+                    }
+                    if (h0) { node = c0; continue; }
+                    if (h1) { node = c1; continue; }
+                } else {
+                    const uint32_t code = (uint32_t)(-(node + 1));
+                    const uint32_t first = code >> 3, count = code & 7u;
+                    for (uint32_t k = first; k < first + count; ++k) {
+                        const uint32_t seq = RT_LDG(s.abvh_prims + k);
+                        if (collect) {
+                            const uint32_t bit = 1u << (seq & 31u), w = seq >> 5;
+                            if (w == 0u) m0 |= bit; else if (w == 1u) m1 |= bit; else if (w == 2u) m2 |= bit; else m3 |= bit;
+                            continue;
+                        }
+                        float t, u = 0.f, v = 0.f;
+                        if ((int)seq < ns) { if (STATS) cnt->sphere++; t = sphere_t(ray, sr, RT_LDG(s.sph_a + seq), RT_LDG(s.sph_b + seq)); }
+                        else { if (STATS) cnt->square++; t = square_t(ray, s.squares[seq - ns], u, v); }
+                        if (!(t > RT_EPSF)) continue;
+                        // sequential strict '<' of the reference == smallest t, earliest in sequence on ties
+                        if (t < h.t || (t == h.t && best_seq != 0x7FFFFFFF && (int)seq < best_seq)) {
+                            best_seq = (int)seq; h.t = t;
+                            if ((int)seq < ns) { h.type = 1; h.obj = (int)seq; } else { h.type = 2; h.obj = (int)seq - ns; hu = u; hv = v; }
+                        }
+                    }
+                }
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+            if (collect) { st.cm0 = m0; st.cm1 = m1; st.cm2 = m2; st.cm3 = m3; done = true; }
+        }
+    } else if (mine) {
+        // Scene::computeShadow over the candidates, ascending sequence index = the reference's order
+        // (spheres by index, then squares by index): one draw per candidate hit until one blocks
+        if (STATS) cnt->shadow++;
+        const SphereRay sr = make_sphere_ray(ray);
+        for (int w = 0; w < 4 && !done; ++w) {
+            uint32_t m = w == 0 ? st.cm0 : (w == 1 ? st.cm1 : (w == 2 ? st.cm2 : st.cm3));
+            while (m) {
+                const int seq = w * 32 + RT_FFS((int)m) - 1;
+                m &= m - 1u;
+                float t, tr, u, v;
+                if (seq < ns) {
+                    if (STATS) cnt->sphere++;
+                    const float4 b = RT_LDG(s.sph_b + seq);
+                    t = sphere_t(ray, sr, RT_LDG(s.sph_a + seq), b);
+                    tr = b.w;
+                } else {
+                    if (STATS) cnt->square++;
+                    t = square_t(ray, s.squares[seq - ns], u, v);
+                    tr = RT_LDG(s.sq_transparency + (seq - ns));
+                }
+                if (t < h.t && t > RT_EPSF) {
+                    if (STATS) cnt->rnd++;
+                    if (st.rng.next() > tr) { blocked = true; done = true; break; }
+                }
+            }
+        }
+    }
+    // meshes: per-ray exact culling traversal, as in variant 3 (closest-hit and shadow lanes together)
+    for (int i = 0; i < s.n_meshes; ++i) {
+        if (done) break;
+        if (STATS) cnt->mesh++;
+        float t; uint32_t ref;
+        if (mesh_closest_bvh<STATS>(ray, s, s.meshes[i], h.t, t, ref, cnt) && t < h.t && t > RT_EPSF) {
+            if (mode == 0) { h.type = 3; h.obj = i; h.t = t; h.ref = ref; }
+            else { if (STATS) cnt->rnd++; if (st.rng.next() > RT_LDG(s.mesh_transparency + i)) { blocked = true; done = true; } }
+        }
+    }
+}
+
 RT_HD void path_begin(PathState &st, const Ray &primary, const Rng &rng, uint32_t path, int max_bounces) {
     st.rng = rng; st.ray = primary; st.mode = 0; st.N = max_bounces; st.depth = 0; st.path = path; st.max_bounces = max_bounces;
 }
@@ -1199,13 +1378,14 @@ RT_COLD void path_shadow_sample(const DScene &s, PathState &st, Counters *cnt) {
 
 // Start lighting with light st.light, or — when the lights are exhausted — scatter and continue.
 // Returns true when the path has ended (result in `out`).
-template <bool STATS>
+template <bool STATS, bool LC = false>
 RT_HD bool path_next_light_or_bounce(const DScene &s, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
     if (st.light < s.n_lights) {
         const V3 L = normalized(ld3(s.lights[st.light].pos) - st.P);
         const float dotLN = dot(L, st.n);
         st.color = st.color + (comp_product(ld3(s.lights[0].color), st.kd) * fmaxr(0.0f, dotLN)) * (float)(1. - (double)st.mat->transparency);
         st.j = 0; st.blocked = 0;
+        if (LC) { st.mode = 3; return false; }   // variant 5: first collect the occluder candidates of this light
         path_shadow_sample<STATS>(s, st, cnt);
         return false;
     }
@@ -1220,16 +1400,17 @@ RT_HD bool path_next_light_or_bounce(const DScene &s, PathState &st, int nb_ech,
 }
 
 // Consume the result of intersect_ray for this lane's ray and set up the next ray.
-template <bool STATS>
+template <bool STATS, bool LC = false>
 RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, float hv, bool blocked, int nb_ech, V3 &out,
                         Counters *cnt) {
+    if (LC && st.mode == 3) { path_shadow_sample<STATS>(s, st, cnt); return false; }   // candidates collected: first sample
     if (st.mode == 1) {
         if (blocked) ++st.blocked;
         if (++st.j < nb_ech) { path_shadow_sample<STATS>(s, st, cnt); return false; }
         const float shadow = (float)(1. - (double)((float)st.blocked / (float)nb_ech));
         st.color = st.color * shadow;
         ++st.light;
-        return path_next_light_or_bounce<STATS>(s, st, nb_ech, out, cnt);
+        return path_next_light_or_bounce<STATS, LC>(s, st, nb_ech, out, cnt);
     }
     // mode 0: shade the closest hit (Scene.h:270-304)
     const Ray &ray = st.ray;
@@ -1279,7 +1460,7 @@ RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, 
     st.P = P; st.n = n; st.kd = kd; st.e = e; st.mat = mat; st.in_d = ray.d;
     st.color = v3(0.f);
     st.light = 0;
-    return path_next_light_or_bounce<STATS>(s, st, nb_ech, out, cnt);
+    return path_next_light_or_bounce<STATS, LC>(s, st, nb_ech, out, cnt);
 }
 
 // ---- camera ------------------------------------------------------------------------------------

@@ -162,7 +162,9 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         q[0] = hit.type; q[1] = hit.type ? hit.obj : 0; q[2] = hit.type == 3 ? f2u(s->d.tri_den[hit.ref].y) : 0; q[3] = f2u(hit.t);
                     }
                     if ((p->variant & 0xFF) >= 2) {   // the ray-level state machine of k_render_regen, one lane
-                        const bool accel = (p->variant & 0xFF) == 3, voted = (p->variant & 0xFF) == 4;
+                        const bool voted = (p->variant & 0xFF) == 4;
+                        const bool lc = (p->variant & 0xFF) == 5 && s->d.abvh_root >= 0 && s->d.n_lights > 0;   // as rt_render_device selects
+                        const bool accel = (p->variant & 0xFF) == 3 || ((p->variant & 0xFF) == 5 && !lc);
                         PathState st;
                         path_begin(st, ray, rng, 0u, p->max_bounces);
                         V3 c = v3(0.f);
@@ -170,6 +172,11 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         if (p->max_bounces == 0) { c = path_fold(st, v3(0.f)); fin = true; }
                         while (!fin) {
                             Hit hit; float hu = 0.f, hv = 0.f; bool blocked;
+                            if (lc) {   // one lane: it always gets the step kind it wants
+                                intersect_lc<false>(s->d, st, st.mode != 1, true, hit, hu, hv, blocked, nullptr);
+                                fin = path_advance<false, true>(s->d, st, hit, hu, hv, blocked, p->nb_ech, c, nullptr);
+                                continue;
+                            }
                             if (voted) intersect_ray_voted<false>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
                             else if (accel) intersect_ray<false, true>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
                             else intersect_ray<false, false>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);

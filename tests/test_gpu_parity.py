@@ -112,6 +112,15 @@ def test_kernel_variants_agree_bit_for_bit(gpu, assets, name):
     f = s.render(W, H, SPP, seed=0, variant=4 | (2 << 16))
     assert np.array_equal(a["linear"].view(np.uint32), e["linear"].view(np.uint32))
     assert np.array_equal(a["linear"].view(np.uint32), f["linear"].view(np.uint32))
+    # variant 5 (occluder candidates per hit and light; falls back to 3 without lights / analytic hierarchy),
+    # traversal thresholds 1, 16 (default) and 32, with and without counters
+    for v in (5 | (1 << 20), 5, 5 | (32 << 20) | (2 << 16)):
+        q = s.render(W, H, SPP, seed=0, variant=v)
+        assert np.array_equal(a["linear"].view(np.uint32), q["linear"].view(np.uint32)), v
+    q = s.render(W, H, SPP, seed=0, variant=5, stats=True)
+    assert np.array_equal(a["linear"].view(np.uint32), q["linear"].view(np.uint32))
+    for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
+        assert a["stats"][k] == q["stats"][k], k
     for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
         assert a["stats"][k] == e["stats"][k], k
     assert np.array_equal(a["linear"].view(np.uint32), b["linear"].view(np.uint32))
@@ -145,9 +154,13 @@ def test_exact_culling_at_scale(gpu, assets, name, w, h, spp):
     a = s.render(w, h, spp, seed=21, variant=1, stats=True)
     b = s.render(w, h, spp, seed=21, variant=3, stats=True)
     c = s.render(w, h, spp, seed=21, variant=4, stats=True)
+    d = s.render(w, h, spp, seed=21, variant=5, stats=True)
     for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
         assert a["stats"][k] == b["stats"][k], (k, a["stats"][k], b["stats"][k])
         assert a["stats"][k] == c["stats"][k], (k, a["stats"][k], c["stats"][k])
+        assert a["stats"][k] == d["stats"][k], (k, a["stats"][k], d["stats"][k])
+    diff = (a["linear"].view(np.uint32) != d["linear"].view(np.uint32)).any(-1)
+    assert not diff.any(), np.argwhere(diff)[:8]
     diff = (a["linear"].view(np.uint32) != b["linear"].view(np.uint32)).any(-1)
     assert not diff.any(), np.argwhere(diff)[:8]
     diff = (a["linear"].view(np.uint32) != c["linear"].view(np.uint32)).any(-1)

@@ -344,7 +344,7 @@ def main():
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     fp32_unfused, fp32_fused = hb.measure_fp32_peak(local)
     # dominant kernel = k_render_paths; per-launch figures of rank 0's shard
-    n_launch = max(1, kst.n_launches // 2)
+    n_launch = max(1, kst.n_chunks)
     k_ms = kernel_ms / args.steps / n_launch
     ach_tflops = my_flops / n_launch / (k_ms * 1e-3) / 1e12
     ach_gbs = my_byts / n_launch / (k_ms * 1e-3) / 1e9

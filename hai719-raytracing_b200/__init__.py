@@ -107,7 +107,7 @@ class RtStats(C.Structure):
                 ("n_sphere_tests", C.c_uint64), ("n_square_tests", C.c_uint64), ("n_mesh_tests", C.c_uint64),
                 ("n_node_visits", C.c_uint64), ("n_tri_tests", C.c_uint64), ("n_tri_full", C.c_uint64),
                 ("n_tex_fetches", C.c_uint64), ("n_random", C.c_uint64), ("kernel_ms", C.c_double),
-                ("n_launches", C.c_uint32), ("n_tiles", C.c_uint32)]
+                ("n_launches", C.c_uint32), ("n_tiles", C.c_uint32), ("n_chunks", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

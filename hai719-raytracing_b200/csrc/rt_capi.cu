@@ -64,6 +64,8 @@ struct RenderArgs {
     unsigned long long *stats;          // 10 counters, or null
     int regen_min;                      // variant 1: refill idle lanes once at least this many are idle
     int t_min;                          // variant 5: run a traversal step once at least this many lanes wait for one
+    const float4 *cam_rays;             // k_camera_rays output per path {dir.xyz, time}, or null: generate in the render kernel
+    const unsigned int *cam_keys;       // ... and the key of the path's random stream (3 draws already taken)
 };
 
 // packed pixel index -> (x, y) via the tile prefix array
@@ -160,8 +162,39 @@ __global__ void __launch_bounds__(128, 4) k_render_paths(const DScene scene, con
 // lane intersects ONE ray (closest-hit or shadow sample) and advances its path; a lane whose path
 // has ended takes the next path index from the global counter (one warp-aggregated atomicAdd,
 // __ballot_sync/__popc ranks). Lanes stay busy whatever the depth at which their paths end.
+// Wavefront stage 1 — camera-ray generation (trace_line's per-sample prologue, main.cpp:189-192, and
+// screen_space_to_world_space_ray, matrixUtilities.h:53-74) for every path of a chunk: one thread per path,
+// fully convergent, instead of a few refilling lanes of the render kernel running ~600 instructions of fp64
+// unprojection each (and keeping them in its instruction-cache footprint). 20 B per path.
+__global__ void __launch_bounds__(256) k_camera_rays(const DCamera cam, const RenderArgs a, float4 *rays, unsigned int *keys) {
+    const unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_paths) return;
+    const unsigned int lp = (unsigned int)(a.pixel_begin + p / (unsigned int)a.spp);
+    const unsigned int smp = (unsigned int)(p % (unsigned int)a.spp);
+    int x, y;
+    packed_to_xy(a, lp, x, y);
+    Rng rng;
+    rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, smp);
+    const Ray ray = primary_ray(cam, x, y, a.width, a.height, rng);
+    rays[p] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.time);
+    keys[p] = rng.key;
+}
+
+#ifndef RT_OPT_REGEN_MERGE
+#define RT_OPT_REGEN_MERGE 1
+#endif
+#ifndef RT_OPT_GRIDCONST
+#define RT_OPT_GRIDCONST 0   /* measured slower on every config (profiles/r01_notes.md) */
+#endif
+#if RT_OPT_GRIDCONST
+// out-of-line device functions take the scene by reference: __grid_constant__ lets them read it from the
+// parameter bank instead of a per-thread local-memory copy (264 STL.128 at kernel entry, LDL on every use)
+#define RT_PARAM __grid_constant__
+#else
+#define RT_PARAM
+#endif
 template <bool STATS, int ACCEL, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_render_regen(const DScene scene, const DCamera cam, const RenderArgs a) {
+__global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScene scene, const RT_PARAM DCamera cam, const RenderArgs a) {
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
@@ -170,50 +203,66 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const DScene scene, 
     st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f; st.t_light = 0.f;
     st.rng.key = 0; st.rng.ctr = 0;
     bool exhausted = false;
-    for (;;) {
-        if (!exhausted) {
-            const unsigned int need = __ballot_sync(0xFFFFFFFFu, st.mode == 2);
-            if (__popc(need) >= a.regen_min || need == 0xFFFFFFFFu) {
-                const int leader = __ffs(need) - 1;
-                const unsigned long long n = (unsigned long long)__popc(need);
-                unsigned long long base = 0;
-                if ((int)lane == leader) base = atomicAdd(a.work_counter, n);
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (base + n >= a.n_paths) exhausted = true;
-                if (st.mode == 2) {
-                    const unsigned long long p = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
-                    if (p < a.n_paths) {
-                        const unsigned int lp = (unsigned int)(a.pixel_begin + p / (unsigned int)a.spp);
-                        const unsigned int smp = (unsigned int)(p % (unsigned int)a.spp);
-                        int x, y;
-                        packed_to_xy(a, lp, x, y);
-                        Rng rng;
-                        rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, smp);
-                        if (STATS) cnt.rnd += 3;
-                        const Ray ray = primary_ray(cam, x, y, a.width, a.height, rng);
-                        path_begin(st, ray, rng, (uint32_t)p, a.max_bounces);
-                        if (a.max_bounces == 0) {   // rayTraceRecursive(ray, 0) / 0
-                            const V3 c = path_fold(st, v3(0.f));
-                            float *o = a.samples + 3ull * p;
-                            o[0] = c.x; o[1] = c.y; o[2] = c.z;
-                            st.mode = 2;
-                        }
-                    }
+    // idle lanes (mask `need`, all of them) take the next paths of the chunk: one warp-aggregated atomicAdd
+    auto refill = [&](unsigned int need) {
+        const int leader = __ffs(need) - 1;
+        const unsigned long long n = (unsigned long long)__popc(need);
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(a.work_counter, n);
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (base + n >= a.n_paths) exhausted = true;
+        if (st.mode == 2) {
+            const unsigned long long p = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
+            if (p < a.n_paths) {
+                Rng rng;
+                Ray ray;
+                if (STATS) cnt.rnd += 3;
+                if (a.cam_rays) {
+                    const float4 r = __ldg(a.cam_rays + p);
+                    ray.o = ld3(cam.pos); ray.d = v3(r.x, r.y, r.z); ray.time = r.w;
+                    rng.key = __ldg(a.cam_keys + p); rng.ctr = 3u;
+                } else {
+                    const unsigned int lp = (unsigned int)(a.pixel_begin + p / (unsigned int)a.spp);
+                    const unsigned int smp = (unsigned int)(p % (unsigned int)a.spp);
+                    int x, y;
+                    packed_to_xy(a, lp, x, y);
+                    rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, smp);
+                    ray = primary_ray(cam, x, y, a.width, a.height, rng);
+                }
+                path_begin(st, ray, rng, (uint32_t)p, a.max_bounces);
+                if (a.max_bounces == 0) {   // rayTraceRecursive(ray, 0) / 0
+                    const V3 c = path_fold(st, v3(0.f));
+                    float *o = a.samples + 3ull * p;
+                    o[0] = c.x; o[1] = c.y; o[2] = c.z;
+                    st.mode = 2;
                 }
             }
         }
-        if (__all_sync(0xFFFFFFFFu, st.mode == 2)) break;
-        Hit h;
-        float hu = 0.f, hv = 0.f;
-        bool blocked;
+    };
+    for (;;) {
         if (ACCEL == 3) {
             // variant 5: a lane wants either a TRAVERSAL step (mode 0 closest hit, mode 3 occluder candidates of a
-            // light) or a SHADOW-SAMPLE step (mode 1: exact tests on its candidate mask). One kind per iteration for
-            // the whole warp: traversal once enough lanes wait for it (or nobody wants a sample), samples otherwise.
-            const bool want_t = st.mode == 0 || st.mode == 3;
-            const unsigned int bt = __ballot_sync(0xFFFFFFFFu, want_t), bs = __ballot_sync(0xFFFFFFFFu, st.mode == 1);
-            const bool run_t = bs == 0u || __popc(bt) >= a.t_min;
-            const bool mine = run_t ? want_t : (st.mode == 1);
+            // light; an idle lane that can still get a path counts as wanting one) or a SHADOW-SAMPLE step (mode 1:
+            // exact tests on its candidate mask). One kind per iteration for the whole warp: traversal once enough
+            // lanes wait for it (or nobody wants a sample), samples otherwise. Idle lanes refill right before a
+            // traversal step, so new paths join the cohort that is about to traverse.
+#if RT_OPT_REGEN_MERGE
+            const unsigned int bi = exhausted ? 0u : __ballot_sync(0xFFFFFFFFu, st.mode == 2);
+#else
+            if (!exhausted) {
+                const unsigned int need = __ballot_sync(0xFFFFFFFFu, st.mode == 2);
+                if (__popc(need) >= a.regen_min || need == 0xFFFFFFFFu) refill(need);
+            }
+            const unsigned int bi = 0u;
+#endif
+            const unsigned int bt = __ballot_sync(0xFFFFFFFFu, st.mode == 0 || st.mode == 3), bs = __ballot_sync(0xFFFFFFFFu, st.mode == 1);
+            if ((bi | bt | bs) == 0u) break;
+            const bool run_t = bs == 0u || __popc(bt | bi) >= a.t_min;
+            if (run_t && bi) refill(bi);
+            const bool mine = run_t ? (st.mode == 0 || st.mode == 3) : (st.mode == 1);
+            Hit h;
+            float hu = 0.f, hv = 0.f;
+            bool blocked;
             intersect_lc<STATS>(scene, st, run_t, mine, h, hu, hv, blocked, &cnt);
             if (mine) {
                 V3 c;
@@ -224,6 +273,14 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const DScene scene, 
             }
             continue;
         }
+        if (!exhausted) {
+            const unsigned int need = __ballot_sync(0xFFFFFFFFu, st.mode == 2);
+            if (__popc(need) >= a.regen_min || need == 0xFFFFFFFFu) refill(need);
+        }
+        if (__all_sync(0xFFFFFFFFu, st.mode == 2)) break;
+        Hit h;
+        float hu = 0.f, hv = 0.f;
+        bool blocked;
         if (ACCEL == 2) intersect_ray_voted<STATS>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
         else intersect_ray<STATS, ACCEL == 1>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
         if (st.mode != 2) {
@@ -357,6 +414,7 @@ struct RtScene {
     size_t bytes = 0;
     // grow-only scratch, reused across calls on the same stream
     float *samples = nullptr; size_t samples_cap = 0;
+    float4 *cam_rays = nullptr; unsigned int *cam_keys = nullptr; size_t cam_cap = 0;   // per path of a chunk (k_camera_rays)
     unsigned long long *counters = nullptr;   // [0] work counter, [1..10] stats
     TileRec *d_tiles = nullptr; unsigned int *d_tile_off = nullptr; size_t tiles_cap = 0;
     std::vector<TileRec> h_tiles; std::vector<unsigned int> h_tile_off;
@@ -494,7 +552,15 @@ int persistent_grid(RtScene *s, const void *kernel, int threads) {
     return s->sm_count * per_sm;
 }
 
-int ensure_scratch(RtScene *s, size_t sample_floats, size_t n_tiles) {
+int ensure_scratch(RtScene *s, size_t sample_floats, size_t n_tiles, size_t cam_paths) {
+    if (cam_paths > s->cam_cap) {
+        if (s->cam_rays) cudaFree(s->cam_rays);
+        if (s->cam_keys) cudaFree(s->cam_keys);
+        s->cam_rays = nullptr; s->cam_keys = nullptr; s->cam_cap = 0;
+        RT_CUDA(cudaMalloc((void **)&s->cam_rays, cam_paths * sizeof(float4)));
+        RT_CUDA(cudaMalloc((void **)&s->cam_keys, cam_paths * sizeof(unsigned int)));
+        s->cam_cap = cam_paths;
+    }
     if (sample_floats > s->samples_cap) {
         if (s->samples) cudaFree(s->samples);
         s->samples = nullptr; s->samples_cap = 0;
@@ -538,6 +604,8 @@ void rt_scene_destroy(RtScene *s) {
     cudaSetDevice(s->device);
     for (void *p : s->allocs) cudaFree(p);
     if (s->samples) cudaFree(s->samples);
+    if (s->cam_rays) cudaFree(s->cam_rays);
+    if (s->cam_keys) cudaFree(s->cam_keys);
     if (s->counters) cudaFree(s->counters);
     if (s->d_tiles) cudaFree(s->d_tiles);
     if (s->d_tile_off) cudaFree(s->d_tile_off);
@@ -731,7 +799,9 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     const unsigned long long max_paths = 16ull << 20;
     unsigned long long chunk_pixels = std::max<unsigned long long>(1, max_paths / (unsigned long long)p->spp);
     chunk_pixels = std::min(chunk_pixels, n_pixels);
-    if ((rc = ensure_scratch(s, (size_t)(chunk_pixels * p->spp * 3ull), n_tiles))) return rc;
+    // bit 28 of variant: generate camera rays inside the render kernel instead of the k_camera_rays pass (A/B switch)
+    const bool cam_split = ((p->variant >> 28) & 1) == 0 && (p->variant & 0xFF) != 1 && !((p->variant & 0xFF) == 0 && s->d.n_meshes == 0 && s->d.abvh_root < 0);
+    if ((rc = ensure_scratch(s, (size_t)(chunk_pixels * p->spp * 3ull), n_tiles, cam_split ? (size_t)(chunk_pixels * p->spp) : 0))) return rc;
     RT_CUDA(cudaMemcpyAsync(s->d_tiles, s->h_tiles.data(), n_tiles * sizeof(TileRec), cudaMemcpyHostToDevice, st));
     RT_CUDA(cudaMemcpyAsync(s->d_tile_off, s->h_tile_off.data(), (n_tiles + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
 
@@ -741,7 +811,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     // variant: low byte = kernel (0 auto, 1 k_render_paths: one path per lane to completion,
     // 2 k_render_regen: ray-level state machine with path regeneration and warp-voted KD traversal);
     // bits 8..15 = regeneration threshold of kernel 2 (idle lanes needed before a refill; 0 = 16)
-    if (p->variant < 0 || (p->variant & 0xFF) > 5 || (p->variant >> 28)) return fail(RT_ERR_INVALID, "unknown kernel variant");
+    if (p->variant < 0 || (p->variant & 0xFF) > 5 || (p->variant >> 29)) return fail(RT_ERR_INVALID, "unknown kernel variant");
     // bits 16..19: CTAs per SM of kernel 3 — 0 auto, 1 = 4 (<= 128 registers), 2 = 6 (<= 80), 3 = 8 (<= 64, a few spills)
     int occ = (p->variant >> 16) & 0xF;
     if (occ == 0) occ = 3;   // 8 CTAs/SM beat 6 and 4 on every config (profiles/r01_notes.md)
@@ -766,7 +836,9 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     a.tiles = s->d_tiles; a.tile_off = s->d_tile_off; a.n_tiles = (int)n_tiles;
     a.width = p->width; a.height = p->height; a.spp = p->spp; a.max_bounces = p->max_bounces; a.nb_ech = p->nb_ech;
     a.regen_min = ((p->variant >> 8) & 0xFF) ? std::min(32, (p->variant >> 8) & 0xFF) : 16;
-    a.t_min = ((p->variant >> 20) & 0xFF) ? std::min(32, (p->variant >> 20) & 0xFF) : 16;   // bits 20..27: traversal threshold of kernel 5
+    // bits 20..27: traversal threshold of kernel 5. Measured (profiles/r01_notes.md): 1 is best — traverse as soon as
+    // any lane wants to; the lanes then catch up with the ones sampling shadows and the warp falls into cohorts by itself
+    a.t_min = ((p->variant >> 20) & 0xFF) ? std::min(32, (p->variant >> 20) & 0xFF) : 1;
     a.seed = p->seed; a.samples = s->samples; a.work_counter = s->counters; a.stats = want_stats ? s->counters + 1 : nullptr;
     uint32_t launches = 0;
     RT_CUDA(cudaMemsetAsync(s->counters, 0, 16 * sizeof(unsigned long long), st));
@@ -778,6 +850,12 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
         if (pb) RT_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long), st));
         const unsigned long long batches = (a.n_paths + 31) / 32;
         const int g = (int)std::min<unsigned long long>((unsigned long long)grid, (batches + 3) / 4);
+        if (cam_split) {
+            a.cam_rays = s->cam_rays; a.cam_keys = s->cam_keys;
+            k_camera_rays<<<(unsigned)((a.n_paths + 255) / 256), 256, 0, st>>>(cam, a, s->cam_rays, s->cam_keys);
+            RT_CUDA(cudaGetLastError());
+            ++launches;
+        }
         fn<<<g, 128, 0, st>>>(s->d, cam, a);
         RT_CUDA(cudaGetLastError());
         k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(s->samples, pb, (unsigned int)np, p->spp, d_linear, d_gamma);
@@ -791,6 +869,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
         RT_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         stats->kernel_ms = ms;
         stats->n_launches = launches;
+        stats->n_chunks = (uint32_t)((n_pixels + chunk_pixels - 1) / chunk_pixels);
         if (want_stats) {
             unsigned long long c[11];
             RT_CUDA(cudaMemcpy(c, s->counters, sizeof c, cudaMemcpyDeviceToHost));

@@ -40,11 +40,57 @@
 // most of their stalled cycles waiting for instruction fetch (ncu: stall_no_instruction 6.5 per issue,
 // profiles/r01_notes.md). The intersection loops stay inline.
 #define RT_COLD __device__ __noinline__
+// Small helpers that are used from a dozen places (normalisation = sqrt + three IEEE divisions, ~45 SASS
+// instructions per copy) are SHARED, not inlined: after variant 5 the kernel waited on instruction fetch more
+// than on anything else (ncu: stall_no_instruction 9.3 per issue, profiles/r01_notes.md), and one hot copy
+// stays in the instruction cache where twenty cold ones do not. RT_OPT_NOINL: 0 = inline everything (old).
+#ifndef RT_OPT_NOINL
+#define RT_OPT_NOINL 1
+#endif
+#if RT_OPT_NOINL >= 1
+#define RT_SHARED1 __device__ __noinline__
+#else
+#define RT_SHARED1 __device__ __forceinline__
+#endif
+#if RT_OPT_NOINL >= 2
+#define RT_SHARED2 __device__ __noinline__
+#else
+#define RT_SHARED2 __device__ __forceinline__
+#endif
+#ifndef RT_OPT_MASKLOOP
+#define RT_OPT_MASKLOOP 0   /* one loop taking the k-th candidate of every lane together: measured 15 % slower */
+#endif
+#ifndef RT_OPT_REACH2
+#define RT_OPT_REACH2 1
+#endif
+#ifndef RT_OPT_WW
+#define RT_OPT_WW 1
+#endif
+#ifndef RT_OPT_NOINL_BOUNCE
+#define RT_OPT_NOINL_BOUNCE 1
+#endif
+#if RT_OPT_NOINL_BOUNCE
+#define RT_SHARED_BOUNCE __device__ __noinline__
+#else
+#define RT_SHARED_BOUNCE __device__ __forceinline__
+#endif
 #define RT_LDG(p) __ldg(p)
 #else
+#define RT_SHARED_BOUNCE inline
+#ifndef RT_OPT_MASKLOOP
+#define RT_OPT_MASKLOOP 0   /* one loop taking the k-th candidate of every lane together: measured 15 % slower */
+#endif
+#ifndef RT_OPT_REACH2
+#define RT_OPT_REACH2 1
+#endif
+#ifndef RT_OPT_WW
+#define RT_OPT_WW 1
+#endif
 #define RT_HD inline
 #define RT_HHD inline
 #define RT_COLD inline
+#define RT_SHARED1 inline
+#define RT_SHARED2 inline
 #define RT_LDG(p) (*(p))
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
@@ -86,7 +132,7 @@ RT_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }   // (
 RT_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 RT_HD V3 comp_product(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
 RT_HD float length(V3 a) { return sqrtf(dot(a, a)); }                        // Vec3.h:32
-RT_HD V3 normalized(V3 a) { const float L = length(a); return v3(a.x / L, a.y / L, a.z / L); }  // Vec3.h:35
+RT_SHARED1 V3 normalized(V3 a) { const float L = length(a); return v3(a.x / L, a.y / L, a.z / L); }  // Vec3.h:35
 RT_HD V3 ld3(const float *p) { return v3(p[0], p[1], p[2]); }
 RT_HD float fminr(float a, float b) { return a < b ? a : b; }                // ::min, Functions.cpp:20
 RT_HD float fmaxr(float a, float b) { return a > b ? a : b; }                // ::max, Functions.cpp:24
@@ -124,7 +170,7 @@ struct Rng {
 };
 // random_unit_vector (Functions.cpp:14-18): a point of the cube [-1,1]^3, normalised. The three
 // draws are constructor arguments, evaluated right to left by g++: z, then y, then x.
-RT_HD V3 random_unit_vector(Rng &rng) {
+RT_SHARED2 V3 random_unit_vector(Rng &rng) {
     const float z = -1.f + 2.f * rng.next();
     const float y = -1.f + 2.f * rng.next();
     const float x = -1.f + 2.f * rng.next();
@@ -205,7 +251,7 @@ struct Ray {
     float time;
 };
 // Ray(o, d, time): the Line constructor normalises d (Line.h:13-16)
-RT_HD Ray make_ray(V3 o, V3 d, float time) { Ray r; r.o = o; r.d = normalized(d); r.time = time; return r; }
+RT_SHARED2 Ray make_ray(V3 o, V3 d, float time) { Ray r; r.o = o; r.d = normalized(d); r.time = time; return r; }
 
 struct Hit {
     int type;       // 0 miss, 1 sphere, 2 square, 3 mesh
@@ -400,28 +446,45 @@ RT_COLD bool leaf_reachable_exact(const DScene &s, const Ray &ray, uint32_t leaf
     }
     return true;
 }
-RT_HD bool leaf_reachable(const DScene &s, const Ray &ray, float t, uint32_t leaf) {
+// the cheap sufficient condition alone (see above); i* = approximate reciprocals of the ray direction
+RT_HD bool leaf_contains_hit(const DScene &s, const Ray &ray, float ix, float iy, float iz, float t, uint32_t leaf) {
     const float4 lo = RT_LDG(s.node_lo + leaf), hi = RT_LDG(s.node_hi + leaf);
+    const float a0 = (lo.x - ray.o.x) * ix, a1 = (hi.x - ray.o.x) * ix;
+    const float b0 = (lo.y - ray.o.y) * iy, b1 = (hi.y - ray.o.y) * iy;
+    const float c0 = (lo.z - ray.o.z) * iz, c1 = (hi.z - ray.o.z) * iz;
+    const float ma = 1e-5f * (fabsf(a0) + fabsf(a1)) + 1e-6f, mb = 1e-5f * (fabsf(b0) + fabsf(b1)) + 1e-6f,
+                mc = 1e-5f * (fabsf(c0) + fabsf(c1)) + 1e-6f;
     bool ok = t > 1e-3f;
-    {
-        const float ix = RT_FAST_RCP(ray.d.x), iy = RT_FAST_RCP(ray.d.y), iz = RT_FAST_RCP(ray.d.z);
-        const float a0 = (lo.x - ray.o.x) * ix, a1 = (hi.x - ray.o.x) * ix;
-        const float b0 = (lo.y - ray.o.y) * iy, b1 = (hi.y - ray.o.y) * iy;
-        const float c0 = (lo.z - ray.o.z) * iz, c1 = (hi.z - ray.o.z) * iz;
-        const float ma = 1e-5f * (fabsf(a0) + fabsf(a1)) + 1e-6f, mb = 1e-5f * (fabsf(b0) + fabsf(b1)) + 1e-6f,
-                    mc = 1e-5f * (fabsf(c0) + fabsf(c1)) + 1e-6f;
-        ok = ok && (fminr(a0, a1) + ma < t) && (t < fmaxr(a0, a1) - ma);
-        ok = ok && (fminr(b0, b1) + mb < t) && (t < fmaxr(b0, b1) - mb);
-        ok = ok && (fminr(c0, c1) + mc < t) && (t < fmaxr(c0, c1) - mc);
-    }
-    if (ok) return true;
+    ok = ok && (fminr(a0, a1) + ma < t) && (t < fmaxr(a0, a1) - ma);
+    ok = ok && (fminr(b0, b1) + mb < t) && (t < fmaxr(b0, b1) - mb);
+    ok = ok && (fminr(c0, c1) + mc < t) && (t < fmaxr(c0, c1) - mc);
+    return ok;
+}
+RT_HD bool leaf_reachable(const DScene &s, const Ray &ray, float t, uint32_t leaf) {
+    if (leaf_contains_hit(s, ray, RT_FAST_RCP(ray.d.x), RT_FAST_RCP(ray.d.y), RT_FAST_RCP(ray.d.z), t, leaf)) return true;
     return leaf_reachable_exact(s, ray, leaf);
 }
-// first reachable reference of the triangle whose references start at r0, or NONE
-RT_HD uint32_t tri_first_reachable(const DScene &s, const Ray &ray, float t, uint32_t r0) {
+RT_COLD bool tri_reachable_exact(const DScene &s, const Ray &ray, uint32_t r0) {
     for (uint32_t r = r0; r != 0xFFFFFFFFu; r = RT_LDG(s.ref_next + r))
-        if (leaf_reachable(s, ray, t, RT_LDG(s.ref_leaf + r))) return r;
-    return 0xFFFFFFFFu;
+        if (leaf_reachable_exact(s, ray, RT_LDG(s.ref_leaf + r))) return true;
+    return false;
+}
+// Is ANY leaf holding the triangle (references chained from r0) reachable? Two passes: the cheap
+// sufficient test on every such leaf first - the hit point lies inside one or two of the 3-5 cells
+// that reference a triangle, and walking the parent chain in fp64 for each cell tried before that
+// one was 20 % of the pond scene's instructions at 1.7 active lanes (profiles/r01_notes.md) - and
+// only if no cell contains the hit with margin, the reference's own arithmetic up the chains.
+RT_HD bool tri_reachable(const DScene &s, const Ray &ray, float t, uint32_t r0) {
+#if RT_OPT_REACH2
+    const float ix = RT_FAST_RCP(ray.d.x), iy = RT_FAST_RCP(ray.d.y), iz = RT_FAST_RCP(ray.d.z);
+    for (uint32_t r = r0; r != 0xFFFFFFFFu; r = RT_LDG(s.ref_next + r))
+        if (leaf_contains_hit(s, ray, ix, iy, iz, t, RT_LDG(s.ref_leaf + r))) return true;
+    return tri_reachable_exact(s, ray, r0);
+#else
+    for (uint32_t r = r0; r != 0xFFFFFFFFu; r = RT_LDG(s.ref_next + r))
+        if (leaf_reachable(s, ray, t, RT_LDG(s.ref_leaf + r))) return true;
+    return false;
+#endif
 }
 // last reachable reference (decides ties between different triangles at the same t)
 RT_COLD uint32_t tri_last_reachable(const DScene &s, const Ray &ray, float t, uint32_t r0) {
@@ -456,7 +519,7 @@ RT_HD void bvh_consider(const Ray &ray, const DScene &s, uint32_t r0, float &bes
     if (STATS) cnt->tri++;
     const float t = triangle_t<STATS>(ray, s, r0, a, b, c, cnt);
     if (t < best_t) {
-        if (tri_first_reachable(s, ray, t, r0) != NONE) { best_t = t; best_ref = r0; }
+        if (tri_reachable(s, ray, t, r0)) { best_t = t; best_ref = r0; }
     } else if (t == best_t && best_ref != NONE && r0 != best_ref) {
         // two different triangles at the same parameter: the reference keeps the one in the LAST
         // reachable leaf (KDTree.cpp:63-67), the FIRST reference inside a shared leaf (:42)
@@ -484,6 +547,37 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
         int stack[64];
         int sp = 0;
         int node = m.bvh_root;
+#if RT_OPT_WW
+        // "while-while": every lane first descends to its next leaf (box tests only), then the lanes that have one
+        // test its triangles together; with one loop doing either per iteration the triangle tests ran at 2.8 of
+        // 32 lanes on the pond scene (profiles/r01_notes.md)
+        const int DONE = 0x7FFFFFFF;
+        for (;;) {
+            while (node >= 0 && node != DONE) {
+                const float4 n0 = RT_LDG(s.bvh_nodes + 4 * node), n1 = RT_LDG(s.bvh_nodes + 4 * node + 1),
+                             n2 = RT_LDG(s.bvh_nodes + 4 * node + 2), n3 = RT_LDG(s.bvh_nodes + 4 * node + 3);
+                if (STATS) cnt->node++;
+                float d0, d1;
+                const bool h0 = bvh_box(ray, iv, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, best_t, d0);
+                const bool h1 = bvh_box(ray, iv, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, best_t, d1);
+                const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
+                if (h0 && h1) {
+                    const bool swap = d1 < d0;
+                    node = swap ? c1 : c0;
+                    stack[sp++] = swap ? c0 : c1;    // depth <= 56 by construction (rt_bvh.hpp)
+                } else if (h0) node = c0;
+                else if (h1) node = c1;
+                else node = sp > 0 ? stack[--sp] : DONE;
+            }
+            if (node == DONE) break;
+            const uint32_t code = (uint32_t)(-(node + 1));
+            const uint32_t first = code >> 3, count = code & 7u;
+            for (uint32_t k = first; k < first + count; ++k)
+                bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+#else
         for (;;) {
             if (node >= 0) {
                 const float4 n0 = RT_LDG(s.bvh_nodes + 4 * node), n1 = RT_LDG(s.bvh_nodes + 4 * node + 1),
@@ -510,6 +604,7 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
             if (sp == 0) break;
             node = stack[--sp];
         }
+#endif
     }
     if (best_ref == NONE) return false;
     t_out = best_t;
@@ -1311,6 +1406,49 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
             if (collect) { st.cm0 = m0; st.cm1 = m1; st.cm2 = m2; st.cm3 = m3; done = true; }
         }
     } else if (mine) {
+#if RT_OPT_MASKLOOP
+        // Scene::computeShadow over the candidates, ascending sequence index = the reference's order
+        // (spheres by index, then squares by index): one draw per candidate hit until one blocks.
+        // All lanes take their k-th candidate together, spheres in a first loop and squares in a second
+        // (squares follow every sphere in the sequence), so both bodies stay convergent.
+        if (STATS) cnt->shadow++;
+        const SphereRay sr = make_sphere_ray(ray);
+        uint32_t m0 = st.cm0, m1 = st.cm1, m2 = st.cm2, m3 = st.cm3;
+        for (;;) {
+            if (done) break;
+            const int base = m0 ? 0 : (m1 ? 32 : (m2 ? 64 : 96));
+            const uint32_t m = m0 ? m0 : (m1 ? m1 : (m2 ? m2 : m3));
+            if (m == 0u) break;
+            const int seq = base + RT_FFS((int)m) - 1;
+            if (seq >= ns) break;
+            const uint32_t rest = m & (m - 1u);
+            if (base == 0) m0 = rest; else if (base == 32) m1 = rest; else if (base == 64) m2 = rest; else m3 = rest;
+            if (STATS) cnt->sphere++;
+            const float4 b = RT_LDG(s.sph_b + seq);
+            const float t = sphere_t(ray, sr, RT_LDG(s.sph_a + seq), b);
+            if (t < h.t && t > RT_EPSF) {
+                if (STATS) cnt->rnd++;
+                if (st.rng.next() > b.w) { blocked = true; done = true; }
+            }
+        }
+        for (;;) {
+            if (done) break;
+            const int base = m0 ? 0 : (m1 ? 32 : (m2 ? 64 : 96));
+            const uint32_t m = m0 ? m0 : (m1 ? m1 : (m2 ? m2 : m3));
+            if (m == 0u) break;
+            const int seq = base + RT_FFS((int)m) - 1;
+            const uint32_t rest = m & (m - 1u);
+            if (base == 0) m0 = rest; else if (base == 32) m1 = rest; else if (base == 64) m2 = rest; else m3 = rest;
+            if (STATS) cnt->square++;
+            float u, v;
+            const float t = square_t(ray, s.squares[seq - ns], u, v);
+            if (t < h.t && t > RT_EPSF) {
+                if (STATS) cnt->rnd++;
+                if (st.rng.next() > RT_LDG(s.sq_transparency + (seq - ns))) { blocked = true; done = true; }
+            }
+        }
+    }
+#else
         // Scene::computeShadow over the candidates, ascending sequence index = the reference's order
         // (spheres by index, then squares by index): one draw per candidate hit until one blocks
         if (STATS) cnt->shadow++;
@@ -1338,6 +1476,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
             }
         }
     }
+#endif
     // meshes: per-ray exact culling traversal, as in variant 3 (closest-hit and shadow lanes together)
     for (int i = 0; i < s.n_meshes; ++i) {
         if (done) break;
@@ -1379,7 +1518,7 @@ RT_COLD void path_shadow_sample(const DScene &s, PathState &st, Counters *cnt) {
 // Start lighting with light st.light, or — when the lights are exhausted — scatter and continue.
 // Returns true when the path has ended (result in `out`).
 template <bool STATS, bool LC = false>
-RT_HD bool path_next_light_or_bounce(const DScene &s, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
+RT_SHARED_BOUNCE bool path_next_light_or_bounce(const DScene &s, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
     if (st.light < s.n_lights) {
         const V3 L = normalized(ld3(s.lights[st.light].pos) - st.P);
         const float dotLN = dot(L, st.n);

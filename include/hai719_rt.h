@@ -29,7 +29,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define HAI719_RT_ABI_VERSION 1
+#define HAI719_RT_ABI_VERSION 2
 
 typedef enum RtStatus {
     RT_OK = 0,
@@ -166,9 +166,13 @@ typedef struct RtRenderParams {
     int32_t rank, n_ranks;
     int32_t tile_w, tile_h;      /* 0 = default 32 x 32                                              */
     int32_t collect_stats;       /* fill the work counters of RtStats (slower)                       */
-    int32_t variant;             /* 0 = auto. Low byte: 1 = one path per lane (k_render_paths), 2 = ray-level
-                                    state machine with path regeneration (k_render_regen); bits 8..15 =
-                                    regeneration threshold of kernel 2. All variants give identical bits. */
+    int32_t variant;             /* 0 = auto. Low byte = kernel: 1 one path per lane (k_render_paths); 2 ray-level
+                                    state machine with path regeneration (k_render_regen), reference-order KD walk;
+                                    3 the same over the exact culling hierarchies; 4 warp-voted walk of those;
+                                    5 occluder candidates per (hit, light) + gated traversal / shadow-sample
+                                    phases. Tuning bits: 8..15 regeneration threshold, 16..19 CTAs per SM,
+                                    20..27 traversal threshold of kernel 5, 28 = no separate camera-ray pass.
+                                    All variants give identical bits (tests/test_gpu_parity.py). */
 } RtRenderParams;
 
 typedef struct RtStats {
@@ -184,6 +188,8 @@ typedef struct RtStats {
     double   kernel_ms;          /* device time of the trace kernels of this call (CUDA events)      */
     uint32_t n_launches;         /* kernels launched by this call                                    */
     uint32_t n_tiles;            /* tiles rendered by this rank                                      */
+    uint32_t n_chunks;           /* launches of the render kernel (the image is rendered in chunks of <= 16 Mi paths) */
+    uint32_t reserved;
 } RtStats;
 
 /* Random numbers. The reference draws from a time-seeded mt19937 shared by all threads without a

@@ -294,6 +294,179 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScen
     if (STATS) flush_counters(cnt, a.stats);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Variant 6 — wavefront. The same per-ray device functions as the state-machine kernel, cut into
+// three kernels per bounce level so that every warp resident on an SM runs the same small piece of
+// code (the single kernel waited on instruction fetch more than on anything else: its hot code is
+// ~2 000 instructions against a 32 KB L1.5 instruction cache, profiles/r01_notes.md):
+//   k_camera_rays  primary rays of the chunk (above)
+//   k_wf_trace     closest hit (Scene::computeIntersection) + shading of the hit (Scene.h:270-304) for
+//                  every live path; paths that miss fold their sky colour and finish
+//   k_wf_light     direct lighting of the hit — per light one cone walk for the occluder candidates,
+//                  then the NB_ECH shadow samples in registers — then Material::scatter; paths
+//                  that used their last bounce fold and finish, the others queue for the next level
+// Both are PERSISTENT: warps fetch batches of 32 queue entries with one atomicAdd, and survivors are
+// appended to the next queue with one warp-aggregated atomicAdd (__ballot_sync/__popc ranks), so the
+// host never needs to know how many paths are alive. Path state between kernels lives in HBM as
+// float4 SoA records (one 128-bit access per field and lane): 40 B ray + 88 B hit + 48 B per bounce.
+struct WfArgs {
+    unsigned int n_paths;              // paths of this chunk (slots 0 .. n_paths-1)
+    int max_bounces, nb_ech, level;
+    const float4 *cam_rays; const unsigned int *cam_keys;   // level 0 input
+    float4 *ray0, *ray1;               // {o.xyz, time}, {d.xyz, bits(N | depth << 8)}
+    uint2 *rng;                        // {key, ctr}
+    float4 *hit0, *hit1, *hit2, *hit3, *hit4;   // {P, time} {n, bits(kind << 28 | obj)} {kd, bits(N | depth << 8)} {e, -} {in_d, -}
+    float4 *rec; unsigned long long rec_stride;
+    unsigned int *q_in, *q_out;        // trace: q_in = live paths (level > 0), q_out = paths with a hit; light: the reverse
+    unsigned int *ctr;                 // per level 4 counters: [4L] trace head, [4L+1] trace count, [4L+2] light head, [4L+3] light count
+    float *samples;
+    unsigned long long *stats;
+};
+
+__device__ __forceinline__ void wf_push(unsigned int *queue, unsigned int *count, bool alive, unsigned int slot) {
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int m = __ballot_sync(0xFFFFFFFFu, alive);
+    if (m == 0u) return;
+    const int leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if ((int)lane == leader) base = atomicAdd(count, (unsigned int)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (alive) queue[base + __popc(m & ((1u << lane) - 1u))] = slot;
+}
+
+template <bool STATS, bool LC>
+__global__ void __launch_bounds__(128, 8) k_wf_trace(const DScene scene, const DCamera cam, const WfArgs w) {
+    Counters cnt;
+    if (STATS) memset(&cnt, 0, sizeof cnt);
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int count = w.level == 0 ? w.n_paths : w.ctr[4 * w.level + 1];
+    for (;;) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(w.ctr + 4 * w.level, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= count) break;
+        const unsigned int i = base + lane;
+        const bool valid = i < count;
+        PathState st;
+        st.mode = 2; st.t_light = 0.f; st.light = 0;
+        st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
+        st.rng.key = 0; st.rng.ctr = 0;
+        st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
+        unsigned int slot = 0;
+        if (valid) {
+            if (w.level == 0) {
+                slot = i;
+                const float4 r = __ldg(w.cam_rays + slot);
+                st.ray.o = ld3(cam.pos); st.ray.d = v3(r.x, r.y, r.z); st.ray.time = r.w;
+                st.rng.key = __ldg(w.cam_keys + slot); st.rng.ctr = 3u;
+                st.N = w.max_bounces; st.depth = 0;
+                if (STATS) cnt.rnd += 3;
+            } else {
+                slot = w.q_in[i];
+                const float4 a = w.ray0[slot], b = w.ray1[slot];
+                const uint2 g = w.rng[slot];
+                st.ray.o = v3(a.x, a.y, a.z); st.ray.time = a.w; st.ray.d = v3(b.x, b.y, b.z);
+                st.N = (int)(f2u(b.w) & 0xFFu); st.depth = (int)(f2u(b.w) >> 8);
+                st.rng.key = g.x; st.rng.ctr = g.y;
+            }
+            st.path = slot; st.mode = 0;
+        }
+        Hit h;
+        float hu = 0.f, hv = 0.f;
+        bool blocked;
+        if (LC) intersect_lc<STATS>(scene, st, true, valid, h, hu, hv, blocked, &cnt);
+        else intersect_ray<STATS, true>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
+        bool lit = false;
+        if (valid) {
+            V3 c;
+            if (path_shade<STATS, true>(scene, st, h, hu, hv, c, &cnt)) {
+                float *o = w.samples + 3ull * slot;
+                o[0] = c.x; o[1] = c.y; o[2] = c.z;
+            } else {
+                lit = true;
+                const uint32_t kind = (uint32_t)h.type, obj = (uint32_t)h.obj;   // st.mat = {sph,sq,mesh}_mat[obj]
+                w.hit0[slot] = make_float4(st.P.x, st.P.y, st.P.z, st.ray.time);
+                w.hit1[slot] = make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | obj));
+                w.hit2[slot] = make_float4(st.kd.x, st.kd.y, st.kd.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8)));
+                w.hit3[slot] = make_float4(st.e.x, st.e.y, st.e.z, 0.f);
+                w.hit4[slot] = make_float4(st.in_d.x, st.in_d.y, st.in_d.z, 0.f);
+                w.rng[slot] = make_uint2(st.rng.key, st.rng.ctr);
+            }
+        }
+        wf_push(w.q_out, w.ctr + 4 * w.level + 3, lit, slot);
+    }
+    if (STATS) flush_counters(cnt, w.stats);
+}
+
+template <bool STATS, bool LC>
+__global__ void __launch_bounds__(128, 8) k_wf_light(const DScene scene, const WfArgs w) {
+    Counters cnt;
+    if (STATS) memset(&cnt, 0, sizeof cnt);
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int count = w.ctr[4 * w.level + 3];
+    for (;;) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(w.ctr + 4 * w.level + 2, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= count) break;
+        const unsigned int i = base + lane;
+        const bool valid = i < count;
+        PathState st;
+        st.mode = 2; st.t_light = 0.f; st.light = 0;
+        st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
+        st.rng.key = 0; st.rng.ctr = 0;
+        st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
+        unsigned int slot = 0;
+        bool fin = true;
+        V3 c = v3(0.f);
+        if (valid) {
+            slot = w.q_in[i];
+            const float4 h0 = w.hit0[slot], h1 = w.hit1[slot], h2 = w.hit2[slot], h3 = w.hit3[slot], h4 = w.hit4[slot];
+            const uint2 g = w.rng[slot];
+            st.P = v3(h0.x, h0.y, h0.z); st.ray.time = h0.w;
+            st.n = v3(h1.x, h1.y, h1.z);
+            const uint32_t code = f2u(h1.w), kind = code >> 28, obj = code & 0x0FFFFFFFu;
+            st.mat = kind == 3u ? scene.mesh_mat + obj : (kind == 2u ? scene.sq_mat + obj : scene.sph_mat + obj);
+            st.kd = v3(h2.x, h2.y, h2.z);
+            st.N = (int)(f2u(h2.w) & 0xFFu); st.depth = (int)(f2u(h2.w) >> 8);
+            st.e = v3(h3.x, h3.y, h3.z);
+            st.in_d = v3(h4.x, h4.y, h4.z);
+            st.rng.key = g.x; st.rng.ctr = g.y;
+            st.path = slot; st.color = v3(0.f); st.light = 0; st.mode = 0;
+            fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
+        }
+        // every lane has the same number of lights and shadow samples ahead of it, so the warp walks
+        // mode 3 (candidates) -> mode 1 x NB_ECH -> next light ... -> scatter in lockstep
+        for (;;) {
+            const bool live = valid && !fin && st.mode != 0;
+            const unsigned int bt = __ballot_sync(0xFFFFFFFFu, live && st.mode == 3), bs = __ballot_sync(0xFFFFFFFFu, live && st.mode == 1);
+            if ((bt | bs) == 0u) break;
+            const bool run_t = bt != 0u;
+            const bool mine = live && (run_t ? st.mode == 3 : st.mode == 1);
+            Hit h;
+            float hu = 0.f, hv = 0.f;
+            bool blocked;
+            if (LC) intersect_lc<STATS>(scene, st, run_t, mine, h, hu, hv, blocked, &cnt);
+            else intersect_ray<STATS, true>(scene, st.ray, mine ? st.mode : 2, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
+            if (mine) fin = path_advance<STATS, LC, true>(scene, st, h, hu, hv, blocked, w.nb_ech, c, &cnt);
+        }
+        bool alive = false;
+        if (valid) {
+            if (fin) {
+                float *o = w.samples + 3ull * slot;
+                o[0] = c.x; o[1] = c.y; o[2] = c.z;
+            } else {
+                alive = true;
+                w.ray0[slot] = make_float4(st.ray.o.x, st.ray.o.y, st.ray.o.z, st.ray.time);
+                w.ray1[slot] = make_float4(st.ray.d.x, st.ray.d.y, st.ray.d.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8)));
+                w.rng[slot] = make_uint2(st.rng.key, st.rng.ctr);
+            }
+        }
+        wf_push(w.q_out, w.ctr + 4 * (w.level + 1) + 1, alive, slot);
+    }
+    if (STATS) flush_counters(cnt, w.stats);
+}
+
 // image[pixel] = (sum of its samples, in sample order) / nsamples ; then gamma
 __global__ void k_resolve(const float *samples, unsigned long long pixel_begin, unsigned int n_pixels, int spp,
                           float *linear_out, float *gamma_out) {
@@ -415,6 +588,9 @@ struct RtScene {
     // grow-only scratch, reused across calls on the same stream
     float *samples = nullptr; size_t samples_cap = 0;
     float4 *cam_rays = nullptr; unsigned int *cam_keys = nullptr; size_t cam_cap = 0;   // per path of a chunk (k_camera_rays)
+    // wavefront state (variant 6), per path of a chunk: 7 float4 fields + rng + 2 queues, and 3 float4 per bounce
+    float4 *wf_f4 = nullptr; uint2 *wf_rng = nullptr; unsigned int *wf_q = nullptr; float4 *wf_rec = nullptr; unsigned int *wf_ctr = nullptr;
+    size_t wf_cap = 0; int wf_bounces = 0;
     unsigned long long *counters = nullptr;   // [0] work counter, [1..10] stats
     TileRec *d_tiles = nullptr; unsigned int *d_tile_off = nullptr; size_t tiles_cap = 0;
     std::vector<TileRec> h_tiles; std::vector<unsigned int> h_tile_off;
@@ -552,6 +728,23 @@ int persistent_grid(RtScene *s, const void *kernel, int threads) {
     return s->sm_count * per_sm;
 }
 
+int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
+    if (paths <= s->wf_cap && max_bounces <= s->wf_bounces) return RT_OK;
+    if (s->wf_f4) cudaFree(s->wf_f4);
+    if (s->wf_rng) cudaFree(s->wf_rng);
+    if (s->wf_q) cudaFree(s->wf_q);
+    if (s->wf_rec) cudaFree(s->wf_rec);
+    s->wf_f4 = nullptr; s->wf_rng = nullptr; s->wf_q = nullptr; s->wf_rec = nullptr; s->wf_cap = 0; s->wf_bounces = 0;
+    paths = std::max(paths, s->wf_cap); max_bounces = std::max(max_bounces, s->wf_bounces);
+    RT_CUDA(cudaMalloc((void **)&s->wf_f4, 7 * paths * sizeof(float4)));
+    RT_CUDA(cudaMalloc((void **)&s->wf_rng, paths * sizeof(uint2)));
+    RT_CUDA(cudaMalloc((void **)&s->wf_q, 2 * paths * sizeof(unsigned int)));
+    RT_CUDA(cudaMalloc((void **)&s->wf_rec, 3 * (size_t)std::max(1, max_bounces) * paths * sizeof(float4)));
+    if (!s->wf_ctr) RT_CUDA(cudaMalloc((void **)&s->wf_ctr, 4 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int)));
+    s->wf_cap = paths; s->wf_bounces = max_bounces;
+    return RT_OK;
+}
+
 int ensure_scratch(RtScene *s, size_t sample_floats, size_t n_tiles, size_t cam_paths) {
     if (cam_paths > s->cam_cap) {
         if (s->cam_rays) cudaFree(s->cam_rays);
@@ -606,6 +799,11 @@ void rt_scene_destroy(RtScene *s) {
     if (s->samples) cudaFree(s->samples);
     if (s->cam_rays) cudaFree(s->cam_rays);
     if (s->cam_keys) cudaFree(s->cam_keys);
+    if (s->wf_f4) cudaFree(s->wf_f4);
+    if (s->wf_rng) cudaFree(s->wf_rng);
+    if (s->wf_q) cudaFree(s->wf_q);
+    if (s->wf_rec) cudaFree(s->wf_rec);
+    if (s->wf_ctr) cudaFree(s->wf_ctr);
     if (s->counters) cudaFree(s->counters);
     if (s->d_tiles) cudaFree(s->d_tiles);
     if (s->d_tile_off) cudaFree(s->d_tile_off);
@@ -796,11 +994,13 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     if (n_pixels == 0) return RT_OK;
 
     // chunking: whole pixels, at most ~16 Mi paths in flight (192 MiB of samples)
-    const unsigned long long max_paths = 16ull << 20;
+    const int kind_req = p->variant & 0xFF;
+    const bool wavefront = kind_req == 6 && p->max_bounces > 0;
+    const unsigned long long max_paths = wavefront ? (8ull << 20) : (16ull << 20);   // wavefront state: ~130 B + 48 B/bounce per path
     unsigned long long chunk_pixels = std::max<unsigned long long>(1, max_paths / (unsigned long long)p->spp);
     chunk_pixels = std::min(chunk_pixels, n_pixels);
     // bit 28 of variant: generate camera rays inside the render kernel instead of the k_camera_rays pass (A/B switch)
-    const bool cam_split = ((p->variant >> 28) & 1) == 0 && (p->variant & 0xFF) != 1 && !((p->variant & 0xFF) == 0 && s->d.n_meshes == 0 && s->d.abvh_root < 0);
+    const bool cam_split = wavefront || ((p->variant >> 28) & 1) == 0 && (p->variant & 0xFF) != 1 && !((p->variant & 0xFF) == 0 && s->d.n_meshes == 0 && s->d.abvh_root < 0);
     if ((rc = ensure_scratch(s, (size_t)(chunk_pixels * p->spp * 3ull), n_tiles, cam_split ? (size_t)(chunk_pixels * p->spp) : 0))) return rc;
     RT_CUDA(cudaMemcpyAsync(s->d_tiles, s->h_tiles.data(), n_tiles * sizeof(TileRec), cudaMemcpyHostToDevice, st));
     RT_CUDA(cudaMemcpyAsync(s->d_tile_off, s->h_tile_off.data(), (n_tiles + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
@@ -811,7 +1011,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     // variant: low byte = kernel (0 auto, 1 k_render_paths: one path per lane to completion,
     // 2 k_render_regen: ray-level state machine with path regeneration and warp-voted KD traversal);
     // bits 8..15 = regeneration threshold of kernel 2 (idle lanes needed before a refill; 0 = 16)
-    if (p->variant < 0 || (p->variant & 0xFF) > 5 || (p->variant >> 29)) return fail(RT_ERR_INVALID, "unknown kernel variant");
+    if (p->variant < 0 || (p->variant & 0xFF) > 6 || (p->variant >> 29)) return fail(RT_ERR_INVALID, "unknown kernel variant");
     // bits 16..19: CTAs per SM of kernel 3 — 0 auto, 1 = 4 (<= 128 registers), 2 = 6 (<= 80), 3 = 8 (<= 64, a few spills)
     int occ = (p->variant >> 16) & 0xF;
     if (occ == 0) occ = 3;   // 8 CTAs/SM beat 6 and 4 on every config (profiles/r01_notes.md)
@@ -819,6 +1019,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     int kind = p->variant & 0xFF;
     // 5 = occluder candidates per (hit, light): needs the analytic hierarchy and at least one light
     const bool lc_ok = s->d.abvh_root >= 0 && s->d.n_lights > 0;
+    if (kind == 6 && !wavefront) kind = 0;   // rayTraceRecursive(ray, 0) / 0: no bounce level to run
     if (kind == 0) kind = lc_ok ? 5 : (s->d.n_meshes > 0 || s->d.abvh_root >= 0) ? 3 : 1;   // measured: profiles/r01_notes.md
     if (kind == 5 && !lc_ok) kind = 3;
     const bool regen = kind >= 2, accel = kind >= 3, voted = kind == 4, lc = kind == 5;
@@ -831,6 +1032,18 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     else            fn = want_stats ? k_render_paths<true> : k_render_paths<false>;
     const void *kern = (const void *)fn;
     const int grid = persistent_grid(s, kern, 128);
+    // wavefront kernels (variant 6): LC = cone candidates per light, possible whenever the analytic hierarchy exists
+    typedef void (*TraceKernel)(const DScene, const DCamera, const WfArgs);
+    typedef void (*LightKernel)(const DScene, const WfArgs);
+    const bool wf_lc = s->d.abvh_root >= 0;
+    TraceKernel wf_trace = want_stats ? (wf_lc ? k_wf_trace<true, true> : k_wf_trace<true, false>) : (wf_lc ? k_wf_trace<false, true> : k_wf_trace<false, false>);
+    LightKernel wf_light = want_stats ? (wf_lc ? k_wf_light<true, true> : k_wf_light<true, false>) : (wf_lc ? k_wf_light<false, true> : k_wf_light<false, false>);
+    int wf_grid_t = 0, wf_grid_l = 0;
+    if (wavefront) {
+        if ((rc = ensure_wavefront(s, (size_t)(chunk_pixels * p->spp), p->max_bounces))) return rc;
+        wf_grid_t = persistent_grid(s, (const void *)wf_trace, 128);
+        wf_grid_l = persistent_grid(s, (const void *)wf_light, 128);
+    }
 
     RenderArgs a{};
     a.tiles = s->d_tiles; a.tile_off = s->d_tile_off; a.n_tiles = (int)n_tiles;
@@ -856,11 +1069,35 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
             RT_CUDA(cudaGetLastError());
             ++launches;
         }
-        fn<<<g, 128, 0, st>>>(s->d, cam, a);
-        RT_CUDA(cudaGetLastError());
+        if (wavefront) {
+            WfArgs w{};
+            const size_t cap = s->wf_cap;
+            w.n_paths = (unsigned int)a.n_paths; w.max_bounces = p->max_bounces; w.nb_ech = p->nb_ech;
+            w.cam_rays = s->cam_rays; w.cam_keys = s->cam_keys;
+            w.ray0 = s->wf_f4; w.ray1 = s->wf_f4 + cap; w.hit0 = s->wf_f4 + 2 * cap; w.hit1 = s->wf_f4 + 3 * cap; w.hit2 = s->wf_f4 + 4 * cap;
+            w.hit3 = s->wf_f4 + 5 * cap; w.hit4 = s->wf_f4 + 6 * cap;
+            w.rng = s->wf_rng; w.rec = s->wf_rec; w.rec_stride = cap;
+            w.ctr = s->wf_ctr; w.samples = s->samples; w.stats = a.stats;
+            RT_CUDA(cudaMemsetAsync(s->wf_ctr, 0, 4 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
+            unsigned int *q_live = s->wf_q, *q_hit = s->wf_q + cap;
+            for (int level = 0; level < p->max_bounces; ++level) {
+                w.level = level;
+                w.q_in = q_live; w.q_out = q_hit;
+                wf_trace<<<std::min(wf_grid_t, g), 128, 0, st>>>(s->d, cam, w);
+                RT_CUDA(cudaGetLastError());
+                w.q_in = q_hit; w.q_out = q_live;
+                wf_light<<<std::min(wf_grid_l, g), 128, 0, st>>>(s->d, w);
+                RT_CUDA(cudaGetLastError());
+                launches += 2;
+            }
+        } else {
+            fn<<<g, 128, 0, st>>>(s->d, cam, a);
+            RT_CUDA(cudaGetLastError());
+            ++launches;
+        }
         k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(s->samples, pb, (unsigned int)np, p->spp, d_linear, d_gamma);
         RT_CUDA(cudaGetLastError());
-        launches += 2;
+        ++launches;
     }
     if (stats) {
         RT_CUDA(cudaEventRecord(s->ev1, st));

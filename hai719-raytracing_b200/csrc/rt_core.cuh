@@ -968,6 +968,10 @@ struct PathState {
     int max_bounces;
     uint32_t cm0, cm1, cm2, cm3;   // variant 5: analytic primitives (sequence index = bit) that can occlude light `light` from P
     V3 rec_c[RT_MAX_BOUNCES], rec_kd[RT_MAX_BOUNCES], rec_e[RT_MAX_BOUNCES];
+    // wavefront kernels (variant 6) keep the per-depth records in global memory instead: entry (3*depth + {0 colour,
+    // 1 kd, 2 e}) of path slot `path` is wf_rec[(3*depth + k) * wf_stride + path]; the arrays above are then unused
+    float4 *wf_rec;
+    unsigned long long wf_stride;
 };
 
 // Scene::computeIntersection and Scene::computeShadow over the same loops. mode 0: closest hit into
@@ -1494,9 +1498,18 @@ RT_HD void path_begin(PathState &st, const Ray &primary, const Rng &rng, uint32_
 }
 
 // fold the records back to front: result_k = (color_k + result_{k+1} (*) kd_k) + e_k  (Scene.h:339-341)
+template <bool WF = false>
 RT_HD V3 path_fold(const PathState &st, V3 tail) {
     V3 r = tail;
-    for (int k = st.depth - 1; k >= 0; --k) r = (st.rec_c[k] + comp_product(r, st.rec_kd[k])) + st.rec_e[k];
+    for (int k = st.depth - 1; k >= 0; --k) {
+        if (WF) {
+            const float4 c = st.wf_rec[(3ull * k + 0) * st.wf_stride + st.path], kd = st.wf_rec[(3ull * k + 1) * st.wf_stride + st.path],
+                         e = st.wf_rec[(3ull * k + 2) * st.wf_stride + st.path];
+            r = (v3(c.x, c.y, c.z) + comp_product(r, v3(kd.x, kd.y, kd.z))) + v3(e.x, e.y, e.z);
+        } else {
+            r = (st.rec_c[k] + comp_product(r, st.rec_kd[k])) + st.rec_e[k];
+        }
+    }
     r = v3(0.f) + r;
     return r / (float)st.max_bounces;
 }
@@ -1517,7 +1530,7 @@ RT_COLD void path_shadow_sample(const DScene &s, PathState &st, Counters *cnt) {
 
 // Start lighting with light st.light, or — when the lights are exhausted — scatter and continue.
 // Returns true when the path has ended (result in `out`).
-template <bool STATS, bool LC = false>
+template <bool STATS, bool LC = false, bool WF = false>
 RT_SHARED_BOUNCE bool path_next_light_or_bounce(const DScene &s, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
     if (st.light < s.n_lights) {
         const V3 L = normalized(ld3(s.lights[st.light].pos) - st.P);
@@ -1530,30 +1543,26 @@ RT_SHARED_BOUNCE bool path_next_light_or_bounce(const DScene &s, PathState &st, 
     }
     Ray in; in.o = st.P; in.d = st.in_d; in.time = st.ray.time;
     st.ray = material_scatter<STATS>(*st.mat, in, st.n, st.P, st.rng, cnt);
-    st.rec_c[st.depth] = st.color; st.rec_kd[st.depth] = st.kd; st.rec_e[st.depth] = st.e;
+    if (WF) {
+        st.wf_rec[(3ull * st.depth + 0) * st.wf_stride + st.path] = make_float4(st.color.x, st.color.y, st.color.z, 0.f);
+        st.wf_rec[(3ull * st.depth + 1) * st.wf_stride + st.path] = make_float4(st.kd.x, st.kd.y, st.kd.z, 0.f);
+        st.wf_rec[(3ull * st.depth + 2) * st.wf_stride + st.path] = make_float4(st.e.x, st.e.y, st.e.z, 0.f);
+    } else {
+        st.rec_c[st.depth] = st.color; st.rec_kd[st.depth] = st.kd; st.rec_e[st.depth] = st.e;
+    }
     ++st.depth;
     --st.N;
-    if (st.N == 0) { out = path_fold(st, v3(0.f)); st.mode = 2; return true; }
+    if (st.N == 0) { out = path_fold<WF>(st, v3(0.f)); st.mode = 2; return true; }
     st.mode = 0;
     return false;
 }
 
-// Consume the result of intersect_ray for this lane's ray and set up the next ray.
-template <bool STATS, bool LC = false>
-RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, float hv, bool blocked, int nb_ech, V3 &out,
-                        Counters *cnt) {
-    if (LC && st.mode == 3) { path_shadow_sample<STATS>(s, st, cnt); return false; }   // candidates collected: first sample
-    if (st.mode == 1) {
-        if (blocked) ++st.blocked;
-        if (++st.j < nb_ech) { path_shadow_sample<STATS>(s, st, cnt); return false; }
-        const float shadow = (float)(1. - (double)((float)st.blocked / (float)nb_ech));
-        st.color = st.color * shadow;
-        ++st.light;
-        return path_next_light_or_bounce<STATS, LC>(s, st, nb_ech, out, cnt);
-    }
-    // mode 0: shade the closest hit (Scene.h:270-304)
+// Shade the closest hit of st.ray (Scene.h:270-304): on a miss the path ends (true, result in `out`); otherwise the
+// hit context (P, n, kd, e, mat, in_d) is set up for lighting.
+template <bool STATS, bool WF = false>
+RT_HD bool path_shade(const DScene &s, PathState &st, const Hit &h, float hu, float hv, V3 &out, Counters *cnt) {
     const Ray &ray = st.ray;
-    if (h.type == 0) { out = path_fold(st, sky_color<STATS>(s, ray.d, st.N, cnt)); st.mode = 2; return true; }
+    if (h.type == 0) { out = path_fold<WF>(st, sky_color<STATS>(s, ray.d, st.N, cnt)); st.mode = 2; return true; }
     V3 P, n, kd, e;
     const DMaterial *mat;
     if (h.type == 1) {
@@ -1599,7 +1608,25 @@ RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, 
     st.P = P; st.n = n; st.kd = kd; st.e = e; st.mat = mat; st.in_d = ray.d;
     st.color = v3(0.f);
     st.light = 0;
-    return path_next_light_or_bounce<STATS, LC>(s, st, nb_ech, out, cnt);
+    return false;
+}
+
+// Consume the result of intersect_ray for this lane's ray and set up the next ray.
+template <bool STATS, bool LC = false, bool WF = false>
+RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, float hv, bool blocked, int nb_ech, V3 &out,
+                        Counters *cnt) {
+    if (LC && st.mode == 3) { path_shadow_sample<STATS>(s, st, cnt); return false; }   // candidates collected: first sample
+    if (st.mode == 1) {
+        if (blocked) ++st.blocked;
+        if (++st.j < nb_ech) { path_shadow_sample<STATS>(s, st, cnt); return false; }
+        const float shadow = (float)(1. - (double)((float)st.blocked / (float)nb_ech));
+        st.color = st.color * shadow;
+        ++st.light;
+        return path_next_light_or_bounce<STATS, LC, WF>(s, st, nb_ech, out, cnt);
+    }
+    // mode 0
+    if (path_shade<STATS, WF>(s, st, h, hu, hv, out, cnt)) return true;
+    return path_next_light_or_bounce<STATS, LC, WF>(s, st, nb_ech, out, cnt);
 }
 
 // ---- camera ------------------------------------------------------------------------------------

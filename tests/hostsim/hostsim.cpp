@@ -161,6 +161,34 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         uint32_t *q = ids + 4 * o;
                         q[0] = hit.type; q[1] = hit.type ? hit.obj : 0; q[2] = hit.type == 3 ? f2u(s->d.tri_den[hit.ref].y) : 0; q[3] = f2u(hit.t);
                     }
+                    if ((p->variant & 0xFF) == 6 && p->max_bounces > 0) {
+                        // the wavefront kernels (k_wf_trace / k_wf_light), one lane: records in "global" memory, stride 1
+                        const bool lc = s->d.abvh_root >= 0;
+                        float4 rec[3 * RT_MAX_BOUNCES];
+                        PathState st;
+                        path_begin(st, ray, rng, 0u, p->max_bounces);
+                        st.wf_rec = rec; st.wf_stride = 1;
+                        V3 c = v3(0.f);
+                        bool fin = false;
+                        for (int level = 0; level < p->max_bounces && !fin; ++level) {
+                            Hit hit; float hu = 0.f, hv = 0.f; bool blocked;
+                            if (lc) intersect_lc<false>(s->d, st, true, true, hit, hu, hv, blocked, nullptr);
+                            else intersect_ray<false, true>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
+                            if (path_shade<false, true>(s->d, st, hit, hu, hv, c, nullptr)) { fin = true; break; }
+                            if (lc) fin = path_next_light_or_bounce<false, true, true>(s->d, st, p->nb_ech, c, nullptr);
+                            else fin = path_next_light_or_bounce<false, false, true>(s->d, st, p->nb_ech, c, nullptr);
+                            while (!fin && st.mode != 0) {
+                                if (lc) {
+                                    intersect_lc<false>(s->d, st, st.mode == 3, true, hit, hu, hv, blocked, nullptr);
+                                    fin = path_advance<false, true, true>(s->d, st, hit, hu, hv, blocked, p->nb_ech, c, nullptr);
+                                } else {
+                                    intersect_ray<false, true>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
+                                    fin = path_advance<false, false, true>(s->d, st, hit, hu, hv, blocked, p->nb_ech, c, nullptr);
+                                }
+                            }
+                        }
+                        acc = acc + c;
+                    } else
                     if ((p->variant & 0xFF) >= 2) {   // the ray-level state machine of k_render_regen, one lane
                         const bool voted = (p->variant & 0xFF) == 4;
                         const bool lc = (p->variant & 0xFF) == 5 && s->d.abvh_root >= 0 && s->d.n_lights > 0;   // as rt_render_device selects

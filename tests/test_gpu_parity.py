@@ -121,6 +121,12 @@ def test_kernel_variants_agree_bit_for_bit(gpu, assets, name):
     assert np.array_equal(a["linear"].view(np.uint32), q["linear"].view(np.uint32))
     for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
         assert a["stats"][k] == q["stats"][k], k
+    # variant 6: wavefront (camera rays / trace+shade / light+scatter kernels per bounce level)
+    for st in (False, True):
+        q = s.render(W, H, SPP, seed=0, variant=6, stats=st)
+        assert np.array_equal(a["linear"].view(np.uint32), q["linear"].view(np.uint32)), st
+    for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
+        assert a["stats"][k] == q["stats"][k], k
     for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
         assert a["stats"][k] == e["stats"][k], k
     assert np.array_equal(a["linear"].view(np.uint32), b["linear"].view(np.uint32))
@@ -155,11 +161,15 @@ def test_exact_culling_at_scale(gpu, assets, name, w, h, spp):
     b = s.render(w, h, spp, seed=21, variant=3, stats=True)
     c = s.render(w, h, spp, seed=21, variant=4, stats=True)
     d = s.render(w, h, spp, seed=21, variant=5, stats=True)
+    e = s.render(w, h, spp, seed=21, variant=6, stats=True)
     for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
         assert a["stats"][k] == b["stats"][k], (k, a["stats"][k], b["stats"][k])
         assert a["stats"][k] == c["stats"][k], (k, a["stats"][k], c["stats"][k])
         assert a["stats"][k] == d["stats"][k], (k, a["stats"][k], d["stats"][k])
+        assert a["stats"][k] == e["stats"][k], (k, a["stats"][k], e["stats"][k])
     diff = (a["linear"].view(np.uint32) != d["linear"].view(np.uint32)).any(-1)
+    assert not diff.any(), np.argwhere(diff)[:8]
+    diff = (a["linear"].view(np.uint32) != e["linear"].view(np.uint32)).any(-1)
     assert not diff.any(), np.argwhere(diff)[:8]
     diff = (a["linear"].view(np.uint32) != b["linear"].view(np.uint32)).any(-1)
     assert not diff.any(), np.argwhere(diff)[:8]

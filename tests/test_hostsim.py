@@ -33,7 +33,7 @@ def sim(hb):
 
 @pytest.mark.parametrize("name", ["cornell_box", "random_spheres", "flamingo_pond", "backrooms_pool", "raccoon",
                                   "rt_in_a_weekend", "flamingo_lake", "config5"])
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_core_functions_on_cpu_match_oracle(hb, ref, assets, sim, name, variant):
     W, H, SPP = 64, 36, 2
     a = ref.scene(name, aspect=W / H)

@@ -44,6 +44,20 @@ WORKLOADS = {
 }
 
 
+def kernel_of(counts, variant):
+    """Name of the render kernel(s) rt_render_device selects (same rule as csrc/rt_capi.cu)."""
+    kind = variant & 0xFF
+    n_an = counts["spheres"] + counts["squares"]
+    abvh = 24 <= n_an <= 128
+    if kind == 0:
+        kind = 6 if abvh else (3 if counts["meshes"] > 0 else 1)
+    if kind == 5 and not (abvh and counts["lights"] > 0):
+        kind = 3
+    return {1: "k_render_paths", 2: "k_render_regen<ACCEL=0>", 3: "k_render_regen<ACCEL=1> (exact culling hierarchies)",
+            4: "k_render_regen<ACCEL=2> (warp-voted walk)", 5: "k_render_regen<ACCEL=3> (occluder candidates per light)",
+            6: "wavefront: k_camera_rays + max_bounces x (k_wf_trace + k_wf_light) per chunk; dominant kernel k_wf_light"}[kind]
+
+
 def flops_and_bytes(st):
     """SURVEY §8(d) contract formulas, from the device work counters of one step."""
     rays = st["n_closest_rays"] + st["n_shadow_rays"]
@@ -358,8 +372,9 @@ def main():
         "unit": "TFLOP/s" if bound == "fp32" else "GB/s",
         "frac": (ach_tflops / fp32_unfused) if bound == "fp32" else (ach_gbs / hbm_peak),
         "traffic": None,
-        "kernel": "k_render_regen<ACCEL>" if (scene.counts()["meshes"] > 0 or scene.counts()["spheres"] + scene.counts()["squares"] >= 24 or (args.variant & 0xFF) >= 2) and (args.variant & 0xFF) != 1 else "k_render_paths",
+        "kernel": kernel_of(scene.counts(), args.variant),
         "kernel_ms_per_launch": k_ms, "launches_per_step": n_launch,
+        "launch": "one chunk of <= 8 Mi (wavefront) / 16 Mi paths: every render kernel of the chunk, CUDA events around them on the launching stream",
         "peak_source": "fp32 unfused FMUL+FADD measured live by rt_measure_fp32_peak (fused: %.1f TFLOP/s); hbm %s" % (fp32_fused, hbm_src),
         "fp32": {"achieved_tflops": ach_tflops, "peak_tflops": fp32_unfused, "frac": ach_tflops / fp32_unfused,
                  "algorithmic_flops_per_ray": my_flops / max(1, my_rays)},

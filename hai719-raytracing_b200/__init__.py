@@ -114,12 +114,13 @@ class RtStats(C.Structure):
 
 
 # every symbol the two headers declare — tests check the libraries export exactly these
-RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy",
-              "rt_scene_device_bytes", "rt_render_pixel_count", "rt_tile_layout", "rt_render", "rt_render_device", "rt_untile_device",
+RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy", "rt_release_cached_memory",
+              "rt_scene_device_bytes", "rt_render_pixel_count", "rt_tile_layout", "rt_render", "rt_render_rgb8", "rt_quantize_device",
+              "rt_render_device", "rt_untile_device",
               "rt_trace_primary", "rt_trace_rays", "rt_shade_rays", "rt_measure_fp32_peak"]
 HOST_SYMBOLS = ["hai_last_error", "hai_scene_new", "hai_scene_free", "hai_scene_setup", "hai_scene_dump",
                 "hai_scene_flatten", "hai_scene_kd_stats", "hai_scene_counts", "hai_default_camera", "hai_render",
-                "hai_scene_device", "hai_scene_invalidate_device", "hai_ray_trace_from_camera"]
+                "hai_scene_device", "hai_scene_invalidate_device", "hai_ray_trace_from_camera", "hai_ray_trace_from_camera_rgb8"]
 
 if not (os.path.exists(LIB_RT) and os.path.exists(LIB_HOST)):
     raise ImportError("hai719-raytracing_b200: native libraries not built (%s). Run `make -C %s` or "
@@ -139,6 +140,8 @@ rt.rt_tile_layout.restype = C.c_int64
 rt.rt_tile_layout.argtypes = [C.POINTER(RtRenderParams), C.c_void_p, C.c_int64]
 rt.rt_render.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p,
                          C.POINTER(RtStats)]
+rt.rt_render_rgb8.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p]
+rt.rt_quantize_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
 rt.rt_render_device.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.POINTER(RtStats)]
 rt.rt_untile_device.argtypes = [C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -168,6 +171,8 @@ host.hai_scene_device.argtypes = [C.c_void_p, C.c_int]
 host.hai_scene_invalidate_device.argtypes = [C.c_void_p]
 host.hai_ray_trace_from_camera.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
                                            C.c_void_p]
+host.hai_ray_trace_from_camera_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
+                                                C.c_int, C.c_void_p]
 
 
 def _rt_check(rc):
@@ -321,6 +326,23 @@ class Scene:
         _rt_check(rt.rt_shade_rays(self.device_handle(device), n, org.ctypes.data, dirs.ctypes.data,
                                    t.ctypes.data if t is not None else None, C.byref(p), rgb.ctypes.data))
         return rgb
+
+    def render_rgb8(self, width, height, spp, seed=0, device=0, camera=None, **kw):
+        """rt_render_rgb8(): the bytes the reference writes to rendu.ppm, quantised on the GPU. (h, w, 3) uint8."""
+        cam = camera or default_camera(width, height)
+        p = render_params(width, height, spp, seed=seed, **kw)
+        x0, y0, x1, y1 = (p.x0, p.y0, p.x1, p.y1) if (p.x0 | p.y0 | p.x1 | p.y1) else (0, 0, width, height)
+        out = np.zeros((y1 - y0, x1 - x0, 3), np.uint8)
+        st = RtStats()
+        _rt_check(rt.rt_render_rgb8(self.device_handle(device), C.byref(cam), C.byref(p), out.ctypes.data, C.byref(st)))
+        return out
+
+    def ray_trace_from_camera_rgb8(self, width, height, nsamples, seed=0, device=0, ppm_path=None, p6=True):
+        """ray_trace_from_camera() with the output stage on the GPU; optional P6 (binary) or P3 (reference text) file."""
+        out = np.zeros((height, width, 3), np.uint8)
+        _host_check(host.hai_ray_trace_from_camera_rgb8(self.h, device, width, height, nsamples, seed,
+                                                        ppm_path.encode() if ppm_path else None, int(bool(p6)), out.ctypes.data))
+        return out
 
     def ray_trace_from_camera(self, width, height, nsamples, seed=0, device=0, ppm_path=None):
         """The whole of the reference's ray_trace_from_camera(): default camera, render, optional P3 file."""

@@ -334,8 +334,11 @@ __device__ __forceinline__ void wf_push(unsigned int *queue, unsigned int *count
     if (alive) queue[base + __popc(m & ((1u << lane) - 1u))] = slot;
 }
 
+#ifndef RT_WF_MINB
+#define RT_WF_MINB 8
+#endif
 template <bool STATS, bool LC>
-__global__ void __launch_bounds__(128, 8) k_wf_trace(const DScene scene, const DCamera cam, const WfArgs w) {
+__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene, const DCamera cam, const WfArgs w) {
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(128, 8) k_wf_trace(const DScene scene, const D
 }
 
 template <bool STATS, bool LC>
-__global__ void __launch_bounds__(128, 8) k_wf_light(const DScene scene, const WfArgs w) {
+__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene, const WfArgs w) {
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
@@ -479,6 +482,16 @@ __global__ void k_resolve(const float *samples, unsigned long long pixel_begin, 
     const unsigned long long o = 3ull * (pixel_begin + i);
     if (linear_out) { linear_out[o] = acc.x; linear_out[o + 1] = acc.y; linear_out[o + 2] = acc.z; }
     if (gamma_out) { gamma_out[o] = gamma_channel(acc.x); gamma_out[o + 1] = gamma_channel(acc.y); gamma_out[o + 2] = gamma_channel(acc.z); }
+}
+
+// main.cpp:258: (int)(255.f * min(1.f, c)); ::min(a, b) = a < b ? a : b (Functions.cpp:20), so a NaN goes through
+// and the reference's cast is undefined for it: defined here as 0, like any negative value
+__global__ void k_quantize(const float *v, size_t n, uint8_t *out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float c = v[i];
+    const float m = 255.f * (1.f < c ? 1.f : c);
+    out[i] = m > 0.f ? (uint8_t)(int)m : (uint8_t)0;
 }
 
 __global__ void k_untile(const TileRec *tiles, const unsigned int *tile_off, int n_tiles, const float *packed,
@@ -579,13 +592,10 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float *out, float a, float b,
 // ------------------------------------------------------------------------------------------------
 // host side of the C ABI
 // ------------------------------------------------------------------------------------------------
-struct RtScene {
-    int device = 0;
-    int sm_count = 0;
-    DScene d{};
-    std::vector<void *> allocs;
-    size_t bytes = 0;
-    // grow-only scratch, reused across calls on the same stream
+// Per-render scratch (grow-only). It outlives the scene that used it: rt_scene_destroy hands it to a per-device pool
+// and the next rt_scene_create on that device takes it back, so re-uploading a scene every frame (the host API's
+// default flow, and bench.py's e2e leg) does not pay cudaMalloc/cudaFree of gigabytes of path state per frame.
+struct Scratch {
     float *samples = nullptr; size_t samples_cap = 0;
     float4 *cam_rays = nullptr; unsigned int *cam_keys = nullptr; size_t cam_cap = 0;   // per path of a chunk (k_camera_rays)
     // wavefront state (variant 6), per path of a chunk: 7 float4 fields + rng + 2 queues, and 3 float4 per bounce
@@ -593,8 +603,36 @@ struct RtScene {
     size_t wf_cap = 0; int wf_bounces = 0;
     unsigned long long *counters = nullptr;   // [0] work counter, [1..10] stats
     TileRec *d_tiles = nullptr; unsigned int *d_tile_off = nullptr; size_t tiles_cap = 0;
-    std::vector<TileRec> h_tiles; std::vector<unsigned int> h_tile_off;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void release() {
+        if (samples) cudaFree(samples);
+        if (cam_rays) cudaFree(cam_rays);
+        if (cam_keys) cudaFree(cam_keys);
+        if (wf_f4) cudaFree(wf_f4);
+        if (wf_rng) cudaFree(wf_rng);
+        if (wf_q) cudaFree(wf_q);
+        if (wf_rec) cudaFree(wf_rec);
+        if (wf_ctr) cudaFree(wf_ctr);
+        if (counters) cudaFree(counters);
+        if (d_tiles) cudaFree(d_tiles);
+        if (d_tile_off) cudaFree(d_tile_off);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        *this = Scratch();
+    }
+};
+namespace {
+std::mutex g_scratch_mu;
+std::map<int, std::vector<Scratch>> g_scratch_pool;   // device -> idle scratch sets
+}  // namespace
+
+struct RtScene : Scratch {
+    int device = 0;
+    int sm_count = 0;
+    DScene d{};
+    std::vector<void *> allocs;
+    size_t bytes = 0;
+    std::vector<TileRec> h_tiles; std::vector<unsigned int> h_tile_off;
 };
 
 namespace {
@@ -795,21 +833,26 @@ int rt_device_count(void) {
 void rt_scene_destroy(RtScene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    cudaDeviceSynchronize();   // nothing of this scene may still be in flight when its arrays go
     for (void *p : s->allocs) cudaFree(p);
-    if (s->samples) cudaFree(s->samples);
-    if (s->cam_rays) cudaFree(s->cam_rays);
-    if (s->cam_keys) cudaFree(s->cam_keys);
-    if (s->wf_f4) cudaFree(s->wf_f4);
-    if (s->wf_rng) cudaFree(s->wf_rng);
-    if (s->wf_q) cudaFree(s->wf_q);
-    if (s->wf_rec) cudaFree(s->wf_rec);
-    if (s->wf_ctr) cudaFree(s->wf_ctr);
-    if (s->counters) cudaFree(s->counters);
-    if (s->d_tiles) cudaFree(s->d_tiles);
-    if (s->d_tile_off) cudaFree(s->d_tile_off);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        g_scratch_pool[s->device].push_back(static_cast<Scratch &>(*s));
+    }
     delete s;
+}
+
+int rt_release_cached_memory(int device) {
+    std::vector<Scratch> idle;
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        auto it = g_scratch_pool.find(device);
+        if (it == g_scratch_pool.end()) return RT_OK;
+        idle.swap(it->second);
+    }
+    RT_CUDA(cudaSetDevice(device));
+    for (Scratch &sc : idle) sc.release();
+    return RT_OK;
 }
 
 size_t rt_scene_device_bytes(const RtScene *s) { return s ? s->bytes : 0; }
@@ -828,6 +871,11 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
     RtScene *s = new RtScene;
     s->device = device;
     s->sm_count = sm_count;
+    {
+        std::lock_guard<std::mutex> lock(g_scratch_mu);
+        std::vector<Scratch> &pool = g_scratch_pool[device];
+        if (!pool.empty()) { static_cast<Scratch &>(*s) = pool.back(); pool.pop_back(); }
+    }
     struct Guard { RtScene *s; bool keep = false; ~Guard() { if (!keep) rt_scene_destroy(s); } } guard{s};
     DScene &d = s->d;
     d.n_spheres = (int)desc->n_spheres; d.n_squares = (int)desc->n_squares; d.n_meshes = (int)desc->n_meshes; d.n_lights = (int)desc->n_lights;
@@ -994,7 +1042,12 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     if (n_pixels == 0) return RT_OK;
 
     // chunking: whole pixels, at most ~16 Mi paths in flight (192 MiB of samples)
-    const int kind_req = p->variant & 0xFF;
+    // Kernel selection (measured on B200, profiles/r01_notes.md): the wavefront (6) wins wherever the analytic
+    // culling hierarchy exists (configs 2, 4, 5: 1.2-1.3x over the state machine); mesh scenes without it (config 3)
+    // are faster in the single state-machine kernel over the exact culling hierarchies (3); scenes with a handful of
+    // analytic primitives and nothing else (config 1) in the plain one-path-per-lane kernel (1).
+    int kind_req = p->variant & 0xFF;
+    if (kind_req == 0 && s->d.abvh_root >= 0) kind_req = 6;
     const bool wavefront = kind_req == 6 && p->max_bounces > 0;
     const unsigned long long max_paths = wavefront ? (8ull << 20) : (16ull << 20);   // wavefront state: ~130 B + 48 B/bounce per path
     unsigned long long chunk_pixels = std::max<unsigned long long>(1, max_paths / (unsigned long long)p->spp);
@@ -1016,7 +1069,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     int occ = (p->variant >> 16) & 0xF;
     if (occ == 0) occ = 3;   // 8 CTAs/SM beat 6 and 4 on every config (profiles/r01_notes.md)
     const int minb = occ - 1;
-    int kind = p->variant & 0xFF;
+    int kind = kind_req;
     // 5 = occluder candidates per (hit, light): needs the analytic hierarchy and at least one light
     const bool lc_ok = s->d.abvh_root >= 0 && s->d.n_lights > 0;
     if (kind == 6 && !wavefront) kind = 0;   // rayTraceRecursive(ray, 0) / 0: no bounce level to run
@@ -1083,10 +1136,10 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
             for (int level = 0; level < p->max_bounces; ++level) {
                 w.level = level;
                 w.q_in = q_live; w.q_out = q_hit;
-                wf_trace<<<std::min(wf_grid_t, g), 128, 0, st>>>(s->d, cam, w);
+                wf_trace<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_t, (batches + 3) / 4), 128, 0, st>>>(s->d, cam, w);
                 RT_CUDA(cudaGetLastError());
                 w.q_in = q_hit; w.q_out = q_live;
-                wf_light<<<std::min(wf_grid_l, g), 128, 0, st>>>(s->d, w);
+                wf_light<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
                 RT_CUDA(cudaGetLastError());
                 launches += 2;
             }
@@ -1220,6 +1273,56 @@ int rt_render(RtScene *s, const RtCamera *camera, const RtRenderParams *p, float
             }
         }
     }
+    return RT_OK;
+}
+
+int rt_quantize_device(const float *d_values, size_t n, uint8_t *d_bytes, int device, void *cuda_stream) {
+    if (!d_values || !d_bytes) return fail(RT_ERR_INVALID, "null argument");
+    if (n == 0) return RT_OK;
+    RT_CUDA(cudaSetDevice(device));
+    k_quantize<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(d_values, n, d_bytes);
+    RT_CUDA(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_render_rgb8(RtScene *s, const RtCamera *camera, const RtRenderParams *p, uint8_t *rgb8, RtStats *stats) {
+    if (!s || !camera || !p || !rgb8) return fail(RT_ERR_INVALID, "null argument");
+    Rect r;
+    int rc = resolve_rect(*p, r);
+    if (rc) return rc;
+    RT_CUDA(cudaSetDevice(s->device));
+    const int64_t np = rt_render_pixel_count(p);
+    if (np <= 0) { if (stats) memset(stats, 0, sizeof *stats); return RT_OK; }
+    const size_t rect_px = (size_t)(r.x1 - r.x0) * (size_t)(r.y1 - r.y0);
+    float *d_packed = nullptr, *d_image = nullptr;
+    uint8_t *d_bytes = nullptr;
+    struct Free { void *&p; ~Free() { if (p) cudaFree(p); } } f1{(void *&)d_packed}, f2{(void *&)d_image}, f3{(void *&)d_bytes};
+    RT_CUDA(cudaMalloc((void **)&d_packed, (size_t)np * 3 * sizeof(float)));
+    RT_CUDA(cudaMalloc((void **)&d_image, rect_px * 3 * sizeof(float)));
+    RT_CUDA(cudaMalloc((void **)&d_bytes, rect_px * 3));
+    RtStats local;
+    rc = rt_render_device(s, camera, p, d_packed, nullptr, nullptr, stats ? stats : &local);
+    if (rc) return rc;
+    if (p->n_ranks > 1) RT_CUDA(cudaMemset(d_image, 0, rect_px * 3 * sizeof(float)));
+    RtRenderParams q = *p;
+    int64_t off0 = 0;
+    if (p->n_ranks > 1) {
+        // untile only this rank's tiles: a one-rank view of the same tile list
+        const int rw = r.x1 - r.x0;
+        std::vector<uint8_t> hb((size_t)np * 3);
+        if ((rc = rt_quantize_device(d_packed, (size_t)np * 3, d_bytes, s->device, nullptr))) return rc;
+        RT_CUDA(cudaMemcpy(hb.data(), d_bytes, hb.size(), cudaMemcpyDeviceToHost));
+        for (size_t t = 0; t < s->h_tiles.size(); ++t) {
+            const TileRec &tr = s->h_tiles[t];
+            const uint8_t *src = hb.data() + 3 * (size_t)s->h_tile_off[t];
+            for (int y = 0; y < tr.h; ++y)
+                memcpy(rgb8 + 3 * ((size_t)(tr.y0 - r.y0 + y) * rw + (tr.x0 - r.x0)), src + 3 * (size_t)y * tr.w, (size_t)tr.w * 3);
+        }
+        return RT_OK;
+    }
+    if ((rc = rt_untile_device(&q, d_packed, &off0, d_image, s->device, nullptr))) return rc;
+    if ((rc = rt_quantize_device(d_image, rect_px * 3, d_bytes, s->device, nullptr))) return rc;
+    RT_CUDA(cudaMemcpy(rgb8, d_bytes, rect_px * 3, cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 

@@ -1,6 +1,7 @@
 #include "Renderer.h"
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <fstream>
 #include <iostream>
 
@@ -58,6 +59,59 @@ void ray_trace_from_camera(const Scene &scene, Camera &camera, int w, int h, uns
                            std::vector<Vec3> &image, const RenderOptions &opt, RtStats *stats) {
     DeviceScene dev(scene, opt.device);
     ray_trace_from_camera(dev, camera, w, h, nsamples, image, opt, stats);
+}
+
+void ray_trace_from_camera_rgb8(const DeviceScene &scene, Camera &camera, int w, int h, unsigned int nsamples,
+                                std::vector<unsigned char> &rgb8, const RenderOptions &opt, RtStats *stats) {
+    camera.apply();
+    MatrixUtilities mu;
+    mu.updateMatrices(camera);
+    RtCamera cam;
+    mu.fill(cam);
+    const RtRenderParams p = make_params(w, h, nsamples, opt);
+    const bool full = (p.x0 | p.y0 | p.x1 | p.y1) == 0;
+    const int rw = full ? w : p.x1 - p.x0, rh = full ? h : p.y1 - p.y0;
+    if (opt.verbose)
+        std::cout << "Ray tracing a " << rw << " x " << rh << " image on CUDA device " << scene.device() << " with "
+                  << nsamples << " samples per pixel" << std::endl;
+    rgb8.assign((size_t)rw * (size_t)rh * 3, 0);
+    const auto t0 = std::chrono::steady_clock::now();
+    check(rt_render_rgb8(scene.handle(), &cam, &p, rgb8.data(), stats), "rt_render_rgb8");
+    const auto t1 = std::chrono::steady_clock::now();
+    if (opt.verbose) std::cout << "  Done in " << std::chrono::duration<double>(t1 - t0).count() << " seconds" << std::endl;
+    if (!opt.ppm_path.empty()) {
+        const bool ok = opt.format == RenderOptions::P6 ? write_ppm_p6(opt.ppm_path, rw, rh, rgb8) : write_ppm_p3(opt.ppm_path, rw, rh, rgb8);
+        if (!ok) std::cout << "Could not open file: " << opt.ppm_path << std::endl;
+    }
+}
+
+bool write_ppm_p3(const std::string &filename, int w, int h, const std::vector<unsigned char> &rgb8) {
+    std::ofstream f(filename.c_str(), std::ios::binary);
+    if (f.fail()) return false;
+    f << "P3" << std::endl << w << " " << h << std::endl << 255 << std::endl;
+    char table[256][4];
+    int len[256];
+    for (int v = 0; v < 256; ++v) len[v] = std::snprintf(table[v], 4, "%d", v);
+    std::vector<char> buf;
+    buf.reserve(1 << 20);
+    const size_t n = (size_t)w * (size_t)h * 3;
+    for (size_t i = 0; i < n; ++i) {
+        const unsigned char v = rgb8[i];
+        buf.insert(buf.end(), table[v], table[v] + len[v]);
+        buf.push_back(' ');
+        if (buf.size() > (1 << 20) - 8) { f.write(buf.data(), (std::streamsize)buf.size()); buf.clear(); }
+    }
+    f.write(buf.data(), (std::streamsize)buf.size());
+    f << std::endl;
+    return !f.fail();
+}
+
+bool write_ppm_p6(const std::string &filename, int w, int h, const std::vector<unsigned char> &rgb8) {
+    std::ofstream f(filename.c_str(), std::ios::binary);
+    if (f.fail()) return false;
+    f << "P6\n" << w << " " << h << "\n255\n";
+    f.write(reinterpret_cast<const char *>(rgb8.data()), (std::streamsize)((size_t)w * (size_t)h * 3));
+    return !f.fail();
 }
 
 bool write_ppm_p3(const std::string &filename, int w, int h, const std::vector<Vec3> &image) {

@@ -35,6 +35,10 @@ struct RenderOptions {
     bool collect_stats = false;
     int variant = 0;
     std::string ppm_path = "./rendu.ppm";   // "" = do not write (the reference always writes)
+    // Output stage. P3: the reference's ASCII file, byte for byte (main.cpp:252-262) — ~400 MB of text
+    // at 8K. P6: the same 8-bit values as binary PPM, quantised on the GPU (rt_render_rgb8): 3 bytes per pixel
+    // cross PCIe and reach the file. The reference's own ppmLoader reads both.
+    enum Format { P3 = 0, P6 = 1 } format = P3;
     bool verbose = true;                    // the reference's two std::cout lines
 };
 
@@ -63,6 +67,15 @@ void ray_trace_from_camera(const Scene &scene, Camera &camera, int w, int h, uns
 
 // main.cpp:252-262 — "P3\n w h\n255\n" then (int)(255.f*min(1.f,c)) per channel, space separated.
 bool write_ppm_p3(const std::string &filename, int w, int h, const std::vector<Vec3> &image);
+// The same file from already quantised bytes (identical output whenever every channel is in [0, 1] or above, i.e. for
+// every image a PPM reader accepts), formatted through a 256-entry table: ~20x faster than operator<< per value.
+bool write_ppm_p3(const std::string &filename, int w, int h, const std::vector<unsigned char> &rgb8);
+// Binary PPM: "P6\n w h\n255\n" + w*h*3 bytes.
+bool write_ppm_p6(const std::string &filename, int w, int h, const std::vector<unsigned char> &rgb8);
+
+// Render straight to 8-bit RGB (rect_h*rect_w*3, row 0 = top): quantisation on the device, see rt_render_rgb8().
+void ray_trace_from_camera_rgb8(const DeviceScene &scene, Camera &camera, int w, int h, unsigned int nsamples,
+                                std::vector<unsigned char> &rgb8, const RenderOptions &opt = RenderOptions(), RtStats *stats = nullptr);
 
 }  // namespace hai719
 #endif

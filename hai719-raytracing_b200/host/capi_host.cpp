@@ -136,4 +136,24 @@ int hai_ray_trace_from_camera(HaiScene *s, int device, int w, int h, int nsample
     });
 }
 
+int hai_ray_trace_from_camera_rgb8(HaiScene *s, int device, int w, int h, int nsamples, uint32_t seed, const char *ppm_path,
+                                   int p6, uint8_t *rgb8) {
+    return guarded([&] {
+        RtScene *dev = hai_scene_device(s, device);
+        if (!dev) throw std::runtime_error(g_err);
+        Camera camera;
+        camera.resize(w, h);
+        camera.move(0., 0., -3.1);
+        hai719::RenderOptions opt;
+        opt.seed = seed;
+        opt.device = device;
+        opt.ppm_path = ppm_path ? ppm_path : "";
+        opt.format = p6 ? hai719::RenderOptions::P6 : hai719::RenderOptions::P3;
+        opt.verbose = false;
+        std::vector<unsigned char> bytes;
+        hai719::ray_trace_from_camera_rgb8(*s->on_device[device], camera, w, h, (unsigned)nsamples, bytes, opt);
+        if (rgb8) std::memcpy(rgb8, bytes.data(), bytes.size());
+    });
+}
+
 }  // extern "C"

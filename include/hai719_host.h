@@ -55,6 +55,11 @@ void hai_scene_invalidate_device(HaiScene *s);
 int hai_ray_trace_from_camera(HaiScene *s, int device, int w, int h, int nsamples, uint32_t seed, const char *ppm_path,
                               float *gamma_rgb);
 
+/* The same with the output stage on the GPU: 8-bit RGB (h*w*3 bytes, row 0 = top) = the values the reference
+ * writes to rendu.ppm. ppm_path (may be NULL): written as binary P6 when p6 != 0, else as the reference's P3 text. */
+int hai_ray_trace_from_camera_rgb8(HaiScene *s, int device, int w, int h, int nsamples, uint32_t seed, const char *ppm_path,
+                                   int p6, uint8_t *rgb8);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -211,7 +211,10 @@ const char *rt_last_error(void);
 
 /* Copies everything it needs to `device`; the caller keeps ownership of the host arrays. */
 int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out);
+/* Frees the scene's arrays. Its render scratch (sample, camera-ray and path-state buffers, grow-only) is kept in a
+ * per-device pool and handed to the next rt_scene_create on that device; rt_release_cached_memory frees the pool. */
 void rt_scene_destroy(RtScene *scene);
+int rt_release_cached_memory(int device);
 size_t rt_scene_device_bytes(const RtScene *scene);
 
 /* Number of pixels this rank renders under `params` (rectangle + tile sharding), i.e. the
@@ -228,6 +231,17 @@ int64_t rt_tile_layout(const RtRenderParams *params, int32_t *tiles, int64_t cap
  * With n_ranks > 1 pixels of other ranks' tiles are left untouched. */
 int rt_render(RtScene *scene, const RtCamera *camera, const RtRenderParams *params,
               float *gamma_rgb, float *linear_rgb, RtStats *stats);
+
+/* Output stage of ray_trace_from_camera() (main.cpp:252-262) on the device: the reference writes
+ * (int)(255.f * min(1.f, c)) per channel; this render returns exactly those values as bytes
+ * (rect_h*rect_w*3, row-major, host memory), quantised on the GPU so that only 3 bytes per pixel
+ * cross PCIe instead of 12. A channel that is negative or NaN — which the reference would print as
+ * a negative number — becomes 0; every value a valid PPM can hold is identical.
+ * With n_ranks > 1 only this rank's tiles are written. */
+int rt_render_rgb8(RtScene *scene, const RtCamera *camera, const RtRenderParams *params, uint8_t *rgb8, RtStats *stats);
+
+/* The same quantisation of n floats already on the device (asynchronous on `cuda_stream`). */
+int rt_quantize_device(const float *d_values, size_t n, uint8_t *d_bytes, int device, void *cuda_stream);
 
 /* Same render with DEVICE output, asynchronous on `cuda_stream` (a cudaStream_t; NULL = default
  * stream). d_gamma_rgb / d_linear_rgb (either may be NULL) receive this rank's pixels PACKED

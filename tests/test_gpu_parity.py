@@ -249,6 +249,36 @@ def test_same_seed_same_bits_and_ppm(gpu, assets, tmp_path):
     assert np.array_equal(np.array(tok[4:], dtype=np.int32), want)
 
 
+@pytest.mark.parametrize("name", ["cornell_box", "random_spheres", "backrooms_pool"])
+def test_output_stage_rgb8_p3_p6(gpu, assets, tmp_path, name):
+    """8-bit quantisation on the device. The bytes equal (int)(255.f*min(1.f,c)) of the float render
+    (main.cpp:258), the P3 file written from them is byte-identical to the reference-format file written from floats,
+    and the P6 file holds the same bytes. Crops and rank shards quantise the same pixels."""
+    w, h, spp = 170, 96, 2
+    s = gpu.Scene(name, aspect=w / h)
+    f = s.render(w, h, spp, seed=3)["gamma"]
+    want = (255.0 * np.minimum(1.0, f.astype(np.float32))).astype(np.int32)
+    assert want.min() >= 0 and want.max() <= 255
+    b = s.render_rgb8(w, h, spp, seed=3)
+    assert b.dtype == np.uint8 and np.array_equal(b.astype(np.int32), want)
+    crop = (20, 10, 150, 90)
+    assert np.array_equal(s.render_rgb8(w, h, spp, seed=3, crop=crop), b[10:90, 20:150])
+    shards = np.zeros_like(b)
+    for r in range(3):
+        part = s.render_rgb8(w, h, spp, seed=3, rank=r, n_ranks=3, tile=(16, 16))
+        shards = np.maximum(shards, part)     # other ranks' tiles are left 0
+    assert np.array_equal(shards, b)
+    # files through the host API (default camera = the one render() uses)
+    s.ray_trace_from_camera(w, h, spp, seed=3, ppm_path=str(tmp_path / "ref_p3.ppm"))
+    c = s.ray_trace_from_camera_rgb8(w, h, spp, seed=3, ppm_path=str(tmp_path / "fast_p3.ppm"), p6=False)
+    d = s.ray_trace_from_camera_rgb8(w, h, spp, seed=3, ppm_path=str(tmp_path / "out_p6.ppm"), p6=True)
+    assert np.array_equal(c, b) and np.array_equal(d, b)
+    assert open(tmp_path / "ref_p3.ppm", "rb").read() == open(tmp_path / "fast_p3.ppm", "rb").read()
+    raw = open(tmp_path / "out_p6.ppm", "rb").read()
+    head = b"P6\n%d %d\n255\n" % (w, h)
+    assert raw.startswith(head) and raw[len(head):] == b.tobytes()
+
+
 def test_device_output_and_untile(gpu, assets):
     """rt_render_device + rt_untile_device with torch-owned device buffers (what bench.py's multi-GPU path does)."""
     torch = pytest.importorskip("torch")

@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScen
 // float4 SoA records (one 128-bit access per field and lane): 40 B ray + 88 B hit + 48 B per bounce.
 struct WfArgs {
     unsigned int n_paths;              // paths of this chunk (slots 0 .. n_paths-1)
+    unsigned int max_grab;             // batches a warp may fetch with one atomic (see wf_next_batch)
     int max_bounces, nb_ech, level;
     const float4 *cam_rays; const unsigned int *cam_keys;   // level 0 input
     float4 *ray0, *ray1;               // {o.xyz, time}, {d.xyz, bits(N | depth << 8)}
@@ -323,15 +324,64 @@ struct WfArgs {
     unsigned long long *stats;
 };
 
-__device__ __forceinline__ void wf_push(unsigned int *queue, unsigned int *count, bool alive, unsigned int slot) {
+// Queue traffic. Every batch of 32 entries used to cost two atomicAdds on two counters of one 32-byte sector (work
+// fetch + append of the survivors): ~1.1 M same-address atomics per chunk, which L2 retires at roughly one per 1.3 ns —
+// the level-0 trace kernel ran exactly that long (0.68 ms for 520 k atomics, profiles/r01_notes.md). Now
+//   * a warp FETCHES several batches per atomic, guided self-scheduling: 8 batches while plenty of work is left,
+//     shrinking to 1 near the end so that the tail stays balanced (scenes with meshes always fetch 1: measured, their
+//     batches are too uneven);
+//   * survivors are STAGED per warp in shared memory (positions from __ballot_sync/__popc, no atomics) and appended to
+//     the global queue 256 at a time with one atomicAdd and coalesced 128-byte stores; the last partial block is appended
+//     with its exact size, so the queue has no holes and the next kernel's warps are full.
+#define WF_STAGE_FLUSH 256
+#define WF_STAGE_CAP (WF_STAGE_FLUSH + 32)
+struct WorkFetch { unsigned int cur, end; };
+__device__ __forceinline__ bool wf_next_batch(unsigned int *head, unsigned int count, unsigned int max_grab, WorkFetch &f, unsigned int &base) {
+    if (f.cur >= f.end) {   // warp-uniform
+        const unsigned int lane = threadIdx.x & 31u;
+        const unsigned int left = count > f.end ? count - f.end : 0u;                 // f.end ~ global progress at the last fetch
+        const unsigned int per_warp = left / (gridDim.x * (blockDim.x >> 5) * 64u);   // half of an even share, in batches
+        const unsigned int grab = 32u * (per_warp < 1u ? 1u : (per_warp > max_grab ? max_grab : per_warp));
+        unsigned int b = 0;
+        if (lane == 0) b = atomicAdd(head, grab);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        if (b >= count) return false;
+        f.cur = b;
+        f.end = b + grab < count ? b + grab : count;
+    }
+    base = f.cur;
+    f.cur += 32u;
+    return true;
+}
+__device__ __forceinline__ void wf_stage_push(unsigned int *queue, unsigned int *count, unsigned int *stage, unsigned int &fill, bool alive,
+                                              unsigned int slot) {
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int m = __ballot_sync(0xFFFFFFFFu, alive);
-    if (m == 0u) return;
-    const int leader = __ffs(m) - 1;
-    unsigned int base = 0;
-    if ((int)lane == leader) base = atomicAdd(count, (unsigned int)__popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (alive) queue[base + __popc(m & ((1u << lane) - 1u))] = slot;
+    if (alive) stage[fill + __popc(m & ((1u << lane) - 1u))] = slot;
+    fill += __popc(m);
+    __syncwarp();
+    if (fill >= WF_STAGE_FLUSH) {
+        unsigned int b = 0;
+        if (lane == 0) b = atomicAdd(count, (unsigned int)WF_STAGE_FLUSH);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        for (unsigned int k = lane; k < WF_STAGE_FLUSH; k += 32u) queue[b + k] = stage[k];
+        const unsigned int rem = fill - WF_STAGE_FLUSH;
+        unsigned int keep = 0;
+        if (lane < rem) keep = stage[WF_STAGE_FLUSH + lane];
+        __syncwarp();
+        if (lane < rem) stage[lane] = keep;
+        fill = rem;
+        __syncwarp();
+    }
+}
+__device__ __forceinline__ void wf_stage_flush(unsigned int *queue, unsigned int *count, unsigned int *stage, unsigned int &fill) {
+    if (fill == 0u) return;
+    const unsigned int lane = threadIdx.x & 31u;
+    unsigned int b = 0;
+    if (lane == 0) b = atomicAdd(count, fill);
+    b = __shfl_sync(0xFFFFFFFFu, b, 0);
+    for (unsigned int k = lane; k < fill; k += 32u) queue[b + k] = stage[k];
+    fill = 0u;
 }
 
 #ifndef RT_WF_MINB
@@ -343,11 +393,13 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int count = w.level == 0 ? w.n_paths : w.ctr[4 * w.level + 1];
+    __shared__ unsigned int stage_all[4][WF_STAGE_CAP];
+    unsigned int *stage = stage_all[threadIdx.x >> 5];
+    unsigned int fill = 0u;
+    WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
     for (;;) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(w.ctr + 4 * w.level, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= count) break;
+        unsigned int base;
+        if (!wf_next_batch(w.ctr + 4 * w.level, count, w.max_grab, fetch, base)) break;
         const unsigned int i = base + lane;
         const bool valid = i < count;
         PathState st;
@@ -396,8 +448,9 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
                 w.rng[slot] = make_uint2(st.rng.key, st.rng.ctr);
             }
         }
-        wf_push(w.q_out, w.ctr + 4 * w.level + 3, lit, slot);
+        wf_stage_push(w.q_out, w.ctr + 4 * w.level + 3, stage, fill, lit, slot);
     }
+    wf_stage_flush(w.q_out, w.ctr + 4 * w.level + 3, stage, fill);
     if (STATS) flush_counters(cnt, w.stats);
 }
 
@@ -407,11 +460,13 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int count = w.ctr[4 * w.level + 3];
+    __shared__ unsigned int stage_all[4][WF_STAGE_CAP];
+    unsigned int *stage = stage_all[threadIdx.x >> 5];
+    unsigned int fill = 0u;
+    WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
     for (;;) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(w.ctr + 4 * w.level + 2, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= count) break;
+        unsigned int base;
+        if (!wf_next_batch(w.ctr + 4 * w.level + 2, count, w.max_grab, fetch, base)) break;
         const unsigned int i = base + lane;
         const bool valid = i < count;
         PathState st;
@@ -465,8 +520,9 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 w.rng[slot] = make_uint2(st.rng.key, st.rng.ctr);
             }
         }
-        wf_push(w.q_out, w.ctr + 4 * (w.level + 1) + 1, alive, slot);
+        wf_stage_push(w.q_out, w.ctr + 4 * (w.level + 1) + 1, stage, fill, alive, slot);
     }
+    wf_stage_flush(w.q_out, w.ctr + 4 * (w.level + 1) + 1, stage, fill);
     if (STATS) flush_counters(cnt, w.stats);
 }
 
@@ -1126,6 +1182,9 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
             WfArgs w{};
             const size_t cap = s->wf_cap;
             w.n_paths = (unsigned int)a.n_paths; w.max_bounces = p->max_bounces; w.nb_ech = p->nb_ech;
+            // mesh scenes: a batch can cost 100x another one (rays that walk a mesh vs rays that miss its box), so warps take
+            // one batch at a time as before; analytic scenes: cheap, even batches, where the fetch atomics were the bottleneck
+            w.max_grab = s->d.n_meshes > 0 ? 1u : 8u;
             w.cam_rays = s->cam_rays; w.cam_keys = s->cam_keys;
             w.ray0 = s->wf_f4; w.ray1 = s->wf_f4 + cap; w.hit0 = s->wf_f4 + 2 * cap; w.hit1 = s->wf_f4 + 3 * cap; w.hit2 = s->wf_f4 + 4 * cap;
             w.hit3 = s->wf_f4 + 5 * cap; w.hit4 = s->wf_f4 + 6 * cap;

@@ -57,15 +57,6 @@
 #else
 #define RT_SHARED2 __device__ __forceinline__
 #endif
-#ifndef RT_OPT_MASKLOOP
-#define RT_OPT_MASKLOOP 0   /* one loop taking the k-th candidate of every lane together: measured 15 % slower */
-#endif
-#ifndef RT_OPT_REACH2
-#define RT_OPT_REACH2 1
-#endif
-#ifndef RT_OPT_WW
-#define RT_OPT_WW 1
-#endif
 #ifndef RT_OPT_NOINL_BOUNCE
 #define RT_OPT_NOINL_BOUNCE 1
 #endif
@@ -77,15 +68,6 @@
 #define RT_LDG(p) __ldg(p)
 #else
 #define RT_SHARED_BOUNCE inline
-#ifndef RT_OPT_MASKLOOP
-#define RT_OPT_MASKLOOP 0   /* one loop taking the k-th candidate of every lane together: measured 15 % slower */
-#endif
-#ifndef RT_OPT_REACH2
-#define RT_OPT_REACH2 1
-#endif
-#ifndef RT_OPT_WW
-#define RT_OPT_WW 1
-#endif
 #define RT_HD inline
 #define RT_HHD inline
 #define RT_COLD inline
@@ -111,6 +93,21 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #define RT_WARP_ALL(pred) (pred)
 #define RT_BALLOT(pred) ((pred) ? 1u : 0u)
 #define RT_POPC(x) ((int)((x) != 0u))
+#endif
+
+// A/B switches of control-flow variants (all give identical results; defaults = what measured fastest on B200,
+// profiles/r01_notes.md). Alternate builds: make -C hai719-raytracing_b200 alt NAME=x DEFS="-DRT_OPT_WW=0".
+#ifndef RT_OPT_MASKLOOP
+#define RT_OPT_MASKLOOP 0   /* shadow candidates: one loop taking the k-th candidate of every lane together (15 % slower) */
+#endif
+#ifndef RT_OPT_REACH2
+#define RT_OPT_REACH2 1     /* leaf reachability: cheap test on every leaf of the triangle first, exact chains only if none passes */
+#endif
+#ifndef RT_OPT_WW
+#define RT_OPT_WW 1         /* mesh culling hierarchy: while-while traversal */
+#endif
+#ifndef RT_OPT_WW_LC
+#define RT_OPT_WW_LC 1      /* analytic culling hierarchy (variants 5, 6): while-while traversal */
 #endif
 
 namespace rt {
@@ -1364,6 +1361,56 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
             int stack[64];
             int sp = 0;
             int node = s.abvh_root;
+#if RT_OPT_WW_LC
+            // while-while: descend to the next leaf with box tests only, then test its primitives — the lanes of a warp
+            // reach their leaves at different iterations, and with one loop doing either the primitive tests ran at 7 of
+            // 32 lanes on the secondary rays of config 2 (profiles/r01_notes.md)
+            const int DONE = 0x7FFFFFFF;
+            for (;;) {
+                while (node >= 0 && node != DONE) {
+                    const float4 n0 = RT_LDG(s.abvh_nodes + 4 * node), n1 = RT_LDG(s.abvh_nodes + 4 * node + 1),
+                                 n2 = RT_LDG(s.abvh_nodes + 4 * node + 2), n3 = RT_LDG(s.abvh_nodes + 4 * node + 3);
+                    if (STATS) cnt->node++;
+                    const float p0 = kq * n3.z + kl, p1 = kq * n3.w + kl;
+                    const float limit = collect ? limit_c : h.t;
+                    float d0, d1;
+                    const bool h0 = cone_box(cone, n0.x - p0, n0.y - p0, n0.z - p0, n0.w + p0, n1.x + p0, n1.y + p0, limit, d0);
+                    const bool h1 = cone_box(cone, n1.z - p1, n1.w - p1, n2.x - p1, n2.y + p1, n2.z + p1, n2.w + p1, limit, d1);
+                    const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
+                    if (h0 && h1) {
+                        const bool swap = d1 < d0;
+                        node = swap ? c1 : c0;
+                        stack[sp++] = swap ? c0 : c1;
+                    } else if (h0) node = c0;
+                    else if (h1) node = c1;
+                    else node = sp > 0 ? stack[--sp] : DONE;
+                }
+                if (node == DONE) break;
+                {
+                    const uint32_t code = (uint32_t)(-(node + 1));
+                    const uint32_t first = code >> 3, count = code & 7u;
+                    for (uint32_t k = first; k < first + count; ++k) {
+                        const uint32_t seq = RT_LDG(s.abvh_prims + k);
+                        if (collect) {
+                            const uint32_t bit = 1u << (seq & 31u), w = seq >> 5;
+                            if (w == 0u) m0 |= bit; else if (w == 1u) m1 |= bit; else if (w == 2u) m2 |= bit; else m3 |= bit;
+                            continue;
+                        }
+                        float t, u = 0.f, v = 0.f;
+                        if ((int)seq < ns) { if (STATS) cnt->sphere++; t = sphere_t(ray, sr, RT_LDG(s.sph_a + seq), RT_LDG(s.sph_b + seq)); }
+                        else { if (STATS) cnt->square++; t = square_t(ray, s.squares[seq - ns], u, v); }
+                        if (!(t > RT_EPSF)) continue;
+                        // sequential strict '<' of the reference == smallest t, earliest in sequence on ties
+                        if (t < h.t || (t == h.t && best_seq != 0x7FFFFFFF && (int)seq < best_seq)) {
+                            best_seq = (int)seq; h.t = t;
+                            if ((int)seq < ns) { h.type = 1; h.obj = (int)seq; } else { h.type = 2; h.obj = (int)seq - ns; hu = u; hv = v; }
+                        }
+                    }
+                }
+                if (sp == 0) break;
+                node = stack[--sp];
+            }
+#else
             for (;;) {
                 if (node >= 0) {
                     const float4 n0 = RT_LDG(s.abvh_nodes + 4 * node), n1 = RT_LDG(s.abvh_nodes + 4 * node + 1),
@@ -1407,6 +1454,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
                 if (sp == 0) break;
                 node = stack[--sp];
             }
+#endif
             if (collect) { st.cm0 = m0; st.cm1 = m1; st.cm2 = m2; st.cm3 = m3; done = true; }
         }
     } else if (mine) {

@@ -20,7 +20,7 @@ import sys
 import tempfile
 
 
-def sass_page(rep, kernel):
+def sass_page(rep, kernel, index=0):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], stdout=subprocess.PIPE,
                          stderr=subprocess.DEVNULL, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -33,9 +33,9 @@ def sass_page(rep, kernel):
             cur["hdr"] = r
         elif cur is not None and cur["hdr"] and len(r) == len(cur["hdr"]):
             cur["rows"].append(dict(zip(cur["hdr"], r)))
-    for b in blocks:
-        if kernel in b["name"]:
-            return b
+    hits = [b for b in blocks if kernel in b["name"]]
+    if len(hits) > index:
+        return hits[index]
     raise SystemExit("kernel %r not in report (has: %s)" % (kernel, [b["name"][:60] for b in blocks]))
 
 
@@ -72,10 +72,11 @@ def main():
     ap.add_argument("report")
     ap.add_argument("lib")
     ap.add_argument("--kernel", default="k_render")
+    ap.add_argument("--index", type=int, default=0, help="n-th launch among those matching --kernel")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--depth", type=int, default=1, help="which level of the inline chain names a 'region' (counted from the kernel body)")
     args = ap.parse_args()
-    blk = sass_page(args.report, args.kernel)
+    blk = sass_page(args.report, args.kernel, args.index)
     rows = blk["rows"]
     print("kernel:", blk["name"])
     base = int(rows[0]["Address"], 16)

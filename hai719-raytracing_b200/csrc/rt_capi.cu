@@ -319,7 +319,10 @@ struct WfArgs {
     float4 *hit0, *hit1, *hit2, *hit3, *hit4;   // {P, time} {n, bits(kind << 28 | obj)} {kd, bits(N | depth << 8)} {e, -} {in_d, -}
     float4 *rec; unsigned long long rec_stride;
     unsigned int *q_in, *q_out;        // trace: q_in = live paths (level > 0), q_out = paths with a hit; light: the reverse
-    unsigned int *ctr;                 // per level 4 counters: [4L] trace head, [4L+1] trace count, [4L+2] light head, [4L+3] light count
+    unsigned int *q_park;              // light phase A -> phase B: hits whose light needs its shadow samples traced
+    float4 *park0, *park1;             // ... and what phase B needs besides the hit record: {colour so far, light | mesh flag << 8}, {cm0..cm3}
+    unsigned int *ctr;                 // per level 6 counters: [6L] trace head, [6L+1] trace count, [6L+2] light head, [6L+3] light count,
+                                       //                       [6L+4] shadow head, [6L+5] shadow count
     float *samples;
     unsigned long long *stats;
 };
@@ -392,14 +395,14 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int count = w.level == 0 ? w.n_paths : w.ctr[4 * w.level + 1];
+    const unsigned int count = w.level == 0 ? w.n_paths : w.ctr[6 * w.level + 1];
     __shared__ unsigned int stage_all[4][WF_STAGE_CAP];
     unsigned int *stage = stage_all[threadIdx.x >> 5];
     unsigned int fill = 0u;
     WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
     for (;;) {
         unsigned int base;
-        if (!wf_next_batch(w.ctr + 4 * w.level, count, w.max_grab, fetch, base)) break;
+        if (!wf_next_batch(w.ctr + 6 * w.level, count, w.max_grab, fetch, base)) break;
         const unsigned int i = base + lane;
         const bool valid = i < count;
         PathState st;
@@ -448,37 +451,51 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
                 w.rng[slot] = make_uint2(st.rng.key, st.rng.ctr);
             }
         }
-        wf_stage_push(w.q_out, w.ctr + 4 * w.level + 3, stage, fill, lit, slot);
+        wf_stage_push(w.q_out, w.ctr + 6 * w.level + 3, stage, fill, lit, slot);
     }
-    wf_stage_flush(w.q_out, w.ctr + 4 * w.level + 3, stage, fill);
+    wf_stage_flush(w.q_out, w.ctr + 6 * w.level + 3, stage, fill);
     if (STATS) flush_counters(cnt, w.stats);
 }
 
-template <bool STATS, bool LC>
+// PHASE 0: everything in one kernel (scenes without the analytic hierarchy: no candidate masks to classify by).
+// PHASE 1: per light, ONE cone walk; a light whose cone holds no possible occluder is finished on the spot (all its
+//          samples are unoccluded: lc_light_unoccluded) and the path goes on to the next light / the scatter. A path
+//          that reaches a light with candidates is PARKED: colour so far, light index and masks go to HBM and the slot
+//          to the shadow queue. Most hits of config 2 never leave this phase.
+// PHASE 2: the parked paths, now packed into full warps: the NB_ECH samples of the parked light, any further light
+//          (walk + samples inline), scatter.
+// Split because a warp is as slow as its slowest lane: with both phases in one loop, one lane that has to sample keeps
+// 31 finished lanes waiting for ten rounds.
+template <bool STATS, bool LC, int PHASE>
 __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene, const WfArgs w) {
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int count = w.ctr[4 * w.level + 3];
+    const unsigned int count = w.ctr[6 * w.level + (PHASE == 2 ? 5 : 3)];
+    unsigned int *const head = w.ctr + 6 * w.level + (PHASE == 2 ? 4 : 2);
+    const unsigned int *const q_in = PHASE == 2 ? w.q_park : w.q_in;
     __shared__ unsigned int stage_all[4][WF_STAGE_CAP];
+    __shared__ unsigned int stage_park_all[PHASE == 1 ? 4 : 1][PHASE == 1 ? WF_STAGE_CAP : 1];
     unsigned int *stage = stage_all[threadIdx.x >> 5];
-    unsigned int fill = 0u;
+    unsigned int *stage_park = stage_park_all[PHASE == 1 ? (threadIdx.x >> 5) : 0];
+    unsigned int fill = 0u, fill_park = 0u;
     WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
     for (;;) {
         unsigned int base;
-        if (!wf_next_batch(w.ctr + 4 * w.level + 2, count, w.max_grab, fetch, base)) break;
+        if (!wf_next_batch(head, count, w.max_grab, fetch, base)) break;
         const unsigned int i = base + lane;
         const bool valid = i < count;
         PathState st;
         st.mode = 2; st.t_light = 0.f; st.light = 0;
         st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
         st.rng.key = 0; st.rng.ctr = 0;
+        st.cm0 = st.cm1 = st.cm2 = st.cm3 = 0u; st.cm_mesh = 0u;
         st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
         unsigned int slot = 0;
-        bool fin = true;
+        bool fin = true, parked = false;
         V3 c = v3(0.f);
         if (valid) {
-            slot = w.q_in[i];
+            slot = q_in[i];
             const float4 h0 = w.hit0[slot], h1 = w.hit1[slot], h2 = w.hit2[slot], h3 = w.hit3[slot], h4 = w.hit4[slot];
             const uint2 g = w.rng[slot];
             st.P = v3(h0.x, h0.y, h0.z); st.ray.time = h0.w;
@@ -490,13 +507,22 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
             st.e = v3(h3.x, h3.y, h3.z);
             st.in_d = v3(h4.x, h4.y, h4.z);
             st.rng.key = g.x; st.rng.ctr = g.y;
-            st.path = slot; st.color = v3(0.f); st.light = 0; st.mode = 0;
-            fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
+            st.path = slot;
+            if (PHASE == 2) {
+                const float4 p0 = w.park0[slot], p1 = w.park1[slot];
+                st.color = v3(p0.x, p0.y, p0.z);
+                st.light = (int)(f2u(p0.w) & 0xFFu); st.cm_mesh = f2u(p0.w) >> 8;
+                st.cm0 = f2u(p1.x); st.cm1 = f2u(p1.y); st.cm2 = f2u(p1.z); st.cm3 = f2u(p1.w);
+                st.j = 0; st.blocked = 0; st.mode = 3;
+                Hit h; h.type = 0; h.obj = -1; h.t = 0.f; h.ref = 0;
+                fin = path_advance<STATS, LC, true>(scene, st, h, 0.f, 0.f, false, w.nb_ech, c, &cnt);   // candidates known: first sample
+            } else {
+                st.color = v3(0.f); st.light = 0; st.mode = 0;
+                fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
+            }
         }
-        // every lane has the same number of lights and shadow samples ahead of it, so the warp walks
-        // mode 3 (candidates) -> mode 1 x NB_ECH -> next light ... -> scatter in lockstep
         for (;;) {
-            const bool live = valid && !fin && st.mode != 0;
+            const bool live = valid && !fin && !parked && st.mode != 0;
             const unsigned int bt = __ballot_sync(0xFFFFFFFFu, live && st.mode == 3), bs = __ballot_sync(0xFFFFFFFFu, live && st.mode == 1);
             if ((bt | bs) == 0u) break;
             const bool run_t = bt != 0u;
@@ -506,11 +532,18 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
             bool blocked;
             if (LC) intersect_lc<STATS>(scene, st, run_t, mine, h, hu, hv, blocked, &cnt);
             else intersect_ray<STATS, true>(scene, st.ray, mine ? st.mode : 2, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
-            if (mine) fin = path_advance<STATS, LC, true>(scene, st, h, hu, hv, blocked, w.nb_ech, c, &cnt);
+            if (mine) {
+                if (PHASE == 1 && !lc_light_unoccluded(st)) parked = true;   // mode 3 only in this phase
+                else fin = path_advance<STATS, LC, true>(scene, st, h, hu, hv, blocked, w.nb_ech, c, &cnt);
+            }
         }
         bool alive = false;
         if (valid) {
-            if (fin) {
+            if (parked) {
+                w.park0[slot] = make_float4(st.color.x, st.color.y, st.color.z, u2f((uint32_t)st.light | (st.cm_mesh << 8)));
+                w.park1[slot] = make_float4(u2f(st.cm0), u2f(st.cm1), u2f(st.cm2), u2f(st.cm3));
+                w.rng[slot] = make_uint2(st.rng.key, st.rng.ctr);
+            } else if (fin) {
                 float *o = w.samples + 3ull * slot;
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
             } else {
@@ -520,9 +553,11 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 w.rng[slot] = make_uint2(st.rng.key, st.rng.ctr);
             }
         }
-        wf_stage_push(w.q_out, w.ctr + 4 * (w.level + 1) + 1, stage, fill, alive, slot);
+        wf_stage_push(w.q_out, w.ctr + 6 * (w.level + 1) + 1, stage, fill, alive, slot);
+        if (PHASE == 1) wf_stage_push(w.q_park, w.ctr + 6 * w.level + 5, stage_park, fill_park, parked, slot);
     }
-    wf_stage_flush(w.q_out, w.ctr + 4 * (w.level + 1) + 1, stage, fill);
+    wf_stage_flush(w.q_out, w.ctr + 6 * (w.level + 1) + 1, stage, fill);
+    if (PHASE == 1) wf_stage_flush(w.q_park, w.ctr + 6 * w.level + 5, stage_park, fill_park);
     if (STATS) flush_counters(cnt, w.stats);
 }
 
@@ -830,11 +865,11 @@ int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
     if (s->wf_rec) cudaFree(s->wf_rec);
     s->wf_f4 = nullptr; s->wf_rng = nullptr; s->wf_q = nullptr; s->wf_rec = nullptr; s->wf_cap = 0; s->wf_bounces = 0;
     paths = std::max(paths, s->wf_cap); max_bounces = std::max(max_bounces, s->wf_bounces);
-    RT_CUDA(cudaMalloc((void **)&s->wf_f4, 7 * paths * sizeof(float4)));
+    RT_CUDA(cudaMalloc((void **)&s->wf_f4, 9 * paths * sizeof(float4)));
     RT_CUDA(cudaMalloc((void **)&s->wf_rng, paths * sizeof(uint2)));
-    RT_CUDA(cudaMalloc((void **)&s->wf_q, 2 * paths * sizeof(unsigned int)));
+    RT_CUDA(cudaMalloc((void **)&s->wf_q, 3 * paths * sizeof(unsigned int)));
     RT_CUDA(cudaMalloc((void **)&s->wf_rec, 3 * (size_t)std::max(1, max_bounces) * paths * sizeof(float4)));
-    if (!s->wf_ctr) RT_CUDA(cudaMalloc((void **)&s->wf_ctr, 4 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int)));
+    if (!s->wf_ctr) RT_CUDA(cudaMalloc((void **)&s->wf_ctr, 6 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int)));
     s->wf_cap = paths; s->wf_bounces = max_bounces;
     return RT_OK;
 }
@@ -1146,7 +1181,9 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     typedef void (*LightKernel)(const DScene, const WfArgs);
     const bool wf_lc = s->d.abvh_root >= 0;
     TraceKernel wf_trace = want_stats ? (wf_lc ? k_wf_trace<true, true> : k_wf_trace<true, false>) : (wf_lc ? k_wf_trace<false, true> : k_wf_trace<false, false>);
-    LightKernel wf_light = want_stats ? (wf_lc ? k_wf_light<true, true> : k_wf_light<true, false>) : (wf_lc ? k_wf_light<false, true> : k_wf_light<false, false>);
+    // light stage: one kernel (no masks to classify by) or walk/classify + sample (see k_wf_light)
+    LightKernel wf_light = want_stats ? (wf_lc ? k_wf_light<true, true, 1> : k_wf_light<true, false, 0>) : (wf_lc ? k_wf_light<false, true, 1> : k_wf_light<false, false, 0>);
+    LightKernel wf_light_b = want_stats ? k_wf_light<true, true, 2> : k_wf_light<false, true, 2>;
     int wf_grid_t = 0, wf_grid_l = 0;
     if (wavefront) {
         if ((rc = ensure_wavefront(s, (size_t)(chunk_pixels * p->spp), p->max_bounces))) return rc;
@@ -1187,10 +1224,11 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
             w.max_grab = s->d.n_meshes > 0 ? 1u : 8u;
             w.cam_rays = s->cam_rays; w.cam_keys = s->cam_keys;
             w.ray0 = s->wf_f4; w.ray1 = s->wf_f4 + cap; w.hit0 = s->wf_f4 + 2 * cap; w.hit1 = s->wf_f4 + 3 * cap; w.hit2 = s->wf_f4 + 4 * cap;
-            w.hit3 = s->wf_f4 + 5 * cap; w.hit4 = s->wf_f4 + 6 * cap;
+            w.hit3 = s->wf_f4 + 5 * cap; w.hit4 = s->wf_f4 + 6 * cap; w.park0 = s->wf_f4 + 7 * cap; w.park1 = s->wf_f4 + 8 * cap;
+            w.q_park = s->wf_q + 2 * cap;
             w.rng = s->wf_rng; w.rec = s->wf_rec; w.rec_stride = cap;
             w.ctr = s->wf_ctr; w.samples = s->samples; w.stats = a.stats;
-            RT_CUDA(cudaMemsetAsync(s->wf_ctr, 0, 4 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
+            RT_CUDA(cudaMemsetAsync(s->wf_ctr, 0, 6 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
             unsigned int *q_live = s->wf_q, *q_hit = s->wf_q + cap;
             for (int level = 0; level < p->max_bounces; ++level) {
                 w.level = level;
@@ -1201,6 +1239,11 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
                 wf_light<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
                 RT_CUDA(cudaGetLastError());
                 launches += 2;
+                if (wf_lc && s->d.n_lights > 0) {
+                    wf_light_b<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
+                    RT_CUDA(cudaGetLastError());
+                    ++launches;
+                }
             }
         } else {
             fn<<<g, 128, 0, st>>>(s->d, cam, a);

@@ -964,6 +964,7 @@ struct PathState {
     float t_light;
     int max_bounces;
     uint32_t cm0, cm1, cm2, cm3;   // variant 5: analytic primitives (sequence index = bit) that can occlude light `light` from P
+    uint32_t cm_mesh;              // ... and whether the cone towards that light can touch any mesh
     V3 rec_c[RT_MAX_BOUNCES], rec_kd[RT_MAX_BOUNCES], rec_e[RT_MAX_BOUNCES];
     // wavefront kernels (variant 6) keep the per-depth records in global memory instead: entry (3*depth + {0 colour,
     // 1 kd, 2 e}) of path slot `path` is wf_rec[(3*depth + k) * wf_stride + path]; the arrays above are then unused
@@ -1327,6 +1328,33 @@ RT_HD bool cone_box(const Cone &c, float lx, float ly, float lz, float hx, float
     return (tn - slack <= tf + slack) && (tf + slack >= 0.f);
 }
 
+// Candidates that provably cannot occlude ANY shadow sample of the cone are dropped when the mask is collected.
+// Every sample ray leaves P + EPSILON*Lj along Lj = normalize(lj - P), |lj - light.pos| <= delta (1.0001 delta + 1e-6
+// here), so for a fixed vector w:   Lj . w  >=  (D . w - delta*|w|) / |lj - P|,   D = light.pos - P.
+//   * non-glass square: Square::intersect returns "no hit" whenever d . n >= 0 (Square.h:78-86). With w = n
+//     (unit): D . n - delta > margin  =>  every sample sees the back face or the edge-on plane.
+//   * sphere: the near root -b - sqrt(delta) is <= 0 < EPSILON whenever b = 2 d . (o - c) >= 0 (see sphere_t). With
+//     w = P - c (and o - c = w + EPSILON*Lj only helps): D . w - delta*|w| > margin  =>  the sphere lies behind every
+//     sample ray. This is the lit side of the very sphere that was hit, and everything on the far side of P.
+// margin = 1e-4 * |w| * (|D| + delta): three orders of magnitude above the rounding of the fp32 dot products the
+// reference-exact tests evaluate (a few eps * |w|), so "cannot occlude" here implies FLT_MAX there.
+RT_HD bool lc_cannot_occlude(const DScene &s, uint32_t seq, int ns, V3 P, float time, V3 D, float delta, float Dlen) {
+    if ((int)seq < ns) {
+        const float4 a = RT_LDG(s.sph_a + seq), b = RT_LDG(s.sph_b + seq);
+        const V3 c = v3(a.x, a.y, a.z) + time * v3(b.x, b.y, b.z);
+        const V3 w = P - c;
+        const float wl = length(w);
+        return dot(D, w) - delta * wl > 1e-4f * wl * (Dlen + delta) + 1e-12f;
+    }
+    const DSquare &q = s.squares[seq - ns];
+    if (q.glass) return false;
+    return dot(D, ld3(q.n)) - delta > 1e-4f * (Dlen + delta) + 1e-12f;
+}
+// No candidate at all (and no mesh in the cone): the NB_ECH samples of this light are all unoccluded. Each would
+// draw three numbers for its direction and nothing else (Scene.h:325-330, computeShadow draws only per candidate hit),
+// so the stream advances by 3*NB_ECH and shadow = 1 - 0/NB_ECH = 1 leaves the colour unchanged (x * 1.0f == x).
+RT_HD bool lc_light_unoccluded(const PathState &st) { return (st.cm0 | st.cm1 | st.cm2 | st.cm3 | st.cm_mesh) == 0u; }
+
 // One step of the variant-5 state machine for the lanes selected by `mine`.
 //   run_t (warp-uniform) true : lanes in mode 0 (closest hit) and mode 3 (collect candidates) walk the
 //                               analytic hierarchy together; mode 0 goes on to the meshes.
@@ -1347,9 +1375,14 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
             if (STATS && !collect) cnt->closest++;
             Cone cone;
             float limit_c = 1.0001f;
+            V3 coneD = v3(0.f);
+            float cone_delta = 0.f, cone_len = 0.f;
             if (collect) {
                 const DLight &L = s.lights[st.light];
-                cone = make_cone(st.P, ld3(L.pos) - st.P, (L.radius / 2.f) * 1.0001f + 1e-6f);
+                coneD = ld3(L.pos) - st.P;
+                cone_delta = (L.radius / 2.f) * 1.0001f + 1e-6f;
+                cone_len = length(coneD);
+                cone = make_cone(st.P, coneD, cone_delta);
             } else {
                 cone = make_cone(ray.o, ray.d, 0.f);
             }
@@ -1392,6 +1425,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
                     for (uint32_t k = first; k < first + count; ++k) {
                         const uint32_t seq = RT_LDG(s.abvh_prims + k);
                         if (collect) {
+                            if (lc_cannot_occlude(s, seq, ns, st.P, ray.time, coneD, cone_delta, cone_len)) continue;
                             const uint32_t bit = 1u << (seq & 31u), w = seq >> 5;
                             if (w == 0u) m0 |= bit; else if (w == 1u) m1 |= bit; else if (w == 2u) m2 |= bit; else m3 |= bit;
                             continue;
@@ -1436,6 +1470,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
                     for (uint32_t k = first; k < first + count; ++k) {
                         const uint32_t seq = RT_LDG(s.abvh_prims + k);
                         if (collect) {
+                            if (lc_cannot_occlude(s, seq, ns, st.P, ray.time, coneD, cone_delta, cone_len)) continue;
                             const uint32_t bit = 1u << (seq & 31u), w = seq >> 5;
                             if (w == 0u) m0 |= bit; else if (w == 1u) m1 |= bit; else if (w == 2u) m2 |= bit; else m3 |= bit;
                             continue;
@@ -1455,7 +1490,22 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
                 node = stack[--sp];
             }
 #endif
-            if (collect) { st.cm0 = m0; st.cm1 = m1; st.cm2 = m2; st.cm3 = m3; done = true; }
+            if (collect) {
+                st.cm0 = m0; st.cm1 = m1; st.cm2 = m2; st.cm3 = m3; done = true;
+                // can the cone touch a mesh? (root of its culling hierarchy; ill-conditioned triangles are outside any box)
+                uint32_t any = 0u;
+                for (int i = 0; i < s.n_meshes && !any; ++i) {
+                    const DMesh &m = s.meshes[i];
+                    if (m.always_count > 0u) { any = 1u; break; }
+                    if (m.bvh_root < 0) continue;
+                    const float4 n0 = RT_LDG(s.bvh_nodes + 4 * m.bvh_root), n1 = RT_LDG(s.bvh_nodes + 4 * m.bvh_root + 1),
+                                 n2 = RT_LDG(s.bvh_nodes + 4 * m.bvh_root + 2);
+                    float d0;
+                    if (cone_box(cone, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, limit_c, d0) ||
+                        cone_box(cone, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, limit_c, d0)) any = 1u;
+                }
+                st.cm_mesh = any;
+            }
         }
     } else if (mine) {
 #if RT_OPT_MASKLOOP
@@ -1663,7 +1713,16 @@ RT_HD bool path_shade(const DScene &s, PathState &st, const Hit &h, float hu, fl
 template <bool STATS, bool LC = false, bool WF = false>
 RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, float hv, bool blocked, int nb_ech, V3 &out,
                         Counters *cnt) {
-    if (LC && st.mode == 3) { path_shadow_sample<STATS>(s, st, cnt); return false; }   // candidates collected: first sample
+    if (LC && st.mode == 3) {   // candidates collected
+        if (lc_light_unoccluded(st)) {
+            if (STATS) { cnt->shadow += nb_ech; cnt->rnd += 3 * nb_ech; }
+            st.rng.ctr += 3u * (uint32_t)nb_ech;
+            ++st.light;
+            return path_next_light_or_bounce<STATS, LC, WF>(s, st, nb_ech, out, cnt);
+        }
+        path_shadow_sample<STATS>(s, st, cnt);   // first sample
+        return false;
+    }
     if (st.mode == 1) {
         if (blocked) ++st.blocked;
         if (++st.j < nb_ech) { path_shadow_sample<STATS>(s, st, cnt); return false; }

@@ -49,7 +49,13 @@ static DImage to_dimg(const RtImage &im) {
     return d;
 }
 
+static std::atomic<unsigned long long> g_dbg_lights(0), g_dbg_unoccluded(0), g_dbg_cands(0);
+
 extern "C" {
+
+// debug: lights lit in wavefront mode (variant 6), how many needed no shadow sample, candidates of the others
+void sim_debug_counts(unsigned long long *out3) { out3[0] = g_dbg_lights; out3[1] = g_dbg_unoccluded; out3[2] = g_dbg_cands; g_dbg_lights = 0; g_dbg_unoccluded = 0; g_dbg_cands = 0; }
+
 
 void *sim_scene_create(const RtSceneDesc *desc) {
     SimScene *s = new SimScene;
@@ -179,7 +185,13 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                             else fin = path_next_light_or_bounce<false, false, true>(s->d, st, p->nb_ech, c, nullptr);
                             while (!fin && st.mode != 0) {
                                 if (lc) {
+                                    const bool was3 = st.mode == 3;
                                     intersect_lc<false>(s->d, st, st.mode == 3, true, hit, hu, hv, blocked, nullptr);
+                                    if (was3) {
+                                        g_dbg_lights++;
+                                        if (lc_light_unoccluded(st)) g_dbg_unoccluded++;
+                                        else g_dbg_cands += __builtin_popcount(st.cm0) + __builtin_popcount(st.cm1) + __builtin_popcount(st.cm2) + __builtin_popcount(st.cm3);
+                                    }
                                     fin = path_advance<false, true, true>(s->d, st, hit, hu, hv, blocked, p->nb_ech, c, nullptr);
                                 } else {
                                     intersect_ray<false, true>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);

@@ -272,7 +272,11 @@ inline void build_analytic_accel(const RtSceneDesc &d, AnalyticAccel &out) {
     using namespace bvh_detail;
     out = AnalyticAccel();
     const uint32_t n = d.n_spheres + d.n_squares;
-    if (n < 24 || n > 128) return;   // below: the linear loops are as fast; above: the occlusion mask is 128 bits
+    // above 128: the occlusion mask is 128 bits. Below 24 the reference's linear loops are as fast for closest-hit rays,
+    // but a scene with lights AND meshes still gets the (tiny) hierarchy: it is what gives it the per-light candidate
+    // walk of variants 5/6 (occluder mask + candidate triangle list instead of a mesh walk per shadow sample).
+    const bool small_ok = d.n_lights > 0 && d.n_meshes > 0;
+    if (n == 0 || n > 128 || (n < 24 && !small_ok)) return;
     std::vector<Prim> prims;
     Box all; all.reset();
     for (uint32_t i = 0; i < d.n_spheres; ++i) {
@@ -319,7 +323,19 @@ inline void build_analytic_accel(const RtSceneDesc &d, AnalyticAccel &out) {
     int max_depth = 0;
     int32_t root = build(prims, 0, prims.size(), out, false, 0, max_depth);
     if (max_depth > 56) { out.nodes.clear(); out.tris.clear(); max_depth = 0; root = build(prims, 0, prims.size(), out, true, 0, max_depth); }
-    out.root = root >= 0 ? root : -1;   // n >= 24 always yields an inner root
+    if (root < 0) {
+        // one or two primitives: a single leaf. Wrap it in a node whose second child is empty (inverted box)
+        Box b; b.reset();
+        float k0 = 0.f;
+        for (const Prim &p : prims) { b.grow(p.box); k0 = std::max(k0, p.coef); }
+        const size_t id = out.nodes.size() / 4;
+        out.nodes.push_back(make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]));
+        out.nodes.push_back(make_float4(b.hi[1], b.hi[2], FLT_MAX, FLT_MAX));
+        out.nodes.push_back(make_float4(FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX));
+        out.nodes.push_back(make_float4(u2f((uint32_t)root), u2f((uint32_t)leaf_code(0, 0)), k0, 0.f));
+        root = (int32_t)id;
+    }
+    out.root = root;
 }
 
 }  // namespace rt

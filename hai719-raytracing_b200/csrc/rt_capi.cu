@@ -320,7 +320,8 @@ struct WfArgs {
     float4 *rec; unsigned long long rec_stride;
     unsigned int *q_in, *q_out;        // trace: q_in = live paths (level > 0), q_out = paths with a hit; light: the reverse
     unsigned int *q_park;              // light phase A -> phase B: hits whose light needs its shadow samples traced
-    float4 *park0, *park1;             // ... and what phase B needs besides the hit record: {colour so far, light | mesh flag << 8}, {cm0..cm3}
+    float4 *park0, *park1;             // ... and what phase B needs besides the hit record: {colour so far, light | (cl_n + 1) << 8}, {cm0..cm3}
+    float4 *park2;                     // candidate triangles, RT_LC_MAXC / 4 float4 planes of rec_stride entries
     unsigned int *ctr;                 // per level 6 counters: [6L] trace head, [6L+1] trace count, [6L+2] light head, [6L+3] light count,
                                        //                       [6L+4] shadow head, [6L+5] shadow count
     float *samples;
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
         st.mode = 2; st.t_light = 0.f; st.light = 0;
         st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
         st.rng.key = 0; st.rng.ctr = 0;
-        st.cm0 = st.cm1 = st.cm2 = st.cm3 = 0u; st.cm_mesh = 0u;
+        st.cm0 = st.cm1 = st.cm2 = st.cm3 = 0u; st.cl_n = 0;
         st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
         unsigned int slot = 0;
         bool fin = true, parked = false;
@@ -511,7 +512,11 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
             if (PHASE == 2) {
                 const float4 p0 = w.park0[slot], p1 = w.park1[slot];
                 st.color = v3(p0.x, p0.y, p0.z);
-                st.light = (int)(f2u(p0.w) & 0xFFu); st.cm_mesh = f2u(p0.w) >> 8;
+                st.light = (int)(f2u(p0.w) & 0xFFu); st.cl_n = (int)((f2u(p0.w) >> 8) & 0xFFu) - 1;
+                for (int q4 = 0; q4 * 4 < st.cl_n; ++q4) {
+                    const float4 v = w.park2[(size_t)q4 * w.rec_stride + slot];
+                    st.cl[4 * q4] = f2u(v.x); st.cl[4 * q4 + 1] = f2u(v.y); st.cl[4 * q4 + 2] = f2u(v.z); st.cl[4 * q4 + 3] = f2u(v.w);
+                }
                 st.cm0 = f2u(p1.x); st.cm1 = f2u(p1.y); st.cm2 = f2u(p1.z); st.cm3 = f2u(p1.w);
                 st.j = 0; st.blocked = 0; st.mode = 3;
                 Hit h; h.type = 0; h.obj = -1; h.t = 0.f; h.ref = 0;
@@ -540,7 +545,9 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
         bool alive = false;
         if (valid) {
             if (parked) {
-                w.park0[slot] = make_float4(st.color.x, st.color.y, st.color.z, u2f((uint32_t)st.light | (st.cm_mesh << 8)));
+                w.park0[slot] = make_float4(st.color.x, st.color.y, st.color.z, u2f((uint32_t)st.light | ((uint32_t)(st.cl_n + 1) << 8)));
+                for (int q4 = 0; q4 * 4 < st.cl_n; ++q4)
+                    w.park2[(size_t)q4 * w.rec_stride + slot] = make_float4(u2f(st.cl[4 * q4]), u2f(st.cl[4 * q4 + 1]), u2f(st.cl[4 * q4 + 2]), u2f(st.cl[4 * q4 + 3]));
                 w.park1[slot] = make_float4(u2f(st.cm0), u2f(st.cm1), u2f(st.cm2), u2f(st.cm3));
                 w.rng[slot] = make_uint2(st.rng.key, st.rng.ctr);
             } else if (fin) {
@@ -695,7 +702,28 @@ struct Scratch {
     unsigned long long *counters = nullptr;   // [0] work counter, [1..10] stats
     TileRec *d_tiles = nullptr; unsigned int *d_tile_off = nullptr; size_t tiles_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // arena for the scene's own arrays (textures, primitives, hierarchies): bump-allocated blocks, reset when the scene
+    // is destroyed and reused by the next scene on this device — a re-upload performs no cudaMalloc/cudaFree at all
+    struct Block { char *base; size_t cap, used; };
+    std::vector<Block> arena;
+    void *arena_alloc(size_t bytes, cudaError_t *err) {
+        *err = cudaSuccess;
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (Block &b : arena)
+            if (b.cap - b.used >= bytes) { void *p = b.base + b.used; b.used += bytes; return p; }
+        Block nb;
+        nb.cap = std::max<size_t>(bytes, (size_t)32 << 20);
+        nb.used = bytes;
+        nb.base = nullptr;
+        *err = cudaMalloc((void **)&nb.base, nb.cap);
+        if (*err != cudaSuccess) return nullptr;
+        arena.push_back(nb);
+        return nb.base;
+    }
+    void arena_reset() { for (Block &b : arena) b.used = 0; }
     void release() {
+        for (Block &b : arena) cudaFree(b.base);
+        arena.clear();
         if (samples) cudaFree(samples);
         if (cam_rays) cudaFree(cam_rays);
         if (cam_keys) cudaFree(cam_keys);
@@ -721,7 +749,6 @@ struct RtScene : Scratch {
     int device = 0;
     int sm_count = 0;
     DScene d{};
-    std::vector<void *> allocs;
     size_t bytes = 0;
     std::vector<TileRec> h_tiles; std::vector<unsigned int> h_tile_off;
 };
@@ -768,9 +795,9 @@ void build_tiles(const RtRenderParams &p, const Rect &r, std::vector<TileRec> &t
 template <class T> int dev_upload(RtScene *s, const T *host, size_t n, const T **out) {
     *out = nullptr;
     if (n == 0) return RT_OK;
-    void *p = nullptr;
-    RT_CUDA(cudaMalloc(&p, n * sizeof(T)));
-    s->allocs.push_back(p);
+    cudaError_t e;
+    void *p = s->arena_alloc(n * sizeof(T), &e);
+    RT_CUDA(e);
     s->bytes += n * sizeof(T);
     RT_CUDA(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
     *out = (const T *)p;
@@ -779,23 +806,25 @@ template <class T> int dev_upload(RtScene *s, const T *host, size_t n, const T *
 template <class T> int dev_alloc(RtScene *s, size_t n, T **out) {
     *out = nullptr;
     if (n == 0) return RT_OK;
-    void *p = nullptr;
-    RT_CUDA(cudaMalloc(&p, n * sizeof(T)));
-    s->allocs.push_back(p);
+    cudaError_t e;
+    void *p = s->arena_alloc(n * sizeof(T), &e);
+    RT_CUDA(e);
     s->bytes += n * sizeof(T);
     *out = (T *)p;
     return RT_OK;
 }
 
-struct DevTmp {   // scratch device buffer, freed on scope exit
+struct DevTmp {   // staging buffer for the precompute kernels: lives in the scene's arena (reclaimed with the scene)
     void *p = nullptr;
-    ~DevTmp() { if (p) cudaFree(p); }
-    cudaError_t put(const void *h, size_t bytes) {
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-        if (e == cudaSuccess && h && bytes) e = cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice);
-        return e;
-    }
+    cudaError_t put(RtScene *s, const void *h, size_t bytes);
 };
+
+cudaError_t DevTmp::put(RtScene *s, const void *h, size_t bytes) {
+    cudaError_t e;
+    p = s->arena_alloc(bytes ? bytes : 1, &e);
+    if (e == cudaSuccess && h && bytes) e = cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice);
+    return e;
+}
 
 DMaterial to_dmat(const RtMaterial &m) {
     DMaterial d{};
@@ -829,11 +858,15 @@ int select_device(int device, int *sm_count) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(RT_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)"); }
     if (device < 0 || device >= n) return fail(RT_ERR_INVALID, "device index out of range");
-    cudaDeviceProp prop;
-    RT_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return fail(RT_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this library is built for sm_100a only");
+    // attribute queries, not cudaGetDeviceProperties: that call takes 3-90 ms when it has to wait behind other driver
+    // activity, and it sat in every scene upload (profiles/r01_notes.md, e2e spikes)
+    int major = 0, minor = 0, sms = 0;
+    RT_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    RT_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    RT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (major != 10) return fail(RT_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(major * 10 + minor) + ", this library is built for sm_100a only");
     RT_CUDA(cudaSetDevice(device));
-    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (sm_count) *sm_count = sms;
     return RT_OK;
 }
 
@@ -865,7 +898,7 @@ int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
     if (s->wf_rec) cudaFree(s->wf_rec);
     s->wf_f4 = nullptr; s->wf_rng = nullptr; s->wf_q = nullptr; s->wf_rec = nullptr; s->wf_cap = 0; s->wf_bounces = 0;
     paths = std::max(paths, s->wf_cap); max_bounces = std::max(max_bounces, s->wf_bounces);
-    RT_CUDA(cudaMalloc((void **)&s->wf_f4, 9 * paths * sizeof(float4)));
+    RT_CUDA(cudaMalloc((void **)&s->wf_f4, (9 + RT_LC_MAXC / 4) * paths * sizeof(float4)));
     RT_CUDA(cudaMalloc((void **)&s->wf_rng, paths * sizeof(uint2)));
     RT_CUDA(cudaMalloc((void **)&s->wf_q, 3 * paths * sizeof(unsigned int)));
     RT_CUDA(cudaMalloc((void **)&s->wf_rec, 3 * (size_t)std::max(1, max_bounces) * paths * sizeof(float4)));
@@ -925,7 +958,7 @@ void rt_scene_destroy(RtScene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();   // nothing of this scene may still be in flight when its arrays go
-    for (void *p : s->allocs) cudaFree(p);
+    s->arena_reset();
     {
         std::lock_guard<std::mutex> lock(g_scratch_mu);
         g_scratch_pool[s->device].push_back(static_cast<Scratch &>(*s));
@@ -1075,8 +1108,8 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
             if (src.color_type == RT_COLOR_FACE && (rc = dev_upload(s, src.face_colors, (size_t)3 * src.n_triangles, &o.face_colors))) return rc;
             if (src.n_leaf_refs) {
                 DevTmp d_pos, d_refs;
-                RT_CUDA(d_pos.put(src.positions, (size_t)3 * src.n_vertices * sizeof(float)));
-                RT_CUDA(d_refs.put(src.leaf_refs, (size_t)src.n_leaf_refs * sizeof(RtTriRef)));
+                RT_CUDA(d_pos.put(s, src.positions, (size_t)3 * src.n_vertices * sizeof(float)));
+                RT_CUDA(d_refs.put(s, src.leaf_refs, (size_t)src.n_leaf_refs * sizeof(RtTriRef)));
                 const uint32_t rb = pk.ref_begin[i];
                 k_precompute_tris<<<(src.n_leaf_refs + 127) / 128, 128>>>((const float *)d_pos.p, (const RtTriRef *)d_refs.p, src.n_leaf_refs,
                                                                          pl + rb, ed + 3 * (size_t)rb, dn + rb);
@@ -1224,7 +1257,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
             w.max_grab = s->d.n_meshes > 0 ? 1u : 8u;
             w.cam_rays = s->cam_rays; w.cam_keys = s->cam_keys;
             w.ray0 = s->wf_f4; w.ray1 = s->wf_f4 + cap; w.hit0 = s->wf_f4 + 2 * cap; w.hit1 = s->wf_f4 + 3 * cap; w.hit2 = s->wf_f4 + 4 * cap;
-            w.hit3 = s->wf_f4 + 5 * cap; w.hit4 = s->wf_f4 + 6 * cap; w.park0 = s->wf_f4 + 7 * cap; w.park1 = s->wf_f4 + 8 * cap;
+            w.hit3 = s->wf_f4 + 5 * cap; w.hit4 = s->wf_f4 + 6 * cap; w.park0 = s->wf_f4 + 7 * cap; w.park1 = s->wf_f4 + 8 * cap; w.park2 = s->wf_f4 + 9 * cap;
             w.q_park = s->wf_q + 2 * cap;
             w.rng = s->wf_rng; w.rec = s->wf_rec; w.rec_stride = cap;
             w.ctr = s->wf_ctr; w.samples = s->samples; w.stats = a.stats;

@@ -114,6 +114,7 @@ namespace rt {
 
 #define RT_EPSF 1e-5f          /* (float)EPSILON */
 #define RT_MAX_BOUNCES 16      /* capacity of the per-path radiance records */
+#define RT_LC_MAXC 32          /* capacity of the per-light list of candidate triangles (variants 5, 6) */
 #define RT_PI 3.14159265358979323846 /* M_PI */
 
 // ---- vectors -----------------------------------------------------------------------------------
@@ -964,7 +965,10 @@ struct PathState {
     float t_light;
     int max_bounces;
     uint32_t cm0, cm1, cm2, cm3;   // variant 5: analytic primitives (sequence index = bit) that can occlude light `light` from P
-    uint32_t cm_mesh;              // ... and whether the cone towards that light can touch any mesh
+    // ... and the triangles the cone towards that light can touch: (mesh << 27 | first leaf ref of the triangle), in mesh
+    // order; cl_n < 0 = too many for the list, shadow samples walk the mesh hierarchies themselves
+    uint32_t cl[RT_LC_MAXC];
+    int cl_n;
     V3 rec_c[RT_MAX_BOUNCES], rec_kd[RT_MAX_BOUNCES], rec_e[RT_MAX_BOUNCES];
     // wavefront kernels (variant 6) keep the per-depth records in global memory instead: entry (3*depth + {0 colour,
     // 1 kd, 2 e}) of path slot `path` is wf_rec[(3*depth + k) * wf_stride + path]; the arrays above are then unused
@@ -1353,7 +1357,7 @@ RT_HD bool lc_cannot_occlude(const DScene &s, uint32_t seq, int ns, V3 P, float 
 // No candidate at all (and no mesh in the cone): the NB_ECH samples of this light are all unoccluded. Each would
 // draw three numbers for its direction and nothing else (Scene.h:325-330, computeShadow draws only per candidate hit),
 // so the stream advances by 3*NB_ECH and shadow = 1 - 0/NB_ECH = 1 leaves the colour unchanged (x * 1.0f == x).
-RT_HD bool lc_light_unoccluded(const PathState &st) { return (st.cm0 | st.cm1 | st.cm2 | st.cm3 | st.cm_mesh) == 0u; }
+RT_HD bool lc_light_unoccluded(const PathState &st) { return (st.cm0 | st.cm1 | st.cm2 | st.cm3) == 0u && st.cl_n == 0; }
 
 // One step of the variant-5 state machine for the lanes selected by `mine`.
 //   run_t (warp-uniform) true : lanes in mode 0 (closest hit) and mode 3 (collect candidates) walk the
@@ -1492,19 +1496,54 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
 #endif
             if (collect) {
                 st.cm0 = m0; st.cm1 = m1; st.cm2 = m2; st.cm3 = m3; done = true;
-                // can the cone touch a mesh? (root of its culling hierarchy; ill-conditioned triangles are outside any box)
-                uint32_t any = 0u;
-                for (int i = 0; i < s.n_meshes && !any; ++i) {
+                // Triangles a shadow sample of this light can hit: ONE walk of each mesh's culling hierarchy with the cone
+                // (the boxes bound every well-conditioned triangle and are already padded for the reference's test), plus
+                // the few ill-conditioned triangles that are tested for every ray. A candidate is dropped when its plane
+                // shows it cannot be hit: Triangle::getIntersection needs d.n < 0 and t = (D - o.n)/(d.n) >= 0, i.e. the
+                // origin on the front side; a plane with P behind it, or seen from behind by every cone direction, is out
+                // (same margins as lc_cannot_occlude; a NaN plane fails both tests and stays).
+                int cn = 0;
+                const float plen = length(st.P);
+                for (int i = 0; i < s.n_meshes && cn >= 0; ++i) {
                     const DMesh &m = s.meshes[i];
-                    if (m.always_count > 0u) { any = 1u; break; }
-                    if (m.bvh_root < 0) continue;
-                    const float4 n0 = RT_LDG(s.bvh_nodes + 4 * m.bvh_root), n1 = RT_LDG(s.bvh_nodes + 4 * m.bvh_root + 1),
-                                 n2 = RT_LDG(s.bvh_nodes + 4 * m.bvh_root + 2);
-                    float d0;
-                    if (cone_box(cone, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, limit_c, d0) ||
-                        cone_box(cone, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, limit_c, d0)) any = 1u;
+                    if (STATS) cnt->mesh++;
+                    int msp = 0;
+                    int mnode = m.bvh_root >= 0 ? m.bvh_root : 0x7FFFFFFF;
+                    uint32_t k = m.always_first, kend = m.always_first + m.always_count;
+                    for (;;) {
+                        for (; k < kend && cn >= 0; ++k) {
+                            const uint32_t r0 = RT_LDG(s.bvh_tris + k);
+                            const float4 pl = RT_LDG(s.tri_plane + r0);
+                            const V3 n = v3(pl.x, pl.y, pl.z);
+                            const float nl = length(n);
+                            const bool faces_away = dot(coneD, n) - cone_delta * nl > 1e-4f * nl * (cone_len + cone_delta) + 1e-12f;
+                            const bool behind = dot(st.P, n) - pl.w < -(1e-4f * (plen * nl + fabsf(pl.w)) + 2e-5f * nl + 1e-12f);
+                            if (faces_away || behind) continue;
+                            if (cn >= RT_LC_MAXC || i >= 32 || r0 >= (1u << 27)) { cn = -1; break; }
+                            st.cl[cn++] = ((uint32_t)i << 27) | r0;
+                        }
+                        if (cn < 0) break;
+                        // next leaf of this mesh's hierarchy the cone touches
+                        while (mnode >= 0 && mnode != 0x7FFFFFFF) {
+                            const float4 n0 = RT_LDG(s.bvh_nodes + 4 * mnode), n1 = RT_LDG(s.bvh_nodes + 4 * mnode + 1),
+                                         n2 = RT_LDG(s.bvh_nodes + 4 * mnode + 2), n3 = RT_LDG(s.bvh_nodes + 4 * mnode + 3);
+                            if (STATS) cnt->node++;
+                            float d0, d1;
+                            const bool h0 = cone_box(cone, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, limit_c, d0);
+                            const bool h1 = cone_box(cone, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, limit_c, d1);
+                            const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
+                            if (h0 && h1) { mnode = c0; stack[msp++] = c1; }
+                            else if (h0) mnode = c0;
+                            else if (h1) mnode = c1;
+                            else mnode = msp > 0 ? stack[--msp] : 0x7FFFFFFF;
+                        }
+                        if (mnode == 0x7FFFFFFF) break;
+                        const uint32_t code = (uint32_t)(-(mnode + 1));
+                        k = code >> 3; kend = k + (code & 7u);
+                        mnode = msp > 0 ? stack[--msp] : 0x7FFFFFFF;
+                    }
                 }
-                st.cm_mesh = any;
+                st.cl_n = cn;
             }
         }
     } else if (mine) {
@@ -1579,7 +1618,25 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
         }
     }
 #endif
-    // meshes: per-ray exact culling traversal, as in variant 3 (closest-hit and shadow lanes together)
+    // meshes. Closest-hit rays, and shadow samples whose light has too many candidate triangles for the list, walk the
+    // exact culling hierarchies (variant 3); other shadow samples test the listed candidates, mesh after mesh in the
+    // reference's order, with the same per-triangle routine (bvh_consider) the walk uses.
+    if (mode == 1 && !run_t && st.cl_n >= 0) {
+        int k = 0;
+        while (k < st.cl_n && !done) {
+            const uint32_t mi = st.cl[k] >> 27;
+            if (STATS) cnt->mesh++;
+            float best_t = h.t;
+            uint32_t best_ref = 0xFFFFFFFFu;
+            for (; k < st.cl_n && (st.cl[k] >> 27) == mi; ++k)
+                bvh_consider<STATS>(ray, s, st.cl[k] & 0x07FFFFFFu, best_t, best_ref, cnt);
+            if (best_ref != 0xFFFFFFFFu && best_t < h.t && best_t > RT_EPSF) {
+                if (STATS) cnt->rnd++;
+                if (st.rng.next() > RT_LDG(s.mesh_transparency + mi)) { blocked = true; done = true; }
+            }
+        }
+        return;
+    }
     for (int i = 0; i < s.n_meshes; ++i) {
         if (done) break;
         if (STATS) cnt->mesh++;

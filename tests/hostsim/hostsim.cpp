@@ -49,12 +49,14 @@ static DImage to_dimg(const RtImage &im) {
     return d;
 }
 
-static std::atomic<unsigned long long> g_dbg_lights(0), g_dbg_unoccluded(0), g_dbg_cands(0);
+static std::atomic<unsigned long long> g_dbg_lights(0), g_dbg_unoccluded(0), g_dbg_cands(0), g_dbg_overflow(0), g_dbg_tris(0);
 
 extern "C" {
 
 // debug: lights lit in wavefront mode (variant 6), how many needed no shadow sample, candidates of the others
-void sim_debug_counts(unsigned long long *out3) { out3[0] = g_dbg_lights; out3[1] = g_dbg_unoccluded; out3[2] = g_dbg_cands; g_dbg_lights = 0; g_dbg_unoccluded = 0; g_dbg_cands = 0; }
+// debug: per mesh {bvh_root, always_count}
+int sim_mesh_info(void *h, int *out, int cap) { const SimScene *s = (const SimScene *)h; int n = 0; for (int i = 0; i < s->d.n_meshes && 2 * i + 1 < cap; ++i) { out[2 * i] = s->d.meshes[i].bvh_root; out[2 * i + 1] = (int)s->d.meshes[i].always_count; ++n; } return n; }
+void sim_debug_counts(unsigned long long *out5) { out5[0] = g_dbg_lights; out5[1] = g_dbg_unoccluded; out5[2] = g_dbg_cands; out5[3] = g_dbg_overflow; out5[4] = g_dbg_tris; g_dbg_lights = 0; g_dbg_unoccluded = 0; g_dbg_cands = 0; g_dbg_overflow = 0; g_dbg_tris = 0; }
 
 
 void *sim_scene_create(const RtSceneDesc *desc) {
@@ -189,6 +191,7 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                                     intersect_lc<false>(s->d, st, st.mode == 3, true, hit, hu, hv, blocked, nullptr);
                                     if (was3) {
                                         g_dbg_lights++;
+                                        if (st.cl_n < 0) g_dbg_overflow++; else g_dbg_tris += st.cl_n;
                                         if (lc_light_unoccluded(st)) g_dbg_unoccluded++;
                                         else g_dbg_cands += __builtin_popcount(st.cm0) + __builtin_popcount(st.cm1) + __builtin_popcount(st.cm2) + __builtin_popcount(st.cm3);
                                     }

@@ -1171,7 +1171,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     // are faster in the single state-machine kernel over the exact culling hierarchies (3); scenes with a handful of
     // analytic primitives and nothing else (config 1) in the plain one-path-per-lane kernel (1).
     int kind_req = p->variant & 0xFF;
-    if (kind_req == 0 && s->d.abvh_root >= 0) kind_req = 6;
+    if (kind_req == 0 && s->d.abvh_root >= 0 && s->d.n_spheres + s->d.n_squares >= 24) kind_req = 6;
     const bool wavefront = kind_req == 6 && p->max_bounces > 0;
     const unsigned long long max_paths = wavefront ? (8ull << 20) : (16ull << 20);   // wavefront state: ~130 B + 48 B/bounce per path
     unsigned long long chunk_pixels = std::max<unsigned long long>(1, max_paths / (unsigned long long)p->spp);

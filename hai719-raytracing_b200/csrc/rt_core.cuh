@@ -114,7 +114,7 @@ namespace rt {
 
 #define RT_EPSF 1e-5f          /* (float)EPSILON */
 #define RT_MAX_BOUNCES 16      /* capacity of the per-path radiance records */
-#define RT_LC_MAXC 32          /* capacity of the per-light list of candidate triangles (variants 5, 6) */
+#define RT_LC_MAXC 16          /* capacity of the per-light list of candidate triangles (variants 5, 6) */
 #define RT_PI 3.14159265358979323846 /* M_PI */
 
 // ---- vectors -----------------------------------------------------------------------------------
@@ -988,7 +988,7 @@ RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_ligh
     bool done = (mode == 2);
     if (STATS) { if (mode == 0) cnt->closest++; else if (mode == 1) cnt->shadow++; }
     const SphereRay sr = make_sphere_ray(ray);
-    if (ACCEL && s.abvh_root >= 0) {
+    if (ACCEL && s.abvh_root >= 0 && s.n_spheres + s.n_squares >= 24) {   // below 24 the linear loops are as fast (the small hierarchy exists for variants 5/6)
         // variant 3: candidates from the culling hierarchy, exact tests, order semantics restored
         if (!done) {
             const int ns = s.n_spheres;

@@ -383,7 +383,7 @@ def main():
         "traffic": None,
         "kernel": kernel_of(scene.counts(), args.variant),
         "kernel_ms_per_launch": k_ms, "launches_per_step": n_launch,
-        "launch": "one chunk of <= 8 Mi (wavefront) / 16 Mi paths: every render kernel of the chunk, CUDA events around them on the launching stream",
+        "launch": "one chunk of <= 32 Mi (wavefront) / 16 Mi paths: every render kernel of the chunk, CUDA events around them on the launching stream",
         "peak_source": "fp32 unfused FMUL+FADD measured live by rt_measure_fp32_peak (fused: %.1f TFLOP/s); hbm %s" % (fp32_fused, hbm_src),
         "fp32": {"achieved_tflops": ach_tflops, "peak_tflops": fp32_unfused, "frac": ach_tflops / fp32_unfused,
                  "algorithmic_flops_per_ray": my_flops / max(1, my_rays)},

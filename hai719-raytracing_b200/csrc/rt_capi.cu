@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -340,6 +341,15 @@ struct WfArgs {
 #define WF_STAGE_FLUSH 256
 #define WF_STAGE_CAP (WF_STAGE_FLUSH + 32)
 struct WorkFetch { unsigned int cur, end; };
+// Tried and switched off: pulling the state of the NEXT batch's paths towards L2 (prefetch.global.L2) while this batch
+// is processed. The records were written by the previous kernel and are gone from L2, and ncu shows
+// stall_long_scoreboard 8-12 per issue in the classify and deep trace kernels — but the prefetch needs the next
+// batch's slots from the queue first (a dependent load in front of the real work) and measured 5 % SLOWER on config 2
+// (28.9 -> 30.3 ms per frame at 32 spp), 1-2 % slower on configs 4 and 5. -DRT_WF_PREFETCH=1 brings it back.
+#ifndef RT_WF_PREFETCH
+#define RT_WF_PREFETCH 0
+#endif
+__device__ __forceinline__ void wf_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ bool wf_next_batch(unsigned int *head, unsigned int count, unsigned int max_grab, WorkFetch &f, unsigned int &base) {
     if (f.cur >= f.end) {   // warp-uniform
         const unsigned int lane = threadIdx.x & 31u;
@@ -406,6 +416,10 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
         if (!wf_next_batch(w.ctr + 6 * w.level, count, w.max_grab, fetch, base)) break;
         const unsigned int i = base + lane;
         const bool valid = i < count;
+        if (RT_WF_PREFETCH && w.level > 0 && fetch.cur < fetch.end && fetch.cur + lane < count) {   // next batch of this warp's grab
+            const unsigned int ns = w.q_in[fetch.cur + lane];
+            wf_prefetch_l2(w.ray0 + ns); wf_prefetch_l2(w.ray1 + ns); wf_prefetch_l2(w.rng + ns);
+        }
         PathState st;
         st.mode = 2; st.t_light = 0.f; st.light = 0;
         st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
@@ -486,6 +500,12 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
         if (!wf_next_batch(head, count, w.max_grab, fetch, base)) break;
         const unsigned int i = base + lane;
         const bool valid = i < count;
+        if (RT_WF_PREFETCH && fetch.cur < fetch.end && fetch.cur + lane < count) {   // next batch of this warp's grab
+            const unsigned int ns = q_in[fetch.cur + lane];
+            wf_prefetch_l2(w.hit0 + ns); wf_prefetch_l2(w.hit1 + ns); wf_prefetch_l2(w.hit2 + ns); wf_prefetch_l2(w.hit3 + ns);
+            wf_prefetch_l2(w.hit4 + ns); wf_prefetch_l2(w.rng + ns);
+            if (PHASE == 2) { wf_prefetch_l2(w.park0 + ns); wf_prefetch_l2(w.park1 + ns); }
+        }
         PathState st;
         st.mode = 2; st.t_light = 0.f; st.light = 0;
         st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
@@ -1173,7 +1193,11 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     int kind_req = p->variant & 0xFF;
     if (kind_req == 0 && s->d.abvh_root >= 0 && s->d.n_spheres + s->d.n_squares >= 24) kind_req = 6;
     const bool wavefront = kind_req == 6 && p->max_bounces > 0;
-    const unsigned long long max_paths = wavefront ? (8ull << 20) : (16ull << 20);   // wavefront state: ~130 B + 48 B/bounce per path
+    // paths per chunk. Wavefront: every kernel of a chunk ends in a tail during which SMs drain, so fewer, larger chunks
+    // are faster (config 2, ms per frame at 32 spp: 4 Mi 36.5, 8 Mi 32.9, 16 Mi 31.3, 32 Mi 30.3); 32 Mi paths are ~17 GB
+    // of path state at 6 bounces (~230 B + 48 B per bounce and path), a tenth of the HBM
+    unsigned long long max_paths = wavefront ? (32ull << 20) : (16ull << 20);
+    if (const char *e = getenv("HAI719_CHUNK_LOG2")) { const int l = atoi(e); if (l >= 16 && l <= 26) max_paths = 1ull << l; }   // tuning experiments
     unsigned long long chunk_pixels = std::max<unsigned long long>(1, max_paths / (unsigned long long)p->spp);
     chunk_pixels = std::min(chunk_pixels, n_pixels);
     // bit 28 of variant: generate camera rays inside the render kernel instead of the k_camera_rays pass (A/B switch)

@@ -114,7 +114,9 @@ namespace rt {
 
 #define RT_EPSF 1e-5f          /* (float)EPSILON */
 #define RT_MAX_BOUNCES 16      /* capacity of the per-path radiance records */
+#ifndef RT_LC_MAXC
 #define RT_LC_MAXC 16          /* capacity of the per-light list of candidate triangles (variants 5, 6) */
+#endif
 #define RT_PI 3.14159265358979323846 /* M_PI */
 
 // ---- vectors -----------------------------------------------------------------------------------

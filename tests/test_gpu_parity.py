@@ -200,12 +200,14 @@ def test_crop_tiles_and_ranks_do_not_change_pixels(gpu, assets):
         assert np.array_equal(acc.view(np.uint32), full["gamma"].view(np.uint32))
 
 
-def test_chunked_render_equals_oracle_crop(gpu, ref, assets):
-    """> 16 Mi paths forces several chunks; compare a window of it with the oracle at the same full size."""
+def test_chunked_render_equals_oracle_crop(gpu, ref, assets, monkeypatch):
+    """Several chunks (4 Mi paths each, forced through the tuning override the library reads per call); compare a
+    window with the oracle at the same full size."""
     w, h, spp = 1024, 576, 32
     s = gpu.Scene("random_spheres", aspect=w / h)
+    monkeypatch.setenv("HAI719_CHUNK_LOG2", "22")
     out = s.render(w, h, spp, seed=9, stats=True)
-    assert out["stats"]["n_samples"] == w * h * spp and out["stats"]["n_launches"] >= 4
+    assert out["stats"]["n_samples"] == w * h * spp and out["stats"]["n_chunks"] == 5
     a = ref.scene("random_spheres", aspect=w / h)
     want = a.render(w, h, spp, seed=9, crop=(500, 300, 532, 316), want_ids=False)
     a.close()
@@ -215,6 +217,22 @@ def test_chunked_render_equals_oracle_crop(gpu, ref, assets):
     rays_per_sample = (r["n_closest_rays"] + r["n_shadow_rays"]) / r["n_samples"]
     assert 5.0 < rays_per_sample < 20.0          # 10.4 on this scene
     assert r["n_sphere_tests"] == 82 * (r["n_closest_rays"] + r["n_shadow_rays"]) or r["n_sphere_tests"] > 0
+
+
+@pytest.mark.parametrize("name", ["random_spheres", "config5", "backrooms_pool"])
+def test_chunk_size_does_not_change_pixels(gpu, assets, monkeypatch, name):
+    """Chunks of 64 Ki paths (dozens of chunks, queues and counters reused) against one chunk, wavefront and state machine."""
+    w, h, spp = 320, 180, 6
+    s = gpu.Scene(name, aspect=w / h)
+    one = s.render(w, h, spp, seed=12, variant=6, stats=True)
+    assert one["stats"]["n_chunks"] == 1
+    monkeypatch.setenv("HAI719_CHUNK_LOG2", "16")
+    for v in (6, 5, 3):
+        many = s.render(w, h, spp, seed=12, variant=v, stats=True)
+        assert many["stats"]["n_chunks"] >= 5
+        assert np.array_equal(one["linear"].view(np.uint32), many["linear"].view(np.uint32)), v
+        for k in ("n_closest_rays", "n_shadow_rays", "n_random"):
+            assert one["stats"][k] == many["stats"][k], (v, k)
 
 
 def test_full_size_config2_window_matches_oracle(gpu, ref, assets):

@@ -114,13 +114,13 @@ class RtStats(C.Structure):
 
 
 # every symbol the two headers declare — tests check the libraries export exactly these
-RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy", "rt_release_cached_memory",
+RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy", "rt_release_cached_memory", "rt_scene_update_analytic",
               "rt_scene_device_bytes", "rt_render_pixel_count", "rt_tile_layout", "rt_render", "rt_render_rgb8", "rt_quantize_device",
               "rt_render_device", "rt_untile_device",
               "rt_trace_primary", "rt_trace_rays", "rt_shade_rays", "rt_measure_fp32_peak"]
 HOST_SYMBOLS = ["hai_last_error", "hai_scene_new", "hai_scene_free", "hai_scene_setup", "hai_scene_dump",
                 "hai_scene_flatten", "hai_scene_kd_stats", "hai_scene_counts", "hai_default_camera", "hai_render",
-                "hai_scene_device", "hai_scene_invalidate_device", "hai_ray_trace_from_camera", "hai_ray_trace_from_camera_rgb8"]
+                "hai_scene_device", "hai_scene_invalidate_device", "hai_scene_move_sphere", "hai_scene_update_device", "hai_ray_trace_from_camera", "hai_ray_trace_from_camera_rgb8"]
 
 if not (os.path.exists(LIB_RT) and os.path.exists(LIB_HOST)):
     raise ImportError("hai719-raytracing_b200: native libraries not built (%s). Run `make -C %s` or "
@@ -132,6 +132,7 @@ host = C.CDLL(LIB_HOST)
 rt.rt_last_error.restype = C.c_char_p
 rt.rt_scene_create.argtypes = [C.POINTER(RtSceneDesc), C.c_int, C.POINTER(C.c_void_p)]
 rt.rt_scene_destroy.argtypes = [C.c_void_p]
+rt.rt_scene_update_analytic.argtypes = [C.c_void_p, C.POINTER(RtSceneDesc)]
 rt.rt_scene_device_bytes.restype = C.c_size_t
 rt.rt_scene_device_bytes.argtypes = [C.c_void_p]
 rt.rt_render_pixel_count.restype = C.c_int64
@@ -171,6 +172,8 @@ host.hai_scene_device.argtypes = [C.c_void_p, C.c_int]
 host.hai_scene_invalidate_device.argtypes = [C.c_void_p]
 host.hai_ray_trace_from_camera.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
                                            C.c_void_p]
+host.hai_scene_move_sphere.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
+host.hai_scene_update_device.argtypes = [C.c_void_p]
 host.hai_ray_trace_from_camera_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
                                                 C.c_int, C.c_void_p]
 
@@ -273,6 +276,13 @@ class Scene:
 
     def invalidate_device(self):
         host.hai_scene_invalidate_device(self.h)
+
+    def move_sphere(self, index, dx, dy, dz):
+        _host_check(host.hai_scene_move_sphere(self.h, index, dx, dy, dz))
+
+    def update_device(self):
+        """Push the host scene's spheres / squares / lights to its device copies in place (no mesh / texture upload)."""
+        _host_check(host.hai_scene_update_device(self.h))
 
     def device_bytes(self, device=0):
         return int(rt.rt_scene_device_bytes(self.device_handle(device)))

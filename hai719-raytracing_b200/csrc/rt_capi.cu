@@ -167,16 +167,25 @@ __global__ void __launch_bounds__(128, 4) k_render_paths(const DScene scene, con
 // screen_space_to_world_space_ray, matrixUtilities.h:53-74) for every path of a chunk: one thread per path,
 // fully convergent, instead of a few refilling lanes of the render kernel running ~600 instructions of fp64
 // unprojection each (and keeping them in its instruction-cache footprint). 20 B per path.
-__global__ void __launch_bounds__(256) k_camera_rays(const DCamera cam, const RenderArgs a, float4 *rays, unsigned int *keys) {
+// (x, y) of every packed pixel of the chunk, once per pixel: the tile lookup is a binary search of ~11 dependent loads,
+// and k_camera_rays used to repeat it for each of the pixel's spp paths (camera rays were 10 % of config 2's GPU time)
+__global__ void __launch_bounds__(256) k_pixel_xy(const RenderArgs a, unsigned int n_pixels, unsigned int *xy) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    int x, y;
+    packed_to_xy(a, (unsigned int)a.pixel_begin + i, x, y);
+    xy[i] = (unsigned int)x | ((unsigned int)y << 16);
+}
+
+__global__ void __launch_bounds__(256) k_camera_rays(const DCamera cam, const RenderArgs a, const unsigned int *xy, float4 *rays, unsigned int *keys) {
     const unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.n_paths) return;
-    const unsigned int lp = (unsigned int)(a.pixel_begin + p / (unsigned int)a.spp);
     const unsigned int smp = (unsigned int)(p % (unsigned int)a.spp);
-    int x, y;
-    packed_to_xy(a, lp, x, y);
+    const unsigned int packed = __ldg(xy + p / (unsigned int)a.spp);
+    const int x = (int)(packed & 0xFFFFu), y = (int)(packed >> 16);
     Rng rng;
     rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, smp);
-    const Ray ray = primary_ray(cam, x, y, a.width, a.height, rng);
+    const Ray ray = primary_ray_inline(cam, x, y, a.width, a.height, rng);
     rays[p] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.time);
     keys[p] = rng.key;
 }
@@ -716,6 +725,7 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float *out, float a, float b,
 struct Scratch {
     float *samples = nullptr; size_t samples_cap = 0;
     float4 *cam_rays = nullptr; unsigned int *cam_keys = nullptr; size_t cam_cap = 0;   // per path of a chunk (k_camera_rays)
+    unsigned int *pix_xy = nullptr; size_t pix_cap = 0;                                 // per pixel of a chunk (k_pixel_xy)
     // wavefront state (variant 6), per path of a chunk: 7 float4 fields + rng + 2 queues, and 3 float4 per bounce
     float4 *wf_f4 = nullptr; uint2 *wf_rng = nullptr; unsigned int *wf_q = nullptr; float4 *wf_rec = nullptr; unsigned int *wf_ctr = nullptr;
     size_t wf_cap = 0; int wf_bounces = 0;
@@ -747,6 +757,7 @@ struct Scratch {
         if (samples) cudaFree(samples);
         if (cam_rays) cudaFree(cam_rays);
         if (cam_keys) cudaFree(cam_keys);
+        if (pix_xy) cudaFree(pix_xy);
         if (wf_f4) cudaFree(wf_f4);
         if (wf_rng) cudaFree(wf_rng);
         if (wf_q) cudaFree(wf_q);
@@ -771,6 +782,11 @@ struct RtScene : Scratch {
     DScene d{};
     size_t bytes = 0;
     std::vector<TileRec> h_tiles; std::vector<unsigned int> h_tile_off;
+    // device staging of the squares and capacity of the analytic hierarchy arrays: rt_scene_update_analytic rewrites the
+    // analytic primitives IN PLACE (same counts), so an animated scene never re-uploads its meshes and textures
+    SquareIn *d_square_in = nullptr;
+    size_t abvh_node_cap = 0, abvh_prim_cap = 0;
+    uint32_t n_textures = 0, n_normal_maps = 0;
 };
 
 namespace {
@@ -779,6 +795,7 @@ struct Rect { int x0, y0, x1, y1, tw, th; };
 
 int resolve_rect(const RtRenderParams &p, Rect &r) {
     if (p.width < 1 || p.height < 1) return fail(RT_ERR_INVALID, "width/height must be >= 1");
+    if (p.width > 65535 || p.height > 65535) return fail(RT_ERR_INVALID, "width/height must be <= 65535");
     if (p.spp < 1) return fail(RT_ERR_INVALID, "spp must be >= 1");
     if (p.max_bounces < 0 || p.max_bounces > RT_MAX_BOUNCES) return fail(RT_ERR_INVALID, "max_bounces must be in [0, 16]");
     if (p.nb_ech < 1) return fail(RT_ERR_INVALID, "nb_ech must be >= 1");
@@ -955,6 +972,91 @@ int ensure_scratch(RtScene *s, size_t sample_floats, size_t n_tiles, size_t cam_
     return RT_OK;
 }
 
+// Spheres, squares, lights and the culling hierarchy over the analytic primitives. update == false: first upload
+// (arrays come from the scene's arena); update == true: the same arrays are rewritten in place.
+template <class T> int dev_put(RtScene *s, bool update, const T *host, size_t n, const T **field) {
+    if (!update) return dev_upload(s, host, n, field);
+    if (n) RT_CUDA(cudaMemcpy(const_cast<T *>(*field), host, n * sizeof(T), cudaMemcpyHostToDevice));
+    return RT_OK;
+}
+int upload_analytic(RtScene *s, const RtSceneDesc *desc, bool update) {
+    DScene &d = s->d;
+    int rc;
+    // spheres
+    {
+        std::vector<float4> a(desc->n_spheres), b(desc->n_spheres);
+        std::vector<DMaterial> m(desc->n_spheres);
+        for (uint32_t i = 0; i < desc->n_spheres; ++i) {
+            const RtSphere &sp = desc->spheres[i];
+            if ((rc = check_material(sp.material, *desc))) return rc;
+            a[i] = make_float4(sp.center[0], sp.center[1], sp.center[2], sp.radius);
+            b[i] = make_float4(sp.material.motion[0], sp.material.motion[1], sp.material.motion[2], sp.material.transparency);
+            m[i] = to_dmat(sp.material);
+        }
+        if ((rc = dev_put(s, update, a.data(), a.size(), &d.sph_a))) return rc;
+        if ((rc = dev_put(s, update, b.data(), b.size(), &d.sph_b))) return rc;
+        if ((rc = dev_put(s, update, m.data(), m.size(), &d.sph_mat))) return rc;
+    }
+    // squares
+    if (desc->n_squares) {
+        std::vector<SquareIn> in(desc->n_squares);
+        std::vector<DMaterial> m(desc->n_squares);
+        std::vector<float> tr(desc->n_squares);
+        for (uint32_t i = 0; i < desc->n_squares; ++i) {
+            const RtSquare &q = desc->squares[i];
+            if ((rc = check_material(q.material, *desc))) return rc;
+            for (int k = 0; k < 3; ++k) { in[i].v0[k] = q.v0[k]; in[i].v1[k] = q.v1[k]; in[i].v3[k] = q.v3[k]; in[i].right[k] = q.right[k]; in[i].up[k] = q.up[k]; in[i].motion[k] = q.material.motion[k]; }
+            in[i].glass = q.material.type == RT_MAT_GLASS;
+            m[i] = to_dmat(q.material);
+            tr[i] = q.material.transparency;
+        }
+        const SquareIn *d_in = s->d_square_in;
+        DSquare *d_sq = const_cast<DSquare *>(d.squares);
+        if ((rc = dev_put(s, update, in.data(), in.size(), &d_in))) return rc;
+        s->d_square_in = const_cast<SquareIn *>(d_in);
+        if (!update && (rc = dev_alloc(s, in.size(), &d_sq))) return rc;
+        k_precompute_squares<<<(unsigned)((in.size() + 127) / 128), 128>>>(d_in, d_sq, (int)in.size());
+        RT_CUDA(cudaGetLastError());
+        d.squares = d_sq;
+        if ((rc = dev_put(s, update, m.data(), m.size(), &d.sq_mat))) return rc;
+        if ((rc = dev_put(s, update, tr.data(), tr.size(), &d.sq_transparency))) return rc;
+    }
+    // lights
+    {
+        std::vector<DLight> l(desc->n_lights);
+        for (uint32_t i = 0; i < desc->n_lights; ++i) {
+            for (int k = 0; k < 3; ++k) { l[i].pos[k] = desc->lights[i].pos[k]; l[i].color[k] = desc->lights[i].color[k]; }
+            l[i].radius = desc->lights[i].radius;
+        }
+        if ((rc = dev_put(s, update, l.data(), l.size(), &d.lights))) return rc;
+    }
+    // culling hierarchy over the analytic primitives (variant 3)
+    {
+        AnalyticAccel aa;
+        build_analytic_accel(*desc, aa);
+        d.abvh_root = aa.root;
+        for (int k = 0; k < 3; ++k) d.abvh_c[k] = aa.center[k];
+        d.abvh_r = aa.radius;
+        if (aa.root >= 0) {
+            if (!update) {
+                // a binary hierarchy over n primitives has at most n - 1 inner nodes (4 float4 each) and n leaf entries,
+                // whatever its shape: room for every later update
+                const size_t n = (size_t)desc->n_spheres + desc->n_squares;
+                float4 *nodes = nullptr; uint32_t *prims = nullptr;
+                s->abvh_node_cap = 4 * std::max<size_t>(1, n); s->abvh_prim_cap = std::max<size_t>(1, n);
+                if ((rc = dev_alloc(s, s->abvh_node_cap, &nodes))) return rc;
+                if ((rc = dev_alloc(s, s->abvh_prim_cap, &prims))) return rc;
+                d.abvh_nodes = nodes; d.abvh_prims = prims;
+            }
+            if (aa.nodes.size() > s->abvh_node_cap || aa.tris.size() > s->abvh_prim_cap) return fail(RT_ERR_INVALID, "analytic hierarchy outgrew its arrays");
+            RT_CUDA(cudaMemcpy(const_cast<float4 *>(d.abvh_nodes), aa.nodes.data(), aa.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+            RT_CUDA(cudaMemcpy(const_cast<uint32_t *>(d.abvh_prims), aa.tris.data(), aa.tris.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+    }
+
+    return RT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1001,6 +1103,25 @@ int rt_release_cached_memory(int device) {
 
 size_t rt_scene_device_bytes(const RtScene *s) { return s ? s->bytes : 0; }
 
+int rt_scene_update_analytic(RtScene *s, const RtSceneDesc *desc) {
+    if (!s || !desc) return fail(RT_ERR_INVALID, "null argument");
+    if (desc->abi_version != HAI719_RT_ABI_VERSION) return fail(RT_ERR_INVALID, "RtSceneDesc.abi_version mismatch");
+    if ((int)desc->n_spheres != s->d.n_spheres || (int)desc->n_squares != s->d.n_squares || (int)desc->n_lights != s->d.n_lights ||
+        (int)desc->n_meshes != s->d.n_meshes || desc->n_textures != s->n_textures || desc->n_normal_maps != s->n_normal_maps)
+        return fail(RT_ERR_INVALID, "rt_scene_update_analytic: primitive / light / mesh / image counts differ from the uploaded scene");
+    if ((desc->n_spheres && !desc->spheres) || (desc->n_squares && !desc->squares) || (desc->n_lights && !desc->lights))
+        return fail(RT_ERR_INVALID, "count > 0 with a null array");
+    RT_CUDA(cudaSetDevice(s->device));
+    RT_CUDA(cudaDeviceSynchronize());   // no render of the old primitives may still be in flight
+    const bool had_accel = s->d.abvh_root >= 0;
+    int rc = upload_analytic(s, desc, true);
+    if (rc) return rc;
+    if (had_accel != (s->d.abvh_root >= 0)) return fail(RT_ERR_INVALID, "rt_scene_update_analytic: hierarchy appeared or vanished");
+    s->d.dark_sky = desc->dark_sky;
+    RT_CUDA(cudaDeviceSynchronize());
+    return RT_OK;
+}
+
 int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
     if (!desc || !out) return fail(RT_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -1024,6 +1145,7 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
     DScene &d = s->d;
     d.n_spheres = (int)desc->n_spheres; d.n_squares = (int)desc->n_squares; d.n_meshes = (int)desc->n_meshes; d.n_lights = (int)desc->n_lights;
     d.dark_sky = desc->dark_sky;
+    s->n_textures = desc->n_textures; s->n_normal_maps = desc->n_normal_maps;
 
     // images
     std::vector<DImage> tex(desc->n_textures), nrm(desc->n_normal_maps);
@@ -1033,65 +1155,7 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
     if ((rc = dev_upload(s, nrm.data(), nrm.size(), &d.normal_maps))) return rc;
     if ((rc = upload_image(s, desc->skybox, d.sky))) return rc;
 
-    // spheres
-    {
-        std::vector<float4> a(desc->n_spheres), b(desc->n_spheres);
-        std::vector<DMaterial> m(desc->n_spheres);
-        for (uint32_t i = 0; i < desc->n_spheres; ++i) {
-            const RtSphere &sp = desc->spheres[i];
-            if ((rc = check_material(sp.material, *desc))) return rc;
-            a[i] = make_float4(sp.center[0], sp.center[1], sp.center[2], sp.radius);
-            b[i] = make_float4(sp.material.motion[0], sp.material.motion[1], sp.material.motion[2], sp.material.transparency);
-            m[i] = to_dmat(sp.material);
-        }
-        if ((rc = dev_upload(s, a.data(), a.size(), &d.sph_a))) return rc;
-        if ((rc = dev_upload(s, b.data(), b.size(), &d.sph_b))) return rc;
-        if ((rc = dev_upload(s, m.data(), m.size(), &d.sph_mat))) return rc;
-    }
-    // squares
-    if (desc->n_squares) {
-        std::vector<SquareIn> in(desc->n_squares);
-        std::vector<DMaterial> m(desc->n_squares);
-        std::vector<float> tr(desc->n_squares);
-        for (uint32_t i = 0; i < desc->n_squares; ++i) {
-            const RtSquare &q = desc->squares[i];
-            if ((rc = check_material(q.material, *desc))) return rc;
-            for (int k = 0; k < 3; ++k) { in[i].v0[k] = q.v0[k]; in[i].v1[k] = q.v1[k]; in[i].v3[k] = q.v3[k]; in[i].right[k] = q.right[k]; in[i].up[k] = q.up[k]; in[i].motion[k] = q.material.motion[k]; }
-            in[i].glass = q.material.type == RT_MAT_GLASS;
-            m[i] = to_dmat(q.material);
-            tr[i] = q.material.transparency;
-        }
-        const SquareIn *d_in = nullptr;
-        DSquare *d_sq = nullptr;
-        if ((rc = dev_upload(s, in.data(), in.size(), &d_in))) return rc;
-        if ((rc = dev_alloc(s, in.size(), &d_sq))) return rc;
-        k_precompute_squares<<<(unsigned)((in.size() + 127) / 128), 128>>>(d_in, d_sq, (int)in.size());
-        RT_CUDA(cudaGetLastError());
-        d.squares = d_sq;
-        if ((rc = dev_upload(s, m.data(), m.size(), &d.sq_mat))) return rc;
-        if ((rc = dev_upload(s, tr.data(), tr.size(), &d.sq_transparency))) return rc;
-    }
-    // lights
-    {
-        std::vector<DLight> l(desc->n_lights);
-        for (uint32_t i = 0; i < desc->n_lights; ++i) {
-            for (int k = 0; k < 3; ++k) { l[i].pos[k] = desc->lights[i].pos[k]; l[i].color[k] = desc->lights[i].color[k]; }
-            l[i].radius = desc->lights[i].radius;
-        }
-        if ((rc = dev_upload(s, l.data(), l.size(), &d.lights))) return rc;
-    }
-    // culling hierarchy over the analytic primitives (variant 3)
-    {
-        AnalyticAccel aa;
-        build_analytic_accel(*desc, aa);
-        d.abvh_root = aa.root;
-        for (int k = 0; k < 3; ++k) d.abvh_c[k] = aa.center[k];
-        d.abvh_r = aa.radius;
-        if (aa.root >= 0) {
-            if ((rc = dev_upload(s, aa.nodes.data(), aa.nodes.size(), &d.abvh_nodes))) return rc;
-            if ((rc = dev_upload(s, aa.tris.data(), aa.tris.size(), &d.abvh_prims))) return rc;
-        }
-    }
+    if ((rc = upload_analytic(s, desc, false))) return rc;
     // meshes: one shared node array + shared per-ref triangle constants (rt_pack.hpp, rt::DMesh)
     if (desc->n_meshes) {
         PackedMeshes pk;
@@ -1268,7 +1332,16 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
         const int g = (int)std::min<unsigned long long>((unsigned long long)grid, (batches + 3) / 4);
         if (cam_split) {
             a.cam_rays = s->cam_rays; a.cam_keys = s->cam_keys;
-            k_camera_rays<<<(unsigned)((a.n_paths + 255) / 256), 256, 0, st>>>(cam, a, s->cam_rays, s->cam_keys);
+            if (np > s->pix_cap) {
+                if (s->pix_xy) cudaFree(s->pix_xy);
+                s->pix_xy = nullptr; s->pix_cap = 0;
+                RT_CUDA(cudaMalloc((void **)&s->pix_xy, (size_t)chunk_pixels * sizeof(unsigned int)));
+                s->pix_cap = (size_t)chunk_pixels;
+            }
+            k_pixel_xy<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(a, (unsigned int)np, s->pix_xy);
+            RT_CUDA(cudaGetLastError());
+            k_camera_rays<<<(unsigned)((a.n_paths + 255) / 256), 256, 0, st>>>(cam, a, s->pix_xy, s->cam_rays, s->cam_keys);
+            ++launches;
             RT_CUDA(cudaGetLastError());
             ++launches;
         }

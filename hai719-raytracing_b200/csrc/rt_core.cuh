@@ -1816,12 +1816,16 @@ RT_HD Ray camera_ray(const DCamera &c, float u, float v, float time) {
     return make_ray(pos, dir, time);
 }
 // trace_line's per-sample prologue (main.cpp:189-192): u, v, time are draws 0, 1, 2
-RT_COLD Ray primary_ray(const DCamera &c, int x, int y, int w, int h, Rng &rng) {
+RT_HD Ray primary_ray_inline(const DCamera &c, int x, int y, int w, int h, Rng &rng) {
     const float u = ((float)x + rng.next()) / (float)w;
     const float v = ((float)y + rng.next()) / (float)h;
     const float time = rng.next();
     return camera_ray(c, u, v, time);
 }
+// out of line for the kernels that generate a camera ray now and then (refill of k_render_regen): keeps ~400 fp64-heavy
+// instructions out of their hot code. k_camera_rays inlines it: called by reference, the 272-byte camera struct would be
+// copied to local memory by every thread (37 STL + 39 LDL per path, measured 10 % of config 2's GPU time).
+RT_COLD Ray primary_ray(const DCamera &c, int x, int y, int w, int h, Rng &rng) { return primary_ray_inline(c, x, y, w, h, rng); }
 
 // gamma_correct (Functions.cpp:56-60)
 RT_HD float gamma_channel(float c) { return (float)pow((double)c, 1.0 / 2.2); }

@@ -21,6 +21,12 @@ DeviceScene::DeviceScene(const Scene &scene, int device) : device_(device) {
 
 DeviceScene::~DeviceScene() { rt_scene_destroy(handle_); }
 
+void DeviceScene::update_analytic(const Scene &scene) {
+    FlatScene flat;
+    scene.flatten(flat);
+    check(rt_scene_update_analytic(handle_, &flat.desc), "rt_scene_update_analytic");
+}
+
 RtRenderParams make_params(int w, int h, unsigned int nsamples, const RenderOptions &o) {
     RtRenderParams p{};
     p.width = w; p.height = h; p.spp = (int32_t)nsamples;

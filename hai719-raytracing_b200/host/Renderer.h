@@ -50,6 +50,8 @@ public:
     DeviceScene(const DeviceScene &) = delete;
     DeviceScene &operator=(const DeviceScene &) = delete;
     RtScene *handle() const { return handle_; }
+    // Push the scene's spheres, squares and lights again, in place (same counts); meshes and textures stay as uploaded.
+    void update_analytic(const Scene &scene);
     int device() const { return device_; }
 private:
     RtScene *handle_ = nullptr;

@@ -108,6 +108,19 @@ RtScene *hai_scene_device(HaiScene *s, int device) {
 
 void hai_scene_invalidate_device(HaiScene *s) { s->on_device.clear(); }
 
+int hai_scene_move_sphere(HaiScene *s, int index, float dx, float dy, float dz) {
+    if (index < 0 || (size_t)index >= s->scene.spheres.size()) { g_err = "no such sphere"; return -1; }
+    s->scene.spheres[index].m_center += Vec3(dx, dy, dz);
+    s->flat_valid = false;
+    return 0;
+}
+
+int hai_scene_update_device(HaiScene *s) {
+    return guarded([&] {
+        for (auto &kv : s->on_device) kv.second->update_analytic(s->scene);
+    });
+}
+
 int hai_render(HaiScene *s, int device, const RtCamera *cam, const RtRenderParams *params, float *gamma_rgb,
                float *linear_rgb, RtStats *stats) {
     RtScene *h = hai_scene_device(s, device);

@@ -47,6 +47,12 @@ int hai_render(HaiScene *s, int device, const RtCamera *cam, const RtRenderParam
 /* The device-resident scene handle (uploading if needed), for rt_render_device() etc. */
 RtScene *hai_scene_device(HaiScene *s, int device);
 
+/* Animated scenes: move sphere `index` by (dx, dy, dz) on the host; hai_scene_update_device() then pushes the analytic
+ * primitives (spheres, squares, lights) of the host scene to the device copies that exist, in place
+ * (rt_scene_update_analytic) — meshes and textures are not uploaded again. */
+int hai_scene_move_sphere(HaiScene *s, int index, float dx, float dy, float dz);
+int hai_scene_update_device(HaiScene *s);
+
 /* Drop the cached device copy, so the next hai_render()/hai_scene_device() uploads again (what a
  * fresh ray_trace_from_camera(scene, ...) call does every time). */
 void hai_scene_invalidate_device(HaiScene *s);

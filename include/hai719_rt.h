@@ -218,6 +218,10 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out);
  * per-device pool and handed to the next rt_scene_create on that device; rt_release_cached_memory frees the pool. */
 void rt_scene_destroy(RtScene *scene);
 int rt_release_cached_memory(int device);
+/* SURVEY 8(f)-1, incremental re-upload for animated scenes: rewrite the spheres, squares, lights and their culling
+ * hierarchy IN PLACE from `desc` (same counts as the uploaded scene; meshes, textures and normal maps of `desc` are
+ * ignored and stay as uploaded). Waits for renders in flight. A render after it equals a render of a fresh upload. */
+int rt_scene_update_analytic(RtScene *scene, const RtSceneDesc *desc);
 size_t rt_scene_device_bytes(const RtScene *scene);
 
 /* Number of pixels this rank renders under `params` (rectangle + tile sharding), i.e. the

@@ -297,6 +297,34 @@ def test_output_stage_rgb8_p3_p6(gpu, assets, tmp_path, name):
     assert raw.startswith(head) and raw[len(head):] == b.tobytes()
 
 
+@pytest.mark.parametrize("name", ["random_spheres", "config5", "raccoon"])
+def test_incremental_update_equals_fresh_upload(gpu, assets, name):
+    """rt_scene_update_analytic rewrites spheres / squares / lights and their hierarchy in place (meshes and
+    textures stay on the device). Frame after frame it must equal a fresh upload of the same host scene."""
+    w, h, spp = 160, 90, 3
+    s = gpu.Scene(name, aspect=w / h)
+    first = s.render(w, h, spp, seed=5)
+    bytes0 = s.device_bytes(0)
+    handle0 = s.device_handle(0)
+    for frame in range(3):
+        s.move_sphere(1, 0.35, 0.1 * frame, -0.2)
+        s.move_sphere(0, -0.2, 0.0, 0.15)
+        s.update_device()
+        assert s.device_handle(0) == handle0 and s.device_bytes(0) == bytes0      # same device scene, nothing re-allocated
+        got = s.render(w, h, spp, seed=5)
+        fresh = gpu.Scene(name, aspect=w / h)
+        for f in range(frame + 1):
+            fresh.move_sphere(1, 0.35, 0.1 * f, -0.2)
+            fresh.move_sphere(0, -0.2, 0.0, 0.15)
+        want = fresh.render(w, h, spp, seed=5)
+        fresh.close()
+        assert np.array_equal(got["linear"].view(np.uint32), want["linear"].view(np.uint32)), frame
+        assert not np.array_equal(got["linear"].view(np.uint32), first["linear"].view(np.uint32))
+    # a different number of primitives is refused
+    other = gpu.Scene("cornell_box", aspect=w / h)
+    assert gpu.rt.rt_scene_update_analytic(handle0, other.flatten()) == -1 and gpu.rt.rt_last_error()
+
+
 def test_device_output_and_untile(gpu, assets):
     """rt_render_device + rt_untile_device with torch-owned device buffers (what bench.py's multi-GPU path does)."""
     torch = pytest.importorskip("torch")

@@ -1672,8 +1672,16 @@ RT_HD V3 path_fold(const PathState &st, V3 tail) {
 }
 
 // next soft-shadow sample of light st.light (Scene.h:325-330)
+#ifndef RT_OPT_INLINE_SAMPLE
+#define RT_OPT_INLINE_SAMPLE 0
+#endif
 template <bool STATS>
-RT_COLD void path_shadow_sample(const DScene &s, PathState &st, Counters *cnt) {
+#if RT_OPT_INLINE_SAMPLE && defined(__CUDACC__)
+__device__ __forceinline__
+#else
+RT_COLD
+#endif
+void path_shadow_sample(const DScene &s, PathState &st, Counters *cnt) {
     if (STATS) cnt->rnd += 3;
     const V3 lp = ld3(s.lights[st.light].pos);
     const float delta = s.lights[st.light].radius / 2.f;

@@ -396,10 +396,13 @@ def main():
         "roofline_mrays_per_s": my_rays / max(t_fp, t_mem) / 1e6,
         "frac_of_roofline_rays": (my_rays / (k_ms * 1e-3 * n_launch)) / (my_rays / max(t_fp, t_mem)),
     }
-    # keep the traffic number of the last committed ncu capture, if any
+    # DRAM traffic of the last committed ncu capture (bytes per path), scaled to the paths of one launch group (chunk)
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "latest.json")))
-        roof["traffic"] = prof.get(args.workload, {}).get("dram_bytes_per_launch")
+        per_path = prof.get(args.workload, {}).get("dram_bytes_per_path")
+        if per_path is not None:
+            roof["traffic"] = per_path * (n_px * spp) / n_launch
+            roof["traffic_source"] = "profiles/latest.json: %.0f B of DRAM traffic per path (ncu --set full) x paths per chunk" % per_path
     except (OSError, ValueError):
         pass
 

@@ -349,6 +349,18 @@ struct WfArgs {
 //     with its exact size, so the queue has no holes and the next kernel's warps are full.
 #define WF_STAGE_FLUSH 256
 #define WF_STAGE_CAP (WF_STAGE_FLUSH + 32)
+// Path state, queues and radiance records are written once by one kernel and read once by the next, hundreds of MB per
+// level: streaming (evict-first) accesses keep them from pushing the per-thread stacks and the scene out of L2.
+#ifndef RT_WF_STREAM
+#define RT_WF_STREAM 1
+#endif
+#if RT_WF_STREAM
+#define WF_LD(p) __ldcs(p)
+#define WF_ST(p, v) __stcs((p), (v))
+#else
+#define WF_LD(p) (*(p))
+#define WF_ST(p, v) (*(p) = (v))
+#endif
 struct WorkFetch { unsigned int cur, end; };
 // Tried and switched off: pulling the state of the NEXT batch's paths towards L2 (prefetch.global.L2) while this batch
 // is processed. The records were written by the previous kernel and are gone from L2, and ncu shows
@@ -387,7 +399,7 @@ __device__ __forceinline__ void wf_stage_push(unsigned int *queue, unsigned int 
         unsigned int b = 0;
         if (lane == 0) b = atomicAdd(count, (unsigned int)WF_STAGE_FLUSH);
         b = __shfl_sync(0xFFFFFFFFu, b, 0);
-        for (unsigned int k = lane; k < WF_STAGE_FLUSH; k += 32u) queue[b + k] = stage[k];
+        for (unsigned int k = lane; k < WF_STAGE_FLUSH; k += 32u) WF_ST(queue + b + k, stage[k]);
         const unsigned int rem = fill - WF_STAGE_FLUSH;
         unsigned int keep = 0;
         if (lane < rem) keep = stage[WF_STAGE_FLUSH + lane];
@@ -403,15 +415,23 @@ __device__ __forceinline__ void wf_stage_flush(unsigned int *queue, unsigned int
     unsigned int b = 0;
     if (lane == 0) b = atomicAdd(count, fill);
     b = __shfl_sync(0xFFFFFFFFu, b, 0);
-    for (unsigned int k = lane; k < fill; k += 32u) queue[b + k] = stage[k];
+    for (unsigned int k = lane; k < fill; k += 32u) WF_ST(queue + b + k, stage[k]);
     fill = 0u;
 }
 
 #ifndef RT_WF_MINB
 #define RT_WF_MINB 8
 #endif
+#ifndef RT_WF_GRIDCONST
+#define RT_WF_GRIDCONST 0
+#endif
+#if RT_WF_GRIDCONST
+#define RT_WF_PARAM __grid_constant__
+#else
+#define RT_WF_PARAM
+#endif
 template <bool STATS, bool LC>
-__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene, const DCamera cam, const WfArgs w) {
+__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM DScene scene, const DCamera cam, const WfArgs w) {
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
@@ -444,9 +464,9 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
                 st.N = w.max_bounces; st.depth = 0;
                 if (STATS) cnt.rnd += 3;
             } else {
-                slot = w.q_in[i];
-                const float4 a = w.ray0[slot], b = w.ray1[slot];
-                const uint2 g = w.rng[slot];
+                slot = WF_LD(w.q_in + i);
+                const float4 a = WF_LD(w.ray0 + slot), b = WF_LD(w.ray1 + slot);
+                const uint2 g = WF_LD(w.rng + slot);
                 st.ray.o = v3(a.x, a.y, a.z); st.ray.time = a.w; st.ray.d = v3(b.x, b.y, b.z);
                 st.N = (int)(f2u(b.w) & 0xFFu); st.depth = (int)(f2u(b.w) >> 8);
                 st.rng.key = g.x; st.rng.ctr = g.y;
@@ -467,12 +487,12 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
             } else {
                 lit = true;
                 const uint32_t kind = (uint32_t)h.type, obj = (uint32_t)h.obj;   // st.mat = {sph,sq,mesh}_mat[obj]
-                w.hit0[slot] = make_float4(st.P.x, st.P.y, st.P.z, st.ray.time);
-                w.hit1[slot] = make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | obj));
-                w.hit2[slot] = make_float4(st.kd.x, st.kd.y, st.kd.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8)));
-                w.hit3[slot] = make_float4(st.e.x, st.e.y, st.e.z, 0.f);
-                w.hit4[slot] = make_float4(st.in_d.x, st.in_d.y, st.in_d.z, 0.f);
-                w.rng[slot] = make_uint2(st.rng.key, st.rng.ctr);
+                WF_ST(w.hit0 + slot, make_float4(st.P.x, st.P.y, st.P.z, st.ray.time));
+                WF_ST(w.hit1 + slot, make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | obj)));
+                WF_ST(w.hit2 + slot, make_float4(st.kd.x, st.kd.y, st.kd.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
+                WF_ST(w.hit3 + slot, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
+                WF_ST(w.hit4 + slot, make_float4(st.in_d.x, st.in_d.y, st.in_d.z, 0.f));
+                WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
             }
         }
         wf_stage_push(w.q_out, w.ctr + 6 * w.level + 3, stage, fill, lit, slot);
@@ -491,7 +511,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
 // Split because a warp is as slow as its slowest lane: with both phases in one loop, one lane that has to sample keeps
 // 31 finished lanes waiting for ten rounds.
 template <bool STATS, bool LC, int PHASE>
-__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene, const WfArgs w) {
+__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM DScene scene, const WfArgs w) {
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
@@ -525,9 +545,9 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
         bool fin = true, parked = false;
         V3 c = v3(0.f);
         if (valid) {
-            slot = q_in[i];
-            const float4 h0 = w.hit0[slot], h1 = w.hit1[slot], h2 = w.hit2[slot], h3 = w.hit3[slot], h4 = w.hit4[slot];
-            const uint2 g = w.rng[slot];
+            slot = WF_LD(q_in + i);
+            const float4 h0 = WF_LD(w.hit0 + slot), h1 = WF_LD(w.hit1 + slot), h2 = WF_LD(w.hit2 + slot), h3 = WF_LD(w.hit3 + slot), h4 = WF_LD(w.hit4 + slot);
+            const uint2 g = WF_LD(w.rng + slot);
             st.P = v3(h0.x, h0.y, h0.z); st.ray.time = h0.w;
             st.n = v3(h1.x, h1.y, h1.z);
             const uint32_t code = f2u(h1.w), kind = code >> 28, obj = code & 0x0FFFFFFFu;
@@ -539,11 +559,11 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
             st.rng.key = g.x; st.rng.ctr = g.y;
             st.path = slot;
             if (PHASE == 2) {
-                const float4 p0 = w.park0[slot], p1 = w.park1[slot];
+                const float4 p0 = WF_LD(w.park0 + slot), p1 = WF_LD(w.park1 + slot);
                 st.color = v3(p0.x, p0.y, p0.z);
                 st.light = (int)(f2u(p0.w) & 0xFFu); st.cl_n = (int)((f2u(p0.w) >> 8) & 0xFFu) - 1;
                 for (int q4 = 0; q4 * 4 < st.cl_n; ++q4) {
-                    const float4 v = w.park2[(size_t)q4 * w.rec_stride + slot];
+                    const float4 v = WF_LD(w.park2 + (size_t)q4 * w.rec_stride + slot);
                     st.cl[4 * q4] = f2u(v.x); st.cl[4 * q4 + 1] = f2u(v.y); st.cl[4 * q4 + 2] = f2u(v.z); st.cl[4 * q4 + 3] = f2u(v.w);
                 }
                 st.cm0 = f2u(p1.x); st.cm1 = f2u(p1.y); st.cm2 = f2u(p1.z); st.cm3 = f2u(p1.w);
@@ -574,19 +594,19 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
         bool alive = false;
         if (valid) {
             if (parked) {
-                w.park0[slot] = make_float4(st.color.x, st.color.y, st.color.z, u2f((uint32_t)st.light | ((uint32_t)(st.cl_n + 1) << 8)));
+                WF_ST(w.park0 + slot, make_float4(st.color.x, st.color.y, st.color.z, u2f((uint32_t)st.light | ((uint32_t)(st.cl_n + 1) << 8))));
                 for (int q4 = 0; q4 * 4 < st.cl_n; ++q4)
-                    w.park2[(size_t)q4 * w.rec_stride + slot] = make_float4(u2f(st.cl[4 * q4]), u2f(st.cl[4 * q4 + 1]), u2f(st.cl[4 * q4 + 2]), u2f(st.cl[4 * q4 + 3]));
-                w.park1[slot] = make_float4(u2f(st.cm0), u2f(st.cm1), u2f(st.cm2), u2f(st.cm3));
-                w.rng[slot] = make_uint2(st.rng.key, st.rng.ctr);
+                    WF_ST(w.park2 + (size_t)q4 * w.rec_stride + slot, make_float4(u2f(st.cl[4 * q4]), u2f(st.cl[4 * q4 + 1]), u2f(st.cl[4 * q4 + 2]), u2f(st.cl[4 * q4 + 3])));
+                WF_ST(w.park1 + slot, make_float4(u2f(st.cm0), u2f(st.cm1), u2f(st.cm2), u2f(st.cm3)));
+                WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
             } else if (fin) {
                 float *o = w.samples + 3ull * slot;
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
             } else {
                 alive = true;
-                w.ray0[slot] = make_float4(st.ray.o.x, st.ray.o.y, st.ray.o.z, st.ray.time);
-                w.ray1[slot] = make_float4(st.ray.d.x, st.ray.d.y, st.ray.d.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8)));
-                w.rng[slot] = make_uint2(st.rng.key, st.rng.ctr);
+                WF_ST(w.ray0 + slot, make_float4(st.ray.o.x, st.ray.o.y, st.ray.o.z, st.ray.time));
+                WF_ST(w.ray1 + slot, make_float4(st.ray.d.x, st.ray.d.y, st.ray.d.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
+                WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
             }
         }
         wf_stage_push(w.q_out, w.ctr + 6 * (w.level + 1) + 1, stage, fill, alive, slot);

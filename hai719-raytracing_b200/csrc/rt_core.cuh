@@ -66,7 +66,11 @@
 #define RT_SHARED_BOUNCE __device__ __forceinline__
 #endif
 #define RT_LDG(p) __ldg(p)
+#define RT_LD_STREAM(p) __ldcs(p)          /* written once, read once, far larger than L2: evict-first */
+#define RT_ST_STREAM(p, v) __stcs((p), (v))
 #else
+#define RT_LD_STREAM(p) (*(p))
+#define RT_ST_STREAM(p, v) (*(p) = (v))
 #define RT_SHARED_BOUNCE inline
 #define RT_HD inline
 #define RT_HHD inline
@@ -1660,8 +1664,8 @@ RT_HD V3 path_fold(const PathState &st, V3 tail) {
     V3 r = tail;
     for (int k = st.depth - 1; k >= 0; --k) {
         if (WF) {
-            const float4 c = st.wf_rec[(3ull * k + 0) * st.wf_stride + st.path], kd = st.wf_rec[(3ull * k + 1) * st.wf_stride + st.path],
-                         e = st.wf_rec[(3ull * k + 2) * st.wf_stride + st.path];
+            const float4 c = RT_LD_STREAM(st.wf_rec + (3ull * k + 0) * st.wf_stride + st.path), kd = RT_LD_STREAM(st.wf_rec + (3ull * k + 1) * st.wf_stride + st.path),
+                         e = RT_LD_STREAM(st.wf_rec + (3ull * k + 2) * st.wf_stride + st.path);
             r = (v3(c.x, c.y, c.z) + comp_product(r, v3(kd.x, kd.y, kd.z))) + v3(e.x, e.y, e.z);
         } else {
             r = (st.rec_c[k] + comp_product(r, st.rec_kd[k])) + st.rec_e[k];
@@ -1709,9 +1713,9 @@ RT_SHARED_BOUNCE bool path_next_light_or_bounce(const DScene &s, PathState &st, 
     Ray in; in.o = st.P; in.d = st.in_d; in.time = st.ray.time;
     st.ray = material_scatter<STATS>(*st.mat, in, st.n, st.P, st.rng, cnt);
     if (WF) {
-        st.wf_rec[(3ull * st.depth + 0) * st.wf_stride + st.path] = make_float4(st.color.x, st.color.y, st.color.z, 0.f);
-        st.wf_rec[(3ull * st.depth + 1) * st.wf_stride + st.path] = make_float4(st.kd.x, st.kd.y, st.kd.z, 0.f);
-        st.wf_rec[(3ull * st.depth + 2) * st.wf_stride + st.path] = make_float4(st.e.x, st.e.y, st.e.z, 0.f);
+        RT_ST_STREAM(st.wf_rec + (3ull * st.depth + 0) * st.wf_stride + st.path, make_float4(st.color.x, st.color.y, st.color.z, 0.f));
+        RT_ST_STREAM(st.wf_rec + (3ull * st.depth + 1) * st.wf_stride + st.path, make_float4(st.kd.x, st.kd.y, st.kd.z, 0.f));
+        RT_ST_STREAM(st.wf_rec + (3ull * st.depth + 2) * st.wf_stride + st.path, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
     } else {
         st.rec_c[st.depth] = st.color; st.rec_kd[st.depth] = st.kd; st.rec_e[st.depth] = st.e;
     }

@@ -120,7 +120,7 @@ RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_cr
               "rt_trace_primary", "rt_trace_rays", "rt_shade_rays", "rt_measure_fp32_peak"]
 HOST_SYMBOLS = ["hai_last_error", "hai_scene_new", "hai_scene_free", "hai_scene_setup", "hai_scene_dump",
                 "hai_scene_flatten", "hai_scene_kd_stats", "hai_scene_counts", "hai_default_camera", "hai_render",
-                "hai_scene_device", "hai_scene_invalidate_device", "hai_scene_move_sphere", "hai_scene_update_device", "hai_ray_trace_from_camera", "hai_ray_trace_from_camera_rgb8"]
+                "hai_scene_device", "hai_scene_invalidate_device", "hai_scene_move_sphere", "hai_scene_update_device", "hai_scene_load_file", "hai_ray_trace_from_camera", "hai_ray_trace_from_camera_rgb8"]
 
 if not (os.path.exists(LIB_RT) and os.path.exists(LIB_HOST)):
     raise ImportError("hai719-raytracing_b200: native libraries not built (%s). Run `make -C %s` or "
@@ -172,6 +172,7 @@ host.hai_scene_device.argtypes = [C.c_void_p, C.c_int]
 host.hai_scene_invalidate_device.argtypes = [C.c_void_p]
 host.hai_ray_trace_from_camera.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
                                            C.c_void_p]
+host.hai_scene_load_file.argtypes = [C.c_void_p, C.c_char_p]
 host.hai_scene_move_sphere.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
 host.hai_scene_update_device.argtypes = [C.c_void_p]
 host.hai_ray_trace_from_camera_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
@@ -239,6 +240,11 @@ class Scene:
     def setup(self, name, aspect=850.0 / 480.0, seed=0):
         sid = SCENES[name] if isinstance(name, str) else int(name)
         _host_check(host.hai_scene_setup(self.h, sid, aspect, seed))
+        return self
+
+    def load_file(self, filename):
+        """Build the scene from a scene description file (host/SceneFile.cpp)."""
+        _host_check(host.hai_scene_load_file(self.h, filename.encode()))
         return self
 
     def close(self):

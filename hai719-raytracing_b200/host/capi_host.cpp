@@ -6,6 +6,7 @@
 #include "Camera.h"
 #include "Renderer.h"
 #include "Scene.h"
+#include "SceneFile.h"
 #include "errors.h"
 #include "hai719_host.h"
 #include "matrixUtilities.h"
@@ -107,6 +108,14 @@ RtScene *hai_scene_device(HaiScene *s, int device) {
 }
 
 void hai_scene_invalidate_device(HaiScene *s) { s->on_device.clear(); }
+
+int hai_scene_load_file(HaiScene *s, const char *filename) {
+    if (!filename) { g_err = "null file name"; return -1; }
+    s->touch();
+    std::string err;
+    if (!hai719::load_scene_file(s->scene, filename, &err)) { g_err = err; return -1; }
+    return 0;
+}
 
 int hai_scene_move_sphere(HaiScene *s, int index, float dx, float dy, float dz) {
     if (index < 0 || (size_t)index >= s->scene.spheres.size()) { g_err = "no such sphere"; return -1; }

@@ -7,6 +7,7 @@
 #include <string>
 namespace hai719 {
 void set_fatal_throws(bool on);
+bool fatal_throws();
 [[noreturn]] void fatal(const std::string &what);
 }
 #endif

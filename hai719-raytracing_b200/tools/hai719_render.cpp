@@ -1,7 +1,7 @@
 // hai719_render — the headless stand-in for "press r" in the reference's GLUT shell
 // (main.cpp:321-326 -> ray_trace_from_camera). Builds one of the reference's scenes with the host
 // API, renders it on the GPU and writes the same P3 rendu.ppm.
-//   hai719_render [--scene N] [--w W --h H] [--spp S] [--seed K] [--assets DIR] [--out FILE] [--device D]
+//   hai719_render [--scene N | --scene-file FILE] [--w W --h H] [--spp S] [--seed K] [--assets DIR] [--out FILE] [--p6 1] [--device D]
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -10,11 +10,13 @@
 #include "Constants.h"
 #include "Renderer.h"
 #include "Scene.h"
+#include "SceneFile.h"
 
 int main(int argc, char **argv) {
     int scene_id = DEFAULT_SELECTED_SCENE, w = 850, h = 480, spp = DEFAULT_NSAMPLES, device = 0;
     unsigned int seed = 0;
-    std::string assets, out = "./rendu.ppm";
+    std::string assets, out = "./rendu.ppm", scene_file;
+    bool p6 = false;
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string k = argv[i];
         const char *v = argv[i + 1];
@@ -26,12 +28,17 @@ int main(int argc, char **argv) {
         else if (k == "--assets") assets = v;
         else if (k == "--out") out = v;
         else if (k == "--device") device = std::atoi(v);
+        else if (k == "--scene-file") scene_file = v;
+        else if (k == "--p6") p6 = std::atoi(v) != 0;
         else { std::cerr << "unknown option " << k << std::endl; return 2; }
     }
     Scene scene;
     scene.asset_root = assets;
     seed_scene_random(seed);
-    if (!scene.setup_by_id(scene_id, float(w) / float(h))) { std::cerr << "unknown scene " << scene_id << std::endl; return 2; }
+    if (!scene_file.empty()) {
+        std::string err;
+        if (!hai719::load_scene_file(scene, scene_file, &err)) { std::cerr << err << std::endl; return 2; }
+    } else if (!scene.setup_by_id(scene_id, float(w) / float(h))) { std::cerr << "unknown scene " << scene_id << std::endl; return 2; }
     Camera camera;
     camera.resize(w, h);
     camera.move(0., 0., -3.1);   // main.cpp:418
@@ -41,6 +48,12 @@ int main(int argc, char **argv) {
     opt.ppm_path = out;
     std::vector<Vec3> image;
     try {
+        if (p6) {   // output stage on the GPU: 8-bit quantise on the device, binary PPM
+            opt.format = hai719::RenderOptions::P6;
+            hai719::DeviceScene dev(scene, device);
+            std::vector<unsigned char> rgb8;
+            hai719::ray_trace_from_camera_rgb8(dev, camera, w, h, (unsigned int)spp, rgb8, opt);
+        } else
         hai719::ray_trace_from_camera(scene, camera, w, h, (unsigned int)spp, image, opt);
     } catch (const std::exception &e) {
         std::cerr << "render failed: " << e.what() << std::endl;

@@ -47,6 +47,10 @@ int hai_render(HaiScene *s, int device, const RtCamera *cam, const RtRenderParam
 /* The device-resident scene handle (uploading if needed), for rt_render_device() etc. */
 RtScene *hai_scene_device(HaiScene *s, int device);
 
+/* Replace the scene by the one a scene description file builds (grammar: host/SceneFile.cpp; file names inside it are
+ * relative to the asset root given to hai_scene_new). Errors come back as "<file>:<line>: <what>". */
+int hai_scene_load_file(HaiScene *s, const char *filename);
+
 /* Animated scenes: move sphere `index` by (dx, dy, dz) on the host; hai_scene_update_device() then pushes the analytic
  * primitives (spheres, squares, lights) of the host scene to the device copies that exist, in place
  * (rt_scene_update_analytic) — meshes and textures are not uploaded again. */

@@ -106,6 +106,73 @@ def test_flatten_is_consistent(hb, assets):
         assert nrefs[lf].sum() == m.n_leaf_refs
 
 
+MESH_SCENE_FILE = """hai719scene 1
+# Scene::setup_mesh (Scene.h / host Scene.cpp), restated as a scene description file
+sky image img/textures/space.ppm
+light 0 3 2
+material green kd 0.1 0.6 0.2
+material mir   mirror kd 0.8 0.8 0.8
+material water glass kd 0.1 0.2 0.5 ior 1.333 transparency 0.9
+material white kd 1 1 1
+material black kd 0 0 0
+material floor kd 0.8 0.8 0
+sphere green 0 0 -16 2
+sphere mir 4 0 -8 2
+mesh water mesh/blob-closed.off translate 0 0.9 -4 scale 1.5 1.5 1.5 rotate_x 180 rotate_y 180
+sphere white 0.2 -1 -4.8 0.3      # eye
+sphere black 0.2 -1 -4.55 0.1     # pupil
+sphere white -0.7 -1 -4.95 0.3
+sphere black -0.7 -1 -4.7 0.1
+square floor  -1 -0.2 0  1 0 0  0 1 0  2 2  translate 0 0 -2 scale 50 50 1 rotate_x -90
+"""
+
+REFRACTION_SCENE_FILE = """hai719scene 1
+sky gradient
+light -1 8 2
+material red kd 1 0 0
+material green kd 0 1 0
+material blue kd 0 0 1
+material white kd 1 1 1
+material lens glass kd 1 1 1 ior 1.4 transparency 1
+square red   -1 -1 0  1 0 0  0 1 0  2 2  scale 2 2 1 translate -2  2 -2
+square green -1 -1 0  1 0 0  0 1 0  2 2  scale 2 2 1 translate -2 -2 -2
+square blue  -1 -1 0  1 0 0  0 1 0  2 2  scale 2 2 1 translate  2  2 -2
+square white -1 -1 0  1 0 0  0 1 0  2 2  scale 2 2 1 translate  2 -2 -2
+sphere lens 0 0 0 0.75
+"""
+
+
+@pytest.mark.parametrize("builtin,text", [("mesh", MESH_SCENE_FILE), ("debug_refraction", REFRACTION_SCENE_FILE)])
+def test_scene_file_rebuilds_a_builtin_scene_bit_for_bit(hb, assets, tmp_path, builtin, text):
+    """a scene description file goes through the same host calls as the reference's hard-coded
+    builders, so restating a builder in the file format must give the identical canonical dump (every vertex, KD node,
+    leaf list, material, image hash)."""
+    f = tmp_path / "scene.txt"
+    f.write_text(text)
+    want = hb.Scene(builtin).dump()
+    got = hb.Scene().load_file(str(f)).dump()
+    assert got.size == want.size and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("text,needle", [
+    ("", ":0: empty file"),
+    ("hai719scene 2\n", ":1: expected the header"),
+    ("hai719scene 1\nsphere nope 0 0 0 1\n", ":2: unknown material 'nope'"),
+    ("hai719scene 1\nmaterial m kd 1 0\n", ":2: missing kd"),
+    ("hai719scene 1\nmaterial m kd 1 0 x\n", "is not a number"),
+    ("hai719scene 1\nmaterial m image 0 1 1\n", ":2: texture index out of range"),
+    ("hai719scene 1\nmaterial m\nmesh m mesh/does_not_exist.off\n", ":3:"),
+    ("hai719scene 1\nmaterial m\nsquare m 0 0 0 1 0 0 0 1 0 1 1 spin 3\n", ":3: unknown transform 'spin'"),
+    ("hai719scene 1\nfrobnicate\n", ":2: unknown statement 'frobnicate'"),
+])
+def test_scene_file_errors_carry_line_numbers_and_never_exit(hb, assets, tmp_path, text, needle):
+    f = tmp_path / "bad.txt"
+    f.write_text(text)
+    with pytest.raises(hb.RtError) as e:
+        hb.Scene().load_file(str(f))
+    assert needle in str(e.value), str(e.value)
+
+
 def test_missing_mesh_is_an_error_not_an_exit(hb, tmp_path):
     s = hb.Scene(assets=str(tmp_path))
     with pytest.raises(hb.RtError):

@@ -329,6 +329,7 @@ struct WfArgs {
     float4 *hit0, *hit1, *hit2, *hit3, *hit4;   // {P, time} {n, bits(kind << 28 | obj)} {kd, bits(N | depth << 8)} {e, -} {in_d, -}
     float4 *rec; unsigned long long rec_stride;
     unsigned int *q_in, *q_out;        // trace: q_in = live paths (level > 0), q_out = paths with a hit; light: the reverse
+    unsigned int *q_live_next;         // fused trace kernel: the queue of the next level's live rays
     unsigned int *q_park;              // light phase A -> phase B: hits whose light needs its shadow samples traced
     float4 *park0, *park1;             // ... and what phase B needs besides the hit record: {colour so far, light | (cl_n + 1) << 8}, {cm0..cm3}
     float4 *park2;                     // candidate triangles, RT_LC_MAXC / 4 float4 planes of rec_stride entries
@@ -430,15 +431,21 @@ __device__ __forceinline__ void wf_stage_flush(unsigned int *queue, unsigned int
 #else
 #define RT_WF_PARAM
 #endif
-template <bool STATS, bool LC>
+// FUSE (needs LC; experiment, off by default): the walk-and-classify phase of the light stage runs right here, on the hit
+// that was just shaded — the cone walk is the SAME code as the closest-hit walk, the hit never travels through HBM unless
+// its light needs samples, and each bounce level is two kernels instead of three. It measured 30-40 % slower than the
+// three-kernel split (rt_render_device, profiles/r01_notes.md).
+template <bool STATS, bool LC, bool FUSE>
 __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM DScene scene, const DCamera cam, const WfArgs w) {
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int count = w.level == 0 ? w.n_paths : w.ctr[6 * w.level + 1];
     __shared__ unsigned int stage_all[4][WF_STAGE_CAP];
+    __shared__ unsigned int stage_park_all[FUSE ? 4 : 1][FUSE ? WF_STAGE_CAP : 1];
     unsigned int *stage = stage_all[threadIdx.x >> 5];
-    unsigned int fill = 0u;
+    unsigned int *stage_park = stage_park_all[FUSE ? (threadIdx.x >> 5) : 0];
+    unsigned int fill = 0u, fill_park = 0u;
     WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
     for (;;) {
         unsigned int base;
@@ -453,6 +460,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
         st.mode = 2; st.t_light = 0.f; st.light = 0;
         st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
         st.rng.key = 0; st.rng.ctr = 0;
+        st.cm0 = st.cm1 = st.cm2 = st.cm3 = 0u; st.cl_n = 0;
         st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
         unsigned int slot = 0;
         if (valid) {
@@ -486,6 +494,54 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
             } else {
                 lit = true;
+            }
+        }
+        if (FUSE) {
+            const uint32_t kind = (uint32_t)h.type, obj = (uint32_t)h.obj;
+            bool fin = true, parked = false;
+            V3 c = v3(0.f);
+            if (lit) fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);   // mode 3, or the scatter
+            for (;;) {
+                const bool live = lit && !fin && !parked && st.mode == 3;
+                if (__ballot_sync(0xFFFFFFFFu, live) == 0u) break;
+                Hit h2;
+                float u2 = 0.f, v2 = 0.f;
+                bool b2;
+                intersect_lc<STATS>(scene, st, true, live, h2, u2, v2, b2, &cnt);
+                if (live) {
+                    if (!lc_light_unoccluded(st)) parked = true;
+                    else fin = path_advance<STATS, LC, true>(scene, st, h2, u2, v2, b2, w.nb_ech, c, &cnt);   // next light, or the scatter
+                }
+            }
+            bool alive = false;
+            if (lit) {
+                if (parked) {
+                    WF_ST(w.hit0 + slot, make_float4(st.P.x, st.P.y, st.P.z, st.ray.time));
+                    WF_ST(w.hit1 + slot, make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | obj)));
+                    WF_ST(w.hit2 + slot, make_float4(st.kd.x, st.kd.y, st.kd.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
+                    WF_ST(w.hit3 + slot, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
+                    WF_ST(w.hit4 + slot, make_float4(st.in_d.x, st.in_d.y, st.in_d.z, 0.f));
+                    WF_ST(w.park0 + slot, make_float4(st.color.x, st.color.y, st.color.z, u2f((uint32_t)st.light | ((uint32_t)(st.cl_n + 1) << 8))));
+                    for (int q4 = 0; q4 * 4 < st.cl_n; ++q4)
+                        WF_ST(w.park2 + (size_t)q4 * w.rec_stride + slot, make_float4(u2f(st.cl[4 * q4]), u2f(st.cl[4 * q4 + 1]), u2f(st.cl[4 * q4 + 2]), u2f(st.cl[4 * q4 + 3])));
+                    WF_ST(w.park1 + slot, make_float4(u2f(st.cm0), u2f(st.cm1), u2f(st.cm2), u2f(st.cm3)));
+                    WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
+                } else if (fin) {
+                    float *o = w.samples + 3ull * slot;
+                    o[0] = c.x; o[1] = c.y; o[2] = c.z;
+                } else {
+                    alive = true;
+                    WF_ST(w.ray0 + slot, make_float4(st.ray.o.x, st.ray.o.y, st.ray.o.z, st.ray.time));
+                    WF_ST(w.ray1 + slot, make_float4(st.ray.d.x, st.ray.d.y, st.ray.d.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
+                    WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
+                }
+            }
+            wf_stage_push(w.q_live_next, w.ctr + 6 * (w.level + 1) + 1, stage, fill, alive, slot);
+            wf_stage_push(w.q_park, w.ctr + 6 * w.level + 5, stage_park, fill_park, parked, slot);
+            continue;
+        }
+        if (valid) {
+            if (lit) {
                 const uint32_t kind = (uint32_t)h.type, obj = (uint32_t)h.obj;   // st.mat = {sph,sq,mesh}_mat[obj]
                 WF_ST(w.hit0 + slot, make_float4(st.P.x, st.P.y, st.P.z, st.ray.time));
                 WF_ST(w.hit1 + slot, make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | obj)));
@@ -497,7 +553,12 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
         }
         wf_stage_push(w.q_out, w.ctr + 6 * w.level + 3, stage, fill, lit, slot);
     }
-    wf_stage_flush(w.q_out, w.ctr + 6 * w.level + 3, stage, fill);
+    if (FUSE) {
+        wf_stage_flush(w.q_live_next, w.ctr + 6 * (w.level + 1) + 1, stage, fill);
+        wf_stage_flush(w.q_park, w.ctr + 6 * w.level + 5, stage_park, fill_park);
+    } else {
+        wf_stage_flush(w.q_out, w.ctr + 6 * w.level + 3, stage, fill);
+    }
     if (STATS) flush_counters(cnt, w.stats);
 }
 
@@ -1296,7 +1357,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     // variant: low byte = kernel (0 auto, 1 k_render_paths: one path per lane to completion,
     // 2 k_render_regen: ray-level state machine with path regeneration and warp-voted KD traversal);
     // bits 8..15 = regeneration threshold of kernel 2 (idle lanes needed before a refill; 0 = 16)
-    if (p->variant < 0 || (p->variant & 0xFF) > 6 || (p->variant >> 29)) return fail(RT_ERR_INVALID, "unknown kernel variant");
+    if (p->variant < 0 || (p->variant & 0xFF) > 6 || (p->variant >> 30)) return fail(RT_ERR_INVALID, "unknown kernel variant");
     // bits 16..19: CTAs per SM of kernel 3 — 0 auto, 1 = 4 (<= 128 registers), 2 = 6 (<= 80), 3 = 8 (<= 64, a few spills)
     int occ = (p->variant >> 16) & 0xF;
     if (occ == 0) occ = 3;   // 8 CTAs/SM beat 6 and 4 on every config (profiles/r01_notes.md)
@@ -1321,7 +1382,12 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     typedef void (*TraceKernel)(const DScene, const DCamera, const WfArgs);
     typedef void (*LightKernel)(const DScene, const WfArgs);
     const bool wf_lc = s->d.abvh_root >= 0;
-    TraceKernel wf_trace = want_stats ? (wf_lc ? k_wf_trace<true, true> : k_wf_trace<true, false>) : (wf_lc ? k_wf_trace<false, true> : k_wf_trace<false, false>);
+    // bit 29 of variant: fuse walk-and-classify into the trace kernel. Measured 30-40 % SLOWER on configs 2, 4 and 5
+    // (36.9 vs 26.2 ms, 110.8 vs 85.3, 98.9 vs 79.7: profiles/r01_notes.md) — one more confirmation that these kernels
+    // want small, single-phase code — so it is off unless asked for; kept because the tests cover it.
+    const bool wf_fuse = wf_lc && ((p->variant >> 29) & 1) != 0;
+    TraceKernel wf_trace = want_stats ? (wf_fuse ? k_wf_trace<true, true, true> : wf_lc ? k_wf_trace<true, true, false> : k_wf_trace<true, false, false>)
+                                      : (wf_fuse ? k_wf_trace<false, true, true> : wf_lc ? k_wf_trace<false, true, false> : k_wf_trace<false, false, false>);
     // light stage: one kernel (no masks to classify by) or walk/classify + sample (see k_wf_light)
     LightKernel wf_light = want_stats ? (wf_lc ? k_wf_light<true, true, 1> : k_wf_light<true, false, 0>) : (wf_lc ? k_wf_light<false, true, 1> : k_wf_light<false, false, 0>);
     LightKernel wf_light_b = want_stats ? k_wf_light<true, true, 2> : k_wf_light<false, true, 2>;
@@ -1382,6 +1448,20 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
             unsigned int *q_live = s->wf_q, *q_hit = s->wf_q + cap;
             for (int level = 0; level < p->max_bounces; ++level) {
                 w.level = level;
+                if (wf_fuse) {
+                    // two live queues alternate by level: this level's kernels read one and append to the other
+                    unsigned int *q_this = (level & 1) ? q_hit : q_live, *q_next = (level & 1) ? q_live : q_hit;
+                    w.q_in = q_this; w.q_live_next = q_next; w.q_out = q_next;
+                    wf_trace<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_t, (batches + 3) / 4), 128, 0, st>>>(s->d, cam, w);
+                    RT_CUDA(cudaGetLastError());
+                    ++launches;
+                    if (s->d.n_lights > 0) {
+                        wf_light_b<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
+                        RT_CUDA(cudaGetLastError());
+                        ++launches;
+                    }
+                    continue;
+                }
                 w.q_in = q_live; w.q_out = q_hit;
                 wf_trace<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_t, (batches + 3) / 4), 128, 0, st>>>(s->d, cam, w);
                 RT_CUDA(cudaGetLastError());

@@ -171,7 +171,8 @@ typedef struct RtRenderParams {
                                     3 the same over the exact culling hierarchies; 4 warp-voted walk of those;
                                     5 occluder candidates per (hit, light) + gated traversal / shadow-sample
                                     phases. Tuning bits: 8..15 regeneration threshold, 16..19 CTAs per SM,
-                                    20..27 traversal threshold of kernel 5, 28 = no separate camera-ray pass.
+                                    20..27 traversal threshold of kernel 5, 28 = no separate camera-ray pass,
+                                    29 = wavefront with walk-and-classify fused into the trace kernel (slower; default: own kernel).
                                     All variants give identical bits (tests/test_gpu_parity.py).
                                     Environment HAI719_CHUNK_LOG2=16..26 (read per call) overrides the number of
                                     paths rendered per chunk (default 2^25 wavefront, 2^24 otherwise): a memory /

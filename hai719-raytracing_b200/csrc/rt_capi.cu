@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScen
 // appended to the next queue with one warp-aggregated atomicAdd (__ballot_sync/__popc ranks), so the
 // host never needs to know how many paths are alive. Path state between kernels lives in HBM as
 // float4 SoA records (one 128-bit access per field and lane): 40 B ray + 88 B hit + 48 B per bounce.
+#define WF_NCTR 8   /* counters per bounce level: trace head/count, light head/count, parked head/count, overflow head/count */
 struct WfArgs {
     unsigned int n_paths;              // paths of this chunk (slots 0 .. n_paths-1)
     unsigned int max_grab;             // batches a warp may fetch with one atomic (see wf_next_batch)
@@ -331,10 +332,12 @@ struct WfArgs {
     unsigned int *q_in, *q_out;        // trace: q_in = live paths (level > 0), q_out = paths with a hit; light: the reverse
     unsigned int *q_live_next;         // fused trace kernel: the queue of the next level's live rays
     unsigned int *q_park;              // light phase A -> phase B: hits whose light needs its shadow samples traced
+    unsigned int *q_over;              // ... those whose candidate-triangle list overflowed: their samples walk the mesh hierarchies,
+    int which_park;                    //     so they get warps of their own (phase B runs once per queue: 0 = q_park, 1 = q_over)
     float4 *park0, *park1;             // ... and what phase B needs besides the hit record: {colour so far, light | (cl_n + 1) << 8}, {cm0..cm3}
     float4 *park2;                     // candidate triangles, RT_LC_MAXC / 4 float4 planes of rec_stride entries
-    unsigned int *ctr;                 // per level 6 counters: [6L] trace head, [6L+1] trace count, [6L+2] light head, [6L+3] light count,
-                                       //                       [6L+4] shadow head, [6L+5] shadow count
+    unsigned int *ctr;                 // per level WF_NCTR counters: [0] trace head, [1] trace count, [2] light head, [3] light count,
+                                       //                             [4] parked head, [5] parked count, [6] overflow head, [7] overflow count
     float *samples;
     unsigned long long *stats;
 };
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int count = w.level == 0 ? w.n_paths : w.ctr[6 * w.level + 1];
+    const unsigned int count = w.level == 0 ? w.n_paths : w.ctr[WF_NCTR * w.level + 1];
     __shared__ unsigned int stage_all[4][WF_STAGE_CAP];
     __shared__ unsigned int stage_park_all[FUSE ? 4 : 1][FUSE ? WF_STAGE_CAP : 1];
     unsigned int *stage = stage_all[threadIdx.x >> 5];
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
     WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
     for (;;) {
         unsigned int base;
-        if (!wf_next_batch(w.ctr + 6 * w.level, count, w.max_grab, fetch, base)) break;
+        if (!wf_next_batch(w.ctr + WF_NCTR * w.level, count, w.max_grab, fetch, base)) break;
         const unsigned int i = base + lane;
         const bool valid = i < count;
         if (RT_WF_PREFETCH && w.level > 0 && fetch.cur < fetch.end && fetch.cur + lane < count) {   // next batch of this warp's grab
@@ -536,8 +539,8 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
                     WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
                 }
             }
-            wf_stage_push(w.q_live_next, w.ctr + 6 * (w.level + 1) + 1, stage, fill, alive, slot);
-            wf_stage_push(w.q_park, w.ctr + 6 * w.level + 5, stage_park, fill_park, parked, slot);
+            wf_stage_push(w.q_live_next, w.ctr + WF_NCTR * (w.level + 1) + 1, stage, fill, alive, slot);
+            wf_stage_push(w.q_park, w.ctr + WF_NCTR * w.level + 5, stage_park, fill_park, parked, slot);
             continue;
         }
         if (valid) {
@@ -551,13 +554,13 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
                 WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
             }
         }
-        wf_stage_push(w.q_out, w.ctr + 6 * w.level + 3, stage, fill, lit, slot);
+        wf_stage_push(w.q_out, w.ctr + WF_NCTR * w.level + 3, stage, fill, lit, slot);
     }
     if (FUSE) {
-        wf_stage_flush(w.q_live_next, w.ctr + 6 * (w.level + 1) + 1, stage, fill);
-        wf_stage_flush(w.q_park, w.ctr + 6 * w.level + 5, stage_park, fill_park);
+        wf_stage_flush(w.q_live_next, w.ctr + WF_NCTR * (w.level + 1) + 1, stage, fill);
+        wf_stage_flush(w.q_park, w.ctr + WF_NCTR * w.level + 5, stage_park, fill_park);
     } else {
-        wf_stage_flush(w.q_out, w.ctr + 6 * w.level + 3, stage, fill);
+        wf_stage_flush(w.q_out, w.ctr + WF_NCTR * w.level + 3, stage, fill);
     }
     if (STATS) flush_counters(cnt, w.stats);
 }
@@ -576,14 +579,16 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int count = w.ctr[6 * w.level + (PHASE == 2 ? 5 : 3)];
-    unsigned int *const head = w.ctr + 6 * w.level + (PHASE == 2 ? 4 : 2);
-    const unsigned int *const q_in = PHASE == 2 ? w.q_park : w.q_in;
+    const unsigned int count = w.ctr[WF_NCTR * w.level + (PHASE == 2 ? 5 + 2 * w.which_park : 3)];
+    unsigned int *const head = w.ctr + WF_NCTR * w.level + (PHASE == 2 ? 4 + 2 * w.which_park : 2);
+    const unsigned int *const q_in = PHASE == 2 ? (w.which_park ? w.q_over : w.q_park) : w.q_in;
     __shared__ unsigned int stage_all[4][WF_STAGE_CAP];
     __shared__ unsigned int stage_park_all[PHASE == 1 ? 4 : 1][PHASE == 1 ? WF_STAGE_CAP : 1];
+    __shared__ unsigned int stage_over_all[PHASE == 1 ? 4 : 1][PHASE == 1 ? WF_STAGE_CAP : 1];
     unsigned int *stage = stage_all[threadIdx.x >> 5];
     unsigned int *stage_park = stage_park_all[PHASE == 1 ? (threadIdx.x >> 5) : 0];
-    unsigned int fill = 0u, fill_park = 0u;
+    unsigned int *stage_over = stage_over_all[PHASE == 1 ? (threadIdx.x >> 5) : 0];
+    unsigned int fill = 0u, fill_park = 0u, fill_over = 0u;
     WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
     for (;;) {
         unsigned int base;
@@ -670,11 +675,17 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
                 WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
             }
         }
-        wf_stage_push(w.q_out, w.ctr + 6 * (w.level + 1) + 1, stage, fill, alive, slot);
-        if (PHASE == 1) wf_stage_push(w.q_park, w.ctr + 6 * w.level + 5, stage_park, fill_park, parked, slot);
+        wf_stage_push(w.q_out, w.ctr + WF_NCTR * (w.level + 1) + 1, stage, fill, alive, slot);
+        if (PHASE == 1) {
+            wf_stage_push(w.q_park, w.ctr + WF_NCTR * w.level + 5, stage_park, fill_park, parked && st.cl_n >= 0, slot);
+            wf_stage_push(w.q_over, w.ctr + WF_NCTR * w.level + 7, stage_over, fill_over, parked && st.cl_n < 0, slot);
+        }
     }
-    wf_stage_flush(w.q_out, w.ctr + 6 * (w.level + 1) + 1, stage, fill);
-    if (PHASE == 1) wf_stage_flush(w.q_park, w.ctr + 6 * w.level + 5, stage_park, fill_park);
+    wf_stage_flush(w.q_out, w.ctr + WF_NCTR * (w.level + 1) + 1, stage, fill);
+    if (PHASE == 1) {
+        wf_stage_flush(w.q_park, w.ctr + WF_NCTR * w.level + 5, stage_park, fill_park);
+        wf_stage_flush(w.q_over, w.ctr + WF_NCTR * w.level + 7, stage_over, fill_over);
+    }
     if (STATS) flush_counters(cnt, w.stats);
 }
 
@@ -1018,9 +1029,9 @@ int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
     paths = std::max(paths, s->wf_cap); max_bounces = std::max(max_bounces, s->wf_bounces);
     RT_CUDA(cudaMalloc((void **)&s->wf_f4, (9 + RT_LC_MAXC / 4) * paths * sizeof(float4)));
     RT_CUDA(cudaMalloc((void **)&s->wf_rng, paths * sizeof(uint2)));
-    RT_CUDA(cudaMalloc((void **)&s->wf_q, 3 * paths * sizeof(unsigned int)));
+    RT_CUDA(cudaMalloc((void **)&s->wf_q, 4 * paths * sizeof(unsigned int)));
     RT_CUDA(cudaMalloc((void **)&s->wf_rec, 3 * (size_t)std::max(1, max_bounces) * paths * sizeof(float4)));
-    if (!s->wf_ctr) RT_CUDA(cudaMalloc((void **)&s->wf_ctr, 6 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int)));
+    if (!s->wf_ctr) RT_CUDA(cudaMalloc((void **)&s->wf_ctr, WF_NCTR * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int)));
     s->wf_cap = paths; s->wf_bounces = max_bounces;
     return RT_OK;
 }
@@ -1441,10 +1452,10 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
             w.cam_rays = s->cam_rays; w.cam_keys = s->cam_keys;
             w.ray0 = s->wf_f4; w.ray1 = s->wf_f4 + cap; w.hit0 = s->wf_f4 + 2 * cap; w.hit1 = s->wf_f4 + 3 * cap; w.hit2 = s->wf_f4 + 4 * cap;
             w.hit3 = s->wf_f4 + 5 * cap; w.hit4 = s->wf_f4 + 6 * cap; w.park0 = s->wf_f4 + 7 * cap; w.park1 = s->wf_f4 + 8 * cap; w.park2 = s->wf_f4 + 9 * cap;
-            w.q_park = s->wf_q + 2 * cap;
+            w.q_park = s->wf_q + 2 * cap; w.q_over = s->wf_q + 3 * cap; w.which_park = 0;
             w.rng = s->wf_rng; w.rec = s->wf_rec; w.rec_stride = cap;
             w.ctr = s->wf_ctr; w.samples = s->samples; w.stats = a.stats;
-            RT_CUDA(cudaMemsetAsync(s->wf_ctr, 0, 6 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
+            RT_CUDA(cudaMemsetAsync(s->wf_ctr, 0, WF_NCTR * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
             unsigned int *q_live = s->wf_q, *q_hit = s->wf_q + cap;
             for (int level = 0; level < p->max_bounces; ++level) {
                 w.level = level;
@@ -1470,9 +1481,17 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
                 RT_CUDA(cudaGetLastError());
                 launches += 2;
                 if (wf_lc && s->d.n_lights > 0) {
+                    w.which_park = 0;
                     wf_light_b<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
                     RT_CUDA(cudaGetLastError());
                     ++launches;
+                    if (s->d.n_meshes > 0) {   // lights whose candidate-triangle list overflowed, in warps of their own
+                        w.which_park = 1;
+                        wf_light_b<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
+                        RT_CUDA(cudaGetLastError());
+                        ++launches;
+                        w.which_park = 0;
+                    }
                 }
             }
         } else {

@@ -113,6 +113,9 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #ifndef RT_OPT_WW_LC
 #define RT_OPT_WW_LC 1      /* analytic culling hierarchy (variants 5, 6): while-while traversal */
 #endif
+#ifndef RT_OPT_MESH_MERGED
+#define RT_OPT_MESH_MERGED 0 /* all meshes in one per-lane walk loop instead of one loop per mesh: measured slower on configs 3 and 5 */
+#endif
 
 namespace rt {
 
@@ -616,6 +619,66 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
     return true;
 }
 
+// All meshes of the scene in ONE per-lane loop (closest-hit and shadow rays): a lane that has finished mesh i goes
+// straight on to mesh i+1 while its neighbours are still inside mesh i, and both execute the same box-test and
+// triangle-test code. With one loop per mesh the lanes of a warp met again after every mesh: the warp paid the SUM over
+// meshes of the slowest lane instead of the slowest lane's sum (pond scene: 8 of 32 lanes active in the walk,
+// profiles/r01_notes.md). Same candidates, same per-triangle routine, same acceptance rules and draw order as
+// mesh_closest_bvh called mesh after mesh.
+template <bool STATS>
+RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rng, Hit &h, bool &blocked, bool &done, Counters *cnt) {
+    if (done || s.n_meshes <= 0) return;
+    const uint32_t NONE = 0xFFFFFFFFu;
+    const int DONE = 0x7FFFFFFF;
+    Inv32 iv; iv.x = safe_inv(ray.d.x); iv.y = safe_inv(ray.d.y); iv.z = safe_inv(ray.d.z);
+    int stack[64];
+    int sp = 0, mi = 0;
+    const DMesh *m = s.meshes;
+    uint32_t k = m->always_first, kend = m->always_first + m->always_count;   // the always-tested triangles come first, like a leaf
+    int node = m->bvh_root >= 0 ? m->bvh_root : DONE;
+    float best_t = h.t;
+    uint32_t best_ref = NONE;
+    if (STATS) cnt->mesh++;
+    for (;;) {
+        if (k < kend) {
+            bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+            ++k;
+        } else if (node == DONE) {
+            // mesh mi is finished: Scene-level acceptance (Scene.h:221-228 closest, 248-253 shadow)
+            if (best_ref != NONE && best_t < h.t && best_t > RT_EPSF) {
+                if (mode == 0) { h.type = 3; h.obj = mi; h.t = best_t; h.ref = best_ref; }
+                else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.mesh_transparency + mi)) { blocked = true; done = true; break; } }
+            }
+            if (++mi >= s.n_meshes) break;
+            m = s.meshes + mi;
+            if (STATS) cnt->mesh++;
+            k = m->always_first; kend = k + m->always_count;
+            node = m->bvh_root >= 0 ? m->bvh_root : DONE;
+            sp = 0;
+            best_t = h.t; best_ref = NONE;
+        } else if (node >= 0) {
+            const float4 n0 = RT_LDG(s.bvh_nodes + 4 * node), n1 = RT_LDG(s.bvh_nodes + 4 * node + 1),
+                         n2 = RT_LDG(s.bvh_nodes + 4 * node + 2), n3 = RT_LDG(s.bvh_nodes + 4 * node + 3);
+            if (STATS) cnt->node++;
+            float d0, d1;
+            const bool h0 = bvh_box(ray, iv, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, best_t, d0);
+            const bool h1 = bvh_box(ray, iv, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, best_t, d1);
+            const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
+            if (h0 && h1) {
+                const bool swap = d1 < d0;
+                node = swap ? c1 : c0;
+                stack[sp++] = swap ? c0 : c1;
+            } else if (h0) node = c0;
+            else if (h1) node = c1;
+            else node = sp > 0 ? stack[--sp] : DONE;
+        } else {
+            const uint32_t code = (uint32_t)(-(node + 1));
+            k = code >> 3; kend = k + (code & 7u);
+            node = sp > 0 ? stack[--sp] : DONE;
+        }
+    }
+}
+
 // ---- analytic primitives through their culling hierarchy (variant 3) ----------------------------
 // Visits every sphere/square whose padded, motion-swept box the ray can touch within [0, limit] and
 // calls f(seq) for it (seq: sphere i -> i, square j -> n_spheres + j). `limit` is re-read after every
@@ -1055,7 +1118,9 @@ RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_ligh
             }
         }
     }
-    if (ACCEL) {
+    if (ACCEL && RT_OPT_MESH_MERGED) {
+        meshes_walk_merged<STATS>(s, ray, mode, rng, h, blocked, done, cnt);
+    } else if (ACCEL) {
         // variant 3: per-mesh exact culling traversal (mesh_closest_bvh), same acceptance rules
         for (int i = 0; i < s.n_meshes; ++i) {
             if (done) break;
@@ -1643,6 +1708,9 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
         }
         return;
     }
+#if RT_OPT_MESH_MERGED
+    meshes_walk_merged<STATS>(s, ray, mode, st.rng, h, blocked, done, cnt);
+#else
     for (int i = 0; i < s.n_meshes; ++i) {
         if (done) break;
         if (STATS) cnt->mesh++;
@@ -1652,6 +1720,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
             else { if (STATS) cnt->rnd++; if (st.rng.next() > RT_LDG(s.mesh_transparency + i)) { blocked = true; done = true; } }
         }
     }
+#endif
 }
 
 RT_HD void path_begin(PathState &st, const Ray &primary, const Rng &rng, uint32_t path, int max_bounces) {

@@ -319,6 +319,8 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScen
 // appended to the next queue with one warp-aggregated atomicAdd (__ballot_sync/__popc ranks), so the
 // host never needs to know how many paths are alive. Path state between kernels lives in HBM as
 // float4 SoA records (one 128-bit access per field and lane): 40 B ray + 88 B hit + 48 B per bounce.
+#define WF_HIT_E 0x08000000u   /* hit record flags in the code word of hit1.w: emission stored / incoming direction stored */
+#define WF_HIT_D 0x04000000u
 #define WF_NCTR 8   /* counters per bounce level: trace head/count, light head/count, parked head/count, overflow head/count */
 struct WfArgs {
     unsigned int n_paths;              // paths of this chunk (slots 0 .. n_paths-1)
@@ -520,10 +522,12 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
             if (lit) {
                 if (parked) {
                     WF_ST(w.hit0 + slot, make_float4(st.P.x, st.P.y, st.P.z, st.ray.time));
-                    WF_ST(w.hit1 + slot, make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | obj)));
+                    const uint32_t has_e = (st.e.x != 0.f || st.e.y != 0.f || st.e.z != 0.f) ? WF_HIT_E : 0u;
+                    const uint32_t has_d = st.mat->type != 0 ? WF_HIT_D : 0u;
+                    WF_ST(w.hit1 + slot, make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | has_e | has_d | obj)));
                     WF_ST(w.hit2 + slot, make_float4(st.kd.x, st.kd.y, st.kd.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
-                    WF_ST(w.hit3 + slot, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
-                    WF_ST(w.hit4 + slot, make_float4(st.in_d.x, st.in_d.y, st.in_d.z, 0.f));
+                    if (has_e) WF_ST(w.hit3 + slot, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
+                    if (has_d) WF_ST(w.hit4 + slot, make_float4(st.in_d.x, st.in_d.y, st.in_d.z, 0.f));
                     WF_ST(w.park0 + slot, make_float4(st.color.x, st.color.y, st.color.z, u2f((uint32_t)st.light | ((uint32_t)(st.cl_n + 1) << 8))));
                     for (int q4 = 0; q4 * 4 < st.cl_n; ++q4)
                         WF_ST(w.park2 + (size_t)q4 * w.rec_stride + slot, make_float4(u2f(st.cl[4 * q4]), u2f(st.cl[4 * q4 + 1]), u2f(st.cl[4 * q4 + 2]), u2f(st.cl[4 * q4 + 3])));
@@ -547,10 +551,14 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
             if (lit) {
                 const uint32_t kind = (uint32_t)h.type, obj = (uint32_t)h.obj;   // st.mat = {sph,sq,mesh}_mat[obj]
                 WF_ST(w.hit0 + slot, make_float4(st.P.x, st.P.y, st.P.z, st.ray.time));
-                WF_ST(w.hit1 + slot, make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | obj)));
+                // emission and incoming direction travel only when they matter (an emitter; a glass or mirror scatter):
+                // the hit record is the largest item of the wavefront's HBM traffic
+                const uint32_t has_e = (st.e.x != 0.f || st.e.y != 0.f || st.e.z != 0.f) ? WF_HIT_E : 0u;
+                const uint32_t has_d = st.mat->type != 0 ? WF_HIT_D : 0u;
+                WF_ST(w.hit1 + slot, make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | has_e | has_d | obj)));
                 WF_ST(w.hit2 + slot, make_float4(st.kd.x, st.kd.y, st.kd.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
-                WF_ST(w.hit3 + slot, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
-                WF_ST(w.hit4 + slot, make_float4(st.in_d.x, st.in_d.y, st.in_d.z, 0.f));
+                if (has_e) WF_ST(w.hit3 + slot, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
+                if (has_d) WF_ST(w.hit4 + slot, make_float4(st.in_d.x, st.in_d.y, st.in_d.z, 0.f));
                 WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
             }
         }
@@ -612,11 +620,13 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
         V3 c = v3(0.f);
         if (valid) {
             slot = WF_LD(q_in + i);
-            const float4 h0 = WF_LD(w.hit0 + slot), h1 = WF_LD(w.hit1 + slot), h2 = WF_LD(w.hit2 + slot), h3 = WF_LD(w.hit3 + slot), h4 = WF_LD(w.hit4 + slot);
+            const float4 h0 = WF_LD(w.hit0 + slot), h1 = WF_LD(w.hit1 + slot), h2 = WF_LD(w.hit2 + slot);
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 h3 = (f2u(h1.w) & WF_HIT_E) ? WF_LD(w.hit3 + slot) : zero4, h4 = (f2u(h1.w) & WF_HIT_D) ? WF_LD(w.hit4 + slot) : zero4;
             const uint2 g = WF_LD(w.rng + slot);
             st.P = v3(h0.x, h0.y, h0.z); st.ray.time = h0.w;
             st.n = v3(h1.x, h1.y, h1.z);
-            const uint32_t code = f2u(h1.w), kind = code >> 28, obj = code & 0x0FFFFFFFu;
+            const uint32_t code = f2u(h1.w), kind = code >> 28, obj = code & 0x03FFFFFFu;
             st.mat = kind == 3u ? scene.mesh_mat + obj : (kind == 2u ? scene.sq_mat + obj : scene.sph_mat + obj);
             st.kd = v3(h2.x, h2.y, h2.z);
             st.N = (int)(f2u(h2.w) & 0xFFu); st.depth = (int)(f2u(h2.w) >> 8);

@@ -117,10 +117,13 @@ class RtStats(C.Structure):
 RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy", "rt_release_cached_memory", "rt_scene_update_analytic",
               "rt_scene_device_bytes", "rt_render_pixel_count", "rt_tile_layout", "rt_render", "rt_render_rgb8", "rt_quantize_device",
               "rt_render_device", "rt_untile_device",
+              "rt_accum_create", "rt_accum_destroy", "rt_accum_reset", "rt_accum_add", "rt_accum_samples", "rt_accum_read",
               "rt_trace_primary", "rt_trace_rays", "rt_shade_rays", "rt_measure_fp32_peak"]
 HOST_SYMBOLS = ["hai_last_error", "hai_scene_new", "hai_scene_free", "hai_scene_setup", "hai_scene_dump",
                 "hai_scene_flatten", "hai_scene_kd_stats", "hai_scene_counts", "hai_default_camera", "hai_render",
-                "hai_scene_device", "hai_scene_invalidate_device", "hai_scene_move_sphere", "hai_scene_update_device", "hai_scene_load_file", "hai_ray_trace_from_camera", "hai_ray_trace_from_camera_rgb8"]
+                "hai_scene_device", "hai_scene_invalidate_device", "hai_scene_move_sphere", "hai_scene_update_device", "hai_scene_load_file", "hai_ray_trace_from_camera", "hai_ray_trace_from_camera_rgb8",
+                "hai_preview_new", "hai_preview_free", "hai_preview_mouse", "hai_preview_motion", "hai_preview_resize", "hai_preview_invalidate",
+                "hai_preview_pass", "hai_preview_frame", "hai_preview_camera"]
 
 if not (os.path.exists(LIB_RT) and os.path.exists(LIB_HOST)):
     raise ImportError("hai719-raytracing_b200: native libraries not built (%s). Run `make -C %s` or "
@@ -152,6 +155,13 @@ rt.rt_shade_rays.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c
                              C.c_void_p]
 
 rt.rt_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+rt.rt_accum_create.argtypes = [C.c_void_p, C.POINTER(RtRenderParams), C.POINTER(C.c_void_p)]
+rt.rt_accum_destroy.argtypes = [C.c_void_p]
+rt.rt_accum_reset.argtypes = [C.c_void_p]
+rt.rt_accum_add.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_int32, C.POINTER(RtStats)]
+rt.rt_accum_samples.restype = C.c_uint32
+rt.rt_accum_samples.argtypes = [C.c_void_p]
+rt.rt_accum_read.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
 host.hai_last_error.restype = C.c_char_p
 host.hai_scene_new.restype = C.c_void_p
@@ -173,6 +183,16 @@ host.hai_scene_invalidate_device.argtypes = [C.c_void_p]
 host.hai_ray_trace_from_camera.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
                                            C.c_void_p]
 host.hai_scene_load_file.argtypes = [C.c_void_p, C.c_char_p]
+host.hai_preview_new.restype = C.c_void_p
+host.hai_preview_new.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32]
+host.hai_preview_free.argtypes = [C.c_void_p]
+host.hai_preview_mouse.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+host.hai_preview_motion.argtypes = [C.c_void_p, C.c_int, C.c_int]
+host.hai_preview_resize.argtypes = [C.c_void_p, C.c_int, C.c_int]
+host.hai_preview_invalidate.argtypes = [C.c_void_p]
+host.hai_preview_pass.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32)]
+host.hai_preview_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+host.hai_preview_camera.argtypes = [C.c_void_p, C.POINTER(RtCamera)]
 host.hai_scene_move_sphere.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
 host.hai_scene_update_device.argtypes = [C.c_void_p]
 host.hai_ray_trace_from_camera_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
@@ -366,3 +386,107 @@ class Scene:
         _host_check(host.hai_ray_trace_from_camera(self.h, device, width, height, nsamples, seed,
                                                    ppm_path.encode() if ppm_path else None, out.ctypes.data))
         return out
+
+    def accumulator(self, width, height, seed=0, device=0, **kw):
+        """rt_accum_*: progressive accumulation over this scene's device copy (keep the Scene alive while it is used)."""
+        return Accumulator(self, width, height, seed=seed, device=device, **kw)
+
+    def preview(self, width, height, seed=0, device=0):
+        """host/Preview.h: the reference's mouse handlers + progressive passes (keep the Scene alive and unchanged)."""
+        return Preview(self, width, height, seed=seed, device=device)
+
+
+class Accumulator:
+    """Progressive accumulation through the C ABI: add(spp) traces spp MORE samples per pixel; read()
+    returns the current mean, bit-identical to one render at the total sample count."""
+
+    def __init__(self, scene, width, height, seed=0, device=0, **kw):
+        self.scene = scene
+        self.params = render_params(width, height, 1, seed=seed, **kw)
+        p = self.params
+        x0, y0, x1, y1 = (p.x0, p.y0, p.x1, p.y1) if (p.x0 | p.y0 | p.x1 | p.y1) else (0, 0, width, height)
+        self.shape = (y1 - y0, x1 - x0, 3)
+        self.h = C.c_void_p()
+        _rt_check(rt.rt_accum_create(scene.device_handle(device), C.byref(p), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            rt.rt_accum_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _rt_check(rt.rt_accum_reset(self.h))
+
+    @property
+    def samples(self):
+        return int(rt.rt_accum_samples(self.h))
+
+    def add(self, spp, camera=None, stats=False):
+        cam = camera or default_camera(self.params.width, self.params.height)
+        st = RtStats()
+        _rt_check(rt.rt_accum_add(self.h, C.byref(cam), spp, C.byref(st)))
+        return st.as_dict() if stats else self.samples
+
+    def read(self):
+        gam = np.zeros(self.shape, np.float32)
+        lin = np.zeros(self.shape, np.float32)
+        rgb8 = np.zeros(self.shape, np.uint8)
+        _rt_check(rt.rt_accum_read(self.h, gam.ctypes.data, lin.ctypes.data, rgb8.ctypes.data))
+        return {"gamma": gam, "linear": lin, "rgb8": rgb8}
+
+
+class Preview:
+    """host/Preview.h through its C wrappers. Buttons: 0 left (rotate), 1 middle (zoom), 2 right (move); state 0 down, 1 up."""
+
+    def __init__(self, scene, width, height, seed=0, device=0):
+        self.scene = scene
+        self.width, self.height = width, height
+        self.h = host.hai_preview_new(scene.h, device, width, height, seed)
+        if not self.h:
+            raise RtError(-1, host.hai_last_error().decode(errors="replace"))
+
+    def close(self):
+        if self.h:
+            host.hai_preview_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def mouse(self, button, state, x, y):
+        _host_check(host.hai_preview_mouse(self.h, button, state, x, y))
+
+    def motion(self, x, y):
+        _host_check(host.hai_preview_motion(self.h, x, y))
+
+    def resize(self, width, height):
+        _host_check(host.hai_preview_resize(self.h, width, height))
+        self.width, self.height = width, height
+
+    def invalidate(self):
+        _host_check(host.hai_preview_invalidate(self.h))
+
+    def render_pass(self, spp=1):
+        n = C.c_uint32()
+        _host_check(host.hai_preview_pass(self.h, spp, C.byref(n)))
+        return n.value
+
+    def camera(self):
+        cam = RtCamera()
+        _host_check(host.hai_preview_camera(self.h, C.byref(cam)))
+        return cam
+
+    def frame(self):
+        rgb8 = np.zeros((self.height, self.width, 3), np.uint8)
+        gam = np.zeros((self.height, self.width, 3), np.float32)
+        _host_check(host.hai_preview_frame(self.h, rgb8.ctypes.data, gam.ctypes.data))
+        return {"rgb8": rgb8, "gamma": gam}

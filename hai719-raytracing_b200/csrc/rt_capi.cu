@@ -67,6 +67,7 @@ struct RenderArgs {
     int t_min;                          // variant 5: run a traversal step once at least this many lanes wait for one
     const float4 *cam_rays;             // k_camera_rays output per path {dir.xyz, time}, or null: generate in the render kernel
     const unsigned int *cam_keys;       // ... and the key of the path's random stream (3 draws already taken)
+    unsigned int sample_base;           // index of this call's first sample of every pixel (progressive accumulation, else 0)
 };
 
 // packed pixel index -> (x, y) via the tile prefix array
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(128, 4) k_render_paths(const DScene scene, con
             int x, y;
             packed_to_xy(a, lp, x, y);
             Rng rng;
-            rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, smp);
+            rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, a.sample_base + smp);
             if (STATS) cnt.rnd += 3;
             const Ray ray = primary_ray(cam, x, y, a.width, a.height, rng);
             const V3 c = trace_path<STATS>(scene, ray, rng, a.max_bounces, a.nb_ech, &cnt);
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256) k_camera_rays(const DCamera cam, const Re
     const unsigned int packed = __ldg(xy + p / (unsigned int)a.spp);
     const int x = (int)(packed & 0xFFFFu), y = (int)(packed >> 16);
     Rng rng;
-    rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, smp);
+    rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, a.sample_base + smp);
     const Ray ray = primary_ray_inline(cam, x, y, a.width, a.height, rng);
     rays[p] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.time);
     keys[p] = rng.key;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScen
                     const unsigned int smp = (unsigned int)(p % (unsigned int)a.spp);
                     int x, y;
                     packed_to_xy(a, lp, x, y);
-                    rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, smp);
+                    rng.init(a.seed, (unsigned int)x + (unsigned int)y * (unsigned int)a.width, a.sample_base + smp);
                     ray = primary_ray(cam, x, y, a.width, a.height, rng);
                 }
                 path_begin(st, ray, rng, (uint32_t)p, a.max_bounces);
@@ -700,15 +701,20 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
 }
 
 // image[pixel] = (sum of its samples, in sample order) / nsamples ; then gamma
+// Progressive accumulation (rt_accum_add): `sum` holds each pixel's running sum over the `prior` samples of earlier
+// passes; this pass continues THAT sum with its own samples in order, stores it back and divides by prior + spp, so
+// the float additions are the very sequence a single render of prior + spp samples performs (main.cpp:188-195).
 __global__ void k_resolve(const float *samples, unsigned long long pixel_begin, unsigned int n_pixels, int spp,
-                          float *linear_out, float *gamma_out) {
+                          float *linear_out, float *gamma_out, float *sum, unsigned int prior) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pixels) return;
     const float *s = samples + 3ull * i * (unsigned int)spp;
-    V3 acc = v3(0.f);
-    for (int k = 0; k < spp; ++k) acc = acc + v3(s[3 * k], s[3 * k + 1], s[3 * k + 2]);
-    acc = acc / (float)(unsigned int)spp;
     const unsigned long long o = 3ull * (pixel_begin + i);
+    V3 acc = v3(0.f);
+    if (sum && prior) acc = v3(sum[o], sum[o + 1], sum[o + 2]);
+    for (int k = 0; k < spp; ++k) acc = acc + v3(s[3 * k], s[3 * k + 1], s[3 * k + 2]);
+    if (sum) { sum[o] = acc.x; sum[o + 1] = acc.y; sum[o + 2] = acc.z; }
+    acc = acc / (float)(prior + (unsigned int)spp);
     if (linear_out) { linear_out[o] = acc.x; linear_out[o + 1] = acc.y; linear_out[o + 2] = acc.z; }
     if (gamma_out) { gamma_out[o] = gamma_channel(acc.x); gamma_out[o + 1] = gamma_channel(acc.y); gamma_out[o + 2] = gamma_channel(acc.z); }
 }
@@ -1337,8 +1343,10 @@ int64_t rt_tile_layout(const RtRenderParams *p, int32_t *out, int64_t cap) {
     return (int64_t)tiles.size();
 }
 
-int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p, float *d_gamma, float *d_linear,
-                     void *cuda_stream, RtStats *stats) {
+// The render behind rt_render_device (sample_base 0, no running sum) and rt_accum_add (samples sample_base ..
+// sample_base + spp - 1 of every pixel, continuing the per-pixel sums in d_sum).
+static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRenderParams *p, float *d_gamma, float *d_linear,
+                              void *cuda_stream, RtStats *stats, unsigned int sample_base, float *d_sum) {
     if (!s || !camera || !p) return fail(RT_ERR_INVALID, "null argument");
     Rect r;
     int rc = resolve_rect(*p, r);
@@ -1427,6 +1435,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     // any lane wants to; the lanes then catch up with the ones sampling shadows and the warp falls into cohorts by itself
     a.t_min = ((p->variant >> 20) & 0xFF) ? std::min(32, (p->variant >> 20) & 0xFF) : 1;
     a.seed = p->seed; a.samples = s->samples; a.work_counter = s->counters; a.stats = want_stats ? s->counters + 1 : nullptr;
+    a.sample_base = sample_base;
     uint32_t launches = 0;
     RT_CUDA(cudaMemsetAsync(s->counters, 0, 16 * sizeof(unsigned long long), st));
     if (stats) RT_CUDA(cudaEventRecord(s->ev0, st));
@@ -1509,7 +1518,7 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
             RT_CUDA(cudaGetLastError());
             ++launches;
         }
-        k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(s->samples, pb, (unsigned int)np, p->spp, d_linear, d_gamma);
+        k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(s->samples, pb, (unsigned int)np, p->spp, d_linear, d_gamma, d_sum, sample_base);
         RT_CUDA(cudaGetLastError());
         ++launches;
     }
@@ -1530,6 +1539,11 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
         }
     }
     return RT_OK;
+}
+
+int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p, float *d_gamma, float *d_linear,
+                     void *cuda_stream, RtStats *stats) {
+    return render_device_impl(s, camera, p, d_gamma, d_linear, cuda_stream, stats, 0u, nullptr);
 }
 
 namespace {
@@ -1684,6 +1698,134 @@ int rt_render_rgb8(RtScene *s, const RtCamera *camera, const RtRenderParams *p, 
     if ((rc = rt_untile_device(&q, d_packed, &off0, d_image, s->device, nullptr))) return rc;
     if ((rc = rt_quantize_device(d_image, rect_px * 3, d_bytes, s->device, nullptr))) return rc;
     RT_CUDA(cudaMemcpy(rgb8, d_bytes, rect_px * 3, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+// ---- progressive accumulation -----------------------------------------------------
+// The reference renders a frame in one go from a key press (main.cpp:200-263, 321-326) and shows nothing in between.
+// An accumulator keeps each pixel's running sample sum on the device; every rt_accum_add() traces `spp` MORE samples per
+// pixel (sample indices continue where the last pass stopped, so the random streams are those of one long render) and
+// refreshes the mean. After passes of s1, s2, ... samples the frame is bit-identical to ONE render at s1 + s2 + ... spp.
+struct RtAccum {
+    RtScene *scene = nullptr;
+    RtRenderParams geo{};
+    Rect rect{};
+    int64_t np = 0;                 // packed pixels of this rank
+    size_t rect_px = 0;
+    unsigned int done = 0;          // samples per pixel so far
+    float *d_sum = nullptr, *d_gamma = nullptr, *d_linear = nullptr, *d_image = nullptr;
+    uint8_t *d_bytes = nullptr;
+    ~RtAccum() {
+        if (d_sum) cudaFree(d_sum);
+        if (d_gamma) cudaFree(d_gamma);
+        if (d_linear) cudaFree(d_linear);
+        if (d_image) cudaFree(d_image);
+        if (d_bytes) cudaFree(d_bytes);
+    }
+};
+
+int rt_accum_create(RtScene *s, const RtRenderParams *geometry, RtAccum **out) {
+    if (!s || !geometry || !out) return fail(RT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    RtRenderParams g = *geometry;
+    if (g.spp < 1) g.spp = 1;       // the per-pass count is an argument of rt_accum_add
+    Rect r;
+    int rc = resolve_rect(g, r);
+    if (rc) return rc;
+    RT_CUDA(cudaSetDevice(s->device));
+    RtAccum *a = new (std::nothrow) RtAccum;
+    if (!a) return fail(RT_ERR_OOM, "out of host memory");
+    struct Guard { RtAccum *a; bool keep = false; ~Guard() { if (!keep) delete a; } } guard{a};
+    a->scene = s; a->geo = g; a->rect = r;
+    a->np = rt_render_pixel_count(&g);
+    a->rect_px = (size_t)(r.x1 - r.x0) * (size_t)(r.y1 - r.y0);
+    const size_t nb = (size_t)std::max<int64_t>(a->np, 1) * 3 * sizeof(float);
+    RT_CUDA(cudaMalloc((void **)&a->d_sum, nb));
+    RT_CUDA(cudaMalloc((void **)&a->d_gamma, nb));
+    RT_CUDA(cudaMalloc((void **)&a->d_linear, nb));
+    RT_CUDA(cudaMalloc((void **)&a->d_image, a->rect_px * 3 * sizeof(float)));
+    RT_CUDA(cudaMalloc((void **)&a->d_bytes, a->rect_px * 3));
+    RT_CUDA(cudaMemset(a->d_sum, 0, nb));
+    RT_CUDA(cudaMemset(a->d_gamma, 0, nb));
+    RT_CUDA(cudaMemset(a->d_linear, 0, nb));
+    guard.keep = true;
+    *out = a;
+    return RT_OK;
+}
+
+void rt_accum_destroy(RtAccum *a) {
+    if (!a) return;
+    cudaSetDevice(a->scene->device);
+    delete a;
+}
+
+int rt_accum_reset(RtAccum *a) {
+    if (!a) return fail(RT_ERR_INVALID, "null argument");
+    a->done = 0;                    // the next pass overwrites the sums (k_resolve ignores them when prior == 0)
+    return RT_OK;
+}
+
+uint32_t rt_accum_samples(const RtAccum *a) { return a ? a->done : 0u; }
+
+int rt_accum_add(RtAccum *a, const RtCamera *camera, int32_t spp, RtStats *stats) {
+    if (!a || !camera) return fail(RT_ERR_INVALID, "null argument");
+    if (spp < 1 || (unsigned long long)a->done + (unsigned long long)spp > 0x7FFFFFFFull) return fail(RT_ERR_INVALID, "bad sample count");
+    RtRenderParams p = a->geo;
+    p.spp = spp;
+    RtStats local;
+    const int rc = render_device_impl(a->scene, camera, &p, a->d_gamma, a->d_linear, nullptr, stats ? stats : &local, a->done, a->d_sum);
+    if (rc) return rc;
+    a->done += (unsigned int)spp;
+    return RT_OK;
+}
+
+int rt_accum_read(RtAccum *a, float *gamma_rgb, float *linear_rgb, uint8_t *rgb8) {
+    if (!a) return fail(RT_ERR_INVALID, "null argument");
+    if (a->done == 0) return fail(RT_ERR_INVALID, "no samples accumulated yet");
+    if (a->np <= 0) return RT_OK;
+    RtScene *s = a->scene;
+    RT_CUDA(cudaSetDevice(s->device));
+    int rc;
+    if (a->geo.n_ranks > 1) {
+        // only this rank's tiles are written, as in rt_render / rt_render_rgb8
+        std::vector<TileRec> tiles; std::vector<unsigned int> off;
+        build_tiles(a->geo, a->rect, tiles, off);
+        const int rw = a->rect.x1 - a->rect.x0;
+        std::vector<float> h((size_t)a->np * 3);
+        float *outs[2] = {gamma_rgb, linear_rgb};
+        const float *srcs[2] = {a->d_gamma, a->d_linear};
+        for (int k = 0; k < 2; ++k) {
+            if (!outs[k]) continue;
+            RT_CUDA(cudaMemcpy(h.data(), srcs[k], h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            for (size_t t = 0; t < tiles.size(); ++t)
+                for (int y = 0; y < tiles[t].h; ++y)
+                    memcpy(outs[k] + 3 * ((size_t)(tiles[t].y0 - a->rect.y0 + y) * rw + (tiles[t].x0 - a->rect.x0)),
+                           h.data() + 3 * ((size_t)off[t] + (size_t)y * tiles[t].w), (size_t)tiles[t].w * 3 * sizeof(float));
+        }
+        if (rgb8) {
+            std::vector<uint8_t> hb((size_t)a->np * 3);
+            if ((rc = rt_quantize_device(a->d_gamma, (size_t)a->np * 3, a->d_bytes, s->device, nullptr))) return rc;
+            RT_CUDA(cudaMemcpy(hb.data(), a->d_bytes, hb.size(), cudaMemcpyDeviceToHost));
+            for (size_t t = 0; t < tiles.size(); ++t)
+                for (int y = 0; y < tiles[t].h; ++y)
+                    memcpy(rgb8 + 3 * ((size_t)(tiles[t].y0 - a->rect.y0 + y) * rw + (tiles[t].x0 - a->rect.x0)),
+                           hb.data() + 3 * ((size_t)off[t] + (size_t)y * tiles[t].w), (size_t)tiles[t].w * 3);
+        }
+        return RT_OK;
+    }
+    int64_t off0 = 0;
+    if (linear_rgb) {
+        if ((rc = rt_untile_device(&a->geo, a->d_linear, &off0, a->d_image, s->device, nullptr))) return rc;
+        RT_CUDA(cudaMemcpy(linear_rgb, a->d_image, a->rect_px * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    if (gamma_rgb || rgb8) {
+        if ((rc = rt_untile_device(&a->geo, a->d_gamma, &off0, a->d_image, s->device, nullptr))) return rc;
+        if (gamma_rgb) RT_CUDA(cudaMemcpy(gamma_rgb, a->d_image, a->rect_px * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (rgb8) {
+            if ((rc = rt_quantize_device(a->d_image, a->rect_px * 3, a->d_bytes, s->device, nullptr))) return rc;
+            RT_CUDA(cudaMemcpy(rgb8, a->d_bytes, a->rect_px * 3, cudaMemcpyDeviceToHost));
+        }
+    }
     return RT_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <memory>
 #include <string>
 #include "Camera.h"
+#include "Preview.h"
 #include "Renderer.h"
 #include "Scene.h"
 #include "SceneFile.h"
@@ -175,6 +176,82 @@ int hai_ray_trace_from_camera_rgb8(HaiScene *s, int device, int w, int h, int ns
         std::vector<unsigned char> bytes;
         hai719::ray_trace_from_camera_rgb8(*s->on_device[device], camera, w, h, (unsigned)nsamples, bytes, opt);
         if (rgb8) std::memcpy(rgb8, bytes.data(), bytes.size());
+    });
+}
+
+// ---- interactive preview (host/Preview.h) ----------------------------------------------------------
+struct HaiPreview {
+    Camera camera;
+    std::unique_ptr<hai719::Preview> preview;
+};
+
+HaiPreview *hai_preview_new(HaiScene *s, int device, int w, int h, uint32_t seed) {
+    HaiPreview *p = nullptr;
+    const int rc = guarded([&] {
+        RtScene *dev = hai_scene_device(s, device);
+        if (!dev) throw std::runtime_error(g_err);
+        p = new HaiPreview;
+        p->camera.resize(w, h);
+        p->camera.move(0., 0., -3.1);      // main.cpp:418
+        hai719::RenderOptions opt;
+        opt.seed = seed;
+        opt.device = device;
+        opt.verbose = false;
+        p->preview.reset(new hai719::Preview(*s->on_device[device], p->camera, w, h, opt));
+    });
+    if (rc) { delete p; return nullptr; }
+    return p;
+}
+
+void hai_preview_free(HaiPreview *p) { delete p; }
+
+int hai_preview_mouse(HaiPreview *p, int button, int state, int x, int y) {
+    return guarded([&] { if (!p) throw std::runtime_error("null preview"); p->preview->mouse(button, state, x, y); });
+}
+
+int hai_preview_motion(HaiPreview *p, int x, int y) {
+    return guarded([&] { if (!p) throw std::runtime_error("null preview"); p->preview->motion(x, y); });
+}
+
+int hai_preview_resize(HaiPreview *p, int w, int h) {
+    return guarded([&] { if (!p) throw std::runtime_error("null preview"); p->preview->resize(w, h); });
+}
+
+int hai_preview_invalidate(HaiPreview *p) {
+    return guarded([&] { if (!p) throw std::runtime_error("null preview"); p->preview->invalidate(); });
+}
+
+int hai_preview_pass(HaiPreview *p, int pass_spp, uint32_t *samples_out) {
+    return guarded([&] {
+        if (!p) throw std::runtime_error("null preview");
+        if (pass_spp < 1) throw std::runtime_error("pass_spp must be >= 1");
+        const unsigned int n = p->preview->pass((unsigned)pass_spp);
+        if (samples_out) *samples_out = n;
+    });
+}
+
+int hai_preview_frame(HaiPreview *p, uint8_t *rgb8, float *gamma_rgb) {
+    return guarded([&] {
+        if (!p) throw std::runtime_error("null preview");
+        if (rgb8) {
+            const std::vector<unsigned char> &px = p->preview->frame_rgb8();
+            std::memcpy(rgb8, px.data(), px.size());
+        }
+        if (gamma_rgb) {
+            std::vector<Vec3> image;
+            p->preview->frame(image);
+            std::memcpy(gamma_rgb, image.data(), image.size() * sizeof(Vec3));
+        }
+    });
+}
+
+int hai_preview_camera(HaiPreview *p, RtCamera *out) {
+    return guarded([&] {
+        if (!p || !out) throw std::runtime_error("null argument");
+        p->camera.apply();
+        MatrixUtilities mu;
+        mu.updateMatrices(p->camera);
+        mu.fill(*out);
     });
 }
 

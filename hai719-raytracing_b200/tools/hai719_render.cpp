@@ -2,12 +2,17 @@
 // (main.cpp:321-326 -> ray_trace_from_camera). Builds one of the reference's scenes with the host
 // API, renders it on the GPU and writes the same P3 rendu.ppm.
 //   hai719_render [--scene N | --scene-file FILE] [--w W --h H] [--spp S] [--seed K] [--assets DIR] [--out FILE] [--p6 1] [--device D]
+//                 [--preview PASSES [--orbit PIXELS]]
+// --preview: progressive refinement instead of one render (host/Preview.h): PASSES passes of --spp samples each, every
+// intermediate frame written as <out>.<pass>.ppm (binary); with --orbit the left mouse button is "dragged" PIXELS to
+// the right after every second pass, which restarts the frame like any camera move in the reference's window would.
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <string>
 #include "Camera.h"
 #include "Constants.h"
+#include "Preview.h"
 #include "Renderer.h"
 #include "Scene.h"
 #include "SceneFile.h"
@@ -17,6 +22,7 @@ int main(int argc, char **argv) {
     unsigned int seed = 0;
     std::string assets, out = "./rendu.ppm", scene_file;
     bool p6 = false;
+    int preview = 0, orbit = 0;
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string k = argv[i];
         const char *v = argv[i + 1];
@@ -30,6 +36,8 @@ int main(int argc, char **argv) {
         else if (k == "--device") device = std::atoi(v);
         else if (k == "--scene-file") scene_file = v;
         else if (k == "--p6") p6 = std::atoi(v) != 0;
+        else if (k == "--preview") preview = std::atoi(v);
+        else if (k == "--orbit") orbit = std::atoi(v);
         else { std::cerr << "unknown option " << k << std::endl; return 2; }
     }
     Scene scene;
@@ -48,7 +56,23 @@ int main(int argc, char **argv) {
     opt.ppm_path = out;
     std::vector<Vec3> image;
     try {
-        if (p6) {   // output stage on the GPU: 8-bit quantise on the device, binary PPM
+        if (preview > 0) {
+            hai719::DeviceScene dev(scene, device);
+            opt.verbose = false;
+            hai719::Preview pv(dev, camera, w, h, opt);
+            for (int pass = 1; pass <= preview; ++pass) {
+                RtStats st;
+                const unsigned int n = pv.pass((unsigned int)spp, &st);
+                const std::string name = out + "." + std::to_string(pass) + ".ppm";
+                if (!pv.save(name)) { std::cerr << "Could not open file: " << name << std::endl; return 1; }
+                std::cout << "pass " << pass << ": " << n << " samples per pixel, " << st.kernel_ms << " ms on the GPU -> " << name << std::endl;
+                if (orbit != 0 && pass % 2 == 0 && pass < preview) {
+                    pv.mouse(hai719::Preview::Left, hai719::Preview::Down, w / 2, h / 2);
+                    pv.motion(w / 2 + orbit, h / 2);
+                    pv.mouse(hai719::Preview::Left, hai719::Preview::Up, w / 2 + orbit, h / 2);
+                }
+            }
+        } else if (p6) {   // output stage on the GPU: 8-bit quantise on the device, binary PPM
             opt.format = hai719::RenderOptions::P6;
             hai719::DeviceScene dev(scene, device);
             std::vector<unsigned char> rgb8;

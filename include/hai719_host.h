@@ -70,6 +70,23 @@ int hai_ray_trace_from_camera(HaiScene *s, int device, int w, int h, int nsample
 int hai_ray_trace_from_camera_rgb8(HaiScene *s, int device, int w, int h, int nsamples, uint32_t seed, const char *ppm_path,
                                    int p6, uint8_t *rgb8);
 
+/* Interactive preview (host/Preview.h): the reference's mouse handlers (main.cpp:344-388; button 0
+ * left = rotate, 1 middle = zoom, 2 right = move; state 0 down, 1 up) drive a Camera placed like main.cpp:418, and
+ * every hai_preview_pass() adds pass_spp samples per pixel to the frame on the GPU (rt_accum_*). Moving the camera
+ * restarts the accumulation. hai_preview_frame() returns the current mean: h*w*3 bytes and/or h*w*3 gamma floats.
+ * A preview refers to the scene's device copy: free it before hai_scene_setup / hai_scene_load_file /
+ * hai_scene_invalidate_device / hai_scene_free on the same scene. */
+typedef struct HaiPreview HaiPreview;
+HaiPreview *hai_preview_new(HaiScene *s, int device, int w, int h, uint32_t seed);
+void hai_preview_free(HaiPreview *p);
+int hai_preview_mouse(HaiPreview *p, int button, int state, int x, int y);
+int hai_preview_motion(HaiPreview *p, int x, int y);
+int hai_preview_resize(HaiPreview *p, int w, int h);
+int hai_preview_invalidate(HaiPreview *p);   /* after hai_scene_update_device(): restart the accumulation */
+int hai_preview_pass(HaiPreview *p, int pass_spp, uint32_t *samples_out);
+int hai_preview_frame(HaiPreview *p, uint8_t *rgb8, float *gamma_rgb);
+int hai_preview_camera(HaiPreview *p, RtCamera *out);   /* the matrices the next pass will use */
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

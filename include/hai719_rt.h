@@ -259,6 +259,24 @@ int rt_quantize_device(const float *d_values, size_t n, uint8_t *d_bytes, int de
 int rt_render_device(RtScene *scene, const RtCamera *camera, const RtRenderParams *params,
                      float *d_gamma_rgb, float *d_linear_rgb, void *cuda_stream, RtStats *stats);
 
+/* SURVEY 8(f)-4, progressive accumulation for an interactive preview. The reference renders a frame in one go on a
+ * key press (main.cpp:200-263, 321-326) and shows nothing until it is finished. An accumulator keeps every pixel's
+ * running sample sum on the device: each rt_accum_add() traces `spp` MORE samples per pixel — their indices continue
+ * where the previous pass stopped, so the random streams are those of one long render — and refreshes the mean.
+ * After passes of s1, s2, ... samples the frame read back is bit-identical to ONE rt_render at spp = s1 + s2 + ...
+ * (trace_line's additions happen in the same order, main.cpp:188-195). `geometry` supplies everything of
+ * RtRenderParams except spp (image size, rectangle, tile sharding, bounces, seed, variant). rt_accum_reset() forgets
+ * the samples (camera moved, scene updated); the scene must outlive the accumulator. All calls are synchronous. */
+typedef struct RtAccum RtAccum;
+int rt_accum_create(RtScene *scene, const RtRenderParams *geometry, RtAccum **out);
+void rt_accum_destroy(RtAccum *accum);
+int rt_accum_reset(RtAccum *accum);
+int rt_accum_add(RtAccum *accum, const RtCamera *camera, int32_t spp, RtStats *stats);
+uint32_t rt_accum_samples(const RtAccum *accum);   /* samples per pixel accumulated so far */
+/* Current mean frame to HOST buffers (any may be NULL): rect_h*rect_w*3 gamma-corrected floats, the same before
+ * gamma, and the reference's 8-bit values (see rt_render_rgb8). With n_ranks > 1 only this rank's tiles are written. */
+int rt_accum_read(RtAccum *accum, float *gamma_rgb, float *linear_rgb, uint8_t *rgb8);
+
 /* Scatter packed per-rank tile buffers (as gathered on one device: rank r's buffer starts at
  * float offset 3*pixel_offsets[r]) into a row-major rect_h*rect_w*3 image. */
 int rt_untile_device(const RtRenderParams *params, const float *d_packed, const int64_t *pixel_offsets,

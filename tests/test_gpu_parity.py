@@ -364,6 +364,74 @@ def test_stochastic_render_agrees_with_the_unmodified_reference(gpu, assets, nam
     assert abs(z_total) < 10.0
 
 
+@pytest.mark.parametrize("name,kw", [("cornell_box", {}), ("random_spheres", {}), ("flamingo_pond", {}), ("backrooms_pool", {}),
+                                     ("random_spheres", {"variant": 3}), ("config5", {"rank": 1, "n_ranks": 2, "tile": (16, 8)}),
+                                     ("raccoon", {"crop": (10, 7, 93, 50)})])
+def test_progressive_passes_equal_one_render(gpu, assets, name, kw):
+    """rt_accum_add continues every pixel's sample sum and random streams, so passes of 1 + 2 + 3 samples
+    give the bits of ONE render at 6 spp - floats before and after gamma and the 8-bit output - whatever the kernel,
+    the rectangle or the sharding; after a reset the accumulator starts over."""
+    w, h = 112, 63
+    s = gpu.Scene(name, aspect=w / h)
+    acc = s.accumulator(w, h, seed=21, **kw)
+    with pytest.raises(gpu.RtError):
+        acc.read()                                   # nothing accumulated yet
+    total = 0
+    for k in (1, 2, 3):
+        total += k
+        assert acc.add(k) == total
+        one = s.render(w, h, total, seed=21, **kw)
+        got = acc.read()
+        assert np.array_equal(got["linear"].view(np.uint32), one["linear"].view(np.uint32)), (name, total)
+        assert np.array_equal(got["gamma"].view(np.uint32), one["gamma"].view(np.uint32)), (name, total)
+        assert np.array_equal(got["rgb8"], s.render_rgb8(w, h, total, seed=21, **kw)), (name, total)
+    acc.reset()
+    assert acc.samples == 0
+    acc.add(2)
+    two = s.render(w, h, 2, seed=21, **kw)
+    assert np.array_equal(acc.read()["linear"].view(np.uint32), two["linear"].view(np.uint32))
+    with pytest.raises(gpu.RtError):
+        acc.add(0)
+    acc.close()
+
+
+def test_preview_mouse_handlers_drive_the_camera_and_restart_the_frame(gpu, assets):
+    """host/Preview.h: the reference's mouse()/motion() logic (main.cpp:344-388) on the reference's Camera; passes refine
+    the frame while the camera rests, any camera change restarts it, and every frame equals a one-shot render from the
+    same camera at the accumulated sample count."""
+    w, h = 128, 72
+    s = gpu.Scene("cornell_box", aspect=w / h)
+    pv = s.preview(w, h, seed=5)
+    assert pv.render_pass(2) == 2 and pv.render_pass(2) == 4
+    f0 = pv.frame()
+    one = s.render(w, h, 4, seed=5)                  # default camera = Camera() + move(0, 0, -3.1), main.cpp:418
+    assert np.array_equal(f0["gamma"].view(np.uint32), one["gamma"].view(np.uint32))
+    assert np.array_equal(f0["rgb8"], s.render_rgb8(w, h, 4, seed=5))
+    cams = [bytes(pv.camera())]
+    # left button: trackball rotation; right button: pan; middle button: zoom
+    for button, (dx, dy) in ((0, (25, 9)), (2, (-14, 6)), (1, (0, 11))):
+        pv.mouse(button, 0, 60, 30)
+        pv.motion(60 + dx, 30 + dy)
+        pv.mouse(button, 1, 60 + dx, 30 + dy)
+        cams.append(bytes(pv.camera()))
+        assert cams[-1] != cams[-2], button        # the camera moved ...
+        assert pv.render_pass(3) == 3                # ... so the frame restarted
+        f = pv.frame()
+        ref_frame = s.render(w, h, 3, seed=5, camera=pv.camera())
+        assert np.array_equal(f["gamma"].view(np.uint32), ref_frame["gamma"].view(np.uint32)), button
+        assert not np.array_equal(f["rgb8"], f0["rgb8"])
+    pv.motion(5, 5)                                  # no button held: nothing happens
+    assert bytes(pv.camera()) == cams[-1] and pv.render_pass(1) == 4
+    pv.invalidate()
+    assert pv.render_pass(1) == 1
+    pv.resize(96, 54)
+    assert pv.render_pass(2) == 2
+    f = pv.frame()
+    assert f["rgb8"].shape == (54, 96, 3)
+    assert np.array_equal(f["gamma"].view(np.uint32), s.render(96, 54, 2, seed=5, camera=pv.camera())["gamma"].view(np.uint32))
+    pv.close()
+
+
 def test_device_output_and_untile(gpu, assets):
     """rt_render_device + rt_untile_device with torch-owned device buffers (what bench.py's multi-GPU path does)."""
     torch = pytest.importorskip("torch")

@@ -221,6 +221,25 @@ def test_loaders_handle_format_variants(hb, tmp_path):
     assert s.flatten().contents.skybox.w == 0
 
 
+def test_preview_and_accumulator_need_a_device_too(hb, assets):
+    """SURVEY 8(f)-4 entry points: same rule, no device - an error with a text, never a CPU render."""
+    if hb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    s = hb.Scene("single_square")
+    with pytest.raises(hb.RtError) as e:
+        s.accumulator(16, 9)
+    assert e.value.status == -2 or "no CUDA device" in str(e.value)
+    with pytest.raises(hb.RtError) as e:
+        s.preview(16, 9)
+    assert "no CUDA device" in str(e.value) or "device" in str(e.value)
+    # null handles are rejected, not dereferenced
+    assert hb.rt.rt_accum_add(None, None, 1, None) == -1 and hb.rt.rt_accum_read(None, None, None, None) == -1
+    assert hb.rt.rt_accum_samples(None) == 0
+    hb.rt.rt_accum_destroy(None)
+    assert hb.host.hai_preview_pass(None, 1, None) != 0 and hb.host.hai_preview_motion(None, 0, 0) != 0
+    hb.host.hai_preview_free(None)
+
+
 def test_no_gpu_means_error_not_fallback(hb, assets):
     """On the CPU-only build box the render path must fail loudly."""
     if hb.device_count() > 0:

@@ -542,13 +542,35 @@ RT_HD void bvh_consider(const Ray &ray, const DScene &s, uint32_t r0, float &bes
 // Closest reachable hit of mesh m with t < limit (limit = the scene's current best / the light
 // distance, exactly the bound Scene::computeIntersection / computeShadow apply to the mesh's
 // answer). Same (t, triangle) as mesh_closest() whenever that answer would be accepted.
+//
+// any_hit (shadow samples): Scene::computeShadow only asks whether the mesh's closest hit lies in (EPSILON, limit)
+// (Scene.h:248-253), i.e. whether SOME reachable hit does and NONE lies in [0, EPSILON]. So the first accepted hit above
+// EPSILON answers the first half, and the search goes on with the bound pulled in to EPSILON: every box further away
+// is culled at once, and what is left can only find a hit at t <= EPSILON, which is then the answer (closest hit too
+// near: the reference does not draw). Same boolean and same draw as the full closest-hit search; t_out is then a
+// witness, not the minimum. Measured (profiles/r01_notes.md): config 3 -1.2 %, config 4 +-0, config 5 +3 % (slower) on
+// the automatic kernels - the shadow rays that cost time are the unoccluded ones grazing the terrain - so it is OFF.
+#ifndef RT_OPT_ANYHIT
+#define RT_OPT_ANYHIT 0
+#endif
+#define RT_ANYHIT_STEP() \
+    if (RT_OPT_ANYHIT && any_hit && best_ref != NONE) { \
+        if (!(best_t > RT_EPSF)) { t_out = best_t; ref_out = best_ref; return true; } \
+        found_t = best_t; found_ref = best_ref; best_t = eps_next; best_ref = NONE; \
+    }
 template <bool STATS>
-RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, float limit, float &t_out, uint32_t &ref_out, Counters *cnt) {
+RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, float limit, float &t_out, uint32_t &ref_out, Counters *cnt,
+                            bool any_hit = false) {
     const uint32_t NONE = 0xFFFFFFFFu;
     float best_t = limit;
     uint32_t best_ref = NONE;
-    for (uint32_t k = m.always_first; k < m.always_first + m.always_count; ++k)
+    const float eps_next = u2f(f2u(RT_EPSF) + 1u);   // t < eps_next  <=>  t <= EPSILON
+    float found_t = 0.f;
+    uint32_t found_ref = NONE;
+    for (uint32_t k = m.always_first; k < m.always_first + m.always_count; ++k) {
         bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+        RT_ANYHIT_STEP()
+    }
     if (m.bvh_root >= 0) {
         Inv32 iv; iv.x = safe_inv(ray.d.x); iv.y = safe_inv(ray.d.y); iv.z = safe_inv(ray.d.z);
         int stack[64];
@@ -579,8 +601,10 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
             if (node == DONE) break;
             const uint32_t code = (uint32_t)(-(node + 1));
             const uint32_t first = code >> 3, count = code & 7u;
-            for (uint32_t k = first; k < first + count; ++k)
+            for (uint32_t k = first; k < first + count; ++k) {
                 bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+                RT_ANYHIT_STEP()
+            }
             if (sp == 0) break;
             node = stack[--sp];
         }
@@ -605,19 +629,23 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
             } else {
                 const uint32_t code = (uint32_t)(-(node + 1));
                 const uint32_t first = code >> 3, count = code & 7u;
-                for (uint32_t k = first; k < first + count; ++k)
+                for (uint32_t k = first; k < first + count; ++k) {
                     bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+                    RT_ANYHIT_STEP()
+                }
             }
             if (sp == 0) break;
             node = stack[--sp];
         }
 #endif
     }
+    if (RT_OPT_ANYHIT && any_hit && found_ref != NONE) { t_out = found_t; ref_out = found_ref; return true; }   // best_ref is NONE here
     if (best_ref == NONE) return false;
     t_out = best_t;
     ref_out = best_ref;
     return true;
 }
+#undef RT_ANYHIT_STEP
 
 // All meshes of the scene in ONE per-lane loop (closest-hit and shadow rays): a lane that has finished mesh i goes
 // straight on to mesh i+1 while its neighbours are still inside mesh i, and both execute the same box-test and
@@ -1126,7 +1154,7 @@ RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_ligh
             if (done) break;
             if (STATS) cnt->mesh++;
             float t; uint32_t ref;
-            if (mesh_closest_bvh<STATS>(ray, s, s.meshes[i], h.t, t, ref, cnt) && t < h.t && t > RT_EPSF) {
+            if (mesh_closest_bvh<STATS>(ray, s, s.meshes[i], h.t, t, ref, cnt, mode != 0) && t < h.t && t > RT_EPSF) {
                 if (mode == 0) { h.type = 3; h.obj = i; h.t = t; h.ref = ref; }
                 else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.mesh_transparency + i)) { blocked = true; done = true; } }
             }
@@ -1715,7 +1743,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
         if (done) break;
         if (STATS) cnt->mesh++;
         float t; uint32_t ref;
-        if (mesh_closest_bvh<STATS>(ray, s, s.meshes[i], h.t, t, ref, cnt) && t < h.t && t > RT_EPSF) {
+        if (mesh_closest_bvh<STATS>(ray, s, s.meshes[i], h.t, t, ref, cnt, mode != 0) && t < h.t && t > RT_EPSF) {
             if (mode == 0) { h.type = 3; h.obj = i; h.t = t; h.ref = ref; }
             else { if (STATS) cnt->rnd++; if (st.rng.next() > RT_LDG(s.mesh_transparency + i)) { blocked = true; done = true; } }
         }

@@ -114,7 +114,7 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #define RT_OPT_WW_LC 1      /* analytic culling hierarchy (variants 5, 6): while-while traversal */
 #endif
 #ifndef RT_OPT_MESH_MERGED
-#define RT_OPT_MESH_MERGED 0 /* all meshes in one per-lane walk loop instead of one loop per mesh: measured slower on configs 3 and 5 */
+#define RT_OPT_MESH_MERGED 1 /* all meshes in one per-lane while-while loop instead of one loop per mesh: config 4 -10 %, config 5 -3 %, config 3 +1 % */
 #endif
 
 namespace rt {
@@ -647,65 +647,69 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
 }
 #undef RT_ANYHIT_STEP
 
-// All meshes of the scene in ONE per-lane loop (closest-hit and shadow rays): a lane that has finished mesh i goes
-// straight on to mesh i+1 while its neighbours are still inside mesh i, and both execute the same box-test and
-// triangle-test code. With one loop per mesh the lanes of a warp met again after every mesh: the warp paid the SUM over
-// meshes of the slowest lane instead of the slowest lane's sum (pond scene: 8 of 32 lanes active in the walk,
-// profiles/r01_notes.md). Same candidates, same per-triangle routine, same acceptance rules and draw order as
-// mesh_closest_bvh called mesh after mesh.
+// All meshes of the scene in ONE per-lane loop. With one loop per mesh the lanes of a warp meet again after every mesh
+// and the warp pays the slowest lane each time: the box tests of the pond scene ran at 8 of 32 lanes
+// (profiles/r01_notes.md). Here a lane that has finished mesh i goes straight on to mesh i+1 while its neighbours are
+// still walking, and all of them share the same three pieces of code per round: pending triangles, descent to the next
+// leaf (box tests only, the tight loop), then either "open the leaf" or "mesh finished". Same candidates, same
+// per-triangle routine, same acceptance rules and draw order as mesh_closest_bvh called mesh after mesh
+// (Scene.h:221-228 closest, 248-253 shadow).
+#define RT_WALK_DESCEND() \
+        while ((unsigned int)node < (unsigned int)MESH_END) { \
+            const float4 n0 = RT_LDG(s.bvh_nodes + 4 * node), n1 = RT_LDG(s.bvh_nodes + 4 * node + 1), \
+                         n2 = RT_LDG(s.bvh_nodes + 4 * node + 2), n3 = RT_LDG(s.bvh_nodes + 4 * node + 3); \
+            if (STATS) cnt->node++; \
+            float d0, d1; \
+            const bool h0 = bvh_box(ray, iv, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, best_t, d0); \
+            const bool h1 = bvh_box(ray, iv, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, best_t, d1); \
+            const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y); \
+            if (h0 && h1) { \
+                const bool swap = d1 < d0; \
+                node = swap ? c1 : c0; \
+                stack[sp++] = swap ? c0 : c1;    /* depth <= 56 by construction (rt_bvh.hpp) */ \
+            } else if (h0) node = c0; \
+            else if (h1) node = c1; \
+            else node = sp > 0 ? stack[--sp] : MESH_END; \
+        }
 template <bool STATS>
 RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rng, Hit &h, bool &blocked, bool &done, Counters *cnt) {
     if (done || s.n_meshes <= 0) return;
     const uint32_t NONE = 0xFFFFFFFFu;
-    const int DONE = 0x7FFFFFFF;
+    const int MESH_END = 0x7FFFFFFD;
     Inv32 iv; iv.x = safe_inv(ray.d.x); iv.y = safe_inv(ray.d.y); iv.z = safe_inv(ray.d.z);
     int stack[64];
     int sp = 0, mi = 0;
-    const DMesh *m = s.meshes;
-    uint32_t k = m->always_first, kend = m->always_first + m->always_count;   // the always-tested triangles come first, like a leaf
-    int node = m->bvh_root >= 0 ? m->bvh_root : DONE;
+    // the always-tested triangles of a mesh come first, like a leaf
+    uint32_t k = s.meshes[0].always_first, kend = k + s.meshes[0].always_count;
+    int node = s.meshes[0].bvh_root >= 0 ? s.meshes[0].bvh_root : MESH_END;
     float best_t = h.t;
     uint32_t best_ref = NONE;
     if (STATS) cnt->mesh++;
     for (;;) {
-        if (k < kend) {
-            bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
-            ++k;
-        } else if (node == DONE) {
-            // mesh mi is finished: Scene-level acceptance (Scene.h:221-228 closest, 248-253 shadow)
-            if (best_ref != NONE && best_t < h.t && best_t > RT_EPSF) {
-                if (mode == 0) { h.type = 3; h.obj = mi; h.t = best_t; h.ref = best_ref; }
-                else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.mesh_transparency + mi)) { blocked = true; done = true; break; } }
-            }
-            if (++mi >= s.n_meshes) break;
-            m = s.meshes + mi;
-            if (STATS) cnt->mesh++;
-            k = m->always_first; kend = k + m->always_count;
-            node = m->bvh_root >= 0 ? m->bvh_root : DONE;
-            sp = 0;
-            best_t = h.t; best_ref = NONE;
-        } else if (node >= 0) {
-            const float4 n0 = RT_LDG(s.bvh_nodes + 4 * node), n1 = RT_LDG(s.bvh_nodes + 4 * node + 1),
-                         n2 = RT_LDG(s.bvh_nodes + 4 * node + 2), n3 = RT_LDG(s.bvh_nodes + 4 * node + 3);
-            if (STATS) cnt->node++;
-            float d0, d1;
-            const bool h0 = bvh_box(ray, iv, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, best_t, d0);
-            const bool h1 = bvh_box(ray, iv, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, best_t, d1);
-            const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
-            if (h0 && h1) {
-                const bool swap = d1 < d0;
-                node = swap ? c1 : c0;
-                stack[sp++] = swap ? c0 : c1;
-            } else if (h0) node = c0;
-            else if (h1) node = c1;
-            else node = sp > 0 ? stack[--sp] : DONE;
-        } else {
+        for (; k < kend; ++k) bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+        RT_WALK_DESCEND()
+        if (node < 0) {   // a leaf: its triangles are tested at the top of the next round
             const uint32_t code = (uint32_t)(-(node + 1));
             k = code >> 3; kend = k + (code & 7u);
-            node = sp > 0 ? stack[--sp] : DONE;
+            node = sp > 0 ? stack[--sp] : MESH_END;
+            continue;
         }
+        // mesh mi is finished
+        if (best_ref != NONE && best_t < h.t && best_t > RT_EPSF) {
+            if (mode == 0) { h.type = 3; h.obj = mi; h.t = best_t; h.ref = best_ref; }
+            else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.mesh_transparency + mi)) { blocked = true; done = true; break; } }
+        }
+        if (++mi >= s.n_meshes) break;
+        const DMesh &m = s.meshes[mi];
+        if (STATS) cnt->mesh++;
+        k = m.always_first; kend = k + m.always_count;
+        node = m.bvh_root >= 0 ? m.bvh_root : MESH_END;
+        sp = 0;
+        best_t = h.t; best_ref = NONE;
     }
 }
+
+#undef RT_WALK_DESCEND
 
 // ---- analytic primitives through their culling hierarchy (variant 3) ----------------------------
 // Visits every sphere/square whose padded, motion-swept box the ray can touch within [0, limit] and
@@ -1458,6 +1462,40 @@ RT_HD bool lc_cannot_occlude(const DScene &s, uint32_t seq, int ns, V3 P, float 
 // so the stream advances by 3*NB_ECH and shadow = 1 - 0/NB_ECH = 1 leaves the colour unchanged (x * 1.0f == x).
 RT_HD bool lc_light_unoccluded(const PathState &st) { return (st.cm0 | st.cm1 | st.cm2 | st.cm3) == 0u && st.cl_n == 0; }
 
+// Scene::computeShadow (Scene.h:235-247) over the analytic occluder candidates of the current light, for the shadow
+// sample in st.ray: ascending sequence index = the reference's order (spheres by index, then squares by index), one
+// draw per candidate hit until one blocks. Returns computeShadow's answer so far (true: blocked, the meshes are skipped).
+template <bool STATS>
+RT_HD bool lc_shadow_analytic(const DScene &s, PathState &st, Counters *cnt) {
+    const Ray &ray = st.ray;
+    const int ns = s.n_spheres;
+    if (STATS) cnt->shadow++;
+    const SphereRay sr = make_sphere_ray(ray);
+    for (int w = 0; w < 4; ++w) {
+        uint32_t m = w == 0 ? st.cm0 : (w == 1 ? st.cm1 : (w == 2 ? st.cm2 : st.cm3));
+        while (m) {
+            const int seq = w * 32 + RT_FFS((int)m) - 1;
+            m &= m - 1u;
+            float t, tr, u, v;
+            if (seq < ns) {
+                if (STATS) cnt->sphere++;
+                const float4 b = RT_LDG(s.sph_b + seq);
+                t = sphere_t(ray, sr, RT_LDG(s.sph_a + seq), b);
+                tr = b.w;
+            } else {
+                if (STATS) cnt->square++;
+                t = square_t(ray, s.squares[seq - ns], u, v);
+                tr = RT_LDG(s.sq_transparency + (seq - ns));
+            }
+            if (t < st.t_light && t > RT_EPSF) {
+                if (STATS) cnt->rnd++;
+                if (st.rng.next() > tr) return true;
+            }
+        }
+    }
+    return false;
+}
+
 // One step of the variant-5 state machine for the lanes selected by `mine`.
 //   run_t (warp-uniform) true : lanes in mode 0 (closest hit) and mode 3 (collect candidates) walk the
 //                               analytic hierarchy together; mode 0 goes on to the meshes.
@@ -1689,32 +1727,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
         }
     }
 #else
-        // Scene::computeShadow over the candidates, ascending sequence index = the reference's order
-        // (spheres by index, then squares by index): one draw per candidate hit until one blocks
-        if (STATS) cnt->shadow++;
-        const SphereRay sr = make_sphere_ray(ray);
-        for (int w = 0; w < 4 && !done; ++w) {
-            uint32_t m = w == 0 ? st.cm0 : (w == 1 ? st.cm1 : (w == 2 ? st.cm2 : st.cm3));
-            while (m) {
-                const int seq = w * 32 + RT_FFS((int)m) - 1;
-                m &= m - 1u;
-                float t, tr, u, v;
-                if (seq < ns) {
-                    if (STATS) cnt->sphere++;
-                    const float4 b = RT_LDG(s.sph_b + seq);
-                    t = sphere_t(ray, sr, RT_LDG(s.sph_a + seq), b);
-                    tr = b.w;
-                } else {
-                    if (STATS) cnt->square++;
-                    t = square_t(ray, s.squares[seq - ns], u, v);
-                    tr = RT_LDG(s.sq_transparency + (seq - ns));
-                }
-                if (t < h.t && t > RT_EPSF) {
-                    if (STATS) cnt->rnd++;
-                    if (st.rng.next() > tr) { blocked = true; done = true; break; }
-                }
-            }
-        }
+        if (lc_shadow_analytic<STATS>(s, st, cnt)) { blocked = true; done = true; }
     }
 #endif
     // meshes. Closest-hit rays, and shadow samples whose light has too many candidate triangles for the list, walk the
@@ -1877,6 +1890,15 @@ RT_HD bool path_shade(const DScene &s, PathState &st, const Hit &h, float hu, fl
     return false;
 }
 
+// The NB_ECH samples of light st.light are in st.blocked: scale the colour (Scene.h:331-333) and go on.
+template <bool STATS, bool LC = false, bool WF = false>
+RT_HD bool path_finish_light(const DScene &s, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
+    const float shadow = (float)(1. - (double)((float)st.blocked / (float)nb_ech));
+    st.color = st.color * shadow;
+    ++st.light;
+    return path_next_light_or_bounce<STATS, LC, WF>(s, st, nb_ech, out, cnt);
+}
+
 // Consume the result of intersect_ray for this lane's ray and set up the next ray.
 template <bool STATS, bool LC = false, bool WF = false>
 RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, float hv, bool blocked, int nb_ech, V3 &out,
@@ -1894,10 +1916,7 @@ RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, 
     if (st.mode == 1) {
         if (blocked) ++st.blocked;
         if (++st.j < nb_ech) { path_shadow_sample<STATS>(s, st, cnt); return false; }
-        const float shadow = (float)(1. - (double)((float)st.blocked / (float)nb_ech));
-        st.color = st.color * shadow;
-        ++st.light;
-        return path_next_light_or_bounce<STATS, LC, WF>(s, st, nb_ech, out, cnt);
+        return path_finish_light<STATS, LC, WF>(s, st, nb_ech, out, cnt);
     }
     // mode 0
     if (path_shade<STATS, WF>(s, st, h, hu, hv, out, cnt)) return true;

@@ -50,6 +50,19 @@ struct Accel {
     std::vector<uint32_t> node_parent;   // per node of the shared node array: parent index, 0xFFFFFFFF for a mesh's synthetic root
 };
 
+// Builder knobs, measured on B200 (profiles/r01_notes.md). Any choice gives the same pixels: the hierarchies only cull.
+//   SAH over all three axes instead of the widest one: config 3 73.4 -> 68.3 ms (2-spp frame), configs 4/5 -1 %
+//   leaves of <= 2 triangles (1: config 3 +8 %, 4: config 4 +8 %); leaves of ONE sphere/square (config 2 -7 %: a sphere test
+//   costs as much as two box tests, so a box that rules it out pays); 32 bins (-1 % against 16)
+#ifndef RT_BVH_SAH_AXES
+#define RT_BVH_SAH_AXES 3
+#endif
+#ifndef RT_BVH_LEAF_TRIS
+#define RT_BVH_LEAF_TRIS 2
+#endif
+#ifndef RT_BVH_LEAF_ANALYTIC
+#define RT_BVH_LEAF_ANALYTIC 1
+#endif
 namespace bvh_detail {
 struct Box {
     float lo[3], hi[3];
@@ -68,7 +81,7 @@ inline int32_t leaf_code(uint32_t first, uint32_t count) { return -(int32_t)(fir
 // returns a child code (>= 0 inner node, < 0 leaf). `median` forces balanced splits (depth <= log2 n),
 // used when the SAH tree came out deeper than the device's traversal stack.
 template <class A>
-inline int32_t build(std::vector<Prim> &prims, size_t begin, size_t end, A &out, bool median, int depth, int &max_depth) {
+inline int32_t build(std::vector<Prim> &prims, size_t begin, size_t end, A &out, bool median, int depth, int &max_depth, size_t LEAF) {
     const size_t n = end - begin;
     max_depth = std::max(max_depth, depth);
     Box cb; cb.reset();
@@ -77,42 +90,49 @@ inline int32_t build(std::vector<Prim> &prims, size_t begin, size_t end, A &out,
     float ext = -1.f;
     for (int a = 0; a < 3; ++a) if (cb.hi[a] - cb.lo[a] > ext) { ext = cb.hi[a] - cb.lo[a]; axis = a; }
     size_t mid = begin;
-    if (n > 2 && median) {
+    if (n > LEAF && median) {
         mid = begin + n / 2;
         std::nth_element(prims.begin() + begin, prims.begin() + mid, prims.begin() + end,
                          [&](const Prim &a, const Prim &b) { return a.c[axis] < b.c[axis]; });
-    } else if (n > 2 && ext > 0.f) {
-        // binned SAH on the widest centroid axis
-        const int NB = 16;
-        Box bb[NB]; int bc[NB];
-        for (int b = 0; b < NB; ++b) { bb[b].reset(); bc[b] = 0; }
-        const float k = NB * (1.f - 1e-6f) / ext;
-        for (size_t i = begin; i < end; ++i) {
-            int b = (int)((prims[i].c[axis] - cb.lo[axis]) * k);
-            b = std::max(0, std::min(NB - 1, b));
-            bb[b].grow(prims[i].box); bc[b]++;
-        }
-        float la[NB], ra[NB]; int lc[NB], rc[NB];
-        Box acc; acc.reset(); int cnt = 0;
-        for (int b = 0; b < NB; ++b) { acc.grow(bb[b]); cnt += bc[b]; la[b] = acc.area(); lc[b] = cnt; }
-        acc.reset(); cnt = 0;
-        for (int b = NB - 1; b >= 0; --b) { acc.grow(bb[b]); cnt += bc[b]; ra[b] = acc.area(); rc[b] = cnt; }
-        float best = FLT_MAX; int bs = -1;
-        for (int b = 0; b + 1 < NB; ++b) {
-            if (lc[b] == 0 || rc[b + 1] == 0) continue;
-            const float cost = la[b] * lc[b] + ra[b + 1] * rc[b + 1];
-            if (cost < best) { best = cost; bs = b; }
+    } else if (n > LEAF && ext > 0.f) {
+        // binned SAH: RT_BVH_SAH_AXES = 1 widest centroid axis only, 3 = the best split over all three axes
+        const int NB = 32, NBMAX = NB;
+        float best = FLT_MAX; int bs = -1, best_axis = axis;
+        for (int a = 0; a < 3; ++a) {
+            if (RT_BVH_SAH_AXES == 1 && a != axis) continue;
+            const float ea = cb.hi[a] - cb.lo[a];
+            if (!(ea > 0.f)) continue;
+            Box bb[NBMAX]; int bc[NBMAX];
+            for (int b = 0; b < NB; ++b) { bb[b].reset(); bc[b] = 0; }
+            const float k = NB * (1.f - 1e-6f) / ea;
+            for (size_t i = begin; i < end; ++i) {
+                int b = (int)((prims[i].c[a] - cb.lo[a]) * k);
+                b = std::max(0, std::min(NB - 1, b));
+                bb[b].grow(prims[i].box); bc[b]++;
+            }
+            float la[NBMAX], ra[NBMAX]; int lc[NBMAX], rc[NBMAX];
+            Box acc; acc.reset(); int cnt = 0;
+            for (int b = 0; b < NB; ++b) { acc.grow(bb[b]); cnt += bc[b]; la[b] = acc.area(); lc[b] = cnt; }
+            acc.reset(); cnt = 0;
+            for (int b = NB - 1; b >= 0; --b) { acc.grow(bb[b]); cnt += bc[b]; ra[b] = acc.area(); rc[b] = cnt; }
+            for (int b = 0; b + 1 < NB; ++b) {
+                if (lc[b] == 0 || rc[b + 1] == 0) continue;
+                const float cost = la[b] * lc[b] + ra[b + 1] * rc[b + 1];
+                if (cost < best) { best = cost; bs = b; best_axis = a; }
+            }
         }
         if (bs >= 0) {
+            const int a = best_axis;
+            const float k = NB * (1.f - 1e-6f) / (cb.hi[a] - cb.lo[a]);
             auto it = std::partition(prims.begin() + begin, prims.begin() + end, [&](const Prim &p) {
-                int b = (int)((p.c[axis] - cb.lo[axis]) * k);
+                int b = (int)((p.c[a] - cb.lo[a]) * k);
                 b = std::max(0, std::min(NB - 1, b));
                 return b <= bs;
             });
             mid = (size_t)(it - prims.begin());
         }
     }
-    if (n <= 2 || ((mid == begin || mid == end) && n <= 7)) {
+    if (n <= LEAF || ((mid == begin || mid == end) && n <= 7)) {
         const uint32_t first = (uint32_t)out.tris.size();
         for (size_t i = begin; i < end; ++i) out.tris.push_back(prims[i].ref);
         return leaf_code(first, (uint32_t)n);
@@ -126,8 +146,8 @@ inline int32_t build(std::vector<Prim> &prims, size_t begin, size_t end, A &out,
     float k0 = 0.f, k1 = 0.f;   // largest per-primitive padding coefficient below each child (0 for triangles)
     for (size_t i = begin; i < mid; ++i) { b0.grow(prims[i].box); k0 = std::max(k0, prims[i].coef); }
     for (size_t i = mid; i < end; ++i) { b1.grow(prims[i].box); k1 = std::max(k1, prims[i].coef); }
-    const int32_t c0 = build(prims, begin, mid, out, median, depth + 1, max_depth);
-    const int32_t c1 = build(prims, mid, end, out, median, depth + 1, max_depth);
+    const int32_t c0 = build(prims, begin, mid, out, median, depth + 1, max_depth, LEAF);
+    const int32_t c1 = build(prims, mid, end, out, median, depth + 1, max_depth, LEAF);
     out.nodes[4 * id + 0] = make_float4(b0.lo[0], b0.lo[1], b0.lo[2], b0.hi[0]);
     out.nodes[4 * id + 1] = make_float4(b0.hi[1], b0.hi[2], b1.lo[0], b1.lo[1]);
     out.nodes[4 * id + 2] = make_float4(b1.lo[2], b1.hi[0], b1.hi[1], b1.hi[2]);
@@ -225,11 +245,11 @@ inline void build_accel(const RtSceneDesc &d, const PackedMeshes &pk, Accel &out
         if (prims.empty()) { out.mesh_root.push_back(-1); continue; }
         const size_t nodes_mark = out.nodes.size(), tris_mark = out.tris.size();
         int max_depth = 0;
-        int32_t root = build(prims, 0, prims.size(), out, false, 0, max_depth);
+        int32_t root = build(prims, 0, prims.size(), out, false, 0, max_depth, RT_BVH_LEAF_TRIS);
         if (max_depth > 56) {   // device stack holds 64 entries
             out.nodes.resize(nodes_mark); out.tris.resize(tris_mark);
             max_depth = 0;
-            root = build(prims, 0, prims.size(), out, true, 0, max_depth);
+            root = build(prims, 0, prims.size(), out, true, 0, max_depth, RT_BVH_LEAF_TRIS);
         }
         if (root >= 0) {
             out.mesh_root.push_back(root);
@@ -321,8 +341,8 @@ inline void build_analytic_accel(const RtSceneDesc &d, AnalyticAccel &out) {
     for (int a = 0; a < 3; ++a) { out.center[a] = 0.5f * (all.lo[a] + all.hi[a]); const float h = 0.5f * (all.hi[a] - all.lo[a]); r2 += h * h; }
     out.radius = std::sqrt(r2);
     int max_depth = 0;
-    int32_t root = build(prims, 0, prims.size(), out, false, 0, max_depth);
-    if (max_depth > 56) { out.nodes.clear(); out.tris.clear(); max_depth = 0; root = build(prims, 0, prims.size(), out, true, 0, max_depth); }
+    int32_t root = build(prims, 0, prims.size(), out, false, 0, max_depth, RT_BVH_LEAF_ANALYTIC);
+    if (max_depth > 56) { out.nodes.clear(); out.tris.clear(); max_depth = 0; root = build(prims, 0, prims.size(), out, true, 0, max_depth, RT_BVH_LEAF_ANALYTIC); }
     if (root < 0) {
         // one or two primitives: a single leaf. Wrap it in a node whose second child is empty (inverted box)
         Box b; b.reset();

@@ -1395,7 +1395,10 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     // 5 = occluder candidates per (hit, light): needs the analytic hierarchy and at least one light
     const bool lc_ok = s->d.abvh_root >= 0 && s->d.n_lights > 0;
     if (kind == 6 && !wavefront) kind = 0;   // rayTraceRecursive(ray, 0) / 0: no bounce level to run
-    if (kind == 0) kind = lc_ok ? 5 : (s->d.n_meshes > 0 || s->d.abvh_root >= 0) ? 3 : 1;   // measured: profiles/r01_notes.md
+    // automatic choice below the wavefront's threshold (measured, profiles/r01_notes.md): the state machine over the exact
+    // culling hierarchies (3) for anything with meshes - the pond scene: 73 ms against 78 for the light-cone kernel (5),
+    // which is only run when asked for - and one path per lane (1) for a handful of analytic primitives
+    if (kind == 0) kind = (s->d.n_meshes > 0 || s->d.abvh_root >= 0) ? 3 : 1;
     if (kind == 5 && !lc_ok) kind = 3;
     const bool regen = kind >= 2, accel = kind >= 3, voted = kind == 4, lc = kind == 5;
     typedef void (*RenderKernel)(const DScene, const DCamera, const RenderArgs);

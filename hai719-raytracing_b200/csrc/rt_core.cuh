@@ -91,9 +91,11 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #define RT_POPC(x) __popc(x)
 #define RT_FFS(x) __ffs(x)
 #define RT_FAST_RCP(x) __fdividef(1.f, (x))   /* 2-ulp reciprocal: only used where a 1e-5 relative margin follows */
+#define RT_FMA(a, b, c) __fmaf_rn((a), (b), (c))   /* explicit: the build runs with -fmad=false; only in the conservative filters */
 #else   /* one lane */
 #define RT_FFS(x) __builtin_ffs(x)
 #define RT_FAST_RCP(x) (1.f / (x))
+#define RT_FMA(a, b, c) fmaf((a), (b), (c))
 #define RT_WARP_ALL(pred) (pred)
 #define RT_BALLOT(pred) ((pred) ? 1u : 0u)
 #define RT_POPC(x) ((int)((x) != 0u))
@@ -501,16 +503,49 @@ RT_COLD uint32_t tri_last_reachable(const DScene &s, const Ray &ray, float t, ui
     return last;
 }
 
-struct Inv32 { float x, y, z; };
+// Box tests of the culling hierarchies as one FMA per plane: (l - o) * iv  ==  l * iv - o * iv with o * iv rounded once per
+// ray (RT_OPT_BOXFMA). The planes then carry an ABSOLUTE error of up to 2^-24 |o * iv| (rounding of the product) next to
+// the relative one of the FMA itself, so the per-ray slack constant grows by 2^-22 max_axis |o * iv| (4x that bound). A ray
+// almost parallel to an axis (|d| < 1e-6) thereby loses its culling - it visits more boxes, never fewer: the hierarchies
+// only filter. 6 instructions fewer per box of ~32. Measured on B200 (profiles/r01_notes.md, r01t): config 3 -2 %, configs 2,
+// 4 and 5 +0.7 % (a few more spill bytes; the walks wait on loads, not on issue slots) - OFF.
+#ifndef RT_OPT_BOXFMA
+#define RT_OPT_BOXFMA 0
+#endif
+struct Inv32 {
+    float x, y, z;
+#if RT_OPT_BOXFMA
+    float ox, oy, oz;   // o * iv
+    float e;            // additive slack: 1e-6 + 2^-22 max |o * iv|
+#endif
+};
 RT_HD float safe_inv(float d) { return fabsf(d) > 1e-30f ? RT_FAST_RCP(d) : (d < 0.f ? -1e30f : 1e30f); }
+RT_HD Inv32 make_inv32(const Ray &r) {
+    Inv32 iv; iv.x = safe_inv(r.d.x); iv.y = safe_inv(r.d.y); iv.z = safe_inv(r.d.z);
+#if RT_OPT_BOXFMA
+    iv.ox = r.o.x * iv.x; iv.oy = r.o.y * iv.y; iv.oz = r.o.z * iv.z;
+    iv.e = 2.4e-7f * fmaxf(fmaxf(fabsf(iv.ox), fabsf(iv.oy)), fabsf(iv.oz)) + 1e-6f;
+#endif
+    return iv;
+}
 // conservative ray/box overlap on [0, limit]; returns the entry parameter through `near`
 RT_HD bool bvh_box(const Ray &r, const Inv32 &iv, float lx, float ly, float lz, float hx, float hy, float hz, float limit, float &near) {
+#if RT_OPT_BOXFMA
+    const float a0 = RT_FMA(lx, iv.x, -iv.ox), a1 = RT_FMA(hx, iv.x, -iv.ox);
+    const float b0 = RT_FMA(ly, iv.y, -iv.oy), b1 = RT_FMA(hy, iv.y, -iv.oy);
+    const float c0 = RT_FMA(lz, iv.z, -iv.oz), c1 = RT_FMA(hz, iv.z, -iv.oz);
+#else
     const float a0 = (lx - r.o.x) * iv.x, a1 = (hx - r.o.x) * iv.x;
     const float b0 = (ly - r.o.y) * iv.y, b1 = (hy - r.o.y) * iv.y;
     const float c0 = (lz - r.o.z) * iv.z, c1 = (hz - r.o.z) * iv.z;
+#endif
     const float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fminf(c0, c1));
     const float tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fmaxf(c0, c1));
+#if RT_OPT_BOXFMA
+    const float slack = RT_FMA(1e-5f, fabsf(tn) + fabsf(tf), iv.e);
+#else
     const float slack = 1e-5f * (fabsf(tn) + fabsf(tf)) + 1e-6f;
+#endif
     near = tn;
     return (tn - slack <= tf + slack) && (tf + slack >= 0.f) && (tn - slack <= limit);
 }
@@ -572,7 +607,7 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
         RT_ANYHIT_STEP()
     }
     if (m.bvh_root >= 0) {
-        Inv32 iv; iv.x = safe_inv(ray.d.x); iv.y = safe_inv(ray.d.y); iv.z = safe_inv(ray.d.z);
+        const Inv32 iv = make_inv32(ray);
         int stack[64];
         int sp = 0;
         int node = m.bvh_root;
@@ -676,7 +711,7 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
     if (done || s.n_meshes <= 0) return;
     const uint32_t NONE = 0xFFFFFFFFu;
     const int MESH_END = 0x7FFFFFFD;
-    Inv32 iv; iv.x = safe_inv(ray.d.x); iv.y = safe_inv(ray.d.y); iv.z = safe_inv(ray.d.z);
+    const Inv32 iv = make_inv32(ray);
     int stack[64];
     int sp = 0, mi = 0;
     // the always-tested triangles of a mesh come first, like a leaf
@@ -717,7 +752,7 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
 // call so a closest-hit caller can shrink it.
 template <bool STATS, class F>
 RT_HD void analytic_candidates(const DScene &s, const Ray &ray, const float &limit, F &&f, Counters *cnt) {
-    Inv32 iv; iv.x = safe_inv(ray.d.x); iv.y = safe_inv(ray.d.y); iv.z = safe_inv(ray.d.z);
+    const Inv32 iv = make_inv32(ray);
     // per-ray enlargement (see build_analytic_accel): quadratic term x 1/r of the spheres below, plus a linear term
     const float dist = length(ray.o - ld3(s.abvh_c)) + s.abvh_r;
     const float kq = 32.f * 5.96e-8f * dist * dist, kl = 64.f * 5.96e-8f * dist;
@@ -1263,7 +1298,7 @@ RT_HD void intersect_ray_voted(const DScene &s, const Ray &ray, int mode, float 
             }
         }
     }
-    Inv32 iv; iv.x = safe_inv(ray.d.x); iv.y = safe_inv(ray.d.y); iv.z = safe_inv(ray.d.z);
+    const Inv32 iv = make_inv32(ray);
     float kq = 0.f, kl = 0.f;          // per-ray box enlargement, analytic phase only (build_analytic_accel)
     int phase = -1;                    // -1: analytic hierarchy; m >= 0: mesh m
     int node = EMPTY, sp = 0;
@@ -1395,8 +1430,15 @@ RT_HD void intersect_ray_voted(const DScene &s, const Ray &ray, int mode, float 
 // Each inequality bounds s from below or above depending on the sign of its coefficient; with
 // delta = 0 it is the ordinary slab test, so closest-hit rays (mode 0) and cones (mode 3) run the
 // same instructions side by side.
+#ifndef RT_OPT_CONEFMA
+#define RT_OPT_CONEFMA 0   /* the same FMA form as bvh_box (RT_OPT_BOXFMA) for the cone: 7 more live registers per lane */
+#endif
 struct Cone {
     V3 o;
+#if RT_OPT_CONEFMA
+    float oax, oay, oaz, obx, oby, obz;   // o / (D + delta), o / (D - delta)
+    float e;                              // additive slack: 1e-6 + 2^-22 max |o * i|
+#endif
     float iax, iay, iaz;    // 1 / (D + delta)
     float ibx, iby, ibz;    // 1 / (D - delta)
     bool nnx, nny, nnz;     // both coefficients negative: the upper face bounds s from below
@@ -1413,11 +1455,21 @@ RT_HD Cone make_cone(V3 o, V3 D, float delta) {
     cone_axis(D.x, delta, c.iax, c.ibx, c.nnx, c.pnx);
     cone_axis(D.y, delta, c.iay, c.iby, c.nny, c.pny);
     cone_axis(D.z, delta, c.iaz, c.ibz, c.nnz, c.pnz);
+#if RT_OPT_CONEFMA
+    c.oax = o.x * c.iax; c.oay = o.y * c.iay; c.oaz = o.z * c.iaz;
+    c.obx = o.x * c.ibx; c.oby = o.y * c.iby; c.obz = o.z * c.ibz;
+    c.e = 2.4e-7f * fmaxf(fmaxf(fmaxf(fabsf(c.oax), fabsf(c.oay)), fmaxf(fabsf(c.oaz), fabsf(c.obx))), fmaxf(fabsf(c.oby), fabsf(c.obz))) + 1e-6f;
+#endif
     return c;
 }
-#define RT_CONE_AXIS(LO, HI, O, IA, IB, NN, PN, TN, TF)                    \
+#if RT_OPT_CONEFMA
+#define RT_CONE_PLANES(LO, HI, O, IA, IB, OA, OB) const float x0 = RT_FMA((LO), (IA), -(OA)), x1 = RT_FMA((HI), (IB), -(OB));
+#else
+#define RT_CONE_PLANES(LO, HI, O, IA, IB, OA, OB) const float x0 = ((LO) - (O)) * (IA), x1 = ((HI) - (O)) * (IB);
+#endif
+#define RT_CONE_AXIS(LO, HI, O, IA, IB, OA, OB, NN, PN, TN, TF)            \
     {                                                                      \
-        const float x0 = ((LO) - (O)) * (IA), x1 = ((HI) - (O)) * (IB);    \
+        RT_CONE_PLANES(LO, HI, O, IA, IB, OA, OB)                          \
         const float un = (NN) ? x1 : x0, uf = (NN) ? x0 : x1;              \
         TN = (PN) ? fmaxf(un, uf) : un;                                    \
         TF = (PN) ? FLT_MAX : uf;                                          \
@@ -1425,12 +1477,22 @@ RT_HD Cone make_cone(V3 o, V3 D, float delta) {
 // conservative cone/box overlap for s in [0, limit]; `near` = entry parameter (child ordering only)
 RT_HD bool cone_box(const Cone &c, float lx, float ly, float lz, float hx, float hy, float hz, float limit, float &near) {
     float tnx, tfx, tny, tfy, tnz, tfz;
-    RT_CONE_AXIS(lx, hx, c.o.x, c.iax, c.ibx, c.nnx, c.pnx, tnx, tfx)
-    RT_CONE_AXIS(ly, hy, c.o.y, c.iay, c.iby, c.nny, c.pny, tny, tfy)
-    RT_CONE_AXIS(lz, hz, c.o.z, c.iaz, c.ibz, c.nnz, c.pnz, tnz, tfz)
+#if RT_OPT_CONEFMA
+    RT_CONE_AXIS(lx, hx, c.o.x, c.iax, c.ibx, c.oax, c.obx, c.nnx, c.pnx, tnx, tfx)
+    RT_CONE_AXIS(ly, hy, c.o.y, c.iay, c.iby, c.oay, c.oby, c.nny, c.pny, tny, tfy)
+    RT_CONE_AXIS(lz, hz, c.o.z, c.iaz, c.ibz, c.oaz, c.obz, c.nnz, c.pnz, tnz, tfz)
+#else
+    RT_CONE_AXIS(lx, hx, c.o.x, c.iax, c.ibx, 0.f, 0.f, c.nnx, c.pnx, tnx, tfx)
+    RT_CONE_AXIS(ly, hy, c.o.y, c.iay, c.iby, 0.f, 0.f, c.nny, c.pny, tny, tfy)
+    RT_CONE_AXIS(lz, hz, c.o.z, c.iaz, c.ibz, 0.f, 0.f, c.nnz, c.pnz, tnz, tfz)
+#endif
     const float tn = fmaxf(fmaxf(tnx, tny), tnz);
     const float tf = fminf(fminf(fminf(tfx, tfy), tfz), limit);
+#if RT_OPT_CONEFMA
+    const float slack = RT_FMA(1e-5f, fabsf(tn) + fabsf(tf), c.e);
+#else
     const float slack = 1e-5f * (fabsf(tn) + fabsf(tf)) + 1e-6f;
+#endif
     near = tn;
     return (tn - slack <= tf + slack) && (tf + slack >= 0.f);
 }

@@ -14,14 +14,13 @@ from conftest import ROOT
 SIM_DIR = os.path.join(ROOT, "tests", "hostsim")
 
 
-@pytest.fixture(scope="module")
-def sim(hb):
-    so = os.path.join(SIM_DIR, "libhostsim.so")
+def _load_sim(hb, so_name, defs):
+    so = os.path.join(SIM_DIR, so_name)
     src = os.path.join(SIM_DIR, "hostsim.cpp")
     core = os.path.join(ROOT, "hai719-raytracing_b200", "csrc", "rt_core.cuh")
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
         subprocess.check_call(["/usr/bin/g++", "-O3", "-fPIC", "-shared", "-std=c++17", "-I", os.path.join(ROOT, "include"),
-                               "-I", os.path.dirname(core), src, "-o", so, "-lpthread"])
+                               "-I", os.path.dirname(core)] + defs + [src, "-o", so, "-lpthread"])
     L = C.CDLL(so)
     L.sim_scene_create.restype = C.c_void_p
     L.sim_scene_create.argtypes = [C.POINTER(hb.RtSceneDesc)]
@@ -31,10 +30,19 @@ def sim(hb):
     return L
 
 
-@pytest.mark.parametrize("name", ["cornell_box", "random_spheres", "flamingo_pond", "backrooms_pool", "raccoon",
-                                  "rt_in_a_weekend", "flamingo_lake", "config5"])
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
-def test_core_functions_on_cpu_match_oracle(hb, ref, assets, sim, name, variant):
+@pytest.fixture(scope="module")
+def sim(hb):
+    return _load_sim(hb, "libhostsim.so", [])
+
+
+@pytest.fixture(scope="module")
+def sim_fma(hb):
+    """The same functions with the box tests of the culling hierarchies in their one-FMA-per-plane form
+    (RT_OPT_BOXFMA / RT_OPT_CONEFMA, off by default): a different conservative filter, so the same bits."""
+    return _load_sim(hb, "libhostsim_fma.so", ["-DRT_OPT_BOXFMA=1", "-DRT_OPT_CONEFMA=1"])
+
+
+def _check_against_oracle(hb, ref, sim, name, variant):
     W, H, SPP = 64, 36, 2
     a = ref.scene(name, aspect=W / H)
     want = a.render(W, H, SPP, seed=2, threads=0)
@@ -51,3 +59,16 @@ def test_core_functions_on_cpu_match_oracle(hb, ref, assets, sim, name, variant)
     assert np.array_equal(ids, want["ids"])
     assert np.array_equal(lin.view(np.uint32), want["linear"].view(np.uint32))
     assert np.array_equal(gam.view(np.uint32), want["gamma"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["random_spheres", "flamingo_pond", "backrooms_pool", "config5"])
+@pytest.mark.parametrize("variant", [3, 5, 6])
+def test_fma_box_tests_keep_the_bits(hb, ref, assets, sim_fma, name, variant):
+    _check_against_oracle(hb, ref, sim_fma, name, variant)
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "random_spheres", "flamingo_pond", "backrooms_pool", "raccoon",
+                                  "rt_in_a_weekend", "flamingo_lake", "config5"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+def test_core_functions_on_cpu_match_oracle(hb, ref, assets, sim, name, variant):
+    _check_against_oracle(hb, ref, sim, name, variant)

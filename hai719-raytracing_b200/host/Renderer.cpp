@@ -86,7 +86,9 @@ void ray_trace_from_camera_rgb8(const DeviceScene &scene, Camera &camera, int w,
     const auto t1 = std::chrono::steady_clock::now();
     if (opt.verbose) std::cout << "  Done in " << std::chrono::duration<double>(t1 - t0).count() << " seconds" << std::endl;
     if (!opt.ppm_path.empty()) {
-        const bool ok = opt.format == RenderOptions::P6 ? write_ppm_p6(opt.ppm_path, rw, rh, rgb8) : write_ppm_p3(opt.ppm_path, rw, rh, rgb8);
+        const bool ok = opt.format == RenderOptions::PNG  ? write_png(opt.ppm_path, rw, rh, rgb8)
+                        : opt.format == RenderOptions::P6 ? write_ppm_p6(opt.ppm_path, rw, rh, rgb8)
+                                                          : write_ppm_p3(opt.ppm_path, rw, rh, rgb8);
         if (!ok) std::cout << "Could not open file: " << opt.ppm_path << std::endl;
     }
 }
@@ -117,6 +119,89 @@ bool write_ppm_p6(const std::string &filename, int w, int h, const std::vector<u
     if (f.fail()) return false;
     f << "P6\n" << w << " " << h << "\n255\n";
     f.write(reinterpret_cast<const char *>(rgb8.data()), (std::streamsize)((size_t)w * (size_t)h * 3));
+    return !f.fail();
+}
+
+namespace {
+struct Crc32 {
+    uint32_t table[256];
+    Crc32() {
+        for (uint32_t n = 0; n < 256; ++n) {
+            uint32_t c = n;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[n] = c;
+        }
+    }
+    uint32_t update(uint32_t crc, const unsigned char *p, size_t n) const {
+        for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xFFu] ^ (crc >> 8);
+        return crc;
+    }
+};
+void put_be32(std::vector<unsigned char> &v, uint32_t x) {
+    v.push_back((unsigned char)(x >> 24)); v.push_back((unsigned char)(x >> 16)); v.push_back((unsigned char)(x >> 8)); v.push_back((unsigned char)x);
+}
+// one PNG chunk: length, type, data, CRC-32 over type + data
+void write_chunk(std::ofstream &f, const Crc32 &crc, const char type[4], const unsigned char *data, size_t n) {
+    std::vector<unsigned char> head;
+    put_be32(head, (uint32_t)n);
+    head.insert(head.end(), type, type + 4);
+    f.write(reinterpret_cast<const char *>(head.data()), 8);
+    if (n) f.write(reinterpret_cast<const char *>(data), (std::streamsize)n);
+    uint32_t c = crc.update(0xFFFFFFFFu, head.data() + 4, 4);
+    c = crc.update(c, data, n) ^ 0xFFFFFFFFu;
+    std::vector<unsigned char> tail;
+    put_be32(tail, c);
+    f.write(reinterpret_cast<const char *>(tail.data()), 4);
+}
+}  // namespace
+
+bool write_png(const std::string &filename, int w, int h, const std::vector<unsigned char> &rgb8) {
+    if (w <= 0 || h <= 0 || rgb8.size() < (size_t)w * (size_t)h * 3) return false;
+    std::ofstream f(filename.c_str(), std::ios::binary);
+    if (f.fail()) return false;
+    static const Crc32 crc;
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    f.write(reinterpret_cast<const char *>(sig), 8);
+    std::vector<unsigned char> ihdr;
+    put_be32(ihdr, (uint32_t)w);
+    put_be32(ihdr, (uint32_t)h);
+    const unsigned char rest[5] = {8, 2, 0, 0, 0};   // 8 bits per channel, truecolour, deflate, adaptive filtering, no interlace
+    ihdr.insert(ihdr.end(), rest, rest + 5);
+    write_chunk(f, crc, "IHDR", ihdr.data(), ihdr.size());
+    // zlib stream: 0x78 0x01, stored blocks of <= 65535 bytes over the filtered scanlines (a 0 byte + the row), Adler-32
+    const size_t row = (size_t)w * 3, raw_n = (row + 1) * (size_t)h;
+    std::vector<unsigned char> z;
+    z.reserve(raw_n + 5 * (raw_n / 65535 + 1) + 6);
+    z.push_back(0x78); z.push_back(0x01);
+    uint32_t a = 1u, b = 0u;                         // Adler-32, reduced often enough not to overflow
+    size_t in_block = 0, produced = 0;
+    auto open_block = [&](size_t len, bool last) {
+        z.push_back(last ? 1 : 0);
+        z.push_back((unsigned char)(len & 0xFF)); z.push_back((unsigned char)(len >> 8));
+        z.push_back((unsigned char)(~len & 0xFF)); z.push_back((unsigned char)((~len >> 8) & 0xFF));
+        in_block = len;
+    };
+    auto put = [&](const unsigned char *p, size_t n) {
+        while (n) {
+            if (in_block == 0) {
+                const size_t left = raw_n - produced, len = left < 65535 ? left : 65535;
+                open_block(len, len == left);
+            }
+            const size_t k = n < in_block ? n : in_block;
+            z.insert(z.end(), p, p + k);
+            for (size_t i = 0; i < k; ++i) { a += p[i]; b += a; if ((i & 2047u) == 2047u) { a %= 65521u; b %= 65521u; } }
+            a %= 65521u; b %= 65521u;
+            p += k; n -= k; in_block -= k; produced += k;
+        }
+    };
+    const unsigned char filter0 = 0;
+    for (int y = 0; y < h; ++y) { put(&filter0, 1); put(rgb8.data() + (size_t)y * row, row); }
+    put_be32(z, (b << 16) | a);
+    for (size_t off = 0; off < z.size(); off += (1u << 20)) {
+        const size_t n = z.size() - off < (1u << 20) ? z.size() - off : (1u << 20);
+        write_chunk(f, crc, "IDAT", z.data() + off, n);
+    }
+    write_chunk(f, crc, "IEND", nullptr, 0);
     return !f.fail();
 }
 

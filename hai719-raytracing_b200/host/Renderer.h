@@ -37,8 +37,9 @@ struct RenderOptions {
     std::string ppm_path = "./rendu.ppm";   // "" = do not write (the reference always writes)
     // Output stage. P3: the reference's ASCII file, byte for byte (main.cpp:252-262) — ~400 MB of text
     // at 8K. P6: the same 8-bit values as binary PPM, quantised on the GPU (rt_render_rgb8): 3 bytes per pixel
-    // cross PCIe and reach the file. The reference's own ppmLoader reads both.
-    enum Format { P3 = 0, P6 = 1 } format = P3;
+    // cross PCIe and reach the file. The reference's own ppmLoader reads both. PNG: the same bytes as 8-bit truecolour PNG
+    // (write_png below) for viewers that do not read PPM.
+    enum Format { P3 = 0, P6 = 1, PNG = 2 } format = P3;
     bool verbose = true;                    // the reference's two std::cout lines
 };
 
@@ -74,6 +75,10 @@ bool write_ppm_p3(const std::string &filename, int w, int h, const std::vector<V
 bool write_ppm_p3(const std::string &filename, int w, int h, const std::vector<unsigned char> &rgb8);
 // Binary PPM: "P6\n w h\n255\n" + w*h*3 bytes.
 bool write_ppm_p6(const std::string &filename, int w, int h, const std::vector<unsigned char> &rgb8);
+// 8-bit RGB PNG of the same bytes, self-contained: IHDR, IDAT chunks of at most 1 MiB holding a zlib
+// stream of STORED deflate blocks (filter type 0 on every row; no compression library in the image, and the renders are
+// noise-like anyway), IEND; CRC-32 and Adler-32 computed here. Any PNG reader decodes it to exactly rgb8.
+bool write_png(const std::string &filename, int w, int h, const std::vector<unsigned char> &rgb8);
 
 // Render straight to 8-bit RGB (rect_h*rect_w*3, row 0 = top): quantisation on the device, see rt_render_rgb8().
 void ray_trace_from_camera_rgb8(const DeviceScene &scene, Camera &camera, int w, int h, unsigned int nsamples,

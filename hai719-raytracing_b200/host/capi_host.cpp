@@ -171,11 +171,22 @@ int hai_ray_trace_from_camera_rgb8(HaiScene *s, int device, int w, int h, int ns
         opt.seed = seed;
         opt.device = device;
         opt.ppm_path = ppm_path ? ppm_path : "";
-        opt.format = p6 ? hai719::RenderOptions::P6 : hai719::RenderOptions::P3;
+        opt.format = p6 == 2 ? hai719::RenderOptions::PNG : p6 ? hai719::RenderOptions::P6 : hai719::RenderOptions::P3;
         opt.verbose = false;
         std::vector<unsigned char> bytes;
         hai719::ray_trace_from_camera_rgb8(*s->on_device[device], camera, w, h, (unsigned)nsamples, bytes, opt);
         if (rgb8) std::memcpy(rgb8, bytes.data(), bytes.size());
+    });
+}
+
+int hai_write_image_rgb8(const char *path, int format, int w, int h, const uint8_t *rgb8) {
+    return guarded([&] {
+        if (!path || !rgb8 || w <= 0 || h <= 0) throw std::runtime_error("hai_write_image_rgb8: bad argument");
+        const std::vector<unsigned char> bytes(rgb8, rgb8 + (size_t)w * (size_t)h * 3);
+        const bool ok = format == 2 ? hai719::write_png(path, w, h, bytes)
+                        : format == 1 ? hai719::write_ppm_p6(path, w, h, bytes)
+                        : format == 0 ? hai719::write_ppm_p3(path, w, h, bytes) : false;
+        if (!ok) throw std::runtime_error(std::string("hai_write_image_rgb8: could not write ") + path);
     });
 }
 

@@ -1,7 +1,7 @@
 // hai719_render — the headless stand-in for "press r" in the reference's GLUT shell
 // (main.cpp:321-326 -> ray_trace_from_camera). Builds one of the reference's scenes with the host
 // API, renders it on the GPU and writes the same P3 rendu.ppm.
-//   hai719_render [--scene N | --scene-file FILE] [--w W --h H] [--spp S] [--seed K] [--assets DIR] [--out FILE] [--p6 1] [--device D]
+//   hai719_render [--scene N | --scene-file FILE] [--w W --h H] [--spp S] [--seed K] [--assets DIR] [--out FILE] [--p6 1 | --png 1] [--device D]
 //                 [--preview PASSES [--orbit PIXELS]]
 // --preview: progressive refinement instead of one render (host/Preview.h): PASSES passes of --spp samples each, every
 // intermediate frame written as <out>.<pass>.ppm (binary); with --orbit the left mouse button is "dragged" PIXELS to
@@ -21,7 +21,7 @@ int main(int argc, char **argv) {
     int scene_id = DEFAULT_SELECTED_SCENE, w = 850, h = 480, spp = DEFAULT_NSAMPLES, device = 0;
     unsigned int seed = 0;
     std::string assets, out = "./rendu.ppm", scene_file;
-    bool p6 = false;
+    bool p6 = false, png = false;
     int preview = 0, orbit = 0;
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string k = argv[i];
@@ -36,6 +36,7 @@ int main(int argc, char **argv) {
         else if (k == "--device") device = std::atoi(v);
         else if (k == "--scene-file") scene_file = v;
         else if (k == "--p6") p6 = std::atoi(v) != 0;
+        else if (k == "--png") png = std::atoi(v) != 0;
         else if (k == "--preview") preview = std::atoi(v);
         else if (k == "--orbit") orbit = std::atoi(v);
         else { std::cerr << "unknown option " << k << std::endl; return 2; }
@@ -72,8 +73,8 @@ int main(int argc, char **argv) {
                     pv.mouse(hai719::Preview::Left, hai719::Preview::Up, w / 2 + orbit, h / 2);
                 }
             }
-        } else if (p6) {   // output stage on the GPU: 8-bit quantise on the device, binary PPM
-            opt.format = hai719::RenderOptions::P6;
+        } else if (p6 || png) {   // output stage on the GPU: 8-bit quantise on the device, binary PPM or PNG
+            opt.format = png ? hai719::RenderOptions::PNG : hai719::RenderOptions::P6;
             hai719::DeviceScene dev(scene, device);
             std::vector<unsigned char> rgb8;
             hai719::ray_trace_from_camera_rgb8(dev, camera, w, h, (unsigned int)spp, rgb8, opt);

@@ -66,9 +66,15 @@ int hai_ray_trace_from_camera(HaiScene *s, int device, int w, int h, int nsample
                               float *gamma_rgb);
 
 /* The same with the output stage on the GPU: 8-bit RGB (h*w*3 bytes, row 0 = top) = the values the reference
- * writes to rendu.ppm. ppm_path (may be NULL): written as binary P6 when p6 != 0, else as the reference's P3 text. */
+ * writes to rendu.ppm. ppm_path (may be NULL): the reference's P3 text when p6 == 0, 8-bit RGB PNG when p6 == 2,
+ * binary P6 for any other value. */
 int hai_ray_trace_from_camera_rgb8(HaiScene *s, int device, int w, int h, int nsamples, uint32_t seed, const char *ppm_path,
                                    int p6, uint8_t *rgb8);
+
+/* The output stage on its own (replaces the file loop of main.cpp:252-262 for bytes that are already
+ * quantised): h*w*3 bytes, row 0 = top, written as format 0 = P3 text (the reference's file, byte for byte),
+ * 1 = binary P6, 2 = 8-bit RGB PNG (stored deflate blocks, no library). Host only, no GPU involved. */
+int hai_write_image_rgb8(const char *path, int format, int w, int h, const uint8_t *rgb8);
 
 /* Interactive preview (host/Preview.h): the reference's mouse handlers (main.cpp:344-388; button 0
  * left = rotate, 1 middle = zoom, 2 right = move; state 0 down, 1 up) drive a Camera placed like main.cpp:418, and

@@ -221,6 +221,55 @@ def test_loaders_handle_format_variants(hb, tmp_path):
     assert s.flatten().contents.skybox.w == 0
 
 
+def _png_decode(data):
+    """Minimal PNG reader for the test: checks signature and every chunk CRC, inflates the IDAT stream with zlib."""
+    import struct
+    import zlib
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, chunks = 8, []
+    while pos < len(data):
+        n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        (crc,) = struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])
+        assert crc == zlib.crc32(typ + body) & 0xFFFFFFFF, typ
+        chunks.append((typ, body))
+        pos += 12 + n
+    assert chunks[0][0] == b"IHDR" and chunks[-1] == (b"IEND", b"")
+    w, h, depth, colour, comp, filt, lace = struct.unpack(">IIBBBBB", chunks[0][1])
+    assert (depth, colour, comp, filt, lace) == (8, 2, 0, 0, 0)
+    idat = [b for t, b in chunks if t == b"IDAT"]
+    assert all(len(b) <= 1 << 20 for b in idat)
+    raw = np.frombuffer(zlib.decompress(b"".join(idat)), np.uint8).reshape(h, 1 + 3 * w)
+    assert not raw[:, 0].any()      # filter type 0 on every row
+    return raw[:, 1:].reshape(h, w, 3), len(idat)
+
+
+@pytest.mark.parametrize("wh", [(1, 1), (5, 3), (213, 103), (700, 520)])
+def test_output_stage_writes_png_p6_and_p3(hb, tmp_path, wh):
+    """the same 8-bit values as PNG (stored blocks: sizes below and above one 65535-byte block and one
+    1 MiB IDAT chunk), binary P6, and the reference's P3 text (main.cpp:252-262)."""
+    w, h = wh
+    rgb = np.random.default_rng(w * 1000 + h).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    png = tmp_path / "a.png"
+    hb.write_image_rgb8(png, rgb, "png")
+    back, n_idat = _png_decode(png.read_bytes())
+    assert np.array_equal(back, rgb)
+    assert n_idat == (2 if w * h * 3 > (1 << 20) else 1)
+    try:
+        from PIL import Image
+        assert np.array_equal(np.asarray(Image.open(png).convert("RGB")), rgb)
+    except ImportError:
+        pass
+    p6 = tmp_path / "a.ppm"
+    hb.write_image_rgb8(p6, rgb, "p6")
+    assert p6.read_bytes() == b"P6\n%d %d\n255\n" % (w, h) + rgb.tobytes()
+    p3 = tmp_path / "b.ppm"
+    hb.write_image_rgb8(p3, rgb, "p3")
+    assert p3.read_bytes() == b"P3\n%d %d\n255\n" % (w, h) + b"".join(b"%d " % v for v in rgb.ravel()) + b"\n"
+    with pytest.raises(hb.RtError):
+        hb.write_image_rgb8(tmp_path / "no_such_dir" / "a.png", rgb, "png")
+
+
 def test_preview_and_accumulator_need_a_device_too(hb, assets):
     """SURVEY 8(f)-4 entry points: same rule, no device - an error with a text, never a CPU render."""
     if hb.device_count() > 0:

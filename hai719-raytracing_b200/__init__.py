@@ -121,7 +121,7 @@ RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_cr
               "rt_trace_primary", "rt_trace_rays", "rt_shade_rays", "rt_measure_fp32_peak"]
 HOST_SYMBOLS = ["hai_last_error", "hai_scene_new", "hai_scene_free", "hai_scene_setup", "hai_scene_dump",
                 "hai_scene_flatten", "hai_scene_kd_stats", "hai_scene_counts", "hai_default_camera", "hai_render",
-                "hai_scene_device", "hai_scene_invalidate_device", "hai_scene_move_sphere", "hai_scene_update_device", "hai_scene_load_file", "hai_ray_trace_from_camera", "hai_ray_trace_from_camera_rgb8", "hai_write_image_rgb8",
+                "hai_scene_device", "hai_scene_invalidate_device", "hai_scene_move_sphere", "hai_scene_update_device", "hai_scene_load_file", "hai_ray_trace_from_camera", "hai_ray_trace_from_camera_rgb8", "hai_write_image_rgb8", "hai_write_exr",
                 "hai_preview_new", "hai_preview_free", "hai_preview_mouse", "hai_preview_motion", "hai_preview_resize", "hai_preview_invalidate",
                 "hai_preview_pass", "hai_preview_frame", "hai_preview_camera"]
 
@@ -198,6 +198,7 @@ host.hai_scene_update_device.argtypes = [C.c_void_p]
 host.hai_ray_trace_from_camera_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
                                                 C.c_int, C.c_void_p]
 host.hai_write_image_rgb8.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+host.hai_write_exr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
 
 
 def _rt_check(rc):
@@ -214,6 +215,14 @@ def write_image_rgb8(path, rgb8, fmt="png"):
     if a.ndim != 3 or a.shape[2] != 3:
         raise ValueError("rgb8 must be h x w x 3")
     _host_check(host.hai_write_image_rgb8(str(path).encode(), IMAGE_FORMATS[fmt], a.shape[1], a.shape[0], a.ctypes.data))
+
+
+def write_exr(path, rgb):
+    """h x w x 3 float32 -> uncompressed scanline OpenEXR (host, no GPU)."""
+    a = np.ascontiguousarray(rgb, dtype=np.float32)
+    if a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError("rgb must be h x w x 3")
+    _host_check(host.hai_write_exr(str(path).encode(), a.shape[1], a.shape[0], a.ctypes.data))
 
 
 def _host_check(rc):

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 
@@ -54,9 +55,14 @@ void ray_trace_from_camera(const DeviceScene &scene, Camera &camera, int w, int 
     image.assign((size_t)rw * (size_t)rh, Vec3(0, 0, 0));
     static_assert(sizeof(Vec3) == 3 * sizeof(float), "Vec3 must be three packed floats");
     const auto t0 = std::chrono::steady_clock::now();
-    check(rt_render(scene.handle(), &cam, &p, reinterpret_cast<float *>(image.data()), nullptr, stats), "rt_render");
+    std::vector<float> linear;
+    if (!opt.exr_path.empty()) linear.assign((size_t)rw * (size_t)rh * 3, 0.f);
+    check(rt_render(scene.handle(), &cam, &p, reinterpret_cast<float *>(image.data()), linear.empty() ? nullptr : linear.data(), stats),
+          "rt_render");
     const auto t1 = std::chrono::steady_clock::now();
     if (opt.verbose) std::cout << "  Done in " << std::chrono::duration<double>(t1 - t0).count() << " seconds" << std::endl;
+    if (!opt.exr_path.empty() && !write_exr(opt.exr_path, rw, rh, linear.data()))
+        std::cout << "Could not open file: " << opt.exr_path << std::endl;
     if (!opt.ppm_path.empty() && !write_ppm_p3(opt.ppm_path, rw, rh, image))
         std::cout << "Could not open file: " << opt.ppm_path << std::endl;
 }
@@ -202,6 +208,77 @@ bool write_png(const std::string &filename, int w, int h, const std::vector<unsi
         write_chunk(f, crc, "IDAT", z.data() + off, n);
     }
     write_chunk(f, crc, "IEND", nullptr, 0);
+    return !f.fail();
+}
+
+namespace {
+void put_le32(std::vector<unsigned char> &v, uint32_t x) {
+    for (int i = 0; i < 4; ++i) v.push_back((unsigned char)(x >> (8 * i)));
+}
+void put_le64(std::vector<unsigned char> &v, uint64_t x) {
+    for (int i = 0; i < 8; ++i) v.push_back((unsigned char)(x >> (8 * i)));
+}
+void put_f32(std::vector<unsigned char> &v, float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    put_le32(v, u);
+}
+void put_str(std::vector<unsigned char> &v, const char *s) {
+    for (; *s; ++s) v.push_back((unsigned char)*s);
+    v.push_back(0);
+}
+// attribute: name, type, byte size, then the value appended by the caller
+void put_attr(std::vector<unsigned char> &v, const char *name, const char *type, uint32_t size) {
+    put_str(v, name);
+    put_str(v, type);
+    put_le32(v, size);
+}
+}  // namespace
+
+bool write_exr(const std::string &filename, int w, int h, const float *rgb) {
+    if (w <= 0 || h <= 0 || !rgb) return false;
+    std::ofstream f(filename.c_str(), std::ios::binary);
+    if (f.fail()) return false;
+    std::vector<unsigned char> head;
+    put_le32(head, 20000630u);   // magic 0x76 0x2f 0x31 0x01
+    put_le32(head, 2u);          // version 2, single-part scanline, short names
+    put_attr(head, "channels", "chlist", 3 * 18 + 1);
+    for (const char *c : {"B", "G", "R"}) {
+        put_str(head, c);
+        put_le32(head, 2u);                                   // FLOAT
+        head.push_back(0); head.push_back(0); head.push_back(0); head.push_back(0);   // pLinear + 3 reserved bytes
+        put_le32(head, 1u); put_le32(head, 1u);               // x / y sampling
+    }
+    head.push_back(0);
+    put_attr(head, "compression", "compression", 1); head.push_back(0);   // NO_COMPRESSION: one scanline per block
+    for (const char *name : {"dataWindow", "displayWindow"}) {
+        put_attr(head, name, "box2i", 16);
+        put_le32(head, 0u); put_le32(head, 0u); put_le32(head, (uint32_t)(w - 1)); put_le32(head, (uint32_t)(h - 1));
+    }
+    put_attr(head, "lineOrder", "lineOrder", 1); head.push_back(0);       // increasing y
+    put_attr(head, "pixelAspectRatio", "float", 4); put_f32(head, 1.f);
+    put_attr(head, "screenWindowCenter", "v2f", 8); put_f32(head, 0.f); put_f32(head, 0.f);
+    put_attr(head, "screenWindowWidth", "float", 4); put_f32(head, 1.f);
+    head.push_back(0);           // end of header
+    const uint64_t row_bytes = (uint64_t)w * 12u, block = 8u + row_bytes;
+    const uint64_t first = head.size() + 8u * (uint64_t)h;
+    for (int y = 0; y < h; ++y) put_le64(head, first + (uint64_t)y * block);
+    f.write(reinterpret_cast<const char *>(head.data()), (std::streamsize)head.size());
+    std::vector<unsigned char> line;
+    std::vector<float> planar((size_t)w * 3);
+    for (int y = 0; y < h; ++y) {
+        line.clear();
+        put_le32(line, (uint32_t)y);
+        put_le32(line, (uint32_t)row_bytes);
+        f.write(reinterpret_cast<const char *>(line.data()), 8);
+        const float *src = rgb + (size_t)y * (size_t)w * 3;
+        for (int x = 0; x < w; ++x) {
+            planar[x] = src[3 * x + 2];                       // B
+            planar[(size_t)w + x] = src[3 * x + 1];           // G
+            planar[2 * (size_t)w + x] = src[3 * x];           // R
+        }
+        f.write(reinterpret_cast<const char *>(planar.data()), (std::streamsize)row_bytes);   // little-endian host
+    }
     return !f.fail();
 }
 

@@ -40,6 +40,8 @@ struct RenderOptions {
     // cross PCIe and reach the file. The reference's own ppmLoader reads both. PNG: the same bytes as 8-bit truecolour PNG
     // (write_png below) for viewers that do not read PPM.
     enum Format { P3 = 0, P6 = 1, PNG = 2 } format = P3;
+    // Float render only: also write the LINEAR image (sum / nsamples, before gamma_correct) as OpenEXR (write_exr below).
+    std::string exr_path;
     bool verbose = true;                    // the reference's two std::cout lines
 };
 
@@ -79,6 +81,9 @@ bool write_ppm_p6(const std::string &filename, int w, int h, const std::vector<u
 // stream of STORED deflate blocks (filter type 0 on every row; no compression library in the image, and the renders are
 // noise-like anyway), IEND; CRC-32 and Adler-32 computed here. Any PNG reader decodes it to exactly rgb8.
 bool write_png(const std::string &filename, int w, int h, const std::vector<unsigned char> &rgb8);
+// Lossless fp32 output: single-part scanline OpenEXR 2, no compression, three FLOAT channels B, G, R (the
+// file stores channels in alphabetical order), data window = display window = the image. rgb: h*w*3 floats, row 0 = top.
+bool write_exr(const std::string &filename, int w, int h, const float *rgb);
 
 // Render straight to 8-bit RGB (rect_h*rect_w*3, row 0 = top): quantisation on the device, see rt_render_rgb8().
 void ray_trace_from_camera_rgb8(const DeviceScene &scene, Camera &camera, int w, int h, unsigned int nsamples,

@@ -190,6 +190,13 @@ int hai_write_image_rgb8(const char *path, int format, int w, int h, const uint8
     });
 }
 
+int hai_write_exr(const char *path, int w, int h, const float *rgb) {
+    return guarded([&] {
+        if (!path || !rgb || w <= 0 || h <= 0) throw std::runtime_error("hai_write_exr: bad argument");
+        if (!hai719::write_exr(path, w, h, rgb)) throw std::runtime_error(std::string("hai_write_exr: could not write ") + path);
+    });
+}
+
 // ---- interactive preview (host/Preview.h) ----------------------------------------------------------
 struct HaiPreview {
     Camera camera;

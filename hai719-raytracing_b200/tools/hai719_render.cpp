@@ -1,7 +1,7 @@
 // hai719_render — the headless stand-in for "press r" in the reference's GLUT shell
 // (main.cpp:321-326 -> ray_trace_from_camera). Builds one of the reference's scenes with the host
 // API, renders it on the GPU and writes the same P3 rendu.ppm.
-//   hai719_render [--scene N | --scene-file FILE] [--w W --h H] [--spp S] [--seed K] [--assets DIR] [--out FILE] [--p6 1 | --png 1] [--device D]
+//   hai719_render [--scene N | --scene-file FILE] [--w W --h H] [--spp S] [--seed K] [--assets DIR] [--out FILE] [--p6 1 | --png 1] [--exr FILE] [--device D]
 //                 [--preview PASSES [--orbit PIXELS]]
 // --preview: progressive refinement instead of one render (host/Preview.h): PASSES passes of --spp samples each, every
 // intermediate frame written as <out>.<pass>.ppm (binary); with --orbit the left mouse button is "dragged" PIXELS to
@@ -22,6 +22,7 @@ int main(int argc, char **argv) {
     unsigned int seed = 0;
     std::string assets, out = "./rendu.ppm", scene_file;
     bool p6 = false, png = false;
+    std::string exr;   // float render: also write the linear image as OpenEXR
     int preview = 0, orbit = 0;
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string k = argv[i];
@@ -37,6 +38,7 @@ int main(int argc, char **argv) {
         else if (k == "--scene-file") scene_file = v;
         else if (k == "--p6") p6 = std::atoi(v) != 0;
         else if (k == "--png") png = std::atoi(v) != 0;
+        else if (k == "--exr") exr = v;
         else if (k == "--preview") preview = std::atoi(v);
         else if (k == "--orbit") orbit = std::atoi(v);
         else { std::cerr << "unknown option " << k << std::endl; return 2; }
@@ -55,6 +57,7 @@ int main(int argc, char **argv) {
     opt.seed = seed;
     opt.device = device;
     opt.ppm_path = out;
+    opt.exr_path = exr;
     std::vector<Vec3> image;
     try {
         if (preview > 0) {

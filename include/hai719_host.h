@@ -75,6 +75,9 @@ int hai_ray_trace_from_camera_rgb8(HaiScene *s, int device, int w, int h, int ns
  * quantised): h*w*3 bytes, row 0 = top, written as format 0 = P3 text (the reference's file, byte for byte),
  * 1 = binary P6, 2 = 8-bit RGB PNG (stored deflate blocks, no library). Host only, no GPU involved. */
 int hai_write_image_rgb8(const char *path, int format, int w, int h, const uint8_t *rgb8);
+/* Lossless fp32 output: h*w*3 floats (row 0 = top; e.g. the linear_rgb of rt_render) as an uncompressed scanline
+ * OpenEXR file with FLOAT channels B, G, R. Host only. */
+int hai_write_exr(const char *path, int w, int h, const float *rgb);
 
 /* Interactive preview (host/Preview.h): the reference's mouse handlers (main.cpp:344-388; button 0
  * left = rotate, 1 middle = zoom, 2 right = move; state 0 down, 1 up) drive a Camera placed like main.cpp:418, and

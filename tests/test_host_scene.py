@@ -270,6 +270,52 @@ def test_output_stage_writes_png_p6_and_p3(hb, tmp_path, wh):
         hb.write_image_rgb8(tmp_path / "no_such_dir" / "a.png", rgb, "png")
 
 
+@pytest.mark.parametrize("wh", [(1, 1), (7, 5), (213, 103)])
+def test_exr_writer_round_trips_floats(hb, tmp_path, wh):
+    """lossless fp32 output. The file is parsed here by the published layout (magic, attributes, offset
+    table, one scanline per block, channels B G R) and, where OpenCV was built with OpenEXR, read back with it."""
+    import struct
+    w, h = wh
+    rng = np.random.default_rng(w + h)
+    rgb = (rng.standard_normal((h, w, 3)) * 10.0 ** rng.integers(-6, 6, (h, w, 3))).astype(np.float32)
+    rgb[0, 0] = (0.0, 1.0, 65504.0)
+    path = tmp_path / "a.exr"
+    hb.write_exr(path, rgb)
+    d = path.read_bytes()
+    assert struct.unpack("<II", d[:8]) == (20000630, 2)
+    pos, attrs = 8, {}
+    while d[pos] != 0:
+        e = d.index(b"\0", pos); name = d[pos:e].decode(); pos = e + 1
+        e = d.index(b"\0", pos); typ = d[pos:e].decode(); pos = e + 1
+        (n,) = struct.unpack("<I", d[pos:pos + 4]); pos += 4
+        attrs[name] = (typ, d[pos:pos + n]); pos += n
+    pos += 1
+    assert attrs["compression"] == ("compression", b"\0") and attrs["lineOrder"] == ("lineOrder", b"\0")
+    assert struct.unpack("<4i", attrs["dataWindow"][1]) == (0, 0, w - 1, h - 1) == struct.unpack("<4i", attrs["displayWindow"][1])
+    ch = attrs["channels"][1]
+    assert [ch[18 * i:18 * i + 1] for i in range(3)] == [b"B", b"G", b"R"] and ch[-1] == 0 and len(ch) == 55
+    assert all(struct.unpack("<i4xii", ch[18 * i + 2:18 * i + 18]) == (2, 1, 1) for i in range(3))
+    offsets = struct.unpack("<%dQ" % h, d[pos:pos + 8 * h])
+    back = np.zeros_like(rgb)
+    for y, off in enumerate(offsets):
+        yy, n = struct.unpack("<ii", d[off:off + 8])
+        assert (yy, n) == (y, 12 * w)
+        planes = np.frombuffer(d[off + 8:off + 8 + n], "<f4").reshape(3, w)
+        back[y] = planes[::-1].T
+    assert offsets[-1] + 8 + 12 * w == len(d)
+    assert np.array_equal(back.view(np.uint32), rgb.view(np.uint32))
+    os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+    try:
+        import cv2
+        img = cv2.imread(str(path), cv2.IMREAD_UNCHANGED)
+    except Exception:
+        img = None
+    if img is not None:
+        assert img.dtype == np.float32 and np.array_equal(img[:, :, ::-1].view(np.uint32), rgb.view(np.uint32))
+    with pytest.raises(hb.RtError):
+        hb.write_exr(tmp_path / "no_such_dir" / "a.exr", rgb)
+
+
 def test_preview_and_accumulator_need_a_device_too(hb, assets):
     """SURVEY 8(f)-4 entry points: same rule, no device - an error with a text, never a CPU render."""
     if hb.device_count() > 0:

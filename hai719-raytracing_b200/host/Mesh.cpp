@@ -11,13 +11,27 @@
 //   every triangle remembers its own index in v[3].
 // Numbers are read with the iostream extractors, as the reference does, so every float parses
 // to the same bits.
+// Hardened: a file the reference would read out of bounds on, or allocate for blindly, is an error with
+// the file name here - wrong magic, counts that cannot fit in the file, a vertex or face list that ends early, a face
+// that names a vertex the file does not have. Every well-formed file parses exactly as before.
 void Mesh::loadOFF(const std::string &filename) {
     std::ifstream in(filename.c_str());
     if (!in) hai719::fatal("cannot open mesh file: " + filename);  // reference: exit(EXIT_FAILURE)
+    in.seekg(0, std::ios::end);
+    const long long file_bytes = (long long)in.tellg();
+    in.seekg(0, std::ios::beg);
 
     std::string magic;
-    unsigned int nV = 0, nT = 0, tmp = 0;
-    in >> magic >> nV >> nT >> tmp;
+    long long nV64 = 0, nT64 = 0, nE64 = 0;
+    in >> magic >> nV64 >> nT64 >> nE64;
+    if (magic != "OFF" && magic != "COFF") hai719::fatal("not an OFF file (magic '" + magic + "'): " + filename);
+    if (!in) hai719::fatal("unreadable OFF header: " + filename);
+    // a vertex line takes at least 6 bytes ("0 0 0\n"), a face line at least 8 ("3 0 1 2\n")
+    if (nV64 < 0 || nT64 < 0 || nV64 > file_bytes / 6 || nT64 > file_bytes / 8)
+        hai719::fatal("OFF counts (" + std::to_string(nV64) + " vertices, " + std::to_string(nT64) + " faces) do not fit in " +
+                      std::to_string(file_bytes) + " bytes: " + filename);
+    const unsigned int nV = (unsigned int)nV64, nT = (unsigned int)nT64;
+    unsigned int tmp = 0;
     vertices.assign(nV, MeshVertex());
     triangles.assign(nT, MeshTriangle());
     vertColors.clear();
@@ -33,6 +47,7 @@ void Mesh::loadOFF(const std::string &filename) {
     } else {
         for (unsigned int i = 0; i < nV; ++i) in >> vertices[i].position;
     }
+    if (!in) hai719::fatal("OFF vertex list ends early or is not numeric: " + filename);
 
     std::string line;
     std::getline(in, line);  // rest of the last vertex line
@@ -41,7 +56,14 @@ void Mesh::loadOFF(const std::string &filename) {
         std::istringstream ls(line);
         int arity;
         ls >> arity;
-        for (unsigned int j = 0; j < 3; ++j) ls >> triangles[i].v[j];
+        long long idx[3] = {0, 0, 0};
+        for (unsigned int j = 0; j < 3; ++j) ls >> idx[j];
+        if (!ls) hai719::fatal("OFF face " + std::to_string(i) + " of " + std::to_string(nT) + " is missing or incomplete: " + filename);
+        for (unsigned int j = 0; j < 3; ++j) {
+            if (idx[j] < 0 || idx[j] >= (long long)nV)
+                hai719::fatal("OFF face " + std::to_string(i) + " names vertex " + std::to_string(idx[j]) + " of " + std::to_string(nV) + ": " + filename);
+            triangles[i].v[j] = (unsigned int)idx[j];
+        }
         if (i == 0 && !(ls >> std::ws).eof()) {
             colorType = ColorType_Face;
             faceColors.resize(nT);

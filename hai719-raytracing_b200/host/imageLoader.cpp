@@ -30,6 +30,17 @@ bool load_ppm(ImageRGB &img, const std::string &name) {
     if (img.w < 1) return fail(img, "Unsupported width: " + std::to_string(img.w));
     if (img.h < 1) return fail(img, "Unsupported height: " + std::to_string(img.h));
     if (bits < 1 || bits > 255) return fail(img, "Unsupported number of bits: " + std::to_string(bits));
+    // Hardened: the pixel count must fit in what is left of the file (3 bytes per pixel in P6, at least
+    // "0 " per sample in P3) before anything is allocated, and a pixel block that ends early is a failed load (empty
+    // image, as for an unreadable file) instead of a half-filled one.
+    if (f.fail()) return fail(img, "Unreadable PPM header: " + name);
+    const std::streamoff here = f.tellg();
+    f.seekg(0, std::ios::end);
+    const long long left = (long long)(f.tellg() - here);
+    f.seekg(here, std::ios::beg);
+    const long long samples = (long long)img.w * (long long)img.h * 3;
+    if (img.w > left || img.h > left || (p6 ? samples > left - 1 : 2 * samples - 1 > left))
+        return fail(img, "PPM pixel data ends early (" + std::to_string(img.w) + " x " + std::to_string(img.h) + "): " + name);
     img.data.assign((size_t)img.w * (size_t)img.h, RGB{0, 0, 0});
     if (p6) {
         f.get();  // the single whitespace byte after maxval
@@ -42,6 +53,7 @@ bool load_ppm(ImageRGB &img, const std::string &name) {
             f >> v; px.b = (unsigned char)v;
         }
     }
+    if (f.fail()) return fail(img, "PPM pixel data ends early or is not numeric: " + name);
     return true;
 }
 }  // namespace ppmLoader

@@ -221,6 +221,45 @@ def test_loaders_handle_format_variants(hb, tmp_path):
     assert s.flatten().contents.skybox.w == 0
 
 
+_OFF4 = "4 {nt} 0\n0 0 0\n1 0 0\n0 1 0\n0 0 1\n"
+
+
+@pytest.mark.parametrize("text,needle", [
+    ("OFF\n" + _OFF4.format(nt=1) + "3 0 1 9\n", "names vertex 9 of 4"),
+    ("OFF\n" + _OFF4.format(nt=1) + "3 0 1 -2\n", "names vertex -2"),
+    ("OFF\n4 1 0\n0 0 0\n1 0 0\n", "do not fit"),
+    ("OFF\n" + _OFF4.format(nt=3) + "3 0 1 2\n", "face 1 of 3 is missing"),
+    ("OFF\n2000000000 2000000000 0\n0 0 0\n", "do not fit"),
+    ("OFF\n-4 -1 0\n", "do not fit"),
+    ("PLY\n4 1 0\n", "not an OFF file"),
+    ("", "not an OFF file"),
+    ("OFF\n4 1 0\n0 0 zero\n1 0 0\n0 1 0\n0 0 1\n3 0 1 2\n", "vertex list"),
+])
+def test_malformed_off_is_an_error_not_a_crash(hb, tmp_path, text, needle):
+    """SURVEY 8(f)-3: files on which Mesh::loadOFF (Mesh.cpp:9-74) would index out of bounds or allocate blindly."""
+    os.makedirs(tmp_path / "mesh")
+    (tmp_path / "mesh" / "flamingo_lowpoly_colored.off").write_text(text)
+    s = hb.Scene(assets=str(tmp_path))
+    with pytest.raises(hb.RtError) as e:
+        s.setup("flamingo")
+    assert needle in str(e.value)
+
+
+@pytest.mark.parametrize("data", [
+    b"P6\n4 4\n255\n\x01\x02\x03", b"P3\n4 4\n255\n1 2 3 4", b"P6\n2000000000 2000000000\n255\n", b"P6\n-4 4\n255\n",
+    b"P6\n0 0\n255\n", b"P9\n2 2\n255\n", b"P3\n1 1\n255\nred green blue\n", b"",
+])
+def test_malformed_ppm_loads_as_no_image(hb, tmp_path, data):
+    """ppmLoader::load_ppm (imageLoader.cpp:21-103) prints and carries on with an empty image; the hardened loader does
+    the same for pixel blocks that end early and sizes that cannot fit in the file, without allocating for them."""
+    os.makedirs(tmp_path / "img" / "textures")
+    (tmp_path / "img" / "textures" / "space.ppm").write_bytes(data)
+    s = hb.Scene(assets=str(tmp_path))
+    s.setup("single_sphere")
+    d = s.flatten().contents
+    assert (d.skybox.w, d.skybox.h) == (0, 0)
+
+
 def _png_decode(data):
     """Minimal PNG reader for the test: checks signature and every chunk CRC, inflates the IDAT stream with zlib."""
     import struct

@@ -115,7 +115,7 @@ class RtStats(C.Structure):
 
 # every symbol the two headers declare — tests check the libraries export exactly these
 RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy", "rt_release_cached_memory", "rt_scene_update_analytic",
-              "rt_scene_device_bytes", "rt_render_pixel_count", "rt_tile_layout", "rt_render", "rt_render_rgb8", "rt_quantize_device",
+              "rt_scene_check", "rt_scene_device_bytes", "rt_render_pixel_count", "rt_tile_layout", "rt_render", "rt_render_rgb8", "rt_quantize_device",
               "rt_render_device", "rt_untile_device",
               "rt_accum_create", "rt_accum_destroy", "rt_accum_reset", "rt_accum_add", "rt_accum_samples", "rt_accum_read",
               "rt_trace_primary", "rt_trace_rays", "rt_shade_rays", "rt_measure_fp32_peak"]
@@ -134,6 +134,7 @@ host = C.CDLL(LIB_HOST)
 
 rt.rt_last_error.restype = C.c_char_p
 rt.rt_scene_create.argtypes = [C.POINTER(RtSceneDesc), C.c_int, C.POINTER(C.c_void_p)]
+rt.rt_scene_check.argtypes = [C.POINTER(RtSceneDesc)]
 rt.rt_scene_destroy.argtypes = [C.c_void_p]
 rt.rt_scene_update_analytic.argtypes = [C.c_void_p, C.POINTER(RtSceneDesc)]
 rt.rt_scene_device_bytes.restype = C.c_size_t

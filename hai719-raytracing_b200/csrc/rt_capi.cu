@@ -1230,6 +1230,24 @@ int rt_scene_update_analytic(RtScene *s, const RtSceneDesc *desc) {
     return RT_OK;
 }
 
+int rt_scene_check(const RtSceneDesc *desc) {
+    if (!desc) return fail(RT_ERR_INVALID, "null argument");
+    if (desc->abi_version != HAI719_RT_ABI_VERSION) return fail(RT_ERR_INVALID, "RtSceneDesc.abi_version mismatch");
+    if ((desc->n_spheres && !desc->spheres) || (desc->n_squares && !desc->squares) || (desc->n_meshes && !desc->meshes) ||
+        (desc->n_lights && !desc->lights) || (desc->n_textures && !desc->textures) || (desc->n_normal_maps && !desc->normal_maps))
+        return fail(RT_ERR_INVALID, "count > 0 with a null array");
+    int rc;
+    for (uint32_t i = 0; i < desc->n_spheres; ++i) if ((rc = check_material(desc->spheres[i].material, *desc))) return rc;
+    for (uint32_t i = 0; i < desc->n_squares; ++i) if ((rc = check_material(desc->squares[i].material, *desc))) return rc;
+    for (uint32_t i = 0; i < desc->n_meshes; ++i) if ((rc = check_material(desc->meshes[i].material, *desc))) return rc;
+    if (desc->n_meshes) {
+        PackedMeshes pk;
+        const std::string why = pack_meshes(*desc, pk);
+        if (!why.empty()) return fail(RT_ERR_INVALID, why);
+    }
+    return RT_OK;
+}
+
 int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
     if (!desc || !out) return fail(RT_ERR_INVALID, "null argument");
     *out = nullptr;

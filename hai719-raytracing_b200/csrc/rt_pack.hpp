@@ -54,6 +54,9 @@ inline std::string pack_meshes(const RtSceneDesc &d, PackedMeshes &out) {
             if (r.v[0] >= m.n_vertices || r.v[1] >= m.n_vertices || r.v[2] >= m.n_vertices) return "leaf ref vertex index out of bounds";
             if (r.tri_index >= m.n_triangles) return "leaf ref triangle index out of bounds";
         }
+        // the shading code follows triangles[] into the per-vertex arrays (vertex colours)
+        for (uint64_t k = 0; k < (uint64_t)3 * m.n_triangles; ++k)
+            if (m.triangles[k] >= m.n_vertices) return "triangle vertex index out of bounds";
         if ((uint64_t)out.total_refs + m.n_leaf_refs >= 0x7FFFFFFFull) return "too many leaf refs";
         out.total_refs += m.n_leaf_refs;
     }

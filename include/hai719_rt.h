@@ -213,6 +213,11 @@ int rt_abi_version(void);
 int rt_device_count(void);                       /* number of usable sm_100 devices, <= 0 if none */
 const char *rt_last_error(void);
 
+/* The consistency checks rt_scene_create applies to a description, on their own and without a device: ABI version,
+ * counts against null arrays, material enums and image indices, KD skip links and leaf ranges, leaf-ref and triangle
+ * vertex indices. RT_OK or RT_ERR_INVALID (reason in rt_last_error). Host arithmetic only. */
+int rt_scene_check(const RtSceneDesc *desc);
+
 /* Copies everything it needs to `device`; the caller keeps ownership of the host arrays. */
 int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out);
 /* Frees the scene's arrays. Its render scratch (sample, camera-ray and path-state buffers, grow-only) is kept in a

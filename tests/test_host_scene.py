@@ -221,6 +221,45 @@ def test_loaders_handle_format_variants(hb, tmp_path):
     assert s.flatten().contents.skybox.w == 0
 
 
+def test_scene_check_accepts_every_builtin_scene(hb, assets):
+    for name in ["cornell_box", "random_spheres", "flamingo_pond", "backrooms_pool", "flamingo_lake", "config5"]:
+        s = hb.Scene(name, aspect=16 / 9)
+        assert hb.rt.rt_scene_check(s.flatten()) == 0, hb.rt.rt_last_error()
+
+
+def test_scene_check_rejects_inconsistent_descriptions(hb, assets):
+    """rt_scene_check = the checks rt_scene_create runs before anything reaches the device: every index the kernels
+    follow (material images, KD skip links, leaf ranges, leaf-ref and triangle vertex indices) must be in range."""
+    s = hb.Scene("flamingo_pond", aspect=16 / 9)
+    d = s.flatten().contents
+    m = d.meshes[0]
+    leaf = next(k for k in range(m.n_nodes) if m.nodes[k].is_leaf)
+    inner = next(k for k in range(m.n_nodes) if not m.nodes[k].is_leaf)
+
+    def rejected(obj, field, value, needle, index=None):
+        old = getattr(obj, field) if index is None else getattr(obj, field)[index]
+        if index is None: setattr(obj, field, value)
+        else: getattr(obj, field)[index] = value
+        rc = hb.rt.rt_scene_check(C.byref(d))
+        msg = hb.rt.rt_last_error().decode()
+        if index is None: setattr(obj, field, old)
+        else: getattr(obj, field)[index] = old
+        assert rc == -1 and needle in msg, (field, rc, msg)
+
+    rejected(d, "abi_version", d.abi_version + 1, "abi_version")
+    rejected(m.material, "image", d.n_textures, "image index")
+    rejected(m.material, "type", 7, "enum")
+    rejected(d.squares[0].material, "normal_map", d.n_normal_maps + 3, "image index")
+    rejected(m.nodes[leaf], "first_ref", m.n_leaf_refs, "leaf range")
+    rejected(m.nodes[inner], "skip", m.n_nodes + 1, "skip link")
+    rejected(m.nodes[inner], "skip", inner, "skip link")
+    rejected(m.leaf_refs[5], "tri_index", m.n_triangles, "triangle index")
+    rejected(m.leaf_refs[5], "v", m.n_vertices, "vertex index", index=1)
+    rejected(m, "triangles", m.n_vertices, "triangle vertex index", index=3 * (m.n_triangles - 1) + 2)
+    assert hb.rt.rt_scene_check(C.byref(d)) == 0     # everything restored
+    assert hb.rt.rt_scene_check(None) == -1
+
+
 _OFF4 = "4 {nt} 0\n0 0 0\n1 0 0\n0 1 0\n0 0 1\n"
 
 

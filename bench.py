@@ -1,22 +1,33 @@
 #!/usr/bin/env python3
 """bench.py — Mrays/s of the render hot path on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4|c5] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--scenes c1,c3,c4,c5|none] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A STEP is one full render of the workload (every pixel x every sample: camera rays, closest-hit and shadow
-traversal, shading, resolve). Ray = one Scene::computeIntersection or Scene::computeShadow call; the count
-comes from the kernels' own work counters on an untimed pass of the same deterministic render.
+A STEP is one full render of a workload (every pixel x every sample: camera rays, closest-hit and shadow
+traversal, shading, resolve). Ray = one Scene::computeIntersection or Scene::computeShadow call of the reference
+("reference-equivalent rays": shadow rays that the kernels PROVE unoccluded without tracing them still count, as the
+reference traces them; the image is bit-identical either way). Counts come from the kernels themselves.
 
-  value  whole-job Mrays/s, scene resident in HBM, output left in HBM (device-timed with CUDA events on
-         the launching stream, barrier + synchronize on both sides, max over ranks)
-  e2e    the same through the reference-facing host API with HOST buffers: every step re-flattens nothing
-         but re-UPLOADS the scene (rt_scene_create, H2D), renders, gathers and copies the framebuffer to
-         pinned host memory (D2H)
-  N > 1  image tiles (32x32, round-robin) are sharded over the ranks; each rank renders its tiles, rank 0
-         gathers the packed tiles with NCCL and untiles them. Total work is fixed => "scaling": "strong".
-  roofline / cpu_baseline: see DESIGN.md §5. The cpu_baseline is the reference itself (oracle/_ref) on the
-         box's host cores on a bounded crop of the same workload; it is a reported baseline, not the target.
+The headline (top-level keys; K timed steps after W warm-up steps) is config 2, random spheres 1920x1080x64 — the
+configuration BASELINE.json's metric is quoted on. `per_scene` then holds EVERY config of BASELINE.json at its stated
+size (c1 850x480x1, c2, c3 3840x2160x16, c4 3840x2160x256, c5 7680x4320x1024), each with its own small step count
+(the long ones run ONE full-size step: c5 is ~35 s on one GPU), with the same keys: value, e2e, roofline, cpu_baseline.
+
+  value  whole-job Mrays/s, scene resident in HBM, framebuffer left in HBM (device-timed with CUDA events on the
+         launching stream, barrier + synchronize on both sides, max over ranks)
+  e2e    the same through the reference-facing call with HOST buffers: every step re-UPLOADS the scene
+         (rt_scene_create: H2D + precompute + hierarchy build), renders and copies the framebuffer into pinned host
+         memory (D2H); wall clock, max over ranks
+  N > 1  one process per GPU; image tiles (32x32, round-robin) are sharded over the ranks. Rank 0 owns the framebuffer
+         (rt_ipc_alloc); the other ranks map it (CUDA IPC over NVLink) and their resolve kernels store their tiles
+         straight into it: no packed buffers, no gather collective, no untile pass (torch.distributed carries the
+         64-byte handle and the barriers). Total work is fixed => "scaling": "strong".
+  roofline      executed-work fractions of the HBM and FP32 roofs + the issue-side figure of the committed ncu capture;
+                the contract-algorithm figure of SURVEY 8(d) is reported as `algorithmic_speedup`
+  cpu_baseline  the reference itself (oracle/_ref) on the box's host cores on a bounded crop of the same workload:
+                the deterministic build on a row pool AND the stock build threaded as the reference threads it
+                (one std::thread per scanline, shared racy mt19937). A reported baseline, not the target.
 """
 import argparse
 import ctypes as C
@@ -42,6 +53,12 @@ WORKLOADS = {
     "c4": dict(scene="backrooms_pool", w=3840, h=2160, spp=256, label="Backrooms pool 3840x2160 256spp (configs[3])"),
     "c5": dict(scene="config5", w=7680, h=4320, spp=1024, label="Motion-blur spheres + triceratops/gorilla 7680x4320 1024spp (configs[4])"),
 }
+
+
+# per-scene measurement plan: (warm-up steps, timed steps, e2e steps, warm-up spp or 0 = full). The long workloads
+# warm up at reduced spp (same kernels, same chunk size, scratch allocated) and time ONE full-size step, which is
+# also their e2e step (upload + render + D2H, device time from the CUDA events inside it).
+PLAN = {"c1": (5, 20, 20, 0), "c2": (3, 5, 3, 0), "c3": (2, 3, 2, 4), "c4": (2, 1, 1, 8), "c5": (2, 1, 1, 1)}
 
 
 def kernel_of(counts, variant):
@@ -153,9 +170,75 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
 
 
+
+def ref_sample(wl, budget_s, ref_scene, cw_max=240, ch_max=136):
+    """Centre crop + spp of the CPU sample so that one pass is ~budget_s of wall time (calibrated with a 1-spp pass of a
+    240x136 crop): first the spp grows up to the workload's, then the crop up to the whole image."""
+    w, h, spp = wl["w"], wl["h"], wl["spp"]
+    cw, ch = min(w, cw_max), min(h, ch_max)
+    crop = ((w - cw) // 2, (h - ch) // 2, (w - cw) // 2 + cw, (h - ch) // 2 + ch)
+    t0 = time.perf_counter(); ref_scene.render(w, h, 1, seed=0, threads=0, crop=crop, want_ids=False); dt = time.perf_counter() - t0
+    s_spp = int(max(1, min(spp, round(budget_s / max(dt, 1e-3)))))
+    grow = (budget_s / max(dt * s_spp, 1e-3)) ** 0.5
+    if s_spp == spp and grow > 1.2:
+        cw, ch = min(w, int(cw * grow)), min(h, int(ch * grow))
+        crop = ((w - cw) // 2, (h - ch) // 2, (w - cw) // 2 + cw, (h - ch) // 2 + ch)
+    return crop, cw, ch, s_spp
+
+
+def count_ref_rays(wl, crop, s_spp):
+    """Rays of the CPU sample, counted by the reference itself: oracle/_ref/libref_count.so is the deterministic build with
+    gcc's function-entry hook on Scene::computeIntersection / Scene::computeShadow (oracle/ref_driver.cpp); same stream,
+    same rays as the timed deterministic build. Never timed."""
+    import oracle_ref
+    w, h = wl["w"], wl["h"]
+    rs = oracle_ref.Ref(kind="count").scene(wl["scene"], aspect=w / h, seed=0)
+    r = rs.render(w, h, s_spp, seed=0, threads=0, crop=crop, want_ids=False)
+    rs.close()
+    return r["n_closest_rays"] + r["n_shadow_rays"]
+
+
+def cpu_baseline_of(wl, budget_s=4.0):
+    """cpu_baseline object for one workload (rank 0, N = 1 only): pooled deterministic reference + the reference's own
+    thread-per-scanline / shared-mt19937 mode (main.cpp:229-238, Functions.cpp:4-8)."""
+    import oracle_ref
+    if not oracle_ref.available():
+        return None
+    cores = os.cpu_count() or 1
+    w, h, spp = wl["w"], wl["h"], wl["spp"]
+    try:
+        ref = oracle_ref.Ref().scene(wl["scene"], aspect=w / h, seed=0)
+        crop, cw, ch, s_spp = ref_sample(wl, budget_s, ref)
+        r = ref.render(w, h, s_spp, seed=0, threads=0, crop=crop, want_ids=False)
+        dt = r["seconds"]
+        ref.close()
+        rays = count_ref_rays(wl, crop, s_spp) if oracle_ref.available(kind="count") else None
+        out = {"value": (rays / dt / 1e6) if rays else None, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+               "sample": "centre crop %dx%d of the %dx%d image plane at %d of %d spp: %d samples, %s rays (counted in the reference: libref_count), "
+                         "%.2f s wall; reference sources built headless (oracle/_ref), deterministic RNG shim, %d-thread row pool"
+                         % (cw, ch, w, h, s_spp, spp, cw * ch * s_spp, rays, dt, cores),
+               "msamples_per_s": cw * ch * s_spp / dt / 1e6, "rays_per_sample": (rays / (cw * ch * s_spp)) if rays else None}
+        if oracle_ref.available(stock=True):
+            st = oracle_ref.Ref(stock=True).scene(wl["scene"], aspect=w / h, seed=0)
+            rr = st.render_rows(w, h, s_spp, crop=crop)
+            st.close()
+            # the stock stream differs from the deterministic one, so its ray count is the deterministic sample's
+            # rays-per-sample x its samples (the mean over >= 3e4 samples; stated, not exact)
+            out["thread_per_row_stock"] = {
+                "value": (rays / rr["seconds"] / 1e6) if rays else None, "unit": "Mrays/s", "msamples_per_s": cw * ch * s_spp / rr["seconds"] / 1e6,
+                "threads": ch, "cores": cores, "seconds": rr["seconds"],
+                "what": "the reference's own threading and RNG: one std::thread per scanline (%d threads at once, main.cpp:229-238), "
+                        "random_float() = ONE shared time-seeded mt19937 without a lock (Functions.cpp:4-8), unmodified; same crop and spp; "
+                        "rays = samples x rays/sample of the deterministic sample" % ch}
+        return out
+    except Exception as e:  # the baseline must never take the GPU number down with it
+        return {"value": None, "unit": "Mrays/s", "cores": cores, "kind": "reference", "sample": "failed: %r" % (e,)}
+
+
 def run_reference(args, wl):
-    """--impl reference: the reference's own CPU render (oracle/_ref, deterministic RNG shim) on all host threads,
-    each step a bounded crop of the same workload."""
+    """--impl reference: the reference's own CPU render (oracle/_ref, deterministic RNG shim) on all host threads, each
+    step a bounded crop of the same workload. Loads nothing of the product: the crop's rays are counted by the
+    reference itself (libref_count.so)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -163,21 +246,12 @@ def run_reference(args, wl):
     if not oracle_ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built and assets/_ref not staged"}))
         return
-    hb = importlib.import_module("hai719-raytracing_b200")
     cores = os.cpu_count() or 1
     w, h, spp = wl["w"], wl["h"], wl["spp"]
     ref = oracle_ref.Ref().scene(wl["scene"], aspect=w / h, seed=0)
-    cw, ch = min(w, 240), min(h, 136)
-    crop = ((w - cw) // 2, (h - ch) // 2, (w - cw) // 2 + cw, (h - ch) // 2 + ch)
-    # calibrate samples-per-pixel of the sample so that one step is ~3 s of wall time
-    t0 = time.perf_counter(); ref.render(w, h, 1, seed=0, threads=0, crop=crop, want_ids=False); dt = time.perf_counter() - t0
-    s_spp = int(max(1, min(spp, round(3.0 / max(dt, 1e-3)))))
-    rays_per_sample = None
-    if hb.device_count() > 0:   # ray count of exactly this crop from the GPU's work counters (identical rays: parity)
-        st = hb.Scene(wl["scene"], aspect=w / h, seed=0).render(w, h, s_spp, seed=0, crop=crop, stats=True, want_linear=False)["stats"]
-        rays = st["n_closest_rays"] + st["n_shadow_rays"]
-    else:
-        rays = None
+    per_step = max(0.5, min(3.0, 150.0 / max(1, args.steps + args.warmup)))   # the whole run ends within a few minutes
+    crop, cw, ch, s_spp = ref_sample(wl, per_step, ref)
+    rays = count_ref_rays(wl, crop, s_spp)
     for _ in range(args.warmup):
         ref.render(w, h, s_spp, seed=0, threads=0, crop=crop, want_ids=False)
     t0 = time.perf_counter()
@@ -185,18 +259,315 @@ def run_reference(args, wl):
         ref.render(w, h, s_spp, seed=0, threads=0, crop=crop, want_ids=False)
     dt = (time.perf_counter() - t0) / args.steps
     samples = cw * ch * s_spp
-    if rays is None:
-        rays = samples * 10.4
     val = rays / dt / 1e6
-    sample = "centre crop %dx%d of the %dx%d image plane at %d of %d spp (%d samples/step, %d rays/step)" % (cw, ch, w, h, s_spp, spp, samples, rays)
+    sample = ("centre crop %dx%d of the %dx%d image plane at %d of %d spp (%d samples/step, %d rays/step counted in the reference itself); the "
+              "per-ray rate of a CPU whose cost per ray does not depend on the image size" % (cw, ch, w, h, s_spp, spp, samples, rays))
     print(json.dumps({
         "impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": wl["label"], "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": config_of(wl, 1, 0, sample=sample),
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "reference", "sample": sample,
                          "msamples_per_s": samples / dt / 1e6},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def config_of(wl, world, variant, **extra):
+    c = {"workload": wl["label"], "scene": wl["scene"], "width": wl["w"], "height": wl["h"], "spp": wl["spp"], "max_bounces": 6, "nb_ech": 10,
+         "seed": 0, "tiles": "32x32 round-robin over ranks" if world > 1 else "32x32", "variant": variant,
+         "ray_unit": "reference-equivalent rays: computeIntersection + computeShadow calls of the reference for this image"}
+    c.update(extra)
+    return c
+
+
+class Bench:
+    """Everything one process (rank) needs to measure workloads: torch / NCCL plumbing, the shared framebuffer."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.hb = importlib.import_module("hai719-raytracing_b200")
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.hb.device_count() < 1:
+            raise SystemExit("bench.py: no sm_100 device; the render path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
+        self.stream = torch.cuda.current_stream()
+        self.fp32_peaks = None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        self.hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        self.hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        try:
+            self.prof = json.load(open(os.path.join(ROOT, "profiles", "latest.json")))
+        except (OSError, ValueError):
+            self.prof = {}
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def sum_over_ranks(self, xs):
+        t = self.torch.tensor([float(x) for x in xs], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return [int(v) for v in t.tolist()]
+
+    # ---- the framebuffer all ranks write into -----------------------------------------------------------------------
+    def framebuffer(self, n_floats):
+        """Device pointer of an n_floats image on rank 0's GPU, valid on this rank. N == 1: a torch tensor. N > 1: rank 0
+        allocates with rt_ipc_alloc, the 64-byte handle travels through torch.distributed, peers map it (rt_ipc_open)."""
+        torch, hb = self.torch, self.hb
+        if self.world == 1:
+            t = torch.zeros(n_floats, dtype=torch.float32, device=self.dev)
+            return t.data_ptr(), t, None
+        handle = torch.zeros(64, dtype=torch.uint8, device=self.dev)
+        ptr = C.c_void_p()
+        if self.rank == 0:
+            hbuf = (C.c_ubyte * 64)()
+            rc = hb.rt.rt_ipc_alloc(self.local, n_floats * 4, C.byref(ptr), hbuf)
+            if rc != 0:
+                raise RuntimeError(hb.rt.rt_last_error().decode())
+            handle.copy_(torch.tensor(list(hbuf), dtype=torch.uint8))
+        self.dist.broadcast(handle, src=0)
+        if self.rank != 0:
+            hbuf = (C.c_ubyte * 64)(*handle.cpu().tolist())
+            rc = hb.rt.rt_ipc_open(self.local, hbuf, C.byref(ptr))
+            if rc != 0:
+                raise RuntimeError("rt_ipc_open: " + hb.rt.rt_last_error().decode())
+        return ptr.value, None, ptr
+
+    def release_framebuffer(self, keep, ptr):
+        if ptr is None:
+            return
+        self.barrier()
+        if self.rank == 0:
+            self.hb.rt.rt_ipc_free(self.local, ptr)
+        else:
+            self.hb.rt.rt_ipc_close(self.local, ptr)
+        self.barrier()
+
+    # ---- one workload ------------------------------------------------------------------------------------------------
+    def measure(self, key, wl, warmup, steps, e2e_steps, warm_spp, headline=False, with_cpu=True):
+        torch, hb, args = self.torch, self.hb, self.args
+        rank, world, local, dev, stream = self.rank, self.world, self.local, self.dev, self.stream
+        w, h, spp = wl["w"], wl["h"], wl["spp"]
+        variant = args.variant if headline else 0
+        scene = hb.Scene(wl["scene"], aspect=w / h, seed=0)
+        cam = hb.default_camera(w, h)
+        handle = scene.device_handle(local)
+        n_img = h * w * 3
+        img_ptr, keep, ipc_ptr = self.framebuffer(n_img)
+        host_img = torch.empty(n_img, dtype=torch.float32).pin_memory() if rank == 0 else None
+
+        def params(c_spp, **kw):
+            return hb.render_params(w, h, c_spp, seed=0, rank=rank, n_ranks=world, tile=(32, 32), **kw)
+
+        def render(p, stats=None):
+            rc = hb.rt.rt_render_device_image(handle, C.byref(cam), C.byref(p), img_ptr, None, stream.cuda_stream, stats)
+            if rc != 0:
+                raise RuntimeError(hb.rt.rt_last_error().decode())
+
+        p_full = params(spp, variant=variant)
+        n_px = int(hb.rt.rt_render_pixel_count(C.byref(p_full)))
+        keys = ["n_samples", "n_closest_rays", "n_shadow_rays", "n_sphere_tests", "n_square_tests", "n_mesh_tests", "n_node_visits",
+                "n_tri_tests", "n_tri_full", "n_tex_fetches", "n_random"]
+
+        def count(c_variant, c_spp, cw=None, chh=None):
+            # counting pass (untimed) into a scratch image of its own size; cw x chh = a smaller image plane (same camera)
+            if cw is None:
+                pc = params(c_spp, collect_stats=True, variant=c_variant)
+                st = hb.RtStats()
+                render(pc, C.byref(st))
+                return st.as_dict()
+            pc = hb.render_params(cw, chh, c_spp, seed=0, rank=rank, n_ranks=world, tile=(32, 32), collect_stats=True, variant=c_variant)
+            st = hb.RtStats()
+            tmp = torch.zeros(cw * chh * 3, dtype=torch.float32, device=dev)
+            ccam = hb.default_camera(cw, chh)
+            rc = hb.rt.rt_render_device_image(handle, C.byref(ccam), C.byref(pc), tmp.data_ptr(), None, stream.cuda_stream, C.byref(st))
+            if rc != 0:
+                raise RuntimeError(hb.rt.rt_last_error().decode())
+            return st.as_dict()
+
+        # ---- warm-up (untimed) ----
+        p_warm = params(warm_spp, variant=variant) if warm_spp else p_full
+        for _ in range(warmup):
+            self.flush.zero_()
+            render(p_warm)
+        self.barrier()
+
+        # ---- timed steps: device time by CUDA events on the launching stream, max over ranks ----
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        kst = hb.RtStats()
+        kernel_ms, launches, chunks = 0.0, 0, 1
+        e2e_each = []
+        scene_bytes = scene.device_bytes(local)
+        fused_e2e = steps == 1 and e2e_steps == 1      # long workloads: the ONE full-size step is both the device-timed and the e2e step
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if fused_e2e:
+            self.barrier()
+            t0 = time.perf_counter()
+            scene.invalidate_device()
+            handle = scene.device_handle(local)        # rt_scene_create: H2D + precompute kernels + hierarchy build
+            ev0.record(stream)
+            render(p_full, C.byref(kst))
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            if world > 1:
+                self.dist.barrier()                    # every rank's tiles are in rank 0's framebuffer
+            if rank == 0:
+                if world > 1:
+                    rc = C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(C.c_void_p(host_img.data_ptr()), C.c_void_p(img_ptr), C.c_size_t(n_img * 4), 2)
+                    if rc != 0:
+                        raise RuntimeError("cudaMemcpy D2H failed: %d" % rc)
+                else:
+                    host_img.copy_(keep, non_blocking=True)
+                torch.cuda.synchronize()
+            e2e_each.append((time.perf_counter() - t0) * 1e3)
+            self.barrier()
+            kernel_ms += kst.kernel_ms; launches += kst.n_launches; chunks = max(1, kst.n_chunks)
+        else:
+            self.barrier()
+            ev0.record(stream)
+            for _ in range(steps):
+                self.flush.zero_()
+                render(p_full, C.byref(kst))   # stats != NULL makes the call wait on its own end event: kernel_ms is that kernel time
+                kernel_ms += kst.kernel_ms; launches += kst.n_launches; chunks = max(1, kst.n_chunks)
+            ev1.record(stream)
+            self.barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms_per_step = self.max_over_ranks(ev0.elapsed_time(ev1)) / steps
+
+        # ---- ray counts: the wavefront tallies them for free (k_wf_tally); other kernels need a counting pass ----
+        my_closest, my_shadow = int(kst.n_closest_rays), int(kst.n_shadow_rays)
+        counted = "queue counters of the timed steps (k_wf_tally)"
+        if my_closest == 0:
+            c = count(variant, spp)
+            my_closest, my_shadow = c["n_closest_rays"], c["n_shadow_rays"]
+            counted = "work counters of an untimed pass of the same deterministic render"
+        rays, samples = self.sum_over_ranks([my_closest + my_shadow, n_px * spp])
+        value = rays / (ms_per_step * 1e-3) / 1e6
+
+        # ---- end to end: upload scene (H2D) + render + D2H of the framebuffer into pinned host memory, per step ----
+        if not fused_e2e:
+            self.barrier()
+            for _ in range(e2e_steps):
+                t0 = time.perf_counter()
+                scene.invalidate_device()
+                handle = scene.device_handle(local)
+                render(p_full)
+                if world > 1:
+                    torch.cuda.synchronize()
+                    self.dist.barrier()
+                if rank == 0:
+                    if world > 1:
+                        rc = C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(C.c_void_p(host_img.data_ptr()), C.c_void_p(img_ptr), C.c_size_t(n_img * 4), 2)
+                        if rc != 0:
+                            raise RuntimeError("cudaMemcpy D2H failed: %d" % rc)
+                    else:
+                        host_img.copy_(keep, non_blocking=True)
+                torch.cuda.synchronize()
+                e2e_each.append((time.perf_counter() - t0) * 1e3)
+                if world > 1:
+                    self.dist.barrier()
+            self.barrier()
+        e2e_ms = self.max_over_ranks(sum(e2e_each) / len(e2e_each))
+        e2e_value = rays / (e2e_ms * 1e-3) / 1e6
+        checksum = float(host_img.double().sum().item()) if rank == 0 else 0.0
+
+        # ---- work per ray for the roofline (untimed, bounded): executed = the timed variant's own counters at <= 4 spp;
+        #      contract = the reference-order traversal (variant 1) on a 960x540 image plane of the same camera at <= 4 spp ----
+        c_spp = min(spp, 4)
+        ex = count(variant, c_spp)
+        cw, chh = min(w, 960), min(h, 540)
+        alg = count(1, c_spp, cw, chh)
+        ex_tot = dict(zip(keys, self.sum_over_ranks([ex[k] for k in keys])))
+        alg_tot = dict(zip(keys, self.sum_over_ranks([alg[k] for k in keys])))
+        self.release_framebuffer(keep, ipc_ptr)
+        if rank != 0:
+            return None
+
+        ex_rays, ex_flops, ex_bytes = flops_and_bytes(ex_tot)
+        al_rays, al_flops, al_bytes = flops_and_bytes(alg_tot)
+        if self.fp32_peaks is None:
+            self.fp32_peaks = hb.measure_fp32_peak(local)
+        fp32_unfused, fp32_fused = self.fp32_peaks
+        k_ms = kernel_ms / steps                                  # this rank's render kernels per step
+        my_rays = my_closest + my_shadow
+        t_step = k_ms * 1e-3
+        ex_fpr, ex_bpr = ex_flops / max(1, ex_rays), ex_bytes / max(1, ex_rays)
+        al_fpr, al_bpr = al_flops / max(1, al_rays), al_bytes / max(1, al_rays)
+        hbm_ach = my_rays * ex_bpr / t_step / 1e9                 # GB/s of executed algorithmic bytes
+        fp_ach = my_rays * ex_fpr / t_step / 1e12
+        hbm_frac, fp_frac = hbm_ach / self.hbm_peak, fp_ach / fp32_unfused
+        bound = "hbm" if hbm_frac >= fp_frac else "fp32"
+        t_roof_contract = max(my_rays * al_fpr / (fp32_unfused * 1e12), my_rays * al_bpr / (self.hbm_peak * 1e9))
+        prof = self.prof.get(key, {})
+        roof = {
+            "bound": bound,
+            "achieved": hbm_ach if bound == "hbm" else fp_ach, "peak": self.hbm_peak if bound == "hbm" else fp32_unfused,
+            "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": max(hbm_frac, fp_frac),
+            "what": "EXECUTED work: the tests the timed kernels really perform (their own counters at %d spp, scaled per ray) at the per-test "
+                    "flop/byte figures of SURVEY 8(d) + 64 B of path state per ray; the slower roof is reported" % c_spp,
+            "hbm": {"achieved_gbs": hbm_ach, "peak_gbs": self.hbm_peak, "frac": hbm_frac, "bytes_per_ray": ex_bpr},
+            "fp32": {"achieved_tflops": fp_ach, "peak_tflops": fp32_unfused, "frac": fp_frac, "flops_per_ray": ex_fpr},
+            "traffic": None,
+            "kernel": kernel_of(scene.counts(), variant),
+            "kernel_ms_per_launch": k_ms / chunks, "launches_per_step": chunks,
+            "launch": "one chunk of <= 32 Mi (wavefront) / 16 Mi paths: every render kernel of the chunk, CUDA events around them on the launching stream",
+            "peak_source": "fp32 unfused FMUL+FADD measured live by rt_measure_fp32_peak (fused: %.1f TFLOP/s; the parity build may not fuse); hbm %s" % (fp32_fused, self.hbm_src),
+            "algorithmic_speedup": {
+                "value": t_roof_contract / t_step,
+                "what": "time the SURVEY 8(d) CONTRACT algorithm (the reference's brute-force loops and both-children KD walk, counted by variant 1 on a "
+                        "%dx%d plane at %d spp) would need at the roofline / measured kernel time; > 1 because the culling hierarchies and the light-cone "
+                        "proof skip most of those tests exactly. A speed-up over the contract algorithm, NOT a utilisation figure." % (cw, chh, c_spp),
+                "contract_flops_per_ray": al_fpr, "contract_bytes_per_ray": al_bpr},
+        }
+        if prof.get("dram_bytes_per_path") is not None:
+            roof["traffic"] = prof["dram_bytes_per_path"] * (n_px * spp) / chunks
+            roof["traffic_source"] = "profiles/latest.json (%s): %.0f B of DRAM traffic per path (ncu) x paths per chunk" % (prof.get("source", "?"), prof["dram_bytes_per_path"])
+        if prof.get("issue") is not None:
+            roof["issue"] = prof["issue"]
+        out = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_of(wl, world, variant, rays_per_step=rays, samples_per_step=samples, rays_per_sample=rays / max(1, samples),
+                                rays_counted_by=counted, warmup_spp=warm_spp or spp,
+                                l2="256 MiB buffer rewritten before every step (L2 flush); path state per step is far larger than L2" if not fused_e2e
+                                   else "one step of >= 10 GB of path state per chunk: inputs far larger than L2",
+                                framebuffer="torch tensor" if world == 1 else "rank 0's image mapped by every rank (CUDA IPC), written by the resolve kernels over NVLink"),
+            "msamples_per_s": samples / (ms_per_step * 1e-3) / 1e6,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(scene_bytes) * world,
+                    "d2h_bytes_per_step": int(n_img * 4), "steps": len(e2e_each),
+                    "what": "rt_scene_create (upload + precompute) + rt_render_device_image + D2H to pinned host, per step; wall clock" +
+                            ("; the same step as `value`" if fused_e2e else "")},
+            "gpu_launches": int(launches) * world,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu_baseline_of(wl) if (with_cpu and world == 1 and not args.no_cpu_baseline) else None,
+            "work_executed_per_ray": {k: ex_tot[k] / max(1, ex_rays) for k in keys[3:]},
+            "image_checksum": checksum,
+        }
+        return out
 
 
 def main():
@@ -206,7 +577,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (diagnostics only)")
+    ap.add_argument("--scenes", default="c1,c3,c4,c5", help="per_scene entries besides the headline workload ('none' = headline only)")
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel of the headline workload (diagnostics only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
     args = ap.parse_args()
@@ -222,235 +594,33 @@ def main():
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
-    import torch
-    import torch.distributed as dist
-    hb = importlib.import_module("hai719-raytracing_b200")
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if hb.device_count() < 1:
-        raise SystemExit("bench.py: no sm_100 device; the render path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    w, h, spp = wl["w"], wl["h"], wl["spp"]
-    scene = hb.Scene(wl["scene"], aspect=w / h, seed=0)
-    cam = hb.default_camera(w, h)
-    handle = scene.device_handle(local)
-    p = hb.render_params(w, h, spp, seed=0, rank=rank, n_ranks=world, tile=(32, 32), variant=args.variant)
-    n_px = int(hb.rt.rt_render_pixel_count(C.byref(p)))
-    counts = [int(hb.rt.rt_render_pixel_count(C.byref(hb.render_params(w, h, spp, rank=r, n_ranks=world, tile=(32, 32))))) for r in range(world)]
-    max_px = max(counts)
-    packed = torch.zeros(max_px * 3, dtype=torch.float32, device=dev)     # equal-sized so all_gather_into_tensor works
-    gathered = torch.zeros(world * max_px * 3, dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
-    image = torch.zeros(h * w * 3, dtype=torch.float32, device=dev) if rank == 0 else None
-    offsets = np.array([r * max_px for r in range(world)], np.int64)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    host_img = torch.empty(h * w * 3, dtype=torch.float32).pin_memory() if rank == 0 else None
-    stream = torch.cuda.current_stream()
-
-    def render_step(stats=None):
-        rc = hb.rt.rt_render_device(handle, C.byref(cam), C.byref(p), packed.data_ptr(), None, stream.cuda_stream, stats)
-        if rc != 0:
-            raise RuntimeError(hb.rt.rt_last_error().decode())
-        if world > 1:
-            dist.gather(packed, list(gathered.view(world, -1).unbind(0)) if rank == 0 else None, dst=0)
-        if rank == 0:
-            src = gathered if world > 1 else packed
-            rc = hb.rt.rt_untile_device(C.byref(p), src.data_ptr(), offsets.ctypes.data, image.data_ptr(), local, stream.cuda_stream)
-            if rc != 0:
-                raise RuntimeError(hb.rt.rt_last_error().decode())
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # untimed counting passes (deterministic => the same rays as the timed steps):
-    #  A. the timed variant with its counters on, full size: exact ray / sample counts of this rank's shard
-    #  B. the reference-order traversal (variant 1) at <= 4 spp: the ALGORITHMIC work per ray of SURVEY 8(d)
-    #     (spheres, squares, KD nodes and triangles the reference's traversal visits), scaled to the full spp
-    keys = ["n_samples", "n_closest_rays", "n_shadow_rays", "n_sphere_tests", "n_square_tests", "n_mesh_tests", "n_node_visits",
-            "n_tri_tests", "n_tri_full", "n_tex_fetches", "n_random"]
-
-    def count(variant, c_spp):
-        pc = hb.render_params(w, h, c_spp, seed=0, rank=rank, n_ranks=world, tile=(32, 32), collect_stats=True, variant=variant)
-        st = hb.RtStats()
-        rc = hb.rt.rt_render_device(handle, C.byref(cam), C.byref(pc), packed.data_ptr(), None, stream.cuda_stream, C.byref(st))
-        if rc != 0:
-            raise RuntimeError(hb.rt.rt_last_error().decode())
-        return st.as_dict()
-
-    executed = count(args.variant, spp)
-    c_spp = min(spp, 4)
-    alg = count(1, c_spp)
-    scale = (executed["n_closest_rays"] + executed["n_shadow_rays"]) / max(1, alg["n_closest_rays"] + alg["n_shadow_rays"])
-    my = {k: (executed[k] if k in ("n_samples", "n_closest_rays", "n_shadow_rays", "n_random") else int(round(alg[k] * scale))) for k in keys}
-    tot = torch.tensor([float(my[k]) for k in keys] + [float(executed[k]) for k in keys], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot)
-    total = {k: int(v) for k, v in zip(keys, tot.tolist()[:len(keys)])}
-    total_executed = {k: int(v) for k, v in zip(keys, tot.tolist()[len(keys):])}
-    rays, flops, byts = flops_and_bytes(total)
-    my_rays, my_flops, my_byts = flops_and_bytes(my)
-    ex_rays, ex_flops, ex_byts = flops_and_bytes(executed)
-
-    for _ in range(args.warmup):
-        flush.zero_()
-        render_step()
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kst = hb.RtStats()
-    kernel_ms = 0.0
-    launches = 0
-    ev0.record(stream)
-    for _ in range(args.steps):
-        flush.zero_()
-        render_step(C.byref(kst))      # stats != NULL makes the call wait on its own end event: kernel_ms is that kernel time
-        kernel_ms += kst.kernel_ms
-        launches += kst.n_launches + (1 if rank == 0 else 0)
-        if os.environ.get("BENCH_DEBUG"):
-            sys.stderr.write("rank %d step kernel_ms %.2f\n" % (rank, kst.kernel_ms))
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = ms.item() / args.steps
-    value = rays / (ms_per_step * 1e-3) / 1e6
-
-    # end to end: upload scene (H2D) + render + gather + untile + D2H of the framebuffer into pinned host memory
-    e2e_steps = max(3, args.steps)
-    scene_bytes = scene.device_bytes(local)
-    barrier()
-    e2e_each = []
-    for _ in range(e2e_steps):
-        t0 = time.perf_counter()
-        scene.invalidate_device()
-        handle = scene.device_handle(local)            # flatten() is cached; this is rt_scene_create: H2D + precompute kernels
-        t1 = time.perf_counter()
-        render_step()
-        t2 = time.perf_counter()
-        if rank == 0:
-            host_img.copy_(image, non_blocking=True)
-        torch.cuda.synchronize()
-        e2e_each.append((time.perf_counter() - t0) * 1e3)
-        if os.environ.get("BENCH_DEBUG"):
-            sys.stderr.write("rank %d e2e step: upload %.2f ms, submit %.2f ms, wait %.2f ms\n" % (rank, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3))
-    barrier()
-    if os.environ.get("BENCH_DEBUG"):
-        sys.stderr.write("rank %d e2e ms per step: %s\n" % (rank, " ".join("%.1f" % t for t in e2e_each)))
-    # mean over the steps; every step is a complete upload + render + gather + untile + D2H
-    e2e_ms = torch.tensor([sum(e2e_each) / len(e2e_each)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = rays / (e2e_ms.item() * 1e-3) / 1e6
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    fp32_unfused, fp32_fused = hb.measure_fp32_peak(local)
-    # dominant kernel = k_render_paths; per-launch figures of rank 0's shard
-    n_launch = max(1, kst.n_chunks)
-    k_ms = kernel_ms / args.steps / n_launch
-    ach_tflops = my_flops / n_launch / (k_ms * 1e-3) / 1e12
-    ach_gbs = my_byts / n_launch / (k_ms * 1e-3) / 1e9
-    t_fp = my_flops / (fp32_unfused * 1e12)
-    t_mem = my_byts / (hbm_peak * 1e9)
-    bound = "fp32" if t_fp >= t_mem else "hbm"
-    roof = {
-        "bound": bound,
-        "achieved": ach_tflops if bound == "fp32" else ach_gbs,
-        "peak": fp32_unfused if bound == "fp32" else hbm_peak,
-        "unit": "TFLOP/s" if bound == "fp32" else "GB/s",
-        "frac": (ach_tflops / fp32_unfused) if bound == "fp32" else (ach_gbs / hbm_peak),
-        "traffic": None,
-        "kernel": kernel_of(scene.counts(), args.variant),
-        "kernel_ms_per_launch": k_ms, "launches_per_step": n_launch,
-        "launch": "one chunk of <= 32 Mi (wavefront) / 16 Mi paths: every render kernel of the chunk, CUDA events around them on the launching stream",
-        "peak_source": "fp32 unfused FMUL+FADD measured live by rt_measure_fp32_peak (fused: %.1f TFLOP/s); hbm %s" % (fp32_fused, hbm_src),
-        "fp32": {"achieved_tflops": ach_tflops, "peak_tflops": fp32_unfused, "frac": ach_tflops / fp32_unfused,
-                 "algorithmic_flops_per_ray": my_flops / max(1, my_rays)},
-        "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak,
-                "algorithmic_bytes_per_ray": my_byts / max(1, my_rays)},
-        "executed": {"note": "work the timed variant actually performed (variant 3 culls tests exactly; node/triangle counts are then "
-                             "those of its own hierarchy), same per-test flop/byte figures",
-                     "flops_per_ray": ex_flops / max(1, ex_rays), "bytes_per_ray": ex_byts / max(1, ex_rays),
-                     "tflops": ex_flops / n_launch / (k_ms * 1e-3) / 1e12, "frac_fp32": ex_flops / n_launch / (k_ms * 1e-3) / 1e12 / fp32_unfused},
-        "roofline_mrays_per_s": my_rays / max(t_fp, t_mem) / 1e6,
-        "frac_of_roofline_rays": (my_rays / (k_ms * 1e-3 * n_launch)) / (my_rays / max(t_fp, t_mem)),
-    }
-    # DRAM traffic of the last committed ncu capture (bytes per path), scaled to the paths of one launch group (chunk)
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "latest.json")))
-        per_path = prof.get(args.workload, {}).get("dram_bytes_per_path")
-        if per_path is not None:
-            roof["traffic"] = per_path * (n_px * spp) / n_launch
-            roof["traffic_source"] = "profiles/latest.json: %.0f B of DRAM traffic per path (ncu --set full) x paths per chunk" % per_path
-    except (OSError, ValueError):
-        pass
-
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            import oracle_ref
-            if oracle_ref.available():
-                cores = os.cpu_count() or 1
-                ref = oracle_ref.Ref().scene(wl["scene"], aspect=w / h, seed=0)
-                cw, ch = min(w, 480), min(h, 270)
-                crop = ((w - cw) // 2, (h - ch) // 2, (w - cw) // 2 + cw, (h - ch) // 2 + ch)
-                t0 = time.perf_counter(); ref.render(w, h, 1, seed=0, threads=0, crop=crop, want_ids=False); dt1 = time.perf_counter() - t0
-                s_spp = int(max(1, min(spp, round(15.0 / max(dt1, 1e-3)))))
-                t0 = time.perf_counter(); ref.render(w, h, s_spp, seed=0, threads=0, crop=crop, want_ids=False); dt = time.perf_counter() - t0
-                cst = scene.render(w, h, s_spp, seed=0, crop=crop, stats=True, want_linear=False)["stats"]
-                crays = cst["n_closest_rays"] + cst["n_shadow_rays"]
-                cpu = {"value": crays / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
-                       "sample": "centre crop %dx%d of the %dx%d image plane at %d of %d spp: %d samples, %d rays, %.1f s wall; reference sources "
-                                 "built headless (oracle/_ref), deterministic RNG shim, %d-thread row pool" % (cw, ch, w, h, s_spp, spp, cw * ch * s_spp, crays, dt, cores),
-                       "msamples_per_s": cw * ch * s_spp / dt / 1e6}
-        except Exception as e:  # the baseline must never take the GPU number down with it
-            cpu = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
-
-    out = {
-        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": wl["label"], "scene": wl["scene"], "width": w, "height": h, "spp": spp, "max_bounces": 6, "nb_ech": 10,
-                   "seed": 0, "tiles": "32x32 round-robin over ranks" if world > 1 else "32x32",
-                   "l2": "256 MiB buffer rewritten before every step (L2 flush); the scene itself is a few MB and is re-read from L2 by design",
-                   "rays_per_step": rays, "samples_per_step": total["n_samples"], "rays_per_sample": rays / total["n_samples"],
-                   "variant": args.variant},
-        "msamples_per_s": total["n_samples"] / (ms_per_step * 1e-3) / 1e6,
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms.item(), "h2d_bytes_per_step": int(scene_bytes),
-                "d2h_bytes_per_step": int(h * w * 3 * 4), "steps": e2e_steps,
-                "what": "rt_scene_create (upload + precompute) + rt_render_device + gather + untile + D2H to pinned host, per step"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roof,
-        "cpu_baseline": cpu,
-        "work": total,
-        "work_executed": total_executed,
-    }
-    sys.stdout.flush()
-    os.write(json_fd, (json.dumps(out) + "\n").encode())
-    if world > 1:
-        dist.destroy_process_group()
+    b = Bench(args)
+    t_start = time.perf_counter()
+    warm = max(3, args.warmup)
+    long_run = args.workload in ("c4", "c5") and not args.spp
+    if long_run:
+        w_, s_, e_, ws_ = PLAN[args.workload]
+        out = b.measure(args.workload, wl, w_, s_, e_, ws_, headline=True)
+    else:
+        out = b.measure(args.workload, wl, warm, args.steps, max(3, min(args.steps, 5)), 0, headline=True)
+    per_scene = {}
+    if b.rank == 0:
+        per_scene[args.workload] = {k: out[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "msamples_per_s", "e2e", "roofline", "cpu_baseline", "config", "gpu_launches", "clocks")}
+    if args.scenes != "none":
+        for key in [k for k in args.scenes.split(",") if k and k != args.workload]:
+            w_, s_, e_, ws_ = PLAN[key]
+            r = b.measure(key, dict(WORKLOADS[key]), w_, s_, e_, ws_)
+            if b.rank == 0:
+                per_scene[key] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "msamples_per_s", "e2e", "roofline", "cpu_baseline", "config", "gpu_launches", "clocks")}
+            if os.environ.get("BENCH_DEBUG") and b.rank == 0:
+                sys.stderr.write("%s: %.0f Mrays/s, %.1f ms/step, e2e %.0f (%.0f s since start)\n" % (key, r["value"], r["ms_per_step"], r["e2e"]["value"], time.perf_counter() - t_start))
+    if b.rank == 0:
+        out["per_scene"] = {k: per_scene[k] for k in sorted(per_scene)}
+        out["bench_wall_s"] = time.perf_counter() - t_start
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
+    if b.world > 1:
+        b.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -114,13 +114,15 @@ class RtStats(C.Structure):
 
 
 # every symbol the two headers declare — tests check the libraries export exactly these
-RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy", "rt_release_cached_memory", "rt_scene_update_analytic",
+RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy", "rt_scene_retain",
+              "rt_render_device_image", "rt_render_multi", "rt_render_multi_device", "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free", "rt_release_cached_memory", "rt_scene_update_analytic",
               "rt_scene_check", "rt_scene_device_bytes", "rt_render_pixel_count", "rt_tile_layout", "rt_render", "rt_render_rgb8", "rt_quantize_device",
               "rt_render_device", "rt_untile_device",
               "rt_accum_create", "rt_accum_destroy", "rt_accum_reset", "rt_accum_add", "rt_accum_samples", "rt_accum_read",
               "rt_trace_primary", "rt_trace_rays", "rt_shade_rays", "rt_measure_fp32_peak"]
 HOST_SYMBOLS = ["hai_last_error", "hai_scene_new", "hai_scene_free", "hai_scene_setup", "hai_scene_dump",
                 "hai_scene_flatten", "hai_scene_kd_stats", "hai_scene_counts", "hai_default_camera", "hai_render",
+                "hai_render_multi", "hai_ray_trace_from_camera_multi",
                 "hai_scene_device", "hai_scene_invalidate_device", "hai_scene_move_sphere", "hai_scene_update_device", "hai_scene_load_file", "hai_ray_trace_from_camera", "hai_ray_trace_from_camera_rgb8", "hai_write_image_rgb8", "hai_write_exr",
                 "hai_preview_new", "hai_preview_free", "hai_preview_mouse", "hai_preview_motion", "hai_preview_resize", "hai_preview_invalidate",
                 "hai_preview_pass", "hai_preview_frame", "hai_preview_camera"]
@@ -149,6 +151,17 @@ rt.rt_render_rgb8.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtRende
 rt.rt_quantize_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
 rt.rt_render_device.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.POINTER(RtStats)]
+rt.rt_render_device_image.argtypes = rt.rt_render_device.argtypes
+rt.rt_scene_retain.argtypes = [C.c_void_p]
+rt.rt_scene_retain.restype = None
+rt.rt_scene_destroy.restype = None
+rt.rt_render_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p,
+                               C.POINTER(RtStats)]
+rt.rt_render_multi_device.argtypes = rt.rt_render_multi.argtypes
+rt.rt_ipc_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+rt.rt_ipc_open.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+rt.rt_ipc_close.argtypes = [C.c_int, C.c_void_p]
+rt.rt_ipc_free.argtypes = [C.c_int, C.c_void_p]
 rt.rt_untile_device.argtypes = [C.POINTER(RtRenderParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
 rt.rt_trace_primary.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p]
 rt.rt_trace_rays.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -178,6 +191,10 @@ host.hai_scene_counts.argtypes = [C.c_void_p, C.c_void_p]
 host.hai_default_camera.argtypes = [C.c_int, C.c_int, C.POINTER(RtCamera)]
 host.hai_render.argtypes = [C.c_void_p, C.c_int, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p,
                             C.c_void_p, C.POINTER(RtStats)]
+host.hai_render_multi.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(RtCamera), C.POINTER(RtRenderParams), C.c_void_p,
+                                  C.c_void_p, C.POINTER(RtStats)]
+host.hai_ray_trace_from_camera_multi.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_char_p,
+                                                 C.c_void_p]
 host.hai_scene_device.restype = C.c_void_p
 host.hai_scene_device.argtypes = [C.c_void_p, C.c_int]
 host.hai_scene_invalidate_device.argtypes = [C.c_void_p]
@@ -355,6 +372,27 @@ class Scene:
                                     lin.ctypes.data if lin is not None else None, C.byref(st)))
         return {"gamma": gam, "linear": lin, "stats": st.as_dict()}
 
+    def render_multi(self, devices, width, height, spp, seed=0, camera=None, want_linear=True, stats=False, **kw):
+        """hai_render_multi(): the frame on several GPUs of one box inside one call (rt_render_multi)."""
+        cam = camera or default_camera(width, height)
+        p = render_params(width, height, spp, seed=seed, collect_stats=stats, **kw)
+        x0, y0, x1, y1 = (p.x0, p.y0, p.x1, p.y1) if (p.x0 | p.y0 | p.x1 | p.y1) else (0, 0, width, height)
+        gam = np.zeros((y1 - y0, x1 - x0, 3), np.float32)
+        lin = np.zeros_like(gam) if want_linear else None
+        st = RtStats()
+        devs = (C.c_int * len(devices))(*devices)
+        _host_check(host.hai_render_multi(self.h, devs, len(devices), C.byref(cam), C.byref(p), gam.ctypes.data,
+                                          lin.ctypes.data if lin is not None else None, C.byref(st)))
+        return {"gamma": gam, "linear": lin, "stats": st.as_dict()}
+
+    def ray_trace_from_camera_multi(self, devices, width, height, nsamples, seed=0, ppm_path=None):
+        """ray_trace_from_camera() with RenderOptions::devices (upload to every device, render, optional P3 file)."""
+        out = np.zeros((height, width, 3), np.float32)
+        devs = (C.c_int * len(devices))(*devices)
+        _host_check(host.hai_ray_trace_from_camera_multi(self.h, devs, len(devices), width, height, nsamples, seed,
+                                                         ppm_path.encode() if ppm_path else None, out.ctypes.data))
+        return out
+
     def trace_primary(self, width, height, seed=0, device=0, camera=None, crop=None):
         cam = camera or default_camera(width, height)
         p = render_params(width, height, 1, seed=seed, crop=crop)
@@ -410,11 +448,11 @@ class Scene:
         return out
 
     def accumulator(self, width, height, seed=0, device=0, **kw):
-        """rt_accum_*: progressive accumulation over this scene's device copy (keep the Scene alive while it is used)."""
+        """rt_accum_*: progressive accumulation over this scene's device copy (the accumulator holds its own reference on it)."""
         return Accumulator(self, width, height, seed=seed, device=device, **kw)
 
     def preview(self, width, height, seed=0, device=0):
-        """host/Preview.h: the reference's mouse handlers + progressive passes (keep the Scene alive and unchanged)."""
+        """host/Preview.h: the reference's mouse handlers + progressive passes (the preview keeps refining the device copy it was created on)."""
         return Preview(self, width, height, seed=seed, device=device)
 
 

@@ -15,12 +15,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "hai719_rt.h"
@@ -704,28 +706,55 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
 // Progressive accumulation (rt_accum_add): `sum` holds each pixel's running sum over the `prior` samples of earlier
 // passes; this pass continues THAT sum with its own samples in order, stores it back and divides by prior + spp, so
 // the float additions are the very sequence a single render of prior + spp samples performs (main.cpp:188-195).
-__global__ void k_resolve(const float *samples, unsigned long long pixel_begin, unsigned int n_pixels, int spp,
-                          float *linear_out, float *gamma_out, float *sum, unsigned int prior) {
+// Output layout: packed (this rank's pixels in tile order) or — image_mode — the pixel's place in the row-major image
+// of the rendered rectangle. In image mode the buffers may live on ANOTHER GPU (peer-mapped over NVLink): every rank's
+// resolve then stores its tiles straight into rank 0's framebuffer — the multi-GPU "gather" is these stores, there is
+// no pack / collective / untile pass behind them.
+__global__ void k_resolve(const RenderArgs a, const unsigned int *xy, unsigned int n_pixels, float *linear_out, float *gamma_out,
+                          float *sum, unsigned int prior, int image_mode, int rx0, int ry0, int rw) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pixels) return;
-    const float *s = samples + 3ull * i * (unsigned int)spp;
-    const unsigned long long o = 3ull * (pixel_begin + i);
+    const int spp = a.spp;
+    const float *s = a.samples + 3ull * i * (unsigned int)spp;
+    const unsigned long long op = 3ull * (a.pixel_begin + i);   // packed position (the running sums are always packed)
+    unsigned long long o = op;
+    if (image_mode) {
+        int x, y;
+        if (xy) { const unsigned int v = __ldg(xy + i); x = (int)(v & 0xFFFFu); y = (int)(v >> 16); }
+        else packed_to_xy(a, (unsigned int)a.pixel_begin + i, x, y);
+        o = 3ull * ((unsigned long long)(y - ry0) * (unsigned long long)rw + (unsigned long long)(x - rx0));
+    }
     V3 acc = v3(0.f);
-    if (sum && prior) acc = v3(sum[o], sum[o + 1], sum[o + 2]);
+    if (sum && prior) acc = v3(sum[op], sum[op + 1], sum[op + 2]);
     for (int k = 0; k < spp; ++k) acc = acc + v3(s[3 * k], s[3 * k + 1], s[3 * k + 2]);
-    if (sum) { sum[o] = acc.x; sum[o + 1] = acc.y; sum[o + 2] = acc.z; }
+    if (sum) { sum[op] = acc.x; sum[op + 1] = acc.y; sum[op + 2] = acc.z; }
     acc = acc / (float)(prior + (unsigned int)spp);
     if (linear_out) { linear_out[o] = acc.x; linear_out[o + 1] = acc.y; linear_out[o + 2] = acc.z; }
     if (gamma_out) { gamma_out[o] = gamma_channel(acc.x); gamma_out[o + 1] = gamma_channel(acc.y); gamma_out[o + 2] = gamma_channel(acc.z); }
 }
 
-// main.cpp:258: (int)(255.f * min(1.f, c)); ::min(a, b) = a < b ? a : b (Functions.cpp:20), so a NaN goes through
-// and the reference's cast is undefined for it: defined here as 0, like any negative value
+// Ray counts of a wavefront chunk from its queue counters, for free: level L traced ctr[L][1] closest-hit rays (level 0:
+// every path) and lit ctr[L][3] hits; every hit fires nb_ech shadow rays at each light (Scene.h:305-334), traced or
+// proven unoccluded. tally[0] += closest rays, tally[1] += hits.
+__global__ void k_wf_tally(const unsigned int *ctr, unsigned int n_paths, int levels, unsigned long long *tally) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long closest = n_paths, hits = 0;
+    for (int l = 0; l < levels; ++l) {
+        if (l > 0) closest += ctr[WF_NCTR * l + 1];
+        hits += ctr[WF_NCTR * l + 3];
+    }
+    tally[0] += closest;
+    tally[1] += hits;
+}
+
+// main.cpp:258: (int)(255.f * std::min<float>(1.f, c)); std::min(a, b) = (b < a) ? b : a, so a NaN pixel becomes 1.f and
+// is written as 255 (the float P3 writer of host/Renderer.cpp does the same); negative values, whose int the reference
+// would print with a minus sign that no PPM reader accepts, are written as 0
 __global__ void k_quantize(const float *v, size_t n, uint8_t *out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float c = v[i];
-    const float m = 255.f * (1.f < c ? 1.f : c);
+    const float m = 255.f * (c < 1.f ? c : 1.f);
     out[i] = m > 0.f ? (uint8_t)(int)m : (uint8_t)0;
 }
 
@@ -840,6 +869,9 @@ struct Scratch {
     unsigned long long *counters = nullptr;   // [0] work counter, [1..10] stats
     TileRec *d_tiles = nullptr; unsigned int *d_tile_off = nullptr; size_t tiles_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float *out_img = nullptr; size_t out_cap = 0;       // framebuffer(s) of rt_render / rt_render_rgb8 / rt_render_multi: no cudaMalloc per frame
+    uint8_t *out_bytes = nullptr; size_t out_bytes_cap = 0;
+    cudaStream_t stream = nullptr;                      // rt_render_multi: this device's stream (one host thread per device)
     // arena for the scene's own arrays (textures, primitives, hierarchies): bump-allocated blocks, reset when the scene
     // is destroyed and reused by the next scene on this device — a re-upload performs no cudaMalloc/cudaFree at all
     struct Block { char *base; size_t cap, used; };
@@ -876,6 +908,9 @@ struct Scratch {
         if (d_tile_off) cudaFree(d_tile_off);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (out_img) cudaFree(out_img);
+        if (out_bytes) cudaFree(out_bytes);
+        if (stream) cudaStreamDestroy(stream);
         *this = Scratch();
     }
 };
@@ -884,7 +919,20 @@ std::mutex g_scratch_mu;
 std::map<int, std::vector<Scratch>> g_scratch_pool;   // device -> idle scratch sets
 }  // namespace
 
+namespace {
+// device copies of per-rank tile tables for rt_untile_device, kept per (device, geometry) so that the
+// per-frame call allocates nothing and never synchronises
+struct UntileKey {
+    int device, w, h, x0, y0, x1, y1, tw, th, nr, rk;
+    bool operator<(const UntileKey &o) const { return memcmp(this, &o, sizeof *this) < 0; }
+};
+struct UntileTab { TileRec *tiles = nullptr; unsigned int *off = nullptr; int n = 0; unsigned int pixels = 0; };
+std::map<UntileKey, UntileTab> g_untile;
+std::mutex g_untile_mu;
+}  // namespace
+
 struct RtScene : Scratch {
+    std::atomic<int> refs{1};   // the creator's handle + one per accumulator / rt_scene_retain: rt_scene_destroy frees at 0
     int device = 0;
     int sm_count = 0;
     DScene d{};
@@ -1037,12 +1085,12 @@ int persistent_grid(RtScene *s, const void *kernel, int threads) {
 
 int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
     if (paths <= s->wf_cap && max_bounces <= s->wf_bounces) return RT_OK;
+    paths = std::max(paths, s->wf_cap); max_bounces = std::max(max_bounces, s->wf_bounces);   // grow-only in both dimensions
     if (s->wf_f4) cudaFree(s->wf_f4);
     if (s->wf_rng) cudaFree(s->wf_rng);
     if (s->wf_q) cudaFree(s->wf_q);
     if (s->wf_rec) cudaFree(s->wf_rec);
     s->wf_f4 = nullptr; s->wf_rng = nullptr; s->wf_q = nullptr; s->wf_rec = nullptr; s->wf_cap = 0; s->wf_bounces = 0;
-    paths = std::max(paths, s->wf_cap); max_bounces = std::max(max_bounces, s->wf_bounces);
     RT_CUDA(cudaMalloc((void **)&s->wf_f4, (9 + RT_LC_MAXC / 4) * paths * sizeof(float4)));
     RT_CUDA(cudaMalloc((void **)&s->wf_rng, paths * sizeof(uint2)));
     RT_CUDA(cudaMalloc((void **)&s->wf_q, 4 * paths * sizeof(unsigned int)));
@@ -1077,6 +1125,22 @@ int ensure_scratch(RtScene *s, size_t sample_floats, size_t n_tiles, size_t cam_
         s->tiles_cap = n_tiles + 1;
     }
     if (!s->ev0) { RT_CUDA(cudaEventCreate(&s->ev0)); RT_CUDA(cudaEventCreate(&s->ev1)); }
+    return RT_OK;
+}
+
+int ensure_out(RtScene *s, size_t floats, size_t bytes) {
+    if (floats > s->out_cap) {
+        if (s->out_img) cudaFree(s->out_img);
+        s->out_img = nullptr; s->out_cap = 0;
+        RT_CUDA(cudaMalloc((void **)&s->out_img, floats * sizeof(float)));
+        s->out_cap = floats;
+    }
+    if (bytes > s->out_bytes_cap) {
+        if (s->out_bytes) cudaFree(s->out_bytes);
+        s->out_bytes = nullptr; s->out_bytes_cap = 0;
+        RT_CUDA(cudaMalloc((void **)&s->out_bytes, bytes));
+        s->out_bytes_cap = bytes;
+    }
     return RT_OK;
 }
 
@@ -1184,8 +1248,11 @@ int rt_device_count(void) {
     return ok;
 }
 
+void rt_scene_retain(RtScene *s) { if (s) s->refs.fetch_add(1); }
+
 void rt_scene_destroy(RtScene *s) {
     if (!s) return;
+    if (s->refs.fetch_sub(1) > 1) return;   // an accumulator or a retained handle still renders from these arrays
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();   // nothing of this scene may still be in flight when its arrays go
     s->arena_reset();
@@ -1206,6 +1273,15 @@ int rt_release_cached_memory(int device) {
     }
     RT_CUDA(cudaSetDevice(device));
     for (Scratch &sc : idle) sc.release();
+    {   // the tile tables rt_untile_device keeps per geometry on this device
+        std::lock_guard<std::mutex> lock(g_untile_mu);
+        for (auto it = g_untile.begin(); it != g_untile.end();) {
+            if (it->first.device != device) { ++it; continue; }
+            if (it->second.tiles) cudaFree(it->second.tiles);
+            if (it->second.off) cudaFree(it->second.off);
+            it = g_untile.erase(it);
+        }
+    }
     return RT_OK;
 }
 
@@ -1364,7 +1440,7 @@ int64_t rt_tile_layout(const RtRenderParams *p, int32_t *out, int64_t cap) {
 // The render behind rt_render_device (sample_base 0, no running sum) and rt_accum_add (samples sample_base ..
 // sample_base + spp - 1 of every pixel, continuing the per-pixel sums in d_sum).
 static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRenderParams *p, float *d_gamma, float *d_linear,
-                              void *cuda_stream, RtStats *stats, unsigned int sample_base, float *d_sum) {
+                              void *cuda_stream, RtStats *stats, unsigned int sample_base, float *d_sum, int image_mode = 0) {
     if (!s || !camera || !p) return fail(RT_ERR_INVALID, "null argument");
     Rect r;
     int rc = resolve_rect(*p, r);
@@ -1539,7 +1615,9 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
             RT_CUDA(cudaGetLastError());
             ++launches;
         }
-        k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(s->samples, pb, (unsigned int)np, p->spp, d_linear, d_gamma, d_sum, sample_base);
+        if (wavefront && !wf_fuse) k_wf_tally<<<1, 32, 0, st>>>(s->wf_ctr, (unsigned int)a.n_paths, p->max_bounces, s->counters + 11);
+        k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(a, cam_split ? s->pix_xy : nullptr, (unsigned int)np, d_linear, d_gamma, d_sum, sample_base,
+                                                                 image_mode, r.x0, r.y0, r.x1 - r.x0);
         RT_CUDA(cudaGetLastError());
         ++launches;
     }
@@ -1551,6 +1629,12 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
         stats->kernel_ms = ms;
         stats->n_launches = launches;
         stats->n_chunks = (uint32_t)((n_pixels + chunk_pixels - 1) / chunk_pixels);
+        if (wavefront && !wf_fuse && !want_stats) {   // ray counts from the queue counters (k_wf_tally): exact, and free
+            unsigned long long c[2];
+            RT_CUDA(cudaMemcpy(c, s->counters + 11, sizeof c, cudaMemcpyDeviceToHost));
+            stats->n_closest_rays = c[0];
+            stats->n_shadow_rays = c[1] * (unsigned long long)s->d.n_lights * (unsigned long long)p->nb_ech;
+        }
         if (want_stats) {
             unsigned long long c[11];
             RT_CUDA(cudaMemcpy(c, s->counters, sizeof c, cudaMemcpyDeviceToHost));
@@ -1567,17 +1651,11 @@ int rt_render_device(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     return render_device_impl(s, camera, p, d_gamma, d_linear, cuda_stream, stats, 0u, nullptr);
 }
 
-namespace {
-// device copies of per-rank tile tables for rt_untile_device, kept per (device, geometry) so that the
-// per-frame call allocates nothing and never synchronises
-struct UntileKey {
-    int device, w, h, x0, y0, x1, y1, tw, th, nr, rk;
-    bool operator<(const UntileKey &o) const { return memcmp(this, &o, sizeof *this) < 0; }
-};
-struct UntileTab { TileRec *tiles = nullptr; unsigned int *off = nullptr; int n = 0; unsigned int pixels = 0; };
-std::map<UntileKey, UntileTab> g_untile;
-std::mutex g_untile_mu;
-}  // namespace
+int rt_render_device_image(RtScene *s, const RtCamera *camera, const RtRenderParams *p, float *d_gamma_image, float *d_linear_image,
+                           void *cuda_stream, RtStats *stats) {
+    return render_device_impl(s, camera, p, d_gamma_image, d_linear_image, cuda_stream, stats, 0u, nullptr, 1);
+}
+
 
 int rt_untile_device(const RtRenderParams *p, const float *d_packed, const int64_t *pixel_offsets, float *d_image,
                      int device, void *cuda_stream) {
@@ -1605,11 +1683,24 @@ int rt_untile_device(const RtRenderParams *p, const float *d_packed, const int64
                 UntileTab t;
                 t.n = (int)tiles.size();
                 t.pixels = off.back();
+                if (g_untile.size() >= 256) {   // a viewer that keeps resizing: bound the cache (entries of this device go)
+                    for (auto jt = g_untile.begin(); jt != g_untile.end();) {
+                        if (jt->first.device != device) { ++jt; continue; }
+                        if (jt->second.tiles) cudaFree(jt->second.tiles);
+                        if (jt->second.off) cudaFree(jt->second.off);
+                        jt = g_untile.erase(jt);
+                    }
+                }
                 if (t.n) {
-                    RT_CUDA(cudaMalloc((void **)&t.tiles, tiles.size() * sizeof(TileRec)));
-                    RT_CUDA(cudaMalloc((void **)&t.off, off.size() * sizeof(unsigned int)));
-                    RT_CUDA(cudaMemcpy(t.tiles, tiles.data(), tiles.size() * sizeof(TileRec), cudaMemcpyHostToDevice));
-                    RT_CUDA(cudaMemcpy(t.off, off.data(), off.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+                    cudaError_t e = cudaMalloc((void **)&t.tiles, tiles.size() * sizeof(TileRec));
+                    if (e == cudaSuccess) e = cudaMalloc((void **)&t.off, off.size() * sizeof(unsigned int));
+                    if (e == cudaSuccess) e = cudaMemcpy(t.tiles, tiles.data(), tiles.size() * sizeof(TileRec), cudaMemcpyHostToDevice);
+                    if (e == cudaSuccess) e = cudaMemcpy(t.off, off.data(), off.size() * sizeof(unsigned int), cudaMemcpyHostToDevice);
+                    if (e != cudaSuccess) {
+                        if (t.tiles) cudaFree(t.tiles);
+                        if (t.off) cudaFree(t.off);
+                        RT_CUDA(e);
+                    }
                 }
                 it = g_untile.emplace(key, t).first;
             }
@@ -1634,39 +1725,38 @@ int rt_render(RtScene *s, const RtCamera *camera, const RtRenderParams *p, float
     if (np <= 0) { if (stats) memset(stats, 0, sizeof *stats); return RT_OK; }
     const size_t rect_px = (size_t)(r.x1 - r.x0) * (size_t)(r.y1 - r.y0);
     const int n_out = (gamma_rgb ? 1 : 0) + (linear_rgb ? 1 : 0);
-    float *d_packed = nullptr, *d_image = nullptr;
-    RT_CUDA(cudaMalloc((void **)&d_packed, (size_t)np * 3 * sizeof(float) * n_out));
-    struct Free { float *&p; ~Free() { if (p) cudaFree(p); } } f1{d_packed}, f2{d_image};
-    float *dg = gamma_rgb ? d_packed : nullptr;
-    float *dl = linear_rgb ? d_packed + (gamma_rgb ? (size_t)np * 3 : 0) : nullptr;
+    const bool sharded = p->n_ranks > 1;
     RtStats local;
+    if (!sharded) {
+        // the resolve kernel writes every pixel at its place in the row-major image: no packed buffer, no untile pass
+        if ((rc = ensure_out(s, rect_px * 3 * n_out, 0))) return rc;
+        float *dg = gamma_rgb ? s->out_img : nullptr;
+        float *dl = linear_rgb ? s->out_img + (gamma_rgb ? rect_px * 3 : 0) : nullptr;
+        rc = render_device_impl(s, camera, p, dg, dl, nullptr, stats ? stats : &local, 0u, nullptr, 1);
+        if (rc) return rc;
+        if (gamma_rgb) RT_CUDA(cudaMemcpy(gamma_rgb, dg, rect_px * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (linear_rgb) RT_CUDA(cudaMemcpy(linear_rgb, dl, rect_px * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        return RT_OK;
+    }
+    // one rank of a sharded render with a HOST image: other ranks' tiles must stay untouched, so the packed pixels come
+    // back and are scattered row by row on the host (ranks on one box write one device image instead: rt_render_multi)
+    if ((rc = ensure_out(s, (size_t)np * 3 * n_out, 0))) return rc;
+    float *dg = gamma_rgb ? s->out_img : nullptr;
+    float *dl = linear_rgb ? s->out_img + (gamma_rgb ? (size_t)np * 3 : 0) : nullptr;
     rc = rt_render_device(s, camera, p, dg, dl, nullptr, stats ? stats : &local);
     if (rc) return rc;
-    const bool sharded = p->n_ranks > 1;
-    if (!sharded) {
-        RT_CUDA(cudaMalloc((void **)&d_image, rect_px * 3 * sizeof(float)));
-        float *outs[2] = {gamma_rgb, linear_rgb};
-        const float *srcs[2] = {dg, dl};
-        for (int k = 0; k < 2; ++k) {
-            if (!outs[k]) continue;
-            if ((rc = rt_untile_device(p, srcs[k], nullptr, d_image, s->device, nullptr))) return rc;
-            RT_CUDA(cudaMemcpy(outs[k], d_image, rect_px * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-        }
-    } else {
-        // other ranks' tiles must stay untouched: bring the packed pixels back and scatter rows on the host
-        std::vector<float> h((size_t)np * 3);
-        float *outs[2] = {gamma_rgb, linear_rgb};
-        const float *srcs[2] = {dg, dl};
-        const int rw = r.x1 - r.x0;
-        for (int k = 0; k < 2; ++k) {
-            if (!outs[k]) continue;
-            RT_CUDA(cudaMemcpy(h.data(), srcs[k], h.size() * sizeof(float), cudaMemcpyDeviceToHost));
-            for (size_t t = 0; t < s->h_tiles.size(); ++t) {
-                const TileRec &tr = s->h_tiles[t];
-                const float *src = h.data() + 3 * (size_t)s->h_tile_off[t];
-                for (int y = 0; y < tr.h; ++y)
-                    memcpy(outs[k] + 3 * ((size_t)(tr.y0 - r.y0 + y) * rw + (tr.x0 - r.x0)), src + 3 * (size_t)y * tr.w, (size_t)tr.w * 3 * sizeof(float));
-            }
+    std::vector<float> h((size_t)np * 3);
+    float *outs[2] = {gamma_rgb, linear_rgb};
+    const float *srcs[2] = {dg, dl};
+    const int rw = r.x1 - r.x0;
+    for (int k = 0; k < 2; ++k) {
+        if (!outs[k]) continue;
+        RT_CUDA(cudaMemcpy(h.data(), srcs[k], h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t t = 0; t < s->h_tiles.size(); ++t) {
+            const TileRec &tr = s->h_tiles[t];
+            const float *src = h.data() + 3 * (size_t)s->h_tile_off[t];
+            for (int y = 0; y < tr.h; ++y)
+                memcpy(outs[k] + 3 * ((size_t)(tr.y0 - r.y0 + y) * rw + (tr.x0 - r.x0)), src + 3 * (size_t)y * tr.w, (size_t)tr.w * 3 * sizeof(float));
         }
     }
     return RT_OK;
@@ -1690,24 +1780,16 @@ int rt_render_rgb8(RtScene *s, const RtCamera *camera, const RtRenderParams *p, 
     const int64_t np = rt_render_pixel_count(p);
     if (np <= 0) { if (stats) memset(stats, 0, sizeof *stats); return RT_OK; }
     const size_t rect_px = (size_t)(r.x1 - r.x0) * (size_t)(r.y1 - r.y0);
-    float *d_packed = nullptr, *d_image = nullptr;
-    uint8_t *d_bytes = nullptr;
-    struct Free { void *&p; ~Free() { if (p) cudaFree(p); } } f1{(void *&)d_packed}, f2{(void *&)d_image}, f3{(void *&)d_bytes};
-    RT_CUDA(cudaMalloc((void **)&d_packed, (size_t)np * 3 * sizeof(float)));
-    RT_CUDA(cudaMalloc((void **)&d_image, rect_px * 3 * sizeof(float)));
-    RT_CUDA(cudaMalloc((void **)&d_bytes, rect_px * 3));
     RtStats local;
-    rc = rt_render_device(s, camera, p, d_packed, nullptr, nullptr, stats ? stats : &local);
-    if (rc) return rc;
-    if (p->n_ranks > 1) RT_CUDA(cudaMemset(d_image, 0, rect_px * 3 * sizeof(float)));
-    RtRenderParams q = *p;
-    int64_t off0 = 0;
     if (p->n_ranks > 1) {
-        // untile only this rank's tiles: a one-rank view of the same tile list
+        // only this rank's tiles are written: quantise the packed pixels, scatter rows on the host
+        if ((rc = ensure_out(s, (size_t)np * 3, (size_t)np * 3))) return rc;
+        rc = rt_render_device(s, camera, p, s->out_img, nullptr, nullptr, stats ? stats : &local);
+        if (rc) return rc;
         const int rw = r.x1 - r.x0;
         std::vector<uint8_t> hb((size_t)np * 3);
-        if ((rc = rt_quantize_device(d_packed, (size_t)np * 3, d_bytes, s->device, nullptr))) return rc;
-        RT_CUDA(cudaMemcpy(hb.data(), d_bytes, hb.size(), cudaMemcpyDeviceToHost));
+        if ((rc = rt_quantize_device(s->out_img, (size_t)np * 3, s->out_bytes, s->device, nullptr))) return rc;
+        RT_CUDA(cudaMemcpy(hb.data(), s->out_bytes, hb.size(), cudaMemcpyDeviceToHost));
         for (size_t t = 0; t < s->h_tiles.size(); ++t) {
             const TileRec &tr = s->h_tiles[t];
             const uint8_t *src = hb.data() + 3 * (size_t)s->h_tile_off[t];
@@ -1716,9 +1798,140 @@ int rt_render_rgb8(RtScene *s, const RtCamera *camera, const RtRenderParams *p, 
         }
         return RT_OK;
     }
-    if ((rc = rt_untile_device(&q, d_packed, &off0, d_image, s->device, nullptr))) return rc;
-    if ((rc = rt_quantize_device(d_image, rect_px * 3, d_bytes, s->device, nullptr))) return rc;
-    RT_CUDA(cudaMemcpy(rgb8, d_bytes, rect_px * 3, cudaMemcpyDeviceToHost));
+    if ((rc = ensure_out(s, rect_px * 3, rect_px * 3))) return rc;
+    rc = render_device_impl(s, camera, p, s->out_img, nullptr, nullptr, stats ? stats : &local, 0u, nullptr, 1);
+    if (rc) return rc;
+    if ((rc = rt_quantize_device(s->out_img, rect_px * 3, s->out_bytes, s->device, nullptr))) return rc;
+    RT_CUDA(cudaMemcpy(rgb8, s->out_bytes, rect_px * 3, cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+// ---- multi-GPU render inside one call (replaces the thread-per-row block main.cpp:229-238) -----------
+// One host thread per device; the scene is replicated (scenes[i] on its own device); tile t of the 32x32 grid goes to
+// device t % n (round-robin: the cost per pixel varies > 100x across an image). Every device's resolve kernel stores
+// its pixels straight into the framebuffer on scenes[0]'s device through peer-mapped memory (NVLink / NVSwitch): the
+// "gather" of the framebuffer is those stores; there is no packed buffer, no collective and no untile pass.
+namespace {
+int enable_peer(int from, int to) {
+    if (from == to) return RT_OK;
+    int can = 0;
+    RT_CUDA(cudaDeviceCanAccessPeer(&can, from, to));
+    if (!can) return fail(RT_ERR_CUDA, "device " + std::to_string(from) + " cannot map memory of device " + std::to_string(to) + " (no peer access)");
+    RT_CUDA(cudaSetDevice(from));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(to, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) RT_CUDA(e);
+    cudaGetLastError();
+    return RT_OK;
+}
+}  // namespace
+
+int rt_render_multi_device(RtScene *const *scenes, int n, const RtCamera *camera, const RtRenderParams *p, float *d_gamma_image,
+                           float *d_linear_image, RtStats *stats) {
+    if (!scenes || n < 1 || !camera || !p) return fail(RT_ERR_INVALID, "null argument");
+    if (!d_gamma_image && !d_linear_image) return fail(RT_ERR_INVALID, "no output buffer");
+    if (p->n_ranks > 1) return fail(RT_ERR_INVALID, "rt_render_multi shards over its devices itself: n_ranks must be <= 1");
+    for (int i = 0; i < n; ++i) {
+        if (!scenes[i]) return fail(RT_ERR_INVALID, "null scene");
+        for (int j = 0; j < i; ++j)
+            if (scenes[j]->device == scenes[i]->device) return fail(RT_ERR_INVALID, "rt_render_multi: two scenes on the same device");
+    }
+    int rc;
+    for (int i = 1; i < n; ++i)
+        if ((rc = enable_peer(scenes[i]->device, scenes[0]->device))) return rc;
+    std::vector<RtStats> st((size_t)n);
+    std::vector<int> rcs((size_t)n, RT_OK);
+    std::vector<std::string> errs((size_t)n);
+    auto work = [&](int i) {
+        RtScene *s = scenes[i];
+        RtRenderParams q = *p;
+        q.rank = i; q.n_ranks = n;
+        int r = RT_OK;
+        if (cudaSetDevice(s->device) != cudaSuccess) r = fail(RT_ERR_CUDA, "cudaSetDevice failed");
+        if (!r && !s->stream && cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) r = fail(RT_ERR_CUDA, "cudaStreamCreate failed");
+        if (!r) r = render_device_impl(s, camera, &q, d_gamma_image, d_linear_image, s->stream, &st[i], 0u, nullptr, 1);
+        if (!r && cudaStreamSynchronize(s->stream) != cudaSuccess) r = fail(RT_ERR_CUDA, std::string("render on device ") + std::to_string(s->device) + ": " + cudaGetErrorString(cudaGetLastError()));
+        rcs[i] = r;
+        if (r) errs[i] = g_err;
+    };
+    std::vector<std::thread> threads;
+    for (int i = 1; i < n; ++i) threads.emplace_back(work, i);
+    work(0);
+    for (std::thread &t : threads) t.join();
+    for (int i = 0; i < n; ++i)
+        if (rcs[i]) return fail(rcs[i], errs[i]);
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int i = 0; i < n; ++i) {
+            const RtStats &x = st[i];
+            stats->n_samples += x.n_samples; stats->n_closest_rays += x.n_closest_rays; stats->n_shadow_rays += x.n_shadow_rays;
+            stats->n_sphere_tests += x.n_sphere_tests; stats->n_square_tests += x.n_square_tests; stats->n_mesh_tests += x.n_mesh_tests;
+            stats->n_node_visits += x.n_node_visits; stats->n_tri_tests += x.n_tri_tests; stats->n_tri_full += x.n_tri_full;
+            stats->n_tex_fetches += x.n_tex_fetches; stats->n_random += x.n_random;
+            stats->kernel_ms = std::max(stats->kernel_ms, x.kernel_ms);   // the devices run side by side
+            stats->n_launches += x.n_launches; stats->n_tiles += x.n_tiles; stats->n_chunks = std::max(stats->n_chunks, x.n_chunks);
+        }
+    }
+    RT_CUDA(cudaSetDevice(scenes[0]->device));
+    return RT_OK;
+}
+
+int rt_render_multi(RtScene *const *scenes, int n, const RtCamera *camera, const RtRenderParams *p, float *gamma_rgb, float *linear_rgb,
+                    RtStats *stats) {
+    if (!scenes || n < 1 || !scenes[0] || !camera || !p) return fail(RT_ERR_INVALID, "null argument");
+    if (!gamma_rgb && !linear_rgb) return fail(RT_ERR_INVALID, "no output buffer");
+    Rect r;
+    int rc = resolve_rect(*p, r);
+    if (rc) return rc;
+    RtScene *s0 = scenes[0];
+    RT_CUDA(cudaSetDevice(s0->device));
+    const size_t rect_px = (size_t)(r.x1 - r.x0) * (size_t)(r.y1 - r.y0);
+    const int n_out = (gamma_rgb ? 1 : 0) + (linear_rgb ? 1 : 0);
+    if ((rc = ensure_out(s0, rect_px * 3 * n_out, 0))) return rc;
+    float *dg = gamma_rgb ? s0->out_img : nullptr;
+    float *dl = linear_rgb ? s0->out_img + (gamma_rgb ? rect_px * 3 : 0) : nullptr;
+    if ((rc = rt_render_multi_device(scenes, n, camera, p, dg, dl, stats))) return rc;
+    if (gamma_rgb) RT_CUDA(cudaMemcpy(gamma_rgb, dg, rect_px * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (linear_rgb) RT_CUDA(cudaMemcpy(linear_rgb, dl, rect_px * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+// ---- framebuffer shared between PROCESSES (one rank per GPU, e.g. under torchrun): CUDA IPC ---------------------------
+// Rank 0 allocates the image (rt_ipc_alloc) and hands the 64-byte handle to the other ranks by any means; they map it
+// (rt_ipc_open) and pass the mapped pointer to rt_render_device_image: their resolve kernels then store into rank 0's
+// memory over NVLink, exactly as the threads of rt_render_multi do inside one process.
+int rt_ipc_alloc(int device, size_t bytes, void **d_ptr, unsigned char *handle64) {
+    if (!d_ptr || !handle64 || bytes == 0) return fail(RT_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    int rc = select_device(device, nullptr);
+    if (rc) return rc;
+    void *p = nullptr;
+    RT_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); RT_CUDA(e); }
+    memcpy(handle64, &h, 64);
+    *d_ptr = p;
+    return RT_OK;
+}
+int rt_ipc_open(int device, const unsigned char *handle64, void **d_ptr) {
+    if (!d_ptr || !handle64) return fail(RT_ERR_INVALID, "null argument");
+    int rc = select_device(device, nullptr);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    RT_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RT_OK;
+}
+int rt_ipc_close(int device, void *d_ptr) {
+    if (!d_ptr) return RT_OK;
+    RT_CUDA(cudaSetDevice(device));
+    RT_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return RT_OK;
+}
+int rt_ipc_free(int device, void *d_ptr) {
+    if (!d_ptr) return RT_OK;
+    RT_CUDA(cudaSetDevice(device));
+    RT_CUDA(cudaFree(d_ptr));
     return RT_OK;
 }
 
@@ -1728,7 +1941,8 @@ int rt_render_rgb8(RtScene *s, const RtCamera *camera, const RtRenderParams *p, 
 // pixel (sample indices continue where the last pass stopped, so the random streams are those of one long render) and
 // refreshes the mean. After passes of s1, s2, ... samples the frame is bit-identical to ONE render at s1 + s2 + ... spp.
 struct RtAccum {
-    RtScene *scene = nullptr;
+    RtScene *scene = nullptr;       // retained: the device arrays outlive the caller's rt_scene_destroy
+    int device = 0;
     RtRenderParams geo{};
     Rect rect{};
     int64_t np = 0;                 // packed pixels of this rank
@@ -1757,7 +1971,7 @@ int rt_accum_create(RtScene *s, const RtRenderParams *geometry, RtAccum **out) {
     RtAccum *a = new (std::nothrow) RtAccum;
     if (!a) return fail(RT_ERR_OOM, "out of host memory");
     struct Guard { RtAccum *a; bool keep = false; ~Guard() { if (!keep) delete a; } } guard{a};
-    a->scene = s; a->geo = g; a->rect = r;
+    a->geo = g; a->rect = r; a->device = s->device;
     a->np = rt_render_pixel_count(&g);
     a->rect_px = (size_t)(r.x1 - r.x0) * (size_t)(r.y1 - r.y0);
     const size_t nb = (size_t)std::max<int64_t>(a->np, 1) * 3 * sizeof(float);
@@ -1769,6 +1983,8 @@ int rt_accum_create(RtScene *s, const RtRenderParams *geometry, RtAccum **out) {
     RT_CUDA(cudaMemset(a->d_sum, 0, nb));
     RT_CUDA(cudaMemset(a->d_gamma, 0, nb));
     RT_CUDA(cudaMemset(a->d_linear, 0, nb));
+    rt_scene_retain(s);
+    a->scene = s;
     guard.keep = true;
     *out = a;
     return RT_OK;
@@ -1776,8 +1992,10 @@ int rt_accum_create(RtScene *s, const RtRenderParams *geometry, RtAccum **out) {
 
 void rt_accum_destroy(RtAccum *a) {
     if (!a) return;
-    cudaSetDevice(a->scene->device);
+    cudaSetDevice(a->device);
+    RtScene *s = a->scene;
     delete a;
+    rt_scene_destroy(s);   // drops the accumulator's reference; frees the scene if the caller already let go of it
 }
 
 int rt_accum_reset(RtAccum *a) {

@@ -9,16 +9,20 @@ void check(int status, const char *what) {
 }  // namespace
 
 Preview::Preview(const DeviceScene &scene, Camera &camera, int w, int h, const RenderOptions &opt)
-    : scene_(scene), camera_(camera), opt_(opt), w_(w), h_(h) {
-    rebuild();
+    : scene_(scene.handle()), camera_(camera), opt_(opt), w_(w), h_(h) {
+    rt_scene_retain(scene_);
+    try { rebuild(); } catch (...) { rt_scene_destroy(scene_); throw; }
 }
 
-Preview::~Preview() { rt_accum_destroy(accum_); }
+Preview::~Preview() {
+    rt_accum_destroy(accum_);
+    rt_scene_destroy(scene_);   // drops this preview's reference
+}
 
 void Preview::rebuild() {
     if (accum_) { rt_accum_destroy(accum_); accum_ = nullptr; }
     const RtRenderParams p = make_params(w_, h_, 1, opt_);
-    check(rt_accum_create(scene_.handle(), &p, &accum_), "rt_accum_create");
+    check(rt_accum_create(scene_, &p, &accum_), "rt_accum_create");
     dirty_ = true;
     rgb8_samples_ = 0;
 }

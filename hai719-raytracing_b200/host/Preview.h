@@ -20,6 +20,8 @@ public:
     enum State { Down = 0, Up = 1 };                        // GLUT_DOWN, GLUT_UP
 
     // `camera` is the caller's (the reference keeps one global Camera, main.cpp:43); it must outlive the preview.
+    // The preview holds its own reference on the scene's device arrays: destroying or re-uploading the DeviceScene
+    // while the preview lives is safe (it goes on refining the scene it was created on).
     Preview(const DeviceScene &scene, Camera &camera, int w, int h, const RenderOptions &opt = RenderOptions());
     ~Preview();
     Preview(const Preview &) = delete;
@@ -41,7 +43,7 @@ public:
 
 private:
     void rebuild();
-    const DeviceScene &scene_;
+    RtScene *scene_;                                        // retained (rt_scene_retain): the device copy outlives its DeviceScene if need be
     Camera &camera_;
     RenderOptions opt_;
     int w_, h_;

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <thread>
 
 namespace hai719 {
 
@@ -20,7 +21,37 @@ DeviceScene::DeviceScene(const Scene &scene, int device) : device_(device) {
     check(rt_scene_create(&flat.desc, device, &handle_), "rt_scene_create");
 }
 
+DeviceScene::DeviceScene(const RtSceneDesc &flat, int device) : device_(device) {
+    check(rt_scene_create(&flat, device, &handle_), "rt_scene_create");
+}
+
 DeviceScene::~DeviceScene() { rt_scene_destroy(handle_); }
+
+MultiDeviceScene::MultiDeviceScene(const Scene &scene, const std::vector<int> &devices) {
+    if (devices.empty()) throw RenderError(RT_ERR_INVALID, "MultiDeviceScene: no device given");
+    FlatScene flat;
+    scene.flatten(flat);
+    copies_.resize(devices.size());
+    std::vector<std::exception_ptr> errors(devices.size());
+    std::vector<std::thread> threads;
+    auto upload = [&](size_t i) {
+        try { copies_[i].reset(new DeviceScene(flat.desc, devices[i])); } catch (...) { errors[i] = std::current_exception(); }
+    };
+    for (size_t i = 1; i < devices.size(); ++i) threads.emplace_back(upload, i);
+    upload(0);
+    for (std::thread &t : threads) t.join();
+    for (const std::exception_ptr &e : errors) if (e) std::rethrow_exception(e);
+}
+
+std::vector<RtScene *> MultiDeviceScene::handles() const {
+    std::vector<RtScene *> h;
+    for (const auto &c : copies_) h.push_back(c->handle());
+    return h;
+}
+
+void MultiDeviceScene::update_analytic(const Scene &scene) {
+    for (auto &c : copies_) c->update_analytic(scene);
+}
 
 void DeviceScene::update_analytic(const Scene &scene) {
     FlatScene flat;
@@ -67,9 +98,42 @@ void ray_trace_from_camera(const DeviceScene &scene, Camera &camera, int w, int 
         std::cout << "Could not open file: " << opt.ppm_path << std::endl;
 }
 
+void ray_trace_from_camera(const MultiDeviceScene &scenes, Camera &camera, int w, int h, unsigned int nsamples,
+                           std::vector<Vec3> &image, const RenderOptions &opt, RtStats *stats) {
+    camera.apply();
+    MatrixUtilities mu;
+    mu.updateMatrices(camera);
+    RtCamera cam;
+    mu.fill(cam);
+    const RtRenderParams p = make_params(w, h, nsamples, opt);
+    const bool full = (p.x0 | p.y0 | p.x1 | p.y1) == 0;
+    const int rw = full ? w : p.x1 - p.x0, rh = full ? h : p.y1 - p.y0;
+    if (opt.verbose)
+        std::cout << "Ray tracing a " << rw << " x " << rh << " image on " << scenes.size() << " CUDA devices with "
+                  << nsamples << " samples per pixel" << std::endl;
+    image.assign((size_t)rw * (size_t)rh, Vec3(0, 0, 0));
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<float> linear;
+    if (!opt.exr_path.empty()) linear.assign((size_t)rw * (size_t)rh * 3, 0.f);
+    const std::vector<RtScene *> handles = scenes.handles();
+    check(rt_render_multi(handles.data(), (int)handles.size(), &cam, &p, reinterpret_cast<float *>(image.data()),
+                          linear.empty() ? nullptr : linear.data(), stats), "rt_render_multi");
+    const auto t1 = std::chrono::steady_clock::now();
+    if (opt.verbose) std::cout << "  Done in " << std::chrono::duration<double>(t1 - t0).count() << " seconds" << std::endl;
+    if (!opt.exr_path.empty() && !write_exr(opt.exr_path, rw, rh, linear.data()))
+        std::cout << "Could not open file: " << opt.exr_path << std::endl;
+    if (!opt.ppm_path.empty() && !write_ppm_p3(opt.ppm_path, rw, rh, image))
+        std::cout << "Could not open file: " << opt.ppm_path << std::endl;
+}
+
 void ray_trace_from_camera(const Scene &scene, Camera &camera, int w, int h, unsigned int nsamples,
                            std::vector<Vec3> &image, const RenderOptions &opt, RtStats *stats) {
-    DeviceScene dev(scene, opt.device);
+    if (opt.devices.size() > 1) {
+        MultiDeviceScene devs(scene, opt.devices);
+        ray_trace_from_camera(devs, camera, w, h, nsamples, image, opt, stats);
+        return;
+    }
+    DeviceScene dev(scene, opt.devices.empty() ? opt.device : opt.devices[0]);
     ray_trace_from_camera(dev, camera, w, h, nsamples, image, opt, stats);
 }
 

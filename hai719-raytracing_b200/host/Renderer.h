@@ -9,6 +9,7 @@
 // There is no CPU path: if the CUDA library reports an error, RenderError is thrown.
 #ifndef HAI719_HOST_RENDERER_H
 #define HAI719_HOST_RENDERER_H
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -29,6 +30,11 @@ struct RenderOptions {
     int nb_ech = NB_ECH;
     uint32_t seed = 0;
     int device = 0;
+    // Several B200s of one box: devices = {0, 1, ..., 7} renders the frame on all of them inside the one call (one host
+    // thread per device, 32x32 tiles round-robin, every device storing its tiles straight into devices[0]'s framebuffer
+    // over NVLink: rt_render_multi). This is what replaces the reference's thread-per-scanline block (main.cpp:229-238).
+    // Empty = the single `device` above. The image is bit-identical whatever the device count.
+    std::vector<int> devices;
     int x0 = 0, y0 = 0, x1 = 0, y1 = 0;     // pixel rectangle, all 0 = full image
     int rank = 0, n_ranks = 1;              // tile sharding (see RtRenderParams)
     int tile_w = 0, tile_h = 0;
@@ -49,6 +55,7 @@ struct RenderOptions {
 class DeviceScene {
 public:
     DeviceScene(const Scene &scene, int device = 0);
+    DeviceScene(const RtSceneDesc &flat, int device);       // an already flattened scene (MultiDeviceScene uploads one flatten() n times)
     ~DeviceScene();
     DeviceScene(const DeviceScene &) = delete;
     DeviceScene &operator=(const DeviceScene &) = delete;
@@ -61,12 +68,27 @@ private:
     int device_ = 0;
 };
 
+// The same scene on several devices of one box (uploads run side by side, one thread per device).
+class MultiDeviceScene {
+public:
+    MultiDeviceScene(const Scene &scene, const std::vector<int> &devices);
+    size_t size() const { return copies_.size(); }
+    const DeviceScene &operator[](size_t i) const { return *copies_[i]; }
+    std::vector<RtScene *> handles() const;
+    void update_analytic(const Scene &scene);
+private:
+    std::vector<std::unique_ptr<DeviceScene>> copies_;
+};
+
 RtRenderParams make_params(int w, int h, unsigned int nsamples, const RenderOptions &opt);
 
 // Render `image` (w*h gamma-corrected Vec3, row 0 = top, like main.cpp:202) from the camera.
 void ray_trace_from_camera(const DeviceScene &scene, Camera &camera, int w, int h, unsigned int nsamples,
                            std::vector<Vec3> &image, const RenderOptions &opt = RenderOptions(), RtStats *stats = nullptr);
-// Convenience: uploads the scene, renders, frees.
+// The same on every device of `scenes` at once (rt_render_multi); opt.rank / n_ranks must be unset.
+void ray_trace_from_camera(const MultiDeviceScene &scenes, Camera &camera, int w, int h, unsigned int nsamples,
+                           std::vector<Vec3> &image, const RenderOptions &opt = RenderOptions(), RtStats *stats = nullptr);
+// Convenience: uploads the scene (to opt.devices if given, else opt.device), renders, frees.
 void ray_trace_from_camera(const Scene &scene, Camera &camera, int w, int h, unsigned int nsamples,
                            std::vector<Vec3> &image, const RenderOptions &opt = RenderOptions(), RtStats *stats = nullptr);
 

@@ -23,6 +23,9 @@ struct HaiScene {
 namespace {
 thread_local std::string g_err;
 template <class F> int guarded(F &&f) {
+    // the C ABI reports through return codes; the C++ API's own default (exit on a missing mesh, like the reference)
+    // is restored when the call returns
+    struct Restore { bool before; ~Restore() { hai719::set_fatal_throws(before); } } restore{hai719::fatal_throws()};
     try {
         hai719::set_fatal_throws(true);
         f();
@@ -138,6 +141,38 @@ int hai_render(HaiScene *s, int device, const RtCamera *cam, const RtRenderParam
     const int rc = rt_render(h, cam, params, gamma_rgb, linear_rgb, stats);
     if (rc != RT_OK) g_err = rt_last_error();
     return rc;
+}
+
+int hai_render_multi(HaiScene *s, const int *devices, int n_devices, const RtCamera *cam, const RtRenderParams *params,
+                     float *gamma_rgb, float *linear_rgb, RtStats *stats) {
+    if (!s || !devices || n_devices < 1) { g_err = "hai_render_multi: bad argument"; return -1; }
+    std::vector<RtScene *> handles;
+    for (int i = 0; i < n_devices; ++i) {
+        RtScene *h = hai_scene_device(s, devices[i]);
+        if (!h) return -1;
+        handles.push_back(h);
+    }
+    const int rc = rt_render_multi(handles.data(), n_devices, cam, params, gamma_rgb, linear_rgb, stats);
+    if (rc != RT_OK) g_err = rt_last_error();
+    return rc;
+}
+
+int hai_ray_trace_from_camera_multi(HaiScene *s, const int *devices, int n_devices, int w, int h, int nsamples, uint32_t seed,
+                                    const char *ppm_path, float *gamma_rgb) {
+    return guarded([&] {
+        if (!s || !devices || n_devices < 1) throw std::runtime_error("hai_ray_trace_from_camera_multi: bad argument");
+        Camera camera;
+        camera.resize(w, h);
+        camera.move(0., 0., -3.1);
+        hai719::RenderOptions opt;
+        opt.seed = seed;
+        opt.devices.assign(devices, devices + n_devices);
+        opt.ppm_path = ppm_path ? ppm_path : "";
+        opt.verbose = false;
+        std::vector<Vec3> image;
+        hai719::ray_trace_from_camera(s->scene, camera, w, h, (unsigned)nsamples, image, opt);   // uploads to every device, renders, frees
+        if (gamma_rgb) std::memcpy(gamma_rgb, image.data(), image.size() * sizeof(Vec3));
+    });
 }
 
 int hai_ray_trace_from_camera(HaiScene *s, int device, int w, int h, int nsamples, uint32_t seed, const char *ppm_path,

@@ -1,7 +1,8 @@
 // hai719_render — the headless stand-in for "press r" in the reference's GLUT shell
 // (main.cpp:321-326 -> ray_trace_from_camera). Builds one of the reference's scenes with the host
 // API, renders it on the GPU and writes the same P3 rendu.ppm.
-//   hai719_render [--scene N | --scene-file FILE] [--w W --h H] [--spp S] [--seed K] [--assets DIR] [--out FILE] [--p6 1 | --png 1] [--exr FILE] [--device D]
+//   hai719_render [--scene N | --scene-file FILE] [--w W --h H] [--spp S] [--seed K] [--assets DIR] [--out FILE] [--p6 1 | --png 1] [--exr FILE] [--device D | --gpus N]
+// --gpus N: render on devices 0..N-1 of this box at once (tiles round-robin, one framebuffer on device 0 written over NVLink)
 //                 [--preview PASSES [--orbit PIXELS]]
 // --preview: progressive refinement instead of one render (host/Preview.h): PASSES passes of --spp samples each, every
 // intermediate frame written as <out>.<pass>.ppm (binary); with --orbit the left mouse button is "dragged" PIXELS to
@@ -23,7 +24,7 @@ int main(int argc, char **argv) {
     std::string assets, out = "./rendu.ppm", scene_file;
     bool p6 = false, png = false;
     std::string exr;   // float render: also write the linear image as OpenEXR
-    int preview = 0, orbit = 0;
+    int preview = 0, orbit = 0, gpus = 1;
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string k = argv[i];
         const char *v = argv[i + 1];
@@ -35,6 +36,7 @@ int main(int argc, char **argv) {
         else if (k == "--assets") assets = v;
         else if (k == "--out") out = v;
         else if (k == "--device") device = std::atoi(v);
+        else if (k == "--gpus") gpus = std::atoi(v);
         else if (k == "--scene-file") scene_file = v;
         else if (k == "--p6") p6 = std::atoi(v) != 0;
         else if (k == "--png") png = std::atoi(v) != 0;
@@ -56,6 +58,7 @@ int main(int argc, char **argv) {
     hai719::RenderOptions opt;
     opt.seed = seed;
     opt.device = device;
+    if (gpus > 1) for (int d = 0; d < gpus; ++d) opt.devices.push_back(d);
     opt.ppm_path = out;
     opt.exr_path = exr;
     std::vector<Vec3> image;

@@ -44,6 +44,13 @@ int hai_default_camera(int w, int h, RtCamera *out);
  * in rt_render(). This is the call a user of the drop-in makes: the e2e number in bench.py. */
 int hai_render(HaiScene *s, int device, const RtCamera *cam, const RtRenderParams *params, float *gamma_rgb,
                float *linear_rgb, RtStats *stats);
+/* The same on several devices of one box at once (rt_render_multi: tiles round-robin over the devices, every device
+ * writing its tiles into devices[0]'s framebuffer over NVLink). Device copies are cached per device like hai_render's. */
+int hai_render_multi(HaiScene *s, const int *devices, int n_devices, const RtCamera *cam, const RtRenderParams *params,
+                     float *gamma_rgb, float *linear_rgb, RtStats *stats);
+/* ray_trace_from_camera() with RenderOptions::devices: upload to every device, render, write the P3 file, free. */
+int hai_ray_trace_from_camera_multi(HaiScene *s, const int *devices, int n_devices, int w, int h, int nsamples, uint32_t seed,
+                                    const char *ppm_path, float *gamma_rgb);
 /* The device-resident scene handle (uploading if needed), for rt_render_device() etc. */
 RtScene *hai_scene_device(HaiScene *s, int device);
 
@@ -83,8 +90,9 @@ int hai_write_exr(const char *path, int w, int h, const float *rgb);
  * left = rotate, 1 middle = zoom, 2 right = move; state 0 down, 1 up) drive a Camera placed like main.cpp:418, and
  * every hai_preview_pass() adds pass_spp samples per pixel to the frame on the GPU (rt_accum_*). Moving the camera
  * restarts the accumulation. hai_preview_frame() returns the current mean: h*w*3 bytes and/or h*w*3 gamma floats.
- * A preview refers to the scene's device copy: free it before hai_scene_setup / hai_scene_load_file /
- * hai_scene_invalidate_device / hai_scene_free on the same scene. */
+ * A preview holds its own reference on the scene's device copy (rt_scene_retain): after hai_scene_setup /
+ * hai_scene_load_file / hai_scene_invalidate_device / hai_scene_free it keeps refining the scene it was created on;
+ * create a new preview to see the new scene. */
 typedef struct HaiPreview HaiPreview;
 HaiPreview *hai_preview_new(HaiScene *s, int device, int w, int h, uint32_t seed);
 void hai_preview_free(HaiPreview *p);

@@ -223,6 +223,11 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out);
 /* Frees the scene's arrays. Its render scratch (sample, camera-ray and path-state buffers, grow-only) is kept in a
  * per-device pool and handed to the next rt_scene_create on that device; rt_release_cached_memory frees the pool. */
 void rt_scene_destroy(RtScene *scene);
+/* A scene handle is reference counted: rt_scene_create returns it with one reference, rt_scene_retain adds one, and
+ * every accumulator (rt_accum_create) holds one of its own. rt_scene_destroy drops one reference; the device arrays
+ * are released with the last. A caller may therefore destroy / re-create its scene while a preview still refines the
+ * old one: the preview keeps rendering the arrays it was created on until it is destroyed itself. */
+void rt_scene_retain(RtScene *scene);
 int rt_release_cached_memory(int device);
 /* SURVEY 8(f)-1, incremental re-upload for animated scenes: rewrite the spheres, squares, lights and their culling
  * hierarchy IN PLACE from `desc` (same counts as the uploaded scene; meshes, textures and normal maps of `desc` are
@@ -264,6 +269,35 @@ int rt_quantize_device(const float *d_values, size_t n, uint8_t *d_bytes, int de
 int rt_render_device(RtScene *scene, const RtCamera *camera, const RtRenderParams *params,
                      float *d_gamma_rgb, float *d_linear_rgb, void *cuda_stream, RtStats *stats);
 
+/* The same render, but every pixel is stored at its place in the ROW-MAJOR image of the rendered rectangle
+ * (rect_h * rect_w * 3 floats, row 0 = top) instead of this rank's packed tile order. The image pointers may be
+ * peer-mapped memory of ANOTHER GPU (cudaDeviceEnablePeerAccess in-process, rt_ipc_open across processes): with
+ * tile sharding (rank / n_ranks) every rank's resolve kernel then writes its tiles straight into one shared
+ * framebuffer over NVLink — no packed buffer, no gather collective, no untile pass. Pixels of other ranks' tiles
+ * are not touched. Asynchronous on `cuda_stream` unless stats != NULL. */
+int rt_render_device_image(RtScene *scene, const RtCamera *camera, const RtRenderParams *params,
+                           float *d_gamma_image, float *d_linear_image, void *cuda_stream, RtStats *stats);
+
+/* Multi-GPU render in ONE call — what replaces the thread-per-scanline block of ray_trace_from_camera()
+ * (main.cpp:229-238) on a box with several B200s. scenes[0..n-1] are the same scene uploaded to n DISTINCT devices;
+ * one host thread per device renders the tiles t with t % n == i (params->rank / n_ranks must be unset) and its
+ * resolve kernel stores them directly into the framebuffer on scenes[0]'s device through peer-mapped memory.
+ * rt_render_multi copies that framebuffer to the HOST buffers (either may be NULL), like rt_render;
+ * rt_render_multi_device leaves it in the device buffers given (on scenes[0]'s device, row-major rectangle).
+ * Both are synchronous. stats: counts summed over the devices, kernel_ms = the slowest device. The image is
+ * bit-identical to rt_render on one device (the random streams are keyed by absolute pixel). */
+int rt_render_multi(RtScene *const *scenes, int n_devices, const RtCamera *camera, const RtRenderParams *params,
+                    float *gamma_rgb, float *linear_rgb, RtStats *stats);
+int rt_render_multi_device(RtScene *const *scenes, int n_devices, const RtCamera *camera, const RtRenderParams *params,
+                           float *d_gamma_image, float *d_linear_image, RtStats *stats);
+
+/* One framebuffer shared by one PROCESS per GPU (torchrun, MPI): rank 0 allocates it and publishes the 64-byte CUDA
+ * IPC handle, the others map it and hand the mapped pointer to rt_render_device_image. */
+int rt_ipc_alloc(int device, size_t bytes, void **d_ptr, unsigned char *handle64);
+int rt_ipc_open(int device, const unsigned char *handle64, void **d_ptr);
+int rt_ipc_close(int device, void *d_ptr);   /* a pointer from rt_ipc_open */
+int rt_ipc_free(int device, void *d_ptr);    /* a pointer from rt_ipc_alloc */
+
 /* SURVEY 8(f)-4, progressive accumulation for an interactive preview. The reference renders a frame in one go on a
  * key press (main.cpp:200-263, 321-326) and shows nothing until it is finished. An accumulator keeps every pixel's
  * running sample sum on the device: each rt_accum_add() traces `spp` MORE samples per pixel — their indices continue
@@ -271,7 +305,8 @@ int rt_render_device(RtScene *scene, const RtCamera *camera, const RtRenderParam
  * After passes of s1, s2, ... samples the frame read back is bit-identical to ONE rt_render at spp = s1 + s2 + ...
  * (trace_line's additions happen in the same order, main.cpp:188-195). `geometry` supplies everything of
  * RtRenderParams except spp (image size, rectangle, tile sharding, bounces, seed, variant). rt_accum_reset() forgets
- * the samples (camera moved, scene updated); the scene must outlive the accumulator. All calls are synchronous. */
+ * the samples (camera moved, scene updated). The accumulator holds a reference on the scene (rt_scene_retain), so
+ * rt_scene_destroy by the caller cannot pull the device arrays from under it. All calls are synchronous. */
 typedef struct RtAccum RtAccum;
 int rt_accum_create(RtScene *scene, const RtRenderParams *geometry, RtAccum **out);
 void rt_accum_destroy(RtAccum *accum);

@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <random>
 #include <string>
 #include <thread>
 #include <unistd.h>
@@ -45,6 +46,32 @@
 #include "KDTree.cpp"
 
 #include "det_rng.h"
+
+// ---- ray counting (libref_count.so only; recipe in oracle/Makefile) ------------------------------------------------
+// The COUNTING build compiles this translation unit (which holds the reference's header-only Scene, Scene.h) with
+// -finstrument-functions: gcc then calls __cyg_profile_func_enter at the entry of every function of the listed files,
+// inlined or not. The hook compares the function address with Scene::computeIntersection (Scene.h:202) and
+// Scene::computeShadow (Scene.h:235) and counts: the reference's own calls, no source line of the reference touched.
+// The counting library is never timed (the hook slows it down); with the deterministic stream it traces exactly the
+// rays the timed deterministic library traces, so its counts are that run's numerator.
+#ifdef ORACLE_COUNT_RAYS
+#pragma GCC diagnostic ignored "-Wpmf-conversions"
+namespace oracle {
+static thread_local uint64_t t_closest = 0, t_shadow = 0;
+static void *fn_closest = nullptr, *fn_shadow = nullptr;
+static std::atomic<uint64_t> g_closest(0), g_shadow(0);
+}
+extern "C" {
+__attribute__((no_instrument_function)) void __cyg_profile_func_enter(void *fn, void *) {
+    if (fn == oracle::fn_closest) ++oracle::t_closest;
+    else if (fn == oracle::fn_shadow) ++oracle::t_shadow;
+}
+__attribute__((no_instrument_function)) void __cyg_profile_func_exit(void *, void *) {}
+}
+#define ORACLE_NOINSTR __attribute__((no_instrument_function))
+#else
+#define ORACLE_NOINSTR
+#endif
 
 namespace oracle {
 static thread_local DetCtx g_ctx = {0u, 0u, 0ull};
@@ -308,10 +335,18 @@ double ref_render(void *h, int w, int ht, int spp, uint32_t seed, int threads, i
     const int cw = x1 - x0, ch = y1 - y0;
     std::atomic<int> next_row(0);
     std::atomic<uint64_t> total_random(0);
+#ifdef ORACLE_COUNT_RAYS
+    oracle::fn_closest = (void *)(&Scene::computeIntersection);
+    oracle::fn_shadow = (void *)(&Scene::computeShadow);
+    oracle::g_closest = 0; oracle::g_shadow = 0;
+#endif
     auto t0 = std::chrono::steady_clock::now();
     auto worker = [&]() {
         MatrixUtilities lmu = mu;  // flags are clear: no GL reads on worker threads
         oracle::ctx().total = 0;
+#ifdef ORACLE_COUNT_RAYS
+        oracle::t_closest = 0; oracle::t_shadow = 0;
+#endif
         for (;;) {
             int r = next_row.fetch_add(1);
             if (r >= ch) break;
@@ -330,7 +365,13 @@ double ref_render(void *h, int w, int ht, int spp, uint32_t seed, int threads, i
                     lmu.screen_space_to_world_space_ray(u, v, pos, dir);
                     Ray ray(pos, dir, oracle::det_next());
                     if (s == 0 && prim_ids) {
+#ifdef ORACLE_COUNT_RAYS
+                        const uint64_t keep = oracle::t_closest;   // the id probe is the driver's call, not the render's
+#endif
                         RaySceneIntersection hit = scene.computeIntersection(ray);
+#ifdef ORACLE_COUNT_RAYS
+                        oracle::t_closest = keep;
+#endif
                         uint32_t *p = prim_ids + 4 * o;
                         p[0] = hit.typeOfIntersectedObject;
                         p[1] = hit.typeOfIntersectedObject ? hit.objectIndex : 0u;
@@ -347,6 +388,9 @@ double ref_render(void *h, int w, int ht, int spp, uint32_t seed, int threads, i
             }
         }
         total_random += oracle::ctx().total;
+#ifdef ORACLE_COUNT_RAYS
+        oracle::g_closest += oracle::t_closest; oracle::g_shadow += oracle::t_shadow;
+#endif
     };
     if (threads == 1) {
         worker();
@@ -406,6 +450,57 @@ void ref_shade_rays(void *h, size_t n, const float *org, const float *dir, const
         Vec3 c = scene.rayTrace(ray);
         rgb[3 * i] = c[0]; rgb[3 * i + 1] = c[1]; rgb[3 * i + 2] = c[2];
     }
+}
+
+// Ray counts of the last ref_render call: {computeIntersection calls, computeShadow calls}. Only the counting build
+// (libref_count.so) counts; the others return 0 and leave `out2` zeroed.
+int ref_ray_counts(uint64_t *out2) {
+    out2[0] = 0; out2[1] = 0;
+#ifdef ORACLE_COUNT_RAYS
+    out2[0] = oracle::g_closest.load(); out2[1] = oracle::g_shadow.load();
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+// ray_trace_from_camera() AS THE REFERENCE THREADS IT (main.cpp:229-238): one std::thread per scanline, all created at
+// once and joined at the end; jitter and time from a thread_local mt19937 seeded by random_device (main.cpp:181,189-192).
+// In libref_stock.so random_float() is the reference's own: ONE function-static mt19937 shared by all those threads
+// without a lock (Functions.cpp:4-8) — the data race and its cache-line ping-pong are part of what is timed.
+// Rows y0..y1-1, columns x0..x1-1 of a w x ht image; gamma_rgb may be null. Returns wall seconds.
+double ref_render_rows(void *h, int w, int ht, int spp, int x0, int y0, int x1, int y1, float *gamma_rgb) {
+    Scene &scene = *((RefScene *)h)->scene;
+    MatrixUtilities mu;
+    make_camera(w, ht, mu);
+    const int cw = x1 - x0;
+    auto t0 = std::chrono::steady_clock::now();
+    auto trace_line = [&](int y) {
+        static thread_local std::mt19937 rng{std::random_device{}()};
+        std::uniform_real_distribution<float> dist(0.f, 1.f);
+        MatrixUtilities lmu = mu;
+        for (int x = x0; x < x1; ++x) {
+            Vec3 acc(0, 0, 0);
+            for (int s = 0; s < spp; ++s) {
+                float u = ((float)(x) + dist(rng)) / w;
+                float v = ((float)(y) + dist(rng)) / ht;
+                Vec3 pos, dir;
+                lmu.screen_space_to_world_space_ray(u, v, pos, dir);
+                acc += scene.rayTrace(Ray(pos, dir, dist(rng)));
+            }
+            acc /= (unsigned int)spp;
+            gamma_correct(acc);
+            if (gamma_rgb) {
+                const size_t o = (size_t)(x - x0) + (size_t)(y - y0) * cw;
+                gamma_rgb[3 * o] = acc[0]; gamma_rgb[3 * o + 1] = acc[1]; gamma_rgb[3 * o + 2] = acc[2];
+            }
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int y = y0; y < y1; ++y) threads.emplace_back(trace_line, y);
+    for (auto &t : threads) t.join();
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
 }
 
 int ref_is_deterministic(void) {

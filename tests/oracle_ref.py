@@ -12,6 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ASSETS = os.path.join(ROOT, "assets", "_ref")
 LIB_DET = os.path.join(ROOT, "oracle", "_ref", "libref_det.so")
 LIB_STOCK = os.path.join(ROOT, "oracle", "_ref", "libref_stock.so")
+LIB_COUNT = os.path.join(ROOT, "oracle", "_ref", "libref_count.so")   # deterministic build that counts the reference's ray calls (never timed)
+LIB_GLIBC = os.path.join(ROOT, "oracle", "_ref", "libref_glibc.so")   # deterministic build without oracle/libm_pin.cpp
+KINDS = {"det": LIB_DET, "stock": LIB_STOCK, "count": LIB_COUNT, "glibc": LIB_GLIBC}
 
 # scene ids: main.cpp:421-432 order; 11 = setup_flamingo_lake (unregistered); 100 = config 5
 SCENES = {
@@ -21,14 +24,19 @@ SCENES = {
 }
 
 
-def available(stock=False):
-    return os.path.exists(LIB_STOCK if stock else LIB_DET) and os.path.isdir(os.path.join(ASSETS, "mesh"))
+def available(stock=False, kind=None):
+    path = KINDS[kind] if kind else (LIB_STOCK if stock else LIB_DET)
+    return os.path.exists(path) and os.path.isdir(os.path.join(ASSETS, "mesh"))
 
 
 class Ref:
-    def __init__(self, stock=False):
-        self.lib = C.CDLL(LIB_STOCK if stock else LIB_DET)
+    def __init__(self, stock=False, kind=None):
+        self.kind = kind or ("stock" if stock else "det")
+        self.lib = C.CDLL(KINDS[self.kind])
         L = self.lib
+        L.ref_ray_counts.argtypes = [C.c_void_p]
+        L.ref_render_rows.restype = C.c_double
+        L.ref_render_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_scene_create.restype = C.c_void_p
         L.ref_scene_create.argtypes = [C.c_int, C.c_float, C.c_uint32, C.c_char_p]
         L.ref_scene_destroy.argtypes = [C.c_void_p]
@@ -83,7 +91,20 @@ class RefScene:
         nrand = C.c_uint64(0)
         secs = self.ref.lib.ref_render(self.h, w, h, spp, seed, threads, x0, y0, x1, y1, lin.ctypes.data,
                                        gam.ctypes.data, ids.ctypes.data if want_ids else None, C.byref(nrand))
-        return {"linear": lin, "gamma": gam, "ids": ids, "seconds": secs, "n_random": nrand.value}
+        out = {"linear": lin, "gamma": gam, "ids": ids, "seconds": secs, "n_random": nrand.value}
+        if self.ref.kind == "count":
+            c = np.zeros(2, np.uint64)
+            self.ref.lib.ref_ray_counts(c.ctypes.data)
+            out["n_closest_rays"], out["n_shadow_rays"] = int(c[0]), int(c[1])
+        return out
+
+    def render_rows(self, w, h, spp, crop=None, want_image=False):
+        """The reference's own threading (main.cpp:229-238): one std::thread per scanline of the crop, all at once;
+        jitter from a thread_local mt19937. With the stock library random_float() is the shared racy generator."""
+        x0, y0, x1, y1 = crop if crop else (0, 0, w, h)
+        gam = np.zeros((y1 - y0, x1 - x0, 3), np.float32) if want_image else None
+        secs = self.ref.lib.ref_render_rows(self.h, w, h, spp, x0, y0, x1, y1, gam.ctypes.data if want_image else None)
+        return {"gamma": gam, "seconds": secs}
 
     def trace_rays(self, org, dirs, time=None):
         org = np.ascontiguousarray(org, np.float32)

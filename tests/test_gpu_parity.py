@@ -336,32 +336,36 @@ def test_stochastic_render_agrees_with_the_unmodified_reference(gpu, assets, nam
       * z = (mean_gpu - mean_ref) / sqrt(se_gpu^2 + se_ref^2) has |mean| < 0.15 and standard deviation < 1.4 over the image
         (1.0 for perfectly normal estimates; path-traced pixels have heavier tails: measured 1.07-1.10 on these scenes),
       * |z| <= 4 for at least 98 % of the values (measured: 99.8-99.9 %), pixels without noise on both sides are equal,
-      * the total energy of the two mean images agrees within 10 of its estimated standard errors (no global bias; the
-        reference side is time-seeded, so the bands are wide enough for this test never to fail by chance: the same
-        statistics between two correct implementations stayed below 0.04 / 1.10 / 0.2 % / 4.6 in every calibration run (the
-        total-energy figure is consistently positive, +1.4 to +4.6: the deterministic stream renders ~0.03 % brighter than
-        the mt19937 build, unexplained and three orders of magnitude inside the RGB tolerance),
-        while a wrong normalisation or a missing light term moves them by orders of magnitude)."""
+      * the total energy of the two mean images agrees within 4 standard errors, the standard error taken from the
+        spread of the per-render totals (no assumption about pixels).
+    The reference side runs on ONE thread here. Round 1 compared against the 16-thread stock build and saw the GPU
+    ~0.03 % brighter (+1.4 to +4.6 standard errors, always positive). Cause, measured on the CPU with 64 renders a
+    side (scripts/energy_offset_probe.py, profiles/r02_notes.md): the reference's shared mt19937 is advanced by all
+    scanline threads WITHOUT a lock (Functions.cpp:4-8), and that data race makes the reference itself render darker
+    than its own race-free single-thread run (debug_refraction: stock16 - stock1 = -0.023 % +- 0.006 %, z = -4.0;
+    deterministic - stock1 = +0.005 % +- 0.006 %, z = +1.0; Cornell: +0.03 % +- 0.18 %, z = +0.2). The counter-based
+    stream agrees with the race-free generator; the offset was the reference's race, not the product's stream."""
     import oracle_ref
     if not oracle_ref.available(stock=True):
         pytest.skip("oracle/_ref/libref_stock.so not built")
-    n = 8
+    n = 12
     s = gpu.Scene(name, aspect=w / h)
     G = np.stack([s.render(w, h, spp, seed=100 + i)["linear"].astype(np.float64) for i in range(n)])
     r = oracle_ref.Ref(stock=True).scene(name, aspect=w / h)
-    R = np.stack([r.render(w, h, spp, seed=i, want_ids=False)["linear"].astype(np.float64) for i in range(n)])
+    R = np.stack([r.render(w, h, spp, seed=i, threads=1, want_ids=False)["linear"].astype(np.float64) for i in range(n)])
     r.close()
     assert not np.array_equal(R[0], R[1])                                    # really stochastic
     mg, mr = G.mean(0), R.mean(0)
     se = np.sqrt(G.var(0, ddof=1) / n + R.var(0, ddof=1) / n)
     noisy = se > 0
     z = (mg - mr)[noisy] / se[noisy]
-    z_total = (mg - mr).sum() / np.sqrt((se ** 2).sum())
+    tg, tr = G.sum((1, 2, 3)), R.sum((1, 2, 3))
+    z_total = (tg.mean() - tr.mean()) / np.sqrt(tg.var(ddof=1) / n + tr.var(ddof=1) / n)
     print(name, "z mean %.3f std %.3f, |z|>4: %.3f %%, total-energy z %.2f" % (z.mean(), z.std(), 100 * (np.abs(z) > 4).mean(), z_total))
     assert abs(z.mean()) < 0.15 and z.std() < 1.4
     assert (np.abs(z) <= 4).mean() >= 0.98
     assert np.abs(mg - mr)[~noisy].max(initial=0.0) <= 1e-6
-    assert abs(z_total) < 10.0
+    assert abs(z_total) < 4.0
 
 
 @pytest.mark.parametrize("name,kw", [("cornell_box", {}), ("random_spheres", {}), ("flamingo_pond", {}), ("backrooms_pool", {}),

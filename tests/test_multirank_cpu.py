@@ -80,3 +80,58 @@ def test_two_rank_gather_and_untile_over_gloo(hb, tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29517", str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:]
+
+
+WORKER_SHARED = r'''
+import importlib, os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+hb = importlib.import_module("hai719-raytracing_b200")
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+w, h, crop = 150, 70, (7, 3, 140, 66)
+x0, y0, x1, y1 = crop
+rw, rh = x1 - x0, y1 - y0
+# rank 0 owns the framebuffer and publishes a 64-byte handle (bench.py: rt_ipc_alloc + dist.broadcast of the CUDA IPC
+# handle; here a file stands in for the device allocation and its name, padded to 64 bytes, for the handle)
+handle = torch.zeros(64, dtype=torch.uint8)
+if rank == 0:
+    path = os.path.join(sys.argv[2], "fb.bin")
+    np.full(rh * rw * 3, -1.0, np.float32).tofile(path)
+    raw = os.path.basename(path).encode()
+    handle[:len(raw)] = torch.tensor(list(raw), dtype=torch.uint8)
+dist.broadcast(handle, src=0)
+name = bytes(handle.tolist()).rstrip(b"\0").decode()
+fb = np.memmap(os.path.join(sys.argv[2], name), np.float32, "r+", shape=(rh * rw * 3,))
+# every rank stores its tiles at the place k_resolve's image mode computes: 3 * ((y - ry0) * rect_w + (x - rx0))
+tiles = hb.tile_layout(hb.render_params(w, h, 1, crop=crop, rank=rank, n_ranks=world, tile=(32, 32)))
+for tx, ty, tw, th in tiles:
+    for y in range(ty, ty + th):
+        for x in range(tx, tx + tw):
+            o = 3 * ((y - y0) * rw + (x - x0))
+            assert fb[o] == -1.0                       # nobody else writes this pixel
+            fb[o:o + 3] = (x + 1000.0 * y, 2.0 * x - y, float(rank))
+fb.flush()
+dist.barrier()                                         # bench.py: stream sync + barrier before rank 0 reads
+if rank == 0:
+    img = np.fromfile(os.path.join(sys.argv[2], name), np.float32).reshape(rh, rw, 3)
+    yy, xx = np.mgrid[y0:y1, x0:x1]
+    assert np.array_equal(img[..., 0], (xx + 1000.0 * yy).astype(np.float32)) and np.array_equal(img[..., 1], (2.0 * xx - yy).astype(np.float32))
+    ntx = -(-rw // 32)
+    owner = ((yy - y0) // 32 * ntx + (xx - x0) // 32) % world
+    assert np.array_equal(img[..., 2], owner.astype(np.float32))      # tile t belongs to rank t % world
+    print("OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_store_into_one_shared_framebuffer_over_gloo(hb, tmp_path):
+    """The N > 1 path of bench.py without a GPU: handle broadcast, each rank's tiles stored at their row-major place in
+    rank 0's framebuffer, barrier, read-back. No packed buffers, no gather, no untile."""
+    script = tmp_path / "worker_shared.py"
+    script.write_text(WORKER_SHARED)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29519")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29519", str(script), ROOT, str(tmp_path)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:]

@@ -75,3 +75,61 @@ def test_oracle_ray_kats_match_golden(ref):
         assert np.array_equal(ids, g["ids"])
         assert np.array_equal(aux.view(np.uint32), g["aux"].view(np.uint32))
         assert np.array_equal(rgb.view(np.uint32), g["rgb"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["mesh", "flamingo_pond", "flamingo_lake", "backrooms_pool"])
+def test_libm_pin_changes_no_pixel(ref, name):
+    """'the oracle is not the reference as it runs on this box' — how many pixels does the atan2f / asinf pin
+    (oracle/libm_pin.cpp) change? libref_glibc.so is the same deterministic build WITHOUT the pin. glibc's functions
+    differ from the correctly rounded value by one ulp on 16 % / 7 % of arguments, but the sky lookup truncates
+    u * width to a texel (Scene.h:157-158): a one-ulp change of u moves the texel only when u * width sits within an ulp of
+    an integer. Measured: 0 of 57 600 pixels (x 4 spp x up to 6 bounces of sky lookups) on every sky scene; the bar is
+    BASELINE's 0.01 % allowance."""
+    import oracle_ref
+    if not oracle_ref.available(kind="glibc"):
+        pytest.skip("oracle/_ref/libref_glibc.so not built")
+    w, h, spp = 320, 180, 4
+    a = ref.scene(name, aspect=w / h).render(w, h, spp, seed=0, threads=0, want_ids=False)
+    b = oracle_ref.Ref(kind="glibc").scene(name, aspect=w / h).render(w, h, spp, seed=0, threads=0, want_ids=False)
+    differ = (a["linear"].view(np.uint32) != b["linear"].view(np.uint32)).any(-1)
+    print(name, "pixels changed by the libm pin: %d of %d" % (differ.sum(), differ.size))
+    assert differ.mean() <= 1e-4
+    assert a["n_random"] == b["n_random"] or differ.any()
+
+
+@pytest.mark.parametrize("name,w,h,spp", [("cornell_box", 96, 54, 2), ("random_spheres", 96, 54, 2), ("flamingo_pond", 64, 36, 1)])
+def test_counting_build_counts_the_references_calls(ref, name, w, h, spp):
+    """libref_count.so (gcc function-entry hook on Scene::computeIntersection / computeShadow) renders the bits of the
+    deterministic build, and its counts obey the structure of rayTraceRecursive (Scene.h:258-342): one closest-hit ray
+    per recursion level reached, NB_ECH shadow rays per light per hit."""
+    import oracle_ref
+    if not oracle_ref.available(kind="count"):
+        pytest.skip("oracle/_ref/libref_count.so not built")
+    a = ref.scene(name, aspect=w / h).render(w, h, spp, seed=0, threads=0)
+    c = oracle_ref.Ref(kind="count").scene(name, aspect=w / h)
+    b = c.render(w, h, spp, seed=0, threads=0)
+    assert np.array_equal(a["linear"].view(np.uint32), b["linear"].view(np.uint32)) and a["n_random"] == b["n_random"]
+    samples = w * h * spp
+    assert samples <= b["n_closest_rays"] <= 6 * samples
+    one = c.render(w, h, spp, seed=0, threads=1)
+    assert (one["n_closest_rays"], one["n_shadow_rays"]) == (b["n_closest_rays"], b["n_shadow_rays"])     # thread-count invariant
+    hits_upper = b["n_closest_rays"] - 0                      # every hit was a closest-hit ray that hit
+    n_lights = {"cornell_box": 0, "random_spheres": 1, "flamingo_pond": 1}[name]
+    assert b["n_shadow_rays"] % (10 * max(1, n_lights)) == 0
+    assert b["n_shadow_rays"] <= 10 * n_lights * hits_upper
+    c.close()
+
+
+def test_thread_per_row_mode_renders_a_plausible_image(ref):
+    """ref_render_rows = the reference's own threading (one std::thread per scanline, main.cpp:229-238) with per-thread
+    mt19937 jitter: stochastic, so only the statistics are compared with the deterministic render."""
+    import oracle_ref
+    if not oracle_ref.available(stock=True):
+        pytest.skip("oracle/_ref/libref_stock.so not built")
+    w, h, spp = 96, 54, 64
+    s = oracle_ref.Ref(stock=True).scene("cornell_box", aspect=w / h)
+    r = s.render_rows(w, h, spp, want_image=True)
+    s.close()
+    want = ref.scene("cornell_box", aspect=w / h).render(w, h, spp, seed=0, threads=0, want_ids=False)["gamma"]
+    assert r["seconds"] > 0 and r["gamma"].shape == (h, w, 3)
+    assert abs(r["gamma"].mean() - want.mean()) < 0.05 * want.mean() + 1e-3     # two independent 64-spp estimates: ~1 % apart

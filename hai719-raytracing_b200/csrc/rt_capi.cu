@@ -134,8 +134,12 @@ __device__ __forceinline__ void flush_counters(const Counters &c, unsigned long 
 
 // One path per lane; warps pull batches of 32 consecutive paths (same pixel for spp >= 32, so a
 // warp's primary rays are coherent) from a global counter until the chunk is exhausted.
+#ifndef RT_PATHS_MINB
+#define RT_PATHS_MINB 4
+#endif
 template <bool STATS>
-__global__ void __launch_bounds__(128, 4) k_render_paths(const DScene scene, const DCamera cam, const RenderArgs a) {
+__global__ void __launch_bounds__(128, RT_PATHS_MINB) k_render_paths(const DScene scene_, const DCamera cam, const RenderArgs a) {
+    const DScene &scene = RT_S(scene_);
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
@@ -207,11 +211,15 @@ __global__ void __launch_bounds__(256) k_camera_rays(const DCamera cam, const Re
 #define RT_PARAM
 #endif
 template <bool STATS, int ACCEL, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScene scene, const RT_PARAM DCamera cam, const RenderArgs a) {
+__global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScene scene_, const RT_PARAM DCamera cam, const RenderArgs a) {
+    const DScene &scene = RT_S(scene_);
+    stage_abvh(scene);
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
     PathState st;
+    PathRecs recs;
+    st.recs = &recs; st.wf_rec = nullptr; st.wf_stride = 0;
     st.mode = 2;
     st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f; st.t_light = 0.f;
     st.rng.key = 0; st.rng.ctr = 0;
@@ -345,6 +353,14 @@ struct WfArgs {
                                        //                             [4] parked head, [5] parked count, [6] overflow head, [7] overflow count
     float *samples;
     unsigned long long *stats;
+    // speculative shadow samples (k_wf_shadow / k_wf_validate below)
+    unsigned int *sp_hdr;              // per path slot: samples validated so far | blocked so far << 8 | guessed draws per sample << 16
+    unsigned short *sp_res;            // per path slot and sample: draws the sample consumed | blocked << 15
+    const unsigned int *sp_q_in;       // this round's parked hits ...
+    const unsigned int *sp_cnt_in;     // ... and how many
+    unsigned int *sp_head, *sp_vhead;  // work-fetch heads of the round's shadow and validate kernels
+    unsigned int *sp_q_out, *sp_cnt_out;   // hits with samples left after this round
+    int sp_enabled;                    // the sample kernel resumes from sp_hdr instead of sample 0
 };
 
 // Queue traffic. Every batch of 32 entries used to cost two atomicAdds on two counters of one 32-byte sector (work
@@ -444,7 +460,9 @@ __device__ __forceinline__ void wf_stage_flush(unsigned int *queue, unsigned int
 // its light needs samples, and each bounce level is two kernels instead of three. It measured 30-40 % slower than the
 // three-kernel split (rt_render_device, profiles/r01_notes.md).
 template <bool STATS, bool LC, bool FUSE>
-__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM DScene scene, const DCamera cam, const WfArgs w) {
+__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM DScene scene_, const DCamera cam, const WfArgs w) {
+    const DScene &scene = RT_S(scene_);
+    stage_abvh(scene);
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
@@ -469,7 +487,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
         st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
         st.rng.key = 0; st.rng.ctr = 0;
         st.cm0 = st.cm1 = st.cm2 = st.cm3 = 0u; st.cl_n = 0;
-        st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
+        st.recs = nullptr; st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
         unsigned int slot = 0;
         if (valid) {
             if (w.level == 0) {
@@ -586,7 +604,9 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
 // Split because a warp is as slow as its slowest lane: with both phases in one loop, one lane that has to sample keeps
 // 31 finished lanes waiting for ten rounds.
 template <bool STATS, bool LC, int PHASE>
-__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM DScene scene, const WfArgs w) {
+__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM DScene scene_, const WfArgs w) {
+    const DScene &scene = RT_S(scene_);
+    stage_abvh(scene);
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
@@ -617,7 +637,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
         st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
         st.rng.key = 0; st.rng.ctr = 0;
         st.cm0 = st.cm1 = st.cm2 = st.cm3 = 0u; st.cl_n = 0;
-        st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
+        st.recs = nullptr; st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
         unsigned int slot = 0;
         bool fin = true, parked = false;
         V3 c = v3(0.f);
@@ -647,8 +667,16 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
                 }
                 st.cm0 = f2u(p1.x); st.cm1 = f2u(p1.y); st.cm2 = f2u(p1.z); st.cm3 = f2u(p1.w);
                 st.j = 0; st.blocked = 0; st.mode = 3;
-                Hit h; h.type = 0; h.obj = -1; h.t = 0.f; h.ref = 0;
-                fin = path_advance<STATS, LC, true>(scene, st, h, 0.f, 0.f, false, w.nb_ech, c, &cnt);   // candidates known: first sample
+                if (w.sp_enabled) {   // samples 0 .. j-1 of the parked light were traced speculatively and validated (k_wf_validate)
+                    const unsigned int hdr = w.sp_hdr[slot];
+                    st.j = (int)(hdr & 0xFFu); st.blocked = (int)((hdr >> 8) & 0xFFu);
+                }
+                if (st.j >= w.nb_ech) {
+                    fin = path_finish_light<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
+                } else {
+                    path_shadow_sample<STATS>(scene, st, &cnt);   // candidates known: the next sample
+                    fin = false;
+                }
             } else {
                 st.color = v3(0.f); st.light = 0; st.mode = 0;
                 fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
@@ -678,6 +706,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
                     WF_ST(w.park2 + (size_t)q4 * w.rec_stride + slot, make_float4(u2f(st.cl[4 * q4]), u2f(st.cl[4 * q4 + 1]), u2f(st.cl[4 * q4 + 2]), u2f(st.cl[4 * q4 + 3])));
                 WF_ST(w.park1 + slot, make_float4(u2f(st.cm0), u2f(st.cm1), u2f(st.cm2), u2f(st.cm3)));
                 WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
+                if (w.sp_enabled) w.sp_hdr[slot] = 3u << 16;   // no sample validated yet; guess: unoccluded samples, 3 draws each
             } else if (fin) {
                 float *o = w.samples + 3ull * slot;
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
@@ -700,6 +729,139 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
         wf_stage_flush(w.q_over, w.ctr + WF_NCTR * w.level + 7, stage_over, fill_over);
     }
     if (STATS) flush_counters(cnt, w.stats);
+}
+
+// ---- speculative shadow samples ---------------------------------------------------------------------------------------
+// The NB_ECH soft-shadow samples of one (hit, light) are SEQUENTIAL in the reference: sample j+1 draws its direction
+// from the stream position sample j left behind, and a sample consumes 3 draws plus one per candidate occluder it hits
+// until one blocks (Scene.h:325-330, 235-255). One lane per hit therefore walks the mesh hierarchies ten times in a row
+// next to 31 lanes doing the same for unrelated hits: the pond scene's walks ran at 9 of 32 lanes. But a sample is a
+// pure function of (hit, light, stream position), and the position is predictable: an unoccluded sample consumes exactly
+// 3 draws, a sample blocked by the first opaque thing it meets exactly 4. So the samples are traced IN PARALLEL, one
+// lane per (hit, sample j), from the GUESSED position base + (j - j0) * guess (guess = 3 at first), adjacent lanes
+// holding the samples of one hit — ten nearly identical rays from one point, which walk the hierarchy in lockstep —
+// and k_wf_validate then checks the guesses in order: sample j is valid iff the draws consumed by the validated samples
+// before it add up to its guessed offset. The validated prefix advances the stream, the blocked count and the guess
+// (the draws the last valid sample consumed); hits with samples left go round again. Every round validates at least one
+// sample per hit, so the fixed number of rounds the host launches never loses anything: whatever is left is finished by
+// the sequential sample kernel (k_wf_light<.., 2>), which resumes at sample j0. Results are bit-identical by
+// construction — only samples traced from the reference's own stream position are ever used.
+template <bool STATS>
+__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_shadow(const RT_WF_PARAM DScene scene_, const WfArgs w) {
+    const DScene &scene = RT_S(scene_);
+    stage_abvh(scene);
+    Counters cnt;
+    if (STATS) memset(&cnt, 0, sizeof cnt);
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int n_hits = *w.sp_cnt_in;
+    const unsigned int nb = (unsigned int)w.nb_ech;
+    const unsigned long long total = (unsigned long long)n_hits * nb;
+    const unsigned int count = total > 0xFFFFFFE0ull ? 0xFFFFFFE0u : (unsigned int)total;   // 32 Mi paths x 10 samples fit; beyond: the rest stays sequential
+    WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
+    for (;;) {
+        unsigned int base;
+        if (!wf_next_batch(w.sp_head, count, w.max_grab > 1u ? 8u : 4u, fetch, base)) break;   // samples are small, even work items: fewer fetch atomics
+        const unsigned int i = base + lane;
+        PathState st;
+        st.recs = nullptr; st.wf_rec = nullptr; st.wf_stride = 0; st.max_bounces = w.max_bounces;
+        st.mode = 2; st.t_light = 0.f; st.light = 0;
+        st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
+        st.rng.key = 0; st.rng.ctr = 0;
+        st.cm0 = st.cm1 = st.cm2 = st.cm3 = 0u; st.cl_n = 0;
+        bool active = i < count;
+        unsigned int slot = 0, j = 0, start = 0;
+        if (active) {
+            const unsigned int e = i / nb;
+            j = i - e * nb;
+            slot = WF_LD(w.sp_q_in + e);
+            const unsigned int hdr = w.sp_hdr[slot];
+            const unsigned int j0 = hdr & 0xFFu, guess = hdr >> 16;
+            active = j >= j0;   // earlier samples are validated already
+            if (active) {
+                const float4 h0 = __ldg(w.hit0 + slot);
+                const uint2 g = __ldg(w.rng + slot);
+                const float4 p0 = __ldg(w.park0 + slot), p1 = __ldg(w.park1 + slot);
+                st.P = v3(h0.x, h0.y, h0.z); st.ray.time = h0.w;
+                st.light = (int)(f2u(p0.w) & 0xFFu); st.cl_n = (int)((f2u(p0.w) >> 8) & 0xFFu) - 1;
+                for (int q4 = 0; q4 * 4 < st.cl_n; ++q4) {
+                    const float4 v = __ldg(w.park2 + (size_t)q4 * w.rec_stride + slot);
+                    st.cl[4 * q4] = f2u(v.x); st.cl[4 * q4 + 1] = f2u(v.y); st.cl[4 * q4 + 2] = f2u(v.z); st.cl[4 * q4 + 3] = f2u(v.w);
+                }
+                st.cm0 = f2u(p1.x); st.cm1 = f2u(p1.y); st.cm2 = f2u(p1.z); st.cm3 = f2u(p1.w);
+                start = g.y + (j - j0) * guess;
+                st.rng.key = g.x; st.rng.ctr = start;
+                st.path = slot; st.N = 0; st.depth = 0; st.j = (int)j; st.blocked = 0;
+                path_shadow_sample<STATS>(scene, st, &cnt);
+            }
+        }
+        Hit h;
+        float hu = 0.f, hv = 0.f;
+        bool blocked;
+        intersect_lc<STATS>(scene, st, false, active, h, hu, hv, blocked, &cnt);
+        if (active) {
+            const unsigned int consumed = st.rng.ctr - start;
+            w.sp_res[(size_t)slot * nb + j] = (unsigned short)((consumed > 0x7FFFu ? 0x7FFFu : consumed) | (blocked ? 0x8000u : 0u));
+        }
+    }
+    if (STATS) {   // tests really performed (speculation included); rays and draws are counted once, by k_wf_validate
+        cnt.shadow = 0; cnt.rnd = 0;
+        flush_counters(cnt, w.stats);
+    }
+}
+
+// One lane per parked hit: validate the guesses of the last k_wf_shadow round in sample order (see above), advance the
+// hit's stream position / blocked count / guess, and queue it for another round if samples are left.
+template <bool STATS>
+__global__ void __launch_bounds__(128) k_wf_validate(const WfArgs w) {
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int count = *w.sp_cnt_in;
+    const unsigned int nb = (unsigned int)w.nb_ech;
+    const bool traced_all = (unsigned long long)count * nb <= 0xFFFFFFE0ull;
+    __shared__ unsigned int stage_all[4][WF_STAGE_CAP];
+    unsigned int *stage = stage_all[threadIdx.x >> 5];
+    unsigned int fill = 0u;
+    unsigned long long n_shadow = 0, n_rnd = 0, n_val = 0, n_pend = 0;
+    WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
+    for (;;) {
+        unsigned int base;
+        if (!wf_next_batch(w.sp_vhead, count, 8u, fetch, base)) break;
+        const unsigned int i = base + lane;
+        bool again = false;
+        unsigned int slot = 0;
+        if (i < count) {
+            slot = WF_LD(w.sp_q_in + i);
+            const unsigned int hdr = w.sp_hdr[slot];
+            const unsigned int j0 = hdr & 0xFFu, guess = hdr >> 16;
+            unsigned int blocked = (hdr >> 8) & 0xFFu, last = guess, off = 0, j = j0;
+            if (traced_all || (unsigned long long)(i + 1) * nb <= 0xFFFFFFE0ull) {
+                for (; j < nb; ++j) {
+                    if ((j - j0) * guess != off) break;
+                    const unsigned int r = w.sp_res[(size_t)slot * nb + j];
+                    const unsigned int consumed = r & 0x7FFFu;
+                    if (consumed == 0x7FFFu) break;   // more draws than the record holds: leave the sample to the sequential kernel
+                    blocked += r >> 15; off += consumed; last = consumed;
+                }
+            }
+            if (j > j0) {
+                uint2 g = w.rng[slot];
+                g.y += off;
+                w.rng[slot] = g;
+                if (STATS) { n_shadow += j - j0; n_rnd += off; }
+            }
+            if (STATS) { n_val += j - j0; n_pend += nb - j0; }
+            w.sp_hdr[slot] = j | (blocked << 8) | ((last > 0xFFFFu ? 3u : last) << 16);
+            again = j < nb && j > j0;   // nothing validated = nothing to gain from another round
+        }
+        wf_stage_push(w.sp_q_out, w.sp_cnt_out, stage, fill, again, slot);
+    }
+    wf_stage_flush(w.sp_q_out, w.sp_cnt_out, stage, fill);
+    if (STATS) {
+        for (int o = 16; o > 0; o >>= 1) { n_shadow += __shfl_down_sync(0xFFFFFFFFu, n_shadow, o); n_rnd += __shfl_down_sync(0xFFFFFFFFu, n_rnd, o); }
+        if (lane == 0) { if (n_shadow) atomicAdd(w.stats + 1, n_shadow); if (n_rnd) atomicAdd(w.stats + 9, n_rnd); }
+        // tuning aid (rt_debug_counters): samples validated / samples that were pending, over all rounds
+        for (int o = 16; o > 0; o >>= 1) { n_val += __shfl_down_sync(0xFFFFFFFFu, n_val, o); n_pend += __shfl_down_sync(0xFFFFFFFFu, n_pend, o); }
+        if (lane == 0) { if (n_val) atomicAdd(w.stats + 12, n_val); if (n_pend) atomicAdd(w.stats + 13, n_pend); }
+    }
 }
 
 // image[pixel] = (sum of its samples, in sample order) / nsamples ; then gamma
@@ -774,8 +936,9 @@ __global__ void k_untile(const TileRec *tiles, const unsigned int *tile_off, int
     image[o] = packed[3ull * lp]; image[o + 1] = packed[3ull * lp + 1]; image[o + 2] = packed[3ull * lp + 2];
 }
 
-__global__ void k_primary_ids(const DScene scene, const DCamera cam, int width, int height, unsigned int seed, int x0,
+__global__ void k_primary_ids(const DScene scene_, const DCamera cam, int width, int height, unsigned int seed, int x0,
                               int y0, int rw, int rh, uint32_t *ids) {
+    const DScene &scene = RT_S(scene_);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rw * rh) return;
     const int x = x0 + i % rw, y = y0 + i / rw;
@@ -791,8 +954,9 @@ __global__ void k_primary_ids(const DScene scene, const DCamera cam, int width, 
     o[3] = f2u(h.t);
 }
 
-__global__ void k_trace_rays(const DScene scene, size_t n, const float *org, const float *dir, const float *time,
+__global__ void k_trace_rays(const DScene scene_, size_t n, const float *org, const float *dir, const float *time,
                              uint32_t *ids, float *aux) {
+    const DScene &scene = RT_S(scene_);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Ray ray = make_ray(ld3(org + 3 * i), ld3(dir + 3 * i), time ? time[i] : 0.f);
@@ -825,8 +989,9 @@ __global__ void k_trace_rays(const DScene scene, size_t n, const float *org, con
     }
 }
 
-__global__ void k_shade_rays(const DScene scene, size_t n, const float *org, const float *dir, const float *time,
+__global__ void k_shade_rays(const DScene scene_, size_t n, const float *org, const float *dir, const float *time,
                              unsigned int seed, int max_bounces, int nb_ech, float *rgb) {
+    const DScene &scene = RT_S(scene_);
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Ray ray = make_ray(ld3(org + 3 * i), ld3(dir + 3 * i), time ? time[i] : 0.f);
@@ -866,12 +1031,19 @@ struct Scratch {
     // wavefront state (variant 6), per path of a chunk: 7 float4 fields + rng + 2 queues, and 3 float4 per bounce
     float4 *wf_f4 = nullptr; uint2 *wf_rng = nullptr; unsigned int *wf_q = nullptr; float4 *wf_rec = nullptr; unsigned int *wf_ctr = nullptr;
     size_t wf_cap = 0; int wf_bounces = 0;
+    // speculative shadow samples: header per path, result per (path, sample), 4 retry queues, counters per (level, queue, round)
+    unsigned int *sp_hdr = nullptr; unsigned short *sp_res = nullptr; unsigned int *sp_q = nullptr; unsigned int *sp_ctr = nullptr;
+    size_t sp_cap = 0; int sp_nb = 0;
     unsigned long long *counters = nullptr;   // [0] work counter, [1..10] stats
     TileRec *d_tiles = nullptr; unsigned int *d_tile_off = nullptr; size_t tiles_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float *out_img = nullptr; size_t out_cap = 0;       // framebuffer(s) of rt_render / rt_render_rgb8 / rt_render_multi: no cudaMalloc per frame
     uint8_t *out_bytes = nullptr; size_t out_bytes_cap = 0;
     cudaStream_t stream = nullptr;                      // rt_render_multi: this device's stream (one host thread per device)
+    // pinned staging for the scene's small arrays: rt_scene_create copies each array here and issues an ASYNCHRONOUS
+    // H2D copy on the null stream (2-3 us each) instead of a synchronous pageable cudaMemcpy (8-10 us each, ~30 per scene);
+    // one stream synchronise at the end of the upload. Arrays that do not fit (meshes, images) are copied synchronously.
+    char *stage = nullptr; size_t stage_cap = 0, stage_used = 0;
     // arena for the scene's own arrays (textures, primitives, hierarchies): bump-allocated blocks, reset when the scene
     // is destroyed and reused by the next scene on this device — a re-upload performs no cudaMalloc/cudaFree at all
     struct Block { char *base; size_t cap, used; };
@@ -903,6 +1075,10 @@ struct Scratch {
         if (wf_q) cudaFree(wf_q);
         if (wf_rec) cudaFree(wf_rec);
         if (wf_ctr) cudaFree(wf_ctr);
+        if (sp_hdr) cudaFree(sp_hdr);
+        if (sp_res) cudaFree(sp_res);
+        if (sp_q) cudaFree(sp_q);
+        if (sp_ctr) cudaFree(sp_ctr);
         if (counters) cudaFree(counters);
         if (d_tiles) cudaFree(d_tiles);
         if (d_tile_off) cudaFree(d_tile_off);
@@ -911,6 +1087,7 @@ struct Scratch {
         if (out_img) cudaFree(out_img);
         if (out_bytes) cudaFree(out_bytes);
         if (stream) cudaStreamDestroy(stream);
+        if (stage) cudaFreeHost(stage);
         *this = Scratch();
     }
 };
@@ -943,9 +1120,61 @@ struct RtScene : Scratch {
     SquareIn *d_square_in = nullptr;
     size_t abvh_node_cap = 0, abvh_prim_cap = 0;
     uint32_t n_textures = 0, n_normal_maps = 0;
+    size_t h2d_bytes = 0;                      // bytes the upload really copied (cached images are not copied again)
+    std::vector<uint64_t> cached_images;       // image-cache entries this scene holds a reference on
 };
 
 namespace {
+
+// The kernels read the scene from the constant bank (rt_core.cuh : c_scene), one copy per device. A render binds its
+// scene for the duration of its launches: the upload is ordered on the render's stream, and a render of ANOTHER scene
+// (or on another stream) on the same device first waits for the event that ends the previous binding, so kernels
+// still in flight keep the constants they were launched with. Host threads serialise per device while they ENQUEUE
+// (launches are asynchronous: a few hundred microseconds), not while the GPU works.
+struct ConstSlot {
+    std::mutex mu;
+    const void *owner = nullptr;
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool used = false;
+};
+std::mutex g_const_mu;
+std::map<int, ConstSlot *> g_const_slots;
+ConstSlot *const_slot(int device) {
+    std::lock_guard<std::mutex> lock(g_const_mu);
+    ConstSlot *&p = g_const_slots[device];
+    if (!p) p = new ConstSlot();
+    return p;
+}
+class SceneBinding {
+public:
+    SceneBinding() {}
+    ~SceneBinding() { done(); }
+    int bind(const RtScene *s, cudaStream_t st);
+    void done() {
+        if (!slot_) return;
+        if (slot_->ev && cudaEventRecord(slot_->ev, st_) == cudaSuccess) slot_->used = true;
+        slot_->mu.unlock();
+        slot_ = nullptr;
+    }
+private:
+    ConstSlot *slot_ = nullptr;
+    cudaStream_t st_ = nullptr;
+};
+int SceneBinding::bind(const RtScene *s, cudaStream_t st) {
+#if RT_SCENE_CONST
+    ConstSlot *c = const_slot(s->device);
+    c->mu.lock();
+    slot_ = c; st_ = st;
+    if (!c->ev) RT_CUDA(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+    if (c->used && (c->owner != (const void *)s || c->last_stream != st)) RT_CUDA(cudaStreamWaitEvent(st, c->ev, 0));
+    RT_CUDA(cudaMemcpyToSymbolAsync(c_scene, &s->d, sizeof(DScene), 0, cudaMemcpyHostToDevice, st));
+    c->owner = s; c->last_stream = st;
+#else
+    (void)s; (void)st;
+#endif
+    return RT_OK;
+}
 
 struct Rect { int x0, y0, x1, y1, tw, th; };
 
@@ -985,6 +1214,25 @@ void build_tiles(const RtRenderParams &p, const Rect &r, std::vector<TileRec> &t
         }
 }
 
+// host -> device for the scene's arrays: through the pinned staging buffer and asynchronous when the piece is small,
+// synchronous otherwise. Everything is ordered on the null stream; rt_scene_create synchronises it once at the end.
+#define RT_STAGE_BYTES ((size_t)1 << 20)
+#define RT_STAGE_PIECE ((size_t)128 << 10)
+cudaError_t h2d(RtScene *s, void *dst, const void *src, size_t bytes) {
+    s->h2d_bytes += bytes;
+    if (bytes <= RT_STAGE_PIECE) {
+        if (!s->stage && cudaMallocHost((void **)&s->stage, RT_STAGE_BYTES) == cudaSuccess) s->stage_cap = RT_STAGE_BYTES;
+        cudaGetLastError();
+        const size_t need = (bytes + 63) & ~(size_t)63;
+        if (s->stage && s->stage_used + need <= s->stage_cap) {
+            char *st = s->stage + s->stage_used;
+            s->stage_used += need;
+            memcpy(st, src, bytes);
+            return cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, 0);
+        }
+    }
+    return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+}
 template <class T> int dev_upload(RtScene *s, const T *host, size_t n, const T **out) {
     *out = nullptr;
     if (n == 0) return RT_OK;
@@ -992,7 +1240,7 @@ template <class T> int dev_upload(RtScene *s, const T *host, size_t n, const T *
     void *p = s->arena_alloc(n * sizeof(T), &e);
     RT_CUDA(e);
     s->bytes += n * sizeof(T);
-    RT_CUDA(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    RT_CUDA(h2d(s, p, host, n * sizeof(T)));
     *out = (const T *)p;
     return RT_OK;
 }
@@ -1015,7 +1263,7 @@ struct DevTmp {   // staging buffer for the precompute kernels: lives in the sce
 cudaError_t DevTmp::put(RtScene *s, const void *h, size_t bytes) {
     cudaError_t e;
     p = s->arena_alloc(bytes ? bytes : 1, &e);
-    if (e == cudaSuccess && h && bytes) e = cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && h && bytes) e = h2d(s, p, h, bytes);
     return e;
 }
 
@@ -1030,9 +1278,65 @@ DMaterial to_dmat(const RtMaterial &m) {
     return d;
 }
 
+// Device-side image cache (RtImage::content_id != 0): textures, normal maps and the sky image stay resident across scene
+// re-uploads. Entries are reference counted by the scenes that use them; unreferenced entries are kept (that is the
+// point) until the cache exceeds its budget, least recently used first, or rt_release_cached_memory is called.
+struct ImgEntry { unsigned char *d = nullptr; size_t bytes = 0; int w = 0, h = 0, refs = 0; unsigned long long stamp = 0; };
+struct ImgCache { std::map<uint64_t, ImgEntry> map; size_t total = 0; unsigned long long clock = 0; };
+std::mutex g_img_mu;
+std::map<int, ImgCache> g_img_cache;
+const size_t RT_IMG_CACHE_BUDGET = (size_t)2 << 30;
+void img_cache_trim(ImgCache &c, size_t budget) {
+    while (c.total > budget) {
+        auto victim = c.map.end();
+        for (auto it = c.map.begin(); it != c.map.end(); ++it)
+            if (it->second.refs == 0 && (victim == c.map.end() || it->second.stamp < victim->second.stamp)) victim = it;
+        if (victim == c.map.end()) break;
+        cudaFree(victim->second.d);
+        c.total -= victim->second.bytes;
+        c.map.erase(victim);
+    }
+}
+void img_cache_release(RtScene *s) {
+    if (s->cached_images.empty()) return;
+    std::lock_guard<std::mutex> lock(g_img_mu);
+    ImgCache &c = g_img_cache[s->device];
+    for (uint64_t id : s->cached_images) {
+        auto it = c.map.find(id);
+        if (it != c.map.end() && it->second.refs > 0) --it->second.refs;
+    }
+    s->cached_images.clear();
+    img_cache_trim(c, RT_IMG_CACHE_BUDGET);
+}
 int upload_image(RtScene *s, const RtImage &im, DImage &out) {
     out.w = 0; out.h = 0; out.rgb = nullptr;
     if (im.w < 1 || im.h < 1 || !im.rgb) return RT_OK;
+    if (im.content_id != 0) {
+        const size_t bytes = (size_t)im.w * im.h * 3;
+        std::lock_guard<std::mutex> lock(g_img_mu);
+        ImgCache &c = g_img_cache[s->device];
+        auto it = c.map.find(im.content_id);
+        if (it != c.map.end() && (it->second.w != im.w || it->second.h != im.h)) {   // an id reused for other pixels: not cacheable
+            it = c.map.end();
+        } else if (it == c.map.end()) {
+            ImgEntry e;
+            e.bytes = bytes; e.w = im.w; e.h = im.h;
+            RT_CUDA(cudaMalloc((void **)&e.d, bytes));
+            const cudaError_t ce = cudaMemcpy(e.d, im.rgb, bytes, cudaMemcpyHostToDevice);
+            if (ce != cudaSuccess) { cudaFree(e.d); RT_CUDA(ce); }
+            s->h2d_bytes += bytes;
+            c.total += bytes;
+            it = c.map.emplace(im.content_id, e).first;
+        }
+        if (it != c.map.end()) {
+            ++it->second.refs;
+            it->second.stamp = ++c.clock;
+            s->cached_images.push_back(im.content_id);
+            s->bytes += bytes;
+            out.w = im.w; out.h = im.h; out.rgb = it->second.d;
+            return RT_OK;
+        }
+    }
     const unsigned char *d = nullptr;
     int rc = dev_upload<unsigned char>(s, im.rgb, (size_t)im.w * im.h * 3, &d);
     if (rc) return rc;
@@ -1100,6 +1404,23 @@ int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
     return RT_OK;
 }
 
+#define SP_MAX_ROUNDS 14
+#define SP_NCTR 4   /* per (level, queue, round): [0] shadow head, [1] validate head, [2] hits in this round's queue, [3] - */
+int ensure_spec(RtScene *s, size_t paths, int nb_ech) {
+    if (paths <= s->sp_cap && nb_ech <= s->sp_nb) return RT_OK;
+    paths = std::max(paths, s->sp_cap); nb_ech = std::max(nb_ech, s->sp_nb);
+    if (s->sp_hdr) cudaFree(s->sp_hdr);
+    if (s->sp_res) cudaFree(s->sp_res);
+    if (s->sp_q) cudaFree(s->sp_q);
+    s->sp_hdr = nullptr; s->sp_res = nullptr; s->sp_q = nullptr; s->sp_cap = 0; s->sp_nb = 0;
+    RT_CUDA(cudaMalloc((void **)&s->sp_hdr, paths * sizeof(unsigned int)));
+    RT_CUDA(cudaMalloc((void **)&s->sp_res, paths * (size_t)nb_ech * sizeof(unsigned short)));
+    RT_CUDA(cudaMalloc((void **)&s->sp_q, 4 * paths * sizeof(unsigned int)));
+    if (!s->sp_ctr) RT_CUDA(cudaMalloc((void **)&s->sp_ctr, (size_t)SP_NCTR * (SP_MAX_ROUNDS + 2) * 2 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int)));
+    s->sp_cap = paths; s->sp_nb = nb_ech;
+    return RT_OK;
+}
+
 int ensure_scratch(RtScene *s, size_t sample_floats, size_t n_tiles, size_t cam_paths) {
     if (cam_paths > s->cam_cap) {
         if (s->cam_rays) cudaFree(s->cam_rays);
@@ -1148,7 +1469,7 @@ int ensure_out(RtScene *s, size_t floats, size_t bytes) {
 // (arrays come from the scene's arena); update == true: the same arrays are rewritten in place.
 template <class T> int dev_put(RtScene *s, bool update, const T *host, size_t n, const T **field) {
     if (!update) return dev_upload(s, host, n, field);
-    if (n) RT_CUDA(cudaMemcpy(const_cast<T *>(*field), host, n * sizeof(T), cudaMemcpyHostToDevice));
+    if (n) RT_CUDA(h2d(s, const_cast<T *>(*field), host, n * sizeof(T)));
     return RT_OK;
 }
 int upload_analytic(RtScene *s, const RtSceneDesc *desc, bool update) {
@@ -1206,7 +1527,9 @@ int upload_analytic(RtScene *s, const RtSceneDesc *desc, bool update) {
     {
         AnalyticAccel aa;
         build_analytic_accel(*desc, aa);
+        if (aa.nodes.size() / 4 > RT_ABVH_MAX_NODES) aa.root = -1;   // cannot happen for <= 128 primitives (n - 1 inner nodes); the staged copy relies on it
         d.abvh_root = aa.root;
+        d.abvh_n_nodes = (int)(aa.nodes.size() / 4);
         for (int k = 0; k < 3; ++k) d.abvh_c[k] = aa.center[k];
         d.abvh_r = aa.radius;
         if (aa.root >= 0) {
@@ -1221,8 +1544,8 @@ int upload_analytic(RtScene *s, const RtSceneDesc *desc, bool update) {
                 d.abvh_nodes = nodes; d.abvh_prims = prims;
             }
             if (aa.nodes.size() > s->abvh_node_cap || aa.tris.size() > s->abvh_prim_cap) return fail(RT_ERR_INVALID, "analytic hierarchy outgrew its arrays");
-            RT_CUDA(cudaMemcpy(const_cast<float4 *>(d.abvh_nodes), aa.nodes.data(), aa.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice));
-            RT_CUDA(cudaMemcpy(const_cast<uint32_t *>(d.abvh_prims), aa.tris.data(), aa.tris.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            RT_CUDA(h2d(s, const_cast<float4 *>(d.abvh_nodes), aa.nodes.data(), aa.nodes.size() * sizeof(float4)));
+            RT_CUDA(h2d(s, const_cast<uint32_t *>(d.abvh_prims), aa.tris.data(), aa.tris.size() * sizeof(uint32_t)));
         }
     }
 
@@ -1255,6 +1578,7 @@ void rt_scene_destroy(RtScene *s) {
     if (s->refs.fetch_sub(1) > 1) return;   // an accumulator or a retained handle still renders from these arrays
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();   // nothing of this scene may still be in flight when its arrays go
+    img_cache_release(s);
     s->arena_reset();
     {
         std::lock_guard<std::mutex> lock(g_scratch_mu);
@@ -1268,11 +1592,15 @@ int rt_release_cached_memory(int device) {
     {
         std::lock_guard<std::mutex> lock(g_scratch_mu);
         auto it = g_scratch_pool.find(device);
-        if (it == g_scratch_pool.end()) return RT_OK;
-        idle.swap(it->second);
+        if (it != g_scratch_pool.end()) idle.swap(it->second);
     }
     RT_CUDA(cudaSetDevice(device));
     for (Scratch &sc : idle) sc.release();
+    {   // images no scene references any more
+        std::lock_guard<std::mutex> lock(g_img_mu);
+        auto it = g_img_cache.find(device);
+        if (it != g_img_cache.end()) img_cache_trim(it->second, 0);
+    }
     {   // the tile tables rt_untile_device keeps per geometry on this device
         std::lock_guard<std::mutex> lock(g_untile_mu);
         for (auto it = g_untile.begin(); it != g_untile.end();) {
@@ -1286,6 +1614,7 @@ int rt_release_cached_memory(int device) {
 }
 
 size_t rt_scene_device_bytes(const RtScene *s) { return s ? s->bytes : 0; }
+size_t rt_scene_h2d_bytes(const RtScene *s) { return s ? s->h2d_bytes : 0; }
 
 int rt_scene_update_analytic(RtScene *s, const RtSceneDesc *desc) {
     if (!s || !desc) return fail(RT_ERR_INVALID, "null argument");
@@ -1297,6 +1626,7 @@ int rt_scene_update_analytic(RtScene *s, const RtSceneDesc *desc) {
         return fail(RT_ERR_INVALID, "count > 0 with a null array");
     RT_CUDA(cudaSetDevice(s->device));
     RT_CUDA(cudaDeviceSynchronize());   // no render of the old primitives may still be in flight
+    s->stage_used = 0;
     const bool had_accel = s->d.abvh_root >= 0;
     int rc = upload_analytic(s, desc, true);
     if (rc) return rc;
@@ -1344,6 +1674,7 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
         if (!pool.empty()) { static_cast<Scratch &>(*s) = pool.back(); pool.pop_back(); }
     }
     struct Guard { RtScene *s; bool keep = false; ~Guard() { if (!keep) rt_scene_destroy(s); } } guard{s};
+    s->stage_used = 0;   // the copies of the scene that used this staging buffer before completed when its upload returned
     DScene &d = s->d;
     d.n_spheres = (int)desc->n_spheres; d.n_squares = (int)desc->n_squares; d.n_meshes = (int)desc->n_meshes; d.n_lights = (int)desc->n_lights;
     d.dark_sky = desc->dark_sky;
@@ -1399,8 +1730,7 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
                 const uint32_t rb = pk.ref_begin[i];
                 k_precompute_tris<<<(src.n_leaf_refs + 127) / 128, 128>>>((const float *)d_pos.p, (const RtTriRef *)d_refs.p, src.n_leaf_refs,
                                                                          pl + rb, ed + 3 * (size_t)rb, dn + rb);
-                RT_CUDA(cudaGetLastError());
-                RT_CUDA(cudaDeviceSynchronize());
+                RT_CUDA(cudaGetLastError());   // the staging arrays live in the scene's arena: no need to wait for the kernel here
             }
             m[i] = to_dmat(src.material);
             tr[i] = src.material.transparency;
@@ -1518,10 +1848,29 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     LightKernel wf_light = want_stats ? (wf_lc ? k_wf_light<true, true, 1> : k_wf_light<true, false, 0>) : (wf_lc ? k_wf_light<false, true, 1> : k_wf_light<false, false, 0>);
     LightKernel wf_light_b = want_stats ? k_wf_light<true, true, 2> : k_wf_light<false, true, 2>;
     int wf_grid_t = 0, wf_grid_l = 0;
+    // Speculative shadow samples (k_wf_shadow / k_wf_validate): rounds of parallel sample tracing in front of the sequential
+    // sample kernel. Exact, tested, and measured SLOWER on every config (profiles/r02_notes.md, r02d/r02e: config 5 67 -> 87 ms,
+    // config 3 74 -> 90-94, config 2 11.4 -> 15.3): 85 % of config 5's parked samples validate in the first round, but a sample
+    // costs what it costs in either kernel (three IEEE normalisations and the candidate tests, not the walk), every round
+    // re-traces what it could not validate, and the sequential kernel stays as slow as its slowest lane. So: off unless asked
+    // for. Wavefront variant bits 20..23: 0 or 15 = off, 1..14 = that many rounds.
+    int sp_rounds = 0;
+    if (wavefront && wf_lc && !wf_fuse && s->d.n_lights > 0 && p->nb_ech <= 255) {
+        const int req = (p->variant >> 20) & 0xF;
+        sp_rounds = (req == 0 || req == 15) ? 0 : std::min(req, SP_MAX_ROUNDS);
+        if (const char *e = getenv("HAI719_SPEC_ROUNDS")) { const int v = atoi(e); if (v >= 0 && v <= SP_MAX_ROUNDS) sp_rounds = v; }   // tuning experiments
+    }
+    typedef void (*ShadowKernel)(const DScene, const WfArgs);
+    typedef void (*ValidateKernel)(const WfArgs);
+    ShadowKernel wf_shadow = want_stats ? k_wf_shadow<true> : k_wf_shadow<false>;
+    ValidateKernel wf_validate = want_stats ? k_wf_validate<true> : k_wf_validate<false>;
+    int wf_grid_s = 0;
     if (wavefront) {
         if ((rc = ensure_wavefront(s, (size_t)(chunk_pixels * p->spp), p->max_bounces))) return rc;
+        if (sp_rounds > 0 && (rc = ensure_spec(s, s->wf_cap, p->nb_ech))) return rc;
         wf_grid_t = persistent_grid(s, (const void *)wf_trace, 128);
         wf_grid_l = persistent_grid(s, (const void *)wf_light, 128);
+        if (sp_rounds > 0) wf_grid_s = persistent_grid(s, (const void *)wf_shadow, 128);
     }
 
     RenderArgs a{};
@@ -1534,6 +1883,8 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     a.seed = p->seed; a.samples = s->samples; a.work_counter = s->counters; a.stats = want_stats ? s->counters + 1 : nullptr;
     a.sample_base = sample_base;
     uint32_t launches = 0;
+    SceneBinding binding;
+    if ((rc = binding.bind(s, st))) return rc;
     RT_CUDA(cudaMemsetAsync(s->counters, 0, 16 * sizeof(unsigned long long), st));
     if (stats) RT_CUDA(cudaEventRecord(s->ev0, st));
     for (unsigned long long pb = 0; pb < n_pixels; pb += chunk_pixels) {
@@ -1572,6 +1923,11 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
             w.rng = s->wf_rng; w.rec = s->wf_rec; w.rec_stride = cap;
             w.ctr = s->wf_ctr; w.samples = s->samples; w.stats = a.stats;
             RT_CUDA(cudaMemsetAsync(s->wf_ctr, 0, WF_NCTR * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
+            w.sp_enabled = sp_rounds > 0 ? 1 : 0;
+            if (sp_rounds > 0) {
+                w.sp_hdr = s->sp_hdr; w.sp_res = s->sp_res;
+                RT_CUDA(cudaMemsetAsync(s->sp_ctr, 0, (size_t)SP_NCTR * (SP_MAX_ROUNDS + 2) * 2 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
+            }
             unsigned int *q_live = s->wf_q, *q_hit = s->wf_q + cap;
             for (int level = 0; level < p->max_bounces; ++level) {
                 w.level = level;
@@ -1596,6 +1952,26 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
                 wf_light<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
                 RT_CUDA(cudaGetLastError());
                 launches += 2;
+                if (sp_rounds > 0) {
+                    // rounds of speculative samples for both parked queues: round r reads the hits the validation of round r - 1
+                    // left unfinished (round 0: everything the classify kernel parked) and writes the ones it leaves unfinished
+                    const size_t scap = s->sp_cap;
+                    for (int q = 0; q < (s->d.n_meshes > 0 ? 2 : 1); ++q) {
+                        unsigned int *cbase = s->sp_ctr + (size_t)SP_NCTR * (SP_MAX_ROUNDS + 2) * (2 * level + q);
+                        for (int r = 0; r < sp_rounds; ++r) {
+                            w.sp_q_in = r == 0 ? (q ? w.q_over : w.q_park) : s->sp_q + (size_t)(2 * q + ((r - 1) & 1)) * scap;
+                            w.sp_cnt_in = r == 0 ? s->wf_ctr + WF_NCTR * level + (q ? 7 : 5) : cbase + SP_NCTR * r + 2;
+                            w.sp_head = cbase + SP_NCTR * r; w.sp_vhead = cbase + SP_NCTR * r + 1;
+                            w.sp_q_out = s->sp_q + (size_t)(2 * q + (r & 1)) * scap;
+                            w.sp_cnt_out = cbase + SP_NCTR * (r + 1) + 2;
+                            wf_shadow<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_s, (batches * (unsigned long long)p->nb_ech + 3) / 4), 128, 0, st>>>(s->d, w);
+                            RT_CUDA(cudaGetLastError());
+                            wf_validate<<<(int)std::min<unsigned long long>((unsigned long long)(2 * s->sm_count), (batches + 3) / 4), 128, 0, st>>>(w);
+                            RT_CUDA(cudaGetLastError());
+                            launches += 2;
+                        }
+                    }
+                }
                 if (wf_lc && s->d.n_lights > 0) {
                     w.which_park = 0;
                     wf_light_b<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
@@ -1621,6 +1997,7 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
         RT_CUDA(cudaGetLastError());
         ++launches;
     }
+    binding.done();
     if (stats) {
         RT_CUDA(cudaEventRecord(s->ev1, st));
         RT_CUDA(cudaEventSynchronize(s->ev1));
@@ -1643,6 +2020,15 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
             stats->n_tex_fetches = c[9]; stats->n_random = c[10];
         }
     }
+    return RT_OK;
+}
+
+// tuning aid, not part of the reference-facing interface: the 16 raw device counters of the last render with collect_stats
+// ([13] / [14]: speculative shadow samples validated / pending, summed over the rounds)
+int rt_debug_counters(RtScene *s, unsigned long long *out16) {
+    if (!s || !out16 || !s->counters) return fail(RT_ERR_INVALID, "no counters");
+    RT_CUDA(cudaSetDevice(s->device));
+    RT_CUDA(cudaMemcpy(out16, s->counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 
@@ -2111,8 +2497,11 @@ int rt_trace_primary(RtScene *s, const RtCamera *camera, const RtRenderParams *p
     RT_CUDA(cudaMalloc((void **)&d, n * 4 * sizeof(uint32_t)));
     DCamera cam;
     fill_camera(*camera, cam);
+    SceneBinding binding;
+    if ((rc = binding.bind(s, nullptr))) { cudaFree(d); return rc; }
     k_primary_ids<<<(unsigned)((n + 127) / 128), 128>>>(s->d, cam, p->width, p->height, p->seed, r.x0, r.y0, rw, rh, d);
     cudaError_t e = cudaGetLastError();
+    binding.done();
     if (e == cudaSuccess) e = cudaMemcpy(ids, d, n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
     cudaFree(d);
     RT_CUDA(e);
@@ -2140,6 +2529,8 @@ int rt_trace_rays(RtScene *s, size_t n, const float *org, const float *dir, cons
     if (time) RT_CUDA(t.put(time, n * 4));
     RT_CUDA(i.put(nullptr, n * 16));
     if (aux) RT_CUDA(a.put(nullptr, n * 32));
+    SceneBinding binding;
+    if (int brc = binding.bind(s, nullptr)) return brc;
     k_trace_rays<<<(unsigned)((n + 127) / 128), 128>>>(s->d, n, (const float *)o.p, (const float *)d.p, time ? (const float *)t.p : nullptr, (uint32_t *)i.p, aux ? (float *)a.p : nullptr);
     RT_CUDA(cudaGetLastError());
     RT_CUDA(cudaMemcpy(ids, i.p, n * 16, cudaMemcpyDeviceToHost));
@@ -2156,6 +2547,8 @@ int rt_shade_rays(RtScene *s, size_t n, const float *org, const float *dir, cons
     RT_CUDA(o.put(org, n * 12)); RT_CUDA(d.put(dir, n * 12));
     if (time) RT_CUDA(t.put(time, n * 4));
     RT_CUDA(c.put(nullptr, n * 12));
+    SceneBinding binding;
+    if (int brc = binding.bind(s, nullptr)) return brc;
     k_shade_rays<<<(unsigned)((n + 127) / 128), 128>>>(s->d, n, (const float *)o.p, (const float *)d.p, time ? (const float *)t.p : nullptr, p->seed, p->max_bounces, p->nb_ech, (float *)c.p);
     RT_CUDA(cudaGetLastError());
     RT_CUDA(cudaMemcpy(rgb, c.p, n * 12, cudaMemcpyDeviceToHost));

@@ -243,6 +243,7 @@ struct DScene {
     const float4 *abvh_nodes;
     const uint32_t *abvh_prims;
     int abvh_root;
+    int abvh_n_nodes;          // inner nodes of that hierarchy (<= 127: it is only built for <= 128 primitives)
     float abvh_c[3], abvh_r;
     const DMaterial *sph_mat, *sq_mat, *mesh_mat;
     const DLight *lights;
@@ -250,6 +251,63 @@ struct DScene {
     DImage sky;
     int dark_sky;
 };
+
+// The scene of the render in flight lives in the constant bank (one upload per render call, rt_capi.cu : SceneBinding):
+// kernels and — what matters — the OUT-OF-LINE helpers read its fields as c[bank][offset] operands. Passed as a kernel
+// parameter and handed on by reference, the 264-byte struct was copied to every thread's local-memory frame at kernel
+// entry (19 STL.128) and read back through LDL by each helper. RT_SCENE_CONST=0 restores the by-value parameter (A/B).
+#ifndef RT_SCENE_CONST
+#define RT_SCENE_CONST 1
+#endif
+#if defined(__CUDACC__) && RT_SCENE_CONST
+__constant__ DScene c_scene;
+#define RT_S(s_) c_scene
+#else
+#define RT_S(s_) (s_)
+#endif
+
+// The analytic culling hierarchy staged in shared memory. It is built for at most 128 primitives, i.e. at most 127 nodes
+// of 64 B: the WHOLE hierarchy fits in 8 KB. Each CTA of the kernels that walk it pulls it in once, at kernel start, with
+// one bulk asynchronous copy (cp.async.bulk global -> shared, completion on an mbarrier: SASS UBLKCP + SYNCS), and the
+// walks then read nodes with LDS instead of LDG (north_star: "top levels staged into shared memory via TMA"; here the top
+// levels are all levels). RT_STAGE_ABVH=0: nodes through L1 (A/B, profiles/r02_notes.md).
+#ifndef RT_STAGE_ABVH
+#define RT_STAGE_ABVH 0
+#endif
+#define RT_ABVH_MAX_NODES 127
+#if defined(__CUDACC__) && RT_STAGE_ABVH
+__device__ __forceinline__ float4 *abvh_sm() { __shared__ alignas(128) float4 a[4 * RT_ABVH_MAX_NODES]; return a; }
+__device__ __forceinline__ void stage_abvh(const DScene &s) {
+    __shared__ alignas(8) unsigned long long mbar;
+    if (s.abvh_root < 0 || s.abvh_n_nodes <= 0 || s.abvh_n_nodes > RT_ABVH_MAX_NODES) return;   // kernel-uniform
+    const unsigned int bar = (unsigned int)__cvta_generic_to_shared(&mbar);
+    const unsigned int dst = (unsigned int)__cvta_generic_to_shared(abvh_sm());
+    const unsigned int bytes = (unsigned int)s.abvh_n_nodes * 64u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"(s.abvh_nodes), "r"(bytes), "r"(bar) : "memory");
+    }
+    unsigned int done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar) : "memory");
+    }
+}
+#define RT_ABVH_NODES(s) ((const float4 *)abvh_sm())   /* rt_scene_create builds no hierarchy beyond RT_ABVH_MAX_NODES nodes */
+#define RT_ABVH_LD(p) (*(p))
+#else
+#if defined(__CUDACC__)
+__device__ __forceinline__ void stage_abvh(const DScene &) {}
+#endif
+#define RT_ABVH_NODES(s) ((s).abvh_nodes)
+#define RT_ABVH_LD(p) RT_LDG(p)
+#endif
 
 struct Counters {   // per-thread work counters (only touched when STATS)
     unsigned long long closest, shadow, sphere, square, mesh, node, tri, tri_full, tex, rnd;
@@ -445,7 +503,8 @@ RT_HD bool mesh_closest(const Ray &ray, const RayInv &inv, const DScene &s, cons
 // ancestor (whose boxes contain it) AABB::intersects keeps tmin < t < tmax at every step and
 // returns true. Anything else — grazing, axis-parallel, tiny t — re-runs the reference's own fp64
 // slab test (slab_hit) up the parent chain, synthetic root (= KDTree::aabb gate) included.
-RT_COLD bool leaf_reachable_exact(const DScene &s, const Ray &ray, uint32_t leaf) {
+RT_COLD bool leaf_reachable_exact(const DScene &s_, const Ray &ray, uint32_t leaf) {
+    const DScene &s = RT_S(s_);
     const RayInv inv = make_inv(ray);
     uint32_t n = leaf;
     while (n != 0xFFFFFFFFu) {
@@ -473,7 +532,8 @@ RT_HD bool leaf_reachable(const DScene &s, const Ray &ray, float t, uint32_t lea
     if (leaf_contains_hit(s, ray, RT_FAST_RCP(ray.d.x), RT_FAST_RCP(ray.d.y), RT_FAST_RCP(ray.d.z), t, leaf)) return true;
     return leaf_reachable_exact(s, ray, leaf);
 }
-RT_COLD bool tri_reachable_exact(const DScene &s, const Ray &ray, uint32_t r0) {
+RT_COLD bool tri_reachable_exact(const DScene &s_, const Ray &ray, uint32_t r0) {
+    const DScene &s = RT_S(s_);
     for (uint32_t r = r0; r != 0xFFFFFFFFu; r = RT_LDG(s.ref_next + r))
         if (leaf_reachable_exact(s, ray, RT_LDG(s.ref_leaf + r))) return true;
     return false;
@@ -496,12 +556,42 @@ RT_HD bool tri_reachable(const DScene &s, const Ray &ray, float t, uint32_t r0) 
 #endif
 }
 // last reachable reference (decides ties between different triangles at the same t)
-RT_COLD uint32_t tri_last_reachable(const DScene &s, const Ray &ray, float t, uint32_t r0) {
+RT_COLD uint32_t tri_last_reachable(const DScene &s_, const Ray &ray, float t, uint32_t r0) {
+    const DScene &s = RT_S(s_);
     uint32_t last = 0xFFFFFFFFu;
     for (uint32_t r = r0; r != 0xFFFFFFFFu; r = RT_LDG(s.ref_next + r))
         if (leaf_reachable(s, ray, t, RT_LDG(s.ref_leaf + r))) last = r;
     return last;
 }
+
+// Traversal stack of the culling-hierarchy walks. The first RT_SM_STACK entries of every thread live in SHARED memory
+// (one column per thread of a [RT_SM_STACK][128] slab: entry k of thread t at slab[k * 128 + t], bank = t mod 32 whatever k,
+// so the lanes of a warp never conflict although each is at its own depth); deeper entries — the builders cap the depth at
+// 56, walks rarely go beyond a dozen pending nodes — spill to a local-memory tail that is normally never touched. Until
+// round 2 the whole stack was `int stack[64]` in local memory: an LDL/STL on the critical path of every push and pop,
+// and 256 B of every thread's frame competing with the scene for L1. All kernels that walk run 128-thread CTAs.
+// One walk is live per thread at any time, so every walk shares the same slab. RT_SM_STACK=0: the old local array (A/B).
+// Measured on B200 (profiles/r02_notes.md, r02c; kernel ms of a 16 / 2 / 4 / 2-spp frame of configs 2 / 3 / 4 / 5): local
+// array 11.4 / 66.0 / 75.5 / 67.0, 12 shared entries 11.7 / 70.5 / 79.9 / 68.5, 16: 11.8 / 70.5 / 80.0 / 68.9, 24: 12.4 / 70.5 /
+// 83.2 / 71.2. SLOWER, more so the larger the slab: 8-12 KB of shared memory per CTA x 8 CTAs come out of the SM's L1, which
+// is what serves the hierarchy nodes, and the local stack's few hot words were L1 hits anyway. So the default is 0.
+#ifndef RT_SM_STACK
+#define RT_SM_STACK 0
+#endif
+#define RT_CTA_THREADS 128
+struct TStack {
+#if defined(__CUDA_ARCH__) && RT_SM_STACK > 0
+    int *sm;
+    int ovf[64 - RT_SM_STACK];
+    __device__ __forceinline__ TStack() { __shared__ int slab[RT_SM_STACK * RT_CTA_THREADS]; sm = slab + threadIdx.x; }
+    __device__ __forceinline__ void put(int sp, int v) { if (sp < RT_SM_STACK) sm[sp * RT_CTA_THREADS] = v; else ovf[sp - RT_SM_STACK] = v; }
+    __device__ __forceinline__ int get(int sp) const { return sp < RT_SM_STACK ? sm[sp * RT_CTA_THREADS] : ovf[sp - RT_SM_STACK]; }
+#else
+    int a[64];
+    RT_HD void put(int sp, int v) { a[sp] = v; }
+    RT_HD int get(int sp) const { return a[sp]; }
+#endif
+};
 
 // Box tests of the culling hierarchies as one FMA per plane: (l - o) * iv  ==  l * iv - o * iv with o * iv rounded once per
 // ray (RT_OPT_BOXFMA). The planes then carry an ABSOLUTE error of up to 2^-24 |o * iv| (rounding of the product) next to
@@ -608,7 +698,7 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
     }
     if (m.bvh_root >= 0) {
         const Inv32 iv = make_inv32(ray);
-        int stack[64];
+        TStack stack;
         int sp = 0;
         int node = m.bvh_root;
 #if RT_OPT_WW
@@ -628,10 +718,10 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
                 if (h0 && h1) {
                     const bool swap = d1 < d0;
                     node = swap ? c1 : c0;
-                    stack[sp++] = swap ? c0 : c1;    // depth <= 56 by construction (rt_bvh.hpp)
+                    stack.put(sp++, swap ? c0 : c1);    // depth <= 56 by construction (rt_bvh.hpp)
                 } else if (h0) node = c0;
                 else if (h1) node = c1;
-                else node = sp > 0 ? stack[--sp] : DONE;
+                else node = sp > 0 ? stack.get(--sp) : DONE;
             }
             if (node == DONE) break;
             const uint32_t code = (uint32_t)(-(node + 1));
@@ -641,7 +731,7 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
                 RT_ANYHIT_STEP()
             }
             if (sp == 0) break;
-            node = stack[--sp];
+            node = stack.get(--sp);
         }
 #else
         for (;;) {
@@ -656,7 +746,7 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
                 if (h0 && h1) {
                     const bool swap = d1 < d0;
                     node = swap ? c1 : c0;
-                    stack[sp++] = swap ? c0 : c1;    // depth <= 56 by construction (rt_bvh.hpp)
+                    stack.put(sp++, swap ? c0 : c1);    // depth <= 56 by construction (rt_bvh.hpp)
                     continue;
                 }
                 if (h0) { node = c0; continue; }
@@ -670,7 +760,7 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
                 }
             }
             if (sp == 0) break;
-            node = stack[--sp];
+            node = stack.get(--sp);
         }
 #endif
     }
@@ -701,10 +791,10 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
             if (h0 && h1) { \
                 const bool swap = d1 < d0; \
                 node = swap ? c1 : c0; \
-                stack[sp++] = swap ? c0 : c1;    /* depth <= 56 by construction (rt_bvh.hpp) */ \
+                stack.put(sp++, swap ? c0 : c1);    /* depth <= 56 by construction (rt_bvh.hpp) */ \
             } else if (h0) node = c0; \
             else if (h1) node = c1; \
-            else node = sp > 0 ? stack[--sp] : MESH_END; \
+            else node = sp > 0 ? stack.get(--sp) : MESH_END; \
         }
 template <bool STATS>
 RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rng, Hit &h, bool &blocked, bool &done, Counters *cnt) {
@@ -712,7 +802,7 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
     const uint32_t NONE = 0xFFFFFFFFu;
     const int MESH_END = 0x7FFFFFFD;
     const Inv32 iv = make_inv32(ray);
-    int stack[64];
+    TStack stack;
     int sp = 0, mi = 0;
     // the always-tested triangles of a mesh come first, like a leaf
     uint32_t k = s.meshes[0].always_first, kend = k + s.meshes[0].always_count;
@@ -726,7 +816,7 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
         if (node < 0) {   // a leaf: its triangles are tested at the top of the next round
             const uint32_t code = (uint32_t)(-(node + 1));
             k = code >> 3; kend = k + (code & 7u);
-            node = sp > 0 ? stack[--sp] : MESH_END;
+            node = sp > 0 ? stack.get(--sp) : MESH_END;
             continue;
         }
         // mesh mi is finished
@@ -756,13 +846,14 @@ RT_HD void analytic_candidates(const DScene &s, const Ray &ray, const float &lim
     // per-ray enlargement (see build_analytic_accel): quadratic term x 1/r of the spheres below, plus a linear term
     const float dist = length(ray.o - ld3(s.abvh_c)) + s.abvh_r;
     const float kq = 32.f * 5.96e-8f * dist * dist, kl = 64.f * 5.96e-8f * dist;
-    int stack[64];
+    TStack stack;
     int sp = 0;
     int node = s.abvh_root;
     for (;;) {
         if (node >= 0) {
-            const float4 n0 = RT_LDG(s.abvh_nodes + 4 * node), n1 = RT_LDG(s.abvh_nodes + 4 * node + 1),
-                         n2 = RT_LDG(s.abvh_nodes + 4 * node + 2), n3 = RT_LDG(s.abvh_nodes + 4 * node + 3);
+            const float4 *const an = RT_ABVH_NODES(s);
+            const float4 n0 = RT_ABVH_LD(an + 4 * node), n1 = RT_ABVH_LD(an + 4 * node + 1),
+                         n2 = RT_ABVH_LD(an + 4 * node + 2), n3 = RT_ABVH_LD(an + 4 * node + 3);
             if (STATS) cnt->node++;
             const float p0 = kq * n3.z + kl, p1 = kq * n3.w + kl;
             float d0, d1;
@@ -772,7 +863,7 @@ RT_HD void analytic_candidates(const DScene &s, const Ray &ray, const float &lim
             if (h0 && h1) {
                 const bool swap = d1 < d0;
                 node = swap ? c1 : c0;
-                stack[sp++] = swap ? c0 : c1;
+                stack.put(sp++, swap ? c0 : c1);
                 continue;
             }
             if (h0) { node = c0; continue; }
@@ -783,7 +874,7 @@ RT_HD void analytic_candidates(const DScene &s, const Ray &ray, const float &lim
             for (uint32_t k = first; k < first + count; ++k) f(RT_LDG(s.abvh_prims + k));
         }
         if (sp == 0) break;
-        node = stack[--sp];
+        node = stack.get(--sp);
     }
 }
 
@@ -884,7 +975,8 @@ RT_HD int texel_index(const DImage &im, float u, float v, float sx, float sy) {
 
 // Material::texture (Material.cpp:63-92). `color` is left untouched for Texture_None.
 template <bool STATS>
-RT_COLD void material_texture(const DScene &s, const DMaterial &m, V3 &color, float u, float v, Counters *cnt) {
+RT_COLD void material_texture(const DScene &s_, const DMaterial &m, V3 &color, float u, float v, Counters *cnt) {
+    const DScene &s = RT_S(s_);
     if (m.texture_type == 1) {
         color = ((int)(u * m.tsx) % 2 == (int)(v * m.tsy) % 2) ? ld3(m.checker1) : ld3(m.checker2);
     } else if (m.texture_type == 2) {
@@ -902,7 +994,8 @@ RT_COLD void material_texture(const DScene &s, const DMaterial &m, V3 &color, fl
 
 // Material::emit (Material.cpp:13-24)
 template <bool STATS>
-RT_COLD V3 material_emit(const DScene &s, const DMaterial &m, float u, float v, Counters *cnt) {
+RT_COLD V3 material_emit(const DScene &s_, const DMaterial &m, float u, float v, Counters *cnt) {
+    const DScene &s = RT_S(s_);
     if (!m.emissive) return v3(0.f);
     V3 c = v3(0.f);
     if (m.texture_type == 0) c = ld3(m.light_color);
@@ -913,7 +1006,8 @@ RT_COLD V3 material_emit(const DScene &s, const DMaterial &m, float u, float v, 
 // Material::get_normal (Material.cpp:114-130): tangent-space map, T/B = the square's stale
 // m_right_vector / m_up_vector members.
 template <bool STATS>
-RT_COLD V3 material_normal(const DScene &s, const DMaterial &m, V3 n, float u, float v, V3 T, V3 B, Counters *cnt) {
+RT_COLD V3 material_normal(const DScene &s_, const DMaterial &m, V3 n, float u, float v, V3 T, V3 B, Counters *cnt) {
+    const DScene &s = RT_S(s_);
     if (m.normal_map < 0) return n;
     const DImage im = s.normal_maps[m.normal_map];
     if (im.w < 1 || im.h < 1) return n;   // reference would dereference an empty image; defined as "no map"
@@ -925,7 +1019,8 @@ RT_COLD V3 material_normal(const DScene &s, const DMaterial &m, V3 n, float u, f
 
 // Scene::skyboxTexture (Scene.h:149-161)
 template <bool STATS>
-RT_COLD V3 sky_color(const DScene &s, V3 d, int n_remaining, Counters *cnt) {
+RT_COLD V3 sky_color(const DScene &s_, V3 d, int n_remaining, Counters *cnt) {
+    const DScene &s = RT_S(s_);
     if (s.sky.w < 1 || s.sky.h < 1) {
         if (s.dark_sky) return v3(0.f);
         const float a = (float)(0.5 * ((double)d.y + 1.0));
@@ -1087,6 +1182,7 @@ RT_HD V3 trace_path(const DScene &s, Ray ray, Rng &rng, int max_bounces, int nb_
 // still execute the intersection loops together; a lane whose path ends takes a new path at once.
 
 
+struct PathRecs { V3 rec_c[RT_MAX_BOUNCES], rec_kd[RT_MAX_BOUNCES], rec_e[RT_MAX_BOUNCES]; };
 struct PathState {
     Rng rng;
     Ray ray;             // the ray to intersect next
@@ -1105,9 +1201,11 @@ struct PathState {
     // order; cl_n < 0 = too many for the list, shadow samples walk the mesh hierarchies themselves
     uint32_t cl[RT_LC_MAXC];
     int cl_n;
-    V3 rec_c[RT_MAX_BOUNCES], rec_kd[RT_MAX_BOUNCES], rec_e[RT_MAX_BOUNCES];
-    // wavefront kernels (variant 6) keep the per-depth records in global memory instead: entry (3*depth + {0 colour,
-    // 1 kd, 2 e}) of path slot `path` is wf_rec[(3*depth + k) * wf_stride + path]; the arrays above are then unused
+    // per-depth radiance records: the state-machine kernels keep them in the thread's frame (PathRecs, 576 B, declared
+    // by the kernel); the wavefront kernels (variant 6) keep them in global memory instead: entry (3*depth + {0 colour,
+    // 1 kd, 2 e}) of path slot `path` is wf_rec[(3*depth + k) * wf_stride + path], and `recs` is null — their frame
+    // does not carry the arrays
+    PathRecs *recs;
     float4 *wf_rec;
     unsigned long long wf_stride;
 };
@@ -1302,7 +1400,7 @@ RT_HD void intersect_ray_voted(const DScene &s, const Ray &ray, int mode, float 
     float kq = 0.f, kl = 0.f;          // per-ray box enlargement, analytic phase only (build_analytic_accel)
     int phase = -1;                    // -1: analytic hierarchy; m >= 0: mesh m
     int node = EMPTY, sp = 0;
-    int stack[64];
+    TStack stack;
     uint32_t k = 0, kend = 0;
     float best_t = h.t;
     uint32_t best_ref = NONE;
@@ -1345,7 +1443,7 @@ RT_HD void intersect_ray_voted(const DScene &s, const Ray &ray, int mode, float 
         } else if (want_node) {
             if (node == EMPTY) {
                 if (sp > 0) {
-                    node = stack[--sp];
+                    node = stack.get(--sp);
                 } else {
                     // the current phase is exhausted
                     if (phase < 0) {
@@ -1397,7 +1495,7 @@ RT_HD void intersect_ray_voted(const DScene &s, const Ray &ray, int mode, float 
                     if (h0 && h1) {
                         const bool swap = d1 < d0;
                         node = swap ? c1 : c0;
-                        stack[sp++] = swap ? c0 : c1;
+                        stack.put(sp++, swap ? c0 : c1);
                     } else if (h0) node = c0;
                     else if (h1) node = c1;
                     else node = EMPTY;
@@ -1594,7 +1692,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
             const float kq = 32.f * 5.96e-8f * dist * dist, kl = 64.f * 5.96e-8f * dist;
             uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
             int best_seq = 0x7FFFFFFF;
-            int stack[64];
+            TStack stack;
             int sp = 0;
             int node = s.abvh_root;
 #if RT_OPT_WW_LC
@@ -1604,8 +1702,9 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
             const int DONE = 0x7FFFFFFF;
             for (;;) {
                 while (node >= 0 && node != DONE) {
-                    const float4 n0 = RT_LDG(s.abvh_nodes + 4 * node), n1 = RT_LDG(s.abvh_nodes + 4 * node + 1),
-                                 n2 = RT_LDG(s.abvh_nodes + 4 * node + 2), n3 = RT_LDG(s.abvh_nodes + 4 * node + 3);
+                    const float4 *const an = RT_ABVH_NODES(s);
+                    const float4 n0 = RT_ABVH_LD(an + 4 * node), n1 = RT_ABVH_LD(an + 4 * node + 1),
+                                 n2 = RT_ABVH_LD(an + 4 * node + 2), n3 = RT_ABVH_LD(an + 4 * node + 3);
                     if (STATS) cnt->node++;
                     const float p0 = kq * n3.z + kl, p1 = kq * n3.w + kl;
                     const float limit = collect ? limit_c : h.t;
@@ -1616,10 +1715,10 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
                     if (h0 && h1) {
                         const bool swap = d1 < d0;
                         node = swap ? c1 : c0;
-                        stack[sp++] = swap ? c0 : c1;
+                        stack.put(sp++, swap ? c0 : c1);
                     } else if (h0) node = c0;
                     else if (h1) node = c1;
-                    else node = sp > 0 ? stack[--sp] : DONE;
+                    else node = sp > 0 ? stack.get(--sp) : DONE;
                 }
                 if (node == DONE) break;
                 {
@@ -1645,13 +1744,14 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
                     }
                 }
                 if (sp == 0) break;
-                node = stack[--sp];
+                node = stack.get(--sp);
             }
 #else
             for (;;) {
                 if (node >= 0) {
-                    const float4 n0 = RT_LDG(s.abvh_nodes + 4 * node), n1 = RT_LDG(s.abvh_nodes + 4 * node + 1),
-                                 n2 = RT_LDG(s.abvh_nodes + 4 * node + 2), n3 = RT_LDG(s.abvh_nodes + 4 * node + 3);
+                    const float4 *const an = RT_ABVH_NODES(s);
+                    const float4 n0 = RT_ABVH_LD(an + 4 * node), n1 = RT_ABVH_LD(an + 4 * node + 1),
+                                 n2 = RT_ABVH_LD(an + 4 * node + 2), n3 = RT_ABVH_LD(an + 4 * node + 3);
                     if (STATS) cnt->node++;
                     const float p0 = kq * n3.z + kl, p1 = kq * n3.w + kl;
                     const float limit = collect ? limit_c : h.t;
@@ -1662,7 +1762,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
                     if (h0 && h1) {
                         const bool swap = d1 < d0;
                         node = swap ? c1 : c0;
-                        stack[sp++] = swap ? c0 : c1;
+                        stack.put(sp++, swap ? c0 : c1);
                         continue;
                     }
                     if (h0) { node = c0; continue; }
@@ -1690,7 +1790,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
                     }
                 }
                 if (sp == 0) break;
-                node = stack[--sp];
+                node = stack.get(--sp);
             }
 #endif
             if (collect) {
@@ -1731,15 +1831,15 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
                             const bool h0 = cone_box(cone, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, limit_c, d0);
                             const bool h1 = cone_box(cone, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, limit_c, d1);
                             const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
-                            if (h0 && h1) { mnode = c0; stack[msp++] = c1; }
+                            if (h0 && h1) { mnode = c0; stack.put(msp++, c1); }
                             else if (h0) mnode = c0;
                             else if (h1) mnode = c1;
-                            else mnode = msp > 0 ? stack[--msp] : 0x7FFFFFFF;
+                            else mnode = msp > 0 ? stack.get(--msp) : 0x7FFFFFFF;
                         }
                         if (mnode == 0x7FFFFFFF) break;
                         const uint32_t code = (uint32_t)(-(mnode + 1));
                         k = code >> 3; kend = k + (code & 7u);
-                        mnode = msp > 0 ? stack[--msp] : 0x7FFFFFFF;
+                        mnode = msp > 0 ? stack.get(--msp) : 0x7FFFFFFF;
                     }
                 }
                 st.cl_n = cn;
@@ -1840,7 +1940,7 @@ RT_HD V3 path_fold(const PathState &st, V3 tail) {
                          e = RT_LD_STREAM(st.wf_rec + (3ull * k + 2) * st.wf_stride + st.path);
             r = (v3(c.x, c.y, c.z) + comp_product(r, v3(kd.x, kd.y, kd.z))) + v3(e.x, e.y, e.z);
         } else {
-            r = (st.rec_c[k] + comp_product(r, st.rec_kd[k])) + st.rec_e[k];
+            r = (st.recs->rec_c[k] + comp_product(r, st.recs->rec_kd[k])) + st.recs->rec_e[k];
         }
     }
     r = v3(0.f) + r;
@@ -1857,7 +1957,8 @@ __device__ __forceinline__
 #else
 RT_COLD
 #endif
-void path_shadow_sample(const DScene &s, PathState &st, Counters *cnt) {
+void path_shadow_sample(const DScene &s_, PathState &st, Counters *cnt) {
+    const DScene &s = RT_S(s_);
     if (STATS) cnt->rnd += 3;
     const V3 lp = ld3(s.lights[st.light].pos);
     const float delta = s.lights[st.light].radius / 2.f;
@@ -1872,7 +1973,8 @@ void path_shadow_sample(const DScene &s, PathState &st, Counters *cnt) {
 // Start lighting with light st.light, or — when the lights are exhausted — scatter and continue.
 // Returns true when the path has ended (result in `out`).
 template <bool STATS, bool LC = false, bool WF = false>
-RT_SHARED_BOUNCE bool path_next_light_or_bounce(const DScene &s, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
+RT_SHARED_BOUNCE bool path_next_light_or_bounce(const DScene &s_, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
+    const DScene &s = RT_S(s_);
     if (st.light < s.n_lights) {
         const V3 L = normalized(ld3(s.lights[st.light].pos) - st.P);
         const float dotLN = dot(L, st.n);
@@ -1889,7 +1991,7 @@ RT_SHARED_BOUNCE bool path_next_light_or_bounce(const DScene &s, PathState &st, 
         RT_ST_STREAM(st.wf_rec + (3ull * st.depth + 1) * st.wf_stride + st.path, make_float4(st.kd.x, st.kd.y, st.kd.z, 0.f));
         RT_ST_STREAM(st.wf_rec + (3ull * st.depth + 2) * st.wf_stride + st.path, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
     } else {
-        st.rec_c[st.depth] = st.color; st.rec_kd[st.depth] = st.kd; st.rec_e[st.depth] = st.e;
+        st.recs->rec_c[st.depth] = st.color; st.recs->rec_kd[st.depth] = st.kd; st.recs->rec_e[st.depth] = st.e;
     }
     ++st.depth;
     --st.N;

@@ -680,11 +680,12 @@ RtMaterial flat_material(const Scene &s, const Material &m) {
     return r;
 }
 RtImage flat_image(const ppmLoader::ImageRGB &im) {
-    RtImage r{0, 0, nullptr};
+    RtImage r{0, 0, nullptr, 0};
     if (im.w >= 1 && im.h >= 1 && im.data.size() >= (size_t)im.w * (size_t)im.h) {
         r.w = im.w;
         r.h = im.h;
         r.rgb = (const uint8_t *)im.data.data();
+        r.content_id = im.content_id;
     }
     return r;
 }

@@ -1,5 +1,7 @@
 #include "imageLoader.h"
 
+#include <atomic>
+
 namespace ppmLoader {
 namespace {
 // skip line breaks, then at most one '#' comment line (imageLoader.cpp:10-18)
@@ -12,6 +14,7 @@ bool fail(ImageRGB &img, const std::string &why) {
     std::cout << why << std::endl;
     img.w = img.h = 0;
     img.data.clear();
+    img.content_id = 0;
     return false;
 }
 }  // namespace
@@ -54,6 +57,8 @@ bool load_ppm(ImageRGB &img, const std::string &name) {
         }
     }
     if (f.fail()) return fail(img, "PPM pixel data ends early or is not numeric: " + name);
+    static std::atomic<unsigned long long> next_id{1};
+    img.content_id = next_id.fetch_add(1);
     return true;
 }
 }  // namespace ppmLoader

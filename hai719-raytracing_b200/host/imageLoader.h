@@ -15,6 +15,9 @@ struct RGB { unsigned char r, g, b; };
 struct ImageRGB {
     int w = 0, h = 0;
     std::vector<RGB> data;
+    // identity of the pixel contents for the device image cache (RtImage::content_id): load_ppm gives every file it loads
+    // a fresh number; code that edits `data` afterwards must set it to 0 (= always upload) or to a number of its own
+    unsigned long long content_id = 0;
 };
 bool load_ppm(ImageRGB &img, const std::string &name);
 }  // namespace ppmLoader

@@ -97,7 +97,7 @@ void *sim_scene_create(const RtSceneDesc *desc) {
     }
     d.lights = s->lights.data();
     build_analytic_accel(*desc, s->aa);
-    d.abvh_root = s->aa.root; d.abvh_nodes = s->aa.nodes.data(); d.abvh_prims = s->aa.tris.data();
+    d.abvh_root = s->aa.root; d.abvh_n_nodes = (int)(s->aa.nodes.size() / 4); d.abvh_nodes = s->aa.nodes.data(); d.abvh_prims = s->aa.tris.data();
     for (int k = 0; k < 3; ++k) d.abvh_c[k] = s->aa.center[k];
     d.abvh_r = s->aa.radius;
     const uint32_t nm = desc->n_meshes;
@@ -175,7 +175,7 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         float4 rec[3 * RT_MAX_BOUNCES];
                         PathState st;
                         path_begin(st, ray, rng, 0u, p->max_bounces);
-                        st.wf_rec = rec; st.wf_stride = 1;
+                        st.recs = nullptr; st.wf_rec = rec; st.wf_stride = 1;
                         V3 c = v3(0.f);
                         bool fin = false;
                         for (int level = 0; level < p->max_bounces && !fin; ++level) {
@@ -209,7 +209,9 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         const bool lc = (p->variant & 0xFF) == 5 && s->d.abvh_root >= 0 && s->d.n_lights > 0;   // as rt_render_device selects
                         const bool accel = (p->variant & 0xFF) == 3 || ((p->variant & 0xFF) == 5 && !lc);
                         PathState st;
+                        PathRecs recs;
                         path_begin(st, ray, rng, 0u, p->max_bounces);
+                        st.recs = &recs;
                         V3 c = v3(0.f);
                         bool fin = false;
                         if (p->max_bounces == 0) { c = path_fold(st, v3(0.f)); fin = true; }

@@ -480,7 +480,7 @@ def test_bad_arguments_are_rejected(gpu, assets):
     d.abi_version = 99
     out = C.c_void_p()
     assert gpu.rt.rt_scene_create(C.byref(d), 0, C.byref(out)) == -1
-    d.abi_version = 2
+    d.abi_version = 3
     assert gpu.rt.rt_scene_create(C.byref(d), 64, C.byref(out)) == -1
 
 

@@ -280,8 +280,9 @@ def test_degenerate_empty_leaves_and_depth_100_tree(gpu, ref, assets):
     stats = [g.kd_stats(m) for m in range(g.counts()["meshes"])]
     deep = int(np.argmax([s["max_depth"] for s in stats]))
     # SURVEY's "empty leaves" are nodes where KDTree::build gave up (depth 100 / equal halves, KDTree.cpp:142): no children
-    # and no triangles. A full binary tree has 2 * leaves - 1 nodes; the surplus is those childless non-leaf nodes (2 here).
-    childless = stats[deep]["nodes"] - (2 * stats[deep]["leaves"] - 1)
+    # and no triangles. A full binary tree with n nodes has (n + 1) / 2 leaf positions; those not filled by a real leaf are
+    # the childless non-leaf nodes (1788 - 1786 = 2 here).
+    childless = (stats[deep]["nodes"] + 1) // 2 - stats[deep]["leaves"]
     assert stats[deep]["max_depth"] >= 100 and childless + stats[deep]["empty_leaves"] == 2, stats
     pos, tri, lo, hi = _mesh_arrays(g, deep)
     rng = np.random.default_rng(11)
@@ -354,3 +355,29 @@ def test_ray_counts_equal_the_references_own_calls(gpu, assets, name, w, h, spp)
     assert st["n_closest_rays"] == want["n_closest_rays"], name
     assert st["n_shadow_rays"] == want["n_shadow_rays"], name
     assert st["n_random"] == want["n_random"], name
+
+
+# ---- speculative shadow samples (k_wf_shadow / k_wf_validate) ---------------------------------------------------------------
+@pytest.mark.parametrize("name,w,h,spp", [("flamingo_pond", 240, 136, 3), ("config5", 240, 136, 2), ("random_spheres", 240, 136, 3),
+                                          ("flamingo", 160, 90, 2), ("raccoon", 160, 90, 2)])
+def test_speculative_shadow_rounds_do_not_change_a_bit(gpu, assets, name, w, h, spp):
+    """The wavefront traces the NB_ECH samples of a parked light in parallel from GUESSED stream positions and keeps only
+    the samples whose guess the validation confirms (rt_capi.cu : k_wf_shadow). Whatever the number of rounds (variant
+    bits 20..23: 15 = off, 1..14 rounds; the rest is finished sequentially) the image, the ray counts and the number of
+    random draws are those of the sequential sample kernel and of the one-path-per-lane kernel (variant 1). Scenes: one
+    and two lights, with and without meshes, list and walk queues; nb_ech 10 and 4."""
+    s = gpu.Scene(name, aspect=w / h, seed=0)
+    want = s.render(w, h, spp, seed=3, variant=1, stats=True)
+    off = s.render(w, h, spp, seed=3, variant=6 | (15 << 20), stats=True)
+    assert np.array_equal(bits(want["linear"]), bits(off["linear"]))
+    for rounds in (1, 2, 3, 6, 14):
+        for st in (False, True):
+            got = s.render(w, h, spp, seed=3, variant=6 | (rounds << 20), stats=st)
+            assert np.array_equal(bits(want["linear"]), bits(got["linear"])), (name, rounds, st)
+            for k in ("n_closest_rays", "n_shadow_rays") + (("n_random", "n_tex_fetches") if st else ()):
+                assert want["stats"][k] == got["stats"][k], (name, rounds, st, k)
+    auto = s.render(w, h, spp, seed=3, variant=6)
+    assert np.array_equal(bits(want["linear"]), bits(auto["linear"]))
+    few = s.render(w, h, spp, seed=3, variant=6 | (2 << 20), nb_ech=4, max_bounces=3)
+    ref4 = s.render(w, h, spp, seed=3, variant=1, nb_ech=4, max_bounces=3)
+    assert np.array_equal(bits(ref4["linear"]), bits(few["linear"]))

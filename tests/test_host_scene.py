@@ -23,7 +23,7 @@ def test_libraries_export_every_declared_symbol(hb):
         src = open(os.path.join(ROOT, "include", header)).read()
         declared = set(re.findall(r"\b(%s[a-z_0-9]+)\s*\(" % prefix, src))
         assert declared == set(names), (declared ^ set(names))
-    assert hb.rt.rt_abi_version() == 2
+    assert hb.rt.rt_abi_version() == 3
 
 
 def test_struct_sizes_match_the_c_header(hb, tmp_path):
@@ -92,7 +92,7 @@ def test_kd_tree_shapes_match_survey(hb, assets):
 def test_flatten_is_consistent(hb, assets):
     s = hb.Scene("flamingo_pond")
     d = s.flatten().contents
-    assert d.abi_version == 2 and d.n_meshes == 2 and d.n_squares == 1 and d.n_lights == 1
+    assert d.abi_version == 3 and d.n_meshes == 2 and d.n_squares == 1 and d.n_lights == 1
     for i in range(d.n_meshes):
         m = d.meshes[i]
         nodes = np.ctypeslib.as_array(C.cast(m.nodes, C.POINTER(C.c_uint32)), shape=(m.n_nodes, 10))

@@ -116,7 +116,7 @@ class RtStats(C.Structure):
 # every symbol the two headers declare — tests check the libraries export exactly these
 RT_SYMBOLS = ["rt_abi_version", "rt_device_count", "rt_last_error", "rt_scene_create", "rt_scene_destroy", "rt_scene_retain",
               "rt_render_device_image", "rt_render_multi", "rt_render_multi_device", "rt_ipc_alloc", "rt_ipc_open", "rt_ipc_close", "rt_ipc_free", "rt_release_cached_memory", "rt_scene_update_analytic",
-              "rt_scene_check", "rt_scene_device_bytes", "rt_scene_h2d_bytes", "rt_debug_counters", "rt_render_pixel_count", "rt_tile_layout", "rt_render", "rt_render_rgb8", "rt_quantize_device",
+              "rt_scene_check", "rt_scene_device_bytes", "rt_scene_h2d_bytes", "rt_render_pixel_count", "rt_tile_layout", "rt_render", "rt_render_rgb8", "rt_quantize_device",
               "rt_render_device", "rt_untile_device",
               "rt_accum_create", "rt_accum_destroy", "rt_accum_reset", "rt_accum_add", "rt_accum_samples", "rt_accum_read",
               "rt_trace_primary", "rt_trace_rays", "rt_shade_rays", "rt_measure_fp32_peak"]
@@ -141,7 +141,6 @@ rt.rt_scene_destroy.argtypes = [C.c_void_p]
 rt.rt_scene_update_analytic.argtypes = [C.c_void_p, C.POINTER(RtSceneDesc)]
 rt.rt_scene_device_bytes.restype = C.c_size_t
 rt.rt_scene_device_bytes.argtypes = [C.c_void_p]
-rt.rt_debug_counters.argtypes = [C.c_void_p, C.c_void_p]
 rt.rt_scene_h2d_bytes.restype = C.c_size_t
 rt.rt_scene_h2d_bytes.argtypes = [C.c_void_p]
 rt.rt_render_pixel_count.restype = C.c_int64
@@ -351,13 +350,6 @@ class Scene:
     def update_device(self):
         """Push the host scene's spheres / squares / lights to its device copies in place (no mesh / texture upload)."""
         _host_check(host.hai_scene_update_device(self.h))
-
-    def debug_counters(self, device=0):
-        o = (C.c_ulonglong * 16)()
-        rc = rt.rt_debug_counters(self.device_handle(device), o)
-        if rc != 0:
-            raise RtError(rc, rt.rt_last_error().decode(errors="replace"))
-        return list(o)
 
     def h2d_bytes(self, device=0):
         """Bytes the last upload of this scene to `device` really copied (cached images are not copied again)."""

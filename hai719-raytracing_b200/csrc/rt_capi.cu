@@ -322,45 +322,55 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScen
 // ~2 000 instructions against a 32 KB L1.5 instruction cache, profiles/r01_notes.md):
 //   k_camera_rays  primary rays of the chunk (above)
 //   k_wf_trace     closest hit (Scene::computeIntersection) + shading of the hit (Scene.h:270-304) for
-//                  every live path; paths that miss fold their sky colour and finish
+//                  every live path; paths that miss fold their sky colour and finish. In a scene
+//                  without lights the light stage is only Material::scatter, so it runs right here
+//                  (NOLIGHT) and the hit never travels through HBM.
 //   k_wf_light     direct lighting of the hit — per light one cone walk for the occluder candidates,
 //                  then the NB_ECH shadow samples in registers — then Material::scatter; paths
 //                  that used their last bounce fold and finish, the others queue for the next level
 // Both are PERSISTENT: warps fetch batches of 32 queue entries with one atomicAdd, and survivors are
-// appended to the next queue with one warp-aggregated atomicAdd (__ballot_sync/__popc ranks), so the
-// host never needs to know how many paths are alive. Path state between kernels lives in HBM as
-// float4 SoA records (one 128-bit access per field and lane): 40 B ray + 88 B hit + 48 B per bounce.
+// appended to the next queue by warp-aggregated block reservation (__ballot_sync/__popc ranks), so the
+// host never needs to know how many paths are alive.
+//
+// Path state between kernels lives in HBM as float4 SoA records (one 128-bit access per field and lane),
+// STORED AT THE QUEUE POSITION of the entry, not at the path's slot: entry i of the live queue has its
+// ray in ray0[i] / ray1[i] / rng_ray[i], entry i of the hit queue its hit in hit0..4[i] / rng_hit[i]; the
+// queue word itself is the path slot (where the radiance records and the final sample go). A kernel
+// therefore reads its input as contiguous 128-byte lines and writes its output the same way. Until round 2
+// the records sat at the slot and were gathered through the queue: half-used sectors from bounce 1 on,
+// 877 B of DRAM traffic per path against 599 B of records (config 2; the light kernel of the pool scene
+// moved 330 B per path and level for 176 B of records, profiles/r02_notes.md).
 #define WF_HIT_E 0x08000000u   /* hit record flags in the code word of hit1.w: emission stored / incoming direction stored */
 #define WF_HIT_D 0x04000000u
-#define WF_NCTR 8   /* counters per bounce level: trace head/count, light head/count, parked head/count, overflow head/count */
+#define WF_NCTR 12  /* counters per bounce level: [0] trace head, [1] live-queue length, [2] light head, [3] hit-queue length, [4] parked
+                       head, [5] parked length, [6] overflow head, [7] overflow length, [8] rays traced, [9] hits lit, [10] mesh-walk
+                       head, [11] mesh-walk length (lengths count reserved positions, padding included; [8] / [9] count real entries) */
+#define WF_INVALID 0xFFFFFFFFu /* queue word of a padding position */
 struct WfArgs {
     unsigned int n_paths;              // paths of this chunk (slots 0 .. n_paths-1)
     unsigned int max_grab;             // batches a warp may fetch with one atomic (see wf_next_batch)
+    unsigned int block;                // queue positions a warp reserves with one atomic (see wf_push)
+    unsigned int mesh_inline_min;      // split trace: lanes of a warp that must touch a mesh for the warp to walk inline (see k_wf_trace)
     int max_bounces, nb_ech, level;
-    const float4 *cam_rays; const unsigned int *cam_keys;   // level 0 input
-    float4 *ray0, *ray1;               // {o.xyz, time}, {d.xyz, bits(N | depth << 8)}
-    uint2 *rng;                        // {key, ctr}
-    float4 *hit0, *hit1, *hit2, *hit3, *hit4;   // {P, time} {n, bits(kind << 28 | obj)} {kd, bits(N | depth << 8)} {e, -} {in_d, -}
-    float4 *rec; unsigned long long rec_stride;
-    unsigned int *q_in, *q_out;        // trace: q_in = live paths (level > 0), q_out = paths with a hit; light: the reverse
-    unsigned int *q_live_next;         // fused trace kernel: the queue of the next level's live rays
-    unsigned int *q_park;              // light phase A -> phase B: hits whose light needs its shadow samples traced
+    const float4 *cam_rays; const unsigned int *cam_keys;   // level 0 input, by slot
+    // live queue of this level (trace input) ...
+    const unsigned int *q_live; const float4 *ray0, *ray1; const uint2 *rng_ray;   // {o.xyz, time}, {d.xyz, bits(N | depth << 8)}, {key, ctr}
+    // ... and of the next level (light output; NOLIGHT: trace output)
+    unsigned int *q_next; float4 *nray0, *nray1; uint2 *nrng;
+    // hit queue of this level (trace output, light input): {P, time} {n, bits(kind << 28 | obj)} {kd, bits(N | depth << 8)} {e, -} {in_d, -}
+    unsigned int *q_hit; float4 *hit0, *hit1, *hit2, *hit3, *hit4; uint2 *rng_hit;
+    float4 *rec; unsigned long long rec_stride;   // radiance records, by slot
+    unsigned int *q_mesh; float4 *mesh_hit;   // trace phase A -> phase B: live-queue positions of the rays that touch a mesh, and their analytic
+                                       // hit so far {t, bits(type << 28 | obj), u, v} (by position in q_mesh)
+    unsigned int *q_park;              // light phase A -> phase B: hit-queue positions whose light needs its shadow samples traced
     unsigned int *q_over;              // ... those whose candidate-triangle list overflowed: their samples walk the mesh hierarchies,
     int which_park;                    //     so they get warps of their own (phase B runs once per queue: 0 = q_park, 1 = q_over)
-    float4 *park0, *park1;             // ... and what phase B needs besides the hit record: {colour so far, light | (cl_n + 1) << 8}, {cm0..cm3}
-    float4 *park2;                     // candidate triangles, RT_LC_MAXC / 4 float4 planes of rec_stride entries
-    unsigned int *ctr;                 // per level WF_NCTR counters: [0] trace head, [1] trace count, [2] light head, [3] light count,
-                                       //                             [4] parked head, [5] parked count, [6] overflow head, [7] overflow count
+    float4 *park0, *park1;             // ... and what phase B needs besides the hit record, by hit-queue position:
+    float4 *park2;                     //     {colour so far, light | (cl_n + 1) << 8}, {cm0..cm3}, RT_LC_MAXC / 4 planes of candidate triangles
+    unsigned long long park_stride;
+    unsigned int *ctr;                 // WF_NCTR counters per level
     float *samples;
     unsigned long long *stats;
-    // speculative shadow samples (k_wf_shadow / k_wf_validate below)
-    unsigned int *sp_hdr;              // per path slot: samples validated so far | blocked so far << 8 | guessed draws per sample << 16
-    unsigned short *sp_res;            // per path slot and sample: draws the sample consumed | blocked << 15
-    const unsigned int *sp_q_in;       // this round's parked hits ...
-    const unsigned int *sp_cnt_in;     // ... and how many
-    unsigned int *sp_head, *sp_vhead;  // work-fetch heads of the round's shadow and validate kernels
-    unsigned int *sp_q_out, *sp_cnt_out;   // hits with samples left after this round
-    int sp_enabled;                    // the sample kernel resumes from sp_hdr instead of sample 0
 };
 
 // Queue traffic. Every batch of 32 entries used to cost two atomicAdds on two counters of one 32-byte sector (work
@@ -369,11 +379,11 @@ struct WfArgs {
 //   * a warp FETCHES several batches per atomic, guided self-scheduling: 8 batches while plenty of work is left,
 //     shrinking to 1 near the end so that the tail stays balanced (scenes with meshes always fetch 1: measured, their
 //     batches are too uneven);
-//   * survivors are STAGED per warp in shared memory (positions from __ballot_sync/__popc, no atomics) and appended to
-//     the global queue 256 at a time with one atomicAdd and coalesced 128-byte stores; the last partial block is appended
-//     with its exact size, so the queue has no holes and the next kernel's warps are full.
-#define WF_STAGE_FLUSH 256
-#define WF_STAGE_CAP (WF_STAGE_FLUSH + 32)
+//   * a warp RESERVES output positions a block at a time (256 for large chunks) with one atomicAdd and hands them to its
+//     survivors in rank order (__ballot_sync/__popc), so every survivor knows its queue position at once and stores its
+//     records there — coalesced, no staging in shared memory. When the kernel ends, the unused tail of a warp's last
+//     block is padded with WF_INVALID words: the consumer skips those positions (they come in runs, so whole batches
+//     are skipped at the price of one 128-byte read).
 // Path state, queues and radiance records are written once by one kernel and read once by the next, hundreds of MB per
 // level: streaming (evict-first) accesses keep them from pushing the per-thread stacks and the scene out of L2.
 #ifndef RT_WF_STREAM
@@ -386,108 +396,123 @@ struct WfArgs {
 #define WF_LD(p) (*(p))
 #define WF_ST(p, v) (*(p) = (v))
 #endif
-struct WorkFetch { unsigned int cur, end; };
-// Tried and switched off: pulling the state of the NEXT batch's paths towards L2 (prefetch.global.L2) while this batch
-// is processed. The records were written by the previous kernel and are gone from L2, and ncu shows
-// stall_long_scoreboard 8-12 per issue in the classify and deep trace kernels — but the prefetch needs the next
-// batch's slots from the queue first (a dependent load in front of the real work) and measured 5 % SLOWER on config 2
-// (28.9 -> 30.3 ms per frame at 32 spp), 1-2 % slower on configs 4 and 5. -DRT_WF_PREFETCH=1 brings it back.
-#ifndef RT_WF_PREFETCH
-#define RT_WF_PREFETCH 0
-#endif
-__device__ __forceinline__ void wf_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-__device__ __forceinline__ bool wf_next_batch(unsigned int *head, unsigned int count, unsigned int max_grab, WorkFetch &f, unsigned int &base) {
-    if (f.cur >= f.end) {   // warp-uniform
+// Per-warp bookkeeping of the persistent loops lives in SHARED memory (a few words per warp, read as broadcasts, written
+// by lane 0): work-fetch window, the current block of each output queue, the count of entries processed. In registers
+// these eight values stayed live across the whole loop body, and at the 64-register cap of these kernels each of them
+// pushed something else of the walk into a spill slot (ptxas: 24 -> 272 bytes of spill stores in k_wf_trace when the
+// queue positions were introduced).
+#define WQ_CUR 0    /* work fetch: next entry of the window, end of the window */
+#define WQ_END 1
+#define WQ_N 2      /* entries really processed (padding excluded) */
+#define WQ_OUT 3    /* output queue k: WQ_OUT + 2k = next free position, + 1 = end of the block */
+#define WQ_WORDS 12
+__device__ __forceinline__ unsigned int *wq_init(unsigned int (*all)[WQ_WORDS]) {
+    unsigned int *ws = all[threadIdx.x >> 5];
+    if ((threadIdx.x & 31u) < WQ_WORDS) ws[threadIdx.x & 31u] = 0u;
+    __syncwarp();
+    return ws;
+}
+__device__ __forceinline__ bool wf_next_batch(unsigned int *head, unsigned int count, unsigned int max_grab, unsigned int *ws, unsigned int &base) {
+    unsigned int cur = ws[WQ_CUR];
+    const unsigned int end = ws[WQ_END];
+    __syncwarp();
+    if (cur >= end) {   // warp-uniform
         const unsigned int lane = threadIdx.x & 31u;
-        const unsigned int left = count > f.end ? count - f.end : 0u;                 // f.end ~ global progress at the last fetch
+        const unsigned int left = count > end ? count - end : 0u;                     // end ~ global progress at the last fetch
         const unsigned int per_warp = left / (gridDim.x * (blockDim.x >> 5) * 64u);   // half of an even share, in batches
         const unsigned int grab = 32u * (per_warp < 1u ? 1u : (per_warp > max_grab ? max_grab : per_warp));
         unsigned int b = 0;
         if (lane == 0) b = atomicAdd(head, grab);
         b = __shfl_sync(0xFFFFFFFFu, b, 0);
         if (b >= count) return false;
-        f.cur = b;
-        f.end = b + grab < count ? b + grab : count;
+        cur = b;
+        if (lane == 0) ws[WQ_END] = b + grab < count ? b + grab : count;
     }
-    base = f.cur;
-    f.cur += 32u;
+    base = cur;
+    if ((threadIdx.x & 31u) == 0u) ws[WQ_CUR] = cur + 32u;
+    __syncwarp();
     return true;
 }
-__device__ __forceinline__ void wf_stage_push(unsigned int *queue, unsigned int *count, unsigned int *stage, unsigned int &fill, bool alive,
-                                              unsigned int slot) {
+// Appends the slots of the lanes with `alive` to output queue k of this warp and returns each such lane's position (all
+// lanes of the warp call it). *length is the queue's length in reserved positions.
+__device__ __forceinline__ unsigned int wf_push(unsigned int *queue, unsigned int *length, unsigned int block, unsigned int *ws, int k, bool alive, unsigned int slot) {
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int m = __ballot_sync(0xFFFFFFFFu, alive);
-    if (alive) stage[fill + __popc(m & ((1u << lane) - 1u))] = slot;
-    fill += __popc(m);
+    if (m == 0u) return 0u;
+    const unsigned int n = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
+    const unsigned int next = ws[WQ_OUT + 2 * k], room = ws[WQ_OUT + 2 * k + 1] - next;
     __syncwarp();
-    if (fill >= WF_STAGE_FLUSH) {
-        unsigned int b = 0;
-        if (lane == 0) b = atomicAdd(count, (unsigned int)WF_STAGE_FLUSH);
-        b = __shfl_sync(0xFFFFFFFFu, b, 0);
-        for (unsigned int k = lane; k < WF_STAGE_FLUSH; k += 32u) WF_ST(queue + b + k, stage[k]);
-        const unsigned int rem = fill - WF_STAGE_FLUSH;
-        unsigned int keep = 0;
-        if (lane < rem) keep = stage[WF_STAGE_FLUSH + lane];
-        __syncwarp();
-        if (lane < rem) stage[lane] = keep;
-        fill = rem;
-        __syncwarp();
+    unsigned int pos = next + rank;
+    if (n > room) {   // warp-uniform: the survivors beyond the room left go to a new block
+        unsigned int nb = 0u;
+        if (lane == 0) nb = atomicAdd(length, block);
+        nb = __shfl_sync(0xFFFFFFFFu, nb, 0);
+        if (rank >= room) pos = nb + (rank - room);
+        if (lane == 0) { ws[WQ_OUT + 2 * k] = nb + (n - room); ws[WQ_OUT + 2 * k + 1] = nb + block; }
+    } else if (lane == 0) {
+        ws[WQ_OUT + 2 * k] = next + n;
     }
+    __syncwarp();
+    if (alive) WF_ST(queue + pos, slot);
+    return pos;
 }
-__device__ __forceinline__ void wf_stage_flush(unsigned int *queue, unsigned int *count, unsigned int *stage, unsigned int &fill) {
-    if (fill == 0u) return;
-    const unsigned int lane = threadIdx.x & 31u;
-    unsigned int b = 0;
-    if (lane == 0) b = atomicAdd(count, fill);
-    b = __shfl_sync(0xFFFFFFFFu, b, 0);
-    for (unsigned int k = lane; k < fill; k += 32u) WF_ST(queue + b + k, stage[k]);
-    fill = 0u;
+// End of the kernel: pad the rest of the warp's last block of output queue k.
+__device__ __forceinline__ void wf_out_finish(unsigned int *queue, const unsigned int *ws, int k) {
+    const unsigned int end = ws[WQ_OUT + 2 * k + 1];
+    for (unsigned int p = ws[WQ_OUT + 2 * k] + (threadIdx.x & 31u); p < end; p += 32u) WF_ST(queue + p, WF_INVALID);
+}
+// Entries a kernel really processed (its input queue's padding excluded): per-warp count, one atomic at the end.
+__device__ __forceinline__ void wf_note_entries(unsigned int *ws, unsigned int ballot) {
+    if ((threadIdx.x & 31u) == 0u) ws[WQ_N] += __popc(ballot);
+}
+__device__ __forceinline__ void wf_count_entries(unsigned int *entries, const unsigned int *ws) {
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0u && ws[WQ_N]) atomicAdd(entries, ws[WQ_N]);
 }
 
 #ifndef RT_WF_MINB
 #define RT_WF_MINB 8
 #endif
-#ifndef RT_WF_GRIDCONST
-#define RT_WF_GRIDCONST 0
-#endif
-#if RT_WF_GRIDCONST
-#define RT_WF_PARAM __grid_constant__
-#else
-#define RT_WF_PARAM
-#endif
-// FUSE (needs LC; experiment, off by default): the walk-and-classify phase of the light stage runs right here, on the hit
-// that was just shaded — the cone walk is the SAME code as the closest-hit walk, the hit never travels through HBM unless
-// its light needs samples, and each bounce level is two kernels instead of three. It measured 30-40 % slower than the
-// three-kernel split (rt_render_device, profiles/r01_notes.md).
-template <bool STATS, bool LC, bool FUSE>
-__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM DScene scene_, const DCamera cam, const WfArgs w) {
+__device__ __forceinline__ void wf_state_init(PathState &st, const WfArgs &w) {
+    st.mode = 2; st.t_light = 0.f; st.light = 0;
+    st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
+    st.rng.key = 0; st.rng.ctr = 0;
+    st.cm0 = st.cm1 = st.cm2 = st.cm3 = 0u; st.cl_n = 0;
+    st.recs = nullptr; st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
+}
+__device__ __forceinline__ void wf_store_ray(const WfArgs &w, unsigned int pos, const PathState &st) {
+    WF_ST(w.nray0 + pos, make_float4(st.ray.o.x, st.ray.o.y, st.ray.o.z, st.ray.time));
+    WF_ST(w.nray1 + pos, make_float4(st.ray.d.x, st.ray.d.y, st.ray.d.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
+    WF_ST(w.nrng + pos, make_uint2(st.rng.key, st.rng.ctr));
+}
+
+// MESH = 0: one kernel per level, analytic primitives and meshes. MESH = 1 / 2: two kernels. Phase 1 intersects the analytic
+// primitives and asks ray_touches_meshes: rays that cannot hit a mesh (most, when the meshes are objects in a room) are shaded
+// at once; the others go to a queue with their analytic hit so far. Phase 2 walks the meshes for THOSE rays only, in full
+// warps, and shades them. In one kernel the few lanes of a warp that walk a mesh kept the rest waiting: the trace kernel
+// of the pool scene ran at 12.6 of 32 lanes (profiles/r02_notes.md).
+template <bool STATS, bool LC, bool NOLIGHT, int MESH>
+__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene_, const DCamera cam, const WfArgs w) {
     const DScene &scene = RT_S(scene_);
     stage_abvh(scene);
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int count = w.level == 0 ? w.n_paths : w.ctr[WF_NCTR * w.level + 1];
-    __shared__ unsigned int stage_all[4][WF_STAGE_CAP];
-    __shared__ unsigned int stage_park_all[FUSE ? 4 : 1][FUSE ? WF_STAGE_CAP : 1];
-    unsigned int *stage = stage_all[threadIdx.x >> 5];
-    unsigned int *stage_park = stage_park_all[FUSE ? (threadIdx.x >> 5) : 0];
-    unsigned int fill = 0u, fill_park = 0u;
-    WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
+    const unsigned int count = MESH == 2 ? w.ctr[WF_NCTR * w.level + 11] : (w.level == 0 ? w.n_paths : w.ctr[WF_NCTR * w.level + 1]);
+    __shared__ unsigned int wq_all[4][WQ_WORDS];
+    unsigned int *const ws = wq_init(wq_all);
     for (;;) {
         unsigned int base;
-        if (!wf_next_batch(w.ctr + WF_NCTR * w.level, count, w.max_grab, fetch, base)) break;
-        const unsigned int i = base + lane;
-        const bool valid = i < count;
-        if (RT_WF_PREFETCH && w.level > 0 && fetch.cur < fetch.end && fetch.cur + lane < count) {   // next batch of this warp's grab
-            const unsigned int ns = w.q_in[fetch.cur + lane];
-            wf_prefetch_l2(w.ray0 + ns); wf_prefetch_l2(w.ray1 + ns); wf_prefetch_l2(w.rng + ns);
+        if (!wf_next_batch(w.ctr + WF_NCTR * w.level + (MESH == 2 ? 10 : 0), count, w.max_grab, ws, base)) break;
+        unsigned int i = base + lane;
+        bool valid = i < count;
+        const unsigned int mi = i;   // MESH == 2: position in the mesh-walk queue
+        if (MESH == 2 && valid) {
+            i = WF_LD(w.q_mesh + mi);   // position of the ray in the live queue (level 0: the path slot)
+            valid = i != WF_INVALID;
         }
         PathState st;
-        st.mode = 2; st.t_light = 0.f; st.light = 0;
-        st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
-        st.rng.key = 0; st.rng.ctr = 0;
-        st.cm0 = st.cm1 = st.cm2 = st.cm3 = 0u; st.cl_n = 0;
-        st.recs = nullptr; st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
+        wf_state_init(st, w);
         unsigned int slot = 0;
         if (valid) {
             if (w.level == 0) {
@@ -496,115 +521,116 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const RT_WF_PARAM 
                 st.ray.o = ld3(cam.pos); st.ray.d = v3(r.x, r.y, r.z); st.ray.time = r.w;
                 st.rng.key = __ldg(w.cam_keys + slot); st.rng.ctr = 3u;
                 st.N = w.max_bounces; st.depth = 0;
-                if (STATS) cnt.rnd += 3;
+                if (STATS && MESH != 2) cnt.rnd += 3;
             } else {
-                slot = WF_LD(w.q_in + i);
-                const float4 a = WF_LD(w.ray0 + slot), b = WF_LD(w.ray1 + slot);
-                const uint2 g = WF_LD(w.rng + slot);
-                st.ray.o = v3(a.x, a.y, a.z); st.ray.time = a.w; st.ray.d = v3(b.x, b.y, b.z);
-                st.N = (int)(f2u(b.w) & 0xFFu); st.depth = (int)(f2u(b.w) >> 8);
-                st.rng.key = g.x; st.rng.ctr = g.y;
+                slot = WF_LD(w.q_live + i);
+                valid = slot != WF_INVALID;
+                if (valid) {
+                    const float4 a = WF_LD(w.ray0 + i), b = WF_LD(w.ray1 + i);
+                    const uint2 g = WF_LD(w.rng_ray + i);
+                    st.ray.o = v3(a.x, a.y, a.z); st.ray.time = a.w; st.ray.d = v3(b.x, b.y, b.z);
+                    st.N = (int)(f2u(b.w) & 0xFFu); st.depth = (int)(f2u(b.w) >> 8);
+                    st.rng.key = g.x; st.rng.ctr = g.y;
+                }
             }
-            st.path = slot; st.mode = 0;
+            if (valid) { st.path = slot; st.mode = 0; }
+        }
+        {
+            const unsigned int bv = __ballot_sync(0xFFFFFFFFu, valid);
+            if (bv == 0u) continue;   // a run of padding
+            if (MESH != 2) wf_note_entries(ws, bv);
         }
         Hit h;
         float hu = 0.f, hv = 0.f;
         bool blocked;
-        if (LC) intersect_lc<STATS>(scene, st, true, valid, h, hu, hv, blocked, &cnt);
-        else intersect_ray<STATS, true>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
-        bool lit = false;
+        if (MESH == 2) {
+            // the analytic hit so far, then the meshes (Scene.h:221-228), as intersect_lc would have gone on
+            h.type = 0; h.obj = -1; h.t = FLT_MAX; h.ref = 0;
+            bool done = !valid;
+            blocked = false;
+            if (valid) {
+                const float4 m = WF_LD(w.mesh_hit + mi);
+                h.t = m.x; h.type = (int)(f2u(m.y) >> 28); h.obj = h.type ? (int)(f2u(m.y) & 0x0FFFFFFFu) : -1; hu = m.z; hv = m.w;
+            }
+            meshes_walk_merged<STATS>(scene, st.ray, 0, st.rng, h, blocked, done, &cnt);
+        } else if (LC) {
+            intersect_lc<STATS>(scene, st, true, valid, h, hu, hv, blocked, &cnt, MESH == 0);
+        } else {
+            intersect_ray<STATS, true>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
+        }
+        if (MESH == 1) {
+            // Rays that touch a mesh: when enough lanes of this warp do, they walk right here (the warp is busy enough);
+            // when only a few do, those lanes leave for the walk kernel with what they have, where they are packed into
+            // full warps, instead of keeping the rest of this warp waiting. The others are final either way.
+            const bool touch = valid && ray_touches_meshes(scene, st.ray, h.t);
+            const unsigned int bt = __ballot_sync(0xFFFFFFFFu, touch);
+            if ((unsigned int)__popc(bt) >= w.mesh_inline_min) {
+                bool done = !touch;
+                meshes_walk_merged<STATS>(scene, st.ray, 0, st.rng, h, blocked, done, &cnt);
+            } else if (bt) {
+                const unsigned int mp = wf_push(w.q_mesh, w.ctr + WF_NCTR * w.level + 11, w.block, ws, 1, touch, i);
+                if (touch) {
+                    WF_ST(w.mesh_hit + mp, make_float4(h.t, u2f(((uint32_t)h.type << 28) | ((uint32_t)h.obj & 0x0FFFFFFFu)), hu, hv));
+                    valid = false;
+                }
+            }
+        }
+        // a path is lit iff its ray hit something (path_shade ends the path on a miss, Scene.h:270-272): the position of its hit
+        // record is reserved BEFORE the hit is shaded, and the record is written in the very branch that shaded it, so that the
+        // shaded values go from registers straight to the record (with the reservation or a merge point in between they made a
+        // round trip through the thread's local-memory frame)
+        unsigned int pos = 0u;
+        if (!NOLIGHT) pos = wf_push(w.q_hit, w.ctr + WF_NCTR * w.level + 3, w.block, ws, 0, valid && h.type != 0, slot);
+        bool alive = false;
         if (valid) {
             V3 c;
             if (path_shade<STATS, true>(scene, st, h, hu, hv, c, &cnt)) {
                 float *o = w.samples + 3ull * slot;
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
-            } else {
-                lit = true;
-            }
-        }
-        if (FUSE) {
-            const uint32_t kind = (uint32_t)h.type, obj = (uint32_t)h.obj;
-            bool fin = true, parked = false;
-            V3 c = v3(0.f);
-            if (lit) fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);   // mode 3, or the scatter
-            for (;;) {
-                const bool live = lit && !fin && !parked && st.mode == 3;
-                if (__ballot_sync(0xFFFFFFFFu, live) == 0u) break;
-                Hit h2;
-                float u2 = 0.f, v2 = 0.f;
-                bool b2;
-                intersect_lc<STATS>(scene, st, true, live, h2, u2, v2, b2, &cnt);
-                if (live) {
-                    if (!lc_light_unoccluded(st)) parked = true;
-                    else fin = path_advance<STATS, LC, true>(scene, st, h2, u2, v2, b2, w.nb_ech, c, &cnt);   // next light, or the scatter
-                }
-            }
-            bool alive = false;
-            if (lit) {
-                if (parked) {
-                    WF_ST(w.hit0 + slot, make_float4(st.P.x, st.P.y, st.P.z, st.ray.time));
-                    const uint32_t has_e = (st.e.x != 0.f || st.e.y != 0.f || st.e.z != 0.f) ? WF_HIT_E : 0u;
-                    const uint32_t has_d = st.mat->type != 0 ? WF_HIT_D : 0u;
-                    WF_ST(w.hit1 + slot, make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | has_e | has_d | obj)));
-                    WF_ST(w.hit2 + slot, make_float4(st.kd.x, st.kd.y, st.kd.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
-                    if (has_e) WF_ST(w.hit3 + slot, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
-                    if (has_d) WF_ST(w.hit4 + slot, make_float4(st.in_d.x, st.in_d.y, st.in_d.z, 0.f));
-                    WF_ST(w.park0 + slot, make_float4(st.color.x, st.color.y, st.color.z, u2f((uint32_t)st.light | ((uint32_t)(st.cl_n + 1) << 8))));
-                    for (int q4 = 0; q4 * 4 < st.cl_n; ++q4)
-                        WF_ST(w.park2 + (size_t)q4 * w.rec_stride + slot, make_float4(u2f(st.cl[4 * q4]), u2f(st.cl[4 * q4 + 1]), u2f(st.cl[4 * q4 + 2]), u2f(st.cl[4 * q4 + 3])));
-                    WF_ST(w.park1 + slot, make_float4(u2f(st.cm0), u2f(st.cm1), u2f(st.cm2), u2f(st.cm3)));
-                    WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
-                } else if (fin) {
+            } else if (NOLIGHT) {
+                // no lights: the light stage would only scatter (Scene.h:305-342 with an empty light list)
+                if (path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt)) {
                     float *o = w.samples + 3ull * slot;
                     o[0] = c.x; o[1] = c.y; o[2] = c.z;
                 } else {
                     alive = true;
-                    WF_ST(w.ray0 + slot, make_float4(st.ray.o.x, st.ray.o.y, st.ray.o.z, st.ray.time));
-                    WF_ST(w.ray1 + slot, make_float4(st.ray.d.x, st.ray.d.y, st.ray.d.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
-                    WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
                 }
-            }
-            wf_stage_push(w.q_live_next, w.ctr + WF_NCTR * (w.level + 1) + 1, stage, fill, alive, slot);
-            wf_stage_push(w.q_park, w.ctr + WF_NCTR * w.level + 5, stage_park, fill_park, parked, slot);
-            continue;
-        }
-        if (valid) {
-            if (lit) {
+            } else {
                 const uint32_t kind = (uint32_t)h.type, obj = (uint32_t)h.obj;   // st.mat = {sph,sq,mesh}_mat[obj]
-                WF_ST(w.hit0 + slot, make_float4(st.P.x, st.P.y, st.P.z, st.ray.time));
+                WF_ST(w.hit0 + pos, make_float4(st.P.x, st.P.y, st.P.z, st.ray.time));
                 // emission and incoming direction travel only when they matter (an emitter; a glass or mirror scatter):
                 // the hit record is the largest item of the wavefront's HBM traffic
                 const uint32_t has_e = (st.e.x != 0.f || st.e.y != 0.f || st.e.z != 0.f) ? WF_HIT_E : 0u;
                 const uint32_t has_d = st.mat->type != 0 ? WF_HIT_D : 0u;
-                WF_ST(w.hit1 + slot, make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | has_e | has_d | obj)));
-                WF_ST(w.hit2 + slot, make_float4(st.kd.x, st.kd.y, st.kd.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
-                if (has_e) WF_ST(w.hit3 + slot, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
-                if (has_d) WF_ST(w.hit4 + slot, make_float4(st.in_d.x, st.in_d.y, st.in_d.z, 0.f));
-                WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
+                WF_ST(w.hit1 + pos, make_float4(st.n.x, st.n.y, st.n.z, u2f((kind << 28) | has_e | has_d | obj)));
+                WF_ST(w.hit2 + pos, make_float4(st.kd.x, st.kd.y, st.kd.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
+                if (has_e) WF_ST(w.hit3 + pos, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
+                if (has_d) WF_ST(w.hit4 + pos, make_float4(st.in_d.x, st.in_d.y, st.in_d.z, 0.f));
+                WF_ST(w.rng_hit + pos, make_uint2(st.rng.key, st.rng.ctr));
             }
         }
-        wf_stage_push(w.q_out, w.ctr + WF_NCTR * w.level + 3, stage, fill, lit, slot);
+        if (NOLIGHT) {
+            pos = wf_push(w.q_next, w.ctr + WF_NCTR * (w.level + 1) + 1, w.block, ws, 0, alive, slot);
+            if (alive) wf_store_ray(w, pos, st);
+        }
     }
-    if (FUSE) {
-        wf_stage_flush(w.q_live_next, w.ctr + WF_NCTR * (w.level + 1) + 1, stage, fill);
-        wf_stage_flush(w.q_park, w.ctr + WF_NCTR * w.level + 5, stage_park, fill_park);
-    } else {
-        wf_stage_flush(w.q_out, w.ctr + WF_NCTR * w.level + 3, stage, fill);
-    }
+    wf_out_finish(NOLIGHT ? w.q_next : w.q_hit, ws, 0);
+    if (MESH == 1) wf_out_finish(w.q_mesh, ws, 1);
+    if (MESH != 2) wf_count_entries(w.ctr + WF_NCTR * w.level + 8, ws);   // closest-hit rays of this level
     if (STATS) flush_counters(cnt, w.stats);
 }
 
 // PHASE 0: everything in one kernel (scenes without the analytic hierarchy: no candidate masks to classify by).
 // PHASE 1: per light, ONE cone walk; a light whose cone holds no possible occluder is finished on the spot (all its
 //          samples are unoccluded: lc_light_unoccluded) and the path goes on to the next light / the scatter. A path
-//          that reaches a light with candidates is PARKED: colour so far, light index and masks go to HBM and the slot
-//          to the shadow queue. Most hits of config 2 never leave this phase.
+//          that reaches a light with candidates is PARKED: colour so far, light index and masks go to HBM and its
+//          hit-queue position to the shadow queue. Most hits of config 2 never leave this phase.
 // PHASE 2: the parked paths, now packed into full warps: the NB_ECH samples of the parked light, any further light
 //          (walk + samples inline), scatter.
 // Split because a warp is as slow as its slowest lane: with both phases in one loop, one lane that has to sample keeps
 // 31 finished lanes waiting for ten rounds.
 template <bool STATS, bool LC, int PHASE>
-__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM DScene scene_, const WfArgs w) {
+__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene_, const WfArgs w) {
     const DScene &scene = RT_S(scene_);
     stage_abvh(scene);
     Counters cnt;
@@ -612,41 +638,39 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int count = w.ctr[WF_NCTR * w.level + (PHASE == 2 ? 5 + 2 * w.which_park : 3)];
     unsigned int *const head = w.ctr + WF_NCTR * w.level + (PHASE == 2 ? 4 + 2 * w.which_park : 2);
-    const unsigned int *const q_in = PHASE == 2 ? (w.which_park ? w.q_over : w.q_park) : w.q_in;
-    __shared__ unsigned int stage_all[4][WF_STAGE_CAP];
-    __shared__ unsigned int stage_park_all[PHASE == 1 ? 4 : 1][PHASE == 1 ? WF_STAGE_CAP : 1];
-    __shared__ unsigned int stage_over_all[PHASE == 1 ? 4 : 1][PHASE == 1 ? WF_STAGE_CAP : 1];
-    unsigned int *stage = stage_all[threadIdx.x >> 5];
-    unsigned int *stage_park = stage_park_all[PHASE == 1 ? (threadIdx.x >> 5) : 0];
-    unsigned int *stage_over = stage_over_all[PHASE == 1 ? (threadIdx.x >> 5) : 0];
-    unsigned int fill = 0u, fill_park = 0u, fill_over = 0u;
-    WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
+    const unsigned int *const q_in = PHASE == 2 ? (w.which_park ? w.q_over : w.q_park) : w.q_hit;
+    __shared__ unsigned int wq_all[4][WQ_WORDS];
+    unsigned int *const ws = wq_init(wq_all);
     for (;;) {
         unsigned int base;
-        if (!wf_next_batch(head, count, w.max_grab, fetch, base)) break;
+        if (!wf_next_batch(head, count, w.max_grab, ws, base)) break;
         const unsigned int i = base + lane;
-        const bool valid = i < count;
-        if (RT_WF_PREFETCH && fetch.cur < fetch.end && fetch.cur + lane < count) {   // next batch of this warp's grab
-            const unsigned int ns = q_in[fetch.cur + lane];
-            wf_prefetch_l2(w.hit0 + ns); wf_prefetch_l2(w.hit1 + ns); wf_prefetch_l2(w.hit2 + ns); wf_prefetch_l2(w.hit3 + ns);
-            wf_prefetch_l2(w.hit4 + ns); wf_prefetch_l2(w.rng + ns);
-            if (PHASE == 2) { wf_prefetch_l2(w.park0 + ns); wf_prefetch_l2(w.park1 + ns); }
-        }
+        bool valid = i < count;
         PathState st;
-        st.mode = 2; st.t_light = 0.f; st.light = 0;
-        st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
-        st.rng.key = 0; st.rng.ctr = 0;
-        st.cm0 = st.cm1 = st.cm2 = st.cm3 = 0u; st.cl_n = 0;
-        st.recs = nullptr; st.wf_rec = w.rec; st.wf_stride = w.rec_stride; st.max_bounces = w.max_bounces;
-        unsigned int slot = 0;
+        wf_state_init(st, w);
+        unsigned int slot = 0, hp = i;   // hp: position of the hit in the hit queue (where its records are)
         bool fin = true, parked = false;
         V3 c = v3(0.f);
         if (valid) {
-            slot = WF_LD(q_in + i);
-            const float4 h0 = WF_LD(w.hit0 + slot), h1 = WF_LD(w.hit1 + slot), h2 = WF_LD(w.hit2 + slot);
+            if (PHASE == 2) {
+                hp = WF_LD(q_in + i);
+                valid = hp != WF_INVALID;
+                if (valid) slot = WF_LD(w.q_hit + hp);
+            } else {
+                slot = WF_LD(q_in + i);
+                valid = slot != WF_INVALID;
+            }
+        }
+        {
+            const unsigned int bv = __ballot_sync(0xFFFFFFFFu, valid);
+            if (bv == 0u) continue;   // a run of padding
+            wf_note_entries(ws, bv);
+        }
+        if (valid) {
+            const float4 h0 = WF_LD(w.hit0 + hp), h1 = WF_LD(w.hit1 + hp), h2 = WF_LD(w.hit2 + hp);
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 h3 = (f2u(h1.w) & WF_HIT_E) ? WF_LD(w.hit3 + slot) : zero4, h4 = (f2u(h1.w) & WF_HIT_D) ? WF_LD(w.hit4 + slot) : zero4;
-            const uint2 g = WF_LD(w.rng + slot);
+            const float4 h3 = (f2u(h1.w) & WF_HIT_E) ? WF_LD(w.hit3 + hp) : zero4, h4 = (f2u(h1.w) & WF_HIT_D) ? WF_LD(w.hit4 + hp) : zero4;
+            const uint2 g = WF_LD(w.rng_hit + hp);
             st.P = v3(h0.x, h0.y, h0.z); st.ray.time = h0.w;
             st.n = v3(h1.x, h1.y, h1.z);
             const uint32_t code = f2u(h1.w), kind = code >> 28, obj = code & 0x03FFFFFFu;
@@ -658,25 +682,17 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
             st.rng.key = g.x; st.rng.ctr = g.y;
             st.path = slot;
             if (PHASE == 2) {
-                const float4 p0 = WF_LD(w.park0 + slot), p1 = WF_LD(w.park1 + slot);
+                const float4 p0 = WF_LD(w.park0 + hp), p1 = WF_LD(w.park1 + hp);
                 st.color = v3(p0.x, p0.y, p0.z);
                 st.light = (int)(f2u(p0.w) & 0xFFu); st.cl_n = (int)((f2u(p0.w) >> 8) & 0xFFu) - 1;
                 for (int q4 = 0; q4 * 4 < st.cl_n; ++q4) {
-                    const float4 v = WF_LD(w.park2 + (size_t)q4 * w.rec_stride + slot);
+                    const float4 v = WF_LD(w.park2 + (size_t)q4 * w.park_stride + hp);
                     st.cl[4 * q4] = f2u(v.x); st.cl[4 * q4 + 1] = f2u(v.y); st.cl[4 * q4 + 2] = f2u(v.z); st.cl[4 * q4 + 3] = f2u(v.w);
                 }
                 st.cm0 = f2u(p1.x); st.cm1 = f2u(p1.y); st.cm2 = f2u(p1.z); st.cm3 = f2u(p1.w);
                 st.j = 0; st.blocked = 0; st.mode = 3;
-                if (w.sp_enabled) {   // samples 0 .. j-1 of the parked light were traced speculatively and validated (k_wf_validate)
-                    const unsigned int hdr = w.sp_hdr[slot];
-                    st.j = (int)(hdr & 0xFFu); st.blocked = (int)((hdr >> 8) & 0xFFu);
-                }
-                if (st.j >= w.nb_ech) {
-                    fin = path_finish_light<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
-                } else {
-                    path_shadow_sample<STATS>(scene, st, &cnt);   // candidates known: the next sample
-                    fin = false;
-                }
+                Hit h; h.type = 0; h.obj = -1; h.t = 0.f; h.ref = 0;
+                fin = path_advance<STATS, LC, true>(scene, st, h, 0.f, 0.f, false, w.nb_ech, c, &cnt);   // candidates known: first sample
             } else {
                 st.color = v3(0.f); st.light = 0; st.mode = 0;
                 fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
@@ -698,170 +714,100 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const RT_WF_PARAM 
                 else fin = path_advance<STATS, LC, true>(scene, st, h, hu, hv, blocked, w.nb_ech, c, &cnt);
             }
         }
-        bool alive = false;
+        // reserve the queue positions first (who is alive / parked is known by now), then write each path's records in the
+        // branch that holds them in registers
+        const bool alive = valid && !parked && !fin;
+        const unsigned int pos = wf_push(w.q_next, w.ctr + WF_NCTR * (w.level + 1) + 1, w.block, ws, 0, alive, st.path);   // st.path = the slot
+        if (PHASE == 1) {
+            wf_push(w.q_park, w.ctr + WF_NCTR * w.level + 5, w.block, ws, 1, parked && st.cl_n >= 0, hp);
+            wf_push(w.q_over, w.ctr + WF_NCTR * w.level + 7, w.block, ws, 2, parked && st.cl_n < 0, hp);
+        }
         if (valid) {
             if (parked) {
-                WF_ST(w.park0 + slot, make_float4(st.color.x, st.color.y, st.color.z, u2f((uint32_t)st.light | ((uint32_t)(st.cl_n + 1) << 8))));
+                WF_ST(w.park0 + hp, make_float4(st.color.x, st.color.y, st.color.z, u2f((uint32_t)st.light | ((uint32_t)(st.cl_n + 1) << 8))));
                 for (int q4 = 0; q4 * 4 < st.cl_n; ++q4)
-                    WF_ST(w.park2 + (size_t)q4 * w.rec_stride + slot, make_float4(u2f(st.cl[4 * q4]), u2f(st.cl[4 * q4 + 1]), u2f(st.cl[4 * q4 + 2]), u2f(st.cl[4 * q4 + 3])));
-                WF_ST(w.park1 + slot, make_float4(u2f(st.cm0), u2f(st.cm1), u2f(st.cm2), u2f(st.cm3)));
-                WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
-                if (w.sp_enabled) w.sp_hdr[slot] = 3u << 16;   // no sample validated yet; guess: unoccluded samples, 3 draws each
+                    WF_ST(w.park2 + (size_t)q4 * w.park_stride + hp, make_float4(u2f(st.cl[4 * q4]), u2f(st.cl[4 * q4 + 1]), u2f(st.cl[4 * q4 + 2]), u2f(st.cl[4 * q4 + 3])));
+                WF_ST(w.park1 + hp, make_float4(u2f(st.cm0), u2f(st.cm1), u2f(st.cm2), u2f(st.cm3)));
+                WF_ST(w.rng_hit + hp, make_uint2(st.rng.key, st.rng.ctr));
             } else if (fin) {
+                float *o = w.samples + 3ull * st.path;
+                o[0] = c.x; o[1] = c.y; o[2] = c.z;
+            } else {
+                wf_store_ray(w, pos, st);
+            }
+        }
+    }
+    wf_out_finish(w.q_next, ws, 0);
+    if (PHASE == 1) {
+        wf_out_finish(w.q_park, ws, 1);
+        wf_out_finish(w.q_over, ws, 2);
+    }
+    if (PHASE != 2) wf_count_entries(w.ctr + WF_NCTR * w.level + 9, ws);   // hits of this level
+    if (STATS) flush_counters(cnt, w.stats);
+}
+
+// The light stage of a scene WITHOUT lights (Scene.h:305-342 with an empty light list): colour stays 0, the path scatters
+// (Material::scatter), records (0, kd, e) and either ends (last bounce: fold) or queues its next ray. Same arithmetic as
+// k_wf_light's phase 1 on such a scene, without the machinery that phase carries for the cone walks (path state in the
+// thread's frame, traversal stack, park queues): the pool scene's light kernel ran at 30 % issue utilisation behind 3 TB/s of
+// DRAM traffic, 490 B of L2 writes per hit of which 92 B were records — the rest was the frame (profiles/r02_notes.md).
+template <bool STATS>
+__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_scatter(const DScene scene_, const WfArgs w) {
+    const DScene &scene = RT_S(scene_);
+    Counters cnt;
+    if (STATS) memset(&cnt, 0, sizeof cnt);
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int count = w.ctr[WF_NCTR * w.level + 3];
+    __shared__ unsigned int wq_all[4][WQ_WORDS];
+    unsigned int *const ws = wq_init(wq_all);
+    for (;;) {
+        unsigned int base;
+        if (!wf_next_batch(w.ctr + WF_NCTR * w.level + 2, count, w.max_grab, ws, base)) break;
+        const unsigned int i = base + lane;
+        unsigned int slot = WF_INVALID;
+        if (i < count) slot = WF_LD(w.q_hit + i);
+        const bool valid = slot != WF_INVALID;
+        {
+            const unsigned int bv = __ballot_sync(0xFFFFFFFFu, valid);
+            if (bv == 0u) continue;   // a run of padding
+            wf_note_entries(ws, bv);
+        }
+        bool alive = false;
+        Ray next; next.o = v3(0.f); next.d = v3(0.f, 0.f, 1.f); next.time = 0.f;
+        Rng rng; rng.key = 0u; rng.ctr = 0u;
+        int N = 0, depth = 0;
+        if (valid) {
+            const float4 h0 = WF_LD(w.hit0 + i), h1 = WF_LD(w.hit1 + i), h2 = WF_LD(w.hit2 + i);
+            const uint32_t code = f2u(h1.w), kind = code >> 28, obj = code & 0x03FFFFFFu;
+            const DMaterial *mat = kind == 3u ? scene.mesh_mat + obj : (kind == 2u ? scene.sq_mat + obj : scene.sph_mat + obj);
+            V3 e = v3(0.f);
+            if (code & WF_HIT_E) { const float4 h3 = WF_LD(w.hit3 + i); e = v3(h3.x, h3.y, h3.z); }
+            Ray in; in.o = v3(h0.x, h0.y, h0.z); in.d = v3(0.f); in.time = h0.w;
+            if (code & WF_HIT_D) { const float4 h4 = WF_LD(w.hit4 + i); in.d = v3(h4.x, h4.y, h4.z); }
+            const uint2 g = WF_LD(w.rng_hit + i);
+            rng.key = g.x; rng.ctr = g.y;
+            N = (int)(f2u(h2.w) & 0xFFu); depth = (int)(f2u(h2.w) >> 8);
+            next = material_scatter<STATS>(*mat, in, v3(h1.x, h1.y, h1.z), in.o, rng, &cnt);
+            wf_rec_store(w.rec, w.rec_stride, slot, depth, v3(0.f), v3(h2.x, h2.y, h2.z), e);
+            ++depth; --N;
+            if (N == 0) {
+                const V3 c = wf_fold(w.rec, w.rec_stride, slot, depth, w.max_bounces, v3(0.f));
                 float *o = w.samples + 3ull * slot;
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
             } else {
                 alive = true;
-                WF_ST(w.ray0 + slot, make_float4(st.ray.o.x, st.ray.o.y, st.ray.o.z, st.ray.time));
-                WF_ST(w.ray1 + slot, make_float4(st.ray.d.x, st.ray.d.y, st.ray.d.z, u2f((uint32_t)st.N | ((uint32_t)st.depth << 8))));
-                WF_ST(w.rng + slot, make_uint2(st.rng.key, st.rng.ctr));
             }
         }
-        wf_stage_push(w.q_out, w.ctr + WF_NCTR * (w.level + 1) + 1, stage, fill, alive, slot);
-        if (PHASE == 1) {
-            wf_stage_push(w.q_park, w.ctr + WF_NCTR * w.level + 5, stage_park, fill_park, parked && st.cl_n >= 0, slot);
-            wf_stage_push(w.q_over, w.ctr + WF_NCTR * w.level + 7, stage_over, fill_over, parked && st.cl_n < 0, slot);
+        const unsigned int pos = wf_push(w.q_next, w.ctr + WF_NCTR * (w.level + 1) + 1, w.block, ws, 0, alive, slot);
+        if (alive) {
+            WF_ST(w.nray0 + pos, make_float4(next.o.x, next.o.y, next.o.z, next.time));
+            WF_ST(w.nray1 + pos, make_float4(next.d.x, next.d.y, next.d.z, u2f((uint32_t)N | ((uint32_t)depth << 8))));
+            WF_ST(w.nrng + pos, make_uint2(rng.key, rng.ctr));
         }
     }
-    wf_stage_flush(w.q_out, w.ctr + WF_NCTR * (w.level + 1) + 1, stage, fill);
-    if (PHASE == 1) {
-        wf_stage_flush(w.q_park, w.ctr + WF_NCTR * w.level + 5, stage_park, fill_park);
-        wf_stage_flush(w.q_over, w.ctr + WF_NCTR * w.level + 7, stage_over, fill_over);
-    }
+    wf_out_finish(w.q_next, ws, 0);
+    wf_count_entries(w.ctr + WF_NCTR * w.level + 9, ws);   // hits of this level
     if (STATS) flush_counters(cnt, w.stats);
-}
-
-// ---- speculative shadow samples ---------------------------------------------------------------------------------------
-// The NB_ECH soft-shadow samples of one (hit, light) are SEQUENTIAL in the reference: sample j+1 draws its direction
-// from the stream position sample j left behind, and a sample consumes 3 draws plus one per candidate occluder it hits
-// until one blocks (Scene.h:325-330, 235-255). One lane per hit therefore walks the mesh hierarchies ten times in a row
-// next to 31 lanes doing the same for unrelated hits: the pond scene's walks ran at 9 of 32 lanes. But a sample is a
-// pure function of (hit, light, stream position), and the position is predictable: an unoccluded sample consumes exactly
-// 3 draws, a sample blocked by the first opaque thing it meets exactly 4. So the samples are traced IN PARALLEL, one
-// lane per (hit, sample j), from the GUESSED position base + (j - j0) * guess (guess = 3 at first), adjacent lanes
-// holding the samples of one hit — ten nearly identical rays from one point, which walk the hierarchy in lockstep —
-// and k_wf_validate then checks the guesses in order: sample j is valid iff the draws consumed by the validated samples
-// before it add up to its guessed offset. The validated prefix advances the stream, the blocked count and the guess
-// (the draws the last valid sample consumed); hits with samples left go round again. Every round validates at least one
-// sample per hit, so the fixed number of rounds the host launches never loses anything: whatever is left is finished by
-// the sequential sample kernel (k_wf_light<.., 2>), which resumes at sample j0. Results are bit-identical by
-// construction — only samples traced from the reference's own stream position are ever used.
-template <bool STATS>
-__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_shadow(const RT_WF_PARAM DScene scene_, const WfArgs w) {
-    const DScene &scene = RT_S(scene_);
-    stage_abvh(scene);
-    Counters cnt;
-    if (STATS) memset(&cnt, 0, sizeof cnt);
-    const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int n_hits = *w.sp_cnt_in;
-    const unsigned int nb = (unsigned int)w.nb_ech;
-    const unsigned long long total = (unsigned long long)n_hits * nb;
-    const unsigned int count = total > 0xFFFFFFE0ull ? 0xFFFFFFE0u : (unsigned int)total;   // 32 Mi paths x 10 samples fit; beyond: the rest stays sequential
-    WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
-    for (;;) {
-        unsigned int base;
-        if (!wf_next_batch(w.sp_head, count, w.max_grab > 1u ? 8u : 4u, fetch, base)) break;   // samples are small, even work items: fewer fetch atomics
-        const unsigned int i = base + lane;
-        PathState st;
-        st.recs = nullptr; st.wf_rec = nullptr; st.wf_stride = 0; st.max_bounces = w.max_bounces;
-        st.mode = 2; st.t_light = 0.f; st.light = 0;
-        st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
-        st.rng.key = 0; st.rng.ctr = 0;
-        st.cm0 = st.cm1 = st.cm2 = st.cm3 = 0u; st.cl_n = 0;
-        bool active = i < count;
-        unsigned int slot = 0, j = 0, start = 0;
-        if (active) {
-            const unsigned int e = i / nb;
-            j = i - e * nb;
-            slot = WF_LD(w.sp_q_in + e);
-            const unsigned int hdr = w.sp_hdr[slot];
-            const unsigned int j0 = hdr & 0xFFu, guess = hdr >> 16;
-            active = j >= j0;   // earlier samples are validated already
-            if (active) {
-                const float4 h0 = __ldg(w.hit0 + slot);
-                const uint2 g = __ldg(w.rng + slot);
-                const float4 p0 = __ldg(w.park0 + slot), p1 = __ldg(w.park1 + slot);
-                st.P = v3(h0.x, h0.y, h0.z); st.ray.time = h0.w;
-                st.light = (int)(f2u(p0.w) & 0xFFu); st.cl_n = (int)((f2u(p0.w) >> 8) & 0xFFu) - 1;
-                for (int q4 = 0; q4 * 4 < st.cl_n; ++q4) {
-                    const float4 v = __ldg(w.park2 + (size_t)q4 * w.rec_stride + slot);
-                    st.cl[4 * q4] = f2u(v.x); st.cl[4 * q4 + 1] = f2u(v.y); st.cl[4 * q4 + 2] = f2u(v.z); st.cl[4 * q4 + 3] = f2u(v.w);
-                }
-                st.cm0 = f2u(p1.x); st.cm1 = f2u(p1.y); st.cm2 = f2u(p1.z); st.cm3 = f2u(p1.w);
-                start = g.y + (j - j0) * guess;
-                st.rng.key = g.x; st.rng.ctr = start;
-                st.path = slot; st.N = 0; st.depth = 0; st.j = (int)j; st.blocked = 0;
-                path_shadow_sample<STATS>(scene, st, &cnt);
-            }
-        }
-        Hit h;
-        float hu = 0.f, hv = 0.f;
-        bool blocked;
-        intersect_lc<STATS>(scene, st, false, active, h, hu, hv, blocked, &cnt);
-        if (active) {
-            const unsigned int consumed = st.rng.ctr - start;
-            w.sp_res[(size_t)slot * nb + j] = (unsigned short)((consumed > 0x7FFFu ? 0x7FFFu : consumed) | (blocked ? 0x8000u : 0u));
-        }
-    }
-    if (STATS) {   // tests really performed (speculation included); rays and draws are counted once, by k_wf_validate
-        cnt.shadow = 0; cnt.rnd = 0;
-        flush_counters(cnt, w.stats);
-    }
-}
-
-// One lane per parked hit: validate the guesses of the last k_wf_shadow round in sample order (see above), advance the
-// hit's stream position / blocked count / guess, and queue it for another round if samples are left.
-template <bool STATS>
-__global__ void __launch_bounds__(128) k_wf_validate(const WfArgs w) {
-    const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int count = *w.sp_cnt_in;
-    const unsigned int nb = (unsigned int)w.nb_ech;
-    const bool traced_all = (unsigned long long)count * nb <= 0xFFFFFFE0ull;
-    __shared__ unsigned int stage_all[4][WF_STAGE_CAP];
-    unsigned int *stage = stage_all[threadIdx.x >> 5];
-    unsigned int fill = 0u;
-    unsigned long long n_shadow = 0, n_rnd = 0, n_val = 0, n_pend = 0;
-    WorkFetch fetch; fetch.cur = 0u; fetch.end = 0u;
-    for (;;) {
-        unsigned int base;
-        if (!wf_next_batch(w.sp_vhead, count, 8u, fetch, base)) break;
-        const unsigned int i = base + lane;
-        bool again = false;
-        unsigned int slot = 0;
-        if (i < count) {
-            slot = WF_LD(w.sp_q_in + i);
-            const unsigned int hdr = w.sp_hdr[slot];
-            const unsigned int j0 = hdr & 0xFFu, guess = hdr >> 16;
-            unsigned int blocked = (hdr >> 8) & 0xFFu, last = guess, off = 0, j = j0;
-            if (traced_all || (unsigned long long)(i + 1) * nb <= 0xFFFFFFE0ull) {
-                for (; j < nb; ++j) {
-                    if ((j - j0) * guess != off) break;
-                    const unsigned int r = w.sp_res[(size_t)slot * nb + j];
-                    const unsigned int consumed = r & 0x7FFFu;
-                    if (consumed == 0x7FFFu) break;   // more draws than the record holds: leave the sample to the sequential kernel
-                    blocked += r >> 15; off += consumed; last = consumed;
-                }
-            }
-            if (j > j0) {
-                uint2 g = w.rng[slot];
-                g.y += off;
-                w.rng[slot] = g;
-                if (STATS) { n_shadow += j - j0; n_rnd += off; }
-            }
-            if (STATS) { n_val += j - j0; n_pend += nb - j0; }
-            w.sp_hdr[slot] = j | (blocked << 8) | ((last > 0xFFFFu ? 3u : last) << 16);
-            again = j < nb && j > j0;   // nothing validated = nothing to gain from another round
-        }
-        wf_stage_push(w.sp_q_out, w.sp_cnt_out, stage, fill, again, slot);
-    }
-    wf_stage_flush(w.sp_q_out, w.sp_cnt_out, stage, fill);
-    if (STATS) {
-        for (int o = 16; o > 0; o >>= 1) { n_shadow += __shfl_down_sync(0xFFFFFFFFu, n_shadow, o); n_rnd += __shfl_down_sync(0xFFFFFFFFu, n_rnd, o); }
-        if (lane == 0) { if (n_shadow) atomicAdd(w.stats + 1, n_shadow); if (n_rnd) atomicAdd(w.stats + 9, n_rnd); }
-        // tuning aid (rt_debug_counters): samples validated / samples that were pending, over all rounds
-        for (int o = 16; o > 0; o >>= 1) { n_val += __shfl_down_sync(0xFFFFFFFFu, n_val, o); n_pend += __shfl_down_sync(0xFFFFFFFFu, n_pend, o); }
-        if (lane == 0) { if (n_val) atomicAdd(w.stats + 12, n_val); if (n_pend) atomicAdd(w.stats + 13, n_pend); }
-    }
 }
 
 // image[pixel] = (sum of its samples, in sample order) / nsamples ; then gamma
@@ -895,16 +841,17 @@ __global__ void k_resolve(const RenderArgs a, const unsigned int *xy, unsigned i
     if (gamma_out) { gamma_out[o] = gamma_channel(acc.x); gamma_out[o + 1] = gamma_channel(acc.y); gamma_out[o + 2] = gamma_channel(acc.z); }
 }
 
-// Ray counts of a wavefront chunk from its queue counters, for free: level L traced ctr[L][1] closest-hit rays (level 0:
-// every path) and lit ctr[L][3] hits; every hit fires nb_ech shadow rays at each light (Scene.h:305-334), traced or
-// proven unoccluded. tally[0] += closest rays, tally[1] += hits.
+// Ray counts of a wavefront chunk from its queue counters, for free: level L traced ctr[L][8] closest-hit rays (level 0:
+// every path) and lit ctr[L][9] hits; every hit fires nb_ech shadow rays at each light (Scene.h:305-334), traced or
+// proven unoccluded. tally[0] += closest rays, tally[1] += hits. (Without lights the hits are not queued, and not needed.)
 __global__ void k_wf_tally(const unsigned int *ctr, unsigned int n_paths, int levels, unsigned long long *tally) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    unsigned long long closest = n_paths, hits = 0;
+    unsigned long long closest = 0, hits = 0;
     for (int l = 0; l < levels; ++l) {
-        if (l > 0) closest += ctr[WF_NCTR * l + 1];
-        hits += ctr[WF_NCTR * l + 3];
+        closest += ctr[WF_NCTR * l + 8];
+        hits += ctr[WF_NCTR * l + 9];
     }
+    (void)n_paths;
     tally[0] += closest;
     tally[1] += hits;
 }
@@ -1028,12 +975,9 @@ struct Scratch {
     float *samples = nullptr; size_t samples_cap = 0;
     float4 *cam_rays = nullptr; unsigned int *cam_keys = nullptr; size_t cam_cap = 0;   // per path of a chunk (k_camera_rays)
     unsigned int *pix_xy = nullptr; size_t pix_cap = 0;                                 // per pixel of a chunk (k_pixel_xy)
-    // wavefront state (variant 6), per path of a chunk: 7 float4 fields + rng + 2 queues, and 3 float4 per bounce
+    // wavefront state (variant 6): 13 float4 planes + 2 rng planes + 4 queues per queue position, and 3 float4 per bounce and path slot
     float4 *wf_f4 = nullptr; uint2 *wf_rng = nullptr; unsigned int *wf_q = nullptr; float4 *wf_rec = nullptr; unsigned int *wf_ctr = nullptr;
-    size_t wf_cap = 0; int wf_bounces = 0;
-    // speculative shadow samples: header per path, result per (path, sample), 4 retry queues, counters per (level, queue, round)
-    unsigned int *sp_hdr = nullptr; unsigned short *sp_res = nullptr; unsigned int *sp_q = nullptr; unsigned int *sp_ctr = nullptr;
-    size_t sp_cap = 0; int sp_nb = 0;
+    size_t wf_cap = 0, wf_pos_cap = 0; int wf_bounces = 0;   // wf_cap: path slots; wf_pos_cap: queue positions (slots + padding of the block reservation)
     unsigned long long *counters = nullptr;   // [0] work counter, [1..10] stats
     TileRec *d_tiles = nullptr; unsigned int *d_tile_off = nullptr; size_t tiles_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1075,10 +1019,6 @@ struct Scratch {
         if (wf_q) cudaFree(wf_q);
         if (wf_rec) cudaFree(wf_rec);
         if (wf_ctr) cudaFree(wf_ctr);
-        if (sp_hdr) cudaFree(sp_hdr);
-        if (sp_res) cudaFree(sp_res);
-        if (sp_q) cudaFree(sp_q);
-        if (sp_ctr) cudaFree(sp_ctr);
         if (counters) cudaFree(counters);
         if (d_tiles) cudaFree(d_tiles);
         if (d_tile_off) cudaFree(d_tile_off);
@@ -1387,6 +1327,12 @@ int persistent_grid(RtScene *s, const void *kernel, int threads) {
     return s->sm_count * per_sm;
 }
 
+#define WF_F4_PLANES (10 + RT_LC_MAXC / 4)   /* ray0 ray1 hit0..hit4 park0 park1 + the candidate-triangle planes + mesh_hit */
+#define WF_Q_PLANES 5   /* live, hit, parked, overflow, mesh-walk */
+#define WF_MAX_BLOCK 256u
+// Queue positions beyond the path count: every warp of a producing kernel may leave the rest of one block of each queue it
+// appends to unused (wf_push), and a queue has at most three producing kernels per level (classify + the two sample passes).
+size_t wf_padding(const RtScene *s) { return (size_t)3 * (size_t)s->sm_count * RT_WF_MINB * 4 * WF_MAX_BLOCK; }
 int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
     if (paths <= s->wf_cap && max_bounces <= s->wf_bounces) return RT_OK;
     paths = std::max(paths, s->wf_cap); max_bounces = std::max(max_bounces, s->wf_bounces);   // grow-only in both dimensions
@@ -1394,30 +1340,14 @@ int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
     if (s->wf_rng) cudaFree(s->wf_rng);
     if (s->wf_q) cudaFree(s->wf_q);
     if (s->wf_rec) cudaFree(s->wf_rec);
-    s->wf_f4 = nullptr; s->wf_rng = nullptr; s->wf_q = nullptr; s->wf_rec = nullptr; s->wf_cap = 0; s->wf_bounces = 0;
-    RT_CUDA(cudaMalloc((void **)&s->wf_f4, (9 + RT_LC_MAXC / 4) * paths * sizeof(float4)));
-    RT_CUDA(cudaMalloc((void **)&s->wf_rng, paths * sizeof(uint2)));
-    RT_CUDA(cudaMalloc((void **)&s->wf_q, 4 * paths * sizeof(unsigned int)));
+    s->wf_f4 = nullptr; s->wf_rng = nullptr; s->wf_q = nullptr; s->wf_rec = nullptr; s->wf_cap = 0; s->wf_pos_cap = 0; s->wf_bounces = 0;
+    const size_t pos = paths + wf_padding(s);
+    RT_CUDA(cudaMalloc((void **)&s->wf_f4, WF_F4_PLANES * pos * sizeof(float4)));
+    RT_CUDA(cudaMalloc((void **)&s->wf_rng, 2 * pos * sizeof(uint2)));
+    RT_CUDA(cudaMalloc((void **)&s->wf_q, WF_Q_PLANES * pos * sizeof(unsigned int)));
     RT_CUDA(cudaMalloc((void **)&s->wf_rec, 3 * (size_t)std::max(1, max_bounces) * paths * sizeof(float4)));
     if (!s->wf_ctr) RT_CUDA(cudaMalloc((void **)&s->wf_ctr, WF_NCTR * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int)));
-    s->wf_cap = paths; s->wf_bounces = max_bounces;
-    return RT_OK;
-}
-
-#define SP_MAX_ROUNDS 14
-#define SP_NCTR 4   /* per (level, queue, round): [0] shadow head, [1] validate head, [2] hits in this round's queue, [3] - */
-int ensure_spec(RtScene *s, size_t paths, int nb_ech) {
-    if (paths <= s->sp_cap && nb_ech <= s->sp_nb) return RT_OK;
-    paths = std::max(paths, s->sp_cap); nb_ech = std::max(nb_ech, s->sp_nb);
-    if (s->sp_hdr) cudaFree(s->sp_hdr);
-    if (s->sp_res) cudaFree(s->sp_res);
-    if (s->sp_q) cudaFree(s->sp_q);
-    s->sp_hdr = nullptr; s->sp_res = nullptr; s->sp_q = nullptr; s->sp_cap = 0; s->sp_nb = 0;
-    RT_CUDA(cudaMalloc((void **)&s->sp_hdr, paths * sizeof(unsigned int)));
-    RT_CUDA(cudaMalloc((void **)&s->sp_res, paths * (size_t)nb_ech * sizeof(unsigned short)));
-    RT_CUDA(cudaMalloc((void **)&s->sp_q, 4 * paths * sizeof(unsigned int)));
-    if (!s->sp_ctr) RT_CUDA(cudaMalloc((void **)&s->sp_ctr, (size_t)SP_NCTR * (SP_MAX_ROUNDS + 2) * 2 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int)));
-    s->sp_cap = paths; s->sp_nb = nb_ech;
+    s->wf_cap = paths; s->wf_pos_cap = pos; s->wf_bounces = max_bounces;
     return RT_OK;
 }
 
@@ -1838,39 +1768,28 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     typedef void (*TraceKernel)(const DScene, const DCamera, const WfArgs);
     typedef void (*LightKernel)(const DScene, const WfArgs);
     const bool wf_lc = s->d.abvh_root >= 0;
-    // bit 29 of variant: fuse walk-and-classify into the trace kernel. Measured 30-40 % SLOWER on configs 2, 4 and 5
-    // (36.9 vs 26.2 ms, 110.8 vs 85.3, 98.9 vs 79.7: profiles/r01_notes.md) — one more confirmation that these kernels
-    // want small, single-phase code — so it is off unless asked for; kept because the tests cover it.
-    const bool wf_fuse = wf_lc && ((p->variant >> 29) & 1) != 0;
-    TraceKernel wf_trace = want_stats ? (wf_fuse ? k_wf_trace<true, true, true> : wf_lc ? k_wf_trace<true, true, false> : k_wf_trace<true, false, false>)
-                                      : (wf_fuse ? k_wf_trace<false, true, true> : wf_lc ? k_wf_trace<false, true, false> : k_wf_trace<false, false, false>);
+    // a scene without lights has no light stage: the trace kernel can scatter itself (NOLIGHT), one kernel per bounce level.
+    // Variant bit 29 asks for it; measured slower (profiles/r02_notes.md), so it is not the default.
+    const bool wf_nolight = s->d.n_lights == 0 && ((p->variant >> 29) & 1) != 0;
+    // scenes with meshes: analytic phase, then the mesh walk for the rays that touch a mesh, in a kernel of its own
+    // (k_wf_trace<.., MESH>); wavefront variant bit 28 switches the split off (A/B)
+    const bool wf_split = wf_lc && !wf_nolight && s->d.n_meshes > 0 && ((p->variant >> 28) & 1) == 0;
+    TraceKernel wf_trace = want_stats ? (wf_lc ? (wf_nolight ? k_wf_trace<true, true, true, 0> : wf_split ? k_wf_trace<true, true, false, 1> : k_wf_trace<true, true, false, 0>)
+                                               : (wf_nolight ? k_wf_trace<true, false, true, 0> : k_wf_trace<true, false, false, 0>))
+                                      : (wf_lc ? (wf_nolight ? k_wf_trace<false, true, true, 0> : wf_split ? k_wf_trace<false, true, false, 1> : k_wf_trace<false, true, false, 0>)
+                                               : (wf_nolight ? k_wf_trace<false, false, true, 0> : k_wf_trace<false, false, false, 0>));
+    TraceKernel wf_trace_mesh = want_stats ? k_wf_trace<true, true, false, 2> : k_wf_trace<false, true, false, 2>;
     // light stage: one kernel (no masks to classify by) or walk/classify + sample (see k_wf_light)
     LightKernel wf_light = want_stats ? (wf_lc ? k_wf_light<true, true, 1> : k_wf_light<true, false, 0>) : (wf_lc ? k_wf_light<false, true, 1> : k_wf_light<false, false, 0>);
     LightKernel wf_light_b = want_stats ? k_wf_light<true, true, 2> : k_wf_light<false, true, 2>;
+    // no lights: the light stage is only the scatter (k_wf_scatter); wavefront variant bit 27 keeps the general kernel (A/B)
+    const bool wf_scatter_only = s->d.n_lights == 0 && !wf_nolight && ((p->variant >> 27) & 1) == 0;
+    if (wf_scatter_only) wf_light = want_stats ? k_wf_scatter<true> : k_wf_scatter<false>;
     int wf_grid_t = 0, wf_grid_l = 0;
-    // Speculative shadow samples (k_wf_shadow / k_wf_validate): rounds of parallel sample tracing in front of the sequential
-    // sample kernel. Exact, tested, and measured SLOWER on every config (profiles/r02_notes.md, r02d/r02e: config 5 67 -> 87 ms,
-    // config 3 74 -> 90-94, config 2 11.4 -> 15.3): 85 % of config 5's parked samples validate in the first round, but a sample
-    // costs what it costs in either kernel (three IEEE normalisations and the candidate tests, not the walk), every round
-    // re-traces what it could not validate, and the sequential kernel stays as slow as its slowest lane. So: off unless asked
-    // for. Wavefront variant bits 20..23: 0 or 15 = off, 1..14 = that many rounds.
-    int sp_rounds = 0;
-    if (wavefront && wf_lc && !wf_fuse && s->d.n_lights > 0 && p->nb_ech <= 255) {
-        const int req = (p->variant >> 20) & 0xF;
-        sp_rounds = (req == 0 || req == 15) ? 0 : std::min(req, SP_MAX_ROUNDS);
-        if (const char *e = getenv("HAI719_SPEC_ROUNDS")) { const int v = atoi(e); if (v >= 0 && v <= SP_MAX_ROUNDS) sp_rounds = v; }   // tuning experiments
-    }
-    typedef void (*ShadowKernel)(const DScene, const WfArgs);
-    typedef void (*ValidateKernel)(const WfArgs);
-    ShadowKernel wf_shadow = want_stats ? k_wf_shadow<true> : k_wf_shadow<false>;
-    ValidateKernel wf_validate = want_stats ? k_wf_validate<true> : k_wf_validate<false>;
-    int wf_grid_s = 0;
     if (wavefront) {
         if ((rc = ensure_wavefront(s, (size_t)(chunk_pixels * p->spp), p->max_bounces))) return rc;
-        if (sp_rounds > 0 && (rc = ensure_spec(s, s->wf_cap, p->nb_ech))) return rc;
         wf_grid_t = persistent_grid(s, (const void *)wf_trace, 128);
         wf_grid_l = persistent_grid(s, (const void *)wf_light, 128);
-        if (sp_rounds > 0) wf_grid_s = persistent_grid(s, (const void *)wf_shadow, 128);
     }
 
     RenderArgs a{};
@@ -1911,75 +1830,65 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
         }
         if (wavefront) {
             WfArgs w{};
-            const size_t cap = s->wf_cap;
+            const size_t pc = s->wf_pos_cap;
             w.n_paths = (unsigned int)a.n_paths; w.max_bounces = p->max_bounces; w.nb_ech = p->nb_ech;
             // mesh scenes: a batch can cost 100x another one (rays that walk a mesh vs rays that miss its box), so warps take
             // one batch at a time as before; analytic scenes: cheap, even batches, where the fetch atomics were the bottleneck
             w.max_grab = s->d.n_meshes > 0 ? 1u : 8u;
+            // output positions a warp reserves per atomic: 256 where the queue atomics were the bottleneck (large chunks);
+            // small chunks take small blocks, so that their queues are not mostly padding
+            w.block = a.n_paths >= (4ull << 20) ? WF_MAX_BLOCK : (a.n_paths >= (256ull << 10) ? 64u : 32u);
+            w.mesh_inline_min = 12u;
+            if (const char *e = getenv("HAI719_MESH_INLINE_MIN")) { const int v = atoi(e); if (v >= 0 && v <= 33) w.mesh_inline_min = (unsigned int)v; }   // tuning experiments
             w.cam_rays = s->cam_rays; w.cam_keys = s->cam_keys;
-            w.ray0 = s->wf_f4; w.ray1 = s->wf_f4 + cap; w.hit0 = s->wf_f4 + 2 * cap; w.hit1 = s->wf_f4 + 3 * cap; w.hit2 = s->wf_f4 + 4 * cap;
-            w.hit3 = s->wf_f4 + 5 * cap; w.hit4 = s->wf_f4 + 6 * cap; w.park0 = s->wf_f4 + 7 * cap; w.park1 = s->wf_f4 + 8 * cap; w.park2 = s->wf_f4 + 9 * cap;
-            w.q_park = s->wf_q + 2 * cap; w.q_over = s->wf_q + 3 * cap; w.which_park = 0;
-            w.rng = s->wf_rng; w.rec = s->wf_rec; w.rec_stride = cap;
+            float4 *const f4 = s->wf_f4;
+            float4 *rayA0 = f4, *rayA1 = f4 + pc;
+            w.hit0 = f4 + 2 * pc; w.hit1 = f4 + 3 * pc; w.hit2 = f4 + 4 * pc; w.hit3 = f4 + 5 * pc; w.hit4 = f4 + 6 * pc;
+            w.park0 = f4 + 7 * pc; w.park1 = f4 + 8 * pc; w.park2 = f4 + 9 * pc; w.park_stride = pc;
+            w.mesh_hit = f4 + (9 + RT_LC_MAXC / 4) * pc; w.q_mesh = s->wf_q + 4 * pc;
+            uint2 *rngA = s->wf_rng;
+            w.rng_hit = s->wf_rng + pc;
+            unsigned int *qA = s->wf_q;
+            w.q_hit = s->wf_q + pc; w.q_park = s->wf_q + 2 * pc; w.q_over = s->wf_q + 3 * pc; w.which_park = 0;
+            w.rec = s->wf_rec; w.rec_stride = s->wf_cap;
             w.ctr = s->wf_ctr; w.samples = s->samples; w.stats = a.stats;
             RT_CUDA(cudaMemsetAsync(s->wf_ctr, 0, WF_NCTR * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
-            w.sp_enabled = sp_rounds > 0 ? 1 : 0;
-            if (sp_rounds > 0) {
-                w.sp_hdr = s->sp_hdr; w.sp_res = s->sp_res;
-                RT_CUDA(cudaMemsetAsync(s->sp_ctr, 0, (size_t)SP_NCTR * (SP_MAX_ROUNDS + 2) * 2 * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
-            }
-            unsigned int *q_live = s->wf_q, *q_hit = s->wf_q + cap;
+            const int gt = (int)std::min<unsigned long long>((unsigned long long)wf_grid_t, (batches + 3) / 4);
+            const int gl = (int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4);
             for (int level = 0; level < p->max_bounces; ++level) {
                 w.level = level;
-                if (wf_fuse) {
-                    // two live queues alternate by level: this level's kernels read one and append to the other
-                    unsigned int *q_this = (level & 1) ? q_hit : q_live, *q_next = (level & 1) ? q_live : q_hit;
-                    w.q_in = q_this; w.q_live_next = q_next; w.q_out = q_next;
-                    wf_trace<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_t, (batches + 3) / 4), 128, 0, st>>>(s->d, cam, w);
+                if (wf_nolight) {
+                    // no hit queue: its arrays are the second live queue, the two alternate by level (a level's kernel reads
+                    // one and appends to the other)
+                    const bool odd = (level & 1) != 0;
+                    w.q_live = odd ? w.q_hit : qA; w.ray0 = odd ? w.hit0 : rayA0; w.ray1 = odd ? w.hit1 : rayA1; w.rng_ray = odd ? w.rng_hit : rngA;
+                    w.q_next = odd ? qA : w.q_hit; w.nray0 = odd ? rayA0 : w.hit0; w.nray1 = odd ? rayA1 : w.hit1; w.nrng = odd ? rngA : w.rng_hit;
+                    wf_trace<<<gt, 128, 0, st>>>(s->d, cam, w);
                     RT_CUDA(cudaGetLastError());
                     ++launches;
-                    if (s->d.n_lights > 0) {
-                        wf_light_b<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
-                        RT_CUDA(cudaGetLastError());
-                        ++launches;
-                    }
                     continue;
                 }
-                w.q_in = q_live; w.q_out = q_hit;
-                wf_trace<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_t, (batches + 3) / 4), 128, 0, st>>>(s->d, cam, w);
+                // the light kernels of level L append the live queue of level L + 1 to the arrays trace L has finished reading
+                w.q_live = qA; w.ray0 = rayA0; w.ray1 = rayA1; w.rng_ray = rngA;
+                w.q_next = qA; w.nray0 = rayA0; w.nray1 = rayA1; w.nrng = rngA;
+                wf_trace<<<gt, 128, 0, st>>>(s->d, cam, w);
                 RT_CUDA(cudaGetLastError());
-                w.q_in = q_hit; w.q_out = q_live;
-                wf_light<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
+                if (wf_split) {
+                    wf_trace_mesh<<<gt, 128, 0, st>>>(s->d, cam, w);
+                    RT_CUDA(cudaGetLastError());
+                    ++launches;
+                }
+                wf_light<<<gl, 128, 0, st>>>(s->d, w);
                 RT_CUDA(cudaGetLastError());
                 launches += 2;
-                if (sp_rounds > 0) {
-                    // rounds of speculative samples for both parked queues: round r reads the hits the validation of round r - 1
-                    // left unfinished (round 0: everything the classify kernel parked) and writes the ones it leaves unfinished
-                    const size_t scap = s->sp_cap;
-                    for (int q = 0; q < (s->d.n_meshes > 0 ? 2 : 1); ++q) {
-                        unsigned int *cbase = s->sp_ctr + (size_t)SP_NCTR * (SP_MAX_ROUNDS + 2) * (2 * level + q);
-                        for (int r = 0; r < sp_rounds; ++r) {
-                            w.sp_q_in = r == 0 ? (q ? w.q_over : w.q_park) : s->sp_q + (size_t)(2 * q + ((r - 1) & 1)) * scap;
-                            w.sp_cnt_in = r == 0 ? s->wf_ctr + WF_NCTR * level + (q ? 7 : 5) : cbase + SP_NCTR * r + 2;
-                            w.sp_head = cbase + SP_NCTR * r; w.sp_vhead = cbase + SP_NCTR * r + 1;
-                            w.sp_q_out = s->sp_q + (size_t)(2 * q + (r & 1)) * scap;
-                            w.sp_cnt_out = cbase + SP_NCTR * (r + 1) + 2;
-                            wf_shadow<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_s, (batches * (unsigned long long)p->nb_ech + 3) / 4), 128, 0, st>>>(s->d, w);
-                            RT_CUDA(cudaGetLastError());
-                            wf_validate<<<(int)std::min<unsigned long long>((unsigned long long)(2 * s->sm_count), (batches + 3) / 4), 128, 0, st>>>(w);
-                            RT_CUDA(cudaGetLastError());
-                            launches += 2;
-                        }
-                    }
-                }
-                if (wf_lc && s->d.n_lights > 0) {
+                if (wf_lc && !wf_scatter_only) {
                     w.which_park = 0;
-                    wf_light_b<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
+                    wf_light_b<<<gl, 128, 0, st>>>(s->d, w);
                     RT_CUDA(cudaGetLastError());
                     ++launches;
                     if (s->d.n_meshes > 0) {   // lights whose candidate-triangle list overflowed, in warps of their own
                         w.which_park = 1;
-                        wf_light_b<<<(int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4), 128, 0, st>>>(s->d, w);
+                        wf_light_b<<<gl, 128, 0, st>>>(s->d, w);
                         RT_CUDA(cudaGetLastError());
                         ++launches;
                         w.which_park = 0;
@@ -1991,7 +1900,7 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
             RT_CUDA(cudaGetLastError());
             ++launches;
         }
-        if (wavefront && !wf_fuse) k_wf_tally<<<1, 32, 0, st>>>(s->wf_ctr, (unsigned int)a.n_paths, p->max_bounces, s->counters + 11);
+        if (wavefront) k_wf_tally<<<1, 32, 0, st>>>(s->wf_ctr, (unsigned int)a.n_paths, p->max_bounces, s->counters + 11);
         k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(a, cam_split ? s->pix_xy : nullptr, (unsigned int)np, d_linear, d_gamma, d_sum, sample_base,
                                                                  image_mode, r.x0, r.y0, r.x1 - r.x0);
         RT_CUDA(cudaGetLastError());
@@ -2006,7 +1915,7 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
         stats->kernel_ms = ms;
         stats->n_launches = launches;
         stats->n_chunks = (uint32_t)((n_pixels + chunk_pixels - 1) / chunk_pixels);
-        if (wavefront && !wf_fuse && !want_stats) {   // ray counts from the queue counters (k_wf_tally): exact, and free
+        if (wavefront && !want_stats) {   // ray counts from the queue counters (k_wf_tally): exact, and free
             unsigned long long c[2];
             RT_CUDA(cudaMemcpy(c, s->counters + 11, sizeof c, cudaMemcpyDeviceToHost));
             stats->n_closest_rays = c[0];
@@ -2020,15 +1929,6 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
             stats->n_tex_fetches = c[9]; stats->n_random = c[10];
         }
     }
-    return RT_OK;
-}
-
-// tuning aid, not part of the reference-facing interface: the 16 raw device counters of the last render with collect_stats
-// ([13] / [14]: speculative shadow samples validated / pending, summed over the rounds)
-int rt_debug_counters(RtScene *s, unsigned long long *out16) {
-    if (!s || !out16 || !s->counters) return fail(RT_ERR_INVALID, "no counters");
-    RT_CUDA(cudaSetDevice(s->device));
-    RT_CUDA(cudaMemcpy(out16, s->counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 

@@ -495,6 +495,11 @@ RT_HD bool mesh_closest(const Ray &ray, const RayInv &inv, const DScene &s, cons
     return true;
 }
 
+// NOTE on the out-of-line (RT_COLD) functions below: they take the ray BY VALUE. By reference, the address of the caller's
+// ray — a member of the kernel's path state — escaped into a call, and the compiler then kept the WHOLE path state in the
+// thread's local-memory frame instead of in registers: every field assignment became an STL, and local stores write through
+// to L2 (ncu, config 2, level-0 trace kernel: 226 M sectors = 7.2 GB of local stores against 1.7 GB of record stores, 5.3 TB/s
+// of L2 write traffic in a 1.35 ms kernel; profiles/r02_notes.md).
 // ---- mesh: exact culling traversal (variant 3, construction and proof sketch in rt_bvh.hpp) ------
 // Is the leaf that holds reference r reachable by the reference's traversal for this ray, given that
 // the triangle was hit at parameter t?  Fast accept: t lies strictly inside the slab interval of
@@ -503,7 +508,7 @@ RT_HD bool mesh_closest(const Ray &ray, const RayInv &inv, const DScene &s, cons
 // ancestor (whose boxes contain it) AABB::intersects keeps tmin < t < tmax at every step and
 // returns true. Anything else — grazing, axis-parallel, tiny t — re-runs the reference's own fp64
 // slab test (slab_hit) up the parent chain, synthetic root (= KDTree::aabb gate) included.
-RT_COLD bool leaf_reachable_exact(const DScene &s_, const Ray &ray, uint32_t leaf) {
+RT_COLD bool leaf_reachable_exact(const DScene &s_, const Ray ray, uint32_t leaf) {
     const DScene &s = RT_S(s_);
     const RayInv inv = make_inv(ray);
     uint32_t n = leaf;
@@ -532,7 +537,7 @@ RT_HD bool leaf_reachable(const DScene &s, const Ray &ray, float t, uint32_t lea
     if (leaf_contains_hit(s, ray, RT_FAST_RCP(ray.d.x), RT_FAST_RCP(ray.d.y), RT_FAST_RCP(ray.d.z), t, leaf)) return true;
     return leaf_reachable_exact(s, ray, leaf);
 }
-RT_COLD bool tri_reachable_exact(const DScene &s_, const Ray &ray, uint32_t r0) {
+RT_COLD bool tri_reachable_exact(const DScene &s_, const Ray ray, uint32_t r0) {
     const DScene &s = RT_S(s_);
     for (uint32_t r = r0; r != 0xFFFFFFFFu; r = RT_LDG(s.ref_next + r))
         if (leaf_reachable_exact(s, ray, RT_LDG(s.ref_leaf + r))) return true;
@@ -556,7 +561,7 @@ RT_HD bool tri_reachable(const DScene &s, const Ray &ray, float t, uint32_t r0) 
 #endif
 }
 // last reachable reference (decides ties between different triangles at the same t)
-RT_COLD uint32_t tri_last_reachable(const DScene &s_, const Ray &ray, float t, uint32_t r0) {
+RT_COLD uint32_t tri_last_reachable(const DScene &s_, const Ray ray, float t, uint32_t r0) {
     const DScene &s = RT_S(s_);
     uint32_t last = 0xFFFFFFFFu;
     for (uint32_t r = r0; r != 0xFFFFFFFFu; r = RT_LDG(s.ref_next + r))
@@ -835,6 +840,24 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
 }
 
 #undef RT_WALK_DESCEND
+
+// Can meshes_walk_merged find anything for this ray below `limit`? Only if some mesh has always-tested triangles or the ray
+// passes the FIRST step of a mesh's walk (one of the two boxes of its root node, same conservative test, same limit):
+// otherwise every walk ends at its root with no candidate. The wavefront uses this to send only such rays to the mesh-walk
+// kernel; the others keep their analytic hit, which is what the walk would have left them with.
+RT_HD bool ray_touches_meshes(const DScene &s, const Ray &ray, float limit) {
+    const Inv32 iv = make_inv32(ray);
+    for (int mi = 0; mi < s.n_meshes; ++mi) {
+        const DMesh &m = s.meshes[mi];
+        if (m.always_count > 0u) return true;
+        if (m.bvh_root < 0) continue;
+        const float4 n0 = RT_LDG(s.bvh_nodes + 4 * m.bvh_root), n1 = RT_LDG(s.bvh_nodes + 4 * m.bvh_root + 1), n2 = RT_LDG(s.bvh_nodes + 4 * m.bvh_root + 2);
+        float d;
+        if (bvh_box(ray, iv, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, limit, d)) return true;
+        if (bvh_box(ray, iv, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, limit, d)) return true;
+    }
+    return false;
+}
 
 // ---- analytic primitives through their culling hierarchy (variant 3) ----------------------------
 // Visits every sphere/square whose padded, motion-swept box the ray can touch within [0, limit] and
@@ -1202,8 +1225,9 @@ struct PathState {
     uint32_t cl[RT_LC_MAXC];
     int cl_n;
     // per-depth radiance records: the state-machine kernels keep them in the thread's frame (PathRecs, 576 B, declared
-    // by the kernel); the wavefront kernels (variant 6) keep them in global memory instead: entry (3*depth + {0 colour,
-    // 1 kd, 2 e}) of path slot `path` is wf_rec[(3*depth + k) * wf_stride + path], and `recs` is null — their frame
+    // by the kernel); the wavefront kernels (variant 6) keep them in global memory instead: the record of depth d of path
+    // slot `path` is the three float4 at wf_rec[3 * (d * wf_stride + path)] ({kd, flags} {colour} {e}: 48 contiguous bytes,
+    // one or two sectors, where three separate planes cost three half-used ones), and `recs` is null — their frame
     // does not carry the arrays
     PathRecs *recs;
     float4 *wf_rec;
@@ -1661,9 +1685,11 @@ RT_HD bool lc_shadow_analytic(const DScene &s, PathState &st, Counters *cnt) {
 //                               analytic hierarchy together; mode 0 goes on to the meshes.
 //   run_t false               : lanes in mode 1 test their candidate mask, then the meshes.
 // Requires s.abvh_root >= 0 (the kernel is only selected for such scenes).
+// with_meshes = false: closest-hit rays stop after the analytic primitives (the wavefront walks the meshes in a kernel of its
+// own, for the rays that touch a mesh at all: ray_touches_meshes below).
 template <bool STATS>
 RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, Hit &h, float &hu, float &hv, bool &blocked,
-                        Counters *cnt) {
+                        Counters *cnt, bool with_meshes = true) {
     const Ray &ray = st.ray;
     const int mode = st.mode;
     h.type = 0; h.obj = -1; h.t = (mode == 0) ? FLT_MAX : st.t_light; h.ref = 0;
@@ -1892,6 +1918,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
         if (lc_shadow_analytic<STATS>(s, st, cnt)) { blocked = true; done = true; }
     }
 #endif
+    if (!with_meshes) return;
     // meshes. Closest-hit rays, and shadow samples whose light has too many candidate triangles for the list, walk the
     // exact culling hierarchies (variant 3); other shadow samples test the listed candidates, mesh after mesh in the
     // reference's order, with the same per-triangle routine (bvh_consider) the walk uses.
@@ -1931,18 +1958,36 @@ RT_HD void path_begin(PathState &st, const Ray &primary, const Rng &rng, uint32_
 }
 
 // fold the records back to front: result_k = (color_k + result_{k+1} (*) kd_k) + e_k  (Scene.h:339-341)
+// The wavefront's radiance records: the record of depth d of path slot `path` is three adjacent float4 {kd, flags} {colour}
+// {e}; colour and e are stored (and read) only when they are not +0 (flags bit 0 / 1), which they mostly are: no light
+// reached / not an emitter. "+0" is tested on the bits: a stored -0 must come back as -0 (x + -0 and x + +0 differ for x = -0).
+RT_HD void wf_rec_store(float4 *wf_rec, unsigned long long stride, uint32_t path, int depth, V3 color, V3 kd, V3 e) {
+    float4 *rec = wf_rec + 3ull * ((unsigned long long)depth * stride + path);
+    const uint32_t fl = ((f2u(color.x) | f2u(color.y) | f2u(color.z)) ? 1u : 0u) | ((f2u(e.x) | f2u(e.y) | f2u(e.z)) ? 2u : 0u);
+    RT_ST_STREAM(rec, make_float4(kd.x, kd.y, kd.z, u2f(fl)));
+    if (fl & 1u) RT_ST_STREAM(rec + 1, make_float4(color.x, color.y, color.z, 0.f));
+    if (fl & 2u) RT_ST_STREAM(rec + 2, make_float4(e.x, e.y, e.z, 0.f));
+}
+// fold the records back to front: result_k = (color_k + result_{k+1} (*) kd_k) + e_k  (Scene.h:339-341), then / MAXBOUNCES (:345-350)
+RT_HD V3 wf_fold(const float4 *wf_rec, unsigned long long stride, uint32_t path, int depth, int max_bounces, V3 tail) {
+    V3 r = tail;
+    for (int k = depth - 1; k >= 0; --k) {
+        const float4 *rec = wf_rec + 3ull * ((unsigned long long)k * stride + path);
+        const float4 kd = RT_LD_STREAM(rec);
+        const uint32_t fl = f2u(kd.w);
+        V3 c = v3(0.f), e = v3(0.f);
+        if (fl & 1u) { const float4 t = RT_LD_STREAM(rec + 1); c = v3(t.x, t.y, t.z); }
+        if (fl & 2u) { const float4 t = RT_LD_STREAM(rec + 2); e = v3(t.x, t.y, t.z); }
+        r = (c + comp_product(r, v3(kd.x, kd.y, kd.z))) + e;
+    }
+    r = v3(0.f) + r;
+    return r / (float)max_bounces;
+}
 template <bool WF = false>
 RT_HD V3 path_fold(const PathState &st, V3 tail) {
+    if (WF) return wf_fold(st.wf_rec, st.wf_stride, st.path, st.depth, st.max_bounces, tail);
     V3 r = tail;
-    for (int k = st.depth - 1; k >= 0; --k) {
-        if (WF) {
-            const float4 c = RT_LD_STREAM(st.wf_rec + (3ull * k + 0) * st.wf_stride + st.path), kd = RT_LD_STREAM(st.wf_rec + (3ull * k + 1) * st.wf_stride + st.path),
-                         e = RT_LD_STREAM(st.wf_rec + (3ull * k + 2) * st.wf_stride + st.path);
-            r = (v3(c.x, c.y, c.z) + comp_product(r, v3(kd.x, kd.y, kd.z))) + v3(e.x, e.y, e.z);
-        } else {
-            r = (st.recs->rec_c[k] + comp_product(r, st.recs->rec_kd[k])) + st.recs->rec_e[k];
-        }
-    }
+    for (int k = st.depth - 1; k >= 0; --k) r = (st.recs->rec_c[k] + comp_product(r, st.recs->rec_kd[k])) + st.recs->rec_e[k];
     r = v3(0.f) + r;
     return r / (float)st.max_bounces;
 }
@@ -1985,11 +2030,11 @@ RT_SHARED_BOUNCE bool path_next_light_or_bounce(const DScene &s_, PathState &st,
         return false;
     }
     Ray in; in.o = st.P; in.d = st.in_d; in.time = st.ray.time;
-    st.ray = material_scatter<STATS>(*st.mat, in, st.n, st.P, st.rng, cnt);
+    Rng rng = st.rng;   // a copy: material_scatter is out of line, and a reference into `st` would pin the whole state in local memory
+    st.ray = material_scatter<STATS>(*st.mat, in, st.n, st.P, rng, cnt);
+    st.rng = rng;
     if (WF) {
-        RT_ST_STREAM(st.wf_rec + (3ull * st.depth + 0) * st.wf_stride + st.path, make_float4(st.color.x, st.color.y, st.color.z, 0.f));
-        RT_ST_STREAM(st.wf_rec + (3ull * st.depth + 1) * st.wf_stride + st.path, make_float4(st.kd.x, st.kd.y, st.kd.z, 0.f));
-        RT_ST_STREAM(st.wf_rec + (3ull * st.depth + 2) * st.wf_stride + st.path, make_float4(st.e.x, st.e.y, st.e.z, 0.f));
+        wf_rec_store(st.wf_rec, st.wf_stride, st.path, st.depth, st.color, st.kd, st.e);
     } else {
         st.recs->rec_c[st.depth] = st.color; st.recs->rec_kd[st.depth] = st.kd; st.recs->rec_e[st.depth] = st.e;
     }

@@ -241,10 +241,6 @@ int rt_scene_update_analytic(RtScene *scene, const RtSceneDesc *desc);
 size_t rt_scene_device_bytes(const RtScene *scene);
 /* Bytes rt_scene_create really copied host -> device for this handle (images found in the device cache are not copied). */
 size_t rt_scene_h2d_bytes(const RtScene *scene);
-/* Tuning aid (no reference counterpart): the 16 raw device counters of the scene's last render with collect_stats:
- * [0] work counter, [1..10] the RtStats counters, [11..12] wavefront ray tally, [13] / [14] speculative shadow samples
- * validated / pending over all rounds (k_wf_validate). */
-int rt_debug_counters(RtScene *scene, unsigned long long *out16);
 
 /* Number of pixels this rank renders under `params` (rectangle + tile sharding), i.e. the
  * element count / 3 of the packed output of rt_render_device(). */

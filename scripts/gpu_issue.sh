@@ -4,5 +4,5 @@
 TAG=$1; WL=$2; SPP=$3; VAR=${4:-0}
 mkdir -p gpurun_out
 timeout 900 ncu --metrics gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active \
-  --clock-control none --kernel-name-base mangled -k regex:"k_wf_.*ILb0|k_camera|k_pixel|k_resolve|k_render_regenILb0|k_render_pathsILb0" -c 400 --csv --log-file gpurun_out/${TAG}.csv \
-  python tools/profile_render.py --workload $WL --spp $SPP --reps 1 --variant $VAR > gpurun_out/${TAG}.log 2>&1
+  --clock-control none --kernel-name-base mangled -k regex:"k_wf_|k_camera|k_pixel|k_resolve|k_render_regen|k_render_paths" -c 400 --csv --log-file gpurun_out/${TAG}.csv \
+  python tools/profile_render.py --workload $WL --spp $SPP --reps 1 --variant $VAR --no-stats > gpurun_out/${TAG}.log 2>&1

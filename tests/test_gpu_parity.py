@@ -125,8 +125,6 @@ def test_kernel_variants_agree_bit_for_bit(gpu, assets, name):
     for st in (False, True):
         q = s.render(W, H, SPP, seed=0, variant=6, stats=st)
         assert np.array_equal(a["linear"].view(np.uint32), q["linear"].view(np.uint32)), st
-        q2 = s.render(W, H, SPP, seed=0, variant=6 | (1 << 29), stats=st)     # walk-and-classify fused into the trace kernel
-        assert np.array_equal(a["linear"].view(np.uint32), q2["linear"].view(np.uint32)), st
     for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):
         assert a["stats"][k] == q["stats"][k], k
     for k in ("n_closest_rays", "n_shadow_rays", "n_random", "n_tex_fetches"):

@@ -357,27 +357,26 @@ def test_ray_counts_equal_the_references_own_calls(gpu, assets, name, w, h, spp)
     assert st["n_random"] == want["n_random"], name
 
 
-# ---- speculative shadow samples (k_wf_shadow / k_wf_validate) ---------------------------------------------------------------
-@pytest.mark.parametrize("name,w,h,spp", [("flamingo_pond", 240, 136, 3), ("config5", 240, 136, 2), ("random_spheres", 240, 136, 3),
-                                          ("flamingo", 160, 90, 2), ("raccoon", 160, 90, 2)])
-def test_speculative_shadow_rounds_do_not_change_a_bit(gpu, assets, name, w, h, spp):
-    """The wavefront traces the NB_ECH samples of a parked light in parallel from GUESSED stream positions and keeps only
-    the samples whose guess the validation confirms (rt_capi.cu : k_wf_shadow). Whatever the number of rounds (variant
-    bits 20..23: 15 = off, 1..14 rounds; the rest is finished sequentially) the image, the ray counts and the number of
-    random draws are those of the sequential sample kernel and of the one-path-per-lane kernel (variant 1). Scenes: one
-    and two lights, with and without meshes, list and walk queues; nb_ech 10 and 4."""
+# ---- queue-position records, block reservation, no-light trace ---------------------------------------------------------------
+@pytest.mark.parametrize("name,w,h,spp", [("random_spheres", 400, 225, 3), ("backrooms_pool", 240, 136, 2), ("config5", 240, 136, 2),
+                                          ("cornell_box", 240, 136, 2), ("flamingo_pond", 240, 136, 2), ("raccoon", 160, 90, 2)])
+def test_wavefront_block_sizes_and_chunking_do_not_change_a_bit(gpu, assets, name, w, h, spp, monkeypatch):
+    """The wavefront stores path state at queue positions that warps reserve a block at a time (32 / 64 / 256 positions by
+    chunk size) and pads the unused tail of a block with invalid entries; scenes without lights (pool, Cornell) scatter
+    inside the trace kernel and alternate two live queues. Small chunks (HAI719_CHUNK_LOG2: many chunks, queues reused,
+    mostly padding) and large ones must give the bits of the one-path-per-lane kernel, and the same ray counts."""
     s = gpu.Scene(name, aspect=w / h, seed=0)
-    want = s.render(w, h, spp, seed=3, variant=1, stats=True)
-    off = s.render(w, h, spp, seed=3, variant=6 | (15 << 20), stats=True)
-    assert np.array_equal(bits(want["linear"]), bits(off["linear"]))
-    for rounds in (1, 2, 3, 6, 14):
+    want = s.render(w, h, spp, seed=4, variant=1, stats=True)
+    for log2 in (None, 16, 18):
+        if log2 is None:
+            monkeypatch.delenv("HAI719_CHUNK_LOG2", raising=False)
+        else:
+            monkeypatch.setenv("HAI719_CHUNK_LOG2", str(log2))
         for st in (False, True):
-            got = s.render(w, h, spp, seed=3, variant=6 | (rounds << 20), stats=st)
-            assert np.array_equal(bits(want["linear"]), bits(got["linear"])), (name, rounds, st)
-            for k in ("n_closest_rays", "n_shadow_rays") + (("n_random", "n_tex_fetches") if st else ()):
-                assert want["stats"][k] == got["stats"][k], (name, rounds, st, k)
-    auto = s.render(w, h, spp, seed=3, variant=6)
-    assert np.array_equal(bits(want["linear"]), bits(auto["linear"]))
-    few = s.render(w, h, spp, seed=3, variant=6 | (2 << 20), nb_ech=4, max_bounces=3)
-    ref4 = s.render(w, h, spp, seed=3, variant=1, nb_ech=4, max_bounces=3)
-    assert np.array_equal(bits(ref4["linear"]), bits(few["linear"]))
+            # bit 29: scenes without lights scatter inside the trace kernel; bit 28: no separate mesh-walk kernel; bit 27: the general
+            # light kernel instead of k_wf_scatter for scenes without lights
+            for v in (6, 6 | (1 << 29), 6 | (1 << 28), 6 | (1 << 27), 6 | (1 << 27) | (1 << 28)):
+                got = s.render(w, h, spp, seed=4, variant=v, stats=st)
+                assert np.array_equal(bits(want["linear"]), bits(got["linear"])), (name, log2, st, v)
+                for k in ("n_closest_rays", "n_shadow_rays") + (("n_random", "n_tex_fetches") if st else ()):
+                    assert want["stats"][k] == got["stats"][k], (name, log2, st, v, k)

@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScen
     const unsigned int lane = threadIdx.x & 31u;
     PathState st;
     PathRecs recs;
-    st.recs = &recs; st.wf_rec = nullptr; st.wf_stride = 0;
+    CandList cands;
+    st.recs = &recs; st.cl = cands.v; st.wf_rec = nullptr; st.wf_stride = 0;
     st.mode = 2;
     st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f; st.t_light = 0.f;
     st.rng.key = 0; st.rng.ctr = 0;
@@ -350,7 +351,6 @@ struct WfArgs {
     unsigned int n_paths;              // paths of this chunk (slots 0 .. n_paths-1)
     unsigned int max_grab;             // batches a warp may fetch with one atomic (see wf_next_batch)
     unsigned int block;                // queue positions a warp reserves with one atomic (see wf_push)
-    unsigned int mesh_inline_min;      // split trace: lanes of a warp that must touch a mesh for the warp to walk inline (see k_wf_trace)
     int max_bounces, nb_ech, level;
     const float4 *cam_rays; const unsigned int *cam_keys;   // level 0 input, by slot
     // live queue of this level (trace input) ...
@@ -473,7 +473,8 @@ __device__ __forceinline__ void wf_count_entries(unsigned int *entries, const un
 #ifndef RT_WF_MINB
 #define RT_WF_MINB 8
 #endif
-__device__ __forceinline__ void wf_state_init(PathState &st, const WfArgs &w) {
+__device__ __forceinline__ void wf_state_init(PathState &st, CandList &cands, const WfArgs &w) {
+    st.cl = cands.v;
     st.mode = 2; st.t_light = 0.f; st.light = 0;
     st.ray.o = v3(0.f); st.ray.d = v3(0.f, 0.f, 1.f); st.ray.time = 0.f;
     st.rng.key = 0; st.rng.ctr = 0;
@@ -487,10 +488,9 @@ __device__ __forceinline__ void wf_store_ray(const WfArgs &w, unsigned int pos, 
 }
 
 // MESH = 0: one kernel per level, analytic primitives and meshes. MESH = 1 / 2: two kernels. Phase 1 intersects the analytic
-// primitives and asks ray_touches_meshes: rays that cannot hit a mesh (most, when the meshes are objects in a room) are shaded
-// at once; the others go to a queue with their analytic hit so far. Phase 2 walks the meshes for THOSE rays only, in full
-// warps, and shades them. In one kernel the few lanes of a warp that walk a mesh kept the rest waiting: the trace kernel
-// of the pool scene ran at 12.6 of 32 lanes (profiles/r02_notes.md).
+// primitives and asks ray_touches_meshes: rays that cannot hit a mesh are shaded at once; the others go to a queue with their
+// analytic hit so far. Phase 2 walks the meshes for THOSE rays only and shades them. Two smaller kernels (frames of 320 and
+// 344 B against 592) instead of one; whether that pays depends on the scene (rt_render_device: wf_split).
 template <bool STATS, bool LC, bool NOLIGHT, int MESH>
 __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene_, const DCamera cam, const WfArgs w) {
     const DScene &scene = RT_S(scene_);
@@ -512,7 +512,8 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
             valid = i != WF_INVALID;
         }
         PathState st;
-        wf_state_init(st, w);
+        CandList cands;
+        wf_state_init(st, cands, w);
         unsigned int slot = 0;
         if (valid) {
             if (w.level == 0) {
@@ -559,20 +560,12 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
             intersect_ray<STATS, true>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
         }
         if (MESH == 1) {
-            // Rays that touch a mesh: when enough lanes of this warp do, they walk right here (the warp is busy enough);
-            // when only a few do, those lanes leave for the walk kernel with what they have, where they are packed into
-            // full warps, instead of keeping the rest of this warp waiting. The others are final either way.
+            // rays that touch a mesh leave for the walk kernel with what they have; the others are final
             const bool touch = valid && ray_touches_meshes(scene, st.ray, h.t);
-            const unsigned int bt = __ballot_sync(0xFFFFFFFFu, touch);
-            if ((unsigned int)__popc(bt) >= w.mesh_inline_min) {
-                bool done = !touch;
-                meshes_walk_merged<STATS>(scene, st.ray, 0, st.rng, h, blocked, done, &cnt);
-            } else if (bt) {
-                const unsigned int mp = wf_push(w.q_mesh, w.ctr + WF_NCTR * w.level + 11, w.block, ws, 1, touch, i);
-                if (touch) {
-                    WF_ST(w.mesh_hit + mp, make_float4(h.t, u2f(((uint32_t)h.type << 28) | ((uint32_t)h.obj & 0x0FFFFFFFu)), hu, hv));
-                    valid = false;
-                }
+            const unsigned int mp = wf_push(w.q_mesh, w.ctr + WF_NCTR * w.level + 11, w.block, ws, 1, touch, i);
+            if (touch) {
+                WF_ST(w.mesh_hit + mp, make_float4(h.t, u2f(((uint32_t)h.type << 28) | ((uint32_t)h.obj & 0x0FFFFFFFu)), hu, hv));
+                valid = false;
             }
         }
         // a path is lit iff its ray hit something (path_shade ends the path on a miss, Scene.h:270-272): the position of its hit
@@ -647,7 +640,8 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
         const unsigned int i = base + lane;
         bool valid = i < count;
         PathState st;
-        wf_state_init(st, w);
+        CandList cands;
+        wf_state_init(st, cands, w);
         unsigned int slot = 0, hp = i;   // hp: position of the hit in the hit queue (where its records are)
         bool fin = true, parked = false;
         V3 c = v3(0.f);
@@ -1771,9 +1765,12 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     // a scene without lights has no light stage: the trace kernel can scatter itself (NOLIGHT), one kernel per bounce level.
     // Variant bit 29 asks for it; measured slower (profiles/r02_notes.md), so it is not the default.
     const bool wf_nolight = s->d.n_lights == 0 && ((p->variant >> 29) & 1) != 0;
-    // scenes with meshes: analytic phase, then the mesh walk for the rays that touch a mesh, in a kernel of its own
-    // (k_wf_trace<.., MESH>); wavefront variant bit 28 switches the split off (A/B)
-    const bool wf_split = wf_lc && !wf_nolight && s->d.n_meshes > 0 && ((p->variant >> 28) & 1) == 0;
+    // Scenes with meshes: analytic phase, then the mesh walk for the rays that touch a mesh, in a kernel of its own
+    // (k_wf_trace<.., MESH>). Measured (profiles/r02_notes.md, r02k-r02m): the pool scene (no lights: the trace stage is 80 % of
+    // the frame) 64.6 -> 61.2 ms per 4-spp frame; config 5 62.5 -> 65.2 and the pond scene 67.0 -> 68.5 (lit scenes: trace is a
+    // quarter of the frame, and nearly every ray touches a mesh's root box there, so the second kernel repeats the pass over the
+    // ray records for all of them). Hence: on for scenes without lights; wavefront variant bit 28 flips the choice (A/B).
+    const bool wf_split = wf_lc && !wf_nolight && s->d.n_meshes > 0 && ((s->d.n_lights == 0) != (((p->variant >> 28) & 1) != 0));
     TraceKernel wf_trace = want_stats ? (wf_lc ? (wf_nolight ? k_wf_trace<true, true, true, 0> : wf_split ? k_wf_trace<true, true, false, 1> : k_wf_trace<true, true, false, 0>)
                                                : (wf_nolight ? k_wf_trace<true, false, true, 0> : k_wf_trace<true, false, false, 0>))
                                       : (wf_lc ? (wf_nolight ? k_wf_trace<false, true, true, 0> : wf_split ? k_wf_trace<false, true, false, 1> : k_wf_trace<false, true, false, 0>)
@@ -1838,8 +1835,6 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
             // output positions a warp reserves per atomic: 256 where the queue atomics were the bottleneck (large chunks);
             // small chunks take small blocks, so that their queues are not mostly padding
             w.block = a.n_paths >= (4ull << 20) ? WF_MAX_BLOCK : (a.n_paths >= (256ull << 10) ? 64u : 32u);
-            w.mesh_inline_min = 12u;
-            if (const char *e = getenv("HAI719_MESH_INLINE_MIN")) { const int v = atoi(e); if (v >= 0 && v <= 33) w.mesh_inline_min = (unsigned int)v; }   // tuning experiments
             w.cam_rays = s->cam_rays; w.cam_keys = s->cam_keys;
             float4 *const f4 = s->wf_f4;
             float4 *rayA0 = f4, *rayA1 = f4 + pc;

@@ -1206,6 +1206,7 @@ RT_HD V3 trace_path(const DScene &s, Ray ray, Rng &rng, int max_bounces, int nb_
 
 
 struct PathRecs { V3 rec_c[RT_MAX_BOUNCES], rec_kd[RT_MAX_BOUNCES], rec_e[RT_MAX_BOUNCES]; };
+struct CandList { uint32_t v[RT_LC_MAXC]; };
 struct PathState {
     Rng rng;
     Ray ray;             // the ray to intersect next
@@ -1222,7 +1223,10 @@ struct PathState {
     uint32_t cm0, cm1, cm2, cm3;   // variant 5: analytic primitives (sequence index = bit) that can occlude light `light` from P
     // ... and the triangles the cone towards that light can touch: (mesh << 27 | first leaf ref of the triangle), in mesh
     // order; cl_n < 0 = too many for the list, shadow samples walk the mesh hierarchies themselves
-    uint32_t cl[RT_LC_MAXC];
+    // The list is an array of its own (CandList, declared by the kernel next to the path state), reached through this
+    // pointer: as a MEMBER array it was indexed dynamically, and that alone kept the whole path state in the thread's
+    // local-memory frame instead of in registers.
+    uint32_t *cl;
     int cl_n;
     // per-depth radiance records: the state-machine kernels keep them in the thread's frame (PathRecs, 576 B, declared
     // by the kernel); the wavefront kernels (variant 6) keep them in global memory instead: the record of depth d of path

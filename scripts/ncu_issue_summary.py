@@ -12,12 +12,17 @@ import collections, csv, json, re, sys
 
 
 def short(name):
-    m = re.match(r"_Z\d+(k_[a-z_0-9]+?)(I(.*))?E?v", name)
+    name = name.strip()
+    if name.startswith("void "):
+        name = name[5:]
+    m = re.match(r"(k_[a-z_0-9]+)(<[^>]*>)?", name)          # demangled: k_wf_trace<0, 1, 0, 0>(rt::DScene, ...)
+    if m:
+        return m.group(1) + (m.group(2) or "").replace(" ", "").replace("(bool)", "").replace("(int)", "")
+    m = re.match(r"_Z\d+(k_[a-z_0-9]+?)(I(.*))?E?v", name)    # mangled
     if not m:
         return name[:40]
-    base, targs = m.group(1), m.group(3) or ""
-    vals = re.findall(r"L[bi](\d+)E", targs)
-    return base + ("<" + ",".join(vals) + ">" if vals else "")
+    vals = re.findall(r"L[bi](\d+)E", m.group(3) or "")
+    return m.group(1) + ("<" + ",".join(vals) + ">" if vals else "")
 
 
 def load(path):

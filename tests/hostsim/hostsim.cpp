@@ -174,6 +174,8 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         const bool lc = s->d.abvh_root >= 0;
                         float4 rec[3 * RT_MAX_BOUNCES];
                         PathState st;
+                        CandList cands;
+                        st.cl = cands.v;
                         path_begin(st, ray, rng, 0u, p->max_bounces);
                         st.recs = nullptr; st.wf_rec = rec; st.wf_stride = 1;
                         V3 c = v3(0.f);
@@ -209,6 +211,8 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         const bool lc = (p->variant & 0xFF) == 5 && s->d.abvh_root >= 0 && s->d.n_lights > 0;   // as rt_render_device selects
                         const bool accel = (p->variant & 0xFF) == 3 || ((p->variant & 0xFF) == 5 && !lc);
                         PathState st;
+                        CandList cands;
+                        st.cl = cands.v;
                         PathRecs recs;
                         path_begin(st, ray, rng, 0u, p->max_bounces);
                         st.recs = &recs;

@@ -1997,17 +1997,13 @@ RT_HD V3 path_fold(const PathState &st, V3 tail) {
 }
 
 // next soft-shadow sample of light st.light (Scene.h:325-330)
-#ifndef RT_OPT_INLINE_SAMPLE
-#define RT_OPT_INLINE_SAMPLE 0
-#endif
+// The wavefront's light kernels (WF) INLINE this and the bounce step below; the state-machine kernels call shared
+// out-of-line copies. Measured (profiles/r02_notes.md, r02n): once nothing else pins the path state in local memory (ray by
+// value, candidate list out of the struct), inlining lets the wavefront keep it in registers / spill slots: config 2
+// 10.8 -> 10.5 ms, config 5 63.3 -> 62.4; the state-machine kernel of config 3, whose hot code is twice as long, loses 1.4 %
+// the same way and keeps the calls. (Round 1 measured the inlined sample neutral to slower: the state was pinned then.)
 template <bool STATS>
-#if RT_OPT_INLINE_SAMPLE && defined(__CUDACC__)
-__device__ __forceinline__
-#else
-RT_COLD
-#endif
-void path_shadow_sample(const DScene &s_, PathState &st, Counters *cnt) {
-    const DScene &s = RT_S(s_);
+RT_HD void path_shadow_sample_body(const DScene &s, PathState &st, Counters *cnt) {
     if (STATS) cnt->rnd += 3;
     const V3 lp = ld3(s.lights[st.light].pos);
     const float delta = s.lights[st.light].radius / 2.f;
@@ -2018,19 +2014,25 @@ void path_shadow_sample(const DScene &s_, PathState &st, Counters *cnt) {
     st.ray = make_ray(st.P + Lj * RT_EPSF, Lj, time);
     st.mode = 1;
 }
+template <bool STATS>
+RT_COLD void path_shadow_sample_shared(const DScene &s_, PathState &st, Counters *cnt) { path_shadow_sample_body<STATS>(RT_S(s_), st, cnt); }
+template <bool STATS, bool WF = false>
+RT_HD void path_shadow_sample(const DScene &s, PathState &st, Counters *cnt) {
+    if (WF) path_shadow_sample_body<STATS>(s, st, cnt);
+    else path_shadow_sample_shared<STATS>(s, st, cnt);
+}
 
 // Start lighting with light st.light, or — when the lights are exhausted — scatter and continue.
 // Returns true when the path has ended (result in `out`).
-template <bool STATS, bool LC = false, bool WF = false>
-RT_SHARED_BOUNCE bool path_next_light_or_bounce(const DScene &s_, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
-    const DScene &s = RT_S(s_);
+template <bool STATS, bool LC, bool WF>
+RT_HD bool path_next_light_or_bounce_body(const DScene &s, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
     if (st.light < s.n_lights) {
         const V3 L = normalized(ld3(s.lights[st.light].pos) - st.P);
         const float dotLN = dot(L, st.n);
         st.color = st.color + (comp_product(ld3(s.lights[0].color), st.kd) * fmaxr(0.0f, dotLN)) * (float)(1. - (double)st.mat->transparency);
         st.j = 0; st.blocked = 0;
         if (LC) { st.mode = 3; return false; }   // variant 5: first collect the occluder candidates of this light
-        path_shadow_sample<STATS>(s, st, cnt);
+        path_shadow_sample<STATS, WF>(s, st, cnt);
         return false;
     }
     Ray in; in.o = st.P; in.d = st.in_d; in.time = st.ray.time;
@@ -2047,6 +2049,15 @@ RT_SHARED_BOUNCE bool path_next_light_or_bounce(const DScene &s_, PathState &st,
     if (st.N == 0) { out = path_fold<WF>(st, v3(0.f)); st.mode = 2; return true; }
     st.mode = 0;
     return false;
+}
+template <bool STATS, bool LC>
+RT_SHARED_BOUNCE bool path_next_light_or_bounce_shared(const DScene &s_, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
+    return path_next_light_or_bounce_body<STATS, LC, false>(RT_S(s_), st, nb_ech, out, cnt);
+}
+template <bool STATS, bool LC = false, bool WF = false>
+RT_HD bool path_next_light_or_bounce(const DScene &s, PathState &st, int nb_ech, V3 &out, Counters *cnt) {
+    if (WF) return path_next_light_or_bounce_body<STATS, LC, true>(s, st, nb_ech, out, cnt);
+    return path_next_light_or_bounce_shared<STATS, LC>(s, st, nb_ech, out, cnt);
 }
 
 // Shade the closest hit of st.ray (Scene.h:270-304): on a miss the path ends (true, result in `out`); otherwise the
@@ -2123,12 +2134,12 @@ RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, 
             ++st.light;
             return path_next_light_or_bounce<STATS, LC, WF>(s, st, nb_ech, out, cnt);
         }
-        path_shadow_sample<STATS>(s, st, cnt);   // first sample
+        path_shadow_sample<STATS, WF>(s, st, cnt);   // first sample
         return false;
     }
     if (st.mode == 1) {
         if (blocked) ++st.blocked;
-        if (++st.j < nb_ech) { path_shadow_sample<STATS>(s, st, cnt); return false; }
+        if (++st.j < nb_ech) { path_shadow_sample<STATS, WF>(s, st, cnt); return false; }
         return path_finish_light<STATS, LC, WF>(s, st, nb_ech, out, cnt);
     }
     // mode 0

@@ -380,3 +380,63 @@ def test_wavefront_block_sizes_and_chunking_do_not_change_a_bit(gpu, assets, nam
                 assert np.array_equal(bits(want["linear"]), bits(got["linear"])), (name, log2, st, v)
                 for k in ("n_closest_rays", "n_shadow_rays") + (("n_random", "n_tex_fetches") if st else ()):
                     assert want["stats"][k] == got["stats"][k], (name, log2, st, v, k)
+
+
+# ---- constant-bank scene binding, device image cache ----------------------------------------------------------------------
+def test_scenes_alternating_on_one_device_and_two_streams_keep_their_own_constants(gpu, assets):
+    """The kernels read the scene descriptor from ONE constant-bank copy per device (rt_core.cuh : c_scene); every render binds
+    its scene on its own stream and waits for the previous binding's event. Two scenes rendered alternately, and two scenes
+    enqueued back to back on two different streams without a host synchronisation in between, must each give the bits of
+    their solo render."""
+    torch = pytest.importorskip("torch")
+    w, h, spp = 160, 90, 2
+    names = ["random_spheres", "cornell_box", "flamingo_pond"]
+    scenes = [gpu.Scene(n, aspect=w / h, seed=0) for n in names]
+    solo = [s.render(w, h, spp, seed=5)["linear"] for s in scenes]
+    for rep in range(3):
+        for s, want in zip(scenes, solo):
+            assert np.array_equal(bits(s.render(w, h, spp, seed=5)["linear"]), bits(want))
+    cam = gpu.default_camera(w, h)
+    p = gpu.render_params(w, h, spp, seed=5)
+    streams = [torch.cuda.Stream() for _ in scenes]
+    imgs = [torch.zeros(h * w * 3, dtype=torch.float32, device="cuda:0") for _ in scenes]
+    for rep in range(3):
+        for s, st, img in zip(scenes, streams, imgs):
+            rc = gpu.rt.rt_render_device_image(s.device_handle(0), C.byref(cam), C.byref(p), None, img.data_ptr(), st.cuda_stream, None)
+            assert rc == 0, gpu.rt.rt_last_error()
+        torch.cuda.synchronize()
+        for img, want in zip(imgs, solo):
+            assert np.array_equal(bits(img.cpu().numpy().reshape(h, w, 3)), bits(want))
+
+
+def test_device_image_cache_skips_resident_images_and_release_frees_them(gpu, assets):
+    """RtImage::content_id (ABI 3): a re-upload of the Cornell box (5 images, 8.4 MB) copies only its small arrays; the same
+    description with the ids zeroed copies everything; after rt_release_cached_memory the images travel again. Same pixels
+    every time."""
+    w, h, spp = 120, 68, 2
+    s = gpu.Scene("cornell_box", aspect=w / h)
+    want = s.render(w, h, spp, seed=1)["linear"]
+    first = s.h2d_bytes(0)
+    s.invalidate_device()
+    again = s.render(w, h, spp, seed=1)["linear"]
+    second = s.h2d_bytes(0)
+    assert np.array_equal(bits(want), bits(again))
+    assert first > 8_000_000 and second < 200_000 and s.device_bytes(0) > 8_000_000, (first, second)   # every Scene object loads (and numbers) its own files
+    # ids zeroed: "contents unknown", every image is uploaded
+    d = s.flatten().contents
+    keep = [(d.textures[i].content_id) for i in range(d.n_textures)] + [(d.normal_maps[i].content_id) for i in range(d.n_normal_maps)]
+    assert all(k != 0 for k in keep)
+    for i in range(d.n_textures):
+        d.textures[i].content_id = 0
+    for i in range(d.n_normal_maps):
+        d.normal_maps[i].content_id = 0
+    out = C.c_void_p()
+    assert gpu.rt.rt_scene_create(C.byref(d), 0, C.byref(out)) == 0, gpu.rt.rt_last_error()
+    assert int(gpu.rt.rt_scene_h2d_bytes(out)) > 8_000_000
+    gpu.rt.rt_scene_destroy(out)
+    # released: the next upload copies the images again
+    s.invalidate_device()
+    assert gpu.rt.rt_release_cached_memory(0) == 0
+    third = s.render(w, h, spp, seed=1)["linear"]
+    assert np.array_equal(bits(want), bits(third))
+    assert s.h2d_bytes(0) > 8_000_000

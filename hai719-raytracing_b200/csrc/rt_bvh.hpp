@@ -41,6 +41,10 @@ struct Accel {
     std::vector<float4> nodes;
     std::vector<uint32_t> tris;          // representative (first) leaf-ref index of each distinct triangle, in BVH leaf order
     std::vector<int32_t> mesh_root;      // per mesh: root node index, -1 = no hierarchy
+    // the same hierarchy with 4-wide nodes (collapse4 below), 8 float4 per node: lo.x lo.y lo.z hi.x hi.y hi.z of the four
+    // children (one float4 per coordinate), their codes, one spare; unused slots have an inverted box and an empty leaf
+    std::vector<float4> nodes4;
+    std::vector<int32_t> mesh_root4;     // per mesh: root node index in nodes4, -1 = no hierarchy
     // per mesh: range of `tris` holding the triangles that are tested for EVERY ray (barycentric test too
     // ill-conditioned to bound the region it accepts, see build_accel)
     std::vector<uint32_t> always_first, always_count;
@@ -156,6 +160,57 @@ inline int32_t build(std::vector<Prim> &prims, size_t begin, size_t end, A &out,
 }
 }  // namespace bvh_detail
 
+// Collapse a binary subtree (child code `code` of Accel::nodes) into 4-wide nodes: a node adopts its two children, then
+// replaces the inner child with the largest box by that child's two children until it has four (or only leaves are left).
+// Returns the code of the subtree in nodes4 (>= 0 node index, < 0 the same leaf code); depth = levels of 4-wide nodes.
+inline int32_t collapse4(const std::vector<float4> &bin, int32_t code, std::vector<float4> &out4, int depth, int &max_depth) {
+    if (code < 0) return code;
+    max_depth = std::max(max_depth, depth + 1);
+    struct Child { int32_t code; float lo[3], hi[3]; };
+    auto children = [&](int32_t n, Child &c0, Child &c1) {
+        const float4 a = bin[4 * (size_t)n], b = bin[4 * (size_t)n + 1], c = bin[4 * (size_t)n + 2], k = bin[4 * (size_t)n + 3];
+        c0.lo[0] = a.x; c0.lo[1] = a.y; c0.lo[2] = a.z; c0.hi[0] = a.w; c0.hi[1] = b.x; c0.hi[2] = b.y;
+        c1.lo[0] = b.z; c1.lo[1] = b.w; c1.lo[2] = c.x; c1.hi[0] = c.y; c1.hi[1] = c.z; c1.hi[2] = c.w;
+        c0.code = (int32_t)f2u(k.x); c1.code = (int32_t)f2u(k.y);
+    };
+    auto area = [](const Child &c) {
+        const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2];
+        return (dx < 0 || dy < 0 || dz < 0) ? -1.f : dx * dy + dy * dz + dz * dx;
+    };
+    Child ch[4];
+    int n = 2;
+    children(code, ch[0], ch[1]);
+    while (n < 4) {
+        int best = -1;
+        for (int i = 0; i < n; ++i) if (ch[i].code >= 0 && (best < 0 || area(ch[i]) > area(ch[best]))) best = i;
+        if (best < 0) break;
+        Child a, b;
+        children(ch[best].code, a, b);
+        ch[best] = a;
+        ch[n++] = b;
+    }
+    const size_t id = out4.size() / 8;
+    out4.resize(out4.size() + 8);
+    float lo[3][4], hi[3][4];
+    int32_t codes[4];
+    for (int i = 0; i < 4; ++i) {
+        if (i < n) {
+            for (int a = 0; a < 3; ++a) { lo[a][i] = ch[i].lo[a]; hi[a][i] = ch[i].hi[a]; }
+            codes[i] = collapse4(bin, ch[i].code, out4, depth + 1, max_depth);
+        } else {
+            for (int a = 0; a < 3; ++a) { lo[a][i] = FLT_MAX; hi[a][i] = -FLT_MAX; }
+            codes[i] = bvh_detail::leaf_code(0, 0);
+        }
+    }
+    for (int a = 0; a < 3; ++a) {
+        out4[8 * id + a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
+        out4[8 * id + 3 + a] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
+    }
+    out4[8 * id + 6] = make_float4(u2f((uint32_t)codes[0]), u2f((uint32_t)codes[1]), u2f((uint32_t)codes[2]), u2f((uint32_t)codes[3]));
+    out4[8 * id + 7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return (int32_t)id;
+}
+
 inline void build_accel(const RtSceneDesc &d, const PackedMeshes &pk, Accel &out) {
     using namespace bvh_detail;
     out = Accel();
@@ -242,7 +297,7 @@ inline void build_accel(const RtSceneDesc &d, const PackedMeshes &pk, Accel &out
         out.always_first.push_back((uint32_t)out.tris.size());
         out.always_count.push_back((uint32_t)always.size());
         out.tris.insert(out.tris.end(), always.begin(), always.end());
-        if (prims.empty()) { out.mesh_root.push_back(-1); continue; }
+        if (prims.empty()) { out.mesh_root.push_back(-1); out.mesh_root4.push_back(-1); continue; }
         const size_t nodes_mark = out.nodes.size(), tris_mark = out.tris.size();
         int max_depth = 0;
         int32_t root = build(prims, 0, prims.size(), out, false, 0, max_depth, RT_BVH_LEAF_TRIS);
@@ -263,6 +318,13 @@ inline void build_accel(const RtSceneDesc &d, const PackedMeshes &pk, Accel &out
             out.nodes.push_back(make_float4(FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX));
             out.nodes.push_back(make_float4(u2f((uint32_t)root), u2f((uint32_t)leaf_code(0, 0)), 0.f, 0.f));
             out.mesh_root.push_back((int32_t)id);
+        }
+        {   // 4-wide copy of this mesh's hierarchy; the walk pushes up to three children per level on a 64-entry stack
+            const size_t mark4 = out.nodes4.size();
+            int depth4 = 0;
+            int32_t r4 = collapse4(out.nodes, out.mesh_root.back(), out.nodes4, 0, depth4);
+            if (3 * depth4 > 60) { out.nodes4.resize(mark4); r4 = -1; }   // deeper than the stack allows: this mesh keeps the binary walk
+            out.mesh_root4.push_back(r4);
         }
     }
 }

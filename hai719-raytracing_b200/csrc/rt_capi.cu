@@ -1628,6 +1628,7 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
         Accel ac;
         build_accel(*desc, pk, ac);
         if ((rc = dev_upload(s, ac.nodes.data(), ac.nodes.size(), &d.bvh_nodes))) return rc;
+        if ((rc = dev_upload(s, ac.nodes4.data(), ac.nodes4.size(), &d.bvh4_nodes))) return rc;
         if ((rc = dev_upload(s, ac.tris.data(), ac.tris.size(), &d.bvh_tris))) return rc;
         if ((rc = dev_upload(s, ac.ref_next.data(), ac.ref_next.size(), &d.ref_next))) return rc;
         if ((rc = dev_upload(s, ac.ref_leaf.data(), ac.ref_leaf.size(), &d.ref_leaf))) return rc;
@@ -1642,7 +1643,7 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
             memset(&o, 0, sizeof o);
             o.node_begin = pk.node_begin[i];
             o.node_end = pk.node_end[i];
-            o.bvh_root = ac.mesh_root[i]; o.always_first = ac.always_first[i]; o.always_count = ac.always_count[i];
+            o.bvh_root = ac.mesh_root[i]; o.bvh4_root = ac.mesh_root4[i]; o.always_first = ac.always_first[i]; o.always_count = ac.always_count[i];
             o.color_type = src.color_type;
             if ((rc = dev_upload(s, src.triangles, (size_t)3 * src.n_triangles, &o.triangles))) return rc;
             if (src.color_type == RT_COLOR_VERTEX && (rc = dev_upload(s, src.vert_colors, (size_t)3 * src.n_vertices, &o.vert_colors))) return rc;

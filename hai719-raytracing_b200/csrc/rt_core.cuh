@@ -216,6 +216,7 @@ struct DSquare {            // per-square constants of Square::intersect hoisted
 struct DMesh {
     uint32_t node_begin, node_end;
     int bvh_root;              // variant 3 (rt_bvh.hpp): root of this mesh's culling BVH, -1 = none
+    int bvh4_root;             // the same hierarchy with 4-wide nodes (DScene::bvh4_nodes), -1 = none: walk the binary one
     uint32_t always_first, always_count;   // range of bvh_tris tested for every ray (ill-conditioned triangles)
     int color_type;
     const float *vert_colors, *face_colors;
@@ -237,6 +238,7 @@ struct DScene {
     const float2 *tri_den;     // per leaf ref: {denom, bits(tri_index within its mesh)}
     // exact culling structure of variant 3 (rt_bvh.hpp)
     const float4 *bvh_nodes;   // 4 per node
+    const float4 *bvh4_nodes;  // 8 per node: lo.x lo.y lo.z hi.x hi.y hi.z of the four children, their codes, spare (rt_bvh.hpp : collapse4)
     const uint32_t *bvh_tris;  // representative leaf ref per distinct triangle, BVH leaf order
     const uint32_t *ref_next, *ref_leaf, *node_parent;
     // culling hierarchy over spheres + squares (rt_bvh.hpp : build_analytic_accel); abvh_root < 0 = linear loops
@@ -801,6 +803,35 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
             else if (h1) node = c1; \
             else node = sp > 0 ? stack.get(--sp) : MESH_END; \
         }
+// The same descent over 4-wide nodes (RT_OPT_BVH4): four box tests per step, the children that are hit sorted by entry
+// parameter with a five-comparator network, the nearest taken, the others pushed far to near. Half the dependent steps of
+// the binary walk for about the same number of box tests.
+#ifndef RT_OPT_BVH4
+#define RT_OPT_BVH4 0
+#endif
+#define RT_CSWAP4(KA, CA, KB, CB) { const bool sw_ = KB < KA; const float tk_ = sw_ ? KB : KA; const int tc_ = sw_ ? CB : CA; KB = sw_ ? KA : KB; CB = sw_ ? CA : CB; KA = tk_; CA = tc_; }
+#define RT_WALK_DESCEND4() \
+        while ((unsigned int)node < (unsigned int)MESH_END) { \
+            const float4 *nb = s.bvh4_nodes + 8 * node; \
+            const float4 lx = RT_LDG(nb), ly = RT_LDG(nb + 1), lz = RT_LDG(nb + 2), hx = RT_LDG(nb + 3), hy = RT_LDG(nb + 4), hz = RT_LDG(nb + 5), cc = RT_LDG(nb + 6); \
+            if (STATS) cnt->node++; \
+            float k0, k1, k2, k3; \
+            const bool h0 = bvh_box(ray, iv, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, best_t, k0); \
+            const bool h1 = bvh_box(ray, iv, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, best_t, k1); \
+            const bool h2 = bvh_box(ray, iv, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, best_t, k2); \
+            const bool h3 = bvh_box(ray, iv, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, best_t, k3); \
+            int c0 = (int)f2u(cc.x), c1 = (int)f2u(cc.y), c2 = (int)f2u(cc.z), c3 = (int)f2u(cc.w); \
+            k0 = h0 ? k0 : FLT_MAX; k1 = h1 ? k1 : FLT_MAX; k2 = h2 ? k2 : FLT_MAX; k3 = h3 ? k3 : FLT_MAX; \
+            const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3; \
+            RT_CSWAP4(k0, c0, k1, c1) RT_CSWAP4(k2, c2, k3, c3) RT_CSWAP4(k0, c0, k2, c2) RT_CSWAP4(k1, c1, k3, c3) RT_CSWAP4(k1, c1, k2, c2) \
+            if (nh == 0) { node = sp > 0 ? stack.get(--sp) : MESH_END; } \
+            else { \
+                if (nh > 3) stack.put(sp++, c3); \
+                if (nh > 2) stack.put(sp++, c2); \
+                if (nh > 1) stack.put(sp++, c1); \
+                node = c0; \
+            } \
+        }
 template <bool STATS>
 RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rng, Hit &h, bool &blocked, bool &done, Counters *cnt) {
     if (done || s.n_meshes <= 0) return;
@@ -811,13 +842,22 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
     int sp = 0, mi = 0;
     // the always-tested triangles of a mesh come first, like a leaf
     uint32_t k = s.meshes[0].always_first, kend = k + s.meshes[0].always_count;
+#if RT_OPT_BVH4
+    bool wide = s.meshes[0].bvh4_root >= 0;
+    int node = wide ? s.meshes[0].bvh4_root : (s.meshes[0].bvh_root >= 0 ? s.meshes[0].bvh_root : MESH_END);
+#else
     int node = s.meshes[0].bvh_root >= 0 ? s.meshes[0].bvh_root : MESH_END;
+#endif
     float best_t = h.t;
     uint32_t best_ref = NONE;
     if (STATS) cnt->mesh++;
     for (;;) {
         for (; k < kend; ++k) bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+#if RT_OPT_BVH4
+        if (wide) { RT_WALK_DESCEND4() } else { RT_WALK_DESCEND() }
+#else
         RT_WALK_DESCEND()
+#endif
         if (node < 0) {   // a leaf: its triangles are tested at the top of the next round
             const uint32_t code = (uint32_t)(-(node + 1));
             k = code >> 3; kend = k + (code & 7u);
@@ -833,13 +873,20 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
         const DMesh &m = s.meshes[mi];
         if (STATS) cnt->mesh++;
         k = m.always_first; kend = k + m.always_count;
+#if RT_OPT_BVH4
+        wide = m.bvh4_root >= 0;
+        node = wide ? m.bvh4_root : (m.bvh_root >= 0 ? m.bvh_root : MESH_END);
+#else
         node = m.bvh_root >= 0 ? m.bvh_root : MESH_END;
+#endif
         sp = 0;
         best_t = h.t; best_ref = NONE;
     }
 }
 
 #undef RT_WALK_DESCEND
+#undef RT_WALK_DESCEND4
+#undef RT_CSWAP4
 
 // Can meshes_walk_merged find anything for this ray below `limit`? Only if some mesh has always-tested triangles or the ray
 // passes the FIRST step of a mesh's walk (one of the two boxes of its root node, same conservative test, same limit):

@@ -103,14 +103,14 @@ void *sim_scene_create(const RtSceneDesc *desc) {
     const uint32_t nm = desc->n_meshes;
     if (!pack_meshes(*desc, s->pk).empty()) { delete s; return nullptr; }
     build_accel(*desc, s->pk, s->ac);
-    d.bvh_nodes = s->ac.nodes.data(); d.bvh_tris = s->ac.tris.data();
+    d.bvh_nodes = s->ac.nodes.data(); d.bvh4_nodes = s->ac.nodes4.data(); d.bvh_tris = s->ac.tris.data();
     d.ref_next = s->ac.ref_next.data(); d.ref_leaf = s->ac.ref_leaf.data(); d.node_parent = s->ac.node_parent.data();
     for (uint32_t i = 0; i < nm; ++i) {
         const RtSceneMesh &src = desc->meshes[i];
         DMesh o;
         memset(&o, 0, sizeof o);
         o.node_begin = s->pk.node_begin[i]; o.node_end = s->pk.node_end[i]; o.color_type = src.color_type;
-        o.bvh_root = s->ac.mesh_root[i]; o.always_first = s->ac.always_first[i]; o.always_count = s->ac.always_count[i];
+        o.bvh_root = s->ac.mesh_root[i]; o.bvh4_root = s->ac.mesh_root4[i]; o.always_first = s->ac.always_first[i]; o.always_count = s->ac.always_count[i];
         for (uint32_t k = 0; k < src.n_leaf_refs; ++k) {
             const RtTriRef &r = src.leaf_refs[k];
             const TriConst c = precompute_triangle(ld3(src.positions + 3 * r.v[0]), ld3(src.positions + 3 * r.v[1]), ld3(src.positions + 3 * r.v[2]), r.tri_index);

@@ -42,6 +42,13 @@ def sim_fma(hb):
     return _load_sim(hb, "libhostsim_fma.so", ["-DRT_OPT_BOXFMA=1", "-DRT_OPT_CONEFMA=1"])
 
 
+@pytest.fixture(scope="module")
+def sim_bvh4(hb):
+    """The mesh walk over the 4-wide copy of the culling hierarchies (RT_OPT_BVH4): another shape of the same
+    conservative filter, so the same bits."""
+    return _load_sim(hb, "libhostsim_bvh4.so", ["-DRT_OPT_BVH4=1"])
+
+
 def _check_against_oracle(hb, ref, sim, name, variant):
     W, H, SPP = 64, 36, 2
     a = ref.scene(name, aspect=W / H)
@@ -72,3 +79,9 @@ def test_fma_box_tests_keep_the_bits(hb, ref, assets, sim_fma, name, variant):
 @pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_core_functions_on_cpu_match_oracle(hb, ref, assets, sim, name, variant):
     _check_against_oracle(hb, ref, sim, name, variant)
+
+
+@pytest.mark.parametrize("name", ["flamingo_pond", "backrooms_pool", "config5", "raccoon", "mesh"])
+@pytest.mark.parametrize("variant", [3, 6])
+def test_four_wide_mesh_walk_keeps_the_bits(hb, ref, assets, sim_bvh4, name, variant):
+    _check_against_oracle(hb, ref, sim_bvh4, name, variant)

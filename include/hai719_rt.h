@@ -167,7 +167,8 @@ typedef struct RtRenderParams {
     uint32_t seed;               /* deterministic stream, see "Random numbers" below                 */
     int32_t x0, y0, x1, y1;      /* pixel rectangle to render; all 0 = whole image                   */
     /* tile sharding: the rectangle is cut into tile_w x tile_h tiles, numbered row-major; this
-     * call renders the tiles t with t % n_ranks == rank. n_ranks <= 1 renders everything.         */
+     * call renders the tiles (tx, ty) of the tile grid with (tx + K * ty) % n_ranks == rank, K = 3 (5 if 3 divides
+     * n_ranks, 1 if 15 does): round-robin along rows, rows shifted against each other. n_ranks <= 1 renders everything. */
     int32_t rank, n_ranks;
     int32_t tile_w, tile_h;      /* 0 = default 32 x 32                                              */
     int32_t collect_stats;       /* fill the work counters of RtStats (slower)                       */
@@ -287,7 +288,7 @@ int rt_render_device_image(RtScene *scene, const RtCamera *camera, const RtRende
 
 /* Multi-GPU render in ONE call — what replaces the thread-per-scanline block of ray_trace_from_camera()
  * (main.cpp:229-238) on a box with several B200s. scenes[0..n-1] are the same scene uploaded to n DISTINCT devices;
- * one host thread per device renders the tiles t with t % n == i (params->rank / n_ranks must be unset) and its
+ * one host thread per device renders the tiles with (tx + K * ty) % n == i (params->rank / n_ranks must be unset) and its
  * resolve kernel stores them directly into the framebuffer on scenes[0]'s device through peer-mapped memory.
  * rt_render_multi copies that framebuffer to the HOST buffers (either may be NULL), like rt_render;
  * rt_render_multi_device leaves it in the device buffers given (on scenes[0]'s device, row-major rectangle).

@@ -9,3 +9,7 @@ for l in 25 26; do
   done
 done
 cat gpurun_out/r02t/chunk.log
+# config 1: kernel variants and CTAs per SM of k_render_paths, three decimals
+for args in "c1 1 1 2 3 6"; do timeout 300 python tools/variance_probe.py $args 2>&1 | grep "^upload 1" >> gpurun_out/r02t/c1.log; done
+bash scripts/gpu_ab.sh r02t/ab_paths "default paths6 paths8" "c1 1 0"
+cat gpurun_out/r02t/c1.log gpurun_out/r02t/ab_paths.log

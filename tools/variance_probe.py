@@ -13,5 +13,5 @@ for rep in range(3):
         ts = []
         for i in range(4):
             ts.append(s.render(w, h, spp, seed=0, want_linear=False, variant=v)["stats"]["kernel_ms"])
-        print("upload %d variant %6d kernel_ms %s" % (rep, v, " ".join("%.1f" % t for t in ts)), flush=True)
+        print("upload %d variant %6d kernel_ms %s" % (rep, v, " ".join(("%.3f" if max(ts) < 5 else "%.1f") % t for t in ts)), flush=True)
     s.invalidate_device()

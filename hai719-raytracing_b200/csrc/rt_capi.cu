@@ -368,13 +368,6 @@ struct WfArgs {
     float4 *park0, *park1;             // ... and what phase B needs besides the hit record, by hit-queue position:
     float4 *park2;                     //     {colour so far, light | (cl_n + 1) << 8}, {cm0..cm3}, RT_LC_MAXC / 4 planes of candidate triangles
     unsigned long long park_stride;
-    // speculative samples for the overflow queue (k_wf_spec_trace / k_wf_spec_validate below), by hit-queue position
-    unsigned int *sp_hdr;              // samples validated so far | blocked so far << 8 | guessed draws per sample << 16
-    unsigned short *sp_res;            // per sample: draws it consumed | blocked << 15
-    const unsigned int *sp_q_in; const unsigned int *sp_len_in;   // this round's hits (hit-queue positions, padded) and the queue's length
-    unsigned int *sp_head, *sp_vhead;  // work-fetch heads of the round's two kernels
-    unsigned int *sp_q_out, *sp_len_out;   // hits with samples left after this round
-    int sp_enabled;
     unsigned int *ctr;                 // WF_NCTR counters per level
     float *samples;
     unsigned long long *stats;
@@ -479,9 +472,6 @@ __device__ __forceinline__ void wf_count_entries(unsigned int *entries, const un
 
 #ifndef RT_WF_MINB
 #define RT_WF_MINB 8
-#endif
-#ifndef RT_SPEC_ROUNDS_DEFAULT
-#define RT_SPEC_ROUNDS_DEFAULT 0   /* speculative-sample rounds for the overflow queue when the variant does not say (see rt_render_device) */
 #endif
 __device__ __forceinline__ void wf_state_init(PathState &st, CandList &cands, const WfArgs &w) {
     st.cl = cands.v;
@@ -695,16 +685,8 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 }
                 st.cm0 = f2u(p1.x); st.cm1 = f2u(p1.y); st.cm2 = f2u(p1.z); st.cm3 = f2u(p1.w);
                 st.j = 0; st.blocked = 0; st.mode = 3;
-                if (w.sp_enabled && w.which_park == 1) {   // samples 0 .. j-1 of the parked light were traced speculatively and validated
-                    const unsigned int hdr = w.sp_hdr[hp];
-                    st.j = (int)(hdr & 0xFFu); st.blocked = (int)((hdr >> 8) & 0xFFu);
-                }
-                if (st.j >= w.nb_ech) {
-                    fin = path_finish_light<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
-                } else {
-                    path_shadow_sample<STATS, true>(scene, st, &cnt);   // candidates known: the next sample
-                    fin = false;
-                }
+                Hit h; h.type = 0; h.obj = -1; h.t = 0.f; h.ref = 0;
+                fin = path_advance<STATS, LC, true>(scene, st, h, 0.f, 0.f, false, w.nb_ech, c, &cnt);   // candidates known: first sample
             } else {
                 st.color = v3(0.f); st.light = 0; st.mode = 0;
                 fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
@@ -741,7 +723,6 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                     WF_ST(w.park2 + (size_t)q4 * w.park_stride + hp, make_float4(u2f(st.cl[4 * q4]), u2f(st.cl[4 * q4 + 1]), u2f(st.cl[4 * q4 + 2]), u2f(st.cl[4 * q4 + 3])));
                 WF_ST(w.park1 + hp, make_float4(u2f(st.cm0), u2f(st.cm1), u2f(st.cm2), u2f(st.cm3)));
                 WF_ST(w.rng_hit + hp, make_uint2(st.rng.key, st.rng.ctr));
-                if (PHASE == 1 && w.sp_enabled && st.cl_n < 0) w.sp_hdr[hp] = 3u << 16;   // nothing validated yet; guess: unoccluded samples, 3 draws each
             } else if (fin) {
                 float *o = w.samples + 3ull * st.path;
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
@@ -757,129 +738,6 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
     }
     if (PHASE != 2) wf_count_entries(w.ctr + WF_NCTR * w.level + 9, ws);   // hits of this level
     if (STATS) flush_counters(cnt, w.stats);
-}
-
-// ---- speculative shadow samples for the overflow queue -------------------------------------------------------------------
-// The NB_ECH soft-shadow samples of one (hit, light) are SEQUENTIAL in the reference: sample j+1 draws its direction from the
-// stream position sample j left behind, and a sample consumes 3 draws plus one per candidate occluder it hits until one
-// blocks (Scene.h:325-330, 235-255). Hits whose candidate-triangle list overflowed walk the mesh hierarchies for every
-// sample, one lane per hit, ten walks in a row next to 31 lanes doing the same for unrelated hits: 2-8 of 32 lanes active
-// (config 5, profiles/r02_notes.md). But a sample is a pure function of (hit, light, stream position), and the position is
-// predictable — an unoccluded sample consumes exactly 3 draws, one blocked by the first opaque thing it meets exactly 4 — so
-// these samples are traced IN PARALLEL, one lane per (hit, sample j), from the GUESSED position base + (j - j0) * guess,
-// adjacent lanes holding the samples of one hit: ten nearly identical rays from one point, which walk in lockstep.
-// k_wf_spec_validate then checks the guesses in order: sample j is valid iff the draws consumed by the validated samples
-// before it add up to its guessed offset. The validated prefix advances the stream, the blocked count and the guess (the draws
-// the last valid sample consumed); hits with samples left go round again, and whatever is left after the last round is
-// finished by the sequential sample kernel, which resumes at sample j0. Bit-identical by construction: only samples traced
-// from the reference's own stream position are ever used. (Round 2 first applied this to ALL parked hits and lost 20-30 %:
-// a list-testing sample costs the same in either kernel. The overflow queue is where the walks dominate.)
-template <bool STATS>
-__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_spec_trace(const DScene scene_, const WfArgs w) {
-    const DScene &scene = RT_S(scene_);
-    stage_abvh(scene);
-    Counters cnt;
-    if (STATS) memset(&cnt, 0, sizeof cnt);
-    const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int nb = (unsigned int)w.nb_ech;
-    const unsigned long long total = (unsigned long long)(*w.sp_len_in) * nb;
-    const unsigned int count = total > 0xFFFFFFE0ull ? 0xFFFFFFE0u : (unsigned int)total;   // beyond 2^32 items the rest stays sequential
-    __shared__ unsigned int wq_all[4][WQ_WORDS];
-    unsigned int *const ws = wq_init(wq_all);
-    for (;;) {
-        unsigned int base;
-        if (!wf_next_batch(w.sp_head, count, 4u, ws, base)) break;
-        const unsigned int i = base + lane;
-        PathState st;
-        CandList cands;
-        wf_state_init(st, cands, w);
-        bool active = i < count;
-        unsigned int hp = 0, j = 0, start = 0;
-        if (active) {
-            const unsigned int e = i / nb;
-            j = i - e * nb;
-            hp = WF_LD(w.sp_q_in + e);
-            active = hp != WF_INVALID;
-        }
-        if (active) {
-            const unsigned int hdr = w.sp_hdr[hp];
-            const unsigned int j0 = hdr & 0xFFu, guess = hdr >> 16;
-            active = j >= j0;   // earlier samples are validated already
-            if (active) {
-                const float4 h0 = __ldg(w.hit0 + hp);
-                const uint2 g = __ldg(w.rng_hit + hp);
-                const float4 p0 = __ldg(w.park0 + hp), p1 = __ldg(w.park1 + hp);
-                st.P = v3(h0.x, h0.y, h0.z); st.ray.time = h0.w;
-                st.light = (int)(f2u(p0.w) & 0xFFu); st.cl_n = -1;
-                st.cm0 = f2u(p1.x); st.cm1 = f2u(p1.y); st.cm2 = f2u(p1.z); st.cm3 = f2u(p1.w);
-                start = g.y + (j - j0) * guess;
-                st.rng.key = g.x; st.rng.ctr = start;
-                st.path = 0; st.N = 0; st.depth = 0; st.j = (int)j; st.blocked = 0;
-                path_shadow_sample<STATS, true>(scene, st, &cnt);
-            }
-        }
-        if (__ballot_sync(0xFFFFFFFFu, active) == 0u) continue;
-        Hit h;
-        float hu = 0.f, hv = 0.f;
-        bool blocked;
-        intersect_lc<STATS>(scene, st, false, active, h, hu, hv, blocked, &cnt);
-        if (active) {
-            const unsigned int consumed = st.rng.ctr - start;
-            w.sp_res[(size_t)hp * nb + j] = (unsigned short)((consumed > 0x7FFFu ? 0x7FFFu : consumed) | (blocked ? 0x8000u : 0u));
-        }
-    }
-    if (STATS) {   // tests really performed (speculation included); rays and draws are counted once, by k_wf_spec_validate
-        cnt.shadow = 0; cnt.rnd = 0;
-        flush_counters(cnt, w.stats);
-    }
-}
-
-// One lane per hit of the round's queue: validate the guesses of the last k_wf_spec_trace in sample order (see above), advance the
-// hit's stream position / blocked count / guess, and queue it for another round if samples are left and something was gained.
-template <bool STATS>
-__global__ void __launch_bounds__(128) k_wf_spec_validate(const WfArgs w) {
-    const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int count = *w.sp_len_in;
-    const unsigned int nb = (unsigned int)w.nb_ech;
-    __shared__ unsigned int wq_all[4][WQ_WORDS];
-    unsigned int *const ws = wq_init(wq_all);
-    unsigned long long n_shadow = 0, n_rnd = 0;
-    for (;;) {
-        unsigned int base;
-        if (!wf_next_batch(w.sp_vhead, count, 8u, ws, base)) break;
-        const unsigned int i = base + lane;
-        bool again = false;
-        unsigned int hp = WF_INVALID;
-        if (i < count) hp = WF_LD(w.sp_q_in + i);
-        if (hp != WF_INVALID) {
-            const unsigned int hdr = w.sp_hdr[hp];
-            const unsigned int j0 = hdr & 0xFFu, guess = hdr >> 16;
-            unsigned int blocked = (hdr >> 8) & 0xFFu, last = guess, off = 0, j = j0;
-            if ((unsigned long long)(i + 1) * nb <= 0xFFFFFFE0ull) {   // this hit's samples were traced
-                for (; j < nb; ++j) {
-                    if ((j - j0) * guess != off) break;
-                    const unsigned int r = w.sp_res[(size_t)hp * nb + j];
-                    const unsigned int consumed = r & 0x7FFFu;
-                    if (consumed == 0x7FFFu) break;   // more draws than the record holds: leave the sample to the sequential kernel
-                    blocked += r >> 15; off += consumed; last = consumed;
-                }
-            }
-            if (j > j0) {
-                uint2 g = w.rng_hit[hp];
-                g.y += off;
-                w.rng_hit[hp] = g;
-                if (STATS) { n_shadow += j - j0; n_rnd += off; }
-            }
-            w.sp_hdr[hp] = j | (blocked << 8) | ((last > 0xFFFFu ? 3u : last) << 16);
-            again = j < nb && j > j0;   // nothing validated = nothing to gain from another round
-        }
-        wf_push(w.sp_q_out, w.sp_len_out, w.block, ws, 0, again, hp);
-    }
-    wf_out_finish(w.sp_q_out, ws, 0);
-    if (STATS) {
-        for (int o = 16; o > 0; o >>= 1) { n_shadow += __shfl_down_sync(0xFFFFFFFFu, n_shadow, o); n_rnd += __shfl_down_sync(0xFFFFFFFFu, n_rnd, o); }
-        if (lane == 0) { if (n_shadow) atomicAdd(w.stats + 1, n_shadow); if (n_rnd) atomicAdd(w.stats + 9, n_rnd); }
-    }
 }
 
 // The light stage of a scene WITHOUT lights (Scene.h:305-342 with an empty light list): colour stays 0, the path scatters
@@ -1113,7 +971,6 @@ struct Scratch {
     unsigned int *pix_xy = nullptr; size_t pix_cap = 0;                                 // per pixel of a chunk (k_pixel_xy)
     // wavefront state (variant 6): 13 float4 planes + 2 rng planes + 4 queues per queue position, and 3 float4 per bounce and path slot
     float4 *wf_f4 = nullptr; uint2 *wf_rng = nullptr; unsigned int *wf_q = nullptr; float4 *wf_rec = nullptr; unsigned int *wf_ctr = nullptr;
-    unsigned int *sp_hdr = nullptr; unsigned short *sp_res = nullptr; unsigned int *sp_q = nullptr; unsigned int *sp_ctr = nullptr; size_t sp_cap = 0; int sp_nb = 0;   // speculative samples (overflow queue)
     size_t wf_cap = 0, wf_pos_cap = 0; int wf_bounces = 0;   // wf_cap: path slots; wf_pos_cap: queue positions (slots + padding of the block reservation)
     unsigned long long *counters = nullptr;   // [0] work counter, [1..10] stats
     TileRec *d_tiles = nullptr; unsigned int *d_tile_off = nullptr; size_t tiles_cap = 0;
@@ -1156,10 +1013,6 @@ struct Scratch {
         if (wf_q) cudaFree(wf_q);
         if (wf_rec) cudaFree(wf_rec);
         if (wf_ctr) cudaFree(wf_ctr);
-        if (sp_hdr) cudaFree(sp_hdr);
-        if (sp_res) cudaFree(sp_res);
-        if (sp_q) cudaFree(sp_q);
-        if (sp_ctr) cudaFree(sp_ctr);
         if (counters) cudaFree(counters);
         if (d_tiles) cudaFree(d_tiles);
         if (d_tile_off) cudaFree(d_tile_off);
@@ -1497,23 +1350,6 @@ int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
     RT_CUDA(cudaMalloc((void **)&s->wf_rec, 3 * (size_t)std::max(1, max_bounces) * paths * sizeof(float4)));
     if (!s->wf_ctr) RT_CUDA(cudaMalloc((void **)&s->wf_ctr, WF_NCTR * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int)));
     s->wf_cap = paths; s->wf_pos_cap = pos; s->wf_bounces = max_bounces;
-    return RT_OK;
-}
-
-#define SP_MAX_ROUNDS 14
-#define SP_NCTR 4   /* per (level, round): [0] trace head, [1] validate head, [2] length of this round's queue, [3] - */
-int ensure_spec(RtScene *s, size_t positions, int nb_ech) {
-    if (positions <= s->sp_cap && nb_ech <= s->sp_nb) return RT_OK;
-    positions = std::max(positions, s->sp_cap); nb_ech = std::max(nb_ech, s->sp_nb);
-    if (s->sp_hdr) cudaFree(s->sp_hdr);
-    if (s->sp_res) cudaFree(s->sp_res);
-    if (s->sp_q) cudaFree(s->sp_q);
-    s->sp_hdr = nullptr; s->sp_res = nullptr; s->sp_q = nullptr; s->sp_cap = 0; s->sp_nb = 0;
-    RT_CUDA(cudaMalloc((void **)&s->sp_hdr, positions * sizeof(unsigned int)));
-    RT_CUDA(cudaMalloc((void **)&s->sp_res, positions * (size_t)nb_ech * sizeof(unsigned short)));
-    RT_CUDA(cudaMalloc((void **)&s->sp_q, 2 * positions * sizeof(unsigned int)));
-    if (!s->sp_ctr) RT_CUDA(cudaMalloc((void **)&s->sp_ctr, (size_t)SP_NCTR * (SP_MAX_ROUNDS + 2) * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int)));
-    s->sp_cap = positions; s->sp_nb = nb_ech;
     return RT_OK;
 }
 
@@ -1890,11 +1726,17 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     const bool wavefront = kind_req == 6 && p->max_bounces > 0;
     // paths per chunk. Wavefront: every kernel of a chunk ends in a tail during which SMs drain, so fewer, larger chunks
     // are faster (config 2, ms per frame at 32 spp: 4 Mi 36.5, 8 Mi 32.9, 16 Mi 31.3, 32 Mi 30.3); 32 Mi paths are ~17 GB
-    // of path state at 6 bounces (~230 B + 48 B per bounce and path), a tenth of the HBM
-    unsigned long long max_paths = wavefront ? (32ull << 20) : (16ull << 20);
+    // of path state at 6 bounces (~230 B + 48 B per bounce and path), a tenth of the HBM. Scenes without meshes take 64 Mi (config 2 at 64 spp: 39.8 -> 38.4 ms; the mesh scenes did not
+    // gain: config 4 122.8 -> 124.6, config 5 116.1 -> 114.6, profiles/r02_notes.md). Chunks are EQUAL: a frame that needs k chunks
+    // gets k chunks of n / k pixels, not k - 1 full ones and a small rest whose kernels are mostly tail.
+    unsigned long long max_paths = wavefront ? ((s->d.n_meshes == 0 ? 64ull : 32ull) << 20) : (16ull << 20);
     if (const char *e = getenv("HAI719_CHUNK_LOG2")) { const int l = atoi(e); if (l >= 16 && l <= 26) max_paths = 1ull << l; }   // tuning experiments
     unsigned long long chunk_pixels = std::max<unsigned long long>(1, max_paths / (unsigned long long)p->spp);
     chunk_pixels = std::min(chunk_pixels, n_pixels);
+    {
+        const unsigned long long n_chunks = (n_pixels + chunk_pixels - 1) / chunk_pixels;
+        chunk_pixels = (n_pixels + n_chunks - 1) / n_chunks;
+    }
     // bit 28 of variant: generate camera rays inside the render kernel instead of the k_camera_rays pass (A/B switch)
     const bool cam_split = wavefront || ((p->variant >> 28) & 1) == 0 && (p->variant & 0xFF) != 1 && !((p->variant & 0xFF) == 0 && s->d.n_meshes == 0 && s->d.abvh_root < 0);
     if ((rc = ensure_scratch(s, (size_t)(chunk_pixels * p->spp * 3ull), n_tiles, cam_split ? (size_t)(chunk_pixels * p->spp) : 0))) return rc;
@@ -1955,22 +1797,9 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     // no lights: the light stage is only the scatter (k_wf_scatter); wavefront variant bit 27 keeps the general kernel (A/B)
     const bool wf_scatter_only = s->d.n_lights == 0 && !wf_nolight && ((p->variant >> 27) & 1) == 0;
     if (wf_scatter_only) wf_light = want_stats ? k_wf_scatter<true> : k_wf_scatter<false>;
-    // Speculative samples for the overflow queue (lights whose candidate-triangle list overflowed: their samples walk the mesh
-    // hierarchies). Wavefront variant bits 20..23: 0 = automatic, 1..14 = that many rounds, 15 = off.
-    int sp_rounds = 0;
-    if (wavefront && wf_lc && s->d.n_lights > 0 && s->d.n_meshes > 0 && p->nb_ech <= 255) {
-        const int req = (p->variant >> 20) & 0xF;
-        sp_rounds = req == 0 ? RT_SPEC_ROUNDS_DEFAULT : (req == 15 ? 0 : std::min(req, SP_MAX_ROUNDS));
-    }
-    typedef void (*SpecTraceKernel)(const DScene, const WfArgs);
-    typedef void (*SpecValidateKernel)(const WfArgs);
-    SpecTraceKernel wf_spec_trace = want_stats ? k_wf_spec_trace<true> : k_wf_spec_trace<false>;
-    SpecValidateKernel wf_spec_validate = want_stats ? k_wf_spec_validate<true> : k_wf_spec_validate<false>;
-    int wf_grid_t = 0, wf_grid_l = 0, wf_grid_s = 0;
+    int wf_grid_t = 0, wf_grid_l = 0;
     if (wavefront) {
         if ((rc = ensure_wavefront(s, (size_t)(chunk_pixels * p->spp), p->max_bounces))) return rc;
-        if (sp_rounds > 0 && (rc = ensure_spec(s, s->wf_pos_cap, p->nb_ech))) return rc;
-        if (sp_rounds > 0) wf_grid_s = persistent_grid(s, (const void *)wf_spec_trace, 128);
         wf_grid_t = persistent_grid(s, (const void *)wf_trace, 128);
         wf_grid_l = persistent_grid(s, (const void *)wf_light, 128);
     }
@@ -2034,11 +1863,6 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
             w.rec = s->wf_rec; w.rec_stride = s->wf_cap;
             w.ctr = s->wf_ctr; w.samples = s->samples; w.stats = a.stats;
             RT_CUDA(cudaMemsetAsync(s->wf_ctr, 0, WF_NCTR * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
-            w.sp_enabled = sp_rounds > 0 ? 1 : 0;
-            if (sp_rounds > 0) {
-                w.sp_hdr = s->sp_hdr; w.sp_res = s->sp_res;
-                RT_CUDA(cudaMemsetAsync(s->sp_ctr, 0, (size_t)SP_NCTR * (SP_MAX_ROUNDS + 2) * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
-            }
             const int gt = (int)std::min<unsigned long long>((unsigned long long)wf_grid_t, (batches + 3) / 4);
             const int gl = (int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4);
             for (int level = 0; level < p->max_bounces; ++level) {
@@ -2073,21 +1897,6 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
                     RT_CUDA(cudaGetLastError());
                     ++launches;
                     if (s->d.n_meshes > 0) {   // lights whose candidate-triangle list overflowed, in warps of their own
-                        // ... after rounds of speculative samples: round r reads the hits the validation of round r - 1 left
-                        // unfinished (round 0: everything the classify kernel put into the overflow queue)
-                        unsigned int *cbase = s->sp_ctr + (size_t)SP_NCTR * (SP_MAX_ROUNDS + 2) * level;
-                        for (int r = 0; r < sp_rounds; ++r) {
-                            w.sp_q_in = r == 0 ? w.q_over : s->sp_q + (size_t)((r - 1) & 1) * s->sp_cap;
-                            w.sp_len_in = r == 0 ? s->wf_ctr + WF_NCTR * level + 7 : cbase + SP_NCTR * r + 2;
-                            w.sp_head = cbase + SP_NCTR * r; w.sp_vhead = cbase + SP_NCTR * r + 1;
-                            w.sp_q_out = s->sp_q + (size_t)(r & 1) * s->sp_cap;
-                            w.sp_len_out = cbase + SP_NCTR * (r + 1) + 2;
-                            wf_spec_trace<<<std::min(wf_grid_s, gl), 128, 0, st>>>(s->d, w);
-                            RT_CUDA(cudaGetLastError());
-                            wf_spec_validate<<<std::min(2 * s->sm_count, gl), 128, 0, st>>>(w);
-                            RT_CUDA(cudaGetLastError());
-                            launches += 2;
-                        }
                         w.which_park = 1;
                         wf_light_b<<<gl, 128, 0, st>>>(s->d, w);
                         RT_CUDA(cudaGetLastError());

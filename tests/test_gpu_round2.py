@@ -440,25 +440,3 @@ def test_device_image_cache_skips_resident_images_and_release_frees_them(gpu, as
     third = s.render(w, h, spp, seed=1)["linear"]
     assert np.array_equal(bits(want), bits(third))
     assert s.h2d_bytes(0) > 8_000_000
-
-
-# ---- speculative shadow samples for the overflow queue (k_wf_spec_trace / k_wf_spec_validate) --------------------------------
-@pytest.mark.parametrize("name,w,h,spp", [("flamingo_pond", 240, 136, 3), ("config5", 240, 136, 2), ("flamingo", 160, 90, 2),
-                                          ("raccoon", 160, 90, 2), ("flamingo_lake", 160, 90, 2)])
-def test_speculative_overflow_samples_do_not_change_a_bit(gpu, assets, name, w, h, spp):
-    """Hits whose candidate-triangle list overflowed get their NB_ECH samples traced in parallel from GUESSED stream positions;
-    only the samples whose guess the validation confirms are kept (rt_capi.cu : k_wf_spec_trace). Whatever the number of rounds
-    (wavefront variant bits 20..23: 15 = off, 1..14 rounds; the rest is finished sequentially) the image, the ray counts and
-    the number of random draws are those of the one-path-per-lane kernel (variant 1). One and two lights, nb_ech 10 and 4,
-    small chunks (queues reused, mostly padding)."""
-    s = gpu.Scene(name, aspect=w / h, seed=0)
-    want = s.render(w, h, spp, seed=3, variant=1, stats=True)
-    for rounds in (15, 1, 2, 3, 6, 14):
-        for st in (False, True):
-            got = s.render(w, h, spp, seed=3, variant=6 | (rounds << 20), stats=st)
-            assert np.array_equal(bits(want["linear"]), bits(got["linear"])), (name, rounds, st)
-            for k in ("n_closest_rays", "n_shadow_rays") + (("n_random", "n_tex_fetches") if st else ()):
-                assert want["stats"][k] == got["stats"][k], (name, rounds, st, k)
-    few = s.render(w, h, spp, seed=3, variant=6 | (2 << 20), nb_ech=4, max_bounces=3)
-    ref4 = s.render(w, h, spp, seed=3, variant=1, nb_ech=4, max_bounces=3)
-    assert np.array_equal(bits(ref4["linear"]), bits(few["linear"]))

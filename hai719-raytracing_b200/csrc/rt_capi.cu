@@ -846,8 +846,8 @@ __global__ void k_wf_tally(const unsigned int *ctr, unsigned int n_paths, int le
         hits += ctr[WF_NCTR * l + 9];
     }
     (void)n_paths;
-    tally[0] += closest;
-    tally[1] += hits;
+    atomicAdd(tally, closest);       // chunks of one frame run on two streams
+    atomicAdd(tally + 1, hits);
 }
 
 // main.cpp:258: (int)(255.f * std::min<float>(1.f, c)); std::min(a, b) = (b < a) ? b : a, so a NaN pixel becomes 1.f and
@@ -982,6 +982,10 @@ struct Scratch {
     // H2D copy on the null stream (2-3 us each) instead of a synchronous pageable cudaMemcpy (8-10 us each, ~30 per scene);
     // one stream synchronise at the end of the upload. Arrays that do not fit (meshes, images) are copied synchronously.
     char *stage = nullptr; size_t stage_cap = 0, stage_used = 0;
+    // The wavefront renders a frame's chunks on TWO streams at once (render_device_impl): the second stream's chunks use this
+    // second set of per-chunk buffers (samples, camera rays, pixel table, wavefront state); everything else is shared.
+    Scratch *second = nullptr;
+    cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // arena for the scene's own arrays (textures, primitives, hierarchies): bump-allocated blocks, reset when the scene
     // is destroyed and reused by the next scene on this device — a re-upload performs no cudaMalloc/cudaFree at all
     struct Block { char *base; size_t cap, used; };
@@ -1022,6 +1026,10 @@ struct Scratch {
         if (out_bytes) cudaFree(out_bytes);
         if (stream) cudaStreamDestroy(stream);
         if (stage) cudaFreeHost(stage);
+        if (aux_stream) cudaStreamDestroy(aux_stream);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (second) { second->release(); delete second; }
         *this = Scratch();
     }
 };
@@ -1334,8 +1342,8 @@ int persistent_grid(RtScene *s, const void *kernel, int threads) {
 #define WF_MAX_BLOCK 256u
 // Queue positions beyond the path count: every warp of a producing kernel may leave the rest of one block of each queue it
 // appends to unused (wf_push), and a queue has at most three producing kernels per level (classify + the two sample passes).
-size_t wf_padding(const RtScene *s) { return (size_t)3 * (size_t)s->sm_count * RT_WF_MINB * 4 * WF_MAX_BLOCK; }
-int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
+size_t wf_padding(int sm_count) { return (size_t)3 * (size_t)sm_count * RT_WF_MINB * 4 * WF_MAX_BLOCK; }
+int ensure_wavefront(Scratch *s, int sm_count, size_t paths, int max_bounces) {
     if (paths <= s->wf_cap && max_bounces <= s->wf_bounces) return RT_OK;
     paths = std::max(paths, s->wf_cap); max_bounces = std::max(max_bounces, s->wf_bounces);   // grow-only in both dimensions
     if (s->wf_f4) cudaFree(s->wf_f4);
@@ -1343,7 +1351,7 @@ int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
     if (s->wf_q) cudaFree(s->wf_q);
     if (s->wf_rec) cudaFree(s->wf_rec);
     s->wf_f4 = nullptr; s->wf_rng = nullptr; s->wf_q = nullptr; s->wf_rec = nullptr; s->wf_cap = 0; s->wf_pos_cap = 0; s->wf_bounces = 0;
-    const size_t pos = paths + wf_padding(s);
+    const size_t pos = paths + wf_padding(sm_count);
     RT_CUDA(cudaMalloc((void **)&s->wf_f4, WF_F4_PLANES * pos * sizeof(float4)));
     RT_CUDA(cudaMalloc((void **)&s->wf_rng, 2 * pos * sizeof(uint2)));
     RT_CUDA(cudaMalloc((void **)&s->wf_q, WF_Q_PLANES * pos * sizeof(unsigned int)));
@@ -1353,7 +1361,8 @@ int ensure_wavefront(RtScene *s, size_t paths, int max_bounces) {
     return RT_OK;
 }
 
-int ensure_scratch(RtScene *s, size_t sample_floats, size_t n_tiles, size_t cam_paths) {
+// per-chunk buffers of one lane (the scene's own Scratch, or its `second`)
+int ensure_lane(Scratch *s, size_t sample_floats, size_t cam_paths, size_t chunk_pixels) {
     if (cam_paths > s->cam_cap) {
         if (s->cam_rays) cudaFree(s->cam_rays);
         if (s->cam_keys) cudaFree(s->cam_keys);
@@ -1362,12 +1371,23 @@ int ensure_scratch(RtScene *s, size_t sample_floats, size_t n_tiles, size_t cam_
         RT_CUDA(cudaMalloc((void **)&s->cam_keys, cam_paths * sizeof(unsigned int)));
         s->cam_cap = cam_paths;
     }
+    if (cam_paths && chunk_pixels > s->pix_cap) {
+        if (s->pix_xy) cudaFree(s->pix_xy);
+        s->pix_xy = nullptr; s->pix_cap = 0;
+        RT_CUDA(cudaMalloc((void **)&s->pix_xy, chunk_pixels * sizeof(unsigned int)));
+        s->pix_cap = chunk_pixels;
+    }
     if (sample_floats > s->samples_cap) {
         if (s->samples) cudaFree(s->samples);
         s->samples = nullptr; s->samples_cap = 0;
         RT_CUDA(cudaMalloc((void **)&s->samples, sample_floats * sizeof(float)));
         s->samples_cap = sample_floats;
     }
+    return RT_OK;
+}
+int ensure_scratch(RtScene *s, size_t sample_floats, size_t n_tiles, size_t cam_paths, size_t chunk_pixels) {
+    int rc = ensure_lane(s, sample_floats, cam_paths, chunk_pixels);
+    if (rc) return rc;
     if (!s->counters) RT_CUDA(cudaMalloc((void **)&s->counters, 16 * sizeof(unsigned long long)));
     if (n_tiles + 1 > s->tiles_cap) {
         if (s->d_tiles) cudaFree(s->d_tiles);
@@ -1731,15 +1751,30 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     // gets k chunks of n / k pixels, not k - 1 full ones and a small rest whose kernels are mostly tail.
     unsigned long long max_paths = wavefront ? ((s->d.n_meshes == 0 ? 64ull : 32ull) << 20) : (16ull << 20);
     if (const char *e = getenv("HAI719_CHUNK_LOG2")) { const int l = atoi(e); if (l >= 16 && l <= 26) max_paths = 1ull << l; }   // tuning experiments
-    unsigned long long chunk_pixels = std::max<unsigned long long>(1, max_paths / (unsigned long long)p->spp);
+    // The wavefront renders the chunks of a frame on TWO streams (lanes) at once, each with its own per-chunk buffers: every
+    // one of a chunk's ~19 persistent kernels ends in a tail of 40-60 us during which SMs drain (one batch of 32 paths takes
+    // that long through the kernel; measured as the intercept of kernel time against chunk size, profiles/r02_notes.md), and
+    // the other lane's kernels fill it. The paths in flight stay what they were: a lane's chunk is half the budget.
+    // Measured (profiles/r02_notes.md, r03a): config 2 38.5 -> 38.4 ms, config 4 121.5 -> 120.0, config 5 115.1 -> 114.0 — within
+    // 1 %, for twice the per-chunk buffers. OFF by default; HAI719_LANES=2 switches it on (A/B).
+    int n_lanes = 1;
+    if (const char *e = getenv("HAI719_LANES")) { if (atoi(e) == 2 && wavefront && n_pixels * (unsigned long long)p->spp >= (2ull << 20)) n_lanes = 2; }
+    unsigned long long chunk_pixels = std::max<unsigned long long>(1, (max_paths / (unsigned long long)n_lanes) / (unsigned long long)p->spp);
     chunk_pixels = std::min(chunk_pixels, n_pixels);
     {
-        const unsigned long long n_chunks = (n_pixels + chunk_pixels - 1) / chunk_pixels;
+        unsigned long long n_chunks = (n_pixels + chunk_pixels - 1) / chunk_pixels;
+        if (n_lanes == 2) n_chunks += n_chunks & 1ull;   // both lanes get the same number of chunks
         chunk_pixels = (n_pixels + n_chunks - 1) / n_chunks;
     }
     // bit 28 of variant: generate camera rays inside the render kernel instead of the k_camera_rays pass (A/B switch)
     const bool cam_split = wavefront || ((p->variant >> 28) & 1) == 0 && (p->variant & 0xFF) != 1 && !((p->variant & 0xFF) == 0 && s->d.n_meshes == 0 && s->d.abvh_root < 0);
-    if ((rc = ensure_scratch(s, (size_t)(chunk_pixels * p->spp * 3ull), n_tiles, cam_split ? (size_t)(chunk_pixels * p->spp) : 0))) return rc;
+    if ((rc = ensure_scratch(s, (size_t)(chunk_pixels * p->spp * 3ull), n_tiles, cam_split ? (size_t)(chunk_pixels * p->spp) : 0, (size_t)chunk_pixels))) return rc;
+    if (n_lanes == 2) {
+        if (!s->second) s->second = new Scratch();
+        if ((rc = ensure_lane(s->second, (size_t)(chunk_pixels * p->spp * 3ull), cam_split ? (size_t)(chunk_pixels * p->spp) : 0, (size_t)chunk_pixels))) return rc;
+        if (!s->aux_stream) RT_CUDA(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+        if (!s->ev_fork) { RT_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming)); RT_CUDA(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming)); }
+    }
     RT_CUDA(cudaMemcpyAsync(s->d_tiles, s->h_tiles.data(), n_tiles * sizeof(TileRec), cudaMemcpyHostToDevice, st));
     RT_CUDA(cudaMemcpyAsync(s->d_tile_off, s->h_tile_off.data(), (n_tiles + 1) * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
 
@@ -1799,7 +1834,8 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     if (wf_scatter_only) wf_light = want_stats ? k_wf_scatter<true> : k_wf_scatter<false>;
     int wf_grid_t = 0, wf_grid_l = 0;
     if (wavefront) {
-        if ((rc = ensure_wavefront(s, (size_t)(chunk_pixels * p->spp), p->max_bounces))) return rc;
+        if ((rc = ensure_wavefront(s, s->sm_count, (size_t)(chunk_pixels * p->spp), p->max_bounces))) return rc;
+        if (n_lanes == 2 && (rc = ensure_wavefront(s->second, s->sm_count, (size_t)(chunk_pixels * p->spp), p->max_bounces))) return rc;
         wf_grid_t = persistent_grid(s, (const void *)wf_trace, 128);
         wf_grid_l = persistent_grid(s, (const void *)wf_light, 128);
     }
@@ -1818,31 +1854,35 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     if ((rc = binding.bind(s, st))) return rc;
     RT_CUDA(cudaMemsetAsync(s->counters, 0, 16 * sizeof(unsigned long long), st));
     if (stats) RT_CUDA(cudaEventRecord(s->ev0, st));
-    for (unsigned long long pb = 0; pb < n_pixels; pb += chunk_pixels) {
+    cudaStream_t const st_caller = st;
+    if (n_lanes == 2) {   // the second lane starts after everything queued on the caller's stream so far (tile table, constants)
+        RT_CUDA(cudaEventRecord(s->ev_fork, st_caller));
+        RT_CUDA(cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
+    }
+    unsigned long long chunk_index = 0;
+    for (unsigned long long pb = 0; pb < n_pixels; pb += chunk_pixels, ++chunk_index) {
         const unsigned long long np = std::min(chunk_pixels, n_pixels - pb);
+        const int lane = n_lanes == 2 ? (int)(chunk_index & 1ull) : 0;
+        Scratch *const L = lane ? s->second : static_cast<Scratch *>(s);   // this chunk's buffers ...
+        st = lane ? s->aux_stream : st_caller;                             // ... and stream
+        a.samples = L->samples;
         a.pixel_begin = pb;
         a.n_paths = np * (unsigned long long)p->spp;
-        if (pb) RT_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long), st));
+        if (pb && !wavefront) RT_CUDA(cudaMemsetAsync(s->counters, 0, sizeof(unsigned long long), st));
         const unsigned long long batches = (a.n_paths + 31) / 32;
         const int g = (int)std::min<unsigned long long>((unsigned long long)grid, (batches + 3) / 4);
         if (cam_split) {
-            a.cam_rays = s->cam_rays; a.cam_keys = s->cam_keys;
-            if (np > s->pix_cap) {
-                if (s->pix_xy) cudaFree(s->pix_xy);
-                s->pix_xy = nullptr; s->pix_cap = 0;
-                RT_CUDA(cudaMalloc((void **)&s->pix_xy, (size_t)chunk_pixels * sizeof(unsigned int)));
-                s->pix_cap = (size_t)chunk_pixels;
-            }
-            k_pixel_xy<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(a, (unsigned int)np, s->pix_xy);
+            a.cam_rays = L->cam_rays; a.cam_keys = L->cam_keys;
+            k_pixel_xy<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(a, (unsigned int)np, L->pix_xy);
             RT_CUDA(cudaGetLastError());
-            k_camera_rays<<<(unsigned)((a.n_paths + 255) / 256), 256, 0, st>>>(cam, a, s->pix_xy, s->cam_rays, s->cam_keys);
+            k_camera_rays<<<(unsigned)((a.n_paths + 255) / 256), 256, 0, st>>>(cam, a, L->pix_xy, L->cam_rays, L->cam_keys);
             ++launches;
             RT_CUDA(cudaGetLastError());
             ++launches;
         }
         if (wavefront) {
             WfArgs w{};
-            const size_t pc = s->wf_pos_cap;
+            const size_t pc = L->wf_pos_cap;
             w.n_paths = (unsigned int)a.n_paths; w.max_bounces = p->max_bounces; w.nb_ech = p->nb_ech;
             // mesh scenes: a batch can cost 100x another one (rays that walk a mesh vs rays that miss its box), so warps take
             // one batch at a time as before; analytic scenes: cheap, even batches, where the fetch atomics were the bottleneck
@@ -1850,19 +1890,19 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
             // output positions a warp reserves per atomic: 256 where the queue atomics were the bottleneck (large chunks);
             // small chunks take small blocks, so that their queues are not mostly padding
             w.block = a.n_paths >= (4ull << 20) ? WF_MAX_BLOCK : (a.n_paths >= (256ull << 10) ? 64u : 32u);
-            w.cam_rays = s->cam_rays; w.cam_keys = s->cam_keys;
-            float4 *const f4 = s->wf_f4;
+            w.cam_rays = L->cam_rays; w.cam_keys = L->cam_keys;
+            float4 *const f4 = L->wf_f4;
             float4 *rayA0 = f4, *rayA1 = f4 + pc;
             w.hit0 = f4 + 2 * pc; w.hit1 = f4 + 3 * pc; w.hit2 = f4 + 4 * pc; w.hit3 = f4 + 5 * pc; w.hit4 = f4 + 6 * pc;
             w.park0 = f4 + 7 * pc; w.park1 = f4 + 8 * pc; w.park2 = f4 + 9 * pc; w.park_stride = pc;
-            w.mesh_hit = f4 + (9 + RT_LC_MAXC / 4) * pc; w.q_mesh = s->wf_q + 4 * pc;
-            uint2 *rngA = s->wf_rng;
-            w.rng_hit = s->wf_rng + pc;
-            unsigned int *qA = s->wf_q;
-            w.q_hit = s->wf_q + pc; w.q_park = s->wf_q + 2 * pc; w.q_over = s->wf_q + 3 * pc; w.which_park = 0;
-            w.rec = s->wf_rec; w.rec_stride = s->wf_cap;
-            w.ctr = s->wf_ctr; w.samples = s->samples; w.stats = a.stats;
-            RT_CUDA(cudaMemsetAsync(s->wf_ctr, 0, WF_NCTR * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
+            w.mesh_hit = f4 + (9 + RT_LC_MAXC / 4) * pc; w.q_mesh = L->wf_q + 4 * pc;
+            uint2 *rngA = L->wf_rng;
+            w.rng_hit = L->wf_rng + pc;
+            unsigned int *qA = L->wf_q;
+            w.q_hit = L->wf_q + pc; w.q_park = L->wf_q + 2 * pc; w.q_over = L->wf_q + 3 * pc; w.which_park = 0;
+            w.rec = L->wf_rec; w.rec_stride = L->wf_cap;
+            w.ctr = L->wf_ctr; w.samples = L->samples; w.stats = a.stats;
+            RT_CUDA(cudaMemsetAsync(L->wf_ctr, 0, WF_NCTR * (RT_MAX_BOUNCES + 2) * sizeof(unsigned int), st));
             const int gt = (int)std::min<unsigned long long>((unsigned long long)wf_grid_t, (batches + 3) / 4);
             const int gl = (int)std::min<unsigned long long>((unsigned long long)wf_grid_l, (batches + 3) / 4);
             for (int level = 0; level < p->max_bounces; ++level) {
@@ -1910,11 +1950,16 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
             RT_CUDA(cudaGetLastError());
             ++launches;
         }
-        if (wavefront) k_wf_tally<<<1, 32, 0, st>>>(s->wf_ctr, (unsigned int)a.n_paths, p->max_bounces, s->counters + 11);
-        k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(a, cam_split ? s->pix_xy : nullptr, (unsigned int)np, d_linear, d_gamma, d_sum, sample_base,
+        if (wavefront) k_wf_tally<<<1, 32, 0, st>>>(L->wf_ctr, (unsigned int)a.n_paths, p->max_bounces, s->counters + 11);
+        k_resolve<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(a, cam_split ? L->pix_xy : nullptr, (unsigned int)np, d_linear, d_gamma, d_sum, sample_base,
                                                                  image_mode, r.x0, r.y0, r.x1 - r.x0);
         RT_CUDA(cudaGetLastError());
         ++launches;
+    }
+    st = st_caller;
+    if (n_lanes == 2) {   // the caller's stream continues when the second lane is done
+        RT_CUDA(cudaEventRecord(s->ev_join, s->aux_stream));
+        RT_CUDA(cudaStreamWaitEvent(st_caller, s->ev_join, 0));
     }
     binding.done();
     if (stats) {

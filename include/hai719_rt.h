@@ -176,13 +176,18 @@ typedef struct RtRenderParams {
                                     state machine with path regeneration (k_render_regen), reference-order KD walk;
                                     3 the same over the exact culling hierarchies; 4 warp-voted walk of those;
                                     5 occluder candidates per (hit, light) + gated traversal / shadow-sample
-                                    phases. Tuning bits: 8..15 regeneration threshold, 16..19 CTAs per SM,
-                                    20..27 traversal threshold of kernel 5, 28 = no separate camera-ray pass,
-                                    29 = wavefront with walk-and-classify fused into the trace kernel (slower; default: own kernel).
-                                    All variants give identical bits (tests/test_gpu_parity.py).
+                                    phases; 6 wavefront (camera rays / trace + shade / light + scatter kernels per
+                                    bounce level, path state at queue positions). Tuning bits: 8..15 regeneration
+                                    threshold, 16..19 CTAs per SM, 20..27 traversal threshold of kernel 5, 28 = no
+                                    separate camera-ray pass (kernels 2-5). Wavefront only: 27 = general light kernel
+                                    instead of the scatter-only kernel for scenes without lights, 28 = flip the choice
+                                    of the split trace (analytic phase + mesh-walk kernel; default: on without lights),
+                                    29 = scatter inside the trace kernel for scenes without lights (slower; off).
+                                    All variants give identical bits (tests/test_gpu_parity.py, test_gpu_round2.py).
                                     Environment HAI719_CHUNK_LOG2=16..26 (read per call) overrides the number of
-                                    paths rendered per chunk (default 2^25 wavefront, 2^24 otherwise): a memory /
-                                    speed knob, results do not depend on it. */
+                                    paths rendered per chunk (default 2^25 wavefront, 2^26 for wavefront scenes without
+                                    meshes, 2^24 otherwise; the chunks of a frame are equal): a memory / speed knob,
+                                    results do not depend on it. */
 } RtRenderParams;
 
 typedef struct RtStats {

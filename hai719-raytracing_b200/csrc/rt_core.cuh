@@ -884,6 +884,74 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
     }
 }
 
+// RESUMABLE form of meshes_walk_merged (kernel variant 7). A warp is as slow as its slowest lane: walks of the pond scene differ
+// so much in length that the state-machine kernel ran 9 of 32 lanes (profiles/r02_notes.md). Here the walk state of a lane
+// (MeshWalk: current node, stack, pending triangles, best so far) outlives the call: the warp leaves the loop as soon as
+// `wait_min` of its lanes have nothing to walk any more (and at least `rounds_min` rounds have run since the call), the caller
+// lets THOSE lanes consume their result and set up their next ray, and calls again; lanes with `pending` set resume where they
+// stopped, the others start a new walk next to them. Same rounds, same candidates, same per-triangle routine, same acceptance
+// rules and draw order as meshes_walk_merged — a lane's walk is only cut into pieces.
+// All lanes of the warp call it together. `counts`: the lane is waiting for something (an idle lane that can get no new path
+// does not count towards wait_min).
+struct MeshWalk {
+    TStack stack;
+    int node, sp, mi;
+    uint32_t k, kend;
+    float best_t;
+    uint32_t best_ref;
+    bool pending;
+};
+template <bool STATS>
+RT_HD void meshes_walk_resumable(const DScene &s, const Ray &ray, int mode, Rng &rng, Hit &h, bool &blocked, bool done, bool counts,
+                                 MeshWalk &w, int wait_min, int rounds_min, Counters *cnt) {
+    const uint32_t NONE = 0xFFFFFFFFu;
+    const int MESH_END = 0x7FFFFFFD;
+    bool active = w.pending || (!done && s.n_meshes > 0);
+    if (active && !w.pending) {
+        w.sp = 0; w.mi = 0;
+        w.k = s.meshes[0].always_first; w.kend = w.k + s.meshes[0].always_count;
+        w.node = s.meshes[0].bvh_root >= 0 ? s.meshes[0].bvh_root : MESH_END;
+        w.best_t = h.t; w.best_ref = NONE;
+        if (STATS) cnt->mesh++;
+    }
+    const Inv32 iv = make_inv32(ray);
+    TStack &stack = w.stack;
+    int node = w.node, sp = w.sp, mi = w.mi;
+    uint32_t k = w.k, kend = w.kend;
+    float best_t = w.best_t;
+    uint32_t best_ref = w.best_ref;
+    for (int round = 1;; ++round) {
+        if (active) {
+            for (; k < kend; ++k) bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+            RT_WALK_DESCEND()
+            if (node < 0) {   // a leaf: its triangles are tested at the top of the next round
+                const uint32_t code = (uint32_t)(-(node + 1));
+                k = code >> 3; kend = k + (code & 7u);
+                node = sp > 0 ? stack.get(--sp) : MESH_END;
+            } else {
+                // mesh mi is finished
+                if (best_ref != NONE && best_t < h.t && best_t > RT_EPSF) {
+                    if (mode == 0) { h.type = 3; h.obj = mi; h.t = best_t; h.ref = best_ref; }
+                    else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.mesh_transparency + mi)) { blocked = true; active = false; } }
+                }
+                if (active && ++mi >= s.n_meshes) active = false;
+                if (active) {
+                    const DMesh &m = s.meshes[mi];
+                    if (STATS) cnt->mesh++;
+                    k = m.always_first; kend = k + m.always_count;
+                    node = m.bvh_root >= 0 ? m.bvh_root : MESH_END;
+                    sp = 0;
+                    best_t = h.t; best_ref = NONE;
+                }
+            }
+        }
+        if (RT_BALLOT(active) == 0u) break;
+        if (round >= rounds_min && RT_POPC(RT_BALLOT(!active && counts)) >= wait_min) break;
+    }
+    w.pending = active;
+    w.node = node; w.sp = sp; w.mi = mi; w.k = k; w.kend = kend; w.best_t = best_t; w.best_ref = best_ref;
+}
+
 #undef RT_WALK_DESCEND
 #undef RT_WALK_DESCEND4
 #undef RT_CSWAP4
@@ -1289,13 +1357,14 @@ struct PathState {
 // (h, hu, hv). mode 1: `blocked` is computeShadow's return value; candidates draw from rng in the
 // reference's order (spheres, squares, meshes) until one blocks. Lanes that have their answer
 // (blocked, or idle) skip the tests; the loops end early only when the whole warp is done.
+// The analytic primitives (spheres, then squares) of intersect_ray; `done` in: this lane has nothing to test (it still takes part
+// in the warp votes); out: blocked.
 template <bool STATS, bool ACCEL>
-RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_light, Rng &rng, Hit &h, float &hu, float &hv,
-                         bool &blocked, Counters *cnt) {
+RT_HD void intersect_ray_analytic(const DScene &s, const Ray &ray, int mode, float t_light, Rng &rng, Hit &h, float &hu, float &hv,
+                                  bool &blocked, bool &done, Counters *cnt) {
     h.type = 0; h.obj = -1; h.t = (mode == 0) ? FLT_MAX : t_light; h.ref = 0;
     blocked = false;
-    bool done = (mode == 2);
-    if (STATS) { if (mode == 0) cnt->closest++; else if (mode == 1) cnt->shadow++; }
+    if (STATS && !done) { if (mode == 0) cnt->closest++; else if (mode == 1) cnt->shadow++; }
     const SphereRay sr = make_sphere_ray(ray);
     if (ACCEL && s.abvh_root >= 0 && s.n_spheres + s.n_squares >= 24) {   // below 24 the linear loops are as fast (the small hierarchy exists for variants 5/6)
         // variant 3: candidates from the culling hierarchy, exact tests, order semantics restored
@@ -1358,6 +1427,12 @@ RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_ligh
             }
         }
     }
+}
+template <bool STATS, bool ACCEL>
+RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_light, Rng &rng, Hit &h, float &hu, float &hv,
+                         bool &blocked, Counters *cnt) {
+    bool done = (mode == 2);
+    intersect_ray_analytic<STATS, ACCEL>(s, ray, mode, t_light, rng, h, hu, hv, blocked, done, cnt);
     if (ACCEL && RT_OPT_MESH_MERGED) {
         meshes_walk_merged<STATS>(s, ray, mode, rng, h, blocked, done, cnt);
     } else if (ACCEL) {
@@ -1429,6 +1504,22 @@ RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_ligh
             }
         }
     }
+}
+
+// intersect_ray<STATS, true> with the resumable mesh walk (kernel variant 7): a lane whose walk is pending keeps its ray and its
+// answer so far (h, hu, hv, blocked live in the caller across calls) and only resumes; the others start a new ray.
+template <bool STATS>
+RT_HD void intersect_ray_resumable(const DScene &s, const Ray &ray, int mode, float t_light, Rng &rng, Hit &h, float &hu, float &hv,
+                                   bool &blocked, MeshWalk &w, int wait_min, int rounds_min, Counters *cnt) {
+    bool done = w.pending || mode == 2;
+    {
+        Hit h2;
+        float u2 = 0.f, v2 = 0.f;
+        bool b2;
+        intersect_ray_analytic<STATS, true>(s, ray, mode, t_light, rng, h2, u2, v2, b2, done, cnt);
+        if (!w.pending) { h = h2; hu = u2; hv = v2; blocked = b2; }
+    }
+    meshes_walk_resumable<STATS>(s, ray, mode, rng, h, blocked, done, mode != 2, w, wait_min, rounds_min, cnt);
 }
 
 // ---- variant 4: ONE warp-voted walk over the analytic hierarchy and every mesh hierarchy ---------
@@ -1738,24 +1829,37 @@ RT_HD bool lc_shadow_analytic(const DScene &s, PathState &st, Counters *cnt) {
 // Requires s.abvh_root >= 0 (the kernel is only selected for such scenes).
 // with_meshes = false: closest-hit rays stop after the analytic primitives (the wavefront walks the meshes in a kernel of its
 // own, for the rays that touch a mesh at all: ray_touches_meshes below).
-template <bool STATS>
+// CLOSEST = true (the wavefront's trace kernels: every ray is a closest-hit ray): the cone degenerates to the ray (delta = 0), so
+// the walk runs the plain slab test (bvh_box, three reciprocals per ray instead of six and no sign selects per plane) on the
+// same padded boxes with the same slack. Both tests are conservative filters in front of the same exact primitive tests with
+// the same order rule (smallest t, earliest in sequence on ties), so the hit is the same; only the number of boxes visited may
+// differ by a rounding. RT_OPT_LC_SLAB=0 keeps the cone test there (A/B).
+#ifndef RT_OPT_LC_SLAB
+#define RT_OPT_LC_SLAB 1
+#endif
+template <bool STATS, bool CLOSEST = false>
 RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, Hit &h, float &hu, float &hv, bool &blocked,
                         Counters *cnt, bool with_meshes = true) {
     const Ray &ray = st.ray;
-    const int mode = st.mode;
+    const int mode = CLOSEST && RT_OPT_LC_SLAB ? 0 : st.mode;
     h.type = 0; h.obj = -1; h.t = (mode == 0) ? FLT_MAX : st.t_light; h.ref = 0;
     blocked = false;
     bool done = !mine;
     const int ns = s.n_spheres;
     if (run_t) {
         if (mine) {
-            const bool collect = (mode == 3);
+            const bool SLAB = CLOSEST && RT_OPT_LC_SLAB;
+            const bool collect = !SLAB && (mode == 3);
             if (STATS && !collect) cnt->closest++;
             Cone cone;
+            Inv32 iv32;
             float limit_c = 1.0001f;
             V3 coneD = v3(0.f);
             float cone_delta = 0.f, cone_len = 0.f;
-            if (collect) {
+            if (SLAB) {
+                iv32 = make_inv32(ray);
+                cone.o = ray.o;
+            } else if (collect) {
                 const DLight &L = s.lights[st.light];
                 coneD = ld3(L.pos) - st.P;
                 cone_delta = (L.radius / 2.f) * 1.0001f + 1e-6f;
@@ -1786,8 +1890,14 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
                     const float p0 = kq * n3.z + kl, p1 = kq * n3.w + kl;
                     const float limit = collect ? limit_c : h.t;
                     float d0, d1;
-                    const bool h0 = cone_box(cone, n0.x - p0, n0.y - p0, n0.z - p0, n0.w + p0, n1.x + p0, n1.y + p0, limit, d0);
-                    const bool h1 = cone_box(cone, n1.z - p1, n1.w - p1, n2.x - p1, n2.y + p1, n2.z + p1, n2.w + p1, limit, d1);
+                    bool h0, h1;
+                    if (SLAB) {
+                        h0 = bvh_box(ray, iv32, n0.x - p0, n0.y - p0, n0.z - p0, n0.w + p0, n1.x + p0, n1.y + p0, limit, d0);
+                        h1 = bvh_box(ray, iv32, n1.z - p1, n1.w - p1, n2.x - p1, n2.y + p1, n2.z + p1, n2.w + p1, limit, d1);
+                    } else {
+                        h0 = cone_box(cone, n0.x - p0, n0.y - p0, n0.z - p0, n0.w + p0, n1.x + p0, n1.y + p0, limit, d0);
+                        h1 = cone_box(cone, n1.z - p1, n1.w - p1, n2.x - p1, n2.y + p1, n2.z + p1, n2.w + p1, limit, d1);
+                    }
                     const int c0 = (int)f2u(n3.x), c1 = (int)f2u(n3.y);
                     if (h0 && h1) {
                         const bool swap = d1 < d0;

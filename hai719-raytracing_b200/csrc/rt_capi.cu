@@ -66,9 +66,7 @@ struct RenderArgs {
     unsigned long long *work_counter;
     unsigned long long *stats;          // 10 counters, or null
     int regen_min;                      // variant 1: refill idle lanes once at least this many are idle
-    int t_min;                          // variant 5: run a traversal step once at least this many lanes wait for one;
-                                        // variant 7: leave the resumable walk once at least this many lanes have none left
-    int walk_rounds;                    // variant 7: ... but not before this many rounds of the walk since it was entered
+    int t_min;                          // variant 5: run a traversal step once at least this many lanes wait for one
     const float4 *cam_rays;             // k_camera_rays output per path {dir.xyz, time}, or null: generate in the render kernel
     const unsigned int *cam_keys;       // ... and the key of the path's random stream (3 draws already taken)
     unsigned int sample_base;           // index of this call's first sample of every pixel (progressive accumulation, else 0)
@@ -263,11 +261,6 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScen
             }
         }
     };
-    MeshWalk walk7;
-    walk7.pending = false;
-    Hit h7; h7.type = 0; h7.obj = -1; h7.t = 0.f; h7.ref = 0;
-    float hu7 = 0.f, hv7 = 0.f;
-    bool blocked7 = false;
     for (;;) {
         if (ACCEL == 3) {
             // variant 5: a lane wants either a TRAVERSAL step (mode 0 closest hit, mode 3 occluder candidates of a
@@ -296,25 +289,6 @@ __global__ void __launch_bounds__(128, MINB) k_render_regen(const RT_PARAM DScen
             if (mine) {
                 V3 c;
                 if (path_advance<STATS, true>(scene, st, h, hu, hv, blocked, a.nb_ech, c, &cnt)) {
-                    float *o = a.samples + 3ull * st.path;
-                    o[0] = c.x; o[1] = c.y; o[2] = c.z;
-                }
-            }
-            continue;
-        }
-        if (ACCEL == 4) {
-            // variant 7: the mesh walk is resumable (meshes_walk_resumable). The warp leaves the walk once a.t_min lanes have no
-            // walk left; those lanes take their result, set up their next ray (or fetch a new path) and join the walkers again.
-            // A lane with a pending walk is never idle (mode 2), and its answer so far lives in h7 / hu7 / hv7 / blocked7.
-            if (!exhausted) {
-                const unsigned int need = __ballot_sync(0xFFFFFFFFu, st.mode == 2);
-                if (need) refill(need);
-            }
-            if (__all_sync(0xFFFFFFFFu, st.mode == 2)) break;
-            intersect_ray_resumable<STATS>(scene, st.ray, st.mode, st.t_light, st.rng, h7, hu7, hv7, blocked7, walk7, a.t_min, a.walk_rounds, &cnt);
-            if (st.mode != 2 && !walk7.pending) {
-                V3 c;
-                if (path_advance<STATS>(scene, st, h7, hu7, hv7, blocked7, a.nb_ech, c, &cnt)) {
                     float *o = a.samples + 3ull * st.path;
                     o[0] = c.x; o[1] = c.y; o[2] = c.z;
                 }
@@ -1810,7 +1784,7 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     // variant: low byte = kernel (0 auto, 1 k_render_paths: one path per lane to completion,
     // 2 k_render_regen: ray-level state machine with path regeneration and warp-voted KD traversal);
     // bits 8..15 = regeneration threshold of kernel 2 (idle lanes needed before a refill; 0 = 16)
-    if (p->variant < 0 || (p->variant & 0xFF) > 7 || (p->variant >> 30)) return fail(RT_ERR_INVALID, "unknown kernel variant");
+    if (p->variant < 0 || (p->variant & 0xFF) > 6 || (p->variant >> 30)) return fail(RT_ERR_INVALID, "unknown kernel variant");
     // bits 16..19: CTAs per SM of kernel 3 — 0 auto, 1 = 4 (<= 128 registers), 2 = 6 (<= 80), 3 = 8 (<= 64, a few spills)
     int occ = (p->variant >> 16) & 0xF;
     if (occ == 0) occ = 3;   // 8 CTAs/SM beat 6 and 4 on every config (profiles/r01_notes.md)
@@ -1824,11 +1798,10 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     // which is only run when asked for - and one path per lane (1) for a handful of analytic primitives
     if (kind == 0) kind = (s->d.n_meshes > 0 || s->d.abvh_root >= 0) ? 3 : 1;
     if (kind == 5 && !lc_ok) kind = 3;
-    const bool regen = kind >= 2, accel = kind >= 3, voted = kind == 4, lc = kind == 5, resum = kind == 7;
+    const bool regen = kind >= 2, accel = kind >= 3, voted = kind == 4, lc = kind == 5;
     typedef void (*RenderKernel)(const DScene, const DCamera, const RenderArgs);
     RenderKernel fn;
-    if (resum)      fn = want_stats ? k_render_regen<true, 4, 4> : minb == 0 ? k_render_regen<false, 4, 4> : minb == 1 ? k_render_regen<false, 4, 6> : k_render_regen<false, 4, 8>;
-    else if (lc)    fn = want_stats ? k_render_regen<true, 3, 4> : minb == 0 ? k_render_regen<false, 3, 4> : minb == 1 ? k_render_regen<false, 3, 6> : k_render_regen<false, 3, 8>;
+    if (lc)         fn = want_stats ? k_render_regen<true, 3, 4> : minb == 0 ? k_render_regen<false, 3, 4> : minb == 1 ? k_render_regen<false, 3, 6> : k_render_regen<false, 3, 8>;
     else if (voted)      fn = want_stats ? k_render_regen<true, 2, 4> : minb == 0 ? k_render_regen<false, 2, 4> : minb == 1 ? k_render_regen<false, 2, 6> : k_render_regen<false, 2, 8>;
     else if (accel) fn = want_stats ? k_render_regen<true, 1, 4> : minb == 0 ? k_render_regen<false, 1, 4> : minb == 1 ? k_render_regen<false, 1, 6> : k_render_regen<false, 1, 8>;
     else if (regen) fn = want_stats ? k_render_regen<true, 0, 4> : k_render_regen<false, 0, 4>;
@@ -1873,10 +1846,7 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     a.regen_min = ((p->variant >> 8) & 0xFF) ? std::min(32, (p->variant >> 8) & 0xFF) : 16;
     // bits 20..27: traversal threshold of kernel 5. Measured (profiles/r01_notes.md): 1 is best — traverse as soon as
     // any lane wants to; the lanes then catch up with the ones sampling shadows and the warp falls into cohorts by itself
-    a.t_min = ((p->variant >> 20) & 0xFF) ? std::min(32, (p->variant >> 20) & 0xFF) : (kind == 7 ? 12 : 1);
-    // variant 7: bits 8..15 (the regeneration threshold of the other state-machine kernels; this one refills every idle lane
-    // whenever the warp is out of the walk) = rounds of the walk before the warp may leave it
-    a.walk_rounds = ((p->variant >> 8) & 0xFF) ? ((p->variant >> 8) & 0xFF) : 4;
+    a.t_min = ((p->variant >> 20) & 0xFF) ? std::min(32, (p->variant >> 20) & 0xFF) : 1;
     a.seed = p->seed; a.samples = s->samples; a.work_counter = s->counters; a.stats = want_stats ? s->counters + 1 : nullptr;
     a.sample_base = sample_base;
     uint32_t launches = 0;

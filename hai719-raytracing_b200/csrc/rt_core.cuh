@@ -884,74 +884,6 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
     }
 }
 
-// RESUMABLE form of meshes_walk_merged (kernel variant 7). A warp is as slow as its slowest lane: walks of the pond scene differ
-// so much in length that the state-machine kernel ran 9 of 32 lanes (profiles/r02_notes.md). Here the walk state of a lane
-// (MeshWalk: current node, stack, pending triangles, best so far) outlives the call: the warp leaves the loop as soon as
-// `wait_min` of its lanes have nothing to walk any more (and at least `rounds_min` rounds have run since the call), the caller
-// lets THOSE lanes consume their result and set up their next ray, and calls again; lanes with `pending` set resume where they
-// stopped, the others start a new walk next to them. Same rounds, same candidates, same per-triangle routine, same acceptance
-// rules and draw order as meshes_walk_merged — a lane's walk is only cut into pieces.
-// All lanes of the warp call it together. `counts`: the lane is waiting for something (an idle lane that can get no new path
-// does not count towards wait_min).
-struct MeshWalk {
-    TStack stack;
-    int node, sp, mi;
-    uint32_t k, kend;
-    float best_t;
-    uint32_t best_ref;
-    bool pending;
-};
-template <bool STATS>
-RT_HD void meshes_walk_resumable(const DScene &s, const Ray &ray, int mode, Rng &rng, Hit &h, bool &blocked, bool done, bool counts,
-                                 MeshWalk &w, int wait_min, int rounds_min, Counters *cnt) {
-    const uint32_t NONE = 0xFFFFFFFFu;
-    const int MESH_END = 0x7FFFFFFD;
-    bool active = w.pending || (!done && s.n_meshes > 0);
-    if (active && !w.pending) {
-        w.sp = 0; w.mi = 0;
-        w.k = s.meshes[0].always_first; w.kend = w.k + s.meshes[0].always_count;
-        w.node = s.meshes[0].bvh_root >= 0 ? s.meshes[0].bvh_root : MESH_END;
-        w.best_t = h.t; w.best_ref = NONE;
-        if (STATS) cnt->mesh++;
-    }
-    const Inv32 iv = make_inv32(ray);
-    TStack &stack = w.stack;
-    int node = w.node, sp = w.sp, mi = w.mi;
-    uint32_t k = w.k, kend = w.kend;
-    float best_t = w.best_t;
-    uint32_t best_ref = w.best_ref;
-    for (int round = 1;; ++round) {
-        if (active) {
-            for (; k < kend; ++k) bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
-            RT_WALK_DESCEND()
-            if (node < 0) {   // a leaf: its triangles are tested at the top of the next round
-                const uint32_t code = (uint32_t)(-(node + 1));
-                k = code >> 3; kend = k + (code & 7u);
-                node = sp > 0 ? stack.get(--sp) : MESH_END;
-            } else {
-                // mesh mi is finished
-                if (best_ref != NONE && best_t < h.t && best_t > RT_EPSF) {
-                    if (mode == 0) { h.type = 3; h.obj = mi; h.t = best_t; h.ref = best_ref; }
-                    else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.mesh_transparency + mi)) { blocked = true; active = false; } }
-                }
-                if (active && ++mi >= s.n_meshes) active = false;
-                if (active) {
-                    const DMesh &m = s.meshes[mi];
-                    if (STATS) cnt->mesh++;
-                    k = m.always_first; kend = k + m.always_count;
-                    node = m.bvh_root >= 0 ? m.bvh_root : MESH_END;
-                    sp = 0;
-                    best_t = h.t; best_ref = NONE;
-                }
-            }
-        }
-        if (RT_BALLOT(active) == 0u) break;
-        if (round >= rounds_min && RT_POPC(RT_BALLOT(!active && counts)) >= wait_min) break;
-    }
-    w.pending = active;
-    w.node = node; w.sp = sp; w.mi = mi; w.k = k; w.kend = kend; w.best_t = best_t; w.best_ref = best_ref;
-}
-
 #undef RT_WALK_DESCEND
 #undef RT_WALK_DESCEND4
 #undef RT_CSWAP4
@@ -1504,22 +1436,6 @@ RT_HD void intersect_ray(const DScene &s, const Ray &ray, int mode, float t_ligh
             }
         }
     }
-}
-
-// intersect_ray<STATS, true> with the resumable mesh walk (kernel variant 7): a lane whose walk is pending keeps its ray and its
-// answer so far (h, hu, hv, blocked live in the caller across calls) and only resumes; the others start a new ray.
-template <bool STATS>
-RT_HD void intersect_ray_resumable(const DScene &s, const Ray &ray, int mode, float t_light, Rng &rng, Hit &h, float &hu, float &hv,
-                                   bool &blocked, MeshWalk &w, int wait_min, int rounds_min, Counters *cnt) {
-    bool done = w.pending || mode == 2;
-    {
-        Hit h2;
-        float u2 = 0.f, v2 = 0.f;
-        bool b2;
-        intersect_ray_analytic<STATS, true>(s, ray, mode, t_light, rng, h2, u2, v2, b2, done, cnt);
-        if (!w.pending) { h = h2; hu = u2; hv = v2; blocked = b2; }
-    }
-    meshes_walk_resumable<STATS>(s, ray, mode, rng, h, blocked, done, mode != 2, w, wait_min, rounds_min, cnt);
 }
 
 // ---- variant 4: ONE warp-voted walk over the analytic hierarchy and every mesh hierarchy ---------

@@ -210,14 +210,6 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         const bool voted = (p->variant & 0xFF) == 4;
                         const bool lc = (p->variant & 0xFF) == 5 && s->d.abvh_root >= 0 && s->d.n_lights > 0;   // as rt_render_device selects
                         const bool accel = (p->variant & 0xFF) == 3 || ((p->variant & 0xFF) == 5 && !lc);
-                        // variant 7: the resumable mesh walk, cut after every `rounds` rounds (wait_min = 0 leaves the walk
-                        // unconditionally: one lane has nobody to wait for) and resumed until it is done
-                        const bool resum = (p->variant & 0xFF) == 7;
-                        const int rounds = ((p->variant >> 8) & 0xFF) ? ((p->variant >> 8) & 0xFF) : 1;
-                        MeshWalk walk;
-                        walk.pending = false;
-                        Hit rhit; rhit.type = 0; rhit.obj = -1; rhit.t = 0.f; rhit.ref = 0;
-                        float rhu = 0.f, rhv = 0.f; bool rblocked = false;
                         PathState st;
                         CandList cands;
                         st.cl = cands.v;
@@ -232,12 +224,6 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                             if (lc) {   // one lane: it always gets the step kind it wants
                                 intersect_lc<false>(s->d, st, st.mode != 1, true, hit, hu, hv, blocked, nullptr);
                                 fin = path_advance<false, true>(s->d, st, hit, hu, hv, blocked, p->nb_ech, c, nullptr);
-                                continue;
-                            }
-                            if (resum) {
-                                intersect_ray_resumable<false>(s->d, st.ray, st.mode, st.t_light, st.rng, rhit, rhu, rhv, rblocked, walk, 0, rounds, nullptr);
-                                if (walk.pending) continue;
-                                fin = path_advance<false>(s->d, st, rhit, rhu, rhv, rblocked, p->nb_ech, c, nullptr);
                                 continue;
                             }
                             if (voted) intersect_ray_voted<false>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);

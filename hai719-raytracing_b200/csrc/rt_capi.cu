@@ -351,6 +351,7 @@ struct WfArgs {
     unsigned int n_paths;              // paths of this chunk (slots 0 .. n_paths-1)
     unsigned int max_grab;             // batches a warp may fetch with one atomic (see wf_next_batch)
     unsigned int block;                // queue positions a warp reserves with one atomic (see wf_push)
+    int sort;                          // trace kernels from bounce 1 on: order every fetched window of the live queue by ray direction (wf_next_batch_sorted)
     int max_bounces, nb_ech, level;
     const float4 *cam_rays; const unsigned int *cam_keys;   // level 0 input, by slot
     // live queue of this level (trace input) ...
@@ -405,6 +406,8 @@ struct WfArgs {
 #define WQ_END 1
 #define WQ_N 2      /* entries really processed (padding excluded) */
 #define WQ_OUT 3    /* output queue k: WQ_OUT + 2k = next free position, + 1 = end of the block */
+#define WQ_BASE 9   /* sorted fetch: first position of the current window, and whether it was sorted */
+#define WQ_SORTED 10
 #define WQ_WORDS 12
 __device__ __forceinline__ unsigned int *wq_init(unsigned int (*all)[WQ_WORDS]) {
     unsigned int *ws = all[threadIdx.x >> 5];
@@ -430,6 +433,106 @@ __device__ __forceinline__ bool wf_next_batch(unsigned int *head, unsigned int c
     }
     base = cur;
     if ((threadIdx.x & 31u) == 0u) ws[WQ_CUR] = cur + 32u;
+    __syncwarp();
+    return true;
+}
+// Coherence from bounce 1 on. The entries of a live queue are in the order their paths were processed: neighbours are samples of
+// the same few pixels, so their rays start close to each other but leave in unrelated directions (a diffuse scatter covers the
+// hemisphere), and the 32 walks of a batch part ways at the first box: the trace kernels of config 2 ran 31 of 32 lanes at bounce 0
+// and 18 / 15 / 13 at bounces 1 / 2 / 3 (profiles/r02_notes.md). The producer therefore tags every live entry with a 6-bit
+// DIRECTION CODE (bits 26..31 of the queue word; path slots are below 2^26): the cell of its ray on an 8 x 8 octahedral map of the
+// sphere, cells numbered along a Morton curve, so that close codes are close directions. The consumer orders every window it
+// fetches (up to 8 batches = 256 entries with one atomic, wf_next_batch) by that code — a counting sort inside the warp:
+// __match_any_sync ranks, 64 counters and a 256-byte permutation per warp in shared memory — and takes its batches in sorted
+// order: 32 rays from nearby origins into nearby directions. Records are read at the permuted positions (a gather inside a
+// 4 KB window per array: every sector is still used by one of the window's batches). Results do not depend on the order in which
+// paths are processed (each path has its own slot, stream and records); only the order of queue entries changes.
+// MEASURED (profiles/r02_notes.md, r03d/e; config 2, 16 spp): lanes of the trace kernels 18.0 -> 20.4 / 14.6 -> 15.6 / 12.6 -> 13.8 at bounces
+// 1 / 2 / 3, warp instructions -6.5 % at bounce 1, but issue utilisation 82.5 -> 73.6 % behind the gathered record loads: frame 10.4 ->
+// 10.6 ms. The walks of a batch differ for reasons a 64-cell direction code over 256 neighbours does not capture. OFF (RT_WF_SORT=0:
+// plain slots in the queue words, no shared memory for the sort); make alt DEFS=-DRT_WF_SORT=1 builds it, HAI719_WF_SORT=0/1 then
+// switches it per call.
+#ifndef RT_WF_SORT
+#define RT_WF_SORT 0
+#endif
+#define WF_SLOT_MASK 0x03FFFFFFu
+__device__ __forceinline__ unsigned int wf_dir_code(V3 d) {
+    const float s = __fdividef(1.f, fabsf(d.x) + fabsf(d.y) + fabsf(d.z) + 1e-30f);
+    float u = d.x * s, v = d.y * s;
+    if (d.z < 0.f) { const float u2 = copysignf(1.f - fabsf(v), u), v2 = copysignf(1.f - fabsf(u), v); u = u2; v = v2; }
+    int iu = (int)(u * 4.f + 4.f), iv = (int)(v * 4.f + 4.f);
+    iu = iu < 0 ? 0 : (iu > 7 ? 7 : iu); iv = iv < 0 ? 0 : (iv > 7 ? 7 : iv);
+    const unsigned int a = (unsigned int)iu, b = (unsigned int)iv;
+    const unsigned int m = (a & 1u) | ((b & 1u) << 1) | ((a & 2u) << 1) | ((b & 2u) << 2) | ((a & 4u) << 2) | ((b & 4u) << 3);
+    return m > 62u ? 62u : m;   // 63 is what a padding word (WF_INVALID) decodes to: sorted to the end of its window
+}
+__device__ __forceinline__ unsigned int wf_live_word(unsigned int slot, V3 d) { return RT_WF_SORT ? slot | (wf_dir_code(d) << 26) : slot; }
+struct WfSortSm { unsigned char perm[256], rank[256]; unsigned short cnt[64]; };   // per warp
+// wf_next_batch with sorted windows: `pos` = the queue position this lane takes in this batch.
+__device__ __forceinline__ bool wf_next_batch_sorted(unsigned int *head, unsigned int count, unsigned int max_grab, unsigned int *ws, const unsigned int *q,
+                                                     WfSortSm *sm, unsigned int &pos) {
+    unsigned int cur = ws[WQ_CUR];
+    const unsigned int end = ws[WQ_END];
+    __syncwarp();
+    const unsigned int lane = threadIdx.x & 31u;
+    if (cur >= end) {   // warp-uniform
+        const unsigned int left = count > end ? count - end : 0u;
+        const unsigned int per_warp = left / (gridDim.x * (blockDim.x >> 5) * 64u);
+        const unsigned int grab = 32u * (per_warp < 1u ? 1u : (per_warp > max_grab ? max_grab : per_warp));
+        unsigned int b = 0;
+        if (lane == 0) b = atomicAdd(head, grab);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        if (b >= count) return false;
+        cur = b;
+        const unsigned int e = b + grab < count ? b + grab : count;
+        const unsigned int n = e - b;
+        const bool sorted = n > 32u && n <= 256u;
+        if (lane == 0) { ws[WQ_END] = e; ws[WQ_BASE] = b; ws[WQ_SORTED] = sorted ? 1u : 0u; }
+        if (sorted) {
+            sm->cnt[lane] = 0; sm->cnt[lane + 32u] = 0;
+            __syncwarp();
+            unsigned long long codes = 0ull;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (32u * j < n) {   // warp-uniform
+                    const unsigned int p = b + 32u * j + lane;
+                    unsigned int code = 63u;
+                    if (p < e) code = WF_LD(q + p) >> 26;
+                    const unsigned int peers = __match_any_sync(0xFFFFFFFFu, code);
+                    const unsigned int before = peers & ((1u << lane) - 1u);
+                    const unsigned int r = sm->cnt[code] + __popc(before);
+                    __syncwarp();
+                    if (before == 0u) sm->cnt[code] = (unsigned short)(sm->cnt[code] + __popc(peers));
+                    __syncwarp();
+                    sm->rank[32 * j + lane] = (unsigned char)r;
+                    codes |= (unsigned long long)code << (6 * j);
+                }
+            }
+            // exclusive prefix sum over the 64 counters: lane L owns codes 2L and 2L + 1
+            const unsigned int c0 = sm->cnt[2u * lane], c1 = sm->cnt[2u * lane + 1u];
+            unsigned int incl = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += t; }
+            const unsigned int excl = incl - (c0 + c1);
+            __syncwarp();
+            sm->cnt[2u * lane] = (unsigned short)excl; sm->cnt[2u * lane + 1u] = (unsigned short)(excl + c0);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (32u * j < n) {
+                    const unsigned int code = (unsigned int)(codes >> (6 * j)) & 63u;
+                    sm->perm[sm->cnt[code] + sm->rank[32 * j + lane]] = (unsigned char)(32 * j + lane);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    const unsigned int wb = ws[WQ_BASE];
+    unsigned int off = cur - wb + lane;
+    if (ws[WQ_SORTED]) off = sm->perm[off];
+    pos = wb + off;
+    __syncwarp();
+    if (lane == 0u) ws[WQ_CUR] = cur + 32u;
     __syncwarp();
     return true;
 }
@@ -501,10 +604,16 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
     const unsigned int count = MESH == 2 ? w.ctr[WF_NCTR * w.level + 11] : (w.level == 0 ? w.n_paths : w.ctr[WF_NCTR * w.level + 1]);
     __shared__ unsigned int wq_all[4][WQ_WORDS];
     unsigned int *const ws = wq_init(wq_all);
+    __shared__ WfSortSm sort_all[RT_WF_SORT && MESH != 2 ? 4 : 1];
+    const bool sorting = RT_WF_SORT && MESH != 2 && w.sort != 0 && w.level > 0;
     for (;;) {
-        unsigned int base;
-        if (!wf_next_batch(w.ctr + WF_NCTR * w.level + (MESH == 2 ? 10 : 0), count, w.max_grab, ws, base)) break;
-        unsigned int i = base + lane;
+        unsigned int base, i;
+        if (sorting) {
+            if (!wf_next_batch_sorted(w.ctr + WF_NCTR * w.level, count, w.max_grab, ws, w.q_live, sort_all + (RT_WF_SORT && MESH != 2 ? (threadIdx.x >> 5) : 0), i)) break;
+        } else {
+            if (!wf_next_batch(w.ctr + WF_NCTR * w.level + (MESH == 2 ? 10 : 0), count, w.max_grab, ws, base)) break;
+            i = base + lane;
+        }
         bool valid = i < count;
         const unsigned int mi = i;   // MESH == 2: position in the mesh-walk queue
         if (MESH == 2 && valid) {
@@ -526,6 +635,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
             } else {
                 slot = WF_LD(w.q_live + i);
                 valid = slot != WF_INVALID;
+                if (RT_WF_SORT) slot &= WF_SLOT_MASK;   // bits 26..31: direction code of the ray (wf_dir_code)
                 if (valid) {
                     const float4 a = WF_LD(w.ray0 + i), b = WF_LD(w.ray1 + i);
                     const uint2 g = WF_LD(w.rng_ray + i);
@@ -603,7 +713,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
             }
         }
         if (NOLIGHT) {
-            pos = wf_push(w.q_next, w.ctr + WF_NCTR * (w.level + 1) + 1, w.block, ws, 0, alive, slot);
+            pos = wf_push(w.q_next, w.ctr + WF_NCTR * (w.level + 1) + 1, w.block, ws, 0, alive, alive ? wf_live_word(slot, st.ray.d) : 0u);
             if (alive) wf_store_ray(w, pos, st);
         }
     }
@@ -711,7 +821,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
         // reserve the queue positions first (who is alive / parked is known by now), then write each path's records in the
         // branch that holds them in registers
         const bool alive = valid && !parked && !fin;
-        const unsigned int pos = wf_push(w.q_next, w.ctr + WF_NCTR * (w.level + 1) + 1, w.block, ws, 0, alive, st.path);   // st.path = the slot
+        const unsigned int pos = wf_push(w.q_next, w.ctr + WF_NCTR * (w.level + 1) + 1, w.block, ws, 0, alive, alive ? wf_live_word(st.path, st.ray.d) : 0u);   // st.path = the slot
         if (PHASE == 1) {
             wf_push(w.q_park, w.ctr + WF_NCTR * w.level + 5, w.block, ws, 1, parked && st.cl_n >= 0, hp);
             wf_push(w.q_over, w.ctr + WF_NCTR * w.level + 7, w.block, ws, 2, parked && st.cl_n < 0, hp);
@@ -792,7 +902,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_scatter(const DScene sce
                 alive = true;
             }
         }
-        const unsigned int pos = wf_push(w.q_next, w.ctr + WF_NCTR * (w.level + 1) + 1, w.block, ws, 0, alive, slot);
+        const unsigned int pos = wf_push(w.q_next, w.ctr + WF_NCTR * (w.level + 1) + 1, w.block, ws, 0, alive, alive ? wf_live_word(slot, next.d) : 0u);
         if (alive) {
             WF_ST(w.nray0 + pos, make_float4(next.o.x, next.o.y, next.o.z, next.time));
             WF_ST(w.nray1 + pos, make_float4(next.d.x, next.d.y, next.d.z, u2f((uint32_t)N | ((uint32_t)depth << 8))));
@@ -1887,6 +1997,10 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
             // mesh scenes: a batch can cost 100x another one (rays that walk a mesh vs rays that miss its box), so warps take
             // one batch at a time as before; analytic scenes: cheap, even batches, where the fetch atomics were the bottleneck
             w.max_grab = s->d.n_meshes > 0 ? 1u : 8u;
+            // windows of the live queue sorted by ray direction from bounce 1 on (wf_next_batch_sorted); HAI719_WF_SORT=0 / 1 overrides (A/B)
+            w.sort = RT_WF_SORT && w.max_grab > 1u ? 1 : 0;
+            if (const char *e = getenv("HAI719_WF_SORT")) w.sort = RT_WF_SORT && atoi(e) != 0 ? 1 : 0;
+            if (const char *e = getenv("HAI719_WF_GRAB")) { const int g_ = atoi(e); if (g_ >= 1 && g_ <= 8) w.max_grab = (unsigned int)g_; }
             // output positions a warp reserves per atomic: 256 where the queue atomics were the bottleneck (large chunks);
             // small chunks take small blocks, so that their queues are not mostly padding
             w.block = a.n_paths >= (4ull << 20) ? WF_MAX_BLOCK : (a.n_paths >= (256ull << 10) ? 64u : 32u);

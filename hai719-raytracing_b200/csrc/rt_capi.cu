@@ -802,6 +802,28 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
             }
         }
+        if (PHASE == 1 && LC && RT_OPT_LC_COLLECT) {
+            // classify: a live lane is always in mode 3 here (a light with candidates parks the path, one without goes on to the next
+            // light or scatters), so only the cone walk is compiled in (intersect_lc<.., COLLECT>) and the unoccluded light is
+            // finished right here (path_advance's mode-3 branch without its first-sample half)
+            for (;;) {
+                const bool mine = valid && !fin && !parked && st.mode == 3;
+                if (__ballot_sync(0xFFFFFFFFu, mine) == 0u) break;
+                Hit h;
+                float hu = 0.f, hv = 0.f;
+                bool blocked;
+                intersect_lc<STATS, false, true>(scene, st, true, mine, h, hu, hv, blocked, &cnt);
+                if (mine) {
+                    if (!lc_light_unoccluded(st)) parked = true;
+                    else {
+                        if (STATS) { cnt.shadow += w.nb_ech; cnt.rnd += 3 * w.nb_ech; }
+                        st.rng.ctr += 3u * (uint32_t)w.nb_ech;
+                        ++st.light;
+                        fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
+                    }
+                }
+            }
+        } else
         for (;;) {
             const bool live = valid && !fin && !parked && st.mode != 0;
             const unsigned int bt = __ballot_sync(0xFFFFFFFFu, live && st.mode == 3), bs = __ballot_sync(0xFFFFFFFFu, live && st.mode == 1);

@@ -1753,11 +1753,19 @@ RT_HD bool lc_shadow_analytic(const DScene &s, PathState &st, Counters *cnt) {
 #ifndef RT_OPT_LC_SLAB
 #define RT_OPT_LC_SLAB 1
 #endif
-template <bool STATS, bool CLOSEST = false>
-RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, Hit &h, float &hu, float &hv, bool &blocked,
+// COLLECT = true (the wavefront's classify kernel, k_wf_light phase 1: every lane that walks is in mode 3): only the cone walk and
+// the candidate collection are compiled in — no exact sphere / square tests in the leaves, no shadow-sample branch, no closest-hit
+// mesh walk. RT_OPT_LC_COLLECT=0 keeps the general function there (A/B).
+#ifndef RT_OPT_LC_COLLECT
+#define RT_OPT_LC_COLLECT 1
+#endif
+template <bool STATS, bool CLOSEST = false, bool COLLECT_ = false>
+RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t_, bool mine, Hit &h, float &hu, float &hv, bool &blocked,
                         Counters *cnt, bool with_meshes = true) {
     const Ray &ray = st.ray;
-    const int mode = CLOSEST && RT_OPT_LC_SLAB ? 0 : st.mode;
+    const bool COLLECT = COLLECT_ && RT_OPT_LC_COLLECT;
+    const bool run_t = (CLOSEST && RT_OPT_LC_SLAB) || COLLECT ? true : run_t_;
+    const int mode = CLOSEST && RT_OPT_LC_SLAB ? 0 : (COLLECT ? 3 : st.mode);
     h.type = 0; h.obj = -1; h.t = (mode == 0) ? FLT_MAX : st.t_light; h.ref = 0;
     blocked = false;
     bool done = !mine;
@@ -1765,7 +1773,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
     if (run_t) {
         if (mine) {
             const bool SLAB = CLOSEST && RT_OPT_LC_SLAB;
-            const bool collect = !SLAB && (mode == 3);
+            const bool collect = COLLECT || (!SLAB && (mode == 3));
             if (STATS && !collect) cnt->closest++;
             Cone cone;
             Inv32 iv32;
@@ -1995,7 +2003,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t, bool mine, H
         if (lc_shadow_analytic<STATS>(s, st, cnt)) { blocked = true; done = true; }
     }
 #endif
-    if (!with_meshes) return;
+    if (!with_meshes || COLLECT) return;   // mode 3 never walks the meshes here (done is set above)
     // meshes. Closest-hit rays, and shadow samples whose light has too many candidate triangles for the list, walk the
     // exact culling hierarchies (variant 3); other shadow samples test the listed candidates, mesh after mesh in the
     // reference's order, with the same per-triangle routine (bvh_consider) the walk uses.

@@ -730,6 +730,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
 //          hit-queue position to the shadow queue. Most hits of config 2 never leave this phase.
 // PHASE 2: the parked paths, now packed into full warps: the NB_ECH samples of the parked light, any further light
 //          (walk + samples inline), scatter.
+// PHASE 3: phase 2 for a scene with exactly ONE light (every BASELINE scene with lights): compiled for the sample tests only.
 // Split because a warp is as slow as its slowest lane: with both phases in one loop, one lane that has to sample keeps
 // 31 finished lanes waiting for ten rounds.
 template <bool STATS, bool LC, int PHASE>
@@ -739,9 +740,9 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
     Counters cnt;
     if (STATS) memset(&cnt, 0, sizeof cnt);
     const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int count = w.ctr[WF_NCTR * w.level + (PHASE == 2 ? 5 + 2 * w.which_park : 3)];
-    unsigned int *const head = w.ctr + WF_NCTR * w.level + (PHASE == 2 ? 4 + 2 * w.which_park : 2);
-    const unsigned int *const q_in = PHASE == 2 ? (w.which_park ? w.q_over : w.q_park) : w.q_hit;
+    const unsigned int count = w.ctr[WF_NCTR * w.level + (PHASE >= 2 ? 5 + 2 * w.which_park : 3)];
+    unsigned int *const head = w.ctr + WF_NCTR * w.level + (PHASE >= 2 ? 4 + 2 * w.which_park : 2);
+    const unsigned int *const q_in = PHASE >= 2 ? (w.which_park ? w.q_over : w.q_park) : w.q_hit;
     __shared__ unsigned int wq_all[4][WQ_WORDS];
     unsigned int *const ws = wq_init(wq_all);
     for (;;) {
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
         bool fin = true, parked = false;
         V3 c = v3(0.f);
         if (valid) {
-            if (PHASE == 2) {
+            if (PHASE >= 2) {
                 hp = WF_LD(q_in + i);
                 valid = hp != WF_INVALID;
                 if (valid) slot = WF_LD(w.q_hit + hp);
@@ -785,7 +786,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
             st.in_d = v3(h4.x, h4.y, h4.z);
             st.rng.key = g.x; st.rng.ctr = g.y;
             st.path = slot;
-            if (PHASE == 2) {
+            if (PHASE >= 2) {
                 const float4 p0 = WF_LD(w.park0 + hp), p1 = WF_LD(w.park1 + hp);
                 st.color = v3(p0.x, p0.y, p0.z);
                 st.light = (int)(f2u(p0.w) & 0xFFu); st.cl_n = (int)((f2u(p0.w) >> 8) & 0xFFu) - 1;
@@ -795,8 +796,13 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 }
                 st.cm0 = f2u(p1.x); st.cm1 = f2u(p1.y); st.cm2 = f2u(p1.z); st.cm3 = f2u(p1.w);
                 st.j = 0; st.blocked = 0; st.mode = 3;
-                Hit h; h.type = 0; h.obj = -1; h.t = 0.f; h.ref = 0;
-                fin = path_advance<STATS, LC, true>(scene, st, h, 0.f, 0.f, false, w.nb_ech, c, &cnt);   // candidates known: first sample
+                if (PHASE == 3) {
+                    path_shadow_sample<STATS, true>(scene, st, &cnt);   // candidates known: first sample
+                    fin = false;
+                } else {
+                    Hit h; h.type = 0; h.obj = -1; h.t = 0.f; h.ref = 0;
+                    fin = path_advance<STATS, LC, true>(scene, st, h, 0.f, 0.f, false, w.nb_ech, c, &cnt);   // candidates known: first sample
+                }
             } else {
                 st.color = v3(0.f); st.light = 0; st.mode = 0;
                 fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
@@ -821,6 +827,22 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                         ++st.light;
                         fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
                     }
+                }
+            }
+        } else if (PHASE == 3) {
+            // samples of a scene with ONE light: a live lane is always in mode 1 here (after the last sample the path scatters: there
+            // is no further light to collect candidates for), so only the sample tests are compiled in (intersect_lc<.., SAMPLE>)
+            for (;;) {
+                const bool mine = valid && !fin && st.mode == 1;
+                if (__ballot_sync(0xFFFFFFFFu, mine) == 0u) break;
+                Hit h;
+                float hu = 0.f, hv = 0.f;
+                bool blocked;
+                intersect_lc<STATS, false, false, true>(scene, st, false, mine, h, hu, hv, blocked, &cnt);
+                if (mine) {
+                    if (blocked) ++st.blocked;
+                    if (++st.j < w.nb_ech) path_shadow_sample<STATS, true>(scene, st, &cnt);
+                    else fin = path_finish_light<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);   // light 1 of 1: scatters
                 }
             }
         } else
@@ -868,7 +890,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
         wf_out_finish(w.q_park, ws, 1);
         wf_out_finish(w.q_over, ws, 2);
     }
-    if (PHASE != 2) wf_count_entries(w.ctr + WF_NCTR * w.level + 9, ws);   // hits of this level
+    if (PHASE < 2) wf_count_entries(w.ctr + WF_NCTR * w.level + 9, ws);   // hits of this level
     if (STATS) flush_counters(cnt, w.stats);
 }
 
@@ -1961,6 +1983,7 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     // light stage: one kernel (no masks to classify by) or walk/classify + sample (see k_wf_light)
     LightKernel wf_light = want_stats ? (wf_lc ? k_wf_light<true, true, 1> : k_wf_light<true, false, 0>) : (wf_lc ? k_wf_light<false, true, 1> : k_wf_light<false, false, 0>);
     LightKernel wf_light_b = want_stats ? k_wf_light<true, true, 2> : k_wf_light<false, true, 2>;
+    if (s->d.n_lights == 1 && RT_OPT_LC_COLLECT) wf_light_b = want_stats ? k_wf_light<true, true, 3> : k_wf_light<false, true, 3>;
     // no lights: the light stage is only the scatter (k_wf_scatter); wavefront variant bit 27 keeps the general kernel (A/B)
     const bool wf_scatter_only = s->d.n_lights == 0 && !wf_nolight && ((p->variant >> 27) & 1) == 0;
     if (wf_scatter_only) wf_light = want_stats ? k_wf_scatter<true> : k_wf_scatter<false>;

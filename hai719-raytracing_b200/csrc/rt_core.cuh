@@ -1759,13 +1759,15 @@ RT_HD bool lc_shadow_analytic(const DScene &s, PathState &st, Counters *cnt) {
 #ifndef RT_OPT_LC_COLLECT
 #define RT_OPT_LC_COLLECT 1
 #endif
-template <bool STATS, bool CLOSEST = false, bool COLLECT_ = false>
+// SAMPLE = true (the sample kernel of a one-light scene, k_wf_light phase 3: every lane that works is in mode 1): only the
+// candidate tests of a shadow sample (masks, triangle list or mesh walk) are compiled in.
+template <bool STATS, bool CLOSEST = false, bool COLLECT_ = false, bool SAMPLE_ = false>
 RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t_, bool mine, Hit &h, float &hu, float &hv, bool &blocked,
                         Counters *cnt, bool with_meshes = true) {
     const Ray &ray = st.ray;
-    const bool COLLECT = COLLECT_ && RT_OPT_LC_COLLECT;
-    const bool run_t = (CLOSEST && RT_OPT_LC_SLAB) || COLLECT ? true : run_t_;
-    const int mode = CLOSEST && RT_OPT_LC_SLAB ? 0 : (COLLECT ? 3 : st.mode);
+    const bool COLLECT = COLLECT_ && RT_OPT_LC_COLLECT, SAMPLE = SAMPLE_ && RT_OPT_LC_COLLECT;
+    const bool run_t = SAMPLE ? false : ((CLOSEST && RT_OPT_LC_SLAB) || COLLECT ? true : run_t_);
+    const int mode = SAMPLE ? 1 : (CLOSEST && RT_OPT_LC_SLAB ? 0 : (COLLECT ? 3 : st.mode));
     h.type = 0; h.obj = -1; h.t = (mode == 0) ? FLT_MAX : st.t_light; h.ref = 0;
     blocked = false;
     bool done = !mine;

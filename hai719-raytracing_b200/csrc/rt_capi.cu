@@ -590,6 +590,7 @@ __device__ __forceinline__ void wf_store_ray(const WfArgs &w, unsigned int pos, 
     WF_ST(w.nrng + pos, make_uint2(st.rng.key, st.rng.ctr));
 }
 
+// MESH = 3: the scene has no meshes (neither the walk nor the triangle shading is compiled in).
 // MESH = 0: one kernel per level, analytic primitives and meshes. MESH = 1 / 2: two kernels. Phase 1 intersects the analytic
 // primitives and asks ray_touches_meshes: rays that cannot hit a mesh are shaded at once; the others go to a queue with their
 // analytic hit so far. Phase 2 walks the meshes for THOSE rays only and shades them. Two smaller kernels (frames of 320 and
@@ -665,7 +666,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
             }
             meshes_walk_merged<STATS>(scene, st.ray, 0, st.rng, h, blocked, done, &cnt);
         } else if (LC) {
-            intersect_lc<STATS, true>(scene, st, true, valid, h, hu, hv, blocked, &cnt, MESH == 0);
+            intersect_lc<STATS, true>(scene, st, true, valid, h, hu, hv, blocked, &cnt, MESH == 0);   // MESH == 3: a scene without meshes
         } else {
             intersect_ray<STATS, true>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
         }
@@ -687,7 +688,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
         bool alive = false;
         if (valid) {
             V3 c;
-            if (path_shade<STATS, true>(scene, st, h, hu, hv, c, &cnt)) {
+            if (path_shade<STATS, true, MESH == 3>(scene, st, h, hu, hv, c, &cnt)) {
                 float *o = w.samples + 3ull * slot;
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
             } else if (NOLIGHT) {
@@ -1979,6 +1980,7 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
                                                : (wf_nolight ? k_wf_trace<true, false, true, 0> : k_wf_trace<true, false, false, 0>))
                                       : (wf_lc ? (wf_nolight ? k_wf_trace<false, true, true, 0> : wf_split ? k_wf_trace<false, true, false, 1> : k_wf_trace<false, true, false, 0>)
                                                : (wf_nolight ? k_wf_trace<false, false, true, 0> : k_wf_trace<false, false, false, 0>));
+    if (wf_lc && !wf_nolight && s->d.n_meshes == 0 && RT_OPT_LC_COLLECT) wf_trace = want_stats ? k_wf_trace<true, true, false, 3> : k_wf_trace<false, true, false, 3>;
     TraceKernel wf_trace_mesh = want_stats ? k_wf_trace<true, true, false, 2> : k_wf_trace<false, true, false, 2>;
     // light stage: one kernel (no masks to classify by) or walk/classify + sample (see k_wf_light)
     LightKernel wf_light = want_stats ? (wf_lc ? k_wf_light<true, true, 1> : k_wf_light<true, false, 0>) : (wf_lc ? k_wf_light<false, true, 1> : k_wf_light<false, false, 0>);

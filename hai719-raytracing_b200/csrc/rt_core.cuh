@@ -2145,7 +2145,8 @@ RT_HD bool path_next_light_or_bounce(const DScene &s, PathState &st, int nb_ech,
 
 // Shade the closest hit of st.ray (Scene.h:270-304): on a miss the path ends (true, result in `out`); otherwise the
 // hit context (P, n, kd, e, mat, in_d) is set up for lighting.
-template <bool STATS, bool WF = false>
+// NOMESH: the scene has no meshes (the triangle branch is not compiled in).
+template <bool STATS, bool WF = false, bool NOMESH = false>
 RT_HD bool path_shade(const DScene &s, PathState &st, const Hit &h, float hu, float hv, V3 &out, Counters *cnt) {
     const Ray &ray = st.ray;
     if (h.type == 0) { out = path_fold<WF>(st, sky_color<STATS>(s, ray.d, st.N, cnt)); st.mode = 2; return true; }
@@ -2164,7 +2165,7 @@ RT_HD bool path_shade(const DScene &s, PathState &st, const Hit &h, float hu, fl
             material_texture<STATS>(s, *mat, kd, tu, tv, cnt);
         }
         e = material_emit<STATS>(s, *mat, tu, tv, cnt);
-    } else if (h.type == 2) {
+    } else if (NOMESH || h.type == 2) {
         mat = s.sq_mat + h.obj;
         const DSquare &q = s.squares[h.obj];
         P = ray.o + h.t * ray.d;

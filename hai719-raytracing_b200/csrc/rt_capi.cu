@@ -734,7 +734,9 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
 // PHASE 3: phase 2 for a scene with exactly ONE light (every BASELINE scene with lights): compiled for the sample tests only.
 // Split because a warp is as slow as its slowest lane: with both phases in one loop, one lane that has to sample keeps
 // 31 finished lanes waiting for ten rounds.
-template <bool STATS, bool LC, int PHASE>
+// NOMESH: the scene has no meshes (phases 1 and 3): no candidate-triangle collection, list or mesh walk is compiled in — the sample kernel
+// then needs no traversal stack at all.
+template <bool STATS, bool LC, int PHASE, bool NOMESH = false>
 __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene_, const WfArgs w) {
     const DScene &scene = RT_S(scene_);
     stage_abvh(scene);
@@ -791,7 +793,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 const float4 p0 = WF_LD(w.park0 + hp), p1 = WF_LD(w.park1 + hp);
                 st.color = v3(p0.x, p0.y, p0.z);
                 st.light = (int)(f2u(p0.w) & 0xFFu); st.cl_n = (int)((f2u(p0.w) >> 8) & 0xFFu) - 1;
-                for (int q4 = 0; q4 * 4 < st.cl_n; ++q4) {
+                for (int q4 = 0; !NOMESH && q4 * 4 < st.cl_n; ++q4) {
                     const float4 v = WF_LD(w.park2 + (size_t)q4 * w.park_stride + hp);
                     st.cl[4 * q4] = f2u(v.x); st.cl[4 * q4 + 1] = f2u(v.y); st.cl[4 * q4 + 2] = f2u(v.z); st.cl[4 * q4 + 3] = f2u(v.w);
                 }
@@ -819,7 +821,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 Hit h;
                 float hu = 0.f, hv = 0.f;
                 bool blocked;
-                intersect_lc<STATS, false, true>(scene, st, true, mine, h, hu, hv, blocked, &cnt);
+                intersect_lc<STATS, false, true>(scene, st, true, mine, h, hu, hv, blocked, &cnt, !NOMESH);
                 if (mine) {
                     if (!lc_light_unoccluded(st)) parked = true;
                     else {
@@ -839,7 +841,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 Hit h;
                 float hu = 0.f, hv = 0.f;
                 bool blocked;
-                intersect_lc<STATS, false, false, true>(scene, st, false, mine, h, hu, hv, blocked, &cnt);
+                intersect_lc<STATS, false, false, true>(scene, st, false, mine, h, hu, hv, blocked, &cnt, !NOMESH);
                 if (mine) {
                     if (blocked) ++st.blocked;
                     if (++st.j < w.nb_ech) path_shadow_sample<STATS, true>(scene, st, &cnt);
@@ -874,7 +876,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
         if (valid) {
             if (parked) {
                 WF_ST(w.park0 + hp, make_float4(st.color.x, st.color.y, st.color.z, u2f((uint32_t)st.light | ((uint32_t)(st.cl_n + 1) << 8))));
-                for (int q4 = 0; q4 * 4 < st.cl_n; ++q4)
+                for (int q4 = 0; !NOMESH && q4 * 4 < st.cl_n; ++q4)
                     WF_ST(w.park2 + (size_t)q4 * w.park_stride + hp, make_float4(u2f(st.cl[4 * q4]), u2f(st.cl[4 * q4 + 1]), u2f(st.cl[4 * q4 + 2]), u2f(st.cl[4 * q4 + 3])));
                 WF_ST(w.park1 + hp, make_float4(u2f(st.cm0), u2f(st.cm1), u2f(st.cm2), u2f(st.cm3)));
                 WF_ST(w.rng_hit + hp, make_uint2(st.rng.key, st.rng.ctr));
@@ -1986,6 +1988,10 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     LightKernel wf_light = want_stats ? (wf_lc ? k_wf_light<true, true, 1> : k_wf_light<true, false, 0>) : (wf_lc ? k_wf_light<false, true, 1> : k_wf_light<false, false, 0>);
     LightKernel wf_light_b = want_stats ? k_wf_light<true, true, 2> : k_wf_light<false, true, 2>;
     if (s->d.n_lights == 1 && RT_OPT_LC_COLLECT) wf_light_b = want_stats ? k_wf_light<true, true, 3> : k_wf_light<false, true, 3>;
+    if (wf_lc && s->d.n_meshes == 0 && RT_OPT_LC_COLLECT) {
+        wf_light = want_stats ? k_wf_light<true, true, 1, true> : k_wf_light<false, true, 1, true>;
+        if (s->d.n_lights == 1) wf_light_b = want_stats ? k_wf_light<true, true, 3, true> : k_wf_light<false, true, 3, true>;
+    }
     // no lights: the light stage is only the scatter (k_wf_scatter); wavefront variant bit 27 keeps the general kernel (A/B)
     const bool wf_scatter_only = s->d.n_lights == 0 && !wf_nolight && ((p->variant >> 27) & 1) == 0;
     if (wf_scatter_only) wf_light = want_stats ? k_wf_scatter<true> : k_wf_scatter<false>;

@@ -1916,7 +1916,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t_, bool mine, 
                 // (same margins as lc_cannot_occlude; a NaN plane fails both tests and stays).
                 int cn = 0;
                 const float plen = length(st.P);
-                for (int i = 0; i < s.n_meshes && cn >= 0; ++i) {
+                for (int i = 0; with_meshes && i < s.n_meshes && cn >= 0; ++i) {   // with_meshes = false: the caller knows the scene has none
                     const DMesh &m = s.meshes[i];
                     if (STATS) cnt->mesh++;
                     int msp = 0;

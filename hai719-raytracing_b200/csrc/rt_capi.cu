@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
         bool alive = false;
         if (valid) {
             V3 c;
-            if (path_shade<STATS, true, MESH == 3>(scene, st, h, hu, hv, c, &cnt)) {
+            if (path_shade<STATS, true, MESH == 3 || MESH == 1>(scene, st, h, hu, hv, c, &cnt)) {   // MESH == 1: rays that may hit a mesh have left for the walk kernel
                 float *o = w.samples + 3ull * slot;
                 o[0] = c.x; o[1] = c.y; o[2] = c.z;
             } else if (NOLIGHT) {

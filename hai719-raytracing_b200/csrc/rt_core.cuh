@@ -605,9 +605,11 @@ struct TStack {
 // the relative one of the FMA itself, so the per-ray slack constant grows by 2^-22 max_axis |o * iv| (4x that bound). A ray
 // almost parallel to an axis (|d| < 1e-6) thereby loses its culling - it visits more boxes, never fewer: the hierarchies
 // only filter. 6 instructions fewer per box of ~32. Measured on B200 (profiles/r01_notes.md, r01t): config 3 -2 %, configs 2,
-// 4 and 5 +0.7 % (a few more spill bytes; the walks wait on loads, not on issue slots) - OFF.
+// 4 and 5 +0.7 % (a few more spill bytes; the walks wait on loads, not on issue slots) - off THEN. Round 2, on the kernels compiled
+// for one mode each (smaller frames, issue utilisation ~80 %; profiles/r02_notes.md, r03n): config 2 32.6 -> 31.6 ms (64 spp), config 3
+// 66.2 -> 62.9, config 4 60.1 -> 58.5, config 5 56.4 -> 55.3 with both this and RT_OPT_CONEFMA - ON.
 #ifndef RT_OPT_BOXFMA
-#define RT_OPT_BOXFMA 0
+#define RT_OPT_BOXFMA 1
 #endif
 struct Inv32 {
     float x, y, z;
@@ -1611,7 +1613,7 @@ RT_HD void intersect_ray_voted(const DScene &s, const Ray &ray, int mode, float 
 // delta = 0 it is the ordinary slab test, so closest-hit rays (mode 0) and cones (mode 3) run the
 // same instructions side by side.
 #ifndef RT_OPT_CONEFMA
-#define RT_OPT_CONEFMA 0   /* the same FMA form as bvh_box (RT_OPT_BOXFMA) for the cone: 7 more live registers per lane */
+#define RT_OPT_CONEFMA 1   /* the same FMA form as bvh_box (RT_OPT_BOXFMA) for the cone: 7 more live registers per lane */
 #endif
 struct Cone {
     V3 o;

@@ -1,0 +1,7 @@
+# round 2, call 3o (1 GPU): FMA box tests on by default + triangle shading out of the analytic trace kernel: parity, timings
+mkdir -p gpurun_out/r03o
+O=gpurun_out/r03o
+timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "rc=$?" >> $O/pytest.log
+tail -3 $O/pytest.log
+for args in "c2 16 0" "c2 64 0" "c4 4 0" "c5 2 0" "c3 2 0" "c3 2 6" "c1 1 0"; do timeout 300 python tools/variance_probe.py $args 2>&1 | grep "^upload 0" >> $O/timings.log; done
+cat $O/timings.log

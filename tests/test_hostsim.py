@@ -37,9 +37,10 @@ def sim(hb):
 
 @pytest.fixture(scope="module")
 def sim_fma(hb):
-    """The same functions with the box tests of the culling hierarchies in their one-FMA-per-plane form
-    (RT_OPT_BOXFMA / RT_OPT_CONEFMA, off by default): a different conservative filter, so the same bits."""
-    return _load_sim(hb, "libhostsim_fma.so", ["-DRT_OPT_BOXFMA=1", "-DRT_OPT_CONEFMA=1"])
+    """The same functions with the box tests of the culling hierarchies in the OTHER form: subtract-then-multiply planes
+    instead of one FMA per plane (RT_OPT_BOXFMA / RT_OPT_CONEFMA = 0; the product build has both on since round 2): a
+    different conservative filter, so the same bits."""
+    return _load_sim(hb, "libhostsim_nofma.so", ["-DRT_OPT_BOXFMA=0", "-DRT_OPT_CONEFMA=0"])
 
 
 @pytest.fixture(scope="module")

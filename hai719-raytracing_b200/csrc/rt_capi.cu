@@ -736,7 +736,8 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
 // 31 finished lanes waiting for ten rounds.
 // NOMESH: the scene has no meshes (phases 1 and 3): no candidate-triangle collection, list or mesh walk is compiled in — the sample kernel
 // then needs no traversal stack at all.
-template <bool STATS, bool LC, int PHASE, bool NOMESH = false>
+// OVER (phase 3): 0 = the park queue (every entry has its candidate-triangle list), 1 = the overflow queue (every entry walks the meshes).
+template <bool STATS, bool LC, int PHASE, bool NOMESH = false, int OVER = 0>
 __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene_, const WfArgs w) {
     const DScene &scene = RT_S(scene_);
     stage_abvh(scene);
@@ -793,7 +794,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 const float4 p0 = WF_LD(w.park0 + hp), p1 = WF_LD(w.park1 + hp);
                 st.color = v3(p0.x, p0.y, p0.z);
                 st.light = (int)(f2u(p0.w) & 0xFFu); st.cl_n = (int)((f2u(p0.w) >> 8) & 0xFFu) - 1;
-                for (int q4 = 0; !NOMESH && q4 * 4 < st.cl_n; ++q4) {
+                for (int q4 = 0; !NOMESH && !(PHASE == 3 && OVER) && q4 * 4 < st.cl_n; ++q4) {
                     const float4 v = WF_LD(w.park2 + (size_t)q4 * w.park_stride + hp);
                     st.cl[4 * q4] = f2u(v.x); st.cl[4 * q4 + 1] = f2u(v.y); st.cl[4 * q4 + 2] = f2u(v.z); st.cl[4 * q4 + 3] = f2u(v.w);
                 }
@@ -841,7 +842,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 Hit h;
                 float hu = 0.f, hv = 0.f;
                 bool blocked;
-                intersect_lc<STATS, false, false, true>(scene, st, false, mine, h, hu, hv, blocked, &cnt, !NOMESH);
+                intersect_lc<STATS, false, false, NOMESH ? 1 : (OVER ? 3 : 2)>(scene, st, false, mine, h, hu, hv, blocked, &cnt, !NOMESH);
                 if (mine) {
                     if (blocked) ++st.blocked;
                     if (++st.j < w.nb_ech) path_shadow_sample<STATS, true>(scene, st, &cnt);
@@ -1988,6 +1989,8 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     LightKernel wf_light = want_stats ? (wf_lc ? k_wf_light<true, true, 1> : k_wf_light<true, false, 0>) : (wf_lc ? k_wf_light<false, true, 1> : k_wf_light<false, false, 0>);
     LightKernel wf_light_b = want_stats ? k_wf_light<true, true, 2> : k_wf_light<false, true, 2>;
     if (s->d.n_lights == 1 && RT_OPT_LC_COLLECT) wf_light_b = want_stats ? k_wf_light<true, true, 3> : k_wf_light<false, true, 3>;
+    LightKernel wf_light_over = wf_light_b;   // the overflow queue's launch
+    if (s->d.n_lights == 1 && s->d.n_meshes > 0 && RT_OPT_LC_COLLECT) wf_light_over = want_stats ? k_wf_light<true, true, 3, false, 1> : k_wf_light<false, true, 3, false, 1>;
     if (wf_lc && s->d.n_meshes == 0 && RT_OPT_LC_COLLECT) {
         wf_light = want_stats ? k_wf_light<true, true, 1, true> : k_wf_light<false, true, 1, true>;
         if (s->d.n_lights == 1) wf_light_b = want_stats ? k_wf_light<true, true, 3, true> : k_wf_light<false, true, 3, true>;
@@ -2105,7 +2108,7 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
                     ++launches;
                     if (s->d.n_meshes > 0) {   // lights whose candidate-triangle list overflowed, in warps of their own
                         w.which_park = 1;
-                        wf_light_b<<<gl, 128, 0, st>>>(s->d, w);
+                        wf_light_over<<<gl, 128, 0, st>>>(s->d, w);
                         RT_CUDA(cudaGetLastError());
                         ++launches;
                         w.which_park = 0;

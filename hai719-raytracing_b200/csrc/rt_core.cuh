@@ -1763,11 +1763,13 @@ RT_HD bool lc_shadow_analytic(const DScene &s, PathState &st, Counters *cnt) {
 #endif
 // SAMPLE = true (the sample kernel of a one-light scene, k_wf_light phase 3: every lane that works is in mode 1): only the
 // candidate tests of a shadow sample (masks, triangle list or mesh walk) are compiled in.
-template <bool STATS, bool CLOSEST = false, bool COLLECT_ = false, bool SAMPLE_ = false>
+// SAMPLE_ = 2 / 3: moreover every lane is known to hold a candidate-triangle list (cl_n >= 0) / to have overflowed it (cl_n < 0): the
+// park queue and the overflow queue are sampled by separate launches, each compiled for its half.
+template <bool STATS, bool CLOSEST = false, bool COLLECT_ = false, int SAMPLE_ = 0>
 RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t_, bool mine, Hit &h, float &hu, float &hv, bool &blocked,
                         Counters *cnt, bool with_meshes = true) {
     const Ray &ray = st.ray;
-    const bool COLLECT = COLLECT_ && RT_OPT_LC_COLLECT, SAMPLE = SAMPLE_ && RT_OPT_LC_COLLECT;
+    const bool COLLECT = COLLECT_ && RT_OPT_LC_COLLECT, SAMPLE = SAMPLE_ != 0 && RT_OPT_LC_COLLECT;
     const bool run_t = SAMPLE ? false : ((CLOSEST && RT_OPT_LC_SLAB) || COLLECT ? true : run_t_);
     const int mode = SAMPLE ? 1 : (CLOSEST && RT_OPT_LC_SLAB ? 0 : (COLLECT ? 3 : st.mode));
     h.type = 0; h.obj = -1; h.t = (mode == 0) ? FLT_MAX : st.t_light; h.ref = 0;
@@ -2011,7 +2013,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t_, bool mine, 
     // meshes. Closest-hit rays, and shadow samples whose light has too many candidate triangles for the list, walk the
     // exact culling hierarchies (variant 3); other shadow samples test the listed candidates, mesh after mesh in the
     // reference's order, with the same per-triangle routine (bvh_consider) the walk uses.
-    if (mode == 1 && !run_t && st.cl_n >= 0) {
+    if (mode == 1 && !run_t && (SAMPLE && SAMPLE_ == 2 ? true : (SAMPLE && SAMPLE_ == 3 ? false : st.cl_n >= 0))) {
         int k = 0;
         while (k < st.cl_n && !done) {
             const uint32_t mi = st.cl[k] >> 27;

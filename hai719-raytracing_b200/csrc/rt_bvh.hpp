@@ -348,6 +348,11 @@ struct AnalyticAccel {
     int32_t root = -1;             // -1: not built (too few or too many primitives)
     float center[3] = {0, 0, 0};
     float radius = 0.f;
+    // a ball that holds every sphere CENTRE at every time in [0, 1]: |o - c_i| <= |o - center_s| + radius_s for every sphere i, which is all
+    // the quadratic term of the per-ray padding needs (eps |o - c|^2 / r); (center, radius) also holds the squares — one large ground
+    // square put R at ~70 in the random-spheres scene and padded a sphere of radius 0.2 by 0.05 (profiles/r02_notes.md, r03r/s)
+    float center_s[3] = {0, 0, 0};
+    float radius_s = 0.f;
 };
 
 inline void build_analytic_accel(const RtSceneDesc &d, AnalyticAccel &out) {
@@ -402,6 +407,25 @@ inline void build_analytic_accel(const RtSceneDesc &d, AnalyticAccel &out) {
     float r2 = 0.f;
     for (int a = 0; a < 3; ++a) { out.center[a] = 0.5f * (all.lo[a] + all.hi[a]); const float h = 0.5f * (all.hi[a] - all.lo[a]); r2 += h * h; }
     out.radius = std::sqrt(r2);
+    {
+        Box cs; cs.reset();
+        bool any = false;
+        for (uint32_t i = 0; i < d.n_spheres; ++i) {
+            const RtSphere &s = d.spheres[i];
+            float c0[3], c1[3];
+            bool finite = true;
+            for (int a = 0; a < 3; ++a) { c0[a] = s.center[a]; c1[a] = s.center[a] + s.material.motion[a]; finite = finite && std::isfinite(c0[a]) && std::isfinite(c1[a]); }
+            if (!finite) continue;   // its box is everything: always visited, whatever the padding
+            cs.grow(c0); cs.grow(c1); any = true;
+        }
+        float q2 = 0.f;
+        for (int a = 0; a < 3; ++a) {
+            out.center_s[a] = any ? 0.5f * (cs.lo[a] + cs.hi[a]) : out.center[a];
+            const float h = any ? 0.5f * (cs.hi[a] - cs.lo[a]) : 0.f;
+            q2 += h * h;
+        }
+        out.radius_s = std::sqrt(q2) * 1.0001f + 1e-6f;   // the device adds time * motion in float
+    }
     int max_depth = 0;
     int32_t root = build(prims, 0, prims.size(), out, false, 0, max_depth, RT_BVH_LEAF_ANALYTIC);
     if (max_depth > 56) { out.nodes.clear(); out.tris.clear(); max_depth = 0; root = build(prims, 0, prims.size(), out, true, 0, max_depth, RT_BVH_LEAF_ANALYTIC); }

@@ -1642,6 +1642,8 @@ int upload_analytic(RtScene *s, const RtSceneDesc *desc, bool update) {
         d.abvh_n_nodes = (int)(aa.nodes.size() / 4);
         for (int k = 0; k < 3; ++k) d.abvh_c[k] = aa.center[k];
         d.abvh_r = aa.radius;
+        for (int k = 0; k < 3; ++k) d.abvh_cs[k] = aa.center_s[k];
+        d.abvh_rs = aa.radius_s;
         if (aa.root >= 0) {
             if (!update) {
                 // a binary hierarchy over n primitives has at most n - 1 inner nodes (4 float4 each) and n leaf entries,

@@ -247,6 +247,7 @@ struct DScene {
     int abvh_root;
     int abvh_n_nodes;          // inner nodes of that hierarchy (<= 127: it is only built for <= 128 primitives)
     float abvh_c[3], abvh_r;
+    float abvh_cs[3], abvh_rs;   // ball of the sphere centres (quadratic term of the per-ray padding), see AnalyticAccel
     const DMaterial *sph_mat, *sq_mat, *mesh_mat;
     const DLight *lights;
     const DImage *textures, *normal_maps;
@@ -916,8 +917,8 @@ template <bool STATS, class F>
 RT_HD void analytic_candidates(const DScene &s, const Ray &ray, const float &limit, F &&f, Counters *cnt) {
     const Inv32 iv = make_inv32(ray);
     // per-ray enlargement (see build_analytic_accel): quadratic term x 1/r of the spheres below, plus a linear term
-    const float dist = length(ray.o - ld3(s.abvh_c)) + s.abvh_r;
-    const float kq = 32.f * 5.96e-8f * dist * dist, kl = 64.f * 5.96e-8f * dist;
+    const float dist = length(ray.o - ld3(s.abvh_c)) + s.abvh_r, dist_s = length(ray.o - ld3(s.abvh_cs)) + s.abvh_rs;
+    const float kq = 32.f * 5.96e-8f * dist_s * dist_s, kl = 64.f * 5.96e-8f * dist;
     TStack stack;
     int sp = 0;
     int node = s.abvh_root;
@@ -1491,8 +1492,8 @@ RT_HD void intersect_ray_voted(const DScene &s, const Ray &ray, int mode, float 
     int best_seq = 0x7FFFFFFF;
     uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
     if (s.abvh_root >= 0) {
-        const float dist = length(ray.o - ld3(s.abvh_c)) + s.abvh_r;
-        kq = 32.f * 5.96e-8f * dist * dist; kl = 64.f * 5.96e-8f * dist;
+        const float dist = length(ray.o - ld3(s.abvh_c)) + s.abvh_r, dist_s = length(ray.o - ld3(s.abvh_cs)) + s.abvh_rs;
+        kq = 32.f * 5.96e-8f * dist_s * dist_s; kl = 64.f * 5.96e-8f * dist;
         node = s.abvh_root;
     }
     for (;;) {
@@ -1799,8 +1800,8 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t_, bool mine, 
                 cone = make_cone(ray.o, ray.d, 0.f);
             }
             const SphereRay sr = make_sphere_ray(ray);
-            const float dist = length(cone.o - ld3(s.abvh_c)) + s.abvh_r;
-            const float kq = 32.f * 5.96e-8f * dist * dist, kl = 64.f * 5.96e-8f * dist;
+            const float dist = length(cone.o - ld3(s.abvh_c)) + s.abvh_r, dist_s = length(cone.o - ld3(s.abvh_cs)) + s.abvh_rs;
+            const float kq = 32.f * 5.96e-8f * dist_s * dist_s, kl = 64.f * 5.96e-8f * dist;
             uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
             int best_seq = 0x7FFFFFFF;
             TStack stack;

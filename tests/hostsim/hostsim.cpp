@@ -100,6 +100,8 @@ void *sim_scene_create(const RtSceneDesc *desc) {
     d.abvh_root = s->aa.root; d.abvh_n_nodes = (int)(s->aa.nodes.size() / 4); d.abvh_nodes = s->aa.nodes.data(); d.abvh_prims = s->aa.tris.data();
     for (int k = 0; k < 3; ++k) d.abvh_c[k] = s->aa.center[k];
     d.abvh_r = s->aa.radius;
+    for (int k = 0; k < 3; ++k) d.abvh_cs[k] = s->aa.center_s[k];
+    d.abvh_rs = s->aa.radius_s;
     const uint32_t nm = desc->n_meshes;
     if (!pack_meshes(*desc, s->pk).empty()) { delete s; return nullptr; }
     build_accel(*desc, s->pk, s->ac);

@@ -801,7 +801,8 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 st.cm0 = f2u(p1.x); st.cm1 = f2u(p1.y); st.cm2 = f2u(p1.z); st.cm3 = f2u(p1.w);
                 st.j = 0; st.blocked = 0; st.mode = 3;
                 if (PHASE == 3) {
-                    path_shadow_sample<STATS, true>(scene, st, &cnt);   // candidates known: first sample
+                    if (NOMESH) path_shadow_sample_body<STATS, true>(scene, st, &cnt);   // candidates known: first sample (normalisations inlined: see normalized_inl)
+                    else path_shadow_sample<STATS, true>(scene, st, &cnt);
                     fin = false;
                 } else {
                     Hit h; h.type = 0; h.obj = -1; h.t = 0.f; h.ref = 0;
@@ -845,7 +846,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene
                 intersect_lc<STATS, false, false, NOMESH ? 1 : (OVER ? 3 : 2)>(scene, st, false, mine, h, hu, hv, blocked, &cnt, !NOMESH);
                 if (mine) {
                     if (blocked) ++st.blocked;
-                    if (++st.j < w.nb_ech) path_shadow_sample<STATS, true>(scene, st, &cnt);
+                    if (++st.j < w.nb_ech) { if (NOMESH) path_shadow_sample_body<STATS, true>(scene, st, &cnt); else path_shadow_sample<STATS, true>(scene, st, &cnt); }
                     else fin = path_finish_light<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);   // light 1 of 1: scatters
                 }
             }

@@ -142,6 +142,10 @@ RT_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * 
 RT_HD V3 comp_product(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
 RT_HD float length(V3 a) { return sqrtf(dot(a, a)); }                        // Vec3.h:32
 RT_SHARED1 V3 normalized(V3 a) { const float L = length(a); return v3(a.x / L, a.y / L, a.z / L); }  // Vec3.h:35
+// the same arithmetic, always inlined: for the few kernels small enough that the call costs more than the copies (the sample kernel
+// of a scene without meshes: three normalisations per shadow sample; config 2 30.4 -> 29.7 ms with every copy inlined, but config 5
+// 53.5 -> 54.0, so only that kernel asks for it; profiles/r02_notes.md, r03v)
+RT_HD V3 normalized_inl(V3 a) { const float L = length(a); return v3(a.x / L, a.y / L, a.z / L); }
 RT_HD V3 ld3(const float *p) { return v3(p[0], p[1], p[2]); }
 RT_HD float fminr(float a, float b) { return a < b ? a : b; }                // ::min, Functions.cpp:20
 RT_HD float fmaxr(float a, float b) { return a > b ? a : b; }                // ::max, Functions.cpp:24
@@ -184,6 +188,12 @@ RT_SHARED2 V3 random_unit_vector(Rng &rng) {
     const float y = -1.f + 2.f * rng.next();
     const float x = -1.f + 2.f * rng.next();
     return normalized(v3(x, y, z));
+}
+RT_HD V3 random_unit_vector_inl(Rng &rng) {
+    const float z = -1.f + 2.f * rng.next();
+    const float y = -1.f + 2.f * rng.next();
+    const float x = -1.f + 2.f * rng.next();
+    return normalized_inl(v3(x, y, z));
 }
 
 // ---- device scene ------------------------------------------------------------------------------
@@ -322,6 +332,7 @@ struct Ray {
 };
 // Ray(o, d, time): the Line constructor normalises d (Line.h:13-16)
 RT_SHARED2 Ray make_ray(V3 o, V3 d, float time) { Ray r; r.o = o; r.d = normalized(d); r.time = time; return r; }
+RT_HD Ray make_ray_inl(V3 o, V3 d, float time) { Ray r; r.o = o; r.d = normalized_inl(d); r.time = time; return r; }
 
 struct Hit {
     int type;       // 0 miss, 1 sphere, 2 square, 3 mesh
@@ -2090,16 +2101,16 @@ RT_HD V3 path_fold(const PathState &st, V3 tail) {
 // value, candidate list out of the struct), inlining lets the wavefront keep it in registers / spill slots: config 2
 // 10.8 -> 10.5 ms, config 5 63.3 -> 62.4; the state-machine kernel of config 3, whose hot code is twice as long, loses 1.4 %
 // the same way and keeps the calls. (Round 1 measured the inlined sample neutral to slower: the state was pinned then.)
-template <bool STATS>
+template <bool STATS, bool INL = false>
 RT_HD void path_shadow_sample_body(const DScene &s, PathState &st, Counters *cnt) {
     if (STATS) cnt->rnd += 3;
     const V3 lp = ld3(s.lights[st.light].pos);
     const float delta = s.lights[st.light].radius / 2.f;
-    const V3 lj = lp + random_unit_vector(st.rng) * delta;
-    const V3 Lj = normalized(lj - st.P);
+    const V3 lj = lp + (INL ? random_unit_vector_inl(st.rng) : random_unit_vector(st.rng)) * delta;
+    const V3 Lj = INL ? normalized_inl(lj - st.P) : normalized(lj - st.P);
     st.t_light = length(lj - st.P);
     const float time = st.ray.time;
-    st.ray = make_ray(st.P + Lj * RT_EPSF, Lj, time);
+    st.ray = INL ? make_ray_inl(st.P + Lj * RT_EPSF, Lj, time) : make_ray(st.P + Lj * RT_EPSF, Lj, time);
     st.mode = 1;
 }
 template <bool STATS>
@@ -2162,7 +2173,7 @@ RT_HD bool path_shade(const DScene &s, PathState &st, const Hit &h, float hu, fl
         const float4 a = RT_LDG(s.sph_a + h.obj), b = RT_LDG(s.sph_b + h.obj);
         const V3 c = v3(a.x, a.y, a.z) + ray.time * v3(b.x, b.y, b.z);
         P = ray.o + h.t * ray.d;
-        n = normalized(P - c);
+        n = NOMESH ? normalized_inl(P - c) : normalized(P - c);
         kd = ld3(mat->kd);
         float tu = 0.f, tv = 0.f;
         if (mat->texture_type != 0) {

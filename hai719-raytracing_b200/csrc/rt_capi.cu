@@ -595,8 +595,18 @@ __device__ __forceinline__ void wf_store_ray(const WfArgs &w, unsigned int pos, 
 // primitives and asks ray_touches_meshes: rays that cannot hit a mesh are shaded at once; the others go to a queue with their
 // analytic hit so far. Phase 2 walks the meshes for THOSE rays only and shades them. Two smaller kernels (frames of 320 and
 // 344 B against 592) instead of one; whether that pays depends on the scene (rt_render_device: wf_split).
+// CTAs per SM of the instantiations for scenes without meshes (A/B knobs; 8 = 64 registers, 7 = 72, 6 = 80)
+#ifndef RT_MINB_TRACE_NOMESH
+#define RT_MINB_TRACE_NOMESH RT_WF_MINB
+#endif
+#ifndef RT_MINB_CLASSIFY_NOMESH
+#define RT_MINB_CLASSIFY_NOMESH RT_WF_MINB
+#endif
+#ifndef RT_MINB_SAMPLE_NOMESH
+#define RT_MINB_SAMPLE_NOMESH RT_WF_MINB
+#endif
 template <bool STATS, bool LC, bool NOLIGHT, int MESH>
-__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene_, const DCamera cam, const WfArgs w) {
+__global__ void __launch_bounds__(128, MESH == 3 ? RT_MINB_TRACE_NOMESH : RT_WF_MINB) k_wf_trace(const DScene scene_, const DCamera cam, const WfArgs w) {
     const DScene &scene = RT_S(scene_);
     stage_abvh(scene);
     Counters cnt;
@@ -738,7 +748,7 @@ __global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_trace(const DScene scene
 // then needs no traversal stack at all.
 // OVER (phase 3): 0 = the park queue (every entry has its candidate-triangle list), 1 = the overflow queue (every entry walks the meshes).
 template <bool STATS, bool LC, int PHASE, bool NOMESH = false, int OVER = 0>
-__global__ void __launch_bounds__(128, RT_WF_MINB) k_wf_light(const DScene scene_, const WfArgs w) {
+__global__ void __launch_bounds__(128, NOMESH ? (PHASE == 3 ? RT_MINB_SAMPLE_NOMESH : RT_MINB_CLASSIFY_NOMESH) : RT_WF_MINB) k_wf_light(const DScene scene_, const WfArgs w) {
     const DScene &scene = RT_S(scene_);
     stage_abvh(scene);
     Counters cnt;

@@ -109,6 +109,14 @@ __global__ void k_precompute_squares(const SquareIn *in, DSquare *out, int n) {
     out[i] = q;
 }
 
+// always_bound_of for the always-tested entries [first, first + count) of bvh_tris (after k_precompute_tris of that mesh, same stream)
+__global__ void k_always_bounds(const uint32_t *tris, uint32_t first, uint32_t count, const float4 *edge, const float2 *den, float4 *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t k = first + i, r0 = tris[k];
+    const AlwaysBound ab = always_bound_of(edge[3 * r0], edge[3 * r0 + 1], edge[3 * r0 + 2], den[r0].x);
+    out[3 * k] = ab.g1; out[3 * k + 1] = ab.g2; out[3 * k + 2] = ab.b;
+}
 __global__ void k_precompute_tris(const float *positions, const RtTriRef *refs, unsigned int n_refs, float4 *plane,
                                   float4 *edge, float2 *den) {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1829,6 +1837,12 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
         if ((rc = dev_upload(s, ac.nodes.data(), ac.nodes.size(), &d.bvh_nodes))) return rc;
         if ((rc = dev_upload(s, ac.nodes4.data(), ac.nodes4.size(), &d.bvh4_nodes))) return rc;
         if ((rc = dev_upload(s, ac.tris.data(), ac.tris.size(), &d.bvh_tris))) return rc;
+        float4 *ab = nullptr;
+        if (!ac.tris.empty()) {
+            if ((rc = dev_alloc(s, (size_t)3 * ac.tris.size(), &ab))) return rc;
+            RT_CUDA(cudaMemsetAsync(ab, 0, (size_t)3 * ac.tris.size() * sizeof(float4)));
+        }
+        d.always_bound = ab;
         if ((rc = dev_upload(s, ac.ref_next.data(), ac.ref_next.size(), &d.ref_next))) return rc;
         if ((rc = dev_upload(s, ac.ref_leaf.data(), ac.ref_leaf.size(), &d.ref_leaf))) return rc;
         if ((rc = dev_upload(s, ac.node_parent.data(), ac.node_parent.size(), &d.node_parent))) return rc;
@@ -1855,6 +1869,10 @@ int rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out) {
                 k_precompute_tris<<<(src.n_leaf_refs + 127) / 128, 128>>>((const float *)d_pos.p, (const RtTriRef *)d_refs.p, src.n_leaf_refs,
                                                                          pl + rb, ed + 3 * (size_t)rb, dn + rb);
                 RT_CUDA(cudaGetLastError());   // the staging arrays live in the scene's arena: no need to wait for the kernel here
+            }
+            if (o.always_count > 0u && ab) {
+                k_always_bounds<<<(o.always_count + 63) / 64, 64>>>(d.bvh_tris, o.always_first, o.always_count, ed, dn, ab);
+                RT_CUDA(cudaGetLastError());
             }
             m[i] = to_dmat(src.material);
             tr[i] = src.material.transparency;

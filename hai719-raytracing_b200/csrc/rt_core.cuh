@@ -250,6 +250,7 @@ struct DScene {
     const float4 *bvh_nodes;   // 4 per node
     const float4 *bvh4_nodes;  // 8 per node: lo.x lo.y lo.z hi.x hi.y hi.z of the four children, their codes, spare (rt_bvh.hpp : collapse4)
     const uint32_t *bvh_tris;  // representative leaf ref per distinct triangle, BVH leaf order
+    const float4 *always_bound; // 3 per entry of bvh_tris, filled for the always-tested ranges only (always_bound_of)
     const uint32_t *ref_next, *ref_leaf, *node_parent;
     // culling hierarchy over spheres + squares (rt_bvh.hpp : build_analytic_accel); abvh_root < 0 = linear loops
     const float4 *abvh_nodes;
@@ -466,6 +467,40 @@ RT_HD float triangle_t(const Ray &ray, const DScene &m, uint32_t ref, float &w0,
         return t;
     }
     return FLT_MAX;
+}
+
+// Where can the reference's barycentric test accept a point, for a triangle too ill-conditioned to be boxed (the "always-tested" list of
+// rt_bvh.hpp: nearly or exactly collinear corners)? It accepts q = p - c0 only if 0 <= u1, u2 <= 1 with u1 = N1 / den,
+// N1 = fl(fl(d11 * d20) - fl(d01 * d21)), d20 = fl(q . e0), d21 = fl(q . e1) (triangle_t), hence only if |N1| <= |den| (1 + eps).
+// On the STORED constants, d11 (q . e0) - d01 (q . e1) = q . g1 exactly, g1 = d11 e0 - d01 e1, and N1 differs from that by at most
+// (4 eps + O(eps^2)) |q| (|d11| |e0| + |d01| |e1|) (three roundings per dot product, one per product, one for the difference). So
+//     |q . g1 / |g1||  <=  alpha1 + beta1 |q|,   alpha1 = 1.001 |den| / |g1|,   beta1 = 8 eps (|d11| |e0| + |d01| |e1|) / |g1|
+// (twice the first-order constant), and the same with g2 = d00 e1 - d01 e0 for u2: the accepted points lie in a slab around the plane
+// through c0 perpendicular to g1 whose half-width grows with the distance from c0 — for collinear corners a thin double wedge around
+// the plane that holds the sliver's line. A light cone whose hull lies on one side of that slab cannot be occluded by the triangle
+// (intersect_lc). beta >= 0.25, g = 0 or a non-finite constant: no statement (alpha = FLT_MAX). Evaluated in double from the float
+// constants, once per always-tested triangle (k_always_bounds / the CPU simulation).
+struct AlwaysBound { float4 g1, g2, b; };   // {g1 / |g1|, alpha1} {g2 / |g2|, alpha2} {beta1, beta2, -, -}
+RT_HD AlwaysBound always_bound_of(float4 ta, float4 tb, float4 tc, float den) {
+    AlwaysBound o;
+    o.g1 = make_float4(0.f, 0.f, 0.f, FLT_MAX); o.g2 = make_float4(0.f, 0.f, 0.f, FLT_MAX); o.b = make_float4(0.f, 0.f, 0.f, 0.f);
+    const double e0[3] = {tb.x, tb.y, tb.z}, e1[3] = {tc.x, tc.y, tc.z};
+    const double d00 = ta.w, d01 = tb.w, d11 = tc.w, dn = fabs((double)den);
+    const double le0 = sqrt(e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2]), le1 = sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+    double g1[3], g2[3], n1 = 0.0, n2 = 0.0;
+    for (int a = 0; a < 3; ++a) { g1[a] = d11 * e0[a] - d01 * e1[a]; g2[a] = d00 * e1[a] - d01 * e0[a]; n1 += g1[a] * g1[a]; n2 += g2[a] * g2[a]; }
+    n1 = sqrt(n1); n2 = sqrt(n2);
+    const double eps = 5.96e-8;
+    if (!(dn > 0.0) || !(dn < 3e38)) { o.b.z = 1.f; return o; }   // den = 0, inf or NaN: N / den is never in [0, 1] — the triangle reports no hit at all
+    if (n1 > 0.0 && n1 < 1e300 && dn < 1e300) {
+        const double alpha = 1.001 * dn / n1, beta = 8.0 * eps * (fabs(d11) * le0 + fabs(d01) * le1) / n1;
+        if (beta < 0.25 && alpha < 1e30) { o.g1 = make_float4((float)(g1[0] / n1), (float)(g1[1] / n1), (float)(g1[2] / n1), (float)alpha * 1.000001f + 1e-37f); o.b.x = (float)beta * 1.000001f; }
+    }
+    if (n2 > 0.0 && n2 < 1e300 && dn < 1e300) {
+        const double alpha = 1.001 * dn / n2, beta = 8.0 * eps * (fabs(d00) * le1 + fabs(d01) * le0) / n2;
+        if (beta < 0.25 && alpha < 1e30) { o.g2 = make_float4((float)(g2[0] / n2), (float)(g2[1] / n2), (float)(g2[2] / n2), (float)alpha * 1.000001f + 1e-37f); o.b.y = (float)beta * 1.000001f; }
+    }
+    return o;
 }
 
 // ---- mesh: stackless pre-order KD traversal ----------------------------------------------------
@@ -1701,13 +1736,43 @@ RT_HD bool cone_box(const Cone &c, float lx, float ly, float lz, float hx, float
 //     sample ray. This is the lit side of the very sphere that was hit, and everything on the far side of P.
 // margin = 1e-4 * |w| * (|D| + delta): three orders of magnitude above the rounding of the fp32 dot products the
 // reference-exact tests evaluate (a few eps * |w|), so "cannot occlude" here implies FLT_MAX there.
+#ifndef RT_OPT_LC_HULL
+#define RT_OPT_LC_HULL 1
+#endif
+// Does a ball (centre P + v, radius r) stay clear of the hull H of P and the ball of sample points, H = union over s in [0, 1] of
+// ball(P + s D, s delta)? Every shadow sample of the light runs inside H (from P + EPSILON L to a point within delta of the light's
+// centre). The distance of the ball's centre from H is min_s f(s), f(s) = |v - s D| - s delta: f is convex (a norm of an affine
+// function minus a linear one), its stationary point solves (a s - b)^2 = delta^2 |v - s D|^2 with a s >= b, i.e.
+// s* = (b + delta sqrt((a cc - b^2) / (a - delta^2))) / a with a = D.D, b = v.D, cc = v.v, and the minimum over the segment is at s*
+// clamped to [0, 1.0001] (the ray ends EPSILON beyond its sample point). An error ds in s* changes f by f'' ds^2 / 2 only. "Clear" asks
+// for f > r + 1e-4 of every length involved; the caller adds the slop of the reference's own test to r.
+RT_HD bool lc_hull_misses(V3 v, V3 D, float delta, float Dlen, float r) {
+    const float A = dot(D, D), d2 = delta * delta;
+    if (!(A > 4.f * d2)) return false;   // P inside or near the ball of sample points: no statement
+    const float B = dot(v, D), CC = dot(v, v);
+    const float cr = fmaxf(A * CC - B * B, 0.f);
+    float sx = (B + delta * sqrtf(cr / (A - d2))) / A;
+    sx = sx < 0.f ? 0.f : (sx > 1.0001f ? 1.0001f : sx);
+    const float f = length(v - sx * D) - sx * delta;
+    return f > r + 1e-4f * (sqrtf(CC) + Dlen + delta + r) + 1e-6f;
+}
 RT_HD bool lc_cannot_occlude(const DScene &s, uint32_t seq, int ns, V3 P, float time, V3 D, float delta, float Dlen) {
     if ((int)seq < ns) {
         const float4 a = RT_LDG(s.sph_a + seq), b = RT_LDG(s.sph_b + seq);
         const V3 c = v3(a.x, a.y, a.z) + time * v3(b.x, b.y, b.z);
         const V3 w = P - c;
         const float wl = length(w);
-        return dot(D, w) - delta * wl > 1e-4f * wl * (Dlen + delta) + 1e-12f;
+        if (dot(D, w) - delta * wl > 1e-4f * wl * (Dlen + delta) + 1e-12f) return true;
+#if RT_OPT_LC_HULL
+        // * sphere, part 2: the sphere stays clear of the hull of P and the ball of sample points (lc_hull_misses). The box test that found
+        //   this candidate is a max-norm cone against a swept, padded box: in config 2, 62 % of the (hit, light) pairs that went on to be
+        //   sampled never hit any of their candidates; with this test 37 % fewer pairs are sampled (profiles/r02_notes.md, r03y). The radius
+        //   carries the slop of the reference's sphere test: a ray that misses the sphere by up to ~2.5 eps (|o - c|^2 / r + r) can still be
+        //   reported as a hit; taken 25x.
+        const float r = fabsf(a.w);
+        if (r > 0.f && lc_hull_misses(c - P, D, delta, Dlen, r + 64.f * 5.96e-8f * (wl * wl / r + r))) return true;
+#endif
+        return false;
     }
     const DSquare &q = s.squares[seq - ns];
     if (q.glass) return false;
@@ -1947,6 +2012,44 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t_, bool mine, 
                             const bool faces_away = dot(coneD, n) - cone_delta * nl > 1e-4f * nl * (cone_len + cone_delta) + 1e-12f;
                             const bool behind = dot(st.P, n) - pl.w < -(1e-4f * (plen * nl + fabsf(pl.w)) + 2e-5f * nl + 1e-12f);
                             if (faces_away || behind) continue;
+#if RT_OPT_LC_HULL
+                            // An always-tested triangle accepts points only inside two slabs around c0 (always_bound_of), and only ON ITS PLANE:
+                            // a sample ray (from P towards P + D + delta u, |u| <= 1) crosses the plane at s = h / -(D + delta u) . n of the way,
+                            // h = P . n - w >= 0, so between s_lo = h / (-D.n + delta |n|) and s_hi = h / (-D.n - delta |n|) when the whole cone
+                            // faces the plane (else anywhere in [0, 1]); the reference's own t carries a relative error of a few eps and an
+                            // absolute one of <= 4 eps (|w| + |o| |n|) / |d . n| (s units: / (-D.n - delta |n|)), taken 4x, and 1e-3 relative. The
+                            // crossing points therefore lie in the capsule around the segment P + [s_lo, s_hi] D with radius s_hi delta. The
+                            // functional q . g is linear: over the capsule it ranges between its values at the two ends -+ the radius, and
+                            // |q| <= Rmax there. The triangle is dropped when the capsule lies on one side of either slab, when the plane lies
+                            // beyond the sample points, or when its stored denominator is 0 / not finite (u1, u2 are then never in [0, 1]).
+                            // These few triangles were the ONLY candidates of 53 % of config 5's (hit, light) pairs — all sampled for nothing
+                            // (profiles/r02_notes.md, r03y).
+                            if (k < m.always_first + m.always_count && s.always_bound) {
+                                const float4 b0 = RT_LDG(s.always_bound + 3 * k), b1 = RT_LDG(s.always_bound + 3 * k + 1), b2 = RT_LDG(s.always_bound + 3 * k + 2);
+                                if (b2.z != 0.f) continue;
+                                const float4 tc0 = RT_LDG(s.tri_edge + 3 * r0);
+                                const V3 c0v = v3(tc0.x, tc0.y, tc0.z);
+                                const float hPn = fmaxf(dot(st.P, n) - pl.w, 0.f), an = -dot(coneD, n), dn_ = cone_delta * nl;
+                                float s_lo = 0.f, s_hi = 1.0001f;
+                                if (an > 2.f * dn_ + 1e-4f * nl * (cone_len + cone_delta) + 1e-12f) {
+                                    const float ds = 16.f * 5.96e-8f * (fabsf(pl.w) + plen * nl) / (an - dn_);
+                                    s_lo = fmaxf(hPn / (an + dn_) * 0.999f - ds, 0.f);
+                                    s_hi = fminf(hPn / (an - dn_) * 1.001f + ds, 1.0001f);
+                                    if (s_lo > 1.0001f) continue;   // the plane lies beyond every sample point
+                                }
+                                const V3 qP = st.P - c0v;
+                                const V3 qA = qP + s_lo * coneD, qB = qP + s_hi * coneD;
+                                const float rad = s_hi * cone_delta;
+                                const float Rmax = fmaxf(length(qA), length(qB)) + rad;
+                                const float absm = 1e-4f * (Rmax + length(c0v) + plen) + 1e-6f;   // rounding of the hit point and of q
+                                const V3 g1v = v3(b0.x, b0.y, b0.z), g2v = v3(b1.x, b1.y, b1.z);
+                                const float hA1 = dot(qA, g1v), hB1 = dot(qB, g1v), lim1 = b0.w + b2.x * Rmax * 1.001f + absm + rad;
+                                const float hA2 = dot(qA, g2v), hB2 = dot(qB, g2v), lim2 = b1.w + b2.y * Rmax * 1.001f + absm + rad;
+                                const bool out1 = b0.w < 1e30f && ((hA1 > lim1 && hB1 > lim1) || (hA1 < -lim1 && hB1 < -lim1));
+                                const bool out2 = b1.w < 1e30f && ((hA2 > lim2 && hB2 > lim2) || (hA2 < -lim2 && hB2 < -lim2));
+                                if (out1 || out2) continue;
+                            }
+#endif
                             if (cn >= RT_LC_MAXC || i >= 32 || r0 >= (1u << 27)) { cn = -1; break; }
                             st.cl[cn++] = ((uint32_t)i << 27) | r0;
                         }

@@ -31,7 +31,7 @@ struct SimScene {
     PackedMeshes pk;
     Accel ac;
     AnalyticAccel aa;
-    std::vector<float4> plane, edge;
+    std::vector<float4> plane, edge, always_bound;
     std::vector<float2> den;
 };
 
@@ -127,6 +127,14 @@ void *sim_scene_create(const RtSceneDesc *desc) {
     }
     d.node_lo = s->pk.lo.data(); d.node_hi = s->pk.hi.data();
     d.tri_plane = s->plane.data(); d.tri_edge = s->edge.data(); d.tri_den = s->den.data();
+    s->always_bound.assign(3 * s->ac.tris.size(), make_float4(0.f, 0.f, 0.f, 0.f));
+    for (const DMesh &o : s->meshes)
+        for (uint32_t k = o.always_first; k < o.always_first + o.always_count; ++k) {
+            const uint32_t r0 = s->ac.tris[k];
+            const AlwaysBound ab = always_bound_of(s->edge[3 * r0], s->edge[3 * r0 + 1], s->edge[3 * r0 + 2], s->den[r0].x);
+            s->always_bound[3 * k] = ab.g1; s->always_bound[3 * k + 1] = ab.g2; s->always_bound[3 * k + 2] = ab.b;
+        }
+    d.always_bound = s->always_bound.empty() ? nullptr : s->always_bound.data();
     d.meshes = s->meshes.data(); d.mesh_mat = s->mesh_mat.data(); d.mesh_transparency = s->mesh_tr.data();
     return s;
 }

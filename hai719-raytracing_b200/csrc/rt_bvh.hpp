@@ -281,6 +281,20 @@ inline void build_accel(const RtSceneDesc &d, const PackedMeshes &pk, Accel &out
                 always.push_back(p.ref);
                 continue;
             }
+            {
+                // The denominator the device STORES (precompute_triangle: float dot products summed left to right, d00 * d11 - d01 * d01,
+                // no FMA), replayed here in float: when it is exactly 0 or not finite, u1 = N / den is never inside [0, 1]
+                // (Triangle.h:62-75: +-inf or NaN fail every comparison) and the triangle can never report a hit: dropped. One of the two
+                // collinear slivers of the triceratops mesh is such a triangle; as an always-tested one it cost every ray a test.
+                const float q0[3] = {(float)c[0][0], (float)c[0][1], (float)c[0][2]};
+                const float fe0[3] = {(float)c[1][0] - q0[0], (float)c[1][1] - q0[1], (float)c[1][2] - q0[2]};
+                const float fe1[3] = {(float)c[2][0] - q0[0], (float)c[2][1] - q0[1], (float)c[2][2] - q0[2]};
+                auto fdot = [](const float *a, const float *b) { const volatile float x = a[0] * b[0], y = a[1] * b[1], z = a[2] * b[2]; const volatile float xy = x + y; return (float)(xy + z); };
+                const float f00 = fdot(fe0, fe0), f01 = fdot(fe0, fe1), f11 = fdot(fe1, fe1);
+                const volatile float pa = f00 * f11, pb = f01 * f01;
+                const float fden = pa - pb;
+                if (fden == 0.f || !std::isfinite(fden)) continue;
+            }
             const double kappa = d00 * d11 / denom;
             const double lmax = std::sqrt(std::max(d00, d11));
             // error analysis of u1 = (d11*d20 - d01*d21)/denom in fp32 gives <= ~36 eps kappa lmax of spatial

@@ -843,10 +843,19 @@ __global__ void __launch_bounds__(128, NOMESH ? (PHASE == 3 ? RT_MINB_SAMPLE_NOM
                 bool blocked;
                 intersect_lc<STATS, false, true>(scene, st, true, mine, h, hu, hv, blocked, &cnt, !NOMESH);
                 if (mine) {
-                    if (!lc_light_unoccluded(st)) parked = true;
-                    else {
+                    bool go_on = false;
+                    if (lc_light_unoccluded(st)) {
                         if (STATS) { cnt.shadow += w.nb_ech; cnt.rnd += 3 * w.nb_ech; }
                         st.rng.ctr += 3u * (uint32_t)w.nb_ech;
+                        go_on = true;
+                    } else if (lc_umbra(scene, st, w.nb_ech)) {
+                        // every sample blocked by construction (the stream already advanced): path_finish_light with blocked = NB_ECH,
+                        // i.e. shadow = (float)(1. - (double)((float)n / (float)n)) = 0.f (Scene.h:331-333)
+                        if (STATS) { cnt.shadow += w.nb_ech; cnt.rnd += 4 * w.nb_ech; }
+                        st.color = st.color * 0.f;
+                        go_on = true;
+                    } else parked = true;
+                    if (go_on) {
                         ++st.light;
                         fin = path_next_light_or_bounce<STATS, LC, true>(scene, st, w.nb_ech, c, &cnt);
                     }

@@ -1756,6 +1756,21 @@ RT_HD bool lc_hull_misses(V3 v, V3 D, float delta, float Dlen, float r) {
     const float f = length(v - sx * D) - sx * delta;
     return f > r + 1e-4f * (sqrtf(CC) + Dlen + delta + r) + 1e-6f;
 }
+// Is the sphere (centre P + v, radius r > 0) hit by EVERY shadow sample of the cone, with EPSILON < t < t_light? Sufficient: P clearly outside
+// it, the whole sphere nearer than every sample point (|v| + r < |D| - delta), and every sample direction inside the cone the sphere
+// subtends shrunk by the slop of the reference's sphere test: a sample direction deviates from D by at most asin(delta / |D|), D from v by
+// theta, and sin(theta + beta) <= sin theta + sin beta, so sin theta + delta / |D| < (r - pad) / |v| (with cos theta > 0) suffices; pad as in
+// lc_cannot_occlude, 1e-3 relative on top. Then the discriminant of the reference's test is positive by ~25x its rounding error, the near root
+// is >= |v| - r > 1e-3 >> EPSILON and <= |v| < t_light.
+RT_HD bool lc_sphere_covers(V3 v, V3 D, float delta, float Dlen, float r) {
+    const float vl = length(v);
+    const float pad = 64.f * 5.96e-8f * (vl * vl / r + r) + 1e-3f * r;
+    if (!(r > pad) || !(vl - r > 1e-3f + 1e-3f * vl) || !(vl + r < (Dlen - delta) * 0.999f) || !(Dlen > 4.f * delta)) return false;
+    const float ct = dot(v, D) / (vl * Dlen);
+    if (!(ct > 0.f)) return false;
+    const float st2 = fmaxf(1.f - ct * ct, 0.f);
+    return sqrtf(st2) + delta / Dlen < ((r - pad) / vl) * 0.999f - 1e-5f;
+}
 RT_HD bool lc_cannot_occlude(const DScene &s, uint32_t seq, int ns, V3 P, float time, V3 D, float delta, float Dlen) {
     if ((int)seq < ns) {
         const float4 a = RT_LDG(s.sph_a + seq), b = RT_LDG(s.sph_b + seq);
@@ -1777,6 +1792,50 @@ RT_HD bool lc_cannot_occlude(const DScene &s, uint32_t seq, int ns, V3 P, float 
     const DSquare &q = s.squares[seq - ns];
     if (q.glass) return false;
     return dot(D, ld3(q.n)) - delta > 1e-4f * (Dlen + delta) + 1e-12f;
+}
+// UMBRA: every candidate is opaque (transparency 0), there are no candidate triangles, and one candidate sphere is hit by every sample of
+// the cone (lc_sphere_covers). Then each of the NB_ECH samples draws its three direction numbers and exactly ONE more — for the first
+// candidate it hits in sequence order, whichever that is — and is blocked iff that draw exceeds the transparency 0 (Scene.h:236-247): no
+// direction, no test needed. A draw of exactly 0 (1 in 2^24) would pass the occluder and go on to the next candidate: such a pair is left
+// to the sample kernel untouched (the stream is only committed when all NB_ECH draws block). In config 2, 40 % of the (hit, light) pairs that
+// used to be sampled are such pairs (profiles/r02_notes.md, r03z). MEASURED: exact (107 GPU tests, CPU simulation), the sample kernels of config 2
+// lose 25-35 % of their time (1.27 -> 0.97 ms per 16-spp frame) — and the classify kernels, which run the check for every pair with a candidate,
+// gain more than that (2.47 -> 3.23 ms: issue utilisation 68-74 % -> 55-60 % around the call): frame 28.6 -> 30.1 ms at 64 spp. OFF.
+#ifndef RT_OPT_LC_UMBRA
+#define RT_OPT_LC_UMBRA 0
+#endif
+// Out of line and by value: inlined, its registers cost the classify kernel's cone walk more than the samples it saves (config 2 28.6 ->
+// 29.9 ms), and a reference into the path state would pin the whole state in the thread's frame. Returns the stream position after the
+// NB_ECH samples, or 0xFFFFFFFF when the pair is not an umbra pair.
+RT_COLD uint32_t lc_umbra_cold(const DScene &s_, V3 P, float time, int light, uint32_t cm0, uint32_t cm1, uint32_t cm2, uint32_t cm3, Rng r, int nb_ech) {
+    const DScene &s = RT_S(s_);
+    const DLight &L = s.lights[light];
+    const V3 D = ld3(L.pos) - P;
+    const float delta = (L.radius / 2.f) * 1.0001f + 1e-6f, Dlen = length(D);
+    const int ns = s.n_spheres;
+    bool cover = false;
+    for (int w = 0; w < 4; ++w) {
+        uint32_t m = w == 0 ? cm0 : (w == 1 ? cm1 : (w == 2 ? cm2 : cm3));
+        while (m) {
+            const int seq = w * 32 + RT_FFS((int)m) - 1;
+            m &= m - 1u;
+            if (seq < ns) {
+                const float4 a = RT_LDG(s.sph_a + seq), b = RT_LDG(s.sph_b + seq);
+                if (b.w != 0.f) return 0xFFFFFFFFu;
+                if (!cover) cover = lc_sphere_covers((v3(a.x, a.y, a.z) + time * v3(b.x, b.y, b.z)) - P, D, delta, Dlen, fabsf(a.w));
+            } else if (RT_LDG(s.sq_transparency + (seq - ns)) != 0.f) return 0xFFFFFFFFu;
+        }
+    }
+    if (!cover) return 0xFFFFFFFFu;
+    for (int j = 0; j < nb_ech; ++j) { r.ctr += 3u; if (!(r.next() > 0.f)) return 0xFFFFFFFFu; }
+    return r.ctr;
+}
+RT_HD bool lc_umbra(const DScene &s, PathState &st, int nb_ech) {
+    if (!RT_OPT_LC_UMBRA || st.cl_n != 0) return false;
+    const uint32_t c = lc_umbra_cold(s, st.P, st.ray.time, st.light, st.cm0, st.cm1, st.cm2, st.cm3, st.rng, nb_ech);
+    if (c == 0xFFFFFFFFu) return false;   // (a stream never gets this far: 2^32 - 1 draws)
+    st.rng.ctr = c;
+    return true;
 }
 // No candidate at all (and no mesh in the cone): the NB_ECH samples of this light are all unoccluded. Each would
 // draw three numbers for its direction and nothing else (Scene.h:325-330, computeShadow draws only per candidate hit),
@@ -2336,6 +2395,11 @@ RT_HD bool path_advance(const DScene &s, PathState &st, const Hit &h, float hu, 
             st.rng.ctr += 3u * (uint32_t)nb_ech;
             ++st.light;
             return path_next_light_or_bounce<STATS, LC, WF>(s, st, nb_ech, out, cnt);
+        }
+        if (lc_umbra(s, st, nb_ech)) {   // every sample blocked by construction
+            if (STATS) { cnt->shadow += nb_ech; cnt->rnd += 4 * nb_ech; }
+            st.blocked = nb_ech;
+            return path_finish_light<STATS, LC, WF>(s, st, nb_ech, out, cnt);
         }
         path_shadow_sample<STATS, WF>(s, st, cnt);   // first sample
         return false;

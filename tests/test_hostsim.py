@@ -18,7 +18,8 @@ def _load_sim(hb, so_name, defs):
     so = os.path.join(SIM_DIR, so_name)
     src = os.path.join(SIM_DIR, "hostsim.cpp")
     core = os.path.join(ROOT, "hai719-raytracing_b200", "csrc", "rt_core.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+    deps = [src] + [os.path.join(os.path.dirname(core), f) for f in os.listdir(os.path.dirname(core)) if f.endswith((".cuh", ".hpp"))]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in deps):
         subprocess.check_call(["/usr/bin/g++", "-O3", "-fPIC", "-shared", "-std=c++17", "-I", os.path.join(ROOT, "include"),
                                "-I", os.path.dirname(core)] + defs + [src, "-o", so, "-lpthread"])
     L = C.CDLL(so)

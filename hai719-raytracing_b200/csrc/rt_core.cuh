@@ -92,7 +92,9 @@ static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #define RT_FFS(x) __ffs(x)
 #define RT_FAST_RCP(x) __fdividef(1.f, (x))   /* 2-ulp reciprocal: only used where a 1e-5 relative margin follows */
 #define RT_FMA(a, b, c) __fmaf_rn((a), (b), (c))   /* explicit: the build runs with -fmad=false; only in the conservative filters */
+#define RT_FAST_SQRT(x) ((x) * __frsqrt_rn(fmaxf((x), 1e-37f)))   /* ~2-ulp square root (0 for x = 0): only where a 1e-4 relative margin follows */
 #else   /* one lane */
+#define RT_FAST_SQRT(x) sqrtf(x)
 #define RT_FFS(x) __builtin_ffs(x)
 #define RT_FAST_RCP(x) (1.f / (x))
 #define RT_FMA(a, b, c) fmaf((a), (b), (c))
@@ -1751,10 +1753,12 @@ RT_HD bool lc_hull_misses(V3 v, V3 D, float delta, float Dlen, float r) {
     if (!(A > 4.f * d2)) return false;   // P inside or near the ball of sample points: no statement
     const float B = dot(v, D), CC = dot(v, v);
     const float cr = fmaxf(A * CC - B * B, 0.f);
-    float sx = (B + delta * sqrtf(cr / (A - d2))) / A;
+    // approximate reciprocals / square roots (2 ulp): three orders of magnitude inside the 1e-4 margin below
+    float sx = (B + delta * RT_FAST_SQRT(cr * RT_FAST_RCP(A - d2))) * RT_FAST_RCP(A);
     sx = sx < 0.f ? 0.f : (sx > 1.0001f ? 1.0001f : sx);
-    const float f = length(v - sx * D) - sx * delta;
-    return f > r + 1e-4f * (sqrtf(CC) + Dlen + delta + r) + 1e-6f;
+    const V3 q = v - sx * D;
+    const float f = RT_FAST_SQRT(dot(q, q)) - sx * delta;
+    return f > r + 1e-4f * (RT_FAST_SQRT(CC) + Dlen + delta + r) + 1e-6f;
 }
 // Is the sphere (centre P + v, radius r > 0) hit by EVERY shadow sample of the cone, with EPSILON < t < t_light? Sufficient: P clearly outside
 // it, the whole sphere nearer than every sample point (|v| + r < |D| - delta), and every sample direction inside the cone the sphere
@@ -1776,7 +1780,7 @@ RT_HD bool lc_cannot_occlude(const DScene &s, uint32_t seq, int ns, V3 P, float 
         const float4 a = RT_LDG(s.sph_a + seq), b = RT_LDG(s.sph_b + seq);
         const V3 c = v3(a.x, a.y, a.z) + time * v3(b.x, b.y, b.z);
         const V3 w = P - c;
-        const float wl = length(w);
+        const float wl = RT_FAST_SQRT(dot(w, w));   // only compared with margins of 1e-4
         if (dot(D, w) - delta * wl > 1e-4f * wl * (Dlen + delta) + 1e-12f) return true;
 #if RT_OPT_LC_HULL
         // * sphere, part 2: the sphere stays clear of the hull of P and the ball of sample points (lc_hull_misses). The box test that found
@@ -1785,7 +1789,7 @@ RT_HD bool lc_cannot_occlude(const DScene &s, uint32_t seq, int ns, V3 P, float 
         //   carries the slop of the reference's sphere test: a ray that misses the sphere by up to ~2.5 eps (|o - c|^2 / r + r) can still be
         //   reported as a hit; taken 25x.
         const float r = fabsf(a.w);
-        if (r > 0.f && lc_hull_misses(c - P, D, delta, Dlen, r + 64.f * 5.96e-8f * (wl * wl / r + r))) return true;
+        if (r > 0.f && lc_hull_misses(c - P, D, delta, Dlen, r + 64.f * 5.96e-8f * (wl * wl * RT_FAST_RCP(r) + r))) return true;
 #endif
         return false;
     }

@@ -375,6 +375,8 @@ struct AnalyticAccel {
     // square put R at ~70 in the random-spheres scene and padded a sphere of radius 0.2 by 0.05 (profiles/r02_notes.md, r03r/s)
     float center_s[3] = {0, 0, 0};
     float radius_s = 0.f;
+    // <= 32 primitives: their padded, motion-swept boxes in sequence order, {lo.xyz, coef} {hi.xyz, 0} (intersect_lc's flat test)
+    std::vector<float4> flat;
 };
 
 inline void build_analytic_accel(const RtSceneDesc &d, AnalyticAccel &out) {
@@ -429,6 +431,12 @@ inline void build_analytic_accel(const RtSceneDesc &d, AnalyticAccel &out) {
     float r2 = 0.f;
     for (int a = 0; a < 3; ++a) { out.center[a] = 0.5f * (all.lo[a] + all.hi[a]); const float h = 0.5f * (all.hi[a] - all.lo[a]); r2 += h * h; }
     out.radius = std::sqrt(r2);
+    if (prims.size() <= 32) {   // prims are still in sequence order here (build() permutes them)
+        for (const Prim &p : prims) {
+            out.flat.push_back(make_float4(p.box.lo[0], p.box.lo[1], p.box.lo[2], p.coef));
+            out.flat.push_back(make_float4(p.box.hi[0], p.box.hi[1], p.box.hi[2], 0.f));
+        }
+    }
     {
         Box cs; cs.reset();
         bool any = false;

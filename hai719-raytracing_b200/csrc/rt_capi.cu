@@ -359,6 +359,7 @@ struct WfArgs {
     unsigned int n_paths;              // paths of this chunk (slots 0 .. n_paths-1)
     unsigned int max_grab;             // batches a warp may fetch with one atomic (see wf_next_batch)
     unsigned int block;                // queue positions a warp reserves with one atomic (see wf_push)
+    int flat;                          // trace kernels: flat box test over <= 32 analytic primitives instead of the hierarchy walk from bounce flat - 1 on (0: never)
     int sort;                          // trace kernels from bounce 1 on: order every fetched window of the live queue by ray direction (wf_next_batch_sorted)
     int max_bounces, nb_ech, level;
     const float4 *cam_rays; const unsigned int *cam_keys;   // level 0 input, by slot
@@ -684,7 +685,9 @@ __global__ void __launch_bounds__(128, MESH == 3 ? RT_MINB_TRACE_NOMESH : RT_WF_
             }
             meshes_walk_merged<STATS>(scene, st.ray, 0, st.rng, h, blocked, done, &cnt);
         } else if (LC) {
-            intersect_lc<STATS, true>(scene, st, true, valid, h, hu, hv, blocked, &cnt, MESH == 0);   // MESH == 3: a scene without meshes
+            // the flat box test (<= 32 analytic primitives) is compiled into the split trace kernel only: that is where small analytic sets end up
+            // (scenes with meshes and no lights); in the other instantiations its code alone cost config 2 and 5 time
+            intersect_lc<STATS, true, false, 0, MESH == 1>(scene, st, true, valid, h, hu, hv, blocked, &cnt, MESH == 0, MESH == 1 && w.flat != 0 && w.level >= w.flat - 1);   // MESH == 3: a scene without meshes
         } else {
             intersect_ray<STATS, true>(scene, st.ray, st.mode, st.t_light, st.rng, h, hu, hv, blocked, &cnt);
         }
@@ -1672,6 +1675,7 @@ int upload_analytic(RtScene *s, const RtSceneDesc *desc, bool update) {
         d.abvh_r = aa.radius;
         for (int k = 0; k < 3; ++k) d.abvh_cs[k] = aa.center_s[k];
         d.abvh_rs = aa.radius_s;
+        if (!update) d.abvh_flat = nullptr;
         if (aa.root >= 0) {
             if (!update) {
                 // a binary hierarchy over n primitives has at most n - 1 inner nodes (4 float4 each) and n leaf entries,
@@ -1686,6 +1690,10 @@ int upload_analytic(RtScene *s, const RtSceneDesc *desc, bool update) {
             if (aa.nodes.size() > s->abvh_node_cap || aa.tris.size() > s->abvh_prim_cap) return fail(RT_ERR_INVALID, "analytic hierarchy outgrew its arrays");
             RT_CUDA(h2d(s, const_cast<float4 *>(d.abvh_nodes), aa.nodes.data(), aa.nodes.size() * sizeof(float4)));
             RT_CUDA(h2d(s, const_cast<uint32_t *>(d.abvh_prims), aa.tris.data(), aa.tris.size() * sizeof(uint32_t)));
+            if (!aa.flat.empty()) {   // same primitive counts on every update: allocated once
+                if (!update) { float4 *fl = nullptr; if ((rc = dev_alloc(s, aa.flat.size(), &fl))) return rc; d.abvh_flat = fl; }
+                if (d.abvh_flat) RT_CUDA(h2d(s, const_cast<float4 *>(d.abvh_flat), aa.flat.data(), aa.flat.size() * sizeof(float4)));
+            }
         }
     }
 
@@ -2094,6 +2102,8 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
             // one batch at a time as before; analytic scenes: cheap, even batches, where the fetch atomics were the bottleneck
             w.max_grab = s->d.n_meshes > 0 ? 1u : 8u;
             // windows of the live queue sorted by ray direction from bounce 1 on (wf_next_batch_sorted); HAI719_WF_SORT=0 / 1 overrides (A/B)
+            w.flat = s->d.abvh_flat ? 2 : 0;   // from bounce 1 on; HAI719_WF_FLAT=0 (never) / 1 (from bounce 0) / 2 overrides (A/B)
+            if (const char *e = getenv("HAI719_WF_FLAT")) w.flat = s->d.abvh_flat ? atoi(e) : 0;
             w.sort = RT_WF_SORT && w.max_grab > 1u ? 1 : 0;
             if (const char *e = getenv("HAI719_WF_SORT")) w.sort = RT_WF_SORT && atoi(e) != 0 ? 1 : 0;
             if (const char *e = getenv("HAI719_WF_GRAB")) { const int g_ = atoi(e); if (g_ >= 1 && g_ <= 8) w.max_grab = (unsigned int)g_; }

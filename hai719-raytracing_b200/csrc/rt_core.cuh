@@ -261,6 +261,7 @@ struct DScene {
     int abvh_n_nodes;          // inner nodes of that hierarchy (<= 127: it is only built for <= 128 primitives)
     float abvh_c[3], abvh_r;
     float abvh_cs[3], abvh_rs;   // ball of the sphere centres (quadratic term of the per-ray padding), see AnalyticAccel
+    const float4 *abvh_flat;     // <= 32 analytic primitives: their padded boxes in sequence order, {lo.xyz, coef} {hi.xyz, -} each; else null
     const DMaterial *sph_mat, *sq_mat, *mesh_mat;
     const DLight *lights;
     const DImage *textures, *normal_maps;
@@ -1905,9 +1906,9 @@ RT_HD bool lc_shadow_analytic(const DScene &s, PathState &st, Counters *cnt) {
 // candidate tests of a shadow sample (masks, triangle list or mesh walk) are compiled in.
 // SAMPLE_ = 2 / 3: moreover every lane is known to hold a candidate-triangle list (cl_n >= 0) / to have overflowed it (cl_n < 0): the
 // park queue and the overflow queue are sampled by separate launches, each compiled for its half.
-template <bool STATS, bool CLOSEST = false, bool COLLECT_ = false, int SAMPLE_ = 0>
+template <bool STATS, bool CLOSEST = false, bool COLLECT_ = false, int SAMPLE_ = 0, bool FLAT = true>
 RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t_, bool mine, Hit &h, float &hu, float &hv, bool &blocked,
-                        Counters *cnt, bool with_meshes = true) {
+                        Counters *cnt, bool with_meshes = true, bool flat = false) {
     const Ray &ray = st.ray;
     const bool COLLECT = COLLECT_ && RT_OPT_LC_COLLECT, SAMPLE = SAMPLE_ != 0 && RT_OPT_LC_COLLECT;
     const bool run_t = SAMPLE ? false : ((CLOSEST && RT_OPT_LC_SLAB) || COLLECT ? true : run_t_);
@@ -1916,6 +1917,40 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t_, bool mine, 
     blocked = false;
     bool done = !mine;
     const int ns = s.n_spheres;
+    if (FLAT && CLOSEST && RT_OPT_LC_SLAB && flat && s.abvh_flat) {   // FLAT = false: not compiled in (kernels that never see such a scene in practice)
+        // FLAT (a scene with <= 32 analytic primitives, from bounce 1 on): every lane tests ALL the primitives' boxes — one convergent loop,
+        // ~25 instructions per box — and keeps the ones it touches in a 32-bit mask; then each lane runs the reference's test on its own
+        // candidates in ascending sequence order (strict '<': the reference's tie rule as it stands). The hierarchy walk over the pool
+        // scene's 30 primitives ran 16.8 of 32 lanes from bounce 1 on, ~2150 warp instructions per batch; this is ~750 + the longest
+        // candidate list of the warp x 45 (profiles/r02_notes.md, r04e).
+        if (mine) {
+            if (STATS) cnt->closest++;
+            const Inv32 iv32 = make_inv32(ray);
+            const SphereRay sr = make_sphere_ray(ray);
+            const float dist = length(ray.o - ld3(s.abvh_c)) + s.abvh_r, dist_s = length(ray.o - ld3(s.abvh_cs)) + s.abvh_rs;
+            const float kq = 32.f * 5.96e-8f * dist_s * dist_s, kl = 64.f * 5.96e-8f * dist;
+            const int n = ns + s.n_squares;
+            uint32_t cand = 0u;
+            for (int i = 0; i < n; ++i) {
+                const float4 lo = RT_LDG(s.abvh_flat + 2 * i), hi = RT_LDG(s.abvh_flat + 2 * i + 1);
+                const float p = kq * lo.w + kl;
+                float tn;
+                if (STATS) cnt->node++;
+                if (bvh_box(ray, iv32, lo.x - p, lo.y - p, lo.z - p, hi.x + p, hi.y + p, hi.z + p, FLT_MAX, tn)) cand |= 1u << i;
+            }
+            while (cand) {
+                const int seq = RT_FFS((int)cand) - 1;
+                cand &= cand - 1u;
+                float t, u = 0.f, v = 0.f;
+                if (seq < ns) { if (STATS) cnt->sphere++; t = sphere_t(ray, sr, RT_LDG(s.sph_a + seq), RT_LDG(s.sph_b + seq)); }
+                else { if (STATS) cnt->square++; t = square_t(ray, s.squares[seq - ns], u, v); }
+                if (t < h.t && t > RT_EPSF) {
+                    h.t = t;
+                    if (seq < ns) { h.type = 1; h.obj = seq; } else { h.type = 2; h.obj = seq - ns; hu = u; hv = v; }
+                }
+            }
+        }
+    } else
     if (run_t) {
         if (mine) {
             const bool SLAB = CLOSEST && RT_OPT_LC_SLAB;

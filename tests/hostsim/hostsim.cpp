@@ -102,6 +102,7 @@ void *sim_scene_create(const RtSceneDesc *desc) {
     d.abvh_r = s->aa.radius;
     for (int k = 0; k < 3; ++k) d.abvh_cs[k] = s->aa.center_s[k];
     d.abvh_rs = s->aa.radius_s;
+    d.abvh_flat = s->aa.flat.empty() ? nullptr : s->aa.flat.data();
     const uint32_t nm = desc->n_meshes;
     if (!pack_meshes(*desc, s->pk).empty()) { delete s; return nullptr; }
     build_accel(*desc, s->pk, s->ac);
@@ -192,7 +193,7 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                         bool fin = false;
                         for (int level = 0; level < p->max_bounces && !fin; ++level) {
                             Hit hit; float hu = 0.f, hv = 0.f; bool blocked;
-                            if (lc) intersect_lc<false>(s->d, st, true, true, hit, hu, hv, blocked, nullptr);
+                            if (lc) intersect_lc<false, true>(s->d, st, true, true, hit, hu, hv, blocked, nullptr, true, level >= 1);   // as k_wf_trace: slab test, flat test from bounce 1 on
                             else intersect_ray<false, true>(s->d, st.ray, st.mode, st.t_light, st.rng, hit, hu, hv, blocked, nullptr);
                             if (path_shade<false, true>(s->d, st, hit, hu, hv, c, nullptr)) { fin = true; break; }
                             if (lc) fin = path_next_light_or_bounce<false, true, true>(s->d, st, p->nb_ech, c, nullptr);

@@ -142,6 +142,213 @@ void *sim_scene_create(const RtSceneDesc *desc) {
 
 void sim_scene_destroy(void *h) { delete (SimScene *)h; }
 
+// ---- property checks of the conservative candidate filters (tests/test_hostsim.py) ---------------------------------
+static float urand(uint32_t &st) { st = st * 1664525u + 1013904223u; return (float)(st >> 8) * (1.0f / 16777216.0f); }
+static V3 vrand(uint32_t &st, float lo, float hi) { const float x = lo + (hi - lo) * urand(st), y = lo + (hi - lo) * urand(st), z = lo + (hi - lo) * urand(st); return v3(x, y, z); }
+
+// lc_cannot_occlude's hull test (lc_hull_misses) against the reference's sphere test: whenever the filter drops a sphere, no shadow
+// sample of that light — generated exactly as path_shadow_sample_body generates them — may get EPSILON < t < t_light from sphere_t.
+// Spheres are placed AT the boundary of the hull +- a relative offset between 1e-6 and 1, so both verdicts occur and the margin is
+// probed. out[0] = cases dropped, out[1] = cases kept, out[2] = hits among the kept ones (the test is not vacuous); returns violations.
+int sim_check_hull(unsigned int seed, int n_cases, int n_rays, unsigned long long *out) {
+    uint32_t st = seed * 2654435761u + 12345u;
+    int bad = 0;
+    out[0] = out[1] = out[2] = 0;
+    for (int k = 0; k < n_cases; ++k) {
+        const float scale = expf(logf(0.1f) + urand(st) * logf(1000.f));   // scene sizes 0.1 .. 100
+        const V3 P = vrand(st, -scale, scale), lp = vrand(st, -scale, scale);
+        const float lrad = scale * (0.01f + 0.5f * urand(st));
+        const float r = scale * expf(logf(0.002f) + urand(st) * logf(500.f));
+        const V3 D = lp - P;
+        const float delta = (lrad / 2.f) * 1.0001f + 1e-6f, Dlen = length(D);
+        if (!(Dlen > 0.f)) continue;
+        // a point on the hull's surface, then the centre at distance r * (1 + e) from it, outwards
+        const float s_ax = urand(st) * 1.2f - 0.1f;
+        const V3 axis = D / Dlen;
+        V3 perp = cross(axis, vrand(st, -1.f, 1.f));
+        if (!(length(perp) > 1e-3f)) continue;
+        perp = perp / length(perp);
+        const float sgn = urand(st) < 0.5f ? -1.f : 1.f;
+        const float e = sgn * expf(logf(1e-6f) + urand(st) * logf(1e6f));
+        const float sc = s_ax < 0.f ? 0.f : (s_ax > 1.f ? 1.f : s_ax);
+        const V3 c = P + s_ax * D + perp * (sc * delta + r * (1.f + e));
+        const float4 a = make_float4(c.x, c.y, c.z, r), b = make_float4(0.f, 0.f, 0.f, 0.f);
+        const V3 w = P - c;
+        const float wl = RT_FAST_SQRT(dot(w, w));
+        const bool dropped = r > 0.f && lc_hull_misses(c - P, D, delta, Dlen, r + 64.f * 5.96e-8f * (wl * wl * RT_FAST_RCP(r) + r));
+        out[dropped ? 0 : 1]++;
+        Rng rng; rng.init(seed, (uint32_t)k, 7u);
+        for (int j = 0; j < n_rays; ++j) {
+            const V3 lj = lp + random_unit_vector(rng) * (lrad / 2.f);
+            const V3 Lj = normalized(lj - P);
+            const float t_light = length(lj - P);
+            const Ray ray = make_ray(P + Lj * RT_EPSF, Lj, 0.f);
+            const float t = sphere_t(ray, make_sphere_ray(ray), a, b);
+            const bool hit = t < t_light && t > RT_EPSF;
+            if (hit && dropped) ++bad;
+            if (hit && !dropped) out[2]++;
+        }
+    }
+    return bad;
+}
+
+// The box padding of build_accel (slop = 128 eps kappa lmax) against the reference's triangle test, for conditioning numbers up to the limit
+// RT_BVH_KAPPA_MAX: every point triangle_t accepts must lie within slop (+ the static pad's 1e-4 of the coordinates) of the TRUE triangle
+// (distance in double). out[0] = triangles, out[1] = accepted hits checked, out[2] = largest accepted distance / slop seen, in 1e-6 units.
+static double pt_seg_d2(const double *p, const double *a, const double *b) {
+    double ab[3], ap[3], t = 0, l = 0;
+    for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ap[k] = p[k] - a[k]; t += ab[k] * ap[k]; l += ab[k] * ab[k]; }
+    t = l > 0 ? t / l : 0; t = t < 0 ? 0 : (t > 1 ? 1 : t);
+    double d = 0;
+    for (int k = 0; k < 3; ++k) { const double q = a[k] + t * ab[k] - p[k]; d += q * q; }
+    return d;
+}
+int sim_check_slop(unsigned int seed, int n_tris, int n_rays, double kappa_lo, double kappa_hi, unsigned long long *out) {
+    uint32_t st = seed * 3266489917u + 5u;
+    int bad = 0;
+    out[0] = out[1] = out[2] = 0;
+    for (int k = 0; k < n_tris; ++k) {
+        const float scale = expf(logf(0.01f) + urand(st) * logf(1e4f));
+        const V3 p0 = vrand(st, -scale, scale);
+        V3 dir = vrand(st, -1.f, 1.f);
+        if (!(length(dir) > 1e-3f)) continue;
+        dir = dir / length(dir);
+        V3 perp = cross(dir, vrand(st, -1.f, 1.f));
+        if (!(length(perp) > 1e-3f)) continue;
+        perp = perp / length(perp);
+        const float len = scale * expf(logf(1e-3f) + urand(st) * logf(1e3f));
+        const float fa = 0.2f + 0.8f * urand(st), fb = 0.2f + 1.8f * urand(st);
+        // kappa = d00 d11 / denom = 1 / sin^2(angle at p0): pick the angle for a kappa in [kappa_lo, kappa_hi]
+        const double kap = exp(log(kappa_lo) + (double)urand(st) * log(kappa_hi / kappa_lo));
+        const float hgt = (float)((double)(fb * len) * tan(asin(1.0 / sqrt(kap))));
+        const V3 p1 = p0 + dir * (fa * len), p2 = p0 + dir * (fb * len) + perp * hgt;
+        const TriConst tc = precompute_triangle(p0, p1, p2, 0u);
+        // the builder's numbers, in double, from the float corners it sees (1.000001f * vertex)
+        double c[3][3];
+        const V3 pv[3] = {p0, p1, p2};
+        for (int v = 0; v < 3; ++v) { c[v][0] = 1.000001f * pv[v].x; c[v][1] = 1.000001f * pv[v].y; c[v][2] = 1.000001f * pv[v].z; }
+        double e0[3], e1[3], d00 = 0, d01 = 0, d11 = 0;
+        for (int a = 0; a < 3; ++a) { e0[a] = c[1][a] - c[0][a]; e1[a] = c[2][a] - c[0][a]; d00 += e0[a] * e0[a]; d01 += e0[a] * e1[a]; d11 += e1[a] * e1[a]; }
+        const double denom = d00 * d11 - d01 * d01;
+        if (!(denom > 0.0)) continue;
+        const double kappa = d00 * d11 / denom, lmax = sqrt(d00 > d11 ? d00 : d11);
+        if (!(kappa <= kappa_hi * 1.5)) continue;
+        const double slop = 128.0 * 5.96e-8 * kappa * lmax;
+        float4 plane[1] = {tc.plane}, edge[3] = {tc.c0, tc.e0, tc.e1};
+        float2 den[1] = {tc.den};
+        DScene d;
+        memset(&d, 0, sizeof d);
+        d.tri_plane = plane; d.tri_edge = edge; d.tri_den = den;
+        out[0]++;
+        const V3 n = v3(tc.plane.x, tc.plane.y, tc.plane.z);
+        if (!(n.x == n.x)) continue;
+        const V3 c0 = v3(tc.c0.x, tc.c0.y, tc.c0.z);
+        for (int j = 0; j < n_rays; ++j) {
+            // a point of the triangle's neighbourhood: barycentric coordinates a little outside [0, 1], by up to a few slops
+            const float over = (float)(4.0 * slop / lmax) * urand(st);
+            const float u1 = -over + (1.f + 2.f * over) * urand(st), u2 = -over + (1.f + 2.f * over) * urand(st);
+            const V3 x = c0 + v3(tc.e0.x, tc.e0.y, tc.e0.z) * u1 + v3(tc.e1.x, tc.e1.y, tc.e1.z) * u2;
+            V3 dd = vrand(st, -1.f, 1.f);
+            if (dot(dd, n) > 0.f) dd = v3(0.f) - dd;
+            if (!(length(dd) > 1e-3f)) continue;
+            const float t0 = scale * (0.01f + 10.f * urand(st));
+            const Ray ray = make_ray(x - (dd / length(dd)) * t0, dd, 0.f);
+            float w0, w1, w2;
+            const float t = triangle_t<false>(ray, d, 0u, w0, w1, w2, nullptr);
+            if (t == FLT_MAX) continue;
+            out[1]++;
+            const V3 pf = ray.o + t * ray.d;
+            const double p[3] = {pf.x, pf.y, pf.z};
+            // distance to the true triangle: inside its prism -> distance to the plane, else to the nearest edge
+            double nn[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+            double q[3] = {p[0] - c[0][0], p[1] - c[0][1], p[2] - c[0][2]};
+            const double d20 = q[0] * e0[0] + q[1] * e0[1] + q[2] * e0[2], d21 = q[0] * e1[0] + q[1] * e1[1] + q[2] * e1[2];
+            const double b1 = (d11 * d20 - d01 * d21) / denom, b2 = (d00 * d21 - d01 * d20) / denom;
+            double dist;
+            if (b1 >= 0 && b2 >= 0 && b1 + b2 <= 1) {
+                const double nl = sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+                dist = fabs(q[0] * nn[0] + q[1] * nn[1] + q[2] * nn[2]) / nl;
+            } else {
+                const double da = pt_seg_d2(p, c[0], c[1]), db = pt_seg_d2(p, c[1], c[2]), dc = pt_seg_d2(p, c[2], c[0]);
+                dist = sqrt(da < db ? (da < dc ? da : dc) : (db < dc ? db : dc));
+            }
+            const double coords = fabs(p[0]) + fabs(p[1]) + fabs(p[2]) + (double)length(ray.o) + (double)t0;
+            const double allow = slop + 1e-4 * coords + 1e-5;
+            const unsigned long long ratio = (unsigned long long)(1e6 * dist / (slop + 1e-30));
+            if (dist <= slop * 100 && ratio > out[2]) out[2] = ratio;
+            if (dist > allow) ++bad;
+        }
+    }
+    return bad;
+}
+
+// always_bound_of against the reference's triangle test (triangle_t on the constants precompute_triangle stores): for nearly and exactly
+// collinear triangles, every point the test ACCEPTS must lie inside both slabs (|q . g| <= alpha + beta |q| + the rounding of q), and a
+// triangle flagged "never" must accept nothing. Rays are aimed at points of the triangle's plane scattered around the sliver's line up
+// to `reach` longest edges away. out[0] = triangles, out[1] = accepted hits checked, out[2] = triangles flagged never; returns violations.
+int sim_check_always(unsigned int seed, int n_tris, int n_rays, float reach, unsigned long long *out) {
+    uint32_t st = seed * 2246822519u + 99u;
+    int bad = 0;
+    out[0] = out[1] = out[2] = 0;
+    for (int k = 0; k < n_tris; ++k) {
+        const float scale = expf(logf(0.01f) + urand(st) * logf(1e4f));
+        const V3 p0 = vrand(st, -scale, scale);
+        V3 dir = vrand(st, -1.f, 1.f);
+        if (!(length(dir) > 1e-3f)) continue;
+        dir = dir / length(dir);
+        V3 perp = cross(dir, vrand(st, -1.f, 1.f));
+        if (!(length(perp) > 1e-3f)) continue;
+        perp = perp / length(perp);
+        const float len = scale * expf(logf(1e-3f) + urand(st) * logf(1e3f));
+        const float fa = 0.2f + 0.8f * urand(st), fb = (urand(st) < 0.3f) ? 2.f * fa : 0.2f + 1.8f * urand(st);   // 30 %: equally spaced corners
+        const float hgt = urand(st) < 0.25f ? 0.f : len * expf(logf(1e-9f) + urand(st) * logf(1e6f));            // 25 %: exactly on the line (before rounding)
+        const V3 p1 = p0 + dir * (fa * len), p2 = p0 + dir * (fb * len) + perp * hgt;
+        const TriConst tc = precompute_triangle(p0, p1, p2, 0u);
+        float4 plane[1] = {tc.plane}, edge[3] = {tc.c0, tc.e0, tc.e1};
+        float2 den[1] = {tc.den};
+        DScene d;
+        memset(&d, 0, sizeof d);
+        d.tri_plane = plane; d.tri_edge = edge; d.tri_den = den;
+        const AlwaysBound ab = always_bound_of(tc.c0, tc.e0, tc.e1, tc.den.x);
+        out[0]++;
+        if (ab.b.z != 0.f) out[2]++;
+        const V3 n = v3(tc.plane.x, tc.plane.y, tc.plane.z);
+        if (!(n.x == n.x)) continue;   // NaN normal: the test rejects everything (dotRN < 0 is never true)
+        const V3 c0 = v3(tc.c0.x, tc.c0.y, tc.c0.z);
+        const float lmax = sqrtf(fmaxf(tc.c0.w, tc.e1.w));
+        // in-plane frame of the STORED triangle
+        V3 ex = v3(tc.e1.x, tc.e1.y, tc.e1.z);
+        if (!(length(ex) > 0.f)) continue;
+        ex = ex / length(ex);
+        V3 ey = cross(n, ex);
+        if (!(length(ey) > 0.f)) continue;
+        ey = ey / length(ey);
+        for (int j = 0; j < n_rays; ++j) {
+            const float along = (urand(st) * 2.f - 1.f) * reach * lmax;
+            const float wid = fabsf(along) * expf(logf(1e-6f) + urand(st) * logf(1e6f)) + lmax * expf(logf(1e-9f) + urand(st) * logf(1e9f)) * (urand(st) < 0.5f ? 1.f : 0.f);
+            const float side = (urand(st) < 0.5f ? -1.f : 1.f) * wid * (urand(st) < 0.3f ? 0.f : 1.f);
+            const V3 x = c0 + ex * along + ey * side;
+            V3 dd = vrand(st, -1.f, 1.f);
+            if (dot(dd, n) > 0.f) dd = v3(0.f) - dd;
+            if (!(length(dd) > 1e-3f)) continue;
+            const float t0 = scale * (0.01f + 10.f * urand(st));
+            const Ray ray = make_ray(x - (dd / length(dd)) * t0, dd, 0.f);
+            float w0, w1, w2;
+            const float t = triangle_t<false>(ray, d, 0u, w0, w1, w2, nullptr);
+            if (t == FLT_MAX) continue;
+            out[1]++;
+            if (ab.b.z != 0.f) { ++bad; continue; }
+            const V3 p = ray.o + t * ray.d;
+            const V3 q = p - c0;
+            const float ql = length(q);
+            const float absm = 1e-4f * (ql + length(c0) + length(ray.o)) + 1e-6f;
+            if (ab.g1.w < 1e30f && fabsf(dot(q, v3(ab.g1.x, ab.g1.y, ab.g1.z))) > ab.g1.w + ab.b.x * ql * 1.001f + absm) ++bad;
+            if (ab.g2.w < 1e30f && fabsf(dot(q, v3(ab.g2.x, ab.g2.y, ab.g2.z))) > ab.g2.w + ab.b.y * ql * 1.001f + absm) ++bad;
+        }
+    }
+    return bad;
+}
+
 static DCamera make_cam(const RtCamera *c) {
     DCamera d;
     for (int i = 0; i < 16; ++i) { d.mvi[i] = c->modelview_inverse[i]; d.pi[i] = c->projection_inverse[i]; }

@@ -87,3 +87,38 @@ def test_core_functions_on_cpu_match_oracle(hb, ref, assets, sim, name, variant)
 @pytest.mark.parametrize("variant", [3, 6])
 def test_four_wide_mesh_walk_keeps_the_bits(hb, ref, assets, sim_bvh4, name, variant):
     _check_against_oracle(hb, ref, sim_bvh4, name, variant)
+
+
+def test_hull_filter_never_drops_a_sphere_a_sample_could_hit(sim):
+    """lc_hull_misses (the occluder-candidate filter for spheres) against the reference's own sphere test, on the functions as compiled:
+    spheres placed at the boundary of the hull of the sample rays, +- relative offsets from 1e-6 to 1; whenever the filter drops one, none
+    of the shadow samples (generated as path_shadow_sample_body generates them) may hit it. Both verdicts must occur, and kept spheres
+    must actually get hit, or the check would be vacuous."""
+    sim.sim_check_hull.argtypes = [C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
+    out = (C.c_ulonglong * 3)()
+    bad = sim.sim_check_hull(20260419, 40000, 48, out)
+    assert bad == 0
+    assert out[0] > 5000 and out[1] > 5000 and out[2] > 50000, list(out)
+
+
+def test_always_tested_triangle_bounds_contain_every_accepted_point(sim):
+    """always_bound_of against triangle_t on the stored constants of precompute_triangle: nearly and exactly collinear triangles (a quarter
+    exactly on a line before rounding, 30 % with equally spaced corners: the shapes whose barycentric test accepts points far from the
+    triangle). Every accepted point lies inside both slabs; a triangle flagged "never" accepts nothing."""
+    sim.sim_check_always.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_ulonglong)]
+    out = (C.c_ulonglong * 3)()
+    bad = sim.sim_check_always(7, 20000, 400, 50.0, out)
+    assert bad == 0
+    assert out[0] > 10000 and out[1] > 10000, list(out)
+
+
+def test_box_padding_covers_what_the_triangle_test_accepts_up_to_the_conditioning_limit(sim):
+    """rt_bvh.hpp boxes a triangle when its conditioning number kappa = d00 d11 / denom is <= RT_BVH_KAPPA_MAX = 4e5 (1e5 until round 2) and
+    pads the box by slop = 128 eps kappa lmax. Checked against triangle_t on the stored constants: every accepted point lies within that
+    slop of the true triangle (distance in double), for kappa from 1e3 to 4e5; out[2] reports how much of the slop was ever used."""
+    sim.sim_check_slop.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_ulonglong)]
+    out = (C.c_ulonglong * 3)()
+    bad = sim.sim_check_slop(11, 20000, 300, 1e3, 4e5, out)
+    assert bad == 0
+    assert out[0] > 10000 and out[1] > 100000, list(out)
+    assert out[2] < 500000, "more than half of the slop used: %d ppm" % out[2]

@@ -884,7 +884,11 @@ RT_HD bool mesh_closest_bvh(const Ray &ray, const DScene &s, const DMesh &m, flo
                 node = c0; \
             } \
         }
-template <bool STATS>
+// ANYHIT (shadow samples only, mode != 0): Scene::computeShadow asks of a mesh only whether its closest hit lies in (EPSILON, limit)
+// (Scene.h:248-253): the first reachable hit above EPSILON answers "some hit does", and the search goes on with the bound pulled in to
+// EPSILON — every box farther away is culled at once — for a hit at t <= EPSILON, which would make the closest hit too near to count.
+// Same boolean, same draw as the full closest-hit search (the reasoning of RT_OPT_ANYHIT in mesh_closest_bvh).
+template <bool STATS, bool ANYHIT = false>
 RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rng, Hit &h, bool &blocked, bool &done, Counters *cnt) {
     if (done || s.n_meshes <= 0) return;
     const uint32_t NONE = 0xFFFFFFFFu;
@@ -902,9 +906,14 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
 #endif
     float best_t = h.t;
     uint32_t best_ref = NONE;
+    bool found = false;   // ANYHIT: this mesh has a reachable hit in (EPSILON, limit)
+    const float eps_next = u2f(f2u(RT_EPSF) + 1u);   // t < eps_next  <=>  t <= EPSILON
     if (STATS) cnt->mesh++;
     for (;;) {
-        for (; k < kend; ++k) bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+        for (; k < kend; ++k) {
+            bvh_consider<STATS>(ray, s, RT_LDG(s.bvh_tris + k), best_t, best_ref, cnt);
+            if (ANYHIT && best_ref != NONE && best_t > RT_EPSF) { found = true; best_t = eps_next; best_ref = NONE; }
+        }
 #if RT_OPT_BVH4
         if (wide) { RT_WALK_DESCEND4() } else { RT_WALK_DESCEND() }
 #else
@@ -916,8 +925,8 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
             node = sp > 0 ? stack.get(--sp) : MESH_END;
             continue;
         }
-        // mesh mi is finished
-        if (best_ref != NONE && best_t < h.t && best_t > RT_EPSF) {
+        // mesh mi is finished (ANYHIT: a hit found above EPSILON counts unless the search below EPSILON found one as well: best_ref set)
+        if (ANYHIT ? (found && best_ref == NONE) : (best_ref != NONE && best_t < h.t && best_t > RT_EPSF)) {
             if (mode == 0) { h.type = 3; h.obj = mi; h.t = best_t; h.ref = best_ref; }
             else { if (STATS) cnt->rnd++; if (rng.next() > RT_LDG(s.mesh_transparency + mi)) { blocked = true; done = true; break; } }
         }
@@ -932,7 +941,7 @@ RT_HD void meshes_walk_merged(const DScene &s, const Ray &ray, int mode, Rng &rn
         node = m.bvh_root >= 0 ? m.bvh_root : MESH_END;
 #endif
         sp = 0;
-        best_t = h.t; best_ref = NONE;
+        best_t = h.t; best_ref = NONE; found = false;
     }
 }
 
@@ -1739,6 +1748,9 @@ RT_HD bool cone_box(const Cone &c, float lx, float ly, float lz, float hx, float
 //     sample ray. This is the lit side of the very sphere that was hit, and everything on the far side of P.
 // margin = 1e-4 * |w| * (|D| + delta): three orders of magnitude above the rounding of the fp32 dot products the
 // reference-exact tests evaluate (a few eps * |w|), so "cannot occlude" here implies FLT_MAX there.
+#ifndef RT_OPT_LC_ANYHIT
+#define RT_OPT_LC_ANYHIT 1   /* any-hit mesh walk for the shadow samples of the overflow queue (meshes_walk_merged<.., ANYHIT>) */
+#endif
 #ifndef RT_OPT_LC_HULL
 #define RT_OPT_LC_HULL 1
 #endif
@@ -2243,7 +2255,7 @@ RT_HD void intersect_lc(const DScene &s, PathState &st, bool run_t_, bool mine, 
         return;
     }
 #if RT_OPT_MESH_MERGED
-    meshes_walk_merged<STATS>(s, ray, mode, st.rng, h, blocked, done, cnt);
+    meshes_walk_merged<STATS, SAMPLE_ == 3 && RT_OPT_LC_ANYHIT>(s, ray, mode, st.rng, h, blocked, done, cnt);   // the overflow queue's samples: any-hit
 #else
     for (int i = 0; i < s.n_meshes; ++i) {
         if (done) break;

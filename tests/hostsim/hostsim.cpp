@@ -408,7 +408,11 @@ void sim_render(void *h, const RtCamera *camera, const RtRenderParams *p, float 
                             while (!fin && st.mode != 0) {
                                 if (lc) {
                                     const bool was3 = st.mode == 3;
-                                    intersect_lc<false>(s->d, st, st.mode == 3, true, hit, hu, hv, blocked, nullptr);
+                                    // as the wavefront's kernels instantiate it: classify = the cone walk only, samples per queue (list / overflow with
+                                    // the any-hit mesh walk)
+                                    if (was3) intersect_lc<false, false, true>(s->d, st, true, true, hit, hu, hv, blocked, nullptr);
+                                    else if (st.cl_n >= 0) intersect_lc<false, false, false, 2>(s->d, st, false, true, hit, hu, hv, blocked, nullptr);
+                                    else intersect_lc<false, false, false, 3>(s->d, st, false, true, hit, hu, hv, blocked, nullptr);
                                     if (was3) {
                                         g_dbg_lights++;
                                         if (st.cl_n < 0) g_dbg_overflow++; else g_dbg_tris += st.cl_n;

@@ -1944,11 +1944,14 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
 
     // chunking: whole pixels, at most ~16 Mi paths in flight (192 MiB of samples)
     // Kernel selection (measured on B200, profiles/r01_notes.md): the wavefront (6) wins wherever the analytic
-    // culling hierarchy exists (configs 2, 4, 5: 1.2-1.3x over the state machine); mesh scenes without it (config 3)
-    // are faster in the single state-machine kernel over the exact culling hierarchies (3); scenes with a handful of
-    // analytic primitives and nothing else (config 1) in the plain one-path-per-lane kernel (1).
+    // culling hierarchy exists (configs 2, 4, 5: 1.2-1.3x over the state machine; config 3 since the end of round 2); mesh scenes
+    // without it (no lights and fewer than 24 analytic primitives) run the single state-machine kernel over the exact culling
+    // hierarchies (3); scenes with a handful of analytic primitives and nothing else (config 1) the plain one-path-per-lane kernel (1).
     int kind_req = p->variant & 0xFF;
-    if (kind_req == 0 && s->d.abvh_root >= 0 && s->d.n_spheres + s->d.n_squares >= 24) kind_req = 6;
+    // (Until the end of round 2 lit mesh scenes with fewer than 24 analytic primitives — the pond scene — stayed on the state machine: the two
+    // were level at 2 spp. At the pond scene's full 16 spp the wavefront, with its kernels compiled per mode and the any-hit overflow samples, takes
+    // 350 ms against 442: adjacent samples of a pixel make coherent batches. profiles/r02_notes.md, r04j.)
+    if (kind_req == 0 && s->d.abvh_root >= 0) kind_req = 6;
     const bool wavefront = kind_req == 6 && p->max_bounces > 0;
     // paths per chunk. Wavefront: every kernel of a chunk ends in a tail during which SMs drain, so fewer, larger chunks
     // are faster (config 2, ms per frame at 32 spp: 4 Mi 36.5, 8 Mi 32.9, 16 Mi 31.3, 32 Mi 30.3); 32 Mi paths are ~17 GB

@@ -67,7 +67,7 @@ def kernel_of(counts, variant):
     n_an = counts["spheres"] + counts["squares"]
     abvh = 24 <= n_an <= 128 or (1 <= n_an < 24 and counts["lights"] > 0 and counts["meshes"] > 0)
     if kind == 0:
-        kind = 6 if 24 <= n_an <= 128 else (3 if counts["meshes"] > 0 else 1)
+        kind = 6 if abvh else (3 if counts["meshes"] > 0 else 1)
     if kind == 5 and not (abvh and counts["lights"] > 0):
         kind = 3
     return {1: "k_render_paths", 2: "k_render_regen<ACCEL=0>", 3: "k_render_regen<ACCEL=1> (exact culling hierarchies)",

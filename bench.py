@@ -61,13 +61,13 @@ WORKLOADS = {
 PLAN = {"c1": (5, 20, 20, 0), "c2": (3, 5, 3, 0), "c3": (2, 3, 2, 4), "c4": (2, 1, 1, 8), "c5": (2, 1, 1, 1)}
 
 
-def kernel_of(counts, variant):
-    """Name of the render kernel(s) rt_render_device selects (same rule as csrc/rt_capi.cu)."""
+def kernel_of(counts, variant, paths=1 << 30):
+    """Name of the render kernel(s) rt_render_device selects (same rule as csrc/rt_capi.cu); paths = paths of one render call."""
     kind = variant & 0xFF
     n_an = counts["spheres"] + counts["squares"]
     abvh = 24 <= n_an <= 128 or (1 <= n_an < 24 and counts["lights"] > 0 and counts["meshes"] > 0)
     if kind == 0:
-        kind = 6 if abvh else (3 if counts["meshes"] > 0 else 1)
+        kind = 6 if abvh and (n_an >= 24 or paths >= (24 << 20)) else (3 if counts["meshes"] > 0 else 1)
     if kind == 5 and not (abvh and counts["lights"] > 0):
         kind = 3
     return {1: "k_render_paths", 2: "k_render_regen<ACCEL=0>", 3: "k_render_regen<ACCEL=1> (exact culling hierarchies)",
@@ -532,7 +532,7 @@ class Bench:
             "hbm": {"achieved_gbs": hbm_ach, "peak_gbs": self.hbm_peak, "frac": hbm_frac, "bytes_per_ray": ex_bpr},
             "fp32": {"achieved_tflops": fp_ach, "peak_tflops": fp32_unfused, "frac": fp_frac, "flops_per_ray": ex_fpr},
             "traffic": None,
-            "kernel": kernel_of(scene.counts(), variant),
+            "kernel": kernel_of(scene.counts(), variant, w * h * spp // max(1, world)),
             "kernel_ms_per_launch": k_ms / chunks, "launches_per_step": chunks,
             "launch": "one chunk of <= 32 Mi (wavefront) / 16 Mi paths: every render kernel of the chunk, CUDA events around them on the launching stream",
             "peak_source": "fp32 unfused FMUL+FADD measured live by rt_measure_fp32_peak (fused: %.1f TFLOP/s; the parity build may not fuse); hbm %s" % (fp32_fused, self.hbm_src),

@@ -1951,7 +1951,11 @@ static int render_device_impl(RtScene *s, const RtCamera *camera, const RtRender
     // (Until the end of round 2 lit mesh scenes with fewer than 24 analytic primitives — the pond scene — stayed on the state machine: the two
     // were level at 2 spp. At the pond scene's full 16 spp the wavefront, with its kernels compiled per mode and the any-hit overflow samples, takes
     // 350 ms against 442: adjacent samples of a pixel make coherent batches. profiles/r02_notes.md, r04j.)
-    if (kind_req == 0 && s->d.abvh_root >= 0) kind_req = 6;
+    // By size (profiles/r04n_*, kernel ms, state machine / wavefront): 2 spp = 16.6 M paths 60.5 / 59.7, 4 spp 118.8 / 99.0, 8 spp 227 / 188.5, 16 spp 442 / 350 — and
+    // on 8 GPUs, where a rank renders 16.6 M paths of the 16-spp frame, 59.5 / 64.2 (max over ranks, r04d / r04m): with fewer than ~24 M paths in a
+    // call the deeper bounces hold a handful of batches per warp and the wavefront's kernels end unevenly. Such calls keep the state machine.
+    if (kind_req == 0 && s->d.abvh_root >= 0 &&
+        (s->d.n_spheres + s->d.n_squares >= 24 || n_pixels * (unsigned long long)p->spp >= (24ull << 20))) kind_req = 6;
     const bool wavefront = kind_req == 6 && p->max_bounces > 0;
     // paths per chunk. Wavefront: every kernel of a chunk ends in a tail during which SMs drain, so fewer, larger chunks
     // are faster (config 2, ms per frame at 32 spp: 4 Mi 36.5, 8 Mi 32.9, 16 Mi 31.3, 32 Mi 30.3); 32 Mi paths are ~17 GB

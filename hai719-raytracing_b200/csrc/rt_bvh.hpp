@@ -85,6 +85,19 @@ struct Prim { Box box; float c[3]; uint32_t ref; float coef = 0.f; };
 
 inline int32_t leaf_code(uint32_t first, uint32_t count) { return -(int32_t)(first * 8u + count) - 1; }
 
+// The barycentric denominator the device stores for a triangle with the (already scaled) float corners c0, c1, c2 — precompute_triangle's
+// arithmetic replayed on the host: float edges, float dot products summed left to right, d00 * d11 - d01 * d01, every operation rounded to
+// float and none fused (volatile). tests/test_hostsim.py compares it bit for bit with precompute_triangle on every triangle of the assets.
+inline float stored_denominator(const float *c0, const float *c1, const float *c2) {
+    const volatile float e0x = c1[0] - c0[0], e0y = c1[1] - c0[1], e0z = c1[2] - c0[2];
+    const volatile float e1x = c2[0] - c0[0], e1y = c2[1] - c0[1], e1z = c2[2] - c0[2];
+    const float e0[3] = {e0x, e0y, e0z}, e1[3] = {e1x, e1y, e1z};
+    auto fdot = [](const float *a, const float *b) { const volatile float x = a[0] * b[0], y = a[1] * b[1], z = a[2] * b[2]; const volatile float xy = x + y; return (float)(xy + z); };
+    const float f00 = fdot(e0, e0), f01 = fdot(e0, e1), f11 = fdot(e1, e1);
+    const volatile float pa = f00 * f11, pb = f01 * f01;
+    return pa - pb;
+}
+
 // returns a child code (>= 0 inner node, < 0 leaf). `median` forces balanced splits (depth <= log2 n),
 // used when the SAH tree came out deeper than the device's traversal stack.
 template <class A>
@@ -282,17 +295,12 @@ inline void build_accel(const RtSceneDesc &d, const PackedMeshes &pk, Accel &out
                 continue;
             }
             {
-                // The denominator the device STORES (precompute_triangle: float dot products summed left to right, d00 * d11 - d01 * d01,
-                // no FMA), replayed here in float: when it is exactly 0 or not finite, u1 = N / den is never inside [0, 1]
-                // (Triangle.h:62-75: +-inf or NaN fail every comparison) and the triangle can never report a hit: dropped. One of the two
-                // collinear slivers of the triceratops mesh is such a triangle; as an always-tested one it cost every ray a test.
-                const float q0[3] = {(float)c[0][0], (float)c[0][1], (float)c[0][2]};
-                const float fe0[3] = {(float)c[1][0] - q0[0], (float)c[1][1] - q0[1], (float)c[1][2] - q0[2]};
-                const float fe1[3] = {(float)c[2][0] - q0[0], (float)c[2][1] - q0[1], (float)c[2][2] - q0[2]};
-                auto fdot = [](const float *a, const float *b) { const volatile float x = a[0] * b[0], y = a[1] * b[1], z = a[2] * b[2]; const volatile float xy = x + y; return (float)(xy + z); };
-                const float f00 = fdot(fe0, fe0), f01 = fdot(fe0, fe1), f11 = fdot(fe1, fe1);
-                const volatile float pa = f00 * f11, pb = f01 * f01;
-                const float fden = pa - pb;
+                // When the denominator the device STORES is exactly 0 or not finite, u1 = N / den is never inside [0, 1] (Triangle.h:62-75:
+                // +-inf or NaN fail every comparison) and the triangle can never report a hit: dropped. One of the two collinear slivers of
+                // the triceratops mesh is such a triangle; as an always-tested one it cost every ray a test.
+                const float q0[3] = {(float)c[0][0], (float)c[0][1], (float)c[0][2]}, q1[3] = {(float)c[1][0], (float)c[1][1], (float)c[1][2]},
+                            q2[3] = {(float)c[2][0], (float)c[2][1], (float)c[2][2]};
+                const float fden = bvh_detail::stored_denominator(q0, q1, q2);
                 if (fden == 0.f || !std::isfinite(fden)) continue;
             }
             const double kappa = d00 * d11 / denom;

@@ -142,6 +142,27 @@ void *sim_scene_create(const RtSceneDesc *desc) {
 
 void sim_scene_destroy(void *h) { delete (SimScene *)h; }
 
+// rt_bvh.hpp's host replay of the stored barycentric denominator against precompute_triangle (the function the device runs, which this file
+// compiles for the host): every leaf reference of every mesh of the scene; returns the number of references whose bits differ.
+int sim_check_den_replay(void *h, const RtSceneDesc *desc, unsigned long long *n_checked) {
+    const SimScene *s = (const SimScene *)h;
+    int bad = 0;
+    size_t ref = 0;
+    *n_checked = 0;
+    for (uint32_t i = 0; i < desc->n_meshes; ++i) {
+        const RtSceneMesh &src = desc->meshes[i];
+        for (uint32_t k = 0; k < src.n_leaf_refs; ++k, ++ref) {
+            const RtTriRef &r = src.leaf_refs[k];
+            float c[3][3];
+            for (int v = 0; v < 3; ++v) for (int a = 0; a < 3; ++a) c[v][a] = 1.000001f * src.positions[3 * r.v[v] + a];
+            const float want = s->den[ref].x, got = bvh_detail::stored_denominator(c[0], c[1], c[2]);
+            if (f2u(want) != f2u(got)) ++bad;
+            ++*n_checked;
+        }
+    }
+    return bad;
+}
+
 // ---- property checks of the conservative candidate filters (tests/test_hostsim.py) ---------------------------------
 static float urand(uint32_t &st) { st = st * 1664525u + 1013904223u; return (float)(st >> 8) * (1.0f / 16777216.0f); }
 static V3 vrand(uint32_t &st, float lo, float hi) { const float x = lo + (hi - lo) * urand(st), y = lo + (hi - lo) * urand(st), z = lo + (hi - lo) * urand(st); return v3(x, y, z); }

@@ -122,3 +122,18 @@ def test_box_padding_covers_what_the_triangle_test_accepts_up_to_the_conditionin
     assert bad == 0
     assert out[0] > 10000 and out[1] > 100000, list(out)
     assert out[2] < 500000, "more than half of the slop used: %d ppm" % out[2]
+
+
+@pytest.mark.parametrize("name", ["flamingo_pond", "backrooms_pool", "config5", "raccoon", "flamingo_lake", "mesh"])
+def test_host_replay_of_the_stored_denominator_matches_the_device_function(hb, assets, sim, name):
+    """rt_bvh.hpp drops a triangle whose STORED barycentric denominator is 0 or not finite (it can never report a hit); it computes that
+    constant on the host (bvh_detail::stored_denominator). Compared bit for bit with precompute_triangle — the function the device runs
+    — on every leaf reference of the scene's meshes."""
+    sim.sim_check_den_replay.argtypes = [C.c_void_p, C.POINTER(hb.RtSceneDesc), C.POINTER(C.c_ulonglong)]
+    s = hb.Scene(name, aspect=16 / 9)
+    d = s.flatten()
+    h = sim.sim_scene_create(d)
+    n = C.c_ulonglong(0)
+    bad = sim.sim_check_den_replay(h, d, C.byref(n))
+    sim.sim_scene_destroy(h)
+    assert bad == 0 and n.value > 0, (bad, n.value)

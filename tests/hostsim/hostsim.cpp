@@ -163,6 +163,26 @@ int sim_check_den_replay(void *h, const RtSceneDesc *desc, unsigned long long *n
     return bad;
 }
 
+// The ball the quadratic padding term takes its distance from (AnalyticAccel::center_s / radius_s) must hold every sphere centre at every time in
+// [0, 1] (the device evaluates c = centre + time * motion in float): returns the number of (sphere, time) pairs outside it; *slack = the smallest margin seen.
+int sim_check_centre_ball(void *h, const RtSceneDesc *desc, float *slack) {
+    const SimScene *s = (const SimScene *)h;
+    int bad = 0;
+    *slack = FLT_MAX;
+    if (s->d.abvh_root < 0) { *slack = 0.f; return 0; }   // no analytic hierarchy (too few primitives): nothing is padded
+    for (uint32_t i = 0; i < desc->n_spheres; ++i)
+        for (int k = 0; k <= 16; ++k) {
+            const float time = (float)k / 16.f;
+            const float4 a = s->sph_a[i], b = s->sph_b[i];
+            const V3 c = v3(a.x, a.y, a.z) + time * v3(b.x, b.y, b.z);
+            const float d = length(c - ld3(s->d.abvh_cs));
+            if (!(d == d)) continue;   // a non-finite centre: its box is everything, the padding does not matter
+            if (d > s->d.abvh_rs) ++bad;
+            if (s->d.abvh_rs - d < *slack) *slack = s->d.abvh_rs - d;
+        }
+    return bad;
+}
+
 // ---- property checks of the conservative candidate filters (tests/test_hostsim.py) ---------------------------------
 static float urand(uint32_t &st) { st = st * 1664525u + 1013904223u; return (float)(st >> 8) * (1.0f / 16777216.0f); }
 static V3 vrand(uint32_t &st, float lo, float hi) { const float x = lo + (hi - lo) * urand(st), y = lo + (hi - lo) * urand(st), z = lo + (hi - lo) * urand(st); return v3(x, y, z); }

@@ -137,3 +137,31 @@ def test_host_replay_of_the_stored_denominator_matches_the_device_function(hb, a
     bad = sim.sim_check_den_replay(h, d, C.byref(n))
     sim.sim_scene_destroy(h)
     assert bad == 0 and n.value > 0, (bad, n.value)
+
+
+@pytest.mark.parametrize("name", ["random_spheres", "config5", "rt_in_a_weekend", "raccoon", "backrooms_pool", "cornell_box"])
+def test_sphere_centres_lie_in_the_ball_the_padding_measures_from(hb, assets, sim, name):
+    """The quadratic term of the per-ray box padding needs D >= |o - c| for every sphere centre c at every time in [0, 1]; D = |o - Cs| + Rs with
+    (Cs, Rs) = AnalyticAccel::center_s / radius_s is that bound iff every centre lies inside the ball."""
+    sim.sim_check_centre_ball.argtypes = [C.c_void_p, C.POINTER(hb.RtSceneDesc), C.POINTER(C.c_float)]
+    s = hb.Scene(name, aspect=16 / 9)
+    d = s.flatten()
+    h = sim.sim_scene_create(d)
+    slack = C.c_float(0)
+    bad = sim.sim_check_centre_ball(h, d, C.byref(slack))
+    sim.sim_scene_destroy(h)
+    assert bad == 0 and (d.contents.n_spheres == 0 or slack.value >= 0.0), (bad, slack.value)
+
+
+def test_always_tested_triangles_of_the_assets(hb, assets, sim):
+    """Which triangles are still tested for every ray (rt_bvh.hpp): with the conditioning limit at 4e5 the pond and pool meshes have none (five and
+    two at 1e5), the triceratops one (its second collinear sliver stores a zero denominator and is dropped: it can never report a hit)."""
+    sim.sim_mesh_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int]
+    want = {"flamingo_pond": [0, 0], "backrooms_pool": [0, 0, 0], "config5": [1, 0]}
+    for name, counts in want.items():
+        s = hb.Scene(name, aspect=16 / 9)
+        h = sim.sim_scene_create(s.flatten())
+        out = (C.c_int * 32)()
+        n = sim.sim_mesh_info(h, out, 32)
+        sim.sim_scene_destroy(h)
+        assert [out[2 * i + 1] for i in range(n)] == counts, name
